@@ -1,0 +1,204 @@
+/* ocf.h - C ABI of the B200-native training/scoring hot path (libocf_b200.so).
+ *
+ * The reference (Epist/omnidirectional_collaborative_filtering) has no FFI: its seam is two
+ * Python classes and the Keras Model methods train.py calls. Each entry point below names the
+ * reference interface it replaces (file:line in the reference tree); INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add at those call sites.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ocf_status otherwise;
+ *     ocf_last_error() gives the message of the calling thread's last failure
+ *   - plain pointers and sizes only; no C++ exceptions cross the boundary
+ *   - HOST pointers unless a parameter is documented as a device pointer; the caller owns every
+ *     host buffer, the library owns all device memory behind its handles
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls
+ *     enqueue work on it and return without synchronising unless they hand results back to a
+ *     host buffer
+ *   - a handle lives on the device that was current when it was created; handles are not
+ *     thread-safe
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ */
+#ifndef OCF_H
+#define OCF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCF_VERSION 100
+
+typedef enum {
+  OCF_OK = 0,
+  OCF_ERR_INVALID = -1,   /* bad argument / unsupported configuration            */
+  OCF_ERR_CUDA = -2,      /* a CUDA runtime call failed (message has the detail)  */
+  OCF_ERR_NOMEM = -3,
+  OCF_ERR_STATE = -4      /* call order (e.g. train step on an eval batch)        */
+} ocf_status;
+
+typedef enum { OCF_ACT_LINEAR = 0, OCF_ACT_SIGMOID, OCF_ACT_TANH, OCF_ACT_RELU,
+               OCF_ACT_ELU, OCF_ACT_SELU, OCF_ACT_SOFTPLUS } ocf_activation;
+/* auxilliary_mask_type, data_reader.py:341-361 */
+typedef enum { OCF_AUX_NONE = 0, OCF_AUX_CAUSAL, OCF_AUX_DROPOUT, OCF_AUX_ZEROS, OCF_AUX_BOTH } ocf_aux;
+/* model_loss, train.py:49 */
+typedef enum { OCF_LOSS_MSE = 0, OCF_LOSS_MAE = 1 } ocf_loss;
+/* optimizer, train.py:50-51 / train_jester.py:61 */
+typedef enum { OCF_OPT_SGD = 0, OCF_OPT_ADAGRAD, OCF_OPT_RMSPROP, OCF_OPT_ADAM } ocf_optimizer;
+
+typedef struct ocf_store ocf_store;   /* device-resident rating store (CSR + CSC)            */
+typedef struct ocf_pair ocf_pair;     /* (input store, target store) of a fixed-split set    */
+typedef struct ocf_batch ocf_batch;   /* one batch: row ids, keep-flags, gathered tiles      */
+typedef struct ocf_model ocf_model;   /* weights, optimizer state, workspaces                */
+
+const char* ocf_last_error(void);
+int ocf_version(void);
+/* Number of CUDA devices visible (0 without a GPU; never fails). */
+int ocf_device_count(void);
+
+/* ---- rating store ------------------------------------------------------------------------
+ * Replaces the per-row (item, rating) lists the reader keeps after loading
+ * (data_reader.py:46-70) together with the id->dense-column map (data_reader.py:24-28, applied
+ * by the caller: `col` already holds dense columns). Rows keep their stored order: draw j of
+ * the reciprocal dropout belongs to the j-th stored rating (data_reader.py:130-134).
+ * Repeated columns inside a row are allowed and resolve last-write-wins like the dense fills
+ * at data_reader.py:158-169. `build_csc` != 0 also builds the column-major index the training
+ * update needs (stores that only feed evaluation can skip it).
+ * Limits: nnz < 2^31, n_cols < 2^31. */
+int ocf_store_create(int64_t n_rows, int64_t n_cols, const int64_t* rowptr, const int32_t* col,
+                     const float* val, int build_csc, ocf_store** out);
+int ocf_store_destroy(ocf_store* store);
+/* info[0]=n_rows, [1]=n_cols, [2]=nnz, [3]=1 if any row repeats a column, [4]=longest column,
+ * [5]=device bytes held */
+int ocf_store_info(const ocf_store* store, int64_t info[6]);
+
+/* Fixed-split valid/test set: row r of `in_store` holds the inputs of row r of `tgt_store`
+ * (user_dicts_valid[0]/[1], data_reader.py:372-380; a None input row is an empty row). */
+int ocf_pair_create(const ocf_store* in_store, const ocf_store* tgt_store, ocf_pair** out);
+int ocf_pair_destroy(ocf_pair* pair);
+
+/* ---- batch construction (kernel K1) -------------------------------------------------------
+ * A batch object owns pinned staging, device tiles and the row->slot map; create a few and
+ * rotate them to overlap the next batch's upload with the current step. */
+int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch** out);
+int ocf_batch_destroy(ocf_batch* batch);
+
+/* build_sparse_batch, data_reader.py:95-200 (dense branch), without the dense arrays:
+ * keep_flags[k] is the reference's random_dropout_split value of the k-th rating of the batch
+ * (rows in batch order, ratings in stored order): 1 = input (and target too when
+ * pass_through), 0 = target. n_flags must equal the total length of the listed rows.
+ * One host->device copy + one kernel on `stream`. */
+int ocf_batch_fill_split(ocf_batch* batch, const ocf_store* store, const int32_t* row_ids,
+                         int32_t n_rows, const uint8_t* keep_flags, int64_t n_flags,
+                         int pass_through, float aux_var_value, void* stream);
+/* build_sparse_batch_fixed_split, data_reader.py:202-298. */
+int ocf_batch_fill_fixed(ocf_batch* batch, const ocf_pair* pair, const int32_t* row_ids,
+                         int32_t n_rows, float aux_var_value, void* stream);
+/* info[0]=rows, [1]=entries, [2]=work items, [3]=target_count (data_reader.py:268; ratings
+ * listed as targets, repeats included), [4]=bytes of the last host->device copy */
+int ocf_batch_info(const ocf_batch* batch, int64_t info[5]);
+/* The dense [rows, n_cols] float64 arrays the reference generator yields (the scatter half of
+ * K1; for parity tests and callers that still want Keras-style feeds). which: 0 = inputs
+ * (ratings_batch_inputs), 1 = input mask, 2 = output mask, 3 = targets, 4 = missing-data mask
+ * (data_reader.py:191-200). Synchronises `stream`. */
+int ocf_batch_densify(const ocf_batch* batch, int which, double* out, void* stream);
+
+/* ---- model --------------------------------------------------------------------------------
+ * omni_model, model.py:33-99, plus compile(), train.py:131-133. */
+typedef struct {
+  int32_t n_cols;            /* input_shape: width of this rank's column slice (== n_cols_total unsharded) */
+  int32_t n_cols_total;      /* catalogue width N the loss is normalised by (B*N, train.py:49) */
+  int32_t n_layers;          /* numlayers (hidden Dense layers), 1..8 */
+  int32_t widths[8];         /* num_hidden_units per hidden layer (the reference uses one width) */
+  int32_t aux;               /* ocf_aux: which mask blocks are concatenated to the data (model.py:47-56) */
+  int32_t activation;        /* ocf_activation, dense_activation */
+  int32_t loss;              /* ocf_loss */
+  float l2;                  /* l2_weight_regulatization, < 0 = None */
+  float dropout_p;           /* dropout_probability, < 0 = None */
+  float aux_var_value;       /* value masks carry (train.py:47) */
+  float rating_range;        /* for nMAE (train.py:118-121) */
+  int32_t max_rows;          /* largest batch */
+  int64_t max_entries;       /* most ratings in one batch */
+  int32_t sharded;           /* 1: column shard; z/dh/row statistics are partial until reduced */
+} ocf_model_config;
+
+int ocf_model_create(const ocf_model_config* cfg, ocf_model** out);
+int ocf_model_destroy(ocf_model* model);
+/* Grow the batch-sized workspaces (weights and optimizer state are kept). No-op when the model
+ * already holds max_rows rows and max_entries ratings per batch. */
+int ocf_model_reserve(ocf_model* model, int32_t max_rows, int64_t max_entries);
+/* Keras get_weights()/set_weights() order and layout (model.py:102-107): for each Dense layer
+ * kernel [fan_in, fan_out] row-major then bias [fan_out]; layer 0 has fan_in = k*n_cols
+ * (data | aux | second mask blocks), the last layer fan_out = n_cols.
+ * index = 2*layer (+1 for the bias). Setting a weight does not touch optimizer state. */
+int ocf_model_num_weights(const ocf_model* model);
+int ocf_model_weight_shape(const ocf_model* model, int index, int64_t shape[2]);
+int ocf_model_set_weight(ocf_model* model, int index, const float* host, int64_t count);
+int ocf_model_get_weight(const ocf_model* model, int index, float* host, int64_t count);
+/* Optimizer (Keras 2.0.4 rules). p1 = rho (RMSprop) or beta_1 (Adam), p2 = beta_2.
+ * Resets the optimizer state and the iteration counter. */
+int ocf_model_set_optimizer(ocf_model* model, int kind, float lr, float p1, float p2,
+                            float epsilon, float decay);
+/* compile(loss=...), train.py:131-133; rating_range feeds nMAE (train.py:118-121). */
+int ocf_model_set_loss(ocf_model* model, int loss, float rating_range);
+/* Which mask the reader feeds into the auxiliary input block(s) (auxilliary_mask_type,
+ * data_reader.py:341-361). Must keep the number of blocks the model was created with. */
+int ocf_model_set_aux(ocf_model* model, int aux);
+/* layer.trainable (model.py:125,136-140,162,167); layer in [0, n_layers]. */
+int ocf_model_set_trainable(ocf_model* model, int layer, int trainable);
+int ocf_model_reset_optimizer(ocf_model* model);
+
+typedef struct {
+  uint64_t dropout_seed;     /* Philox key of the hidden dropout masks (oracle/philox.py) */
+  uint32_t step;             /* counter word; normally the running step index */
+  int32_t row0;              /* global index of this batch's first row (multi-GPU row slices) */
+  int32_t rows_total;        /* B of the loss normalisation; 0 = the batch's own row count */
+  int32_t phase;             /* 0 = whole step; 1..3 = sharded phases (see below) */
+} ocf_step_args;
+
+/* Metrics of one step, train.py:102-121 + the Keras loss:
+ * [0] loss (with the L2 term) [1] mean_absolute_error [2] accurate_MAE [3] nMAE
+ * [4] accurate_RMSE [5] accurate_MSE [6] sum of squared errors [7] count_nonzero(t+y) */
+#define OCF_N_METRICS 8
+
+/* One optimisation step on a split batch: model.train_on_batch as driven by fit_generator,
+ * train.py:157. Metrics are computed before the update with dropout active, as in Keras.
+ * host_metrics may be NULL: the values stay in the device log (ocf_model_read_metrics) and
+ * the call does not synchronise.
+ * Sharded models run the step in three phases with a collective between them (the caller
+ * reduces the buffer ocf_model_buffer() names, in place, over the column shards):
+ *   phase 1: gather + encoder partial sums        -> all-reduce OCF_BUF_Z
+ *   phase 2: activations, decoder, loss partials  -> all-reduce OCF_BUF_DH and OCF_BUF_ROWSTATS
+ *   phase 3: backward, fused optimizer update, metrics */
+int ocf_train_step(ocf_model* model, ocf_batch* batch, const ocf_step_args* args,
+                   float* host_metrics, void* stream);
+/* model.test_on_batch as driven by evaluate_generator (train.py:208,218): forward only,
+ * dropout off. Sharded: phases 1, 2 then 3 (metrics only). */
+int ocf_eval_step(ocf_model* model, ocf_batch* batch, const ocf_step_args* args,
+                  float* host_metrics, void* stream);
+/* model.predict (train.py:239): out[rows, n_cols] = output_mask * full_predictions. */
+int ocf_predict(ocf_model* model, ocf_batch* batch, float* out, void* stream);
+/* Full-catalogue scoring: out[rows, n_cols] = full_predictions (model.py:82-84, the tensor
+ * before the mask multiply). `out_is_device` != 0: out is a device pointer and the call does
+ * not synchronise. */
+int ocf_score(ocf_model* model, ocf_batch* batch, float* out, int out_is_device, void* stream);
+/* Copies `count` metric records starting at step slot `first` of the device log to the host
+ * (synchronises `stream`). The log keeps the last 4096 steps. */
+int ocf_model_read_metrics(ocf_model* model, int64_t first, int32_t count, float* host,
+                           void* stream);
+/* Number of steps logged so far (train + eval). */
+int64_t ocf_model_steps_logged(const ocf_model* model);
+
+typedef enum { OCF_BUF_Z = 0, OCF_BUF_DH = 1, OCF_BUF_ROWSTATS = 2 } ocf_buffer;
+/* Device pointer + float count of a buffer a sharded step exchanges between phases. */
+int ocf_model_buffer(ocf_model* model, int which, void** device_ptr, int64_t* count);
+/* Device pointer of a weight (kernel or bias, Keras index) in the library's internal layout,
+ * for collectives over replicated parameters; count in floats. */
+int ocf_model_weight_device(ocf_model* model, int index, void** device_ptr, int64_t* count);
+/* Number of kernels of this library launched by the calling process so far. */
+int64_t ocf_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCF_H */

@@ -1,0 +1,126 @@
+"""ctypes binding of `csrc/libocf_b200.so` (C ABI: `include/ocf.h`).
+
+The library is the product; there is no CPU fallback. `lib()` raises `OcfError` when the
+shared object is missing (run `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C omnidirectional_collaborative_filtering_b200/csrc`), and every compute call raises
+when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "csrc", "libocf_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "ocf.h")
+
+
+class OcfError(RuntimeError):
+    pass
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [
+        ("n_cols", C.c_int32), ("n_cols_total", C.c_int32), ("n_layers", C.c_int32),
+        ("widths", C.c_int32 * 8), ("aux", C.c_int32), ("activation", C.c_int32),
+        ("loss", C.c_int32), ("l2", C.c_float), ("dropout_p", C.c_float),
+        ("aux_var_value", C.c_float), ("rating_range", C.c_float), ("max_rows", C.c_int32),
+        ("max_entries", C.c_int64), ("sharded", C.c_int32),
+    ]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [("dropout_seed", C.c_uint64), ("step", C.c_uint32), ("row0", C.c_int32),
+                ("rows_total", C.c_int32), ("phase", C.c_int32)]
+
+
+ACTIVATIONS = {"linear": 0, None: 0, "sigmoid": 1, "tanh": 2, "relu": 3, "elu": 4, "selu": 5, "softplus": 6}
+AUX_TYPES = {None: 0, "causal": 1, "dropout": 2, "zeros": 3, "both": 4}
+LOSSES = {"mean_squared_error": 0, "mse": 0, "mean_absolute_error": 1, "mae": 1}
+OPTIMIZERS = {"sgd": 0, "adagrad": 1, "rmsprop": 2, "adam": 3}
+N_METRICS = 8
+BUF_Z, BUF_DH, BUF_ROWSTATS = 0, 1, 2
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "ocf_last_error": (C.c_char_p, []),
+    "ocf_version": (C.c_int, []),
+    "ocf_device_count": (C.c_int, []),
+    "ocf_kernel_launches": (C.c_int64, []),
+    "ocf_store_create": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.c_int, C.POINTER(_P)]),
+    "ocf_store_destroy": (C.c_int, [_P]),
+    "ocf_store_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "ocf_pair_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "ocf_pair_destroy": (C.c_int, [_P]),
+    "ocf_batch_create": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(_P)]),
+    "ocf_batch_destroy": (C.c_int, [_P]),
+    "ocf_batch_fill_split": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_int, C.c_float, _P]),
+    "ocf_batch_fill_fixed": (C.c_int, [_P, _P, _P, C.c_int32, C.c_float, _P]),
+    "ocf_batch_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "ocf_batch_densify": (C.c_int, [_P, C.c_int, _P, _P]),
+    "ocf_model_create": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(_P)]),
+    "ocf_model_destroy": (C.c_int, [_P]),
+    "ocf_model_reserve": (C.c_int, [_P, C.c_int32, C.c_int64]),
+    "ocf_model_num_weights": (C.c_int, [_P]),
+    "ocf_model_weight_shape": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64)]),
+    "ocf_model_set_weight": (C.c_int, [_P, C.c_int, _P, C.c_int64]),
+    "ocf_model_get_weight": (C.c_int, [_P, C.c_int, _P, C.c_int64]),
+    "ocf_model_set_optimizer": (C.c_int, [_P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "ocf_model_set_loss": (C.c_int, [_P, C.c_int, C.c_float]),
+    "ocf_model_set_aux": (C.c_int, [_P, C.c_int]),
+    "ocf_model_set_trainable": (C.c_int, [_P, C.c_int, C.c_int]),
+    "ocf_model_reset_optimizer": (C.c_int, [_P]),
+    "ocf_train_step": (C.c_int, [_P, _P, C.POINTER(StepArgs), _P, _P]),
+    "ocf_eval_step": (C.c_int, [_P, _P, C.POINTER(StepArgs), _P, _P]),
+    "ocf_predict": (C.c_int, [_P, _P, _P, _P]),
+    "ocf_score": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "ocf_model_read_metrics": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
+    "ocf_model_steps_logged": (C.c_int64, [_P]),
+    "ocf_model_buffer": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "ocf_model_weight_device": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64)]),
+}
+
+_lib = None
+
+
+def header_symbols():
+    """Every function name `include/ocf.h` declares."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ocf_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    """The loaded library; raises OcfError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise OcfError("libocf_b200.so is not built (%s); there is no CPU fallback" % SO_PATH)
+        handle = C.CDLL(SO_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().ocf_last_error()
+        raise OcfError("ocf error %d: %s" % (status, msg.decode() if msg else "?"))
+
+
+def require_gpu():
+    if lib().ocf_device_count() < 1:
+        raise OcfError("no CUDA device: the hot path is CUDA-only (sm_100a), there is no CPU fallback")
+
+
+def ptr(array):
+    """Host pointer of a C-contiguous NumPy array (None -> NULL)."""
+    if array is None:
+        return None
+    assert array.flags["C_CONTIGUOUS"]
+    return array.ctypes.data_as(C.c_void_p)

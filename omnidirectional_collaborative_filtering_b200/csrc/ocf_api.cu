@@ -1,0 +1,1027 @@
+// libocf_b200: the C ABI of include/ocf.h over the kernels in ocf_kernels.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ocf_kernels.cuh"
+
+namespace ocf {
+
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+int fail(int code, const std::string& msg) {
+  last_error() = msg;
+  return code;
+}
+std::atomic<long long> g_launches{0};
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int pad_h(int h) { return (int)align_up((size_t)h, HPAD); }
+
+// Device allocations of one handle, freed together.
+struct Arena {
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  int alloc(void** out, size_t n, bool zero) {
+    *out = nullptr;
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(out, n);
+    if (e != cudaSuccess) return fail(OCF_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(n) + "): " + cudaGetErrorString(e));
+    ptrs.push_back(*out);
+    bytes += n;
+    if (zero) OCF_CUDA(cudaMemset(*out, 0, n));
+    return OCF_OK;
+  }
+  template <typename T> int get(T** out, size_t count, bool zero = false) {
+    return alloc(reinterpret_cast<void**>(out), count * sizeof(T), zero);
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+    bytes = 0;
+  }
+};
+
+}  // namespace ocf
+
+using namespace ocf;
+
+// ============================================================================================
+// handles
+// ============================================================================================
+struct ocf_store {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0, max_col_len = 0;
+  bool has_dups = false, has_csc = false;
+  std::vector<int64_t> h_rowptr;
+  StoreDev dev{};
+  Arena mem;
+};
+
+struct ocf_pair {
+  const ocf_store* in = nullptr;
+  const ocf_store* tg = nullptr;
+  uint8_t* d_in_overlap = nullptr;
+  Arena mem;
+};
+
+struct ocf_batch {
+  int max_rows = 0;
+  int64_t max_entries = 0;
+  int max_items = 0;
+  size_t staging_bytes = 0;
+  uint8_t* h_staging = nullptr;   // pinned
+  uint8_t* d_staging = nullptr;
+  cudaEvent_t copied = nullptr;
+  bool copy_pending = false;
+  int32_t* d_ent_col = nullptr;
+  float* d_ent_val = nullptr;
+  uint8_t* d_codes = nullptr;
+  uint32_t* d_rowslot = nullptr;
+  int64_t rowslot_rows = 0;
+  uint32_t tag = 0;
+  BatchDev dev{};
+  int mode = 0;                   // 0 empty, 1 split, 2 fixed
+  const ocf_store* store = nullptr;
+  float aux_value = -1.f;
+  int64_t target_count = 0;
+  size_t last_h2d = 0;
+  Arena mem;
+};
+
+struct Layer {
+  int fan_in = 0, fan_out = 0;    // true sizes (Keras)
+  int rows = 0, hp = 0;           // internal: W is [rows, hp] (decoder: [n_cols, hp_in])
+  float *W = nullptr, *b = nullptr;
+  float *Ws1 = nullptr, *Ws2 = nullptr, *bs1 = nullptr, *bs2 = nullptr;
+  int bias_len = 0;
+  bool trainable = true;
+};
+
+struct ocf_model {
+  ocf_model_config cfg{};
+  int L = 0, nblk = 1;
+  int3 bits{};
+  std::vector<Layer> layers;      // 0 = encoder, 1..L-1 hidden, L = decoder
+  std::vector<int> hp;            // padded hidden widths
+  int max_items = 0;
+  // workspaces
+  float *P1 = nullptr, *P2 = nullptr, *itemstats = nullptr, *rowstats = nullptr, *dy = nullptr;
+  std::vector<float*> zsum, act, h, dscale, dz;
+  float* dh_top = nullptr;
+  float* dense_out = nullptr;
+  float* regparts = nullptr;
+  float* d_log = nullptr;
+  float* h_rec = nullptr;         // pinned
+  int* d_err = nullptr;
+  int64_t steps_logged = 0;
+  // optimizer
+  int opt_kind = OCF_OPT_ADAGRAD;
+  float lr = 0.005f, p1 = 0.9f, p2 = 0.999f, eps = 1e-8f, decay = 0.f;
+  int64_t iterations = 0;
+  bool has_s1 = false, has_s2 = false;
+  Arena mem, opt_mem, dense_mem, ws_mem;
+};
+
+constexpr int LOG_CAP = 4096;
+constexpr int LOG_W = OCF_N_METRICS;
+constexpr int N_REGPART = 64;
+
+// ============================================================================================
+// misc
+// ============================================================================================
+extern "C" const char* ocf_last_error(void) { return last_error().c_str(); }
+extern "C" int ocf_version(void) { return OCF_VERSION; }
+extern "C" int ocf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" int64_t ocf_kernel_launches(void) { return (int64_t)g_launches.load(); }
+
+// ============================================================================================
+// store
+// ============================================================================================
+extern "C" int ocf_store_create(int64_t n_rows, int64_t n_cols, const int64_t* rowptr, const int32_t* col,
+                                const float* val, int build_csc, ocf_store** out) {
+  OCF_REQUIRE(out != nullptr && rowptr != nullptr, "ocf_store_create: null argument");
+  *out = nullptr;
+  OCF_REQUIRE(n_rows >= 0 && n_cols > 0 && n_cols < (int64_t(1) << 31), "ocf_store_create: bad shape");
+  OCF_REQUIRE(rowptr[0] == 0, "ocf_store_create: rowptr[0] must be 0");
+  const int64_t nnz = rowptr[n_rows];
+  OCF_REQUIRE(nnz >= 0 && nnz < (int64_t(1) << 31), "ocf_store_create: nnz must be < 2^31");
+  OCF_REQUIRE(nnz == 0 || (col != nullptr && val != nullptr), "ocf_store_create: null col/val");
+  for (int64_t r = 0; r < n_rows; ++r)
+    OCF_REQUIRE(rowptr[r + 1] >= rowptr[r], "ocf_store_create: rowptr not monotone");
+  ocf_store* s = new ocf_store();
+  s->n_rows = n_rows; s->n_cols = n_cols; s->nnz = nnz;
+  s->h_rowptr.assign(rowptr, rowptr + n_rows + 1);
+
+  // repeated columns inside a row -> next_dup chains (last-write-wins resolution in K1)
+  std::vector<int32_t> stamp((size_t)n_cols, -1), lastpos;
+  std::vector<int32_t> next_dup;
+  for (int64_t r = 0; r < n_rows && !s->has_dups; ++r)
+    for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const int32_t c = col[e];
+      if (c < 0 || c >= n_cols) { delete s; return fail(OCF_ERR_INVALID, "ocf_store_create: column out of range"); }
+      if (stamp[c] == (int32_t)r) { s->has_dups = true; break; }
+      stamp[c] = (int32_t)r;
+    }
+  if (s->has_dups) {
+    next_dup.assign((size_t)nnz, -1);
+    lastpos.assign((size_t)n_cols, -1);
+    std::fill(stamp.begin(), stamp.end(), -1);
+    for (int64_t r = 0; r < n_rows; ++r) {
+      const int64_t a = rowptr[r], b = rowptr[r + 1];
+      for (int64_t e = b - 1; e >= a; --e) {
+        const int32_t c = col[e];
+        if (c < 0 || c >= n_cols) { delete s; return fail(OCF_ERR_INVALID, "ocf_store_create: column out of range"); }
+        next_dup[e] = (stamp[c] == (int32_t)r) ? lastpos[c] : -1;
+        stamp[c] = (int32_t)r;
+        lastpos[c] = (int32_t)(e - a);
+      }
+    }
+  }
+  int st = OCF_OK;
+  int64_t* d_rowptr = nullptr; int32_t* d_col = nullptr; float* d_val = nullptr; int32_t* d_nd = nullptr;
+  auto bail = [&](int code) { s->mem.release(); delete s; return code; };
+  if ((st = s->mem.get(&d_rowptr, (size_t)n_rows + 1)) || (st = s->mem.get(&d_col, (size_t)nnz)) ||
+      (st = s->mem.get(&d_val, (size_t)nnz)))
+    return bail(st);
+  if (cudaMemcpy(d_rowptr, rowptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+      (nnz && cudaMemcpy(d_col, col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice) != cudaSuccess) ||
+      (nnz && cudaMemcpy(d_val, val, sizeof(float) * nnz, cudaMemcpyHostToDevice) != cudaSuccess))
+    return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
+  if (s->has_dups) {
+    if ((st = s->mem.get(&d_nd, (size_t)nnz))) return bail(st);
+    if (cudaMemcpy(d_nd, next_dup.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
+  }
+  s->dev.rowptr = d_rowptr; s->dev.col = d_col; s->dev.val = d_val; s->dev.next_dup = d_nd;
+  if (build_csc) {
+    // counting sort in CSR order: entries of a column come out ordered by (row, position)
+    std::vector<int64_t> colptr((size_t)n_cols + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) colptr[(size_t)col[e] + 1]++;
+    for (int64_t c = 0; c < n_cols; ++c) {
+      s->max_col_len = std::max(s->max_col_len, colptr[c + 1]);
+      colptr[c + 1] += colptr[c];
+    }
+    std::vector<int64_t> cursor(colptr.begin(), colptr.end() - 1);
+    std::vector<int32_t> crow((size_t)nnz), cj((size_t)nnz);
+    for (int64_t r = 0; r < n_rows; ++r)
+      for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+        const int64_t k = cursor[col[e]]++;
+        crow[k] = (int32_t)r;
+        cj[k] = (int32_t)(e - rowptr[r]);
+      }
+    int64_t* d_colptr = nullptr; int32_t* d_crow = nullptr; int32_t* d_cj = nullptr;
+    if ((st = s->mem.get(&d_colptr, (size_t)n_cols + 1)) || (st = s->mem.get(&d_crow, (size_t)nnz)) ||
+        (st = s->mem.get(&d_cj, (size_t)nnz)))
+      return bail(st);
+    if (cudaMemcpy(d_colptr, colptr.data(), sizeof(int64_t) * (n_cols + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+        (nnz && cudaMemcpy(d_crow, crow.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice) != cudaSuccess) ||
+        (nnz && cudaMemcpy(d_cj, cj.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice) != cudaSuccess))
+      return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
+    s->dev.colptr = d_colptr; s->dev.crow = d_crow; s->dev.cj = d_cj;
+    s->has_csc = true;
+  }
+  *out = s;
+  return OCF_OK;
+}
+
+extern "C" int ocf_store_destroy(ocf_store* s) {
+  if (s) { s->mem.release(); delete s; }
+  return OCF_OK;
+}
+
+extern "C" int ocf_store_info(const ocf_store* s, int64_t info[6]) {
+  OCF_REQUIRE(s && info, "ocf_store_info: null argument");
+  info[0] = s->n_rows; info[1] = s->n_cols; info[2] = s->nnz; info[3] = s->has_dups ? 1 : 0;
+  info[4] = s->max_col_len; info[5] = (int64_t)s->mem.bytes;
+  return OCF_OK;
+}
+
+extern "C" int ocf_pair_create(const ocf_store* in, const ocf_store* tg, ocf_pair** out) {
+  OCF_REQUIRE(in && tg && out, "ocf_pair_create: null argument");
+  *out = nullptr;
+  OCF_REQUIRE(in->n_rows == tg->n_rows && in->n_cols == tg->n_cols, "ocf_pair_create: stores must have the same rows and columns");
+  ocf_pair* p = new ocf_pair();
+  p->in = in; p->tg = tg;
+  // input ratings whose column is also a target of the same row (missing-data mask counted once)
+  std::vector<int32_t> hc_in((size_t)in->nnz), hc_tg((size_t)tg->nnz);
+  if (in->nnz && cudaMemcpy(hc_in.data(), in->dev.col, sizeof(int32_t) * in->nnz, cudaMemcpyDeviceToHost) != cudaSuccess) { delete p; return fail(OCF_ERR_CUDA, "ocf_pair_create: download failed"); }
+  if (tg->nnz && cudaMemcpy(hc_tg.data(), tg->dev.col, sizeof(int32_t) * tg->nnz, cudaMemcpyDeviceToHost) != cudaSuccess) { delete p; return fail(OCF_ERR_CUDA, "ocf_pair_create: download failed"); }
+  std::vector<int32_t> stamp((size_t)in->n_cols, -1);
+  std::vector<uint8_t> ov((size_t)in->nnz, 0);
+  bool any = false;
+  for (int64_t r = 0; r < in->n_rows; ++r) {
+    for (int64_t e = tg->h_rowptr[r]; e < tg->h_rowptr[r + 1]; ++e) stamp[hc_tg[e]] = (int32_t)r;
+    for (int64_t e = in->h_rowptr[r]; e < in->h_rowptr[r + 1]; ++e)
+      if (stamp[hc_in[e]] == (int32_t)r) { ov[e] = 1; any = true; }
+  }
+  if (any) {
+    int st = p->mem.get(&p->d_in_overlap, (size_t)in->nnz);
+    if (st) { delete p; return st; }
+    if (cudaMemcpy(p->d_in_overlap, ov.data(), ov.size(), cudaMemcpyHostToDevice) != cudaSuccess) { p->mem.release(); delete p; return fail(OCF_ERR_CUDA, "ocf_pair_create: upload failed"); }
+  }
+  *out = p;
+  return OCF_OK;
+}
+
+extern "C" int ocf_pair_destroy(ocf_pair* p) {
+  if (p) { p->mem.release(); delete p; }
+  return OCF_OK;
+}
+
+// ============================================================================================
+// batch
+// ============================================================================================
+static size_t staging_layout(int B, int n_items, int64_t n_entries, size_t off[6]) {
+  size_t o = 0;
+  off[0] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // row_ids
+  off[1] = o; o = align_up(o + sizeof(int32_t) * (B + 1), 16);       // ent_off
+  off[2] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // in_len
+  off[3] = o; o = align_up(o + sizeof(int32_t) * (B + 1), 16);       // item_ptr
+  off[4] = o; o = align_up(o + sizeof(int4) * (size_t)n_items, 16);  // items
+  off[5] = o; o = align_up(o + (size_t)n_entries, 16);               // flags
+  return o;
+}
+
+extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch** out) {
+  OCF_REQUIRE(out != nullptr, "ocf_batch_create: null argument");
+  *out = nullptr;
+  OCF_REQUIRE(max_rows > 0 && max_rows <= MAX_BATCH_ROWS, "ocf_batch_create: max_rows must be in 1..4096");
+  OCF_REQUIRE(max_entries >= 0 && max_entries < (int64_t(1) << 31), "ocf_batch_create: bad max_entries");
+  ocf_batch* b = new ocf_batch();
+  b->max_rows = max_rows; b->max_entries = max_entries;
+  b->max_items = (int)(max_entries / 32 + max_rows + 1);
+  size_t off[6];
+  b->staging_bytes = staging_layout(max_rows, b->max_items, max_entries, off);
+  auto bail = [&](int code) { b->mem.release(); if (b->h_staging) cudaFreeHost(b->h_staging); if (b->copied) cudaEventDestroy(b->copied); delete b; return code; };
+  if (cudaMallocHost(reinterpret_cast<void**>(&b->h_staging), b->staging_bytes) != cudaSuccess)
+    return bail(fail(OCF_ERR_NOMEM, "ocf_batch_create: pinned allocation failed"));
+  if (cudaEventCreateWithFlags(&b->copied, cudaEventDisableTiming) != cudaSuccess)
+    return bail(fail(OCF_ERR_CUDA, "ocf_batch_create: event creation failed"));
+  int st;
+  if ((st = b->mem.get(&b->d_staging, b->staging_bytes)) || (st = b->mem.get(&b->d_ent_col, (size_t)max_entries)) ||
+      (st = b->mem.get(&b->d_ent_val, (size_t)max_entries)) || (st = b->mem.get(&b->d_codes, (size_t)max_entries)))
+    return bail(st);
+  *out = b;
+  return OCF_OK;
+}
+
+extern "C" int ocf_batch_destroy(ocf_batch* b) {
+  if (b) {
+    b->mem.release();
+    if (b->d_rowslot) cudaFree(b->d_rowslot);
+    if (b->h_staging) cudaFreeHost(b->h_staging);
+    if (b->copied) cudaEventDestroy(b->copied);
+    delete b;
+  }
+  return OCF_OK;
+}
+
+// Work items: chunks of <= CH ratings of one row, CH sized so that the row-centric kernels get
+// a few CTAs per SM whatever the batch looks like.
+static int pick_chunk(int64_t n_entries) {
+  const int64_t target_items = 148 * 6;
+  int64_t ch = (n_entries + target_items - 1) / target_items;
+  ch = (int64_t)align_up((size_t)std::max<int64_t>(ch, 1), 32);
+  return (int)std::min<int64_t>(std::max<int64_t>(ch, 32), 512);
+}
+
+static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const std::vector<int64_t>& rp_a,
+                       const std::vector<int64_t>* rp_b, int64_t n_store_rows, const uint8_t* flags,
+                       int64_t n_flags, cudaStream_t stream) {
+  OCF_REQUIRE(n_rows > 0 && n_rows <= b->max_rows, "batch fill: row count exceeds the batch capacity");
+  if (b->copy_pending) { OCF_CUDA(cudaEventSynchronize(b->copied)); b->copy_pending = false; }
+  // pass 1: lengths
+  int64_t total = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    const int32_t row = row_ids[r];
+    OCF_REQUIRE(row >= 0 && row < n_store_rows, "batch fill: row id out of range");
+    total += rp_a[row + 1] - rp_a[row];
+    if (rp_b) total += (*rp_b)[row + 1] - (*rp_b)[row];
+  }
+  OCF_REQUIRE(total <= b->max_entries, "batch fill: more ratings than the batch capacity");
+  if (flags != nullptr || n_flags >= 0) OCF_REQUIRE(n_flags == total, "batch fill: n_flags must equal the total length of the listed rows");
+  const int ch = pick_chunk(total);
+  int64_t n_items = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    const int32_t row = row_ids[r];
+    int64_t n = rp_a[row + 1] - rp_a[row];
+    if (rp_b) n += (*rp_b)[row + 1] - (*rp_b)[row];
+    n_items += (n + ch - 1) / ch;
+  }
+  OCF_REQUIRE(n_items <= b->max_items, "batch fill: too many work items");
+  size_t off[6];
+  const size_t bytes = staging_layout(n_rows, (int)n_items, total, off);
+  uint8_t* hs = b->h_staging;
+  int32_t* h_rows = reinterpret_cast<int32_t*>(hs + off[0]);
+  int32_t* h_eoff = reinterpret_cast<int32_t*>(hs + off[1]);
+  int32_t* h_inlen = reinterpret_cast<int32_t*>(hs + off[2]);
+  int32_t* h_iptr = reinterpret_cast<int32_t*>(hs + off[3]);
+  int4* h_items = reinterpret_cast<int4*>(hs + off[4]);
+  int64_t e = 0; int it = 0; int64_t tcount = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    const int32_t row = row_ids[r];
+    const int64_t na = rp_a[row + 1] - rp_a[row];
+    const int64_t nb = rp_b ? (*rp_b)[row + 1] - (*rp_b)[row] : 0;
+    h_rows[r] = row; h_eoff[r] = (int32_t)e; h_inlen[r] = (int32_t)na; h_iptr[r] = it;
+    const int64_t n = na + nb;
+    for (int64_t s0 = 0; s0 < n; s0 += ch) h_items[it++] = make_int4(r, (int)s0, (int)std::min<int64_t>(ch, n - s0), 0);
+    e += n; tcount += nb;
+  }
+  h_eoff[n_rows] = (int32_t)e; h_iptr[n_rows] = it;
+  if (flags != nullptr && total > 0) std::memcpy(hs + off[5], flags, (size_t)total);
+  OCF_CUDA(cudaMemcpyAsync(b->d_staging, hs, bytes, cudaMemcpyHostToDevice, stream));
+  OCF_CUDA(cudaEventRecord(b->copied, stream));
+  b->copy_pending = true;
+  b->last_h2d = bytes;
+  b->target_count = tcount;
+  BatchDev& d = b->dev;
+  d.B = n_rows; d.n_items = (int)n_items; d.n_entries = (int)total;
+  d.row_ids = reinterpret_cast<const int32_t*>(b->d_staging + off[0]);
+  d.ent_off = reinterpret_cast<const int32_t*>(b->d_staging + off[1]);
+  d.in_len = reinterpret_cast<const int32_t*>(b->d_staging + off[2]);
+  d.item_ptr = reinterpret_cast<const int32_t*>(b->d_staging + off[3]);
+  d.items = reinterpret_cast<const int4*>(b->d_staging + off[4]);
+  d.flags = b->d_staging + off[5];
+  d.ent_col = b->d_ent_col; d.ent_val = b->d_ent_val; d.codes = b->d_codes;
+  return OCF_OK;
+}
+
+extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows,
+                                    const uint8_t* keep_flags, int64_t n_flags, int pass_through,
+                                    float aux_var_value, void* stream_) {
+  OCF_REQUIRE(b && store && row_ids, "ocf_batch_fill_split: null argument");
+  OCF_REQUIRE(keep_flags != nullptr || n_flags == 0, "ocf_batch_fill_split: null keep_flags");
+  cudaStream_t stream = as_stream(stream_);
+  {  // the row -> slot map needs distinct rows
+    std::vector<int32_t> tmp(row_ids, row_ids + std::max(n_rows, 0));
+    std::sort(tmp.begin(), tmp.end());
+    OCF_REQUIRE(std::adjacent_find(tmp.begin(), tmp.end()) == tmp.end(), "ocf_batch_fill_split: a row appears twice in the batch");
+  }
+  if (b->rowslot_rows < store->n_rows) {
+    if (b->d_rowslot) { OCF_CUDA(cudaStreamSynchronize(stream)); cudaFree(b->d_rowslot); b->d_rowslot = nullptr; }
+    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_rowslot), sizeof(uint32_t) * (size_t)std::max<int64_t>(store->n_rows, 1)));
+    b->rowslot_rows = store->n_rows;
+    b->tag = 0;
+  }
+  if (b->tag == 0 || b->tag >= (1u << (32 - SLOT_BITS)) - 1 || b->store != store) {
+    OCF_CUDA(cudaMemsetAsync(b->d_rowslot, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(b->rowslot_rows, 1), stream));
+    b->tag = 0;
+  }
+  b->tag += 1;
+  OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, keep_flags, n_flags, stream));
+  b->dev.rowslot = b->d_rowslot;
+  b->dev.tag = b->tag;
+  b->mode = 1; b->store = store; b->aux_value = aux_var_value;
+  // in split mode every listed rating is a target when pass_through, else the flag-0 ones
+  int64_t tc = 0;
+  if (pass_through) tc = n_flags; else for (int64_t k = 0; k < n_flags; ++k) tc += keep_flags[k] == 0;
+  b->target_count = tc;
+  if (b->dev.n_items > 0) {
+    k_gather_split<<<b->dev.n_items, 128, 0, stream>>>(store->dev, b->dev, pass_through ? 1 : 0);
+    OCF_LAUNCHED();
+  }
+  return OCF_OK;
+}
+
+extern "C" int ocf_batch_fill_fixed(ocf_batch* b, const ocf_pair* pair, const int32_t* row_ids, int32_t n_rows,
+                                    float aux_var_value, void* stream_) {
+  OCF_REQUIRE(b && pair && row_ids, "ocf_batch_fill_fixed: null argument");
+  cudaStream_t stream = as_stream(stream_);
+  OCF_TRY(batch_stage(b, row_ids, n_rows, pair->in->h_rowptr, &pair->tg->h_rowptr, pair->in->n_rows, nullptr, -1, stream));
+  b->dev.rowslot = nullptr; b->dev.tag = 0;
+  b->mode = 2; b->store = pair->tg; b->aux_value = aux_var_value;
+  if (b->dev.n_items > 0) {
+    k_gather_fixed<<<b->dev.n_items, 128, 0, stream>>>(pair->in->dev, pair->tg->dev, pair->d_in_overlap, b->dev);
+    OCF_LAUNCHED();
+  }
+  return OCF_OK;
+}
+
+extern "C" int ocf_batch_info(const ocf_batch* b, int64_t info[5]) {
+  OCF_REQUIRE(b && info, "ocf_batch_info: null argument");
+  info[0] = b->dev.B; info[1] = b->dev.n_entries; info[2] = b->dev.n_items; info[3] = b->target_count;
+  info[4] = (int64_t)b->last_h2d;
+  return OCF_OK;
+}
+
+extern "C" int ocf_batch_densify(const ocf_batch* b, int which, double* out, void* stream_) {
+  OCF_REQUIRE(b && out, "ocf_batch_densify: null argument");
+  OCF_REQUIRE(b->mode != 0, "ocf_batch_densify: batch is empty");
+  OCF_REQUIRE(which >= 0 && which <= 4, "ocf_batch_densify: which must be 0..4");
+  cudaStream_t stream = as_stream(stream_);
+  const int64_t n_cols = b->store->n_cols;
+  const size_t count = (size_t)b->dev.B * (size_t)n_cols;
+  double* d_out = nullptr;
+  OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_out), count * sizeof(double)));
+  cudaError_t e = cudaMemsetAsync(d_out, 0, count * sizeof(double), stream);
+  if (e == cudaSuccess && b->dev.n_entries > 0) {
+    k_densify<<<(b->dev.n_entries + 255) / 256, 256, 0, stream>>>(b->dev, which, (double)b->aux_value, (int)n_cols, d_out);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, count * sizeof(double), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(OCF_ERR_CUDA, std::string("ocf_batch_densify: ") + cudaGetErrorString(e));
+  return OCF_OK;
+}
+
+// ============================================================================================
+// model
+// ============================================================================================
+static void aux_bits(int aux, int& nblk, int3& bits) {
+  bits = make_int3(CODE_IN, 0, 0);
+  nblk = 1;
+  switch (aux) {
+    case OCF_AUX_CAUSAL: nblk = 2; bits.y = CODE_OBS; break;
+    case OCF_AUX_DROPOUT: nblk = 2; bits.y = CODE_IN; break;
+    case OCF_AUX_ZEROS: nblk = 2; bits.y = 0; break;
+    case OCF_AUX_BOTH: nblk = 3; bits.y = CODE_IN; bits.z = CODE_OBS; break;
+    default: break;
+  }
+}
+
+// Batch-sized buffers (activations, work-item partials, per-entry gradients).
+static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
+  m->ws_mem.release();
+  m->dense_mem.release();
+  m->dense_out = nullptr;
+  m->cfg.max_rows = max_rows;
+  m->cfg.max_entries = max_entries;
+  m->max_items = (int)(max_entries / 32 + max_rows + 1);
+  const int L = m->L, Bm = max_rows;
+  m->zsum.assign(L, nullptr); m->act.assign(L, nullptr); m->h.assign(L, nullptr);
+  m->dscale.assign(L, nullptr); m->dz.assign(L, nullptr);
+  const bool drop = m->cfg.dropout_p > 0.f;
+  Arena& ws = m->ws_mem;
+  for (int l = 0; l < L; ++l) {
+    const size_t n = (size_t)Bm * m->hp[l];
+    OCF_TRY(ws.get(&m->zsum[l], n, true));
+    OCF_TRY(ws.get(&m->act[l], n, true));
+    OCF_TRY(ws.get(&m->dz[l], n, true));
+    if (drop) { OCF_TRY(ws.get(&m->h[l], n, true)); OCF_TRY(ws.get(&m->dscale[l], n, true)); }
+    else m->h[l] = m->act[l];
+  }
+  OCF_TRY(ws.get(&m->P1, (size_t)m->max_items * m->hp[0]));
+  OCF_TRY(ws.get(&m->P2, (size_t)m->max_items * m->hp[L - 1]));
+  OCF_TRY(ws.get(&m->itemstats, (size_t)m->max_items * ROWSTAT_W));
+  OCF_TRY(ws.get(&m->rowstats, (size_t)Bm * ROWSTAT_W, true));
+  OCF_TRY(ws.get(&m->dy, (size_t)max_entries, true));
+  OCF_TRY(ws.get(&m->dh_top, (size_t)Bm * m->hp[L - 1], true));
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
+  OCF_REQUIRE(cfg && out, "ocf_model_create: null argument");
+  *out = nullptr;
+  OCF_REQUIRE(cfg->n_cols > 0 && cfg->n_cols_total >= cfg->n_cols, "ocf_model_create: bad n_cols");
+  OCF_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= 8, "ocf_model_create: n_layers must be 1..8");
+  OCF_REQUIRE(cfg->aux >= OCF_AUX_NONE && cfg->aux <= OCF_AUX_BOTH, "ocf_model_create: bad aux");
+  OCF_REQUIRE(cfg->activation >= OCF_ACT_LINEAR && cfg->activation <= OCF_ACT_SOFTPLUS, "ocf_model_create: bad activation");
+  OCF_REQUIRE(cfg->loss == OCF_LOSS_MSE || cfg->loss == OCF_LOSS_MAE, "ocf_model_create: bad loss");
+  OCF_REQUIRE(cfg->max_rows > 0 && cfg->max_rows <= MAX_BATCH_ROWS, "ocf_model_create: max_rows must be 1..4096");
+  OCF_REQUIRE(cfg->max_entries > 0 && cfg->max_entries < (int64_t(1) << 31), "ocf_model_create: bad max_entries");
+  OCF_REQUIRE(cfg->dropout_p < 1.0f, "ocf_model_create: dropout_p must be < 1");
+  for (int l = 0; l < cfg->n_layers; ++l)
+    OCF_REQUIRE(cfg->widths[l] > 0 && cfg->widths[l] <= MAX_HP, "ocf_model_create: hidden widths must be 1..1024");
+  ocf_model* m = new ocf_model();
+  m->cfg = *cfg;
+  m->L = cfg->n_layers;
+  aux_bits(cfg->aux, m->nblk, m->bits);
+  m->max_items = (int)(cfg->max_entries / 32 + cfg->max_rows + 1);
+  const int L = m->L, N = cfg->n_cols, Bm = cfg->max_rows;
+  for (int l = 0; l < L; ++l) m->hp.push_back(pad_h(cfg->widths[l]));
+  m->layers.resize(L + 1);
+  int st = OCF_OK;
+  auto bail = [&](int code) { m->mem.release(); m->opt_mem.release(); m->ws_mem.release(); if (m->h_rec) cudaFreeHost(m->h_rec); delete m; return code; };
+  for (int l = 0; l <= L && !st; ++l) {
+    Layer& ly = m->layers[l];
+    if (l == 0) { ly.fan_in = m->nblk * N; ly.fan_out = cfg->widths[0]; ly.rows = m->nblk * N; ly.hp = m->hp[0]; ly.bias_len = m->hp[0]; }
+    else if (l < L) { ly.fan_in = cfg->widths[l - 1]; ly.fan_out = cfg->widths[l]; ly.rows = m->hp[l - 1]; ly.hp = m->hp[l]; ly.bias_len = m->hp[l]; }
+    else { ly.fan_in = cfg->widths[L - 1]; ly.fan_out = N; ly.rows = N; ly.hp = m->hp[L - 1]; ly.bias_len = N; }
+    st = m->mem.get(&ly.W, (size_t)ly.rows * ly.hp, true);
+    if (!st) st = m->mem.get(&ly.b, (size_t)ly.bias_len, true);
+  }
+  if (st) return bail(st);
+  if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_log, (size_t)LOG_CAP * LOG_W, true)) ||
+      (st = m->mem.get(&m->d_err, 1, true)))
+    return bail(st);
+  if ((st = alloc_workspace(m, cfg->max_rows, cfg->max_entries))) return bail(st);
+  if (cudaMallocHost(reinterpret_cast<void**>(&m->h_rec), sizeof(float) * LOG_CAP * LOG_W) != cudaSuccess)
+    return bail(fail(OCF_ERR_NOMEM, "ocf_model_create: pinned allocation failed"));
+  *out = m;
+  st = ocf_model_set_optimizer(m, OCF_OPT_ADAGRAD, 0.005f, 0.9f, 0.999f, 1e-8f, 0.f);   // train.py:50-51
+  if (st) { *out = nullptr; return bail(st); }
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_destroy(ocf_model* m) {
+  if (m) {
+    m->mem.release(); m->opt_mem.release(); m->dense_mem.release(); m->ws_mem.release();
+    if (m->h_rec) cudaFreeHost(m->h_rec);
+    delete m;
+  }
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_reserve(ocf_model* m, int32_t max_rows, int64_t max_entries) {
+  OCF_REQUIRE(m, "ocf_model_reserve: null argument");
+  OCF_REQUIRE(max_rows > 0 && max_rows <= MAX_BATCH_ROWS && max_entries > 0 && max_entries < (int64_t(1) << 31), "ocf_model_reserve: bad sizes");
+  if (max_rows <= m->cfg.max_rows && max_entries <= m->cfg.max_entries) return OCF_OK;
+  OCF_CUDA(cudaDeviceSynchronize());
+  return alloc_workspace(m, std::max(max_rows, m->cfg.max_rows), std::max(max_entries, m->cfg.max_entries));
+}
+
+extern "C" int ocf_model_num_weights(const ocf_model* m) { return m ? 2 * (m->L + 1) : 0; }
+
+extern "C" int ocf_model_weight_shape(const ocf_model* m, int index, int64_t shape[2]) {
+  OCF_REQUIRE(m && shape && index >= 0 && index < 2 * (m->L + 1), "ocf_model_weight_shape: bad argument");
+  const Layer& ly = m->layers[index / 2];
+  if (index % 2 == 0) { shape[0] = ly.fan_in; shape[1] = ly.fan_out; }
+  else { shape[0] = ly.fan_out; shape[1] = 1; }
+  return OCF_OK;
+}
+
+// Keras layout <-> internal layout. Kernels of layers 0..L-1: [fan_in, fan_out] -> [rows, hp]
+// (fan_out padded); decoder kernel [H, N] -> transposed [N, hp].
+static int weight_io(const ocf_model* m, int index, float* host, int64_t count, bool to_device) {
+  const int l = index / 2;
+  const Layer& ly = m->layers[l];
+  const bool is_bias = index % 2 == 1;
+  const bool dec = l == m->L;
+  if (is_bias) {
+    OCF_REQUIRE(count == ly.fan_out, "weight i/o: wrong element count");
+    if (to_device) OCF_CUDA(cudaMemcpy(ly.b, host, sizeof(float) * ly.fan_out, cudaMemcpyHostToDevice));
+    else OCF_CUDA(cudaMemcpy(host, ly.b, sizeof(float) * ly.fan_out, cudaMemcpyDeviceToHost));
+    return OCF_OK;
+  }
+  OCF_REQUIRE(count == (int64_t)ly.fan_in * ly.fan_out, "weight i/o: wrong element count");
+  if (!dec) {
+    const size_t spitch = sizeof(float) * ly.fan_out, dpitch = sizeof(float) * ly.hp;
+    if (to_device) OCF_CUDA(cudaMemcpy2D(ly.W, dpitch, host, spitch, spitch, ly.fan_in, cudaMemcpyHostToDevice));
+    else OCF_CUDA(cudaMemcpy2D(host, spitch, ly.W, dpitch, spitch, ly.fan_in, cudaMemcpyDeviceToHost));
+    return OCF_OK;
+  }
+  // decoder: transpose through a host block of <= 32768 catalogue columns at a time
+  const int H = ly.fan_in, N = ly.fan_out, hp = ly.hp;
+  const int blk = 32768;
+  std::vector<float> tmp((size_t)std::min(blk, N) * hp);
+  for (int c0 = 0; c0 < N; c0 += blk) {
+    const int nc = std::min(blk, N - c0);
+    if (to_device) {
+      std::fill(tmp.begin(), tmp.end(), 0.f);
+      for (int k = 0; k < H; ++k) {
+        const float* src = host + (size_t)k * N + c0;
+        for (int c = 0; c < nc; ++c) tmp[(size_t)c * hp + k] = src[c];
+      }
+      OCF_CUDA(cudaMemcpy(ly.W + (size_t)c0 * hp, tmp.data(), sizeof(float) * (size_t)nc * hp, cudaMemcpyHostToDevice));
+    } else {
+      OCF_CUDA(cudaMemcpy(tmp.data(), ly.W + (size_t)c0 * hp, sizeof(float) * (size_t)nc * hp, cudaMemcpyDeviceToHost));
+      for (int k = 0; k < H; ++k) {
+        float* dst = host + (size_t)k * N + c0;
+        for (int c = 0; c < nc; ++c) dst[c] = tmp[(size_t)c * hp + k];
+      }
+    }
+  }
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_set_weight(ocf_model* m, int index, const float* host, int64_t count) {
+  OCF_REQUIRE(m && host && index >= 0 && index < 2 * (m->L + 1), "ocf_model_set_weight: bad argument");
+  OCF_CUDA(cudaDeviceSynchronize());
+  return weight_io(m, index, const_cast<float*>(host), count, true);
+}
+
+extern "C" int ocf_model_get_weight(const ocf_model* m, int index, float* host, int64_t count) {
+  OCF_REQUIRE(m && host && index >= 0 && index < 2 * (m->L + 1), "ocf_model_get_weight: bad argument");
+  OCF_CUDA(cudaDeviceSynchronize());
+  return weight_io(m, index, host, count, false);
+}
+
+extern "C" int ocf_model_reset_optimizer(ocf_model* m) {
+  OCF_REQUIRE(m, "ocf_model_reset_optimizer: null argument");
+  OCF_CUDA(cudaDeviceSynchronize());
+  m->iterations = 0;
+  for (Layer& ly : m->layers) {
+    if (ly.Ws1) OCF_CUDA(cudaMemset(ly.Ws1, 0, sizeof(float) * (size_t)ly.rows * ly.hp));
+    if (ly.Ws2) OCF_CUDA(cudaMemset(ly.Ws2, 0, sizeof(float) * (size_t)ly.rows * ly.hp));
+    if (ly.bs1) OCF_CUDA(cudaMemset(ly.bs1, 0, sizeof(float) * ly.bias_len));
+    if (ly.bs2) OCF_CUDA(cudaMemset(ly.bs2, 0, sizeof(float) * ly.bias_len));
+  }
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_set_optimizer(ocf_model* m, int kind, float lr, float p1, float p2, float epsilon, float decay) {
+  OCF_REQUIRE(m, "ocf_model_set_optimizer: null argument");
+  OCF_REQUIRE(kind >= OCF_OPT_SGD && kind <= OCF_OPT_ADAM, "ocf_model_set_optimizer: bad kind");
+  OCF_CUDA(cudaDeviceSynchronize());
+  const bool s1 = kind != OCF_OPT_SGD, s2 = kind == OCF_OPT_ADAM;
+  if (s1 != m->has_s1 || s2 != m->has_s2) {
+    m->opt_mem.release();
+    for (Layer& ly : m->layers) { ly.Ws1 = ly.Ws2 = ly.bs1 = ly.bs2 = nullptr; }
+    for (Layer& ly : m->layers) {
+      if (s1) { OCF_TRY(m->opt_mem.get(&ly.Ws1, (size_t)ly.rows * ly.hp, true)); OCF_TRY(m->opt_mem.get(&ly.bs1, (size_t)ly.bias_len, true)); }
+      if (s2) { OCF_TRY(m->opt_mem.get(&ly.Ws2, (size_t)ly.rows * ly.hp, true)); OCF_TRY(m->opt_mem.get(&ly.bs2, (size_t)ly.bias_len, true)); }
+    }
+    m->has_s1 = s1; m->has_s2 = s2;
+  }
+  m->opt_kind = kind; m->lr = lr; m->p1 = p1; m->p2 = p2; m->eps = epsilon; m->decay = decay;
+  return ocf_model_reset_optimizer(m);
+}
+
+extern "C" int ocf_model_set_loss(ocf_model* m, int loss, float rating_range) {
+  OCF_REQUIRE(m && (loss == OCF_LOSS_MSE || loss == OCF_LOSS_MAE), "ocf_model_set_loss: bad argument");
+  m->cfg.loss = loss;
+  m->cfg.rating_range = rating_range;
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_set_aux(ocf_model* m, int aux) {
+  OCF_REQUIRE(m && aux >= OCF_AUX_NONE && aux <= OCF_AUX_BOTH, "ocf_model_set_aux: bad argument");
+  int nblk; int3 bits;
+  aux_bits(aux, nblk, bits);
+  OCF_REQUIRE(nblk == m->nblk, "ocf_model_set_aux: this mask type feeds a different number of input blocks than the model has");
+  m->cfg.aux = aux; m->bits = bits;
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_set_trainable(ocf_model* m, int layer, int trainable) {
+  OCF_REQUIRE(m && layer >= 0 && layer <= m->L, "ocf_model_set_trainable: bad argument");
+  m->layers[layer].trainable = trainable != 0;
+  return OCF_OK;
+}
+
+extern "C" int64_t ocf_model_steps_logged(const ocf_model* m) { return m ? m->steps_logged : 0; }
+
+extern "C" int ocf_model_buffer(ocf_model* m, int which, void** ptr, int64_t* count) {
+  OCF_REQUIRE(m && ptr && count, "ocf_model_buffer: null argument");
+  switch (which) {
+    case OCF_BUF_Z: *ptr = m->zsum[0]; *count = (int64_t)m->cfg.max_rows * m->hp[0]; break;
+    case OCF_BUF_DH: *ptr = m->dh_top; *count = (int64_t)m->cfg.max_rows * m->hp[m->L - 1]; break;
+    case OCF_BUF_ROWSTATS: *ptr = m->rowstats; *count = (int64_t)m->cfg.max_rows * ROWSTAT_W; break;
+    default: return fail(OCF_ERR_INVALID, "ocf_model_buffer: unknown buffer");
+  }
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_weight_device(ocf_model* m, int index, void** ptr, int64_t* count) {
+  OCF_REQUIRE(m && ptr && count && index >= 0 && index < 2 * (m->L + 1), "ocf_model_weight_device: bad argument");
+  const Layer& ly = m->layers[index / 2];
+  if (index % 2 == 0) { *ptr = ly.W; *count = (int64_t)ly.rows * ly.hp; }
+  else { *ptr = ly.b; *count = ly.bias_len; }
+  return OCF_OK;
+}
+
+// ============================================================================================
+// step orchestration
+// ============================================================================================
+#define OCF_NV_SWITCH(hp, ...)                                   \
+  switch ((hp) / 128) {                                          \
+    case 1: { constexpr int NV = 1; __VA_ARGS__; } break;        \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; } break;        \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; } break;        \
+    case 4: { constexpr int NV = 4; __VA_ARGS__; } break;        \
+    case 5: { constexpr int NV = 5; __VA_ARGS__; } break;        \
+    case 6: { constexpr int NV = 6; __VA_ARGS__; } break;        \
+    case 7: { constexpr int NV = 7; __VA_ARGS__; } break;        \
+    default: { constexpr int NV = 8; __VA_ARGS__; } break;       \
+  }
+
+static OptDev make_opt(const ocf_model* m) {
+  OptDev o{};
+  o.kind = m->opt_kind;
+  double lr = (double)m->lr;
+  if (m->decay > 0.f) lr *= 1.0 / (1.0 + (double)m->decay * (double)m->iterations);
+  if (m->opt_kind == OCF_OPT_ADAM) {
+    const double t = (double)(m->iterations + 1);
+    lr *= std::sqrt(1.0 - std::pow((double)m->p2, t)) / (1.0 - std::pow((double)m->p1, t));
+  }
+  o.lr = (float)lr;
+  o.p1 = m->p1; o.one_m_p1 = (float)(1.0 - (double)m->p1);
+  o.p2 = m->p2; o.one_m_p2 = (float)(1.0 - (double)m->p2);
+  o.eps = m->eps;
+  o.l2x2 = m->cfg.l2 >= 0.f ? (float)(2.0 * (double)m->cfg.l2) : 0.f;
+  o.dense = (m->opt_kind == OCF_OPT_RMSPROP || m->opt_kind == OCF_OPT_ADAM || o.l2x2 != 0.f) ? 1 : 0;
+  return o;
+}
+
+static int check_step(const ocf_model* m, const ocf_batch* b, bool train) {
+  OCF_REQUIRE(m && b, "step: null argument");
+  if (b->mode == 0) return fail(OCF_ERR_STATE, "step: the batch has not been filled");
+  if (train && b->mode != 1) return fail(OCF_ERR_STATE, "train step needs a split batch (ocf_batch_fill_split)");
+  if (train && !b->store->has_csc) return fail(OCF_ERR_STATE, "train step needs a store built with build_csc");
+  OCF_REQUIRE(b->store->n_cols == m->cfg.n_cols, "step: the batch's store and the model disagree on n_cols");
+  OCF_REQUIRE(b->dev.B <= m->cfg.max_rows && b->dev.n_entries <= m->cfg.max_entries && b->dev.n_items <= m->max_items,
+              "step: the batch exceeds the model's workspace");
+  return OCF_OK;
+}
+
+// phase 1: encoder partial sums -> zsum[0]
+static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
+  const BatchDev& bt = b->dev;
+  const int hp0 = m->hp[0];
+  if (bt.n_items > 0) {
+    OCF_NV_SWITCH(hp0, k_enc_fwd<NV><<<bt.n_items, 128, 0, st>>>(bt, m->layers[0].W, m->cfg.n_cols, m->nblk, m->bits,
+                                                                b->aux_value, reinterpret_cast<float4*>(m->P1)));
+    OCF_LAUNCHED();
+  }
+  k_rowsum<<<bt.B, 128, 0, st>>>(reinterpret_cast<const float4*>(m->P1), bt.item_ptr, hp0 / 4,
+                                 reinterpret_cast<float4*>(m->zsum[0]), nullptr, nullptr);
+  OCF_LAUNCHED();
+  return OCF_OK;
+}
+
+static int launch_gemm(bool ta, bool tb, const float* A, int lda, const float* Bm, int ldb, int M, int N, int K,
+                       const GemmEpi& ep, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  if (!ta && !tb) k_sgemm<false, false><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
+  else if (ta && !tb) k_sgemm<true, false><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
+  else if (!ta && tb) k_sgemm<false, true><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
+  else k_sgemm<true, true><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
+  OCF_LAUNCHED();
+  return OCF_OK;
+}
+
+// bias + activation (+ dropout) of layer l from zsum[l]
+static int launch_act(ocf_model* m, int l, int B, bool training, const ocf_step_args* args, cudaStream_t st) {
+  const int hp = m->hp[l];
+  const bool drop = training && m->cfg.dropout_p > 0.f;
+  const int total = B * (hp / 4);
+  const uint64_t seed = args ? args->dropout_seed : 0;
+  k_bias_act<<<(total + 255) / 256, 256, 0, st>>>(
+      reinterpret_cast<const float4*>(m->zsum[l]), reinterpret_cast<const float4*>(m->layers[l].b), B,
+      m->cfg.widths[l], hp / 4, m->cfg.activation, reinterpret_cast<float4*>(m->act[l]),
+      reinterpret_cast<float4*>(drop ? m->h[l] : m->act[l]), drop ? reinterpret_cast<float4*>(m->dscale[l]) : nullptr,
+      m->cfg.dropout_p, make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)), args ? args->step : 0u,
+      (uint32_t)l, args ? args->row0 : 0);
+  OCF_LAUNCHED();
+  return OCF_OK;
+}
+
+// phase 2: activations, hidden layers, decoder at the target entries, loss partials -> dh_top, rowstats
+static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args,
+                        float* dense_out, cudaStream_t st) {
+  const BatchDev& bt = b->dev;
+  const int L = m->L, B = bt.B;
+  const bool drop = training && m->cfg.dropout_p > 0.f;
+  OCF_TRY(launch_act(m, 0, B, training, args, st));
+  for (int l = 1; l < L; ++l) {
+    GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];
+    const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
+    OCF_TRY(launch_gemm(false, false, hin, m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
+    OCF_TRY(launch_act(m, l, B, training, args, st));
+  }
+  const float* htop = drop ? m->h[L - 1] : m->act[L - 1];
+  const int hpt = m->hp[L - 1];
+  const int rows_total = (args && args->rows_total > 0) ? args->rows_total : B;
+  const double bn = (double)rows_total * (double)m->cfg.n_cols_total;
+  const float gscale = (float)((m->cfg.loss == OCF_LOSS_MSE ? 2.0 : 1.0) / bn);
+  if (bt.n_items > 0) {
+    if (training) {
+      OCF_NV_SWITCH(hpt, k_dec_fwd<NV, true><<<bt.n_items, 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, b->aux_value, gscale,
+                                                                          m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2), m->itemstats, dense_out, m->cfg.n_cols));
+    } else {
+      OCF_NV_SWITCH(hpt, k_dec_fwd<NV, false><<<bt.n_items, 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, b->aux_value, gscale,
+                                                                           m->cfg.loss, nullptr, nullptr, m->itemstats, dense_out, m->cfg.n_cols));
+    }
+    OCF_LAUNCHED();
+  }
+  if (training) {
+    k_rowsum<<<B, 128, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, hpt / 4,
+                                reinterpret_cast<float4*>(m->dh_top), m->itemstats, m->rowstats);
+  } else {
+    k_rowsum<<<B, 128, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, 0, nullptr, m->itemstats, m->rowstats);
+  }
+  OCF_LAUNCHED();
+  return OCF_OK;
+}
+
+static int launch_metrics(ocf_model* m, int B, const ocf_step_args* args, int n_reg, cudaStream_t st) {
+  const int rows_total = (args && args->rows_total > 0) ? args->rows_total : B;
+  float* rec = m->d_log + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
+  k_metrics<<<1, 32, 0, st>>>(m->rowstats, B, (float)rows_total, (float)m->cfg.n_cols_total, m->cfg.rating_range,
+                              m->cfg.loss, m->regparts, n_reg, m->cfg.l2 >= 0.f ? m->cfg.l2 : 0.f, rec);
+  OCF_LAUNCHED();
+  m->steps_logged += 1;
+  return OCF_OK;
+}
+
+static int launch_reg(ocf_model* m, cudaStream_t st) {
+  if (m->cfg.l2 < 0.f) return 0;
+  for (int l = 0; l <= m->L; ++l) {
+    const Layer& ly = m->layers[l];
+    k_sumsq<<<N_REGPART, 256, 0, st>>>(ly.W, (size_t)ly.rows * ly.hp, m->regparts + (size_t)l * N_REGPART);
+    g_launches.fetch_add(1);
+  }
+  return N_REGPART * (m->L + 1);
+}
+
+// phase 3 (training): backward through the hidden layers, fused updates, metrics
+static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* args, cudaStream_t st) {
+  const BatchDev& bt = b->dev;
+  const int L = m->L, B = bt.B;
+  const bool drop = m->cfg.dropout_p > 0.f;
+  const OptDev opt = make_opt(m);
+  const int n_reg = launch_reg(m, st);          // L2 term of the reported loss uses pre-update weights
+  // top hidden layer: dz and its bias
+  {
+    const int l = L - 1;
+    Layer& ly = m->layers[l];
+    k_dz_bias<<<(m->hp[l] + 127) / 128, 128, 0, st>>>(m->dh_top, m->act[l], drop ? m->dscale[l] : nullptr, B, m->hp[l],
+                                                     m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt, ly.trainable ? 1 : 0);
+    OCF_LAUNCHED();
+  }
+  for (int l = L - 1; l >= 1; --l) {
+    Layer& ly = m->layers[l];
+    // dz_{l-1} = (dz_l . W_l^T) * dropout scale * act'(a_{l-1})   (uses W_l before its update)
+    GemmEpi ep{}; ep.kind = EPI_DZ; ep.C = m->dz[l - 1]; ep.ldc = m->hp[l - 1]; ep.aux0 = m->act[l - 1];
+    ep.aux1 = drop ? m->dscale[l - 1] : nullptr; ep.act = m->cfg.activation;
+    OCF_TRY(launch_gemm(false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
+    Layer& lo = m->layers[l - 1];
+    k_dz_bias<<<(m->hp[l - 1] + 127) / 128, 128, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
+                                                         m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0);
+    OCF_LAUNCHED();
+    if (ly.trainable) {
+      // dW_l = h_{l-1}^T . dz_l, fused with the update of W_l
+      GemmEpi eu{}; eu.kind = EPI_UPDATE; eu.C = ly.W; eu.ldc = m->hp[l]; eu.s1 = ly.Ws1; eu.s2 = ly.Ws2; eu.opt = opt;
+      const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
+      OCF_TRY(launch_gemm(true, false, hin, m->hp[l - 1], m->dz[l], m->hp[l], m->hp[l - 1], m->hp[l], B, eu, st));
+    }
+  }
+  // catalogue-wide kernels: encoder rows and decoder rows of every touched column
+  Layer& enc = m->layers[0];
+  Layer& dec = m->layers[L];
+  if ((enc.trainable || dec.trainable) && (bt.n_entries > 0 || opt.dense)) {
+    ColArgs a{};
+    a.s = b->store->dev; a.bt = bt; a.dy = m->dy;
+    a.hdec = drop ? m->h[L - 1] : m->act[L - 1]; a.dz0 = m->dz[0];
+    a.WdecT = dec.W; a.Wd_s1 = dec.Ws1; a.Wd_s2 = dec.Ws2; a.bdec = dec.b; a.bd_s1 = dec.bs1; a.bd_s2 = dec.bs2;
+    a.Wenc = enc.W; a.We_s1 = enc.Ws1; a.We_s2 = enc.Ws2;
+    a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.aux_val = b->aux_value; a.opt = opt;
+    a.err_flag = m->d_err;
+    a.list_cap = 2 * (int)align_up((size_t)B, 32) + 32;
+    int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (96 * 1024) / ((size_t)a.list_cap * 12)));
+    const size_t smem = (size_t)warps * a.list_cap * 12;
+    const int grid = (m->cfg.n_cols + warps - 1) / warps;
+    auto launch = [&](int hpx, int do_dec, int do_enc) -> int {
+      a.do_dec = do_dec; a.do_enc = do_enc;
+      OCF_NV_SWITCH(hpx, {
+        if (smem > 48 * 1024) OCF_CUDA(cudaFuncSetAttribute(k_col_update<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_col_update<NV><<<grid, warps * 32, smem, st>>>(a);
+      });
+      OCF_LAUNCHED();
+      return OCF_OK;
+    };
+    const int hpd = m->hp[L - 1], hpe = m->hp[0];
+    if (hpd == hpe) OCF_TRY(launch(hpd, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0));
+    else {
+      if (dec.trainable) OCF_TRY(launch(hpd, 1, 0));
+      if (enc.trainable) OCF_TRY(launch(hpe, 0, 1));
+    }
+  }
+  m->iterations += 1;
+  return launch_metrics(m, B, args, n_reg, st);
+}
+
+static int finish_step(ocf_model* m, float* host_metrics, cudaStream_t st) {
+  if (host_metrics == nullptr) return OCF_OK;
+  const float* rec = m->d_log + (size_t)((m->steps_logged - 1) % LOG_CAP) * LOG_W;
+  OCF_CUDA(cudaMemcpyAsync(m->h_rec, rec, sizeof(float) * LOG_W, cudaMemcpyDeviceToHost, st));
+  OCF_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(host_metrics, m->h_rec, sizeof(float) * LOG_W);
+  return OCF_OK;
+}
+
+extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
+  OCF_TRY(check_step(m, b, true));
+  cudaStream_t st = as_stream(stream_);
+  const int phase = args ? args->phase : 0;
+  OCF_REQUIRE(phase >= 0 && phase <= 3, "ocf_train_step: phase must be 0..3");
+  if (phase == 0 || phase == 1) OCF_TRY(phase_encode(m, b, st));
+  if (phase == 0 || phase == 2) OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
+  if (phase == 0 || phase == 3) { OCF_TRY(phase_update(m, b, args, st)); OCF_TRY(finish_step(m, host_metrics, st)); }
+  return OCF_OK;
+}
+
+extern "C" int ocf_eval_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
+  OCF_TRY(check_step(m, b, false));
+  cudaStream_t st = as_stream(stream_);
+  const int phase = args ? args->phase : 0;
+  OCF_REQUIRE(phase >= 0 && phase <= 3, "ocf_eval_step: phase must be 0..3");
+  if (phase == 0 || phase == 1) OCF_TRY(phase_encode(m, b, st));
+  if (phase == 0 || phase == 2) OCF_TRY(phase_decode(m, b, false, args, nullptr, st));
+  if (phase == 0 || phase == 3) {
+    const int n_reg = launch_reg(m, st);
+    OCF_TRY(launch_metrics(m, b->dev.B, args, n_reg, st));
+    OCF_TRY(finish_step(m, host_metrics, st));
+  }
+  return OCF_OK;
+}
+
+static int ensure_dense(ocf_model* m) {
+  if (m->dense_out) return OCF_OK;
+  return m->dense_mem.get(&m->dense_out, (size_t)m->cfg.max_rows * m->cfg.n_cols);
+}
+
+extern "C" int ocf_predict(ocf_model* m, ocf_batch* b, float* out, void* stream_) {
+  OCF_TRY(check_step(m, b, false));
+  OCF_REQUIRE(out != nullptr, "ocf_predict: null output");
+  cudaStream_t st = as_stream(stream_);
+  OCF_TRY(ensure_dense(m));
+  const size_t count = (size_t)b->dev.B * m->cfg.n_cols;
+  OCF_CUDA(cudaMemsetAsync(m->dense_out, 0, sizeof(float) * count, st));
+  OCF_TRY(phase_encode(m, b, st));
+  OCF_TRY(phase_decode(m, b, false, nullptr, m->dense_out, st));
+  OCF_CUDA(cudaMemcpyAsync(out, m->dense_out, sizeof(float) * count, cudaMemcpyDeviceToHost, st));
+  OCF_CUDA(cudaStreamSynchronize(st));
+  return OCF_OK;
+}
+
+extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_device, void* stream_) {
+  OCF_TRY(check_step(m, b, false));
+  OCF_REQUIRE(out != nullptr, "ocf_score: null output");
+  cudaStream_t st = as_stream(stream_);
+  const int L = m->L, B = b->dev.B;
+  OCF_TRY(phase_encode(m, b, st));
+  OCF_TRY(launch_act(m, 0, B, false, nullptr, st));
+  for (int l = 1; l < L; ++l) {
+    GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];
+    OCF_TRY(launch_gemm(false, false, m->act[l - 1], m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
+    OCF_TRY(launch_act(m, l, B, false, nullptr, st));
+  }
+  float* dst = out;
+  if (!out_is_device) { OCF_TRY(ensure_dense(m)); dst = m->dense_out; }
+  GemmEpi ep{}; ep.kind = EPI_BIAS_COL; ep.C = dst; ep.ldc = m->cfg.n_cols; ep.aux0 = m->layers[L].b;
+  OCF_TRY(launch_gemm(false, true, m->act[L - 1], m->hp[L - 1], m->layers[L].W, m->hp[L - 1], B, m->cfg.n_cols, m->hp[L - 1], ep, st));
+  if (!out_is_device) {
+    OCF_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * (size_t)B * m->cfg.n_cols, cudaMemcpyDeviceToHost, st));
+    OCF_CUDA(cudaStreamSynchronize(st));
+  }
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_read_metrics(ocf_model* m, int64_t first, int32_t count, float* host, void* stream_) {
+  OCF_REQUIRE(m && host, "ocf_model_read_metrics: null argument");
+  OCF_REQUIRE(count >= 0 && count <= LOG_CAP && first >= 0 && first + count <= m->steps_logged &&
+              first + LOG_CAP >= m->steps_logged, "ocf_model_read_metrics: range not in the log");
+  cudaStream_t st = as_stream(stream_);
+  for (int32_t k = 0; k < count; ++k) {
+    const float* rec = m->d_log + (size_t)((first + k) % LOG_CAP) * LOG_W;
+    OCF_CUDA(cudaMemcpyAsync(m->h_rec + (size_t)k * LOG_W, rec, sizeof(float) * LOG_W, cudaMemcpyDeviceToHost, st));
+  }
+  int err = 0;
+  OCF_CUDA(cudaMemcpyAsync(&err, m->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  OCF_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(host, m->h_rec, sizeof(float) * (size_t)count * LOG_W);
+  if (err != 0) return fail(OCF_ERR_STATE, "a catalogue column matched more batch entries than the update kernel's list holds (rows repeat a column too often)");
+  return OCF_OK;
+}

@@ -1,0 +1,608 @@
+// Hand-written sm_100a kernels of the training / scoring hot path.
+//
+// Data layout in HBM:
+//   * rating store: CSR (rowptr i64, col i32, val f32) + CSC index (colptr i64, crow i32, cj i32)
+//   * encoder kernel  Wenc  [k*N, HP]  (Keras layout, fan_out padded to a multiple of 128)
+//   * decoder kernel  WdecT [N, HP]    (TRANSPOSED Keras layout: one contiguous row per
+//     catalogue column, so the loss at an observed entry is one coalesced 4*HP-byte read)
+//   * activations [B, HP] fp32
+// Every catalogue-wide operation is therefore a gather of 4*HP-byte rows: row-centric kernels
+// (one work item = a chunk of one batch row's ratings) for the activation-side products,
+// a column-centric kernel (one warp per catalogue column) for the weight-side products fused
+// with the optimizer update. All reductions run in a fixed order (no float atomics).
+#pragma once
+
+#include "ocf_common.cuh"
+
+namespace ocf {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ============================================================================================
+// K1: CSR gather. Turns (row ids, keep flags) into the batch's rating tiles: column, value and
+// a code byte saying which of the reference's dense arrays the rating is the live writer of.
+// Replaces the per-rating Python loop of data_reader.py:122-170 / :226-268.
+// One CTA per work item (a chunk of <= CH ratings of one row); reads and writes are contiguous.
+// ============================================================================================
+__global__ void __launch_bounds__(128)
+k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
+  const int4 it = bt.items[blockIdx.x];
+  const int b = it.x, start = it.y, len = it.z;
+  const int row = bt.row_ids[b];
+  const int64_t src0 = s.rowptr[row];
+  const int p0 = bt.ent_off[b];
+  if (start == 0 && threadIdx.x == 0) bt.rowslot[row] = (bt.tag << SLOT_BITS) | (uint32_t)b;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const int j = start + i;
+    const int64_t src = src0 + j;
+    const int p = p0 + j;
+    const uint8_t f = bt.flags[p];
+    bool in_live = f != 0;
+    bool tg_live = (f == 0) || pass_through;
+    bool obs_live = true;
+    if (s.next_dup != nullptr) {
+      int k = s.next_dup[src];
+      while (k >= 0) {               // later ratings of the same column overwrite this one
+        obs_live = false;
+        const uint8_t fk = bt.flags[p0 + k];
+        if (fk != 0) in_live = false;
+        if (fk == 0 || pass_through) tg_live = false;
+        k = s.next_dup[src0 + k];
+      }
+    }
+    bt.ent_col[p] = s.col[src];
+    bt.ent_val[p] = s.val[src];
+    bt.codes[p] = (uint8_t)((in_live ? CODE_IN : 0) | (obs_live ? CODE_OBS : 0) | (tg_live ? CODE_TGT : 0));
+  }
+}
+
+// Fixed-split valid/test batches: a batch row is the input store's row followed by the target
+// store's row. in_overlap[e] != 0 marks input ratings whose column is also a target of the row
+// (the missing-data mask is then carried by the target entry only).
+__global__ void __launch_bounds__(128)
+k_gather_fixed(StoreDev sin, StoreDev stg, const uint8_t* __restrict__ in_overlap, BatchDev bt) {
+  const int4 it = bt.items[blockIdx.x];
+  const int b = it.x, start = it.y, len = it.z;
+  const int row = bt.row_ids[b];
+  const int nin = bt.in_len[b];
+  const int64_t in0 = sin.rowptr[row], tg0 = stg.rowptr[row];
+  const int p0 = bt.ent_off[b];
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const int j = start + i;
+    const int p = p0 + j;
+    int c; float v; uint8_t code;
+    if (j < nin) {
+      const int64_t src = in0 + j;
+      c = sin.col[src]; v = sin.val[src];
+      const bool live = sin.next_dup == nullptr || sin.next_dup[src] < 0;
+      const bool also_target = in_overlap != nullptr && in_overlap[src] != 0;
+      code = live ? (uint8_t)(CODE_IN | (also_target ? 0 : CODE_OBS)) : 0;
+    } else {
+      const int64_t src = tg0 + (j - nin);
+      c = stg.col[src]; v = stg.val[src];
+      const bool live = stg.next_dup == nullptr || stg.next_dup[src] < 0;
+      code = live ? (uint8_t)(CODE_TGT | CODE_OBS) : 0;
+    }
+    bt.ent_col[p] = c; bt.ent_val[p] = v; bt.codes[p] = code;
+  }
+}
+
+// The scatter half of K1: the dense float64 [B, N] arrays of data_reader.py:191-200, for parity
+// tests and callers that want Keras-style feeds. `out` must be zeroed.
+__global__ void k_densify(BatchDev bt, int which, double aux_val, int n_cols, double* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= bt.n_entries) return;
+  // batch row of entry p: binary search in ent_off
+  int lo = 0, hi = bt.B;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (bt.ent_off[mid] <= p) lo = mid; else hi = mid; }
+  const uint8_t code = bt.codes[p];
+  const double v = (double)bt.ent_val[p];
+  double w; bool on;
+  switch (which) {
+    case 0: on = code & CODE_IN; w = v; break;
+    case 1: on = code & CODE_IN; w = aux_val; break;
+    case 2: on = code & CODE_TGT; w = aux_val; break;
+    case 3: on = code & CODE_TGT; w = v; break;
+    default: on = code & CODE_OBS; w = aux_val; break;
+  }
+  if (on) out[(size_t)lo * n_cols + bt.ent_col[p]] = w;
+}
+
+// ============================================================================================
+// K2: encoder, sparse-row x dense Wenc (SpMM). Work item = chunk of one batch row; the 4 warps of
+// the CTA split the chunk's ratings, each warp accumulates full HP-wide rows (NV float4 per
+// lane, 512-byte coalesced segments), then the warps are summed in a fixed order.
+// x0 = [data | aux | second] (model.py:47-56) is never formed: block k of the concatenation is
+// rows [k*N, (k+1)*N) of Wenc, selected by the entry's code bits.
+// ============================================================================================
+template <int NV>
+__global__ void __launch_bounds__(128)
+k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int3 bits,
+          float aux_val, float4* __restrict__ P) {
+  constexpr int HP = NV * 128;
+  __shared__ float4 red[4][HP / 4];
+  const int4 it = bt.items[blockIdx.x];
+  const int len = it.z;
+  const int p0 = bt.ent_off[it.x] + it.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int base = warp * 32; base < len; base += 128) {
+    const int i = base + lane;
+    int c = 0, code = 0; float val = 0.f;
+    if (i < len) { c = bt.ent_col[p0 + i]; val = bt.ent_val[p0 + i]; code = bt.codes[p0 + i]; }
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int bit = blk == 0 ? bits.x : (blk == 1 ? bits.y : bits.z);
+      const float coef = blk == 0 ? val : aux_val;
+      unsigned m = __ballot_sync(FULL, (code & bit) != 0);
+      const float* Wb = Wenc + (size_t)blk * n_cols * HP + lane * 4;
+      while (m) {
+        const int j0 = __ffs(m) - 1; m &= m - 1;
+        const bool two = m != 0;
+        const int j1 = two ? __ffs(m) - 1 : j0; m &= m - 1;
+        const int c0 = __shfl_sync(FULL, c, j0), c1 = __shfl_sync(FULL, c, j1);
+        const float f0 = __shfl_sync(FULL, coef, j0);
+        const float f1 = two ? __shfl_sync(FULL, coef, j1) : 0.f;
+        const float* r0 = Wb + (size_t)c0 * HP;
+        const float* r1 = Wb + (size_t)c1 * HP;
+        float4 w0[NV], w1[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { w0[v] = ldg4(r0 + v * 128); w1[v] = ldg4(r1 + v * 128); }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { fma4(acc[v], f0, w0[v]); fma4(acc[v], f1, w1[v]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) red[warp][v * 32 + lane] = acc[v];
+  __syncthreads();
+  for (int u = threadIdx.x; u < HP / 4; u += 128) {
+    float4 s = red[0][u];
+    const float4 a = red[1][u], b2 = red[2][u], c2 = red[3][u];
+    s.x = ((s.x + a.x) + b2.x) + c2.x; s.y = ((s.y + a.y) + b2.y) + c2.y;
+    s.z = ((s.z + a.z) + b2.z) + c2.z; s.w = ((s.w + a.w) + b2.w) + c2.w;
+    P[(size_t)blockIdx.x * (HP / 4) + u] = s;
+  }
+}
+
+// Sum of the work-item partials of each batch row, in item order. Also sums the per-item loss
+// statistics into per-row statistics when given.
+__global__ void __launch_bounds__(128)
+k_rowsum(const float4* __restrict__ P, const int32_t* __restrict__ item_ptr, int hp4,
+         float4* __restrict__ out, const float* __restrict__ itemstats, float* __restrict__ rowstats) {
+  const int b = blockIdx.x;
+  const int i0 = item_ptr[b], i1 = item_ptr[b + 1];
+  for (int u = threadIdx.x; u < hp4; u += blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = i0; it < i1; ++it) {
+      const float4 p = P[(size_t)it * hp4 + u];
+      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    out[(size_t)b * hp4 + u] = s;
+  }
+  if (itemstats != nullptr && threadIdx.x < ROWSTAT_W) {
+    float s = 0.f;
+    for (int it = i0; it < i1; ++it) s += itemstats[(size_t)it * ROWSTAT_W + threadIdx.x];
+    rowstats[(size_t)b * ROWSTAT_W + threadIdx.x] = s;
+  }
+}
+
+// z + bias -> activation -> inverted dropout (model.py:66-73). Padded units are forced to 0.
+// a_out: activation before dropout (needed for the derivative), h_out: what the next layer sees,
+// dscale: 0 or 1/(1-p) per element (null when dropout is off).
+__global__ void __launch_bounds__(256)
+k_bias_act(const float4* __restrict__ zsum, const float4* __restrict__ bias, int B, int H, int hp4,
+           int act, float4* __restrict__ a_out, float4* __restrict__ h_out, float4* __restrict__ dscale,
+           float p_drop, uint2 key, uint32_t step, uint32_t layer, int row0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * hp4) return;
+  const int b = idx / hp4, u4 = idx - b * hp4;
+  const float4 z = zsum[idx], bb = bias[u4];
+  float a[4] = {z.x + bb.x, z.y + bb.y, z.z + bb.z, z.w + bb.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = (u4 * 4 + k < H) ? act_fwd(act, a[k]) : 0.f;
+  a_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
+  if (dscale != nullptr) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)u4, (uint32_t)(b + row0), layer, step), key);
+    const uint32_t thresh = (uint32_t)floor((double)p_drop * 16777216.0);
+    const float inv = 1.0f / (1.0f - p_drop);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    float sc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sc[k] = ((rr[k] >> 8) >= thresh) ? inv : 0.f; a[k] *= sc[k]; }
+    dscale[idx] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+  }
+  h_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+// ============================================================================================
+// K3: decoder at the observed target entries (SDDMM) fused with bias, output mask, masked
+// loss, metrics and the loss gradient; accumulates dL/dh on the fly. The dense [B, N]
+// reconstruction (model.py:82-86) is never formed.
+//   full = h . WdecT[c] + b[c];  y = m * full (m = aux_var_value);  e = y - t
+//   dL/dfull = m * 2e/(B N)   (mean_squared_error)   or   m * sign(e)/(B N)   (mean_absolute_error)
+// ============================================================================================
+template <int NV, bool TRAIN>
+__global__ void __launch_bounds__(128)
+k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict__ bdec,
+          const float* __restrict__ h, float aux_val, float gscale, int loss_kind,
+          float* __restrict__ dy, float4* __restrict__ P2, float* __restrict__ itemstats,
+          float* __restrict__ dense_out, int n_cols) {
+  constexpr int HP = NV * 128;
+  __shared__ float4 red[TRAIN ? 4 : 1][HP / 4];
+  __shared__ float sred[4][3];
+  const int4 it = bt.items[blockIdx.x];
+  const int b = it.x, len = it.z;
+  const int p0 = bt.ent_off[b] + it.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 hreg[NV], dh[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    hreg[v] = ldg4(h + (size_t)b * HP + v * 128 + lane * 4);
+    dh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float sse = 0.f, sae = 0.f, cnt = 0.f;
+
+  for (int base = warp * 32; base < len; base += 128) {
+    const int i = base + lane;
+    int c = 0, code = 0; float t = 0.f;
+    if (i < len) { c = bt.ent_col[p0 + i]; t = bt.ent_val[p0 + i]; code = bt.codes[p0 + i]; }
+    unsigned m = __ballot_sync(FULL, (code & CODE_TGT) != 0);
+    if (TRAIN && i < len && !(code & CODE_TGT)) dy[p0 + i] = 0.f;
+    while (m) {
+      const int j0 = __ffs(m) - 1; m &= m - 1;
+      const bool two = m != 0;
+      const int j1 = two ? __ffs(m) - 1 : j0; m &= m - 1;
+      const int c0 = __shfl_sync(FULL, c, j0), c1 = __shfl_sync(FULL, c, j1);
+      const float t0 = __shfl_sync(FULL, t, j0), t1 = __shfl_sync(FULL, t, j1);
+      const float* r0 = WdecT + (size_t)c0 * HP + lane * 4;
+      const float* r1 = WdecT + (size_t)c1 * HP + lane * 4;
+      float4 w0[NV], w1[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { w0[v] = ldg4(r0 + v * 128); w1[v] = ldg4(r1 + v * 128); }
+      const float bias0 = __ldg(bdec + c0), bias1 = __ldg(bdec + c1);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { d0 = dot4(w0[v], hreg[v], d0); d1 = dot4(w1[v], hreg[v], d1); }
+      d0 = warp_sum(d0); d1 = warp_sum(d1);
+      {
+        const float y = aux_val * (d0 + bias0), e = y - t0;
+        sse = fmaf(e, e, sse); sae += fabsf(e); cnt += ((t0 + y) != 0.f) ? 1.f : 0.f;
+        if (dense_out != nullptr && lane == 0) dense_out[(size_t)b * n_cols + c0] = y;
+        if (TRAIN) {
+          const float ge = loss_kind == OCF_LOSS_MSE ? gscale * e : gscale * (float)((e > 0.f) - (e < 0.f));
+          const float dyv = aux_val * ge;
+          if (lane == 0) dy[p0 + base + j0] = dyv;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) fma4(dh[v], dyv, w0[v]);
+        }
+      }
+      if (two) {
+        const float y = aux_val * (d1 + bias1), e = y - t1;
+        sse = fmaf(e, e, sse); sae += fabsf(e); cnt += ((t1 + y) != 0.f) ? 1.f : 0.f;
+        if (dense_out != nullptr && lane == 0) dense_out[(size_t)b * n_cols + c1] = y;
+        if (TRAIN) {
+          const float ge = loss_kind == OCF_LOSS_MSE ? gscale * e : gscale * (float)((e > 0.f) - (e < 0.f));
+          const float dyv = aux_val * ge;
+          if (lane == 0) dy[p0 + base + j1] = dyv;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) fma4(dh[v], dyv, w1[v]);
+        }
+      }
+    }
+  }
+  if (lane == 0) { sred[warp][0] = sse; sred[warp][1] = sae; sred[warp][2] = cnt; }
+  if (TRAIN) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) red[warp][v * 32 + lane] = dh[v];
+  }
+  __syncthreads();
+  if (TRAIN) {
+    for (int u = threadIdx.x; u < HP / 4; u += 128) {
+      float4 s = red[0][u];
+      const float4 a = red[1][u], b2 = red[2][u], c2 = red[3][u];
+      s.x = ((s.x + a.x) + b2.x) + c2.x; s.y = ((s.y + a.y) + b2.y) + c2.y;
+      s.z = ((s.z + a.z) + b2.z) + c2.z; s.w = ((s.w + a.w) + b2.w) + c2.w;
+      P2[(size_t)blockIdx.x * (HP / 4) + u] = s;
+    }
+  }
+  if (threadIdx.x < 3)
+    itemstats[(size_t)blockIdx.x * ROWSTAT_W + threadIdx.x] =
+        ((sred[0][threadIdx.x] + sred[1][threadIdx.x]) + sred[2][threadIdx.x]) + sred[3][threadIdx.x];
+  if (threadIdx.x == 3) itemstats[(size_t)blockIdx.x * ROWSTAT_W + 3] = 0.f;
+}
+
+// dz = dh * dropout scale * act'(a) for one hidden layer, the bias gradient (column sum over the
+// batch in row order) and the bias update. One thread per hidden unit.
+// dh_is_dz: the input already is dz (produced by the EPI_DZ GEMM epilogue).
+__global__ void __launch_bounds__(128)
+k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float* __restrict__ dscale,
+          int B, int HP, int act, int dh_is_dz, float* __restrict__ dz, float* __restrict__ bias,
+          float* __restrict__ s1, float* __restrict__ s2, OptDev o, int trainable) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= HP) return;
+  float g = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const size_t k = (size_t)b * HP + u;
+    float d = dh[k];
+    if (!dh_is_dz) {
+      if (dscale != nullptr) d *= dscale[k];
+      d *= act_bwd(act, a[k]);
+      dz[k] = d;
+    }
+    g += d;
+  }
+  if (trainable) {
+    o.l2x2 = 0.f;                     // Keras regularises kernels only (model.py:66,82)
+    float w = bias[u], t1 = s1 ? s1[u] : 0.f, t2 = s2 ? s2[u] : 0.f;
+    opt_apply(o, g, w, t1, t2);
+    bias[u] = w;
+    if (s1) s1[u] = t1;
+    if (s2) s2[u] = t2;
+  }
+}
+
+// ============================================================================================
+// Dense GEMM for the hidden HxH layers and the SIMT scoring path (fp32, 64x64x16 tiles).
+//   C[M,N] = A'[M,K] * B'[K,N],  A'(m,k) = TA ? A[k*lda+m] : A[m*lda+k],
+//                                B'(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
+// ============================================================================================
+enum { EPI_STORE = 0, EPI_DZ = 1, EPI_UPDATE = 2, EPI_BIAS_COL = 3 };
+
+struct GemmEpi {
+  int kind;
+  float* C; int ldc;
+  const float* aux0;   // EPI_DZ: activation a [M, ldc];   EPI_BIAS_COL: bias [N]
+  const float* aux1;   // EPI_DZ: dropout scale or null
+  float* s1; float* s2;  // EPI_UPDATE: optimizer state, same layout as C (C = the weight)
+  int act;
+  OptDev opt;
+};
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+        int M, int N, int K, GemmEpi ep) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + r * 256;
+      int kk, mm;
+      if (TA) { mm = e & 63; kk = e >> 6; } else { kk = e & 15; mm = e >> 4; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float va = 0.f;
+      if (gm < M && gk < K) va = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      As[kk][mm] = va;
+      int kb, nn;
+      if (TB) { kb = e & 15; nn = e >> 4; } else { nn = e & 63; kb = e >> 6; }
+      const int gn = n0 + nn, gkb = k0 + kb;
+      float vb = 0.f;
+      if (gn < N && gkb < K) vb = TB ? Bm[(size_t)gn * ldb + gkb] : Bm[(size_t)gkb * ldb + gn];
+      Bs[kb][nn] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      const size_t k = (size_t)gm * ep.ldc + gn;
+      float v = acc[i][j];
+      switch (ep.kind) {
+        case EPI_STORE: ep.C[k] = v; break;
+        case EPI_DZ:
+          if (ep.aux1 != nullptr) v *= ep.aux1[k];
+          ep.C[k] = v * act_bwd(ep.act, ep.aux0[k]);
+          break;
+        case EPI_UPDATE: {
+          float w = ep.C[k], t1 = ep.s1 ? ep.s1[k] : 0.f, t2 = ep.s2 ? ep.s2[k] : 0.f;
+          opt_apply(ep.opt, v, w, t1, t2);
+          ep.C[k] = w;
+          if (ep.s1) ep.s1[k] = t1;
+          if (ep.s2) ep.s2[k] = t2;
+        } break;
+        default: ep.C[k] = v + ep.aux0[gn]; break;
+      }
+    }
+  }
+}
+
+// ============================================================================================
+// K4: weight-side products fused with the optimizer update. One warp per catalogue column c:
+//   1. scan the store's CSC list of c, keep the entries whose row is in this batch
+//      (rowslot lookup) -> per-warp list in shared memory, in CSC order (deterministic)
+//   2. decoder row:   g = sum_b dy[b,c] * h[b,:]       -> update WdecT[c,:], b_dec[c]
+//   3. encoder rows:  g = sum_b x0[b, blk*N+c] * dz[b,:] -> update Wenc[blk*N+c,:] per block
+// The gradient lives in registers only; W and its optimizer state are read once and written
+// once, and only for columns the batch touches unless the rule is dense (RMSprop/Adam/L2).
+// ============================================================================================
+struct ColArgs {
+  StoreDev s; BatchDev bt;
+  const float* dy; const float* hdec; const float* dz0;
+  float* WdecT; float* Wd_s1; float* Wd_s2;
+  float* bdec; float* bd_s1; float* bd_s2;
+  float* Wenc; float* We_s1; float* We_s2;
+  int n_cols; int nblk; int3 bits; float aux_val;
+  OptDev opt; int do_dec; int do_enc;
+  int list_cap; int* err_flag;
+};
+
+template <int NV>
+__device__ __forceinline__ void col_pass(const uint32_t* lb, int n, int sel_bit, int use, float aux_val,
+                                         const float* __restrict__ X, float* __restrict__ Wrow,
+                                         float* __restrict__ S1row, float* __restrict__ S2row,
+                                         const OptDev& o, int lane, float& coef_sum) {
+  constexpr int HP = NV * 128;
+  float4 g[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool touched = false;
+  float cs = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t bc = lb[i * 3];
+    if (!((bc >> 16) & sel_bit)) continue;
+    const float coef = use == 0 ? __uint_as_float(lb[i * 3 + 1]) : (use == 2 ? __uint_as_float(lb[i * 3 + 2]) : aux_val);
+    const float* x = X + (size_t)(bc & 0xffffu) * HP + lane * 4;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) fma4(g[v], coef, ldg4(x + v * 128));
+    cs += coef;
+    touched = true;
+  }
+  coef_sum = cs;
+  if (!touched && !o.dense) return;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int off = v * 128 + lane * 4;
+    float4 w = *reinterpret_cast<float4*>(Wrow + off);
+    float4 t1 = S1row ? *reinterpret_cast<float4*>(S1row + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 t2 = S2row ? *reinterpret_cast<float4*>(S2row + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    opt_apply(o, g[v].x, w.x, t1.x, t2.x);
+    opt_apply(o, g[v].y, w.y, t1.y, t2.y);
+    opt_apply(o, g[v].z, w.z, t1.z, t2.z);
+    opt_apply(o, g[v].w, w.w, t1.w, t2.w);
+    *reinterpret_cast<float4*>(Wrow + off) = w;
+    if (S1row) *reinterpret_cast<float4*>(S1row + off) = t1;
+    if (S2row) *reinterpret_cast<float4*>(S2row + off) = t2;
+  }
+}
+
+template <int NV>
+__global__ void k_col_update(ColArgs a) {
+  constexpr int HP = NV * 128;
+  extern __shared__ uint32_t col_smem[];
+  const int warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * warps + warp;
+  if (c >= a.n_cols) return;
+  uint32_t* lb = col_smem + (size_t)warp * a.list_cap * 3;
+  const int64_t e0 = a.s.colptr[c], e1 = a.s.colptr[c + 1];
+  const unsigned lt = (1u << lane) - 1u;
+  int n = 0;
+  for (int64_t eb = e0; eb < e1; eb += 32) {
+    const int64_t e = eb + lane;
+    bool match = false;
+    uint32_t code = 0, b = 0; float v = 0.f, d = 0.f;
+    if (e < e1) {
+      const uint32_t slot = a.bt.rowslot[a.s.crow[e]];
+      if ((slot >> SLOT_BITS) == a.bt.tag) {
+        b = slot & (uint32_t)(MAX_BATCH_ROWS - 1);
+        const int p = a.bt.ent_off[b] + a.s.cj[e];
+        code = a.bt.codes[p];
+        v = a.bt.ent_val[p];
+        d = a.dy[p];
+        match = code != 0;
+      }
+    }
+    const unsigned m = __ballot_sync(FULL, match);
+    if (m) {
+      const int cntm = __popc(m);
+      if (n + cntm > a.list_cap) { if (lane == 0) atomicExch(a.err_flag, 1); break; }
+      if (match) {
+        const int pos = n + __popc(m & lt);
+        lb[pos * 3] = b | (code << 16);
+        lb[pos * 3 + 1] = __float_as_uint(v);
+        lb[pos * 3 + 2] = __float_as_uint(d);
+      }
+      n += cntm;
+    }
+  }
+  __syncwarp();
+  if (n == 0 && !a.opt.dense) return;
+  float cs;
+  if (a.do_dec) {
+    col_pass<NV>(lb, n, CODE_TGT, 2, a.aux_val, a.hdec, a.WdecT + (size_t)c * HP,
+                 a.Wd_s1 ? a.Wd_s1 + (size_t)c * HP : nullptr, a.Wd_s2 ? a.Wd_s2 + (size_t)c * HP : nullptr,
+                 a.opt, lane, cs);
+    if (lane == 0) {                    // decoder bias: column-local gradient sum_b dy[b,c]
+      OptDev ob = a.opt; ob.l2x2 = 0.f;
+      float w = a.bdec[c], t1 = a.bd_s1 ? a.bd_s1[c] : 0.f, t2 = a.bd_s2 ? a.bd_s2[c] : 0.f;
+      opt_apply(ob, cs, w, t1, t2);
+      a.bdec[c] = w;
+      if (a.bd_s1) a.bd_s1[c] = t1;
+      if (a.bd_s2) a.bd_s2[c] = t2;
+    }
+  }
+  if (a.do_enc) {
+    for (int blk = 0; blk < a.nblk; ++blk) {
+      const int bit = blk == 0 ? a.bits.x : (blk == 1 ? a.bits.y : a.bits.z);
+      const size_t r = ((size_t)blk * a.n_cols + c) * HP;
+      if (bit == 0 && !a.opt.dense) continue;
+      col_pass<NV>(lb, n, bit, blk == 0 ? 0 : 1, a.aux_val, a.dz0, a.Wenc + r,
+                   a.We_s1 ? a.We_s1 + r : nullptr, a.We_s2 ? a.We_s2 + r : nullptr, a.opt, lane, cs);
+    }
+  }
+}
+
+// Sum of squares of a kernel (for the L2 term of the reported loss), 64 fixed partials.
+__global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ w, size_t n, float* __restrict__ part) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s = fmaf(w[i], w[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += sh[k];
+    part[blockIdx.x] = t;
+  }
+}
+
+// Per-step metric record from the per-row statistics (train.py:102-121 + the Keras loss).
+// One warp, fixed summation order.
+__global__ void __launch_bounds__(32)
+k_metrics(const float* __restrict__ rowstats, int B, float rows_total, float n_cols_total,
+          float rating_range, int loss_kind, const float* __restrict__ regparts, int n_reg, float l2,
+          float* __restrict__ rec) {
+  const int lane = threadIdx.x;
+  float sse = 0.f, sae = 0.f, cnt = 0.f, srt = 0.f, reg = 0.f;
+  for (int b = lane; b < B; b += 32) {
+    const float s = rowstats[b * ROWSTAT_W];
+    sse += s; sae += rowstats[b * ROWSTAT_W + 1]; cnt += rowstats[b * ROWSTAT_W + 2];
+    srt += sqrtf(s);
+  }
+  for (int k = lane; k < n_reg; k += 32) reg += regparts[k];
+  sse = warp_sum(sse); sae = warp_sum(sae); cnt = warp_sum(cnt); srt = warp_sum(srt); reg = warp_sum(reg);
+  if (lane == 0) {
+    const float bn = rows_total * n_cols_total;
+    const float mse = sse / bn, mae = sae / bn;
+    const float acc_mae = sae / cnt;
+    rec[0] = (loss_kind == OCF_LOSS_MSE ? mse : mae) + (n_reg > 0 ? l2 * reg : 0.f);
+    rec[1] = mae;
+    rec[2] = acc_mae;
+    rec[3] = acc_mae / rating_range;
+    rec[4] = sqrtf(rows_total / cnt) * srt / rows_total;
+    rec[5] = sse / cnt;
+    rec[6] = sse;
+    rec[7] = cnt;
+  }
+}
+
+}  // namespace ocf

@@ -1,0 +1,306 @@
+"""Host-side mirror of the reference's `data_reader` (same constructor, attributes, generator
+protocol and NumPy global-RNG consumption), minus the per-rating Python loop.
+
+What stays on the host (cheap, O(B) per batch + one vectorised RNG draw):
+  * set selection, lazy permutation, floor(n/B) batches, the infinite None tail
+    (`data_reader.py:314-419`)
+  * the RNG replay: `uniform(lo, hi, B)` then one `random_sample(sum n)` compared against the
+    per-row cdf - bit-identical to the B calls of `np.random.choice([0,1], n, p=[1-s, s])` at
+    `data_reader.py:120,130`
+What moves to the GPU (`ocf_batch_fill_*`, kernel K1): everything that touches a rating.
+
+A generator yields `Batch` objects. `omni_model.model.fit_generator/evaluate_generator/predict`
+consume them directly (no dense arrays anywhere); unpacking one like the reference's tuples,
+`input_list, targets = batch`, materialises the reference's dense float64 arrays through the
+CUDA scatter kernel, so reference-style callers keep working.
+"""
+from __future__ import annotations
+
+import json
+import pickle
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .store import BatchRing, RatingStore, StorePair
+from .synthetic import Csr, FixedSplit
+
+
+def _csr_from_lists(lists, col_of, n_cols) -> Csr:
+    """Per-row [(item, rating), ...] lists (None = no list) -> CSR, stored order kept."""
+    lens = np.fromiter((0 if l is None else len(l) for l in lists), dtype=np.int64, count=len(lists))
+    rowptr = np.zeros(len(lists) + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    col = np.empty(int(rowptr[-1]), dtype=np.int32)
+    val = np.empty(int(rowptr[-1]), dtype=np.float32)
+    k = 0
+    for l in lists:
+        if not l:
+            continue
+        for pair in l:
+            col[k] = col_of[pair[0]]           # data_reader.py:135 (KeyError like the reference)
+            val[k] = pair[1]
+            k += 1
+    return Csr(len(lists), n_cols, rowptr, col, val)
+
+
+class Batch(object):
+    """One batch as (row ids, keep flags) + the stores they index. Host-only until uploaded."""
+
+    def __init__(self, reader, kind, source, rows, flags, pass_through, aux_type, aux_value,
+                 target_count, return_target_count):
+        self.reader = reader
+        self.kind = kind                       # "split" | "fixed"
+        self.source = source                   # RatingStore | StorePair
+        self.rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self.flags = flags
+        self.pass_through = bool(pass_through)
+        self.aux_type = aux_type
+        self.aux_value = float(aux_value)
+        self.target_count = int(target_count)
+        self.return_target_count = bool(return_target_count)
+        self.n_rows = int(self.rows.size)
+        self.n_cols = int(source.n_cols)
+        self.n_entries = int(source.lengths[self.rows].sum())
+        self._device = None
+
+    def upload(self, stream=None):
+        """Stage + copy + gather (K1) into one of the reader's device batch buffers."""
+        ring = self.reader._ring_for(self.n_rows, self.n_entries)
+        dev = ring.next()
+        if self.kind == "split":
+            dev.fill_split(self.source, self.rows, self.flags, self.pass_through, self.aux_value, stream)
+        else:
+            dev.fill_fixed(self.source, self.rows, self.aux_value, stream)
+        self._device = dev
+        return dev
+
+    # -- reference-shaped view ---------------------------------------------------------------
+    def to_dense(self, stream=None):
+        """(input_list, targets) exactly as `data_reader.py:354-363` builds them (float64)."""
+        dev = self.upload(stream)
+        get = lambda which: dev.densify(which, self.n_rows, self.n_cols, stream)
+        x, mask_in, mask_out, t, observed = 0, 1, 2, 3, 4
+        if self.aux_type is None:
+            feed = [get(x), get(mask_out)]
+        else:
+            if self.aux_type == "causal":
+                aux = get(observed)
+            elif self.aux_type in ("dropout", "both"):
+                aux = get(mask_in)
+            elif self.aux_type == "zeros":
+                aux = np.zeros((self.n_rows, self.n_cols))
+            else:
+                raise ValueError("Auxilliary mask type %r doesn't exist" % (self.aux_type,))
+            feed = [get(x), aux, get(mask_out)]
+            if self.aux_type == "both":
+                feed.append(get(observed))
+        return feed, get(t)
+
+    def _as_tuple(self):
+        feed, targets = self.to_dense()
+        if self.return_target_count:
+            return (feed, targets, self.target_count)
+        return (feed, targets)
+
+    def __iter__(self):
+        return iter(self._as_tuple())
+
+    def __len__(self):
+        return 3 if self.return_target_count else 2
+
+    def __getitem__(self, k):
+        if k == 2 and self.return_target_count:
+            return self.target_count
+        return self._as_tuple()[k]
+
+
+class data_reader(object):
+    """Drop-in for `data_reader.data_reader` (`data_reader.py:11-83`).
+
+    Extra keyword `data`: instead of reading `filepath + name + ".json"` files, take
+      * a dict {file base name: object} with the same names the reference loads
+        (`unique_items_list`, `ratingsByUser_dicts_train`, ...), or
+      * a `synthetic.FixedSplit` (CSR arrays; `eval_mode="fixed_split"` only).
+    """
+
+    def __init__(self, num_items, num_users, filepath, nonsequentialusers=False, use_json=True,
+                 eval_mode="ablation", useTimestamps=False, reverse_user_item_data=False, data=None,
+                 stream=None):
+        if useTimestamps:
+            raise NotImplementedError("useTimestamps is broken in the reference (data_reader.py:132,359,409) "
+                                      "and out of scope here")
+        if eval_mode not in ("ablation", "fixed_split"):
+            raise ValueError("eval_mode must be 'ablation' or 'fixed_split'")
+        self.num_items = int(num_items)
+        self.num_users = int(num_users)
+        self.filepath = filepath
+        self.nonsequentialusers = nonsequentialusers
+        self.eval_mode = eval_mode
+        self.useTimestamps = useTimestamps
+        self.stream = stream
+        self._files = data if isinstance(data, dict) else None
+        self._rings = {}
+        self._stores = {}
+        if isinstance(data, FixedSplit):
+            self._init_from_split(data)
+        else:
+            self._init_from_files(use_json, reverse_user_item_data)
+        print("Finished loading data")
+
+    # -- loading -----------------------------------------------------------------------------
+    def load_data(self, filepath, filename, use_json):
+        if self._files is not None:
+            return self._files[filename]
+        if use_json:
+            with open(filepath + filename + ".json", "r") as f:
+                return json.load(f)
+        with open(filepath + filename + ".p", "rb") as f:
+            return pickle.load(f)
+
+    def _init_from_files(self, use_json, reverse):
+        N = self.num_items
+        self.unique_items = self.load_data(self.filepath, "unique_users_list" if reverse else "unique_items_list", use_json)
+        self.items_to_densevec = {item: i for i, item in enumerate(self.unique_items)}       # :24-28
+        self.densevec_to_items = {i: item for i, item in enumerate(self.unique_items)}
+        if self.nonsequentialusers:                                                           # :30-44
+            self.unique_users = self.load_data(self.filepath, "unique_items_list" if reverse else "unique_users_list", use_json)
+            self.users_to_densevec = {u: i for i, u in enumerate(self.unique_users)}
+            self.densevec_to_users = {i: u for i, u in enumerate(self.unique_users)}
+        else:
+            self.densevec_to_users = {i: i for i in range(self.num_users)}
+        base = "ratingsByItem" if reverse else "ratingsByUser"                                # :46-49
+        if self.eval_mode == "ablation":
+            user_dict = self.load_data(self.filepath, base + "_dict", use_json)               # :55
+            lists = []
+            for i in range(self.num_users):
+                raw = self.densevec_to_users[i]
+                lists.append(user_dict[raw] if raw in user_dict else user_dict[str(raw)])
+            self._stores["train"] = RatingStore(_csr_from_lists(lists, self.items_to_densevec, N), build_csc=True)
+        else:
+            train = self.load_data(self.filepath, base + "_dicts_train", use_json)            # :67-70
+            valid = self.load_data(self.filepath, base + "_dicts_valid", use_json)
+            test = self.load_data(self.filepath, base + "_dicts_test", use_json)
+            self.train_set = list(train.keys())                                               # :78-80
+            self.val_set = list(valid[1].keys())
+            self.test_set = list(test[1].keys())
+            self.train_set_size = len(self.train_set)                                         # :73-75
+            self.val_set_size = len(self.val_set)
+            self.test_set_size = len(self.test_set)
+            col_of = self.items_to_densevec
+            self._stores["train"] = RatingStore(_csr_from_lists(list(train.values()), col_of, N), build_csc=True)
+            for name, (ins, tgs), keys in (("valid", valid, self.val_set), ("test", test, self.test_set)):
+                pair = StorePair(RatingStore(_csr_from_lists([ins[k] for k in keys], col_of, N)),
+                                 RatingStore(_csr_from_lists([tgs[k] for k in keys], col_of, N)))
+                self._stores[name] = pair
+
+    def _init_from_split(self, fs: FixedSplit):
+        if self.eval_mode != "fixed_split":
+            raise ValueError("a FixedSplit only serves eval_mode='fixed_split'")
+        if fs.n_cols != self.num_items:
+            raise ValueError("num_items (%d) must equal the split's column count (%d)" % (self.num_items, fs.n_cols))
+        self.unique_items = list(range(fs.n_cols))
+        self.train_set = [str(int(k)) for k in fs.train_keys]
+        self.val_set = [str(int(k)) for k in fs.valid_keys]
+        self.test_set = [str(int(k)) for k in fs.test_keys]
+        self.train_set_size, self.val_set_size, self.test_set_size = len(self.train_set), len(self.val_set), len(self.test_set)
+        self._stores["train"] = RatingStore(fs.train, build_csc=True)
+        self._stores["valid"] = StorePair(RatingStore(fs.valid_in), RatingStore(fs.valid_tg))
+        self._stores["test"] = StorePair(RatingStore(fs.test_in), RatingStore(fs.test_tg))
+
+    # -- ablation row split --------------------------------------------------------------------
+    def split_for_validation(self, val_split, seed=None):
+        """`data_reader.py:300-312`."""
+        self.val_split = val_split
+        if seed is not None:
+            np.random.seed(seed)
+        order = np.random.permutation(self.num_users)
+        self.train_set_size = int(self.num_users * val_split[0])
+        self.val_set_size = int(self.num_users * val_split[1])
+        self.test_set_size = int(self.num_users * val_split[2])
+        self.train_set = order[0:self.train_set_size]
+        self.val_set = order[self.train_set_size:self.train_set_size + self.val_set_size]
+        self.test_set = order[self.train_set_size + self.val_set_size:]
+
+    # -- device buffers ------------------------------------------------------------------------
+    def max_batch_entries(self, batch_size) -> int:
+        """Upper bound of the ratings in any batch of `batch_size` rows of any set."""
+        best = 1
+        for src in self._stores.values():
+            lens = np.sort(np.asarray(src.lengths))
+            best = max(best, int(lens[-int(batch_size):].sum()))
+        return best
+
+    def _ring_for(self, rows, entries):
+        ring = self._rings.get(rows)
+        if ring is None or not ring.fits(rows, entries):
+            if ring is not None:
+                ring.close()
+            ring = BatchRing(rows, max(self.max_batch_entries(rows), entries))
+            self._rings[rows] = ring
+        return ring
+
+    def store(self, which):
+        return self._stores[which]
+
+    # -- the generator ---------------------------------------------------------------------------
+    def data_gen(self, batch_size, data_sparsity, train_val_test="train", shuffle=True,
+                 auxilliary_mask_type="dropout", aux_var_value=-1, return_target_count=False,
+                 sparse_representation=False, pass_through_input_training=False):
+        """`data_reader.py:314-419`. Yields `Batch` objects, then None for ever."""
+        if sparse_representation:
+            raise NotImplementedError("sparse_representation needs a patched Keras backend in the reference "
+                                      "(train.py:53); batches here are never dense in the first place")
+        if auxilliary_mask_type not in _lib.AUX_TYPES:
+            print("Auxilliary mask type ", auxilliary_mask_type, " doesn't exist")
+            raise ValueError(auxilliary_mask_type)
+        if train_val_test == "train":
+            order, n = self.train_set, self.train_set_size
+        elif train_val_test == "valid":
+            order, n = self.val_set, self.val_set_size
+        elif train_val_test == "test":
+            order, n = self.test_set, self.test_set_size
+        else:
+            raise ValueError(train_val_test)
+        split_mode = self.eval_mode == "ablation" or train_val_test == "train"      # :331
+        if self.eval_mode == "ablation":
+            rows = np.asarray(order, dtype=np.int64)       # dense row ids == store rows (:124-125)
+            source = self._stores["train"]
+        else:
+            rows = np.arange(len(order), dtype=np.int64)   # k-th key == k-th store row
+            source = self._stores[train_val_test]
+        if shuffle:
+            rows = rows[np.random.permutation(len(order))]                          # :326-327
+        batch_size = int(batch_size)
+        num_batches = int(np.floor(n / batch_size))                                  # :329
+        if split_mode and np.isscalar(data_sparsity):
+            data_sparsity = [data_sparsity, data_sparsity]      # the reference crashes here (Appendix B)
+        lengths = source.lengths
+        for i in range(num_batches):
+            brow = rows[i * batch_size:(i + 1) * batch_size]
+            if split_mode:
+                n_b = lengths[brow]
+                keep = np.random.uniform(low=data_sparsity[0], high=data_sparsity[1], size=batch_size)   # :120
+                u = np.random.random_sample(int(n_b.sum()))                                               # :130
+                p0 = 1 - keep
+                flags = (u >= np.repeat(p0 / (p0 + keep), n_b)).astype(np.uint8)
+                tcount = flags.size if pass_through_input_training else int(flags.size - flags.sum())
+                yield Batch(self, "split", source, brow, flags, pass_through_input_training,
+                            auxilliary_mask_type, aux_var_value, tcount, False)
+            else:
+                tcount = int(source.tgt_store.lengths[brow].sum())                                        # :268
+                yield Batch(self, "fixed", source, brow, None, False, auxilliary_mask_type,
+                            aux_var_value, tcount, return_target_count)
+        while True:                                                                                        # :418-419
+            yield None
+
+    def close(self):
+        for ring in self._rings.values():
+            ring.close()
+        self._rings = {}
+        for s in self._stores.values():
+            if isinstance(s, StorePair):
+                s.close(); s.in_store.close(); s.tgt_store.close()
+            else:
+                s.close()

@@ -1,0 +1,440 @@
+"""Host-side mirror of the reference's `omni_model` (`model.py:33-170`) and of the Keras `Model`
+methods `train.py` calls on it, over the CUDA library.
+
+    omni_m = omni_model(numlayers, num_hidden_units, num_items, batch_size, dense_activation=..., ...)
+    m = omni_m.model
+    m.compile(optimizer=Adagrad(lr=0.005, epsilon=1e-08, decay=0.0), loss='mean_squared_error')
+    history = m.fit_generator(train_gen, steps, validation_data=valid_gen, validation_steps=vsteps)
+
+Arithmetic runs in `csrc/` kernels; nothing here computes.
+Differences from Keras that a caller can see:
+  * generators yield `data_reader.Batch` objects, not dense arrays
+  * `num_hidden_units` may be a list of widths (superset; the reference uses one width)
+  * `save`/`load` use `.npz` (h5py is not available); optimizer state is not saved, matching
+    what `train.py:183-189` strips before testing
+  * dropout masks come from Philox (oracle/philox.py defines the spec), not TensorFlow's RNG
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .optimizers import Optimizer, get as get_optimizer
+
+METRIC_NAMES = ["loss", "mean_absolute_error", "accurate_MAE", "nMAE", "accurate_RMSE", "accurate_MSE"]
+
+
+class History(object):
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+
+class OmniNet(object):
+    """The object `omni_model.model` exposes (stands in for the Keras `Model`)."""
+
+    def __init__(self, owner):
+        self.owner = owner
+        self._handle = None
+        self._capacity = (0, 0)
+        self.optimizer: Optimizer = get_optimizer("adagrad")
+        self.loss = "mean_squared_error"
+        self.rating_range = 1.0
+        self.metrics_names = list(METRIC_NAMES)
+        self.stream = None
+        self._step = 0
+        self._compiled = False
+
+    # -- C handle -----------------------------------------------------------------------------
+    def _ensure(self, n_rows=None, n_entries=None, aux_type="keep"):
+        o = self.owner
+        if aux_type != "keep" and aux_type != o.aux_kind:
+            o.set_aux_kind(aux_type)       # the reader decides what the aux block holds
+        rows = max(int(n_rows or o.batch_size), self._capacity[0])
+        entries = max(int(n_entries or 1), self._capacity[1])
+        if self._handle is None:
+            _lib.require_gpu()
+            cfg = _lib.ModelConfig()
+            cfg.n_cols = o.local_cols
+            cfg.n_cols_total = o.input_shape
+            cfg.n_layers = o.numlayers
+            for i, w in enumerate(o.widths):
+                cfg.widths[i] = w
+            cfg.aux = _lib.AUX_TYPES[o.aux_kind]
+            cfg.activation = _lib.ACTIVATIONS[o.dense_activation]
+            cfg.loss = _lib.LOSSES[self.loss]
+            cfg.l2 = -1.0 if o.l2 is None else float(o.l2)
+            cfg.dropout_p = -1.0 if o.dropout_probability is None else float(o.dropout_probability)
+            cfg.aux_var_value = -1.0
+            cfg.rating_range = float(self.rating_range)
+            cfg.max_rows = rows
+            cfg.max_entries = entries
+            cfg.sharded = int(o.sharded)
+            out = C.c_void_p()
+            _lib.check(_lib.lib().ocf_model_create(C.byref(cfg), C.byref(out)))
+            self._handle = out
+            self._capacity = (rows, entries)
+            self._push_weights(o._host_weights)
+            o._host_weights = None
+            self._push_optimizer()
+            for l, t in enumerate(o.trainable):
+                _lib.check(_lib.lib().ocf_model_set_trainable(self._handle, l, int(t)))
+        elif rows > self._capacity[0] or entries > self._capacity[1]:
+            _lib.check(_lib.lib().ocf_model_reserve(self._handle, rows, entries))
+            self._capacity = (rows, entries)
+        return self._handle
+
+    def _push_weights(self, weights):
+        for i, w in enumerate(weights):
+            w = np.ascontiguousarray(w, dtype=np.float32)
+            _lib.check(_lib.lib().ocf_model_set_weight(self._handle, i, _lib.ptr(w), w.size))
+
+    def _push_optimizer(self):
+        opt = self.optimizer
+        _lib.check(_lib.lib().ocf_model_set_optimizer(self._handle, _lib.OPTIMIZERS[opt.kind], opt.lr, opt.p1,
+                                                      opt.p2, opt.epsilon, opt.decay))
+        _lib.check(_lib.lib().ocf_model_set_loss(self._handle, _lib.LOSSES[self.loss], float(self.rating_range)))
+
+    # -- Keras surface --------------------------------------------------------------------------
+    def compile(self, optimizer="adagrad", loss="mean_squared_error", metrics=None, rating_range=None):
+        """`m.compile(...)`, train.py:131-133. The metric set is fixed to train.py's five
+        (`metrics` is accepted and ignored); `rating_range` feeds nMAE (train.py:118-121)."""
+        if loss not in _lib.LOSSES:
+            raise ValueError("loss must be mean_squared_error or mean_absolute_error")
+        self.optimizer = get_optimizer(optimizer)
+        self.loss = loss
+        if rating_range is not None:
+            self.rating_range = float(rating_range)
+        self._compiled = True
+        if self._handle is not None:
+            self._push_optimizer()
+
+    def get_weights(self) -> List[np.ndarray]:
+        o = self.owner
+        if self._handle is None:
+            return [w.copy() for w in o._host_weights]
+        out = []
+        shape = (C.c_int64 * 2)()
+        for i in range(2 * (o.numlayers + 1)):
+            _lib.check(_lib.lib().ocf_model_weight_shape(self._handle, i, shape))
+            arr = np.empty((shape[0], shape[1]) if i % 2 == 0 else (shape[0],), dtype=np.float32)
+            _lib.check(_lib.lib().ocf_model_get_weight(self._handle, i, _lib.ptr(arr), arr.size))
+            out.append(arr)
+        return out
+
+    def set_weights(self, weights):
+        o = self.owner
+        shapes = o.weight_shapes()
+        if len(weights) != len(shapes):
+            raise ValueError("expected %d weight arrays, got %d" % (len(shapes), len(weights)))
+        ws = []
+        for w, s in zip(weights, shapes):
+            w = np.asarray(w, dtype=np.float32)
+            if tuple(w.shape) != tuple(s):
+                raise ValueError("weight shape %s does not match %s" % (w.shape, s))
+            ws.append(np.ascontiguousarray(w))
+        if self._handle is None:
+            o._host_weights = ws
+        else:
+            self._push_weights(ws)
+
+    def _args(self, batch, phase=0, training=True):
+        a = _lib.StepArgs()
+        a.dropout_seed = self.owner.dropout_seed
+        a.step = self._step & 0xFFFFFFFF
+        a.row0 = 0
+        a.rows_total = 0
+        a.phase = phase
+        return a
+
+    def _metrics_from(self, rec):
+        return [float(rec[0]), float(rec[1]), float(rec[2]), float(rec[3]), float(rec[4]), float(rec[5])]
+
+    def train_on_batch(self, batch, sync=True):
+        """One optimisation step. Returns the six metric values when `sync`, else None (the
+        values stay in the device log; see `read_metrics`)."""
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+        dev = batch.upload(self.stream)
+        args = self._args(batch)
+        rec = np.empty(_lib.N_METRICS, dtype=np.float32) if sync else None
+        _lib.check(_lib.lib().ocf_train_step(h, dev.handle, C.byref(args), _lib.ptr(rec), self.stream))
+        self._step += 1
+        return self._metrics_from(rec) if sync else None
+
+    def test_on_batch(self, batch, sync=True):
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+        dev = batch.upload(self.stream)
+        args = self._args(batch, training=False)
+        rec = np.empty(_lib.N_METRICS, dtype=np.float32) if sync else None
+        _lib.check(_lib.lib().ocf_eval_step(h, dev.handle, C.byref(args), _lib.ptr(rec), self.stream))
+        return self._metrics_from(rec) if sync else None
+
+    def read_metrics(self, first, count):
+        """[count, 8] records of steps first..first+count-1 from the device log."""
+        out = np.empty((count, _lib.N_METRICS), dtype=np.float32)
+        if count:
+            _lib.check(_lib.lib().ocf_model_read_metrics(self._handle, first, count, _lib.ptr(out), self.stream))
+        return out
+
+    def _run(self, generator, steps, train):
+        """`steps` batches through train/eval steps without a host sync per step; the metric
+        records are read back once at the end (each at most 4096 steps)."""
+        steps = int(steps)
+        rows = []
+        done = 0
+        while done < steps:
+            chunk = min(steps - done, 2048)
+            first = None
+            for _ in range(chunk):
+                batch = next(generator)
+                if batch is None:
+                    raise StopIteration("generator ran out of batches (it yields None after floor(n/B) batches)")
+                if first is None:
+                    self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+                    first = _lib.lib().ocf_model_steps_logged(self._handle)
+                (self.train_on_batch if train else self.test_on_batch)(batch, sync=False)
+            rows.append(self.read_metrics(first, chunk))
+            done += chunk
+        return np.concatenate(rows, axis=0) if rows else np.zeros((0, _lib.N_METRICS), dtype=np.float32)
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, verbose=1, callbacks=None,
+                      validation_data=None, validation_steps=None, **_ignored):
+        """`m.fit_generator(train_gen, steps, validation_data=valid_gen, validation_steps=...)`,
+        train.py:157-158. Per-epoch value = mean of the per-batch values; training values are
+        pre-update with dropout on, validation has dropout off (Keras semantics)."""
+        hist = History()
+        for epoch in range(int(epochs)):
+            recs = self._run(generator, steps_per_epoch, train=True)
+            mean = recs[:, :6].astype(np.float64).mean(axis=0) if len(recs) else np.full(6, np.nan)
+            for name, v in zip(METRIC_NAMES, mean):
+                hist.history.setdefault(name, []).append(float(v))
+            if validation_data is not None:
+                vals = self.evaluate_generator(validation_data, validation_steps)
+                for name, v in zip(METRIC_NAMES, vals):
+                    hist.history.setdefault("val_" + name, []).append(float(v))
+            hist.epoch.append(epoch)
+            if verbose:
+                print(" - ".join("%s: %.4f" % (k, v[-1]) for k, v in hist.history.items()))
+        return hist
+
+    def evaluate_generator(self, generator, steps, **_ignored):
+        """train.py:208,218. Returns [loss, mae, accurate_MAE, nMAE, accurate_RMSE, accurate_MSE]."""
+        recs = self._run(generator, steps, train=False)
+        return [float(v) for v in recs[:, :6].astype(np.float64).mean(axis=0)]
+
+    def predict(self, batch, batch_size=None, verbose=0):
+        """`best_m.predict(input_list)`, train.py:239: output_mask * full_predictions, [B, N] float32."""
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+        dev = batch.upload(self.stream)
+        out = np.empty((batch.n_rows, self.owner.local_cols), dtype=np.float32)
+        _lib.check(_lib.lib().ocf_predict(h, dev.handle, _lib.ptr(out), self.stream))
+        return out
+
+    def score(self, batch):
+        """Full-catalogue scores `full_predictions` (model.py:82-84), [B, N] float32."""
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+        dev = batch.upload(self.stream)
+        out = np.empty((batch.n_rows, self.owner.local_cols), dtype=np.float32)
+        _lib.check(_lib.lib().ocf_score(h, dev.handle, _lib.ptr(out), 0, self.stream))
+        return out
+
+    def save(self, path):
+        """`m.save(...)`, train.py:169 (weights + architecture as .npz; no optimizer state)."""
+        o = self.owner
+        np.savez(path if path.endswith(".npz") else path + ".npz", *self.get_weights(),
+                 config=np.array(repr(o.config())))
+
+    def save_weights(self, path):
+        np.savez(path if path.endswith(".npz") else path + ".npz", *self.get_weights())
+
+    def load_weights(self, path):
+        with np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False) as f:
+            keys = sorted((k for k in f.files if k.startswith("arr_")), key=lambda k: int(k[4:]))
+            self.set_weights([f[k] for k in keys])
+
+    def close(self):
+        if self._handle is not None:
+            _lib.lib().ocf_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class omni_model(object):
+    """Drop-in for `model.omni_model` (`model.py:33-99`)."""
+
+    def __init__(self, numlayers, num_hidden_units, input_shape, batch_size, dense_activation="tanh",
+                 use_causal_info=True, use_timestamps=False, use_both_masks=False,
+                 l2_weight_regulatization=None, sparse_representation=False, dropout_probability=None,
+                 use_sparse_masking_layer=False, auxilliary_mask_type="default", local_cols=None):
+        if use_timestamps:
+            raise NotImplementedError("use_timestamps: the reference's timestamp path is broken and out of scope")
+        if sparse_representation:
+            raise NotImplementedError("sparse_representation: inputs are never dense here; leave it False")
+        if use_sparse_masking_layer:
+            raise NotImplementedError("Dynamic_Masking_Layer cannot be constructed in the reference "
+                                      "(model.py:186); the decoder kernel already evaluates observed entries only")
+        if dense_activation not in _lib.ACTIVATIONS:
+            raise ValueError("unsupported dense_activation %r" % (dense_activation,))
+        self.numlayers = int(numlayers)
+        if isinstance(num_hidden_units, (list, tuple)):
+            self.widths = [int(w) for w in num_hidden_units]
+            if len(self.widths) != self.numlayers:
+                raise ValueError("need one width per hidden layer")
+        else:
+            self.widths = [int(num_hidden_units)] * self.numlayers
+        if not 1 <= self.numlayers <= 8:
+            raise ValueError("numlayers must be 1..8")
+        self.num_hidden_units = self.widths[0]
+        self.input_shape = int(input_shape)
+        self.batch_size = int(batch_size)
+        self.dense_activation = dense_activation
+        self.use_causal_info = bool(use_causal_info)
+        self.use_both_masks = bool(use_both_masks)
+        self.l2 = l2_weight_regulatization
+        self.dropout_probability = dropout_probability
+        self.k_blocks = 1 + int(self.use_causal_info) + int(self.use_both_masks)
+        # Which mask the aux block holds is the reader's choice (auxilliary_mask_type); the
+        # model only fixes how many blocks are concatenated (model.py:47-56).
+        if auxilliary_mask_type == "default":
+            auxilliary_mask_type = ("both" if self.use_both_masks else "dropout") if self.use_causal_info else None
+        self.set_aux_kind(auxilliary_mask_type)
+        self.local_cols = self.input_shape if local_cols is None else int(local_cols)
+        self.sharded = self.local_cols != self.input_shape
+        self.trainable = [True] * (self.numlayers + 1)
+        # Keras draws one seed per kernel initializer and per Dropout layer from the global NumPy
+        # RNG while the graph is built; keep that stream position.
+        dims = [self.k_blocks * self.local_cols] + self.widths + [self.local_cols]
+        fan = [self.k_blocks * self.input_shape] + self.widths + [self.input_shape]
+        self._host_weights = []
+        seeds = []
+        for l in range(self.numlayers + 1):
+            seed = int(np.random.randint(10e6))
+            lim = np.sqrt(6.0 / (fan[l] + fan[l + 1]))                  # glorot_uniform
+            rs = np.random.RandomState(seed)
+            self._host_weights.append(rs.uniform(-lim, lim, size=(dims[l], dims[l + 1])).astype(np.float32))
+            self._host_weights.append(np.zeros(dims[l + 1], dtype=np.float32))
+            if l < self.numlayers and dropout_probability is not None:
+                seeds.append(int(np.random.randint(10e6)))
+        self.dropout_seed = (seeds[0] if seeds else 0) | (0x0CF << 32)
+        self.model = OmniNet(self)
+
+    def set_aux_kind(self, aux_type):
+        k = {None: 1, "causal": 2, "dropout": 2, "zeros": 2, "both": 3}[aux_type]
+        if k != self.k_blocks:
+            raise ValueError("auxilliary_mask_type %r feeds %d input blocks but the model was built for %d "
+                             "(use_causal_info / use_both_masks, model.py:47-56)" % (aux_type, k, self.k_blocks))
+        self.aux_kind = aux_type
+        net = getattr(self, "model", None)
+        if net is not None and net._handle is not None:
+            _lib.check(_lib.lib().ocf_model_set_aux(net._handle, _lib.AUX_TYPES[aux_type]))
+
+    def config(self):
+        return dict(numlayers=self.numlayers, num_hidden_units=self.widths, input_shape=self.input_shape,
+                    batch_size=self.batch_size, dense_activation=self.dense_activation,
+                    use_causal_info=self.use_causal_info, use_both_masks=self.use_both_masks,
+                    l2_weight_regulatization=self.l2, dropout_probability=self.dropout_probability,
+                    auxilliary_mask_type=self.aux_kind)
+
+    def weight_shapes(self):
+        dims = [self.k_blocks * self.local_cols] + self.widths + [self.local_cols]
+        out = []
+        for l in range(self.numlayers + 1):
+            out += [(dims[l], dims[l + 1]), (dims[l + 1],)]
+        return out
+
+    # -- model.py:102-107 ---------------------------------------------------------------------
+    def save_weights(self, filename):
+        self.model.save_weights(filename)
+
+    def load_weights(self, weights):
+        self.model.set_weights(weights)
+
+    # -- weight transfer, model.py:109-170 -------------------------------------------------------
+    # Every Dense layer of this architecture touches a width-H tensor, so the reference's
+    # "dense layers with input or output width == num_hidden_units" filter selects all L+1.
+    def _dense_pairs(self):
+        w = self.model.get_weights()
+        return [[w[2 * l], w[2 * l + 1]] for l in range(self.numlayers + 1)]
+
+    def _set_dense(self, l, pair):
+        w = self.model.get_weights()
+        w[2 * l], w[2 * l + 1] = pair[0], pair[1]
+        self.model.set_weights(w)
+
+    def _set_trainable(self, l, flag):
+        self.trainable[l] = bool(flag)
+        if self.model._handle is not None:
+            _lib.check(_lib.lib().ocf_model_set_trainable(self.model._handle, l, int(bool(flag))))
+
+    def replace_dense_layer_weights(self, donor_model, layers_to_replace, make_layers_trainable=False):
+        donor = _donor_pairs(donor_model)
+        if layers_to_replace == "all":
+            layers_to_replace = [True] * len(donor)
+        for l in range(self.numlayers + 1):
+            if layers_to_replace[l]:
+                self._set_dense(l, donor[l])
+                self._set_trainable(l, make_layers_trainable)
+                print("Loaded weights for dense layer ", l)
+
+    def manually_load_all_weights(self, donor_model):
+        self.model.set_weights(_donor_weights(donor_model))
+
+    def make_trainable(self):
+        for l in range(self.numlayers):
+            self._set_trainable(l, True)
+        if self.input_shape == self.num_hidden_units:
+            self._set_trainable(self.numlayers, True)
+
+    def load_and_fix_for_denoising_autoencoders(self, donor_model):
+        donor = _donor_pairs(donor_model)
+        print("Number of weight layers to donate", len(donor))
+        n_side = int(len(donor) / 2)
+        n_new = self.numlayers + 1
+        for l in range(n_new):
+            if l < n_side:
+                self._set_dense(l, donor[l])
+                self._set_trainable(l, False)
+                print("Loaded and fixed weights for dense layer ", l, " from donor dense layer ", l)
+            elif l >= n_new - n_side:
+                src = len(donor) - (n_new - l)
+                self._set_dense(l, donor[src])
+                self._set_trainable(l, False)
+                print("Loaded and fixed weights for dense layer ", l, " from donor dense layer ", src)
+
+
+def _donor_weights(donor):
+    if isinstance(donor, omni_model):
+        donor = donor.model
+    if isinstance(donor, OmniNet):
+        return donor.get_weights()
+    return [np.asarray(w) for w in donor]          # a plain weight list
+
+
+def _donor_pairs(donor):
+    w = _donor_weights(donor)
+    return [[w[2 * l], w[2 * l + 1]] for l in range(len(w) // 2)]
+
+
+def load_model(path):
+    """`keras.models.load_model(...)` stand-in for files written by `OmniNet.save` (train.py:139,191)."""
+    import ast
+    with np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False) as f:
+        cfg = ast.literal_eval(str(f["config"]))
+        keys = sorted((k for k in f.files if k.startswith("arr_")), key=lambda k: int(k[4:]))
+        weights = [f[k] for k in keys]
+    state = np.random.get_state()                   # loading must not disturb the caller's stream
+    om = omni_model(cfg["numlayers"], cfg["num_hidden_units"], cfg["input_shape"], cfg["batch_size"],
+                    dense_activation=cfg["dense_activation"], use_causal_info=cfg["use_causal_info"],
+                    use_both_masks=cfg["use_both_masks"], l2_weight_regulatization=cfg["l2_weight_regulatization"],
+                    dropout_probability=cfg["dropout_probability"], auxilliary_mask_type=cfg["auxilliary_mask_type"])
+    np.random.set_state(state)
+    om.model.set_weights(weights)
+    return om.model

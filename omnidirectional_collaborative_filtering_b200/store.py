@@ -1,0 +1,170 @@
+"""Device-resident rating stores and batch buffers (thin owners of the C handles)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .synthetic import Csr
+
+
+class RatingStore(object):
+    """One set of per-row rating lists (what `data_reader.py:46-70` keeps as dicts) as CSR on
+    the host, uploaded to HBM on first use. `build_csc` adds the column index training needs."""
+
+    def __init__(self, csr: Csr, build_csc: bool = False):
+        self.csr = csr
+        self.build_csc = bool(build_csc)
+        self._handle = None
+
+    @property
+    def n_rows(self):
+        return self.csr.n_rows
+
+    @property
+    def n_cols(self):
+        return self.csr.n_cols
+
+    @property
+    def lengths(self):
+        return np.diff(self.csr.rowptr)
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            _lib.require_gpu()
+            rowptr = np.ascontiguousarray(self.csr.rowptr, dtype=np.int64)
+            col = np.ascontiguousarray(self.csr.col, dtype=np.int32)
+            val = np.ascontiguousarray(self.csr.val, dtype=np.float32)
+            out = C.c_void_p()
+            _lib.check(_lib.lib().ocf_store_create(self.csr.n_rows, self.csr.n_cols, _lib.ptr(rowptr),
+                                                   _lib.ptr(col), _lib.ptr(val), int(self.build_csc),
+                                                   C.byref(out)))
+            self._handle = out
+        return self._handle
+
+    def info(self):
+        buf = (C.c_int64 * 6)()
+        _lib.check(_lib.lib().ocf_store_info(self.handle, buf))
+        return dict(zip(("n_rows", "n_cols", "nnz", "has_dups", "max_col_len", "device_bytes"), list(buf)))
+
+    def close(self):
+        if self._handle is not None:
+            _lib.lib().ocf_store_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class StorePair(object):
+    """Fixed-split valid/test set: inputs and targets with aligned rows (`data_reader.py:372-380`)."""
+
+    def __init__(self, in_store: RatingStore, tgt_store: RatingStore):
+        assert in_store.n_rows == tgt_store.n_rows and in_store.n_cols == tgt_store.n_cols
+        self.in_store, self.tgt_store = in_store, tgt_store
+        self._handle = None
+
+    @property
+    def n_rows(self):
+        return self.tgt_store.n_rows
+
+    @property
+    def n_cols(self):
+        return self.tgt_store.n_cols
+
+    @property
+    def lengths(self):
+        return self.in_store.lengths + self.tgt_store.lengths
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            out = C.c_void_p()
+            _lib.check(_lib.lib().ocf_pair_create(self.in_store.handle, self.tgt_store.handle, C.byref(out)))
+            self._handle = out
+        return self._handle
+
+    def close(self):
+        if self._handle is not None:
+            _lib.lib().ocf_pair_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBatch(object):
+    """One `ocf_batch`: pinned staging + device tiles."""
+
+    def __init__(self, max_rows: int, max_entries: int):
+        _lib.require_gpu()
+        self.max_rows, self.max_entries = int(max_rows), int(max(max_entries, 1))
+        out = C.c_void_p()
+        _lib.check(_lib.lib().ocf_batch_create(self.max_rows, self.max_entries, C.byref(out)))
+        self.handle = out
+
+    def fill_split(self, store: RatingStore, rows: np.ndarray, flags: np.ndarray, pass_through: bool,
+                   aux_value: float, stream=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        _lib.check(_lib.lib().ocf_batch_fill_split(self.handle, store.handle, _lib.ptr(rows), rows.size,
+                                                   _lib.ptr(flags), flags.size, int(bool(pass_through)),
+                                                   float(aux_value), stream))
+
+    def fill_fixed(self, pair: StorePair, rows: np.ndarray, aux_value: float, stream=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        _lib.check(_lib.lib().ocf_batch_fill_fixed(self.handle, pair.handle, _lib.ptr(rows), rows.size,
+                                                   float(aux_value), stream))
+
+    def info(self):
+        buf = (C.c_int64 * 5)()
+        _lib.check(_lib.lib().ocf_batch_info(self.handle, buf))
+        return dict(zip(("rows", "entries", "items", "target_count", "h2d_bytes"), list(buf)))
+
+    def densify(self, which: int, n_rows: int, n_cols: int, stream=None) -> np.ndarray:
+        out = np.empty((n_rows, n_cols), dtype=np.float64)
+        _lib.check(_lib.lib().ocf_batch_densify(self.handle, int(which), _lib.ptr(out), stream))
+        return out
+
+    def close(self):
+        if self.handle is not None:
+            _lib.lib().ocf_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchRing(object):
+    """A few DeviceBatch objects used round-robin, so staging batch i+1 on the host overlaps
+    the device work of batch i."""
+
+    def __init__(self, max_rows: int, max_entries: int, depth: int = 3):
+        self.max_rows, self.max_entries = int(max_rows), int(max_entries)
+        self.slots = [DeviceBatch(max_rows, max_entries) for _ in range(depth)]
+        self.cursor = 0
+
+    def fits(self, rows: int, entries: int) -> bool:
+        return rows <= self.max_rows and entries <= self.max_entries
+
+    def next(self) -> DeviceBatch:
+        slot = self.slots[self.cursor]
+        self.cursor = (self.cursor + 1) % len(self.slots)
+        return slot
+
+    def close(self):
+        for s in self.slots:
+            s.close()
+        self.slots = []

@@ -1,0 +1,53 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol the header
+declares, and refuses to compute without a GPU (no silent CPU fallback)."""
+import ctypes as C
+import subprocess
+
+import numpy as np
+import pytest
+
+from omnidirectional_collaborative_filtering_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = _lib.header_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), "include/ocf.h declares %s but libocf_b200.so does not export it" % name
+    assert set(names) == set(_lib._SIGNATURES), "ctypes signatures out of sync with include/ocf.h"
+    assert lib.ocf_version() == 100
+
+
+def test_exports_are_plain_c():
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.SO_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(_lib.header_symbols()) <= exported
+
+
+def test_kernels_are_sm100a():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = _lib.lib()
+    out = C.c_void_p()
+    rowptr = np.array([0, 2, 1], dtype=np.int64)           # not monotone
+    col = np.zeros(2, dtype=np.int32); val = np.zeros(2, dtype=np.float32)
+    st = lib.ocf_store_create(2, 4, _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), 0, C.byref(out))
+    assert st == -1 and b"monotone" in lib.ocf_last_error()
+    cfg = _lib.ModelConfig()
+    cfg.n_cols = 10; cfg.n_cols_total = 10; cfg.n_layers = 0
+    st = lib.ocf_model_create(C.byref(cfg), C.byref(out))
+    assert st == -1 and b"n_layers" in lib.ocf_last_error()
+
+
+@pytest.mark.skipif(_lib.lib().ocf_device_count() > 0, reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    from omnidirectional_collaborative_filtering_b200.store import RatingStore
+    from omnidirectional_collaborative_filtering_b200.synthetic import Csr
+    s = RatingStore(Csr(1, 3, np.array([0, 1], dtype=np.int64), np.array([1], dtype=np.int32),
+                        np.array([2.0], dtype=np.float32)))
+    with pytest.raises(_lib.OcfError):
+        s.handle
