@@ -94,6 +94,9 @@ int ocf_batch_fill_split(ocf_batch* batch, const ocf_store* store, const int32_t
 /* build_sparse_batch_fixed_split, data_reader.py:202-298. */
 int ocf_batch_fill_fixed(ocf_batch* batch, const ocf_pair* pair, const int32_t* row_ids,
                          int32_t n_rows, float aux_var_value, void* stream);
+/* Re-runs K1 on the row ids / keep flags already resident in the batch's device staging (no
+ * host->device copy). */
+int ocf_batch_regather(ocf_batch* batch, void* stream);
 /* info[0]=rows, [1]=entries, [2]=work items, [3]=target_count (data_reader.py:268; ratings
  * listed as targets, repeats included), [4]=bytes of the last host->device copy */
 int ocf_batch_info(const ocf_batch* batch, int64_t info[5]);
@@ -195,6 +198,13 @@ int ocf_model_buffer(ocf_model* model, int which, void** device_ptr, int64_t* co
 /* Device pointer of a weight (kernel or bias, Keras index) in the library's internal layout,
  * for collectives over replicated parameters; count in floats. */
 int ocf_model_weight_device(ocf_model* model, int index, void** device_ptr, int64_t* count);
+/* Per-kernel timing with CUDA events recorded on the launching stream around the named kernels
+ * (tag 0 = K1 gather, 1 = K2 encoder, 2 = K3 decoder/loss, 3 = K4 column update, 4 = scoring
+ * GEMM). Off by default; ocf_profile_read synchronises the device and sums the elapsed times
+ * of the launches recorded since the last reset. */
+int ocf_profile_enable(int on);
+int ocf_profile_reset(void);
+int ocf_profile_read(int tag, double* total_ms, int64_t* count);
 /* Number of kernels of this library launched by the calling process so far. */
 int64_t ocf_kernel_launches(void);
 

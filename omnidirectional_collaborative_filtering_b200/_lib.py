@@ -57,6 +57,10 @@ _SIGNATURES = {
     "ocf_batch_destroy": (C.c_int, [_P]),
     "ocf_batch_fill_split": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_int, C.c_float, _P]),
     "ocf_batch_fill_fixed": (C.c_int, [_P, _P, _P, C.c_int32, C.c_float, _P]),
+    "ocf_batch_regather": (C.c_int, [_P, _P]),
+    "ocf_profile_enable": (C.c_int, [C.c_int]),
+    "ocf_profile_reset": (C.c_int, []),
+    "ocf_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ocf_batch_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "ocf_batch_densify": (C.c_int, [_P, C.c_int, _P, _P]),
     "ocf_model_create": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(_P)]),

@@ -87,6 +87,8 @@ struct ocf_batch {
   BatchDev dev{};
   int mode = 0;                   // 0 empty, 1 split, 2 fixed
   const ocf_store* store = nullptr;
+  const ocf_pair* pair = nullptr;
+  int pass_through = 0;
   float aux_value = -1.f;
   int64_t target_count = 0;
   size_t last_h2d = 0;
@@ -142,6 +144,54 @@ extern "C" int ocf_device_count(void) {
   return n;
 }
 extern "C" int64_t ocf_kernel_launches(void) { return (int64_t)g_launches.load(); }
+
+
+// ---- optional per-kernel timing with CUDA events on the launching stream -------------------
+namespace ocf {
+constexpr int N_TAGS = 8;
+struct Profiler {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[N_TAGS];
+  size_t used[N_TAGS] = {0};
+  cudaEvent_t pending = nullptr;
+  void begin(int tag, cudaStream_t st) {
+    if (!on) return;
+    if (used[tag] == ev[tag].size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      ev[tag].push_back({a, b});
+    }
+    cudaEventRecord(ev[tag][used[tag]].first, st);
+  }
+  void end(int tag, cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(ev[tag][used[tag]].second, st);
+    used[tag] += 1;
+  }
+};
+static Profiler g_prof;
+}  // namespace ocf
+
+extern "C" int ocf_profile_enable(int on) {
+  g_prof.on = on != 0;
+  return OCF_OK;
+}
+extern "C" int ocf_profile_reset(void) {
+  for (int t = 0; t < N_TAGS; ++t) g_prof.used[t] = 0;
+  return OCF_OK;
+}
+extern "C" int ocf_profile_read(int tag, double* total_ms, int64_t* count) {
+  OCF_REQUIRE(tag >= 0 && tag < N_TAGS && total_ms && count, "ocf_profile_read: bad argument");
+  OCF_CUDA(cudaDeviceSynchronize());
+  double tot = 0.0;
+  for (size_t k = 0; k < g_prof.used[tag]; ++k) {
+    float ms = 0.f;
+    OCF_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[tag][k].first, g_prof.ev[tag][k].second));
+    tot += ms;
+  }
+  *total_ms = tot; *count = (int64_t)g_prof.used[tag];
+  return OCF_OK;
+}
 
 // ============================================================================================
 // store
@@ -395,6 +445,17 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
   return OCF_OK;
 }
 
+// K1 on the row ids / flags already resident in the batch's device staging.
+static int launch_gather(ocf_batch* b, cudaStream_t stream) {
+  if (b->dev.n_items == 0) return OCF_OK;
+  g_prof.begin(0, stream);
+  if (b->mode == 1) k_gather_split<<<b->dev.n_items, 128, 0, stream>>>(b->store->dev, b->dev, b->pass_through);
+  else k_gather_fixed<<<b->dev.n_items, 128, 0, stream>>>(b->pair->in->dev, b->pair->tg->dev, b->pair->d_in_overlap, b->dev);
+  OCF_LAUNCHED();
+  g_prof.end(0, stream);
+  return OCF_OK;
+}
+
 extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows,
                                     const uint8_t* keep_flags, int64_t n_flags, int pass_through,
                                     float aux_var_value, void* stream_) {
@@ -425,11 +486,8 @@ extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const 
   int64_t tc = 0;
   if (pass_through) tc = n_flags; else for (int64_t k = 0; k < n_flags; ++k) tc += keep_flags[k] == 0;
   b->target_count = tc;
-  if (b->dev.n_items > 0) {
-    k_gather_split<<<b->dev.n_items, 128, 0, stream>>>(store->dev, b->dev, pass_through ? 1 : 0);
-    OCF_LAUNCHED();
-  }
-  return OCF_OK;
+  b->pass_through = pass_through ? 1 : 0;
+  return launch_gather(b, stream);
 }
 
 extern "C" int ocf_batch_fill_fixed(ocf_batch* b, const ocf_pair* pair, const int32_t* row_ids, int32_t n_rows,
@@ -439,11 +497,14 @@ extern "C" int ocf_batch_fill_fixed(ocf_batch* b, const ocf_pair* pair, const in
   OCF_TRY(batch_stage(b, row_ids, n_rows, pair->in->h_rowptr, &pair->tg->h_rowptr, pair->in->n_rows, nullptr, -1, stream));
   b->dev.rowslot = nullptr; b->dev.tag = 0;
   b->mode = 2; b->store = pair->tg; b->aux_value = aux_var_value;
-  if (b->dev.n_items > 0) {
-    k_gather_fixed<<<b->dev.n_items, 128, 0, stream>>>(pair->in->dev, pair->tg->dev, pair->d_in_overlap, b->dev);
-    OCF_LAUNCHED();
-  }
-  return OCF_OK;
+  b->pair = pair;
+  return launch_gather(b, stream);
+}
+
+extern "C" int ocf_batch_regather(ocf_batch* b, void* stream_) {
+  OCF_REQUIRE(b, "ocf_batch_regather: null argument");
+  if (b->mode == 0) return fail(OCF_ERR_STATE, "ocf_batch_regather: the batch has not been filled");
+  return launch_gather(b, as_stream(stream_));
 }
 
 extern "C" int ocf_batch_info(const ocf_batch* b, int64_t info[5]) {
@@ -770,9 +831,11 @@ static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
   const BatchDev& bt = b->dev;
   const int hp0 = m->hp[0];
   if (bt.n_items > 0) {
+    g_prof.begin(1, st);
     OCF_NV_SWITCH(hp0, k_enc_fwd<NV><<<bt.n_items, 128, 0, st>>>(bt, m->layers[0].W, m->cfg.n_cols, m->nblk, m->bits,
                                                                 b->aux_value, reinterpret_cast<float4*>(m->P1)));
     OCF_LAUNCHED();
+    g_prof.end(1, st);
   }
   k_rowsum<<<bt.B, 128, 0, st>>>(reinterpret_cast<const float4*>(m->P1), bt.item_ptr, hp0 / 4,
                                  reinterpret_cast<float4*>(m->zsum[0]), nullptr, nullptr);
@@ -826,6 +889,7 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   const double bn = (double)rows_total * (double)m->cfg.n_cols_total;
   const float gscale = (float)((m->cfg.loss == OCF_LOSS_MSE ? 2.0 : 1.0) / bn);
   if (bt.n_items > 0) {
+    g_prof.begin(2, st);
     if (training) {
       OCF_NV_SWITCH(hpt, k_dec_fwd<NV, true><<<bt.n_items, 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, b->aux_value, gscale,
                                                                           m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2), m->itemstats, dense_out, m->cfg.n_cols));
@@ -834,6 +898,7 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
                                                                            m->cfg.loss, nullptr, nullptr, m->itemstats, dense_out, m->cfg.n_cols));
     }
     OCF_LAUNCHED();
+    g_prof.end(2, st);
   }
   if (training) {
     k_rowsum<<<B, 128, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, hpt / 4,
@@ -922,11 +987,13 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
       return OCF_OK;
     };
     const int hpd = m->hp[L - 1], hpe = m->hp[0];
+    g_prof.begin(3, st);
     if (hpd == hpe) OCF_TRY(launch(hpd, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0));
     else {
       if (dec.trainable) OCF_TRY(launch(hpd, 1, 0));
       if (enc.trainable) OCF_TRY(launch(hpe, 0, 1));
     }
+    g_prof.end(3, st);
   }
   m->iterations += 1;
   return launch_metrics(m, B, args, n_reg, st);
@@ -1001,7 +1068,9 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   float* dst = out;
   if (!out_is_device) { OCF_TRY(ensure_dense(m)); dst = m->dense_out; }
   GemmEpi ep{}; ep.kind = EPI_BIAS_COL; ep.C = dst; ep.ldc = m->cfg.n_cols; ep.aux0 = m->layers[L].b;
+  g_prof.begin(4, st);
   OCF_TRY(launch_gemm(false, true, m->act[L - 1], m->hp[L - 1], m->layers[L].W, m->hp[L - 1], B, m->cfg.n_cols, m->hp[L - 1], ep, st));
+  g_prof.end(4, st);
   if (!out_is_device) {
     OCF_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * (size_t)B * m->cfg.n_cols, cudaMemcpyDeviceToHost, st));
     OCF_CUDA(cudaStreamSynchronize(st));
