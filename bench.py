@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Headline benchmark: training ratings/s of the autoencoder hot path on synthetic data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ml10m] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of `batch_size` rows (train.py:30: 128):
+K1 gather -> K2 encoder -> K3 decoder + masked loss + gradient -> K4 fused backward/optimizer.
+A "rating" is one stored rating of the batch's rows (each is read, split into input/target by its
+keep flag and consumed by the step).
+
+  value  device-timed (CUDA events) over K steps whose row ids and keep flags are already
+         resident in HBM; the working set (weights + optimizer state + store) is far larger than
+         L2 for the default workload, so no explicit flush is needed (config.l2 says which)
+  e2e    the same K steps through the public API (`data_reader.data_gen` -> `model.train_on_batch`):
+         host RNG replay + pinned staging + H2D of row ids/flags + kernels + D2H of the metrics,
+         every step, wall-clock between device synchronisations
+  roofline       per-kernel CUDA-event times of a third, instrumented pass; the dominant kernel's
+                 algorithmic bytes / time against MEASURED_PEAKS.json
+  cpu_baseline   the oracle port of the reference (per-rating Python batch loop + dense NumPy
+                 model step) on the host cores, bounded sample
+`--impl reference` times that CPU port alone as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs / SURVEY.md section 8(d). reverse=True: rows are items, columns users.
+    "ml1m": dict(shape="ml1m", reverse=True, layers=1, hidden=500, act="sigmoid", aux=None, sparsity=[1.0, 1.0],
+                 pass_through=True, opt=("adagrad", 0.005), dropout=0.2, aux_value=-1),
+    "jester": dict(shape="jester", reverse=False, layers=2, hidden=256, act="tanh", aux="causal", sparsity=[0.5, 0.5],
+                   pass_through=False, opt=("rmsprop", 0.001), dropout=None, aux_value=1),
+    "ml10m": dict(shape="ml10m", reverse=True, layers=1, hidden=512, act="sigmoid", aux="dropout", sparsity=[0.5, 0.5],
+                  pass_through=False, opt=("adagrad", 0.005), dropout=0.2, aux_value=-1),
+    "ml10m_users": dict(shape="ml10m", reverse=False, layers=1, hidden=512, act="sigmoid", aux="dropout",
+                        sparsity=[0.5, 0.5], pass_through=False, opt=("adagrad", 0.005), dropout=0.2, aux_value=-1),
+    "ml20m": dict(shape="ml20m", reverse=False, layers=2, hidden=[1000, 500], act="sigmoid", aux=None,
+                  sparsity=[0.5, 0.5], pass_through=False, opt=("adagrad", 0.005), dropout=0.2, aux_value=-1),
+    "netflix": dict(shape="netflix", reverse=True, layers=1, hidden=1000, act="sigmoid", aux=None, sparsity=[1.0, 1.0],
+                    pass_through=True, opt=("adagrad", 0.005), dropout=0.2, aux_value=-1),
+    "small": dict(shape="small", reverse=True, layers=1, hidden=64, act="sigmoid", aux=None, sparsity=[1.0, 1.0],
+                  pass_through=True, opt=("adagrad", 0.005), dropout=0.2, aux_value=-1),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_dataset(w, seed=0):
+    """The workload's synthetic FixedSplit; cached under /tmp so the N=1,2,4,8 runs of one box
+    (and the reference arm) do not each spend ~20 s regenerating it."""
+    import pickle
+    from omnidirectional_collaborative_filtering_b200 import synthetic
+    path = "/tmp/ocf_b200_%s_%d_%d.pkl" % (w["shape"], int(w["reverse"]), seed)
+    if os.path.exists(path):
+        try:
+            with open(path, "rb") as f:
+                return pickle.load(f)
+        except Exception:
+            pass
+    fs = synthetic.make_fixed_split(w["shape"], reverse_user_item_data=w["reverse"], seed=seed)
+    try:
+        tmp = path + ".%d.tmp" % os.getpid()
+        with open(tmp, "wb") as f:
+            pickle.dump(fs, f, protocol=4)
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return fs
+
+
+def touched(batch, k_mask_blocks):
+    """Unique catalogue columns the batch touches as inputs / as targets (for algorithmic bytes)."""
+    csr = batch.source.csr
+    cols = np.concatenate([csr.col[csr.rowptr[r]:csr.rowptr[r + 1]] for r in batch.rows])
+    f = batch.flags.astype(bool)
+    u_in = np.unique(cols[f]).size
+    u_tg = np.unique(cols if batch.pass_through else cols[~f]).size
+    return u_in, u_tg, int(f.sum()), int(cols.size if batch.pass_through else (~f).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port (reference algorithm, per-rating Python loop + dense NumPy)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(w, fs, batch_size, steps, warmup, budget_s=None, seed=0):
+    from oracle import ref_batches, ref_model
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    rs = np.random.RandomState(seed)
+    n_batches = steps + warmup
+    rows = rs.permutation(fs.train.n_rows)[:n_batches * batch_size]
+    n_batches = min(n_batches, len(rows) // batch_size)
+    rows = rows[:n_batches * batch_size]
+    train = {}
+
+    def add_rows(batch_rows):                             # dict-of-lists form, built lazily per batch (untimed)
+        for r in batch_rows:
+            c, v = fs.train.row(int(r))
+            train[str(int(r))] = [[int(ci), float(vi)] for ci, vi in zip(c, v)]
+
+    data = ref_batches.RefData(fs.n_cols, fs.train.n_rows, list(range(fs.n_cols)), eval_mode="fixed_split",
+                               train=train, valid=({}, {}), test=({}, {}))
+    order = [str(int(r)) for r in rows]
+    aux = w["aux"]
+    model = ref_model.RefModel(w["layers"], w["hidden"], fs.n_cols, batch_size, dense_activation=w["act"],
+                               use_causal_info=aux is not None, use_both_masks=aux == "both",
+                               dropout_probability=w["dropout"], dtype=np.float32, rng=np.random.RandomState(1))
+    model.compile(ref_model.RefOptimizer(w["opt"][0], lr=w["opt"][1]), "mean_squared_error", rating_range=fs.rating_range)
+    rng = np.random.RandomState(seed + 1)
+    t_batch = t_model = 0.0
+    ratings = 0
+    done = 0
+    t_start = time.perf_counter()
+    for i in range(n_batches):
+        add_rows(rows[i * batch_size:(i + 1) * batch_size])
+        t0 = time.perf_counter()
+        arrays = ref_batches.split_batch_loop(data, order, batch_size, i * batch_size, w["sparsity"], w["aux_value"],
+                                              w["pass_through"], rng)
+        feed = ref_batches.feed_list(arrays, aux)
+        t1 = time.perf_counter()
+        model.train_on_batch(feed, arrays[3])
+        t2 = time.perf_counter()
+        if i >= warmup:
+            t_batch += t1 - t0
+            t_model += t2 - t1
+            ratings += sum(len(train[k]) for k in order[i * batch_size:(i + 1) * batch_size])
+            done += 1
+            if budget_s is not None and done >= 2 and time.perf_counter() - t_start > budget_s:
+                break
+    total = t_batch + t_model
+    return {"value": ratings / total if total > 0 else 0.0, "unit": "ratings/s", "cores": int(threads), "kind": "port",
+            "sample": "%d steps of %d rows (%d ratings) of the same workload; batch build %.1f%% / model step %.1f%% of the time"
+                      % (done, batch_size, ratings, 100 * t_batch / max(total, 1e-9), 100 * t_model / max(total, 1e-9)),
+            "ms_per_step": 1e3 * total / max(done, 1), "steps": done,
+            "overlapped_value": ratings / max(t_batch, t_model, 1e-9)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ml10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch-size", type=int, default=128)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = args.batch_size
+    cfg = {"workload": "%s-shaped synthetic (%s), rows=%s, L=%d, H=%s, %s, aux=%s, train_sparsity=%s, pass_through=%s, %s lr=%g, dropout=%s, batch_size=%d"
+           % (args.workload, w["shape"], "items" if w["reverse"] else "users", w["layers"], w["hidden"], w["act"], w["aux"],
+              w["sparsity"], w["pass_through"], w["opt"][0], w["opt"][1], w["dropout"], B)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        fs = make_dataset(w)
+        warm = max(1, min(args.warmup, 2))
+        res = cpu_reference(w, fs, B, args.steps, warm, budget_s=150.0)
+        line = {"impl": "reference", "metric": "train ratings/sec", "value": res["value"], "unit": "ratings/s",
+                "n_gpus": args.gpus, "steps": res["steps"], "warmup": warm, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg, "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": "ratings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    from omnidirectional_collaborative_filtering_b200 import _lib, optimizers
+    from omnidirectional_collaborative_filtering_b200.data_reader import data_reader
+    from omnidirectional_collaborative_filtering_b200.model import omni_model
+    from omnidirectional_collaborative_filtering_b200.store import DeviceBatch
+
+    if world > 1:
+        from omnidirectional_collaborative_filtering_b200 import dist as ocf_dist
+        return ocf_dist.bench_main(args, w, cfg, rank, world)
+
+    torch.cuda.set_device(0)
+    lib = _lib.lib()
+    fs = make_dataset(w)
+    rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs)
+    aux = w["aux"]
+    np.random.seed(0)
+    om = omni_model(w["layers"], w["hidden"], fs.n_cols, B, dense_activation=w["act"], use_causal_info=aux is not None,
+                    use_both_masks=aux == "both", dropout_probability=w["dropout"], auxilliary_mask_type=aux)
+    m = om.model
+    opt = {"adagrad": optimizers.Adagrad, "rmsprop": optimizers.RMSprop, "adam": optimizers.Adam}[w["opt"][0]](lr=w["opt"][1])
+    m.compile(opt, "mean_squared_error", rating_range=fs.rating_range)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def gen():
+        return rd.data_gen(B, w["sparsity"], "train", True, aux, w["aux_value"], pass_through_input_training=w["pass_through"])
+
+    # ---- value: K steps on batches whose row ids / flags are resident in HBM --------------------
+    g = gen()
+    plans = []
+    while len(plans) < K + W:
+        b = next(g)
+        if b is None:
+            g = gen()
+            continue
+        plans.append(b)
+    m._ensure(B, max(p.n_entries for p in plans), aux)
+    resident = []
+    for p in plans:
+        dev = DeviceBatch(p.n_rows, p.n_entries)
+        dev.fill_split(p.source, p.rows, p.flags, p.pass_through, p.aux_value, None)
+        resident.append(dev)
+    import ctypes as C
+    sargs = _lib.StepArgs()
+    sargs.dropout_seed = om.dropout_seed
+
+    def device_steps(devs, first_step):
+        for k, dev in enumerate(devs):
+            sargs.step = first_step + k
+            _lib.check(lib.ocf_batch_regather(dev.handle, None))
+            _lib.check(lib.ocf_train_step(m._handle, dev.handle, C.byref(sargs), None, None))
+
+    device_steps(resident[:W], 0)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.ocf_kernel_launches()
+    torch.cuda.synchronize()
+    e0.record()
+    device_steps(resident[W:], W)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.ocf_kernel_launches() - launches0
+    ms = e0.elapsed_time(e1)
+    ratings = sum(p.n_entries for p in plans[W:])
+    value = ratings / (ms * 1e-3)
+
+    # ---- roofline: instrumented pass over the same resident batches ------------------------------
+    lib.ocf_profile_reset()
+    lib.ocf_profile_enable(1)
+    device_steps(resident[W:], W + K)
+    torch.cuda.synchronize()
+    lib.ocf_profile_enable(0)
+    tag_names = ["k_gather_split (K1)", "k_enc_fwd (K2)", "k_dec_fwd (K3)", "k_col_scan (K4a)", "k_row_update (K4b)"]
+    tag_ms = []
+    for t in (0, 1, 2, 3, 5):
+        tot, cnt = C.c_double(), C.c_int64()
+        _lib.check(lib.ocf_profile_read(t, C.byref(tot), C.byref(cnt)))
+        tag_ms.append(tot.value / max(cnt.value, 1))
+    H = w["hidden"] if isinstance(w["hidden"], int) else w["hidden"]
+    h_enc = H if isinstance(H, int) else H[0]
+    h_dec = H if isinstance(H, int) else H[-1]
+    k_in = 1 + (1 if aux in ("dropout", "both") else 0)          # encoder blocks selected by the input bit
+    k_obs = (1 if aux in ("causal", "both") else 0)
+    st = np.array([touched(p, 0) for p in plans[W:]], dtype=np.float64).mean(axis=0)   # u_in, u_tg, n_in, n_tg
+    u_obs = np.mean([np.unique(np.concatenate([p.source.csr.col[p.source.csr.rowptr[r]:p.source.csr.rowptr[r + 1]]
+                                               for r in p.rows])).size for p in plans[W:W + 8]])
+    n_all = ratings / K
+    state_words = {"sgd": 2, "adagrad": 4, "rmsprop": 4, "adam": 6}[w["opt"][0]]
+    alg = [
+        9.0 * n_all * 2,                                                       # K1: read col,val,flag + write col,val,code
+        4.0 * h_enc * (st[2] * k_in + n_all * k_obs),                          # K2: one Wenc row per contributing entry
+        4.0 * h_dec * st[3],                                                   # K3: one WdecT row per target entry
+        4.0 * fs.train.nnz + 21.0 * n_all,                                     # K4a: CSC row ids of the store + the batch entries it matches
+        4.0 * state_words * (h_dec * st[1] + h_enc * (st[0] * k_in + u_obs * k_obs)),   # K4b: W + state, read + write, touched rows
+    ]
+    peak, peak_src = peaks()
+    dom = int(np.argmax(tag_ms))
+    kernels = {tag_names[t]: {"ms": tag_ms[t], "algorithmic_bytes": alg[t], "GB/s": alg[t] / (tag_ms[t] * 1e-3) / 1e9 if tag_ms[t] > 0 else None}
+               for t in range(5)}
+    achieved = alg[dom] / (tag_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": tag_names[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": tag_ms[dom] / (ms / K)}
+
+    # ---- e2e: the public API, host buffers in, metrics out, every step ---------------------------
+    g = gen()
+    for _ in range(W):
+        b = next(g)
+        if b is None:
+            g = gen(); b = next(g)
+        m.train_on_batch(b, sync=True)
+    torch.cuda.synchronize()
+    h2d = 0
+    e_ratings = 0
+    prev = None
+    t0 = time.perf_counter()
+    for _ in range(K):
+        b = next(g)                               # host: RNG replay -> row ids + keep flags
+        if b is None:
+            g = gen(); b = next(g)
+        m.train_on_batch(b, sync=False)           # pinned staging + H2D(row ids, flags) + kernels + D2H(metrics)
+        step_id = m.steps_logged() - 1
+        if prev is not None:
+            m.wait_metrics(prev)                  # read step i-1's result while step i runs
+        prev = step_id
+        e_ratings += b.n_entries
+        h2d += b._device.info()["h2d_bytes"]
+    m.wait_metrics(prev)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    line = {"metric": "train ratings/sec", "value": value, "unit": "ratings/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(cfg, l2="no flush: weights+optimizer state+store (%.0f MB) exceed the 126 MB L2"
+                                                % ((sum(np.prod(s) for s in om.weight_shapes()) * 4 * state_words / 2 + fs.train.nnz * 16) / 1e6),
+                                                ratings_per_step=ratings / K),
+            "clocks": clocks,
+            "e2e": {"value": e_ratings / e2e_s, "unit": "ratings/s", "h2d_bytes_per_step": h2d / K,
+                    "d2h_bytes_per_step": 4 * _lib.N_METRICS, "ms_per_step": 1e3 * e2e_s / K},
+            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference(w, fs, B, 1000, 1, budget_s=args.cpu_seconds).items()
+                                if k in ("value", "unit", "cores", "kind", "sample", "overlapped_value")}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -189,6 +189,10 @@ int ocf_score(ocf_model* model, ocf_batch* batch, float* out, int out_is_device,
  * (synchronises `stream`). The log keeps the last 4096 steps. */
 int ocf_model_read_metrics(ocf_model* model, int64_t first, int32_t count, float* host,
                            void* stream);
+/* Waits for one step (one of the last 64) to finish and copies its metric record; later steps
+ * already enqueued keep running. Every step's record is copied to pinned host memory right
+ * behind its kernels, so this is the per-step device->host read of a pipelined caller. */
+int ocf_model_wait_metrics(ocf_model* model, int64_t step, float* host);
 /* Number of steps logged so far (train + eval). */
 int64_t ocf_model_steps_logged(const ocf_model* model);
 

@@ -121,6 +121,11 @@ struct ocf_model {
   float* h_rec = nullptr;         // pinned
   int* d_err = nullptr;
   int64_t steps_logged = 0;
+  cudaEvent_t step_ev[64] = {nullptr};
+  uint32_t* col_matches = nullptr;
+  int4* col_tasks = nullptr;
+  int* col_counters = nullptr;
+  int sm_count = 148;
   // optimizer
   int opt_kind = OCF_OPT_ADAGRAD;
   float lr = 0.005f, p1 = 0.9f, p2 = 0.999f, eps = 1e-8f, decay = 0.f;
@@ -277,6 +282,17 @@ extern "C" int ocf_store_create(int64_t n_rows, int64_t n_cols, const int64_t* r
         (nnz && cudaMemcpy(d_cj, cj.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice) != cudaSuccess))
       return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
     s->dev.colptr = d_colptr; s->dev.crow = d_crow; s->dev.cj = d_cj;
+    // longest columns first: the scan's tail is its longest column, start those early
+    std::vector<int32_t> order((size_t)n_cols);
+    for (int64_t c = 0; c < n_cols; ++c) order[c] = (int32_t)c;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+      return colptr[x + 1] - colptr[x] > colptr[y + 1] - colptr[y];
+    });
+    int32_t* d_order = nullptr;
+    if ((st = s->mem.get(&d_order, (size_t)n_cols))) return bail(st);
+    if (cudaMemcpy(d_order, order.data(), sizeof(int32_t) * n_cols, cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
+    s->dev.col_order = d_order;
     s->has_csc = true;
   }
   *out = s;
@@ -330,6 +346,13 @@ extern "C" int ocf_pair_destroy(ocf_pair* p) {
 // ============================================================================================
 // batch
 // ============================================================================================
+// Upper bound of the work items of any batch within (max_rows, max_entries): pick_chunk() keeps
+// the chunk length >= ceil(entries / TARGET_ITEMS), so items <= TARGET_ITEMS + rows.
+constexpr int64_t TARGET_ITEMS = 148 * 6;
+static int max_items_for(int max_rows, int64_t max_entries) {
+  return (int)std::min<int64_t>(max_entries / 32 + max_rows + 1, TARGET_ITEMS + max_rows + 1);
+}
+
 static size_t staging_layout(int B, int n_items, int64_t n_entries, size_t off[6]) {
   size_t o = 0;
   off[0] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // row_ids
@@ -348,7 +371,7 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
   OCF_REQUIRE(max_entries >= 0 && max_entries < (int64_t(1) << 31), "ocf_batch_create: bad max_entries");
   ocf_batch* b = new ocf_batch();
   b->max_rows = max_rows; b->max_entries = max_entries;
-  b->max_items = (int)(max_entries / 32 + max_rows + 1);
+  b->max_items = max_items_for(max_rows, max_entries);
   size_t off[6];
   b->staging_bytes = staging_layout(max_rows, b->max_items, max_entries, off);
   auto bail = [&](int code) { b->mem.release(); if (b->h_staging) cudaFreeHost(b->h_staging); if (b->copied) cudaEventDestroy(b->copied); delete b; return code; };
@@ -378,10 +401,9 @@ extern "C" int ocf_batch_destroy(ocf_batch* b) {
 // Work items: chunks of <= CH ratings of one row, CH sized so that the row-centric kernels get
 // a few CTAs per SM whatever the batch looks like.
 static int pick_chunk(int64_t n_entries) {
-  const int64_t target_items = 148 * 6;
-  int64_t ch = (n_entries + target_items - 1) / target_items;
+  int64_t ch = (n_entries + TARGET_ITEMS - 1) / TARGET_ITEMS;
   ch = (int64_t)align_up((size_t)std::max<int64_t>(ch, 1), 32);
-  return (int)std::min<int64_t>(std::max<int64_t>(ch, 32), 512);
+  return (int)std::max<int64_t>(ch, 32);
 }
 
 static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const std::vector<int64_t>& rp_a,
@@ -558,7 +580,7 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   m->dense_out = nullptr;
   m->cfg.max_rows = max_rows;
   m->cfg.max_entries = max_entries;
-  m->max_items = (int)(max_entries / 32 + max_rows + 1);
+  m->max_items = max_items_for(max_rows, max_entries);
   const int L = m->L, Bm = max_rows;
   m->zsum.assign(L, nullptr); m->act.assign(L, nullptr); m->h.assign(L, nullptr);
   m->dscale.assign(L, nullptr); m->dz.assign(L, nullptr);
@@ -578,6 +600,7 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   OCF_TRY(ws.get(&m->rowstats, (size_t)Bm * ROWSTAT_W, true));
   OCF_TRY(ws.get(&m->dy, (size_t)max_entries, true));
   OCF_TRY(ws.get(&m->dh_top, (size_t)Bm * m->hp[L - 1], true));
+  OCF_TRY(ws.get(&m->col_matches, (size_t)max_entries * 3));
   return OCF_OK;
 }
 
@@ -598,7 +621,6 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   m->cfg = *cfg;
   m->L = cfg->n_layers;
   aux_bits(cfg->aux, m->nblk, m->bits);
-  m->max_items = (int)(cfg->max_entries / 32 + cfg->max_rows + 1);
   const int L = m->L, N = cfg->n_cols, Bm = cfg->max_rows;
   for (int l = 0; l < L; ++l) m->hp.push_back(pad_h(cfg->widths[l]));
   m->layers.resize(L + 1);
@@ -614,11 +636,16 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   }
   if (st) return bail(st);
   if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_log, (size_t)LOG_CAP * LOG_W, true)) ||
-      (st = m->mem.get(&m->d_err, 1, true)))
+      (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) ||
+      (st = m->mem.get(&m->col_counters, 2, true)))
     return bail(st);
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev); if (m->sm_count <= 0) m->sm_count = 148; }
   if ((st = alloc_workspace(m, cfg->max_rows, cfg->max_entries))) return bail(st);
   if (cudaMallocHost(reinterpret_cast<void**>(&m->h_rec), sizeof(float) * LOG_CAP * LOG_W) != cudaSuccess)
     return bail(fail(OCF_ERR_NOMEM, "ocf_model_create: pinned allocation failed"));
+  for (int k = 0; k < 64; ++k)
+    if (cudaEventCreateWithFlags(&m->step_ev[k], cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(OCF_ERR_CUDA, "ocf_model_create: event creation failed"));
   *out = m;
   st = ocf_model_set_optimizer(m, OCF_OPT_ADAGRAD, 0.005f, 0.9f, 0.999f, 1e-8f, 0.f);   // train.py:50-51
   if (st) { *out = nullptr; return bail(st); }
@@ -629,6 +656,7 @@ extern "C" int ocf_model_destroy(ocf_model* m) {
   if (m) {
     m->mem.release(); m->opt_mem.release(); m->dense_mem.release(); m->ws_mem.release();
     if (m->h_rec) cudaFreeHost(m->h_rec);
+    for (int k = 0; k < 64; ++k) if (m->step_ev[k]) cudaEventDestroy(m->step_ev[k]);
     delete m;
   }
   return OCF_OK;
@@ -837,8 +865,8 @@ static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
     OCF_LAUNCHED();
     g_prof.end(1, st);
   }
-  k_rowsum<<<bt.B, 128, 0, st>>>(reinterpret_cast<const float4*>(m->P1), bt.item_ptr, hp0 / 4,
-                                 reinterpret_cast<float4*>(m->zsum[0]), nullptr, nullptr);
+  k_rowsum<<<bt.B, hp0, (size_t)hp0 * 16, st>>>(reinterpret_cast<const float4*>(m->P1), bt.item_ptr, hp0 / 4,
+                                                reinterpret_cast<float4*>(m->zsum[0]), nullptr, nullptr);
   OCF_LAUNCHED();
   return OCF_OK;
 }
@@ -901,10 +929,10 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
     g_prof.end(2, st);
   }
   if (training) {
-    k_rowsum<<<B, 128, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, hpt / 4,
-                                reinterpret_cast<float4*>(m->dh_top), m->itemstats, m->rowstats);
+    k_rowsum<<<B, hpt, (size_t)hpt * 16, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, hpt / 4,
+                                               reinterpret_cast<float4*>(m->dh_top), m->itemstats, m->rowstats);
   } else {
-    k_rowsum<<<B, 128, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, 0, nullptr, m->itemstats, m->rowstats);
+    k_rowsum<<<B, 32, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, 0, nullptr, m->itemstats, m->rowstats);
   }
   OCF_LAUNCHED();
   return OCF_OK;
@@ -916,6 +944,11 @@ static int launch_metrics(ocf_model* m, int B, const ocf_step_args* args, int n_
   k_metrics<<<1, 32, 0, st>>>(m->rowstats, B, (float)rows_total, (float)m->cfg.n_cols_total, m->cfg.rating_range,
                               m->cfg.loss, m->regparts, n_reg, m->cfg.l2 >= 0.f ? m->cfg.l2 : 0.f, rec);
   OCF_LAUNCHED();
+  // every step's record goes back to pinned host memory right behind its kernels; readers wait
+  // on the step's event instead of the whole stream
+  float* hrec = m->h_rec + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
+  OCF_CUDA(cudaMemcpyAsync(hrec, rec, sizeof(float) * LOG_W, cudaMemcpyDeviceToHost, st));
+  OCF_CUDA(cudaEventRecord(m->step_ev[m->steps_logged % 64], st));
   m->steps_logged += 1;
   return OCF_OK;
 }
@@ -930,6 +963,23 @@ static int launch_reg(ocf_model* m, cudaStream_t st) {
   return N_REGPART * (m->L + 1);
 }
 
+template <int NV>
+static int launch_row_update_nv(int kind, int grid, const RowArgs& r, cudaStream_t st) {
+  switch (kind) {
+    case OCF_OPT_SGD: k_row_update<NV, OCF_OPT_SGD><<<grid, 256, 0, st>>>(r); break;
+    case OCF_OPT_ADAGRAD: k_row_update<NV, OCF_OPT_ADAGRAD><<<grid, 256, 0, st>>>(r); break;
+    case OCF_OPT_RMSPROP: k_row_update<NV, OCF_OPT_RMSPROP><<<grid, 256, 0, st>>>(r); break;
+    default: k_row_update<NV, OCF_OPT_ADAM><<<grid, 256, 0, st>>>(r); break;
+  }
+  OCF_LAUNCHED();
+  return OCF_OK;
+}
+
+static int launch_row_update(int hp, int kind, int grid, const RowArgs& r, cudaStream_t st) {
+  OCF_NV_SWITCH(hp, return launch_row_update_nv<NV>(kind, grid, r, st));
+  return OCF_OK;
+}
+
 // phase 3 (training): backward through the hidden layers, fused updates, metrics
 static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* args, cudaStream_t st) {
   const BatchDev& bt = b->dev;
@@ -941,7 +991,7 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   {
     const int l = L - 1;
     Layer& ly = m->layers[l];
-    k_dz_bias<<<(m->hp[l] + 127) / 128, 128, 0, st>>>(m->dh_top, m->act[l], drop ? m->dscale[l] : nullptr, B, m->hp[l],
+    k_dz_bias<<<m->hp[l] / 32, 256, 0, st>>>(m->dh_top, m->act[l], drop ? m->dscale[l] : nullptr, B, m->hp[l],
                                                      m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt, ly.trainable ? 1 : 0);
     OCF_LAUNCHED();
   }
@@ -952,7 +1002,7 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     ep.aux1 = drop ? m->dscale[l - 1] : nullptr; ep.act = m->cfg.activation;
     OCF_TRY(launch_gemm(false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
     Layer& lo = m->layers[l - 1];
-    k_dz_bias<<<(m->hp[l - 1] + 127) / 128, 128, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
+    k_dz_bias<<<m->hp[l - 1] / 32, 256, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
                                                          m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0);
     OCF_LAUNCHED();
     if (ly.trainable) {
@@ -965,47 +1015,55 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   // catalogue-wide kernels: encoder rows and decoder rows of every touched column
   Layer& enc = m->layers[0];
   Layer& dec = m->layers[L];
-  if ((enc.trainable || dec.trainable) && (bt.n_entries > 0 || opt.dense)) {
+  const int hpd = m->hp[L - 1], hpe = m->hp[0];
+  auto col_update = [&](int do_dec, int do_enc, int hpx) -> int {
+    if (!do_dec && !do_enc) return OCF_OK;
+    OCF_CUDA(cudaMemsetAsync(m->col_counters, 0, 2 * sizeof(int), st));
     ColArgs a{};
     a.s = b->store->dev; a.bt = bt; a.dy = m->dy;
-    a.hdec = drop ? m->h[L - 1] : m->act[L - 1]; a.dz0 = m->dz[0];
-    a.WdecT = dec.W; a.Wd_s1 = dec.Ws1; a.Wd_s2 = dec.Ws2; a.bdec = dec.b; a.bd_s1 = dec.bs1; a.bd_s2 = dec.bs2;
-    a.Wenc = enc.W; a.We_s1 = enc.Ws1; a.We_s2 = enc.Ws2;
-    a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.aux_val = b->aux_value; a.opt = opt;
-    a.err_flag = m->d_err;
+    a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.dense = opt.dense;
+    a.do_dec = do_dec; a.do_enc = do_enc;
+    a.err_flag = m->d_err; a.matches = m->col_matches; a.tasks = m->col_tasks; a.counters = m->col_counters;
     a.list_cap = 2 * (int)align_up((size_t)B, 32) + 32;
-    int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (96 * 1024) / ((size_t)a.list_cap * 12)));
+    const int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (96 * 1024) / ((size_t)a.list_cap * 12)));
     const size_t smem = (size_t)warps * a.list_cap * 12;
-    const int grid = (m->cfg.n_cols + warps - 1) / warps;
-    auto launch = [&](int hpx, int do_dec, int do_enc) -> int {
-      a.do_dec = do_dec; a.do_enc = do_enc;
-      OCF_NV_SWITCH(hpx, {
-        if (smem > 48 * 1024) OCF_CUDA(cudaFuncSetAttribute(k_col_update<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_col_update<NV><<<grid, warps * 32, smem, st>>>(a);
-      });
-      OCF_LAUNCHED();
-      return OCF_OK;
-    };
-    const int hpd = m->hp[L - 1], hpe = m->hp[0];
+    if (smem > 48 * 1024) OCF_CUDA(cudaFuncSetAttribute(k_col_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_prof.begin(3, st);
-    if (hpd == hpe) OCF_TRY(launch(hpd, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0));
-    else {
-      if (dec.trainable) OCF_TRY(launch(hpd, 1, 0));
-      if (enc.trainable) OCF_TRY(launch(hpe, 0, 1));
-    }
+    k_col_scan<<<(m->cfg.n_cols + warps - 1) / warps, warps * 32, smem, st>>>(a);
+    OCF_LAUNCHED();
     g_prof.end(3, st);
+    RowArgs r{};
+    r.matches = m->col_matches; r.tasks = m->col_tasks; r.counters = m->col_counters;
+    r.hdec = drop ? m->h[L - 1] : m->act[L - 1]; r.dz0 = m->dz[0];
+    r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
+    r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
+    r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.aux_val = b->aux_value; r.opt = opt;
+    g_prof.begin(5, st);
+    OCF_TRY(launch_row_update(hpx, opt.kind, m->sm_count * 6, r, st));
+    g_prof.end(5, st);
+    return OCF_OK;
+  };
+  if (bt.n_entries > 0 || opt.dense) {
+    // decoder and encoder rows share one padded width in the reference's architectures (one
+    // num_hidden_units): one scan feeds both. A width list with different ends scans twice.
+    if (hpd == hpe) OCF_TRY(col_update(dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd));
+    else { OCF_TRY(col_update(dec.trainable ? 1 : 0, 0, hpd)); OCF_TRY(col_update(0, enc.trainable ? 1 : 0, hpe)); }
   }
   m->iterations += 1;
   return launch_metrics(m, B, args, n_reg, st);
 }
 
-static int finish_step(ocf_model* m, float* host_metrics, cudaStream_t st) {
-  if (host_metrics == nullptr) return OCF_OK;
-  const float* rec = m->d_log + (size_t)((m->steps_logged - 1) % LOG_CAP) * LOG_W;
-  OCF_CUDA(cudaMemcpyAsync(m->h_rec, rec, sizeof(float) * LOG_W, cudaMemcpyDeviceToHost, st));
-  OCF_CUDA(cudaStreamSynchronize(st));
-  std::memcpy(host_metrics, m->h_rec, sizeof(float) * LOG_W);
+extern "C" int ocf_model_wait_metrics(ocf_model* m, int64_t step, float* host) {
+  OCF_REQUIRE(m && host, "ocf_model_wait_metrics: null argument");
+  OCF_REQUIRE(step >= 0 && step < m->steps_logged && step + 64 > m->steps_logged, "ocf_model_wait_metrics: step not among the last 64");
+  OCF_CUDA(cudaEventSynchronize(m->step_ev[step % 64]));
+  std::memcpy(host, m->h_rec + (size_t)(step % LOG_CAP) * LOG_W, sizeof(float) * LOG_W);
   return OCF_OK;
+}
+
+static int finish_step(ocf_model* m, float* host_metrics, cudaStream_t) {
+  if (host_metrics == nullptr) return OCF_OK;
+  return ocf_model_wait_metrics(m, m->steps_logged - 1, host_metrics);
 }
 
 extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
@@ -1083,14 +1141,12 @@ extern "C" int ocf_model_read_metrics(ocf_model* m, int64_t first, int32_t count
   OCF_REQUIRE(count >= 0 && count <= LOG_CAP && first >= 0 && first + count <= m->steps_logged &&
               first + LOG_CAP >= m->steps_logged, "ocf_model_read_metrics: range not in the log");
   cudaStream_t st = as_stream(stream_);
-  for (int32_t k = 0; k < count; ++k) {
-    const float* rec = m->d_log + (size_t)((first + k) % LOG_CAP) * LOG_W;
-    OCF_CUDA(cudaMemcpyAsync(m->h_rec + (size_t)k * LOG_W, rec, sizeof(float) * LOG_W, cudaMemcpyDeviceToHost, st));
-  }
   int err = 0;
   OCF_CUDA(cudaMemcpyAsync(&err, m->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
   OCF_CUDA(cudaStreamSynchronize(st));
-  std::memcpy(host, m->h_rec, sizeof(float) * (size_t)count * LOG_W);
+  if (m->steps_logged > 0) OCF_CUDA(cudaEventSynchronize(m->step_ev[(m->steps_logged - 1) % 64]));
+  for (int32_t k = 0; k < count; ++k)
+    std::memcpy(host + (size_t)k * LOG_W, m->h_rec + (size_t)((first + k) % LOG_CAP) * LOG_W, sizeof(float) * LOG_W);
   if (err != 0) return fail(OCF_ERR_STATE, "a catalogue column matched more batch entries than the update kernel's list holds (rows repeat a column too often)");
   return OCF_OK;
 }

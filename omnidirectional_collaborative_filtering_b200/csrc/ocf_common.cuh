@@ -64,6 +64,7 @@ struct StoreDev {
   const int64_t* colptr;     // CSC: entries of column c are [colptr[c], colptr[c+1])
   const int32_t* crow;       //   row of the entry
   const int32_t* cj;         //   position of the entry inside its row
+  const int32_t* col_order;  //   columns sorted by length, longest first (scan schedule)
 };
 
 // Device view of one batch. The first group is uploaded by the host in one copy, the second
@@ -97,25 +98,38 @@ struct OptDev {
   int dense;         // 1: every parameter changes every step (RMSprop, Adam, L2)
 };
 
+// sqrt / divide of the update rules use the MUFU approximations (<= 2 ulp): the IEEE-rounded
+// versions cost ~5x the instructions and made the update kernel issue-bound (profiles/r01).
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <int KIND>
+__device__ __forceinline__ void opt_apply_k(const OptDev& o, float g, float& w, float& s1, float& s2) {
+  g = fmaf(o.l2x2, w, g);
+  if (KIND == OCF_OPT_SGD) {
+    w = fmaf(-o.lr, g, w);
+  } else if (KIND == OCF_OPT_ADAGRAD) {
+    s1 = fmaf(g, g, s1);
+    w -= __fdividef(o.lr * g, fast_sqrt(s1) + o.eps);
+  } else if (KIND == OCF_OPT_RMSPROP) {
+    s1 = fmaf(o.one_m_p1 * g, g, o.p1 * s1);
+    w -= __fdividef(o.lr * g, fast_sqrt(s1) + o.eps);
+  } else {  // Adam
+    s1 = fmaf(o.one_m_p1, g, o.p1 * s1);
+    s2 = fmaf(o.one_m_p2 * g, g, o.p2 * s2);
+    w -= __fdividef(o.lr * s1, fast_sqrt(s2) + o.eps);
+  }
+}
+
 __device__ __forceinline__ void opt_apply(const OptDev& o, float g, float& w, float& s1, float& s2) {
-  g += o.l2x2 * w;
   switch (o.kind) {
-    case OCF_OPT_SGD:
-      w -= o.lr * g;
-      break;
-    case OCF_OPT_ADAGRAD:
-      s1 += g * g;
-      w -= o.lr * g / (sqrtf(s1) + o.eps);
-      break;
-    case OCF_OPT_RMSPROP:
-      s1 = o.p1 * s1 + o.one_m_p1 * g * g;
-      w -= o.lr * g / (sqrtf(s1) + o.eps);
-      break;
-    default:  // Adam
-      s1 = o.p1 * s1 + o.one_m_p1 * g;
-      s2 = o.p2 * s2 + o.one_m_p2 * g * g;
-      w -= o.lr * s1 / (sqrtf(s2) + o.eps);
-      break;
+    case OCF_OPT_SGD: opt_apply_k<OCF_OPT_SGD>(o, g, w, s1, s2); break;
+    case OCF_OPT_ADAGRAD: opt_apply_k<OCF_OPT_ADAGRAD>(o, g, w, s1, s2); break;
+    case OCF_OPT_RMSPROP: opt_apply_k<OCF_OPT_RMSPROP>(o, g, w, s1, s2); break;
+    default: opt_apply_k<OCF_OPT_ADAM>(o, g, w, s1, s2); break;
   }
 }
 

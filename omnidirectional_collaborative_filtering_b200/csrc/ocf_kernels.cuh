@@ -167,20 +167,30 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
   }
 }
 
-// Sum of the work-item partials of each batch row, in item order. Also sums the per-item loss
-// statistics into per-row statistics when given.
-__global__ void __launch_bounds__(128)
+// Sum of the work-item partials of each batch row in a fixed order: the row's items are dealt
+// round-robin to 4 thread groups, the 4 group sums are added in group order. Also sums the
+// per-item loss statistics into per-row statistics when given. blockDim = 4 * hp4.
+__global__ void __launch_bounds__(1024)
 k_rowsum(const float4* __restrict__ P, const int32_t* __restrict__ item_ptr, int hp4,
          float4* __restrict__ out, const float* __restrict__ itemstats, float* __restrict__ rowstats) {
+  extern __shared__ float4 rs_smem[];      // [4][hp4]
   const int b = blockIdx.x;
   const int i0 = item_ptr[b], i1 = item_ptr[b + 1];
-  for (int u = threadIdx.x; u < hp4; u += blockDim.x) {
+  if (hp4 > 0) {
+    const int q = threadIdx.x / hp4, u = threadIdx.x - q * hp4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int it = i0; it < i1; ++it) {
+    for (int it = i0 + q; it < i1; it += 4) {
       const float4 p = P[(size_t)it * hp4 + u];
       s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
     }
-    out[(size_t)b * hp4 + u] = s;
+    rs_smem[q * hp4 + u] = s;
+    __syncthreads();
+    if (q == 0) {
+      const float4 a = rs_smem[hp4 + u], b2 = rs_smem[2 * hp4 + u], c2 = rs_smem[3 * hp4 + u];
+      s.x = ((s.x + a.x) + b2.x) + c2.x; s.y = ((s.y + a.y) + b2.y) + c2.y;
+      s.z = ((s.z + a.z) + b2.z) + c2.z; s.w = ((s.w + a.w) + b2.w) + c2.w;
+      out[(size_t)b * hp4 + u] = s;
+    }
   }
   if (itemstats != nullptr && threadIdx.x < ROWSTAT_W) {
     float s = 0.f;
@@ -315,26 +325,35 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
 }
 
 // dz = dh * dropout scale * act'(a) for one hidden layer, the bias gradient (column sum over the
-// batch in row order) and the bias update. One thread per hidden unit.
+// batch) and the bias update. One CTA per 32 hidden units; its 8 warps deal the batch rows
+// round-robin and their partial column sums are added in warp order.
 // dh_is_dz: the input already is dz (produced by the EPI_DZ GEMM epilogue).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float* __restrict__ dscale,
           int B, int HP, int act, int dh_is_dz, float* __restrict__ dz, float* __restrict__ bias,
           float* __restrict__ s1, float* __restrict__ s2, OptDev o, int trainable) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= HP) return;
+  __shared__ float part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * 32 + lane;
   float g = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const size_t k = (size_t)b * HP + u;
-    float d = dh[k];
-    if (!dh_is_dz) {
-      if (dscale != nullptr) d *= dscale[k];
-      d *= act_bwd(act, a[k]);
-      dz[k] = d;
+  if (u < HP) {
+    for (int b = warp; b < B; b += 8) {
+      const size_t k = (size_t)b * HP + u;
+      float d = dh[k];
+      if (!dh_is_dz) {
+        if (dscale != nullptr) d *= dscale[k];
+        d *= act_bwd(act, a[k]);
+        dz[k] = d;
+      }
+      g += d;
     }
-    g += d;
   }
-  if (trainable) {
+  part[warp][lane] = g;
+  __syncthreads();
+  if (warp == 0 && u < HP && trainable) {
+    g = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) g += part[w][lane];
     o.l2x2 = 0.f;                     // Keras regularises kernels only (model.py:66,82)
     float w = bias[u], t1 = s1 ? s1[u] : 0.f, t2 = s2 ? s2[u] : 0.f;
     opt_apply(o, g, w, t1, t2);
@@ -434,127 +453,181 @@ k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int 
 }
 
 // ============================================================================================
-// K4: weight-side products fused with the optimizer update. One warp per catalogue column c:
-//   1. scan the store's CSC list of c, keep the entries whose row is in this batch
-//      (rowslot lookup) -> per-warp list in shared memory, in CSC order (deterministic)
-//   2. decoder row:   g = sum_b dy[b,c] * h[b,:]       -> update WdecT[c,:], b_dec[c]
-//   3. encoder rows:  g = sum_b x0[b, blk*N+c] * dz[b,:] -> update Wenc[blk*N+c,:] per block
-// The gradient lives in registers only; W and its optimizer state are read once and written
-// once, and only for columns the batch touches unless the rule is dense (RMSprop/Adam/L2).
+// K4: weight-side products fused with the optimizer update, in two kernels.
+//
+// k_col_scan   one warp per catalogue column c: scan the store's CSC list of c, keep the entries
+//              whose row is in this batch (rowslot lookup). Their (batch row, code, value, dy)
+//              records go to a global match list in CSC order (deterministic), and one task per
+//              weight row that must change is appended to a task list:
+//                array 0      decoder row  WdecT[c,:]  (+ b_dec[c])   needs a target entry
+//                array 1+blk  encoder row  Wenc[blk*N+c,:]            needs an entry with the block's bit
+//              With a dense rule (RMSprop / Adam / L2) every row gets a task.
+// k_row_update one warp per task, persistent grid: issue the loads of the weight row and its
+//              optimizer state, accumulate the gradient from the matched activations
+//                decoder:  g = sum_b dy[b,c] * h[b,:]        encoder:  g = sum_b x0[b,blk*N+c] * dz[b,:]
+//              in registers, apply the update, store. W and state are read once and written once
+//              (16 B/param for Adagrad/RMSprop, 24 for Adam), only for rows that change.
 // ============================================================================================
 struct ColArgs {
   StoreDev s; BatchDev bt;
-  const float* dy; const float* hdec; const float* dz0;
-  float* WdecT; float* Wd_s1; float* Wd_s2;
-  float* bdec; float* bd_s1; float* bd_s2;
-  float* Wenc; float* We_s1; float* We_s2;
-  int n_cols; int nblk; int3 bits; float aux_val;
-  OptDev opt; int do_dec; int do_enc;
+  const float* dy;
+  int n_cols; int nblk; int3 bits; int dense; int do_dec; int do_enc;
   int list_cap; int* err_flag;
+  uint32_t* matches;      // [max_entries * 3]  b | code << 16, value bits, dy bits
+  int4* tasks;            // [n_cols * (nblk + 1)]  (column, array, first match, match count)
+  int* counters;          // [0] matches used, [1] tasks
 };
 
-template <int NV>
-__device__ __forceinline__ void col_pass(const uint32_t* lb, int n, int sel_bit, int use, float aux_val,
-                                         const float* __restrict__ X, float* __restrict__ Wrow,
-                                         float* __restrict__ S1row, float* __restrict__ S2row,
-                                         const OptDev& o, int lane, float& coef_sum) {
-  constexpr int HP = NV * 128;
-  float4 g[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  bool touched = false;
-  float cs = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const uint32_t bc = lb[i * 3];
-    if (!((bc >> 16) & sel_bit)) continue;
-    const float coef = use == 0 ? __uint_as_float(lb[i * 3 + 1]) : (use == 2 ? __uint_as_float(lb[i * 3 + 2]) : aux_val);
-    const float* x = X + (size_t)(bc & 0xffffu) * HP + lane * 4;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) fma4(g[v], coef, ldg4(x + v * 128));
-    cs += coef;
-    touched = true;
-  }
-  coef_sum = cs;
-  if (!touched && !o.dense) return;
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    const int off = v * 128 + lane * 4;
-    float4 w = *reinterpret_cast<float4*>(Wrow + off);
-    float4 t1 = S1row ? *reinterpret_cast<float4*>(S1row + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 t2 = S2row ? *reinterpret_cast<float4*>(S2row + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-    opt_apply(o, g[v].x, w.x, t1.x, t2.x);
-    opt_apply(o, g[v].y, w.y, t1.y, t2.y);
-    opt_apply(o, g[v].z, w.z, t1.z, t2.z);
-    opt_apply(o, g[v].w, w.w, t1.w, t2.w);
-    *reinterpret_cast<float4*>(Wrow + off) = w;
-    if (S1row) *reinterpret_cast<float4*>(S1row + off) = t1;
-    if (S2row) *reinterpret_cast<float4*>(S2row + off) = t2;
-  }
-}
+constexpr int SCAN_U = 8;   // CSC entries per lane per round: independent load chains in flight
 
-template <int NV>
-__global__ void k_col_update(ColArgs a) {
-  constexpr int HP = NV * 128;
+__global__ void k_col_scan(ColArgs a) {
   extern __shared__ uint32_t col_smem[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * warps + warp;
-  if (c >= a.n_cols) return;
+  const int slot_id = blockIdx.x * warps + warp;
+  if (slot_id >= a.n_cols) return;
+  const int c = a.s.col_order[slot_id];
   uint32_t* lb = col_smem + (size_t)warp * a.list_cap * 3;
   const int64_t e0 = a.s.colptr[c], e1 = a.s.colptr[c + 1];
   const unsigned lt = (1u << lane) - 1u;
   int n = 0;
-  for (int64_t eb = e0; eb < e1; eb += 32) {
-    const int64_t e = eb + lane;
-    bool match = false;
-    uint32_t code = 0, b = 0; float v = 0.f, d = 0.f;
-    if (e < e1) {
-      const uint32_t slot = a.bt.rowslot[a.s.crow[e]];
-      if ((slot >> SLOT_BITS) == a.bt.tag) {
-        b = slot & (uint32_t)(MAX_BATCH_ROWS - 1);
-        const int p = a.bt.ent_off[b] + a.s.cj[e];
+  uint32_t any_code = 0;
+  bool overflow = false;
+  for (int64_t eb = e0; eb < e1 && !overflow; eb += 32 * SCAN_U) {
+    // round: SCAN_U x 32 entries; all row ids first, then all slot lookups, then the matches
+    int row[SCAN_U]; uint32_t slot[SCAN_U];
+#pragma unroll
+    for (int u = 0; u < SCAN_U; ++u) {
+      const int64_t e = eb + u * 32 + lane;
+      row[u] = e < e1 ? a.s.crow[e] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < SCAN_U; ++u) slot[u] = row[u] >= 0 ? a.bt.rowslot[row[u]] : 0u;
+#pragma unroll
+    for (int u = 0; u < SCAN_U; ++u) {
+      bool match = row[u] >= 0 && (slot[u] >> SLOT_BITS) == a.bt.tag;
+      uint32_t code = 0, b = 0; float v = 0.f, d = 0.f;
+      if (match) {
+        b = slot[u] & (uint32_t)(MAX_BATCH_ROWS - 1);
+        const int p = a.bt.ent_off[b] + a.s.cj[eb + u * 32 + lane];
         code = a.bt.codes[p];
         v = a.bt.ent_val[p];
         d = a.dy[p];
         match = code != 0;
       }
-    }
-    const unsigned m = __ballot_sync(FULL, match);
-    if (m) {
-      const int cntm = __popc(m);
-      if (n + cntm > a.list_cap) { if (lane == 0) atomicExch(a.err_flag, 1); break; }
-      if (match) {
-        const int pos = n + __popc(m & lt);
-        lb[pos * 3] = b | (code << 16);
-        lb[pos * 3 + 1] = __float_as_uint(v);
-        lb[pos * 3 + 2] = __float_as_uint(d);
+      const unsigned m = __ballot_sync(FULL, match);
+      if (m) {
+        const int cntm = __popc(m);
+        if (n + cntm > a.list_cap) { if (lane == 0) atomicExch(a.err_flag, 1); overflow = true; break; }
+        if (match) {
+          const int pos = n + __popc(m & lt);
+          lb[pos * 3] = b | (code << 16);
+          lb[pos * 3 + 1] = __float_as_uint(v);
+          lb[pos * 3 + 2] = __float_as_uint(d);
+          any_code |= code;
+        }
+        n += cntm;
       }
-      n += cntm;
     }
   }
+  if (n == 0 && !a.dense) return;
+  any_code = __reduce_or_sync(FULL, any_code);
   __syncwarp();
-  if (n == 0 && !a.opt.dense) return;
-  float cs;
-  if (a.do_dec) {
-    col_pass<NV>(lb, n, CODE_TGT, 2, a.aux_val, a.hdec, a.WdecT + (size_t)c * HP,
-                 a.Wd_s1 ? a.Wd_s1 + (size_t)c * HP : nullptr, a.Wd_s2 ? a.Wd_s2 + (size_t)c * HP : nullptr,
-                 a.opt, lane, cs);
-    if (lane == 0) {                    // decoder bias: column-local gradient sum_b dy[b,c]
-      OptDev ob = a.opt; ob.l2x2 = 0.f;
-      float w = a.bdec[c], t1 = a.bd_s1 ? a.bd_s1[c] : 0.f, t2 = a.bd_s2 ? a.bd_s2[c] : 0.f;
-      opt_apply(ob, cs, w, t1, t2);
-      a.bdec[c] = w;
-      if (a.bd_s1) a.bd_s1[c] = t1;
-      if (a.bd_s2) a.bd_s2[c] = t2;
-    }
-  }
-  if (a.do_enc) {
+  // which weight rows of this column change
+  int n_tasks = 0;
+  int arr[4];
+  if (a.do_dec && (a.dense || (any_code & CODE_TGT))) arr[n_tasks++] = 0;
+  if (a.do_enc)
     for (int blk = 0; blk < a.nblk; ++blk) {
       const int bit = blk == 0 ? a.bits.x : (blk == 1 ? a.bits.y : a.bits.z);
-      const size_t r = ((size_t)blk * a.n_cols + c) * HP;
-      if (bit == 0 && !a.opt.dense) continue;
-      col_pass<NV>(lb, n, bit, blk == 0 ? 0 : 1, a.aux_val, a.dz0, a.Wenc + r,
-                   a.We_s1 ? a.We_s1 + r : nullptr, a.We_s2 ? a.We_s2 + r : nullptr, a.opt, lane, cs);
+      if (a.dense || (any_code & bit)) arr[n_tasks++] = 1 + blk;
+    }
+  if (n_tasks == 0) return;
+  int base = 0, tbase = 0;
+  if (lane == 0) {
+    base = n > 0 ? atomicAdd(&a.counters[0], n) : 0;
+    tbase = atomicAdd(&a.counters[1], n_tasks);
+  }
+  base = __shfl_sync(FULL, base, 0);
+  tbase = __shfl_sync(FULL, tbase, 0);
+  for (int i = lane; i < n * 3; i += 32) a.matches[(size_t)base * 3 + i] = lb[i];
+  if (lane < n_tasks) a.tasks[tbase + lane] = make_int4(c, arr[lane], base, n);
+}
+
+struct RowArgs {
+  const uint32_t* matches; const int4* tasks; const int* counters;
+  const float* hdec; const float* dz0;
+  float* WdecT; float* Wd_s1; float* Wd_s2;
+  float* bdec; float* bd_s1; float* bd_s2;
+  float* Wenc; float* We_s1; float* We_s2;
+  int n_cols; int3 bits; float aux_val;
+  OptDev opt;
+};
+
+template <int NV, int KIND>
+__global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
+  constexpr int HP = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_tasks = a.counters[1];
+  for (int t = gwarp; t < n_tasks; t += nwarps) {
+    const int4 task = a.tasks[t];
+    const int c = task.x, arr = task.y, base = task.z, n = task.w;
+    const size_t r = arr == 0 ? (size_t)c * HP : ((size_t)(arr - 1) * a.n_cols + c) * HP;
+    float* Wrow = (arr == 0 ? a.WdecT : a.Wenc) + r + lane * 4;
+    float* S1row = (arr == 0 ? a.Wd_s1 : a.We_s1);
+    float* S2row = (arr == 0 ? a.Wd_s2 : a.We_s2);
+    // the row and its state first: these are the HBM loads, everything below overlaps them
+    float4 w[NV], t1[NV], t2[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      w[v] = *reinterpret_cast<const float4*>(Wrow + v * 128);
+      if (KIND != OCF_OPT_SGD) t1[v] = *reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128);
+      if (KIND == OCF_OPT_ADAM) t2[v] = *reinterpret_cast<const float4*>(S2row + r + lane * 4 + v * 128);
+    }
+    const float* X = (arr == 0 ? a.hdec : a.dz0) + lane * 4;
+    const uint32_t bit = arr == 0 ? CODE_TGT : (arr == 1 ? a.bits.x : (arr == 2 ? a.bits.y : a.bits.z));
+    float4 g[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cs = 0.f;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      // lanes fetch up to 32 match records, then the warp walks them in order
+      uint32_t bc = 0; float coef = 0.f;
+      if (i0 + lane < n) {
+        const uint32_t* rec = a.matches + (size_t)(base + i0 + lane) * 3;
+        bc = rec[0];
+        coef = arr == 0 ? __uint_as_float(rec[2]) : (arr == 1 ? __uint_as_float(rec[1]) : a.aux_val);
+      }
+      unsigned m = __ballot_sync(FULL, ((bc >> 16) & bit) != 0);
+      while (m) {
+        const int j = __ffs(m) - 1; m &= m - 1;
+        const uint32_t b = __shfl_sync(FULL, bc, j) & 0xffffu;
+        const float cf = __shfl_sync(FULL, coef, j);
+        const float* x = X + (size_t)b * HP;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) fma4(g[v], cf, ldg4(x + v * 128));
+        cs += cf;
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      opt_apply_k<KIND>(a.opt, g[v].x, w[v].x, t1[v].x, t2[v].x);
+      opt_apply_k<KIND>(a.opt, g[v].y, w[v].y, t1[v].y, t2[v].y);
+      opt_apply_k<KIND>(a.opt, g[v].z, w[v].z, t1[v].z, t2[v].z);
+      opt_apply_k<KIND>(a.opt, g[v].w, w[v].w, t1[v].w, t2[v].w);
+      *reinterpret_cast<float4*>(Wrow + v * 128) = w[v];
+      if (KIND != OCF_OPT_SGD) *reinterpret_cast<float4*>(S1row + r + lane * 4 + v * 128) = t1[v];
+      if (KIND == OCF_OPT_ADAM) *reinterpret_cast<float4*>(S2row + r + lane * 4 + v * 128) = t2[v];
+    }
+    if (arr == 0 && lane == 0) {          // decoder bias: column-local gradient sum_b dy[b,c]
+      OptDev ob = a.opt; ob.l2x2 = 0.f;   // Keras regularises kernels only
+      float wb = a.bdec[c], b1 = KIND != OCF_OPT_SGD ? a.bd_s1[c] : 0.f, b2 = KIND == OCF_OPT_ADAM ? a.bd_s2[c] : 0.f;
+      opt_apply_k<KIND>(ob, cs, wb, b1, b2);
+      a.bdec[c] = wb;
+      if (KIND != OCF_OPT_SGD) a.bd_s1[c] = b1;
+      if (KIND == OCF_OPT_ADAM) a.bd_s2[c] = b2;
     }
   }
 }

@@ -49,12 +49,14 @@ class OmniNet(object):
         self._compiled = False
 
     # -- C handle -----------------------------------------------------------------------------
-    def _ensure(self, n_rows=None, n_entries=None, aux_type="keep"):
+    def _ensure(self, n_rows=None, n_entries=None, aux_type="keep", reader=None):
         o = self.owner
         if aux_type != "keep" and aux_type != o.aux_kind:
             o.set_aux_kind(aux_type)       # the reader decides what the aux block holds
         rows = max(int(n_rows or o.batch_size), self._capacity[0])
         entries = max(int(n_entries or 1), self._capacity[1])
+        if reader is not None and (self._handle is None or entries > self._capacity[1]):
+            entries = max(entries, reader.max_batch_entries(rows))     # size the workspaces once
         if self._handle is None:
             _lib.require_gpu()
             cfg = _lib.ModelConfig()
@@ -156,7 +158,7 @@ class OmniNet(object):
     def train_on_batch(self, batch, sync=True):
         """One optimisation step. Returns the six metric values when `sync`, else None (the
         values stay in the device log; see `read_metrics`)."""
-        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
         args = self._args(batch)
         rec = np.empty(_lib.N_METRICS, dtype=np.float32) if sync else None
@@ -165,12 +167,22 @@ class OmniNet(object):
         return self._metrics_from(rec) if sync else None
 
     def test_on_batch(self, batch, sync=True):
-        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
         args = self._args(batch, training=False)
         rec = np.empty(_lib.N_METRICS, dtype=np.float32) if sync else None
         _lib.check(_lib.lib().ocf_eval_step(h, dev.handle, C.byref(args), _lib.ptr(rec), self.stream))
         return self._metrics_from(rec) if sync else None
+
+    def steps_logged(self):
+        return int(_lib.lib().ocf_model_steps_logged(self._handle)) if self._handle is not None else 0
+
+    def wait_metrics(self, step):
+        """The six metric values of logged step `step` (one of the last 64); waits for that step
+        only, later steps keep running."""
+        rec = np.empty(_lib.N_METRICS, dtype=np.float32)
+        _lib.check(_lib.lib().ocf_model_wait_metrics(self._handle, int(step), _lib.ptr(rec)))
+        return self._metrics_from(rec)
 
     def read_metrics(self, first, count):
         """[count, 8] records of steps first..first+count-1 from the device log."""
@@ -193,7 +205,7 @@ class OmniNet(object):
                 if batch is None:
                     raise StopIteration("generator ran out of batches (it yields None after floor(n/B) batches)")
                 if first is None:
-                    self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+                    self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
                     first = _lib.lib().ocf_model_steps_logged(self._handle)
                 (self.train_on_batch if train else self.test_on_batch)(batch, sync=False)
             rows.append(self.read_metrics(first, chunk))
@@ -227,7 +239,7 @@ class OmniNet(object):
 
     def predict(self, batch, batch_size=None, verbose=0):
         """`best_m.predict(input_list)`, train.py:239: output_mask * full_predictions, [B, N] float32."""
-        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
         out = np.empty((batch.n_rows, self.owner.local_cols), dtype=np.float32)
         _lib.check(_lib.lib().ocf_predict(h, dev.handle, _lib.ptr(out), self.stream))
@@ -235,7 +247,7 @@ class OmniNet(object):
 
     def score(self, batch):
         """Full-catalogue scores `full_predictions` (model.py:82-84), [B, N] float32."""
-        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type)
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
         out = np.empty((batch.n_rows, self.owner.local_cols), dtype=np.float32)
         _lib.check(_lib.lib().ocf_score(h, dev.handle, _lib.ptr(out), 0, self.stream))

@@ -56,19 +56,29 @@ SHAPES: Dict[str, Shape] = {
 
 
 def _skewed_ids(rng: np.random.RandomState, n: int, size: int, alpha: float) -> np.ndarray:
-    """`size` ids in [0,n) with a Zipf-like popularity profile (exponent alpha)."""
-    # inverse-CDF sampling of p(i) ~ (i+1)^-alpha on a shuffled id space
-    w = (np.arange(1, n + 1, dtype=np.float64)) ** (-alpha)
-    cdf = np.cumsum(w)
-    cdf /= cdf[-1]
-    ranks = np.searchsorted(cdf, rng.random_sample(size), side="right")
+    """`size` ids in [0,n) with a Zipf-like popularity profile, p(rank) ~ (rank+1)^-alpha
+    (continuous inverse-CDF: rank = n * u^(1/(1-alpha))), on a shuffled id space."""
+    u = rng.random_sample(size)
+    ranks = np.floor(n * np.power(u, 1.0 / (1.0 - alpha))).astype(np.int64)
     np.minimum(ranks, n - 1, out=ranks)
     relabel = rng.permutation(n)
-    return relabel[ranks].astype(np.int64)
+    return relabel[ranks]
 
 
-def make_ratings(shape: Shape, seed: int = 0, user_alpha: float = 0.6,
-                 item_alpha: float = 0.9) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def _stable_group_order(keys: np.ndarray) -> np.ndarray:
+    """argsort(keys, kind='stable') for non-negative keys < 2^32, as two 16-bit radix passes
+    (NumPy only uses radix sort for <= 16-bit integers; this is ~5x faster at 1e7 keys)."""
+    keys = np.asarray(keys, dtype=np.int64)
+    lo = (keys & 0xFFFF).astype(np.uint16)
+    order = np.argsort(lo, kind="stable")
+    if keys.size and int(keys.max()) >= (1 << 16):
+        hi = (keys >> 16).astype(np.uint16)
+        order = order[np.argsort(hi[order], kind="stable")]
+    return order
+
+
+def make_ratings(shape: Shape, seed: int = 0, user_alpha: float = 0.45,
+                 item_alpha: float = 0.65) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Unique (user, item) pairs with ratings, in a random order.
 
     Returns (user int32[nnz'], item int32[nnz'], rating float32[nnz']); nnz' == shape.nnz
@@ -102,7 +112,8 @@ def make_ratings(shape: Shape, seed: int = 0, user_alpha: float = 0.6,
         # mildly skewed towards the upper half of the alphabet, like real rating data
         p = np.linspace(0.6, 1.6, alphabet.size)
         p /= p.sum()
-        r = alphabet[rng.choice(alphabet.size, size=keys.size, p=p)]
+        r = alphabet[np.minimum(np.searchsorted(np.cumsum(p), rng.random_sample(keys.size), side="right"),
+                                alphabet.size - 1)]
     else:
         r = np.round(rng.uniform(-10.0, 10.0, size=keys.size), 2).astype(np.float32)
     return users, items, r.astype(np.float32)
@@ -147,8 +158,11 @@ def csr_from_coo(rows: np.ndarray, cols: np.ndarray, vals: np.ndarray, n_cols: i
     """
     rows = np.asarray(rows, dtype=np.int64)
     if row_keys is None:
-        uniq, first = np.unique(rows, return_index=True)
-        row_keys = uniq[np.argsort(first, kind="stable")]
+        hi0 = int(rows.max(initial=-1)) + 1
+        first = np.full(hi0, rows.size, dtype=np.int64)
+        first[rows[::-1]] = np.arange(rows.size - 1, -1, -1, dtype=np.int64)   # last write wins = first appearance
+        present = np.flatnonzero(first < rows.size)
+        row_keys = present[np.argsort(first[present], kind="stable")]
     row_keys = np.asarray(row_keys, dtype=np.int64)
     hi = int(max(rows.max(initial=-1), row_keys.max(initial=-1))) + 1
     rank = np.full(hi, -1, dtype=np.int64)
@@ -157,7 +171,7 @@ def csr_from_coo(rows: np.ndarray, cols: np.ndarray, vals: np.ndarray, n_cols: i
     keep = rr >= 0
     if not keep.all():
         rr, cols, vals = rr[keep], cols[keep], vals[keep]
-    order = np.argsort(rr, kind="stable")
+    order = _stable_group_order(rr)
     counts = np.bincount(rr, minlength=row_keys.size)
     rowptr = np.zeros(row_keys.size + 1, dtype=np.int64)
     np.cumsum(counts, out=rowptr[1:])
