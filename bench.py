@@ -262,7 +262,7 @@ def main():
             g = gen()
             continue
         plans.append(b)
-    m._ensure(B, max(p.n_entries for p in plans), aux)
+    m._ensure(B, max(p.n_entries for p in plans), aux, rd)      # workspaces sized once for any batch of the set
     resident = []
     for p in plans:
         dev = DeviceBatch(p.n_rows, p.n_entries)
@@ -332,21 +332,25 @@ def main():
                 "share_of_step": tag_ms[dom] / (ms / K)}
 
     # ---- e2e: the public API, host buffers in, metrics out, every step ---------------------------
-    g = gen()
+    def endless():
+        g = gen()
+        while True:
+            b = next(g)
+            if b is None:
+                g = gen()
+                continue
+            yield b
+
+    stream_of_batches = endless()
     for _ in range(W):
-        b = next(g)
-        if b is None:
-            g = gen(); b = next(g)
-        m.train_on_batch(b, sync=True)
+        m.train_on_batch(next(stream_of_batches), sync=True)
     torch.cuda.synchronize()
     h2d = 0
     e_ratings = 0
     prev = None
     t0 = time.perf_counter()
     for _ in range(K):
-        b = next(g)                               # host: RNG replay -> row ids + keep flags
-        if b is None:
-            g = gen(); b = next(g)
+        b = next(stream_of_batches)               # host: RNG replay -> row ids + keep flags
         m.train_on_batch(b, sync=False)           # pinned staging + H2D(row ids, flags) + kernels + D2H(metrics)
         step_id = m.steps_logged() - 1
         if prev is not None:

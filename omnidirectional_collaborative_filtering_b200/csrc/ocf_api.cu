@@ -123,6 +123,8 @@ struct ocf_model {
   int64_t steps_logged = 0;
   cudaEvent_t step_ev[64] = {nullptr};
   uint32_t* col_matches = nullptr;
+  int32_t* col_mcol = nullptr;
+  int2* col_seg = nullptr;
   int4* col_tasks = nullptr;
   int* col_counters = nullptr;
   int sm_count = 148;
@@ -282,17 +284,39 @@ extern "C" int ocf_store_create(int64_t n_rows, int64_t n_cols, const int64_t* r
         (nnz && cudaMemcpy(d_cj, cj.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice) != cudaSuccess))
       return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
     s->dev.colptr = d_colptr; s->dev.crow = d_crow; s->dev.cj = d_cj;
-    // longest columns first: the scan's tail is its longest column, start those early
-    std::vector<int32_t> order((size_t)n_cols);
-    for (int64_t c = 0; c < n_cols; ++c) order[c] = (int32_t)c;
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-      return colptr[x + 1] - colptr[x] > colptr[y + 1] - colptr[y];
-    });
-    int32_t* d_order = nullptr;
-    if ((st = s->mem.get(&d_order, (size_t)n_cols))) return bail(st);
-    if (cudaMemcpy(d_order, order.data(), sizeof(int32_t) * n_cols, cudaMemcpyHostToDevice) != cudaSuccess)
+    // scan schedule: consecutive columns grouped up to SCAN_T entries (a longer column is its own
+    // group); groups with the most entries first so the long ones start early
+    std::vector<int2> groups;
+    int scan_t = SCAN_SUB;
+    while (scan_t < SCAN_T_MAX && nnz / scan_t > 148 * 5) scan_t *= 2;
+    {
+      const int64_t SCAN_T = scan_t;
+      int64_t c0 = 0;
+      while (c0 < n_cols) {
+        int64_t c1 = c0 + 1;
+        while (c1 < n_cols && colptr[c1 + 1] - colptr[c0] <= SCAN_T) ++c1;
+        if (colptr[c1] > colptr[c0]) groups.push_back(make_int2((int)c0, (int)c1));
+        c0 = c1;
+      }
+      std::stable_sort(groups.begin(), groups.end(), [&](const int2& x, const int2& y) {
+        return colptr[x.y] - colptr[x.x] > colptr[y.y] - colptr[y.x];
+      });
+    }
+    int2* d_groups = nullptr;
+    if ((st = s->mem.get(&d_groups, groups.size()))) return bail(st);
+    if (!groups.empty() && cudaMemcpy(d_groups, groups.data(), sizeof(int2) * groups.size(), cudaMemcpyHostToDevice) != cudaSuccess)
       return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
-    s->dev.col_order = d_order;
+    s->dev.groups = d_groups;
+    s->dev.n_groups = (int)groups.size();
+    s->dev.scan_t = scan_t;
+    std::vector<int32_t> ccol((size_t)nnz);
+    for (int64_t c = 0; c < n_cols; ++c)
+      for (int64_t e = colptr[c]; e < colptr[c + 1]; ++e) ccol[e] = (int32_t)c;
+    int32_t* d_ccol = nullptr;
+    if ((st = s->mem.get(&d_ccol, (size_t)nnz))) return bail(st);
+    if (nnz && cudaMemcpy(d_ccol, ccol.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
+    s->dev.ccol = d_ccol;
     s->has_csc = true;
   }
   *out = s;
@@ -601,6 +625,7 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   OCF_TRY(ws.get(&m->dy, (size_t)max_entries, true));
   OCF_TRY(ws.get(&m->dh_top, (size_t)Bm * m->hp[L - 1], true));
   OCF_TRY(ws.get(&m->col_matches, (size_t)max_entries * 3));
+  OCF_TRY(ws.get(&m->col_mcol, (size_t)max_entries));
   return OCF_OK;
 }
 
@@ -636,7 +661,7 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   }
   if (st) return bail(st);
   if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_log, (size_t)LOG_CAP * LOG_W, true)) ||
-      (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) ||
+      (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_seg, (size_t)N, true)) ||
       (st = m->mem.get(&m->col_counters, 2, true)))
     return bail(st);
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev); if (m->sm_count <= 0) m->sm_count = 148; }
@@ -1019,25 +1044,34 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   auto col_update = [&](int do_dec, int do_enc, int hpx) -> int {
     if (!do_dec && !do_enc) return OCF_OK;
     OCF_CUDA(cudaMemsetAsync(m->col_counters, 0, 2 * sizeof(int), st));
+    if (opt.dense) OCF_CUDA(cudaMemsetAsync(m->col_seg, 0, sizeof(int2) * (size_t)m->cfg.n_cols, st));
     ColArgs a{};
     a.s = b->store->dev; a.bt = bt; a.dy = m->dy;
     a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.dense = opt.dense;
     a.do_dec = do_dec; a.do_enc = do_enc;
-    a.err_flag = m->d_err; a.matches = m->col_matches; a.tasks = m->col_tasks; a.counters = m->col_counters;
-    a.list_cap = 2 * (int)align_up((size_t)B, 32) + 32;
-    const int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (96 * 1024) / ((size_t)a.list_cap * 12)));
-    const size_t smem = (size_t)warps * a.list_cap * 12;
-    if (smem > 48 * 1024) OCF_CUDA(cudaFuncSetAttribute(k_col_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    g_prof.begin(3, st);
-    k_col_scan<<<(m->cfg.n_cols + warps - 1) / warps, warps * 32, smem, st>>>(a);
-    OCF_LAUNCHED();
-    g_prof.end(3, st);
+    a.err_flag = m->d_err; a.matches = m->col_matches; a.mcol = m->col_mcol; a.tasks = m->col_tasks;
+    a.colseg = m->col_seg; a.counters = m->col_counters; a.max_matches = (int)m->cfg.max_entries;
+    const int64_t words = (b->store->n_rows + 31) / 32;
+    a.bitmap_words = words <= 40 * 1024 ? (int)words : 0;             // <= 160 KB of shared memory
+    const size_t smem = (size_t)a.bitmap_words * 4;
+    if (smem > 40 * 1024) OCF_CUDA(cudaFuncSetAttribute(k_col_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (200 * 1024) / std::max<size_t>(smem + 5 * 1024, 1)));
+    const int grid = std::max(1, std::min(m->sm_count * per_sm, b->store->dev.n_groups));
+    if (bt.n_entries > 0 && b->store->dev.n_groups > 0) {
+      g_prof.begin(3, st);
+      k_col_scan<<<grid, 256, smem, st>>>(a);
+      OCF_LAUNCHED();
+      g_prof.end(3, st);
+    }
     RowArgs r{};
-    r.matches = m->col_matches; r.tasks = m->col_tasks; r.counters = m->col_counters;
+    r.matches = m->col_matches; r.tasks = m->col_tasks; r.colseg = m->col_seg; r.counters = m->col_counters;
     r.hdec = drop ? m->h[L - 1] : m->act[L - 1]; r.dz0 = m->dz[0];
     r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
     r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
     r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.aux_val = b->aux_value; r.opt = opt;
+    r.dense = opt.dense; r.n_arr = 0;
+    if (do_dec) r.arr_map[r.n_arr++] = 0;
+    if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
     g_prof.begin(5, st);
     OCF_TRY(launch_row_update(hpx, opt.kind, m->sm_count * 6, r, st));
     g_prof.end(5, st);

@@ -64,7 +64,10 @@ struct StoreDev {
   const int64_t* colptr;     // CSC: entries of column c are [colptr[c], colptr[c+1])
   const int32_t* crow;       //   row of the entry
   const int32_t* cj;         //   position of the entry inside its row
-  const int32_t* col_order;  //   columns sorted by length, longest first (scan schedule)
+  const int32_t* ccol;       //   column of the entry (CSC expanded; read for matches only)
+  const int2* groups;        //   scan schedule: groups of consecutive columns [x, y), <= scan_t entries each or one longer column; largest first
+  int n_groups;
+  int scan_t;                //   4096, 8192 or 16384: picked so that a scan is about one group per resident CTA
 };
 
 // Device view of one batch. The first group is uploaded by the host in one copy, the second

@@ -455,112 +455,183 @@ k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int 
 // ============================================================================================
 // K4: weight-side products fused with the optimizer update, in two kernels.
 //
-// k_col_scan   one warp per catalogue column c: scan the store's CSC list of c, keep the entries
-//              whose row is in this batch (rowslot lookup). Their (batch row, code, value, dy)
-//              records go to a global match list in CSC order (deterministic), and one task per
-//              weight row that must change is appended to a task list:
+// k_col_scan   streams the store's CSC row ids once. A CTA owns a group of consecutive catalogue
+//              columns (<= SCAN_T entries, or one longer column) and tests every entry's row
+//              against a shared-memory bitmap of the batch's rows. The matches (~1 % of the
+//              entries) are compacted IN CSC ORDER (ballot words + prefix sum, no sorting, no
+//              float atomics) into a global match list as (batch row, code, value, dy) records,
+//              so each column's matches are contiguous and deterministic. One task per weight row
+//              that must change is appended to a task list:
 //                array 0      decoder row  WdecT[c,:]  (+ b_dec[c])   needs a target entry
 //                array 1+blk  encoder row  Wenc[blk*N+c,:]            needs an entry with the block's bit
-//              With a dense rule (RMSprop / Adam / L2) every row gets a task.
+//              With a dense rule (RMSprop / Adam / L2) every row changes: the scan only records
+//              each touched column's segment and the update enumerates all (column, array) pairs.
 // k_row_update one warp per task, persistent grid: issue the loads of the weight row and its
 //              optimizer state, accumulate the gradient from the matched activations
 //                decoder:  g = sum_b dy[b,c] * h[b,:]        encoder:  g = sum_b x0[b,blk*N+c] * dz[b,:]
 //              in registers, apply the update, store. W and state are read once and written once
 //              (16 B/param for Adagrad/RMSprop, 24 for Adam), only for rows that change.
 // ============================================================================================
+constexpr int SCAN_SUB = 4096;            // CSC entries per sub-block (256 threads x 16 loads in flight)
+constexpr int SCAN_T_MAX = 16384;         // largest scan block (a store picks 4096, 8192 or 16384)
+constexpr int SCAN_WORDS_MAX = SCAN_T_MAX / 32;
+
 struct ColArgs {
   StoreDev s; BatchDev bt;
   const float* dy;
   int n_cols; int nblk; int3 bits; int dense; int do_dec; int do_enc;
-  int list_cap; int* err_flag;
+  int* err_flag;
   uint32_t* matches;      // [max_entries * 3]  b | code << 16, value bits, dy bits
-  int4* tasks;            // [n_cols * (nblk + 1)]  (column, array, first match, match count)
+  int32_t* mcol;          // [max_entries]      catalogue column of the match
+  int4* tasks;            // sparse rules: (column, array, first match, match count)
+  int2* colseg;           // dense rules:  per column (first match, match count), zeroed per step
   int* counters;          // [0] matches used, [1] tasks
+  int bitmap_words;       // 32-bit words of the shared-memory row bitmap (0: too many rows, skip it)
+  int max_matches;
 };
 
-constexpr int SCAN_U = 8;   // CSC entries per lane per round: independent load chains in flight
-
-__global__ void k_col_scan(ColArgs a) {
+__global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
   extern __shared__ uint32_t col_smem[];
-  const int warps = blockDim.x >> 5;
+  __shared__ uint32_t words[SCAN_WORDS_MAX];
+  __shared__ int prefix[SCAN_WORDS_MAX + 1];
+  __shared__ int s_base, s_tbase;
+  __shared__ int s_wsum[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot_id = blockIdx.x * warps + warp;
-  if (slot_id >= a.n_cols) return;
-  const int c = a.s.col_order[slot_id];
-  uint32_t* lb = col_smem + (size_t)warp * a.list_cap * 3;
-  const int64_t e0 = a.s.colptr[c], e1 = a.s.colptr[c + 1];
-  const unsigned lt = (1u << lane) - 1u;
-  int n = 0;
-  uint32_t any_code = 0;
-  bool overflow = false;
-  for (int64_t eb = e0; eb < e1 && !overflow; eb += 32 * SCAN_U) {
-    // round: SCAN_U x 32 entries; all row ids first, then all slot lookups, then the matches
-    int row[SCAN_U]; uint32_t slot[SCAN_U];
-#pragma unroll
-    for (int u = 0; u < SCAN_U; ++u) {
-      const int64_t e = eb + u * 32 + lane;
-      row[u] = e < e1 ? a.s.crow[e] : -1;
+  const int T = a.s.scan_t, nwords = T / 32;
+  uint32_t* bitmap = col_smem;
+  if (a.bitmap_words > 0) {
+    for (int i = threadIdx.x; i < a.bitmap_words; i += blockDim.x) bitmap[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.bt.B; i += blockDim.x) {
+      const int r = a.bt.row_ids[i];
+      atomicOr(&bitmap[r >> 5], 1u << (r & 31));
     }
+    __syncthreads();
+  }
+  for (int g = blockIdx.x; g < a.s.n_groups; g += gridDim.x) {
+    const int2 grp = a.s.groups[g];
+    const int64_t e0 = a.s.colptr[grp.x], e1 = a.s.colptr[grp.y];
+    const int nblocks = (int)((e1 - e0 + T - 1) / T);
+
+    // phase 1 of a block: match bit of every entry -> words[], exclusive prefix of the word
+    // popcounts -> prefix[], block total -> prefix[nwords]
+    auto find = [&](int64_t eb) {
+      for (int sb = 0; sb < T / SCAN_SUB; ++sb) {
+        int row[16];
 #pragma unroll
-    for (int u = 0; u < SCAN_U; ++u) slot[u] = row[u] >= 0 ? a.bt.rowslot[row[u]] : 0u;
-#pragma unroll
-    for (int u = 0; u < SCAN_U; ++u) {
-      bool match = row[u] >= 0 && (slot[u] >> SLOT_BITS) == a.bt.tag;
-      uint32_t code = 0, b = 0; float v = 0.f, d = 0.f;
-      if (match) {
-        b = slot[u] & (uint32_t)(MAX_BATCH_ROWS - 1);
-        const int p = a.bt.ent_off[b] + a.s.cj[eb + u * 32 + lane];
-        code = a.bt.codes[p];
-        v = a.bt.ent_val[p];
-        d = a.dy[p];
-        match = code != 0;
-      }
-      const unsigned m = __ballot_sync(FULL, match);
-      if (m) {
-        const int cntm = __popc(m);
-        if (n + cntm > a.list_cap) { if (lane == 0) atomicExch(a.err_flag, 1); overflow = true; break; }
-        if (match) {
-          const int pos = n + __popc(m & lt);
-          lb[pos * 3] = b | (code << 16);
-          lb[pos * 3 + 1] = __float_as_uint(v);
-          lb[pos * 3 + 2] = __float_as_uint(d);
-          any_code |= code;
+        for (int i = 0; i < 16; ++i) {
+          const int64_t e = eb + sb * SCAN_SUB + (warp + 8 * i) * 32 + lane;
+          row[i] = e < e1 ? a.s.crow[e] : -1;
         }
-        n += cntm;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          bool match = row[i] >= 0;
+          if (match && a.bitmap_words > 0) match = (bitmap[row[i] >> 5] >> (row[i] & 31)) & 1u;
+          if (match) match = (a.bt.rowslot[row[i]] >> SLOT_BITS) == a.bt.tag;
+          const unsigned m = __ballot_sync(FULL, match);
+          if (lane == 0) words[sb * (SCAN_SUB / 32) + warp + 8 * i] = m;
+        }
       }
+      __syncthreads();
+      if (warp == 0) {
+        int run = 0;
+        for (int k = 0; k < nwords / 32; ++k) {
+          const int cnt = __popc(words[k * 32 + lane]);
+          int inc = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+          prefix[k * 32 + lane] = run + inc - cnt;
+          run += __shfl_sync(FULL, inc, 31);
+        }
+        if (lane == 0) prefix[nwords] = run;
+      }
+      __syncthreads();
+    };
+
+    int total = 0;
+    if (nblocks == 1) { find(e0); total = prefix[nwords]; }
+    else for (int blk = 0; blk < nblocks; ++blk) { find(e0 + (int64_t)blk * T); total += prefix[nwords]; __syncthreads(); }
+    if (total == 0) continue;
+    if (threadIdx.x == 0) {
+      const int got = atomicAdd(&a.counters[0], total);
+      if (got + total > a.max_matches) { atomicExch(a.err_flag, 1); s_base = -1; } else s_base = got;
+    }
+    __syncthreads();
+    const int base = s_base;
+    if (base < 0) continue;
+    int running = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int64_t eb = e0 + (int64_t)blk * T;
+      if (nblocks > 1) find(eb);
+      // phase 2: one thread per match (their dependent load chains run side by side): locate the
+      // t-th set bit of the block, fetch the batch record, write it at CSC rank base+running+t
+      const int block_total = prefix[nwords];
+      for (int t = threadIdx.x; t < block_total; t += blockDim.x) {
+        int wlo = 0, whi = nwords;
+        while (whi - wlo > 1) { const int mid = (wlo + whi) >> 1; if (prefix[mid] <= t) wlo = mid; else whi = mid; }
+        const int bitpos = __fns(words[wlo], 0, t - prefix[wlo] + 1);
+        const int64_t e = eb + wlo * 32 + bitpos;
+        const uint32_t b = a.bt.rowslot[a.s.crow[e]] & (uint32_t)(MAX_BATCH_ROWS - 1);
+        const int p = a.bt.ent_off[b] + a.s.cj[e];
+        const size_t idx = (size_t)(base + running + t);
+        a.matches[idx * 3] = b | ((uint32_t)a.bt.codes[p] << 16);
+        a.matches[idx * 3 + 1] = __float_as_uint(a.bt.ent_val[p]);
+        a.matches[idx * 3 + 2] = __float_as_uint(a.dy[p]);
+        a.mcol[idx] = a.s.ccol[e];
+      }
+      running += block_total;
+      __syncthreads();
+    }
+    // phase 3: one head per column segment creates that column's tasks. Task slots are
+    // allocated with ONE atomic per 256 matches (block scan of the per-head task counts):
+    // per-column atomics on a single counter serialise in L2 and dominated this kernel.
+    for (int i0 = 0; i0 < total; i0 += blockDim.x) {
+      const int i = i0 + threadIdx.x;
+      int c = -1, n = 0, n_tasks = 0;
+      int arr[4];
+      if (i < total) {
+        c = __ldcg(a.mcol + base + i);
+        if (i == 0 || __ldcg(a.mcol + base + i - 1) != c) {
+          uint32_t any_code = 0;
+          while (i + n < total && __ldcg(a.mcol + base + i + n) == c) { any_code |= __ldcg(a.matches + (size_t)(base + i + n) * 3) >> 16; ++n; }
+          if (a.dense) a.colseg[c] = make_int2(base + i, n);
+          else {
+            if (a.do_dec && (any_code & CODE_TGT)) arr[n_tasks++] = 0;
+            if (a.do_enc)
+              for (int blk = 0; blk < a.nblk; ++blk) {
+                const int bit = blk == 0 ? a.bits.x : (blk == 1 ? a.bits.y : a.bits.z);
+                if (any_code & bit) arr[n_tasks++] = 1 + blk;
+              }
+          }
+        }
+      }
+      if (a.dense) continue;
+      int inc = n_tasks;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) s_wsum[warp] = inc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w2 = 0; w2 < 8; ++w2) { const int t = s_wsum[w2]; s_wsum[w2] = tot; tot += t; }
+        s_tbase = tot > 0 ? atomicAdd(&a.counters[1], tot) : 0;
+      }
+      __syncthreads();
+      const int slot = s_tbase + s_wsum[warp] + inc - n_tasks;
+      for (int k = 0; k < n_tasks; ++k) a.tasks[slot + k] = make_int4(c, arr[k], base + i, n);
+      __syncthreads();
     }
   }
-  if (n == 0 && !a.dense) return;
-  any_code = __reduce_or_sync(FULL, any_code);
-  __syncwarp();
-  // which weight rows of this column change
-  int n_tasks = 0;
-  int arr[4];
-  if (a.do_dec && (a.dense || (any_code & CODE_TGT))) arr[n_tasks++] = 0;
-  if (a.do_enc)
-    for (int blk = 0; blk < a.nblk; ++blk) {
-      const int bit = blk == 0 ? a.bits.x : (blk == 1 ? a.bits.y : a.bits.z);
-      if (a.dense || (any_code & bit)) arr[n_tasks++] = 1 + blk;
-    }
-  if (n_tasks == 0) return;
-  int base = 0, tbase = 0;
-  if (lane == 0) {
-    base = n > 0 ? atomicAdd(&a.counters[0], n) : 0;
-    tbase = atomicAdd(&a.counters[1], n_tasks);
-  }
-  base = __shfl_sync(FULL, base, 0);
-  tbase = __shfl_sync(FULL, tbase, 0);
-  for (int i = lane; i < n * 3; i += 32) a.matches[(size_t)base * 3 + i] = lb[i];
-  if (lane < n_tasks) a.tasks[tbase + lane] = make_int4(c, arr[lane], base, n);
 }
 
 struct RowArgs {
-  const uint32_t* matches; const int4* tasks; const int* counters;
+  const uint32_t* matches; const int4* tasks; const int2* colseg; const int* counters;
   const float* hdec; const float* dz0;
   float* WdecT; float* Wd_s1; float* Wd_s2;
   float* bdec; float* bd_s1; float* bd_s2;
   float* Wenc; float* We_s1; float* We_s2;
   int n_cols; int3 bits; float aux_val;
+  int dense; int n_arr; int arr_map[4];
   OptDev opt;
 };
 
@@ -570,10 +641,15 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_tasks = a.counters[1];
-  for (int t = gwarp; t < n_tasks; t += nwarps) {
-    const int4 task = a.tasks[t];
-    const int c = task.x, arr = task.y, base = task.z, n = task.w;
+  const long long n_tasks = a.dense ? (long long)a.n_cols * a.n_arr : (long long)a.counters[1];
+  for (long long t = gwarp; t < n_tasks; t += nwarps) {
+    int c, arr, base, n;
+    if (a.dense) {
+      c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
+      const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
+    } else {
+      const int4 task = a.tasks[t]; c = task.x; arr = task.y; base = task.z; n = task.w;
+    }
     const size_t r = arr == 0 ? (size_t)c * HP : ((size_t)(arr - 1) * a.n_cols + c) * HP;
     float* Wrow = (arr == 0 ? a.WdecT : a.Wenc) + r + lane * 4;
     float* S1row = (arr == 0 ? a.Wd_s1 : a.We_s1);
@@ -583,8 +659,8 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       w[v] = *reinterpret_cast<const float4*>(Wrow + v * 128);
-      if (KIND != OCF_OPT_SGD) t1[v] = *reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128);
-      if (KIND == OCF_OPT_ADAM) t2[v] = *reinterpret_cast<const float4*>(S2row + r + lane * 4 + v * 128);
+      t1[v] = KIND != OCF_OPT_SGD ? *reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      t2[v] = KIND == OCF_OPT_ADAM ? *reinterpret_cast<const float4*>(S2row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float* X = (arr == 0 ? a.hdec : a.dz0) + lane * 4;
     const uint32_t bit = arr == 0 ? CODE_TGT : (arr == 1 ? a.bits.x : (arr == 2 ? a.bits.y : a.bits.z));

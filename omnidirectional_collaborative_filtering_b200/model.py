@@ -192,24 +192,28 @@ class OmniNet(object):
         return out
 
     def _run(self, generator, steps, train):
-        """`steps` batches through train/eval steps without a host sync per step; the metric
-        records are read back once at the end (each at most 4096 steps)."""
+        """`steps` batches through train/eval steps. Steps are enqueued without a host sync (the
+        host builds batch i+1's row ids / flags while the device runs step i) and the metric
+        records, copied to pinned memory behind every step, are read back in chunks."""
         steps = int(steps)
         rows = []
-        done = 0
-        while done < steps:
-            chunk = min(steps - done, 2048)
-            first = None
-            for _ in range(chunk):
-                batch = next(generator)
-                if batch is None:
-                    raise StopIteration("generator ran out of batches (it yields None after floor(n/B) batches)")
-                if first is None:
-                    self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
-                    first = _lib.lib().ocf_model_steps_logged(self._handle)
-                (self.train_on_batch if train else self.test_on_batch)(batch, sync=False)
-            rows.append(self.read_metrics(first, chunk))
-            done += chunk
+        first = None
+        pending = 0
+        for _ in range(steps):
+            batch = next(generator)
+            if batch is None:
+                raise StopIteration("generator ran out of batches (it yields None after floor(n/B) batches)")
+            if first is None:
+                self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
+                first = _lib.lib().ocf_model_steps_logged(self._handle)
+            (self.train_on_batch if train else self.test_on_batch)(batch, sync=False)
+            pending += 1
+            if pending == 2048:
+                rows.append(self.read_metrics(first, pending))
+                first += pending
+                pending = 0
+        if pending:
+            rows.append(self.read_metrics(first, pending))
         return np.concatenate(rows, axis=0) if rows else np.zeros((0, _lib.N_METRICS), dtype=np.float32)
 
     def fit_generator(self, generator, steps_per_epoch, epochs=1, verbose=1, callbacks=None,
