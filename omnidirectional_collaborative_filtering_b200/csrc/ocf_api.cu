@@ -288,7 +288,7 @@ extern "C" int ocf_store_create(int64_t n_rows, int64_t n_cols, const int64_t* r
     // group); groups with the most entries first so the long ones start early
     std::vector<int2> groups;
     int scan_t = SCAN_SUB;
-    while (scan_t < SCAN_T_MAX && nnz / scan_t > 148 * 5) scan_t *= 2;
+    while (scan_t < SCAN_T_MAX && nnz / scan_t > 148 * 5 * 3 / 2) scan_t *= 2;   // about one group per resident CTA
     {
       const int64_t SCAN_T = scan_t;
       int64_t c0 = 0;
@@ -1055,7 +1055,7 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     a.bitmap_words = words <= 40 * 1024 ? (int)words : 0;             // <= 160 KB of shared memory
     const size_t smem = (size_t)a.bitmap_words * 4;
     if (smem > 40 * 1024) OCF_CUDA(cudaFuncSetAttribute(k_col_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (200 * 1024) / std::max<size_t>(smem + 5 * 1024, 1)));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (200 * 1024) / std::max<size_t>(smem + 16 * 1024, 1)));
     const int grid = std::max(1, std::min(m->sm_count * per_sm, b->store->dev.n_groups));
     if (bt.n_entries > 0 && b->store->dev.n_groups > 0) {
       g_prof.begin(3, st);

@@ -475,6 +475,7 @@ k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int 
 constexpr int SCAN_SUB = 4096;            // CSC entries per sub-block (256 threads x 16 loads in flight)
 constexpr int SCAN_T_MAX = 16384;         // largest scan block (a store picks 4096, 8192 or 16384)
 constexpr int SCAN_WORDS_MAX = SCAN_T_MAX / 32;
+constexpr int SCAN_STAGE = 2048;          // matches of one group staged in shared memory for task creation
 
 struct ColArgs {
   StoreDev s; BatchDev bt;
@@ -496,6 +497,8 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
   __shared__ int prefix[SCAN_WORDS_MAX + 1];
   __shared__ int s_base, s_tbase;
   __shared__ int s_wsum[8];
+  __shared__ int s_mc[SCAN_STAGE];
+  __shared__ uint8_t s_code[SCAN_STAGE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = a.s.scan_t, nwords = T / 32;
   uint32_t* bitmap = col_smem;
@@ -516,18 +519,20 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
     // phase 1 of a block: match bit of every entry -> words[], exclusive prefix of the word
     // popcounts -> prefix[], block total -> prefix[nwords]
     auto find = [&](int64_t eb) {
+      const int lim = (int)min((int64_t)T, e1 - eb);          // entries of this block
+      const int32_t* cr = a.s.crow + eb;
       for (int sb = 0; sb < T / SCAN_SUB; ++sb) {
         int row[16];
+        const int off0 = sb * SCAN_SUB + warp * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) row[i] = off0 + i * 256 < lim ? cr[off0 + i * 256] : -1;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int64_t e = eb + sb * SCAN_SUB + (warp + 8 * i) * 32 + lane;
-          row[i] = e < e1 ? a.s.crow[e] : -1;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
+          // the bitmap holds exactly this batch's rows, so membership needs no global lookup;
+          // only stores with too many rows for shared memory fall back to the row -> slot map
           bool match = row[i] >= 0;
-          if (match && a.bitmap_words > 0) match = (bitmap[row[i] >> 5] >> (row[i] & 31)) & 1u;
-          if (match) match = (a.bt.rowslot[row[i]] >> SLOT_BITS) == a.bt.tag;
+          if (match) match = a.bitmap_words > 0 ? ((bitmap[row[i] >> 5] >> (row[i] & 31)) & 1u) != 0
+                                                : (a.bt.rowslot[row[i]] >> SLOT_BITS) == a.bt.tag;
           const unsigned m = __ballot_sync(FULL, match);
           if (lane == 0) words[sb * (SCAN_SUB / 32) + warp + 8 * i] = m;
         }
@@ -585,15 +590,33 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
     // phase 3: one head per column segment creates that column's tasks. Task slots are
     // allocated with ONE atomic per 256 matches (block scan of the per-head task counts):
     // per-column atomics on a single counter serialise in L2 and dominated this kernel.
+    // (the group's match columns / codes are staged in shared memory first: a head thread walks
+    // its segment there; walking a heavy column's ~B matches through L2 was this kernel's tail)
+    const bool staged = total <= SCAN_STAGE;
+    if (staged) {
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        s_mc[i] = __ldcg(a.mcol + base + i);
+        s_code[i] = (uint8_t)(__ldcg(a.matches + (size_t)(base + i) * 3) >> 16);
+      }
+      __syncthreads();
+    }
     for (int i0 = 0; i0 < total; i0 += blockDim.x) {
       const int i = i0 + threadIdx.x;
       int c = -1, n = 0, n_tasks = 0;
       int arr[4];
       if (i < total) {
-        c = __ldcg(a.mcol + base + i);
-        if (i == 0 || __ldcg(a.mcol + base + i - 1) != c) {
-          uint32_t any_code = 0;
-          while (i + n < total && __ldcg(a.mcol + base + i + n) == c) { any_code |= __ldcg(a.matches + (size_t)(base + i + n) * 3) >> 16; ++n; }
+        uint32_t any_code = 0;
+        bool head;
+        if (staged) {
+          c = s_mc[i];
+          head = i == 0 || s_mc[i - 1] != c;
+          if (head) while (i + n < total && s_mc[i + n] == c) { any_code |= s_code[i + n]; ++n; }
+        } else {
+          c = __ldcg(a.mcol + base + i);
+          head = i == 0 || __ldcg(a.mcol + base + i - 1) != c;
+          if (head) while (i + n < total && __ldcg(a.mcol + base + i + n) == c) { any_code |= __ldcg(a.matches + (size_t)(base + i + n) * 3) >> 16; ++n; }
+        }
+        if (head) {
           if (a.dense) a.colseg[c] = make_int2(base + i, n);
           else {
             if (a.do_dec && (any_code & CODE_TGT)) arr[n_tasks++] = 0;
