@@ -179,7 +179,9 @@ int ocf_train_step(ocf_model* model, ocf_batch* batch, const ocf_step_args* args
  * dropout off. Sharded: phases 1, 2 then 3 (metrics only). */
 int ocf_eval_step(ocf_model* model, ocf_batch* batch, const ocf_step_args* args,
                   float* host_metrics, void* stream);
-/* model.predict (train.py:239): out[rows, n_cols] = output_mask * full_predictions. */
+/* model.predict (train.py:239): out[rows, n_cols] = output_mask * full_predictions.
+ * Sharded models: the caller runs ocf_eval_step phase 1 and the OCF_BUF_Z all-reduce first; the
+ * output holds this shard's columns. The same holds for ocf_score. */
 int ocf_predict(ocf_model* model, ocf_batch* batch, float* out, void* stream);
 /* Full-catalogue scoring: out[rows, n_cols] = full_predictions (model.py:82-84, the tensor
  * before the mask multiply). `out_is_device` != 0: out is a device pointer and the call does
@@ -196,7 +198,9 @@ int ocf_model_wait_metrics(ocf_model* model, int64_t step, float* host);
 /* Number of steps logged so far (train + eval). */
 int64_t ocf_model_steps_logged(const ocf_model* model);
 
-typedef enum { OCF_BUF_Z = 0, OCF_BUF_DH = 1, OCF_BUF_ROWSTATS = 2 } ocf_buffer;
+/* OCF_BUF_STATS_DH: the row statistics [max_rows, 4] immediately followed by dL/dh [max_rows, hp];
+ * a shard all-reduces its prefix of 4*max_rows + rows*hp floats with one collective. */
+typedef enum { OCF_BUF_Z = 0, OCF_BUF_DH = 1, OCF_BUF_ROWSTATS = 2, OCF_BUF_STATS_DH = 3 } ocf_buffer;
 /* Device pointer + float count of a buffer a sharded step exchanges between phases. */
 int ocf_model_buffer(ocf_model* model, int which, void** device_ptr, int64_t* count);
 /* Device pointer of a weight (kernel or bias, Keras index) in the library's internal layout,

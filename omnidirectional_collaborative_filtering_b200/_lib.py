@@ -40,7 +40,7 @@ AUX_TYPES = {None: 0, "causal": 1, "dropout": 2, "zeros": 3, "both": 4}
 LOSSES = {"mean_squared_error": 0, "mse": 0, "mean_absolute_error": 1, "mae": 1}
 OPTIMIZERS = {"sgd": 0, "adagrad": 1, "rmsprop": 2, "adam": 3}
 N_METRICS = 8
-BUF_Z, BUF_DH, BUF_ROWSTATS = 0, 1, 2
+BUF_Z, BUF_DH, BUF_ROWSTATS, BUF_STATS_DH = 0, 1, 2, 3
 
 _P = C.c_void_p
 _SIGNATURES = {

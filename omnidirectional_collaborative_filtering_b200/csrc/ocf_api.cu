@@ -621,9 +621,11 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   OCF_TRY(ws.get(&m->P1, (size_t)m->max_items * m->hp[0]));
   OCF_TRY(ws.get(&m->P2, (size_t)m->max_items * m->hp[L - 1]));
   OCF_TRY(ws.get(&m->itemstats, (size_t)m->max_items * ROWSTAT_W));
-  OCF_TRY(ws.get(&m->rowstats, (size_t)Bm * ROWSTAT_W, true));
   OCF_TRY(ws.get(&m->dy, (size_t)max_entries, true));
-  OCF_TRY(ws.get(&m->dh_top, (size_t)Bm * m->hp[L - 1], true));
+  // [row statistics | dL/dh of the top hidden layer] share one allocation: a column shard
+  // all-reduces both with a single collective over the prefix 4*max_rows + B*hp floats
+  OCF_TRY(ws.get(&m->rowstats, (size_t)Bm * ROWSTAT_W + (size_t)Bm * m->hp[L - 1], true));
+  m->dh_top = m->rowstats + (size_t)Bm * ROWSTAT_W;
   OCF_TRY(ws.get(&m->col_matches, (size_t)max_entries * 3));
   OCF_TRY(ws.get(&m->col_mcol, (size_t)max_entries));
   return OCF_OK;
@@ -822,6 +824,7 @@ extern "C" int ocf_model_buffer(ocf_model* m, int which, void** ptr, int64_t* co
     case OCF_BUF_Z: *ptr = m->zsum[0]; *count = (int64_t)m->cfg.max_rows * m->hp[0]; break;
     case OCF_BUF_DH: *ptr = m->dh_top; *count = (int64_t)m->cfg.max_rows * m->hp[m->L - 1]; break;
     case OCF_BUF_ROWSTATS: *ptr = m->rowstats; *count = (int64_t)m->cfg.max_rows * ROWSTAT_W; break;
+    case OCF_BUF_STATS_DH: *ptr = m->rowstats; *count = (int64_t)m->cfg.max_rows * (ROWSTAT_W + m->hp[m->L - 1]); break;
     default: return fail(OCF_ERR_INVALID, "ocf_model_buffer: unknown buffer");
   }
   return OCF_OK;
@@ -1138,7 +1141,7 @@ extern "C" int ocf_predict(ocf_model* m, ocf_batch* b, float* out, void* stream_
   OCF_TRY(ensure_dense(m));
   const size_t count = (size_t)b->dev.B * m->cfg.n_cols;
   OCF_CUDA(cudaMemsetAsync(m->dense_out, 0, sizeof(float) * count, st));
-  OCF_TRY(phase_encode(m, b, st));
+  if (!m->cfg.sharded) OCF_TRY(phase_encode(m, b, st));   // a shard's caller has run phase 1 + the z all-reduce
   OCF_TRY(phase_decode(m, b, false, nullptr, m->dense_out, st));
   OCF_CUDA(cudaMemcpyAsync(out, m->dense_out, sizeof(float) * count, cudaMemcpyDeviceToHost, st));
   OCF_CUDA(cudaStreamSynchronize(st));
@@ -1150,7 +1153,7 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   OCF_REQUIRE(out != nullptr, "ocf_score: null output");
   cudaStream_t st = as_stream(stream_);
   const int L = m->L, B = b->dev.B;
-  OCF_TRY(phase_encode(m, b, st));
+  if (!m->cfg.sharded) OCF_TRY(phase_encode(m, b, st));   // a shard's caller has run phase 1 + the z all-reduce
   OCF_TRY(launch_act(m, 0, B, false, nullptr, st));
   for (int l = 1; l < L; ++l) {
     GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];

@@ -49,7 +49,7 @@ class Batch(object):
     """One batch as (row ids, keep flags) + the stores they index. Host-only until uploaded."""
 
     def __init__(self, reader, kind, source, rows, flags, pass_through, aux_type, aux_value,
-                 target_count, return_target_count):
+                 target_count, return_target_count, n_ratings=None):
         self.reader = reader
         self.kind = kind                       # "split" | "fixed"
         self.source = source                   # RatingStore | StorePair
@@ -62,7 +62,8 @@ class Batch(object):
         self.return_target_count = bool(return_target_count)
         self.n_rows = int(self.rows.size)
         self.n_cols = int(source.n_cols)
-        self.n_entries = int(source.lengths[self.rows].sum())
+        self.n_entries = int(source.lengths[self.rows].sum())      # ratings this (shard of the) batch holds
+        self.n_ratings = int(n_ratings) if n_ratings is not None else self.n_entries   # of the full rows
         self._device = None
 
     def upload(self, stream=None):
@@ -127,7 +128,7 @@ class data_reader(object):
 
     def __init__(self, num_items, num_users, filepath, nonsequentialusers=False, use_json=True,
                  eval_mode="ablation", useTimestamps=False, reverse_user_item_data=False, data=None,
-                 stream=None):
+                 stream=None, shard=None):
         if useTimestamps:
             raise NotImplementedError("useTimestamps is broken in the reference (data_reader.py:132,359,409) "
                                       "and out of scope here")
@@ -147,6 +148,16 @@ class data_reader(object):
             self._init_from_split(data)
         else:
             self._init_from_files(use_json, reverse_user_item_data)
+        # column shard (rank, world): this process keeps catalogue columns [lo, hi) of every set;
+        # rows, set orders and the RNG replay stay those of the full data (dist.py)
+        self.shard = shard
+        self.col_range = (0, self.num_items)
+        if shard is not None:
+            rank, world = shard
+            lo, hi = rank * self.num_items // world, (rank + 1) * self.num_items // world
+            self.col_range = (lo, hi)
+            self._stores = {k: v.column_shard(lo, hi) for k, v in self._stores.items()}
+        self.local_cols = self.col_range[1] - self.col_range[0]
         print("Finished loading data")
 
     # -- loading -----------------------------------------------------------------------------
@@ -276,7 +287,9 @@ class data_reader(object):
         num_batches = int(np.floor(n / batch_size))                                  # :329
         if split_mode and np.isscalar(data_sparsity):
             data_sparsity = [data_sparsity, data_sparsity]      # the reference crashes here (Appendix B)
-        lengths = source.lengths
+        src_split = source if split_mode else None
+        lengths = source.full_lengths if split_mode else None      # the RNG replay runs on full rows
+        sharded = split_mode and source.orig_pos is not None
         for i in range(num_batches):
             brow = rows[i * batch_size:(i + 1) * batch_size]
             if split_mode:
@@ -286,12 +299,21 @@ class data_reader(object):
                 p0 = 1 - keep
                 flags = (u >= np.repeat(p0 / (p0 + keep), n_b)).astype(np.uint8)
                 tcount = flags.size if pass_through_input_training else int(flags.size - flags.sum())
+                n_ratings = flags.size
+                if sharded:             # keep the flags of the ratings this column shard holds
+                    rp = src_split.csr.rowptr
+                    loc = rp[brow + 1] - rp[brow]
+                    full_off = np.cumsum(n_b) - n_b
+                    loc_off = np.cumsum(loc) - loc
+                    ent = np.repeat(rp[brow] - loc_off, loc) + np.arange(int(loc.sum()), dtype=np.int64)
+                    flags = flags[np.repeat(full_off, loc) + src_split.orig_pos[ent]]
                 yield Batch(self, "split", source, brow, flags, pass_through_input_training,
-                            auxilliary_mask_type, aux_var_value, tcount, False)
+                            auxilliary_mask_type, aux_var_value, tcount, False, n_ratings)
             else:
-                tcount = int(source.tgt_store.lengths[brow].sum())                                        # :268
+                tcount = int(source.tgt_store.full_lengths[brow].sum())                                   # :268
+                n_ratings = tcount + int(source.in_store.full_lengths[brow].sum())
                 yield Batch(self, "fixed", source, brow, None, False, auxilliary_mask_type,
-                            aux_var_value, tcount, return_target_count)
+                            aux_var_value, tcount, return_target_count, n_ratings)
         while True:                                                                                        # :418-419
             yield None
 

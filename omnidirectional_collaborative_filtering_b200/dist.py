@@ -1,0 +1,248 @@
+"""Multi-GPU: column (catalogue-dimension) sharding over one process per GPU.
+
+Why columns. At the reference's batch size the step is bound by the weight + optimizer-state
+stream, not by the batch, so replicating the weights and all-reducing
+their gradients (66-440 MB per step on ML-10M shapes) cannot scale. The model is separable over
+catalogue columns instead: the encoder is a sum over input columns and the decoder, loss and both
+big weight updates are per output column. Rank g of G therefore owns columns [gN/G, (g+1)N/G):
+those rows of W_enc (every input block), those rows of W_dec^T / entries of b_dec, and those
+ratings of every store. All ranks walk the SAME global batch of rows (same NumPy stream, same row
+order, same keep flags), and one step exchanges only activations:
+
+    phase 1  gather + encoder partial sums          -> all-reduce z        [rows, H]
+    phase 2  activations, decoder, loss partials    -> all-reduce (row stats | dL/dh)  [rows, 4 + H]
+    phase 3  backward + fused optimizer update of the rank's own columns, metrics
+
+Hidden layers and biases are replicated and receive identical updates on every rank. The result
+is the single-GPU model at global batch `rows` (up to fp32 summation order), which is how a
+data-parallel run of G x per-GPU-batch is obtained here ("weak" scaling in bench.py).
+
+`torch.distributed` (NCCL over NVLink/NVSwitch on GPUs; gloo for the CPU tests of the host
+logic) is the plumbing: the collectives run on torch tensors that alias the library's buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+def col_range(n_cols: int, rank: int, world: int):
+    return rank * n_cols // world, (rank + 1) * n_cols // world
+
+
+# ---- weights: full Keras lists <-> per-rank slices ------------------------------------------------
+def slice_weights(full: Sequence[np.ndarray], k_blocks: int, n_cols: int, lo: int, hi: int) -> List[np.ndarray]:
+    """The rank's part of a full `get_weights()` list: rows [blk*N+lo, blk*N+hi) of the first
+    kernel for every input block, columns [lo, hi) of the last kernel and bias; the rest whole."""
+    out = [np.array(w, dtype=np.float32) for w in full]
+    out[0] = np.concatenate([full[0][b * n_cols + lo:b * n_cols + hi] for b in range(k_blocks)], axis=0)
+    out[-2] = np.ascontiguousarray(full[-2][:, lo:hi])
+    out[-1] = np.ascontiguousarray(full[-1][lo:hi])
+    return out
+
+
+def merge_weights(parts: Sequence[Sequence[np.ndarray]], k_blocks: int, n_cols: int) -> List[np.ndarray]:
+    """Inverse of `slice_weights` over all ranks' lists (rank order)."""
+    world = len(parts)
+    out = [np.array(w) for w in parts[0]]
+    blocks = []
+    for b in range(k_blocks):
+        for r in range(world):
+            lo, hi = col_range(n_cols, r, world)
+            w = parts[r][0]
+            blocks.append(w[b * (hi - lo):(b + 1) * (hi - lo)])
+    out[0] = np.concatenate(blocks, axis=0)
+    out[-2] = np.concatenate([p[-2] for p in parts], axis=1)
+    out[-1] = np.concatenate([p[-1] for p in parts], axis=0)
+    return out
+
+
+class _DeviceArray(object):
+    """Minimal `__cuda_array_interface__` carrier so torch can alias a library buffer."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class ShardComm(object):
+    """The two collectives of a sharded step, on torch tensors aliasing the model's buffers."""
+
+    def __init__(self, net, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.net = net
+        self._capacity = None
+        self.z = self.stats_dh = None
+
+    def _alias(self):
+        net = self.net
+        if self._capacity == net._capacity and self.z is not None:
+            return
+        lib = _lib.lib()
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        _lib.check(lib.ocf_model_buffer(net._handle, _lib.BUF_Z, C.byref(ptr), C.byref(cnt)))
+        self.z = self.torch.as_tensor(_DeviceArray(ptr.value, cnt.value), device="cuda")
+        _lib.check(lib.ocf_model_buffer(net._handle, _lib.BUF_STATS_DH, C.byref(ptr), C.byref(cnt)))
+        self.stats_dh = self.torch.as_tensor(_DeviceArray(ptr.value, cnt.value), device="cuda")
+        self._capacity = net._capacity
+        self.hp0 = self.z.numel() // net._capacity[0]
+        self.hpt = self.stats_dh.numel() // net._capacity[0] - 4
+
+    def reduce_z(self, rows: int):
+        self._alias()
+        self.dist.all_reduce(self.z[:rows * self.hp0], group=self.group)
+
+    def reduce_stats_dh(self, rows: int, with_dh: bool):
+        self._alias()
+        n = 4 * self._capacity[0] + (rows * self.hpt if with_dh else 0)
+        self.dist.all_reduce(self.stats_dh[:n], group=self.group)
+
+
+def sharded_model(rank: int, world: int, numlayers, num_hidden_units, input_shape, batch_size, **kw):
+    """`omni_model` for this rank's column slice. Every rank must call it with the same NumPy
+    global RNG state: the full glorot initialisation is drawn identically everywhere and sliced."""
+    from .model import omni_model
+    lo, hi = col_range(int(input_shape), rank, world)
+    om = omni_model(numlayers, num_hidden_units, input_shape, batch_size, local_cols=hi - lo, col_lo=lo, **kw)
+    om.model.comm = ShardComm(om.model)
+    return om
+
+
+def gather_full_weights(om, group=None) -> List[np.ndarray]:
+    """Full Keras-layout weight list assembled from all ranks (every rank gets it)."""
+    import torch.distributed as dist
+    local = om.model.get_weights()
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, local, group=group)
+    return merge_weights(parts, om.k_blocks, om.input_shape)
+
+
+# ---- bench.py, N > 1 ----------------------------------------------------------------------------------
+def bench_main(args, w, cfg, rank, world):
+    """`bench.py --gpus N` under torchrun: weak scaling, global batch = N x batch_size rows, columns
+    sharded over the ranks. Timed with CUDA events, barrier + synchronize on both sides, max over
+    ranks; rank 0 prints the JSON line."""
+    import json
+    import time
+    import torch
+    import torch.distributed as dist
+    import bench
+    from . import optimizers
+    from .data_reader import data_reader
+    from .store import DeviceBatch
+
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.lib()
+    B = args.batch_size * world
+    fs = None
+    if rank == 0:
+        fs = bench.make_dataset(w)             # generate (or load the /tmp cache) once
+    dist.barrier()
+    if fs is None:
+        fs = bench.make_dataset(w)
+    rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs, shard=(rank, world))
+    aux = w["aux"]
+    np.random.seed(0)
+    om = sharded_model(rank, world, w["layers"], w["hidden"], fs.n_cols, B, dense_activation=w["act"],
+                       use_causal_info=aux is not None, use_both_masks=aux == "both",
+                       dropout_probability=w["dropout"], auxilliary_mask_type=aux)
+    m = om.model
+    opt = {"adagrad": optimizers.Adagrad, "rmsprop": optimizers.RMSprop, "adam": optimizers.Adam}[w["opt"][0]](lr=w["opt"][1])
+    m.compile(opt, "mean_squared_error", rating_range=fs.rating_range)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def gen():
+        return rd.data_gen(B, w["sparsity"], "train", True, aux, w["aux_value"], pass_through_input_training=w["pass_through"])
+
+    def endless():
+        g = gen()
+        while True:
+            b = next(g)
+            if b is None:
+                g = gen()
+                continue
+            yield b
+
+    batches = endless()
+    plans = [next(batches) for _ in range(K + W)]
+    m._ensure(B, max(p.n_entries for p in plans), aux, rd)
+    resident = []
+    for p in plans:
+        dev = DeviceBatch(p.n_rows, p.n_entries)
+        dev.fill_split(p.source, p.rows, p.flags, p.pass_through, p.aux_value, None)
+        resident.append(dev)
+
+    def device_steps(devs, first):
+        for k, dev in enumerate(devs):
+            _lib.check(lib.ocf_batch_regather(dev.handle, None))
+            m.step_on_device_batch(dev, B, first + k, train=True)
+
+    device_steps(resident[:W], 0)
+    torch.cuda.synchronize()
+    sampler = bench.ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.ocf_kernel_launches()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    device_steps(resident[W:], W)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = lib.ocf_kernel_launches() - launches0
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ratings = sum(p.n_ratings for p in plans[W:])        # ratings of the global batches (all ranks together)
+
+    # e2e through the public API on every rank: host RNG replay + H2D + phases/collectives + D2H
+    for _ in range(W):
+        m.train_on_batch(next(batches), sync=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    h2d = e_ratings = 0
+    prev = None
+    t0 = time.perf_counter()
+    for _ in range(K):
+        b = next(batches)
+        m.train_on_batch(b, sync=False)
+        sid = m.steps_logged() - 1
+        if prev is not None:
+            m.wait_metrics(prev)
+        prev = sid
+        e_ratings += b.n_ratings
+        h2d += b._device.info()["h2d_bytes"]
+    m.wait_metrics(prev)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    h2d_all = torch.tensor([float(h2d)], device="cuda")
+    dist.all_reduce(h2d_all)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        line = {"metric": "train ratings/sec", "value": ratings / (ms * 1e-3), "unit": "ratings/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(cfg, parallelism="column-sharded x%d, global batch %d rows (%d per GPU), 2 NCCL all-reduces of [rows, H] per step"
+                               % (world, B, args.batch_size), ratings_per_step=ratings / K,
+                               l2="no flush: per-rank weights + optimizer state exceed the 126 MB L2"),
+                "clocks": clocks,
+                "e2e": {"value": e_ratings / float(e2e.item()), "unit": "ratings/s",
+                        "h2d_bytes_per_step": float(h2d_all.item()) / K, "d2h_bytes_per_step": 4 * _lib.N_METRICS * world,
+                        "ms_per_step": 1e3 * float(e2e.item()) / K},
+                "gpu_launches": int(launches)}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

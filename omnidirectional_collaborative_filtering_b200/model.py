@@ -45,6 +45,7 @@ class OmniNet(object):
         self.rating_range = 1.0
         self.metrics_names = list(METRIC_NAMES)
         self.stream = None
+        self.comm = None                # dist.ShardComm when this model is a column shard
         self._step = 0
         self._compiled = False
 
@@ -155,14 +156,38 @@ class OmniNet(object):
     def _metrics_from(self, rec):
         return [float(rec[0]), float(rec[1]), float(rec[2]), float(rec[3]), float(rec[4]), float(rec[5])]
 
+    def _run_step(self, h, dev_handle, n_rows, args, rec, train):
+        """One step through the C ABI; a column shard runs it as three phases with the two
+        activation all-reduces between them (dist.py)."""
+        fn = _lib.lib().ocf_train_step if train else _lib.lib().ocf_eval_step
+        if self.comm is None:
+            args.phase = 0
+            _lib.check(fn(h, dev_handle, C.byref(args), _lib.ptr(rec), self.stream))
+            return
+        args.phase = 1
+        _lib.check(fn(h, dev_handle, C.byref(args), None, self.stream))
+        self.comm.reduce_z(n_rows)
+        args.phase = 2
+        _lib.check(fn(h, dev_handle, C.byref(args), None, self.stream))
+        self.comm.reduce_stats_dh(n_rows, with_dh=train)
+        args.phase = 3
+        _lib.check(fn(h, dev_handle, C.byref(args), _lib.ptr(rec), self.stream))
+
+    def step_on_device_batch(self, dev, n_rows, step, train=True):
+        """A step on an already-filled DeviceBatch, no host sync (bench.py's device-timed loop)."""
+        args = _lib.StepArgs()
+        args.dropout_seed = self.owner.dropout_seed
+        args.step = int(step) & 0xFFFFFFFF
+        self._run_step(self._handle, dev.handle, n_rows, args, None, train)
+
     def train_on_batch(self, batch, sync=True):
         """One optimisation step. Returns the six metric values when `sync`, else None (the
-        values stay in the device log; see `read_metrics`)."""
+        values stay in the device log; see `read_metrics` / `wait_metrics`)."""
         h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
         args = self._args(batch)
         rec = np.empty(_lib.N_METRICS, dtype=np.float32) if sync else None
-        _lib.check(_lib.lib().ocf_train_step(h, dev.handle, C.byref(args), _lib.ptr(rec), self.stream))
+        self._run_step(h, dev.handle, batch.n_rows, args, rec, True)
         self._step += 1
         return self._metrics_from(rec) if sync else None
 
@@ -171,7 +196,7 @@ class OmniNet(object):
         dev = batch.upload(self.stream)
         args = self._args(batch, training=False)
         rec = np.empty(_lib.N_METRICS, dtype=np.float32) if sync else None
-        _lib.check(_lib.lib().ocf_eval_step(h, dev.handle, C.byref(args), _lib.ptr(rec), self.stream))
+        self._run_step(h, dev.handle, batch.n_rows, args, rec, False)
         return self._metrics_from(rec) if sync else None
 
     def steps_logged(self):
@@ -245,6 +270,7 @@ class OmniNet(object):
         """`best_m.predict(input_list)`, train.py:239: output_mask * full_predictions, [B, N] float32."""
         h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
+        self._shard_encode(h, dev, batch)
         out = np.empty((batch.n_rows, self.owner.local_cols), dtype=np.float32)
         _lib.check(_lib.lib().ocf_predict(h, dev.handle, _lib.ptr(out), self.stream))
         return out
@@ -253,9 +279,19 @@ class OmniNet(object):
         """Full-catalogue scores `full_predictions` (model.py:82-84), [B, N] float32."""
         h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
+        self._shard_encode(h, dev, batch)
         out = np.empty((batch.n_rows, self.owner.local_cols), dtype=np.float32)
         _lib.check(_lib.lib().ocf_score(h, dev.handle, _lib.ptr(out), 0, self.stream))
         return out
+
+    def _shard_encode(self, h, dev, batch):
+        """Column shards: encoder partial sums + their all-reduce before predict/score (this
+        rank's output then holds its own columns)."""
+        if self.comm is None:
+            return
+        args = self._args(batch, phase=1, training=False)
+        _lib.check(_lib.lib().ocf_eval_step(h, dev.handle, C.byref(args), None, self.stream))
+        self.comm.reduce_z(batch.n_rows)
 
     def save(self, path):
         """`m.save(...)`, train.py:169 (weights + architecture as .npz; no optimizer state)."""
@@ -289,7 +325,7 @@ class omni_model(object):
     def __init__(self, numlayers, num_hidden_units, input_shape, batch_size, dense_activation="tanh",
                  use_causal_info=True, use_timestamps=False, use_both_masks=False,
                  l2_weight_regulatization=None, sparse_representation=False, dropout_probability=None,
-                 use_sparse_masking_layer=False, auxilliary_mask_type="default", local_cols=None):
+                 use_sparse_masking_layer=False, auxilliary_mask_type="default", local_cols=None, col_lo=0):
         if use_timestamps:
             raise NotImplementedError("use_timestamps: the reference's timestamp path is broken and out of scope")
         if sparse_representation:
@@ -327,18 +363,22 @@ class omni_model(object):
         self.trainable = [True] * (self.numlayers + 1)
         # Keras draws one seed per kernel initializer and per Dropout layer from the global NumPy
         # RNG while the graph is built; keep that stream position.
-        dims = [self.k_blocks * self.local_cols] + self.widths + [self.local_cols]
-        fan = [self.k_blocks * self.input_shape] + self.widths + [self.input_shape]
-        self._host_weights = []
+        self.col_lo = int(col_lo)
+        dims = [self.k_blocks * self.input_shape] + self.widths + [self.input_shape]
+        full = []
         seeds = []
         for l in range(self.numlayers + 1):
             seed = int(np.random.randint(10e6))
-            lim = np.sqrt(6.0 / (fan[l] + fan[l + 1]))                  # glorot_uniform
+            lim = np.sqrt(6.0 / (dims[l] + dims[l + 1]))                # glorot_uniform
             rs = np.random.RandomState(seed)
-            self._host_weights.append(rs.uniform(-lim, lim, size=(dims[l], dims[l + 1])).astype(np.float32))
-            self._host_weights.append(np.zeros(dims[l + 1], dtype=np.float32))
+            full.append(rs.uniform(-lim, lim, size=(dims[l], dims[l + 1])).astype(np.float32))
+            full.append(np.zeros(dims[l + 1], dtype=np.float32))
             if l < self.numlayers and dropout_probability is not None:
                 seeds.append(int(np.random.randint(10e6)))
+        if self.sharded:        # a column shard keeps its slice of the full initialisation
+            from .dist import slice_weights
+            full = slice_weights(full, self.k_blocks, self.input_shape, self.col_lo, self.col_lo + self.local_cols)
+        self._host_weights = full
         self.dropout_seed = (seeds[0] if seeds else 0) | (0x0CF << 32)
         self.model = OmniNet(self)
 

@@ -14,10 +14,14 @@ class RatingStore(object):
     """One set of per-row rating lists (what `data_reader.py:46-70` keeps as dicts) as CSR on
     the host, uploaded to HBM on first use. `build_csc` adds the column index training needs."""
 
-    def __init__(self, csr: Csr, build_csc: bool = False):
+    def __init__(self, csr: Csr, build_csc: bool = False, orig_pos=None, full_lengths=None):
         self.csr = csr
         self.build_csc = bool(build_csc)
         self._handle = None
+        # column shards (dist.py): position of each kept rating inside its full row, and the full
+        # row lengths (the RNG replay and target counts are defined on full rows)
+        self.orig_pos = orig_pos
+        self._full_lengths = full_lengths
 
     @property
     def n_rows(self):
@@ -30,6 +34,21 @@ class RatingStore(object):
     @property
     def lengths(self):
         return np.diff(self.csr.rowptr)
+
+    @property
+    def full_lengths(self):
+        return self.lengths if self._full_lengths is None else self._full_lengths
+
+    def column_shard(self, lo: int, hi: int) -> "RatingStore":
+        """The ratings of catalogue columns [lo, hi), relabelled to 0..hi-lo-1 (rows unchanged)."""
+        c = self.csr
+        keep = (c.col >= lo) & (c.col < hi)
+        rows = np.repeat(np.arange(c.n_rows, dtype=np.int64), np.diff(c.rowptr))
+        pos = np.arange(c.nnz, dtype=np.int64) - c.rowptr[rows]
+        rowptr = np.zeros(c.n_rows + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows[keep], minlength=c.n_rows), out=rowptr[1:])
+        local = Csr(c.n_rows, hi - lo, rowptr, (c.col[keep] - lo).astype(np.int32), c.val[keep].copy())
+        return RatingStore(local, self.build_csc, orig_pos=pos[keep].astype(np.int32), full_lengths=self.lengths)
 
     @property
     def handle(self):
@@ -81,6 +100,9 @@ class StorePair(object):
     @property
     def lengths(self):
         return self.in_store.lengths + self.tgt_store.lengths
+
+    def column_shard(self, lo: int, hi: int) -> "StorePair":
+        return StorePair(self.in_store.column_shard(lo, hi), self.tgt_store.column_shard(lo, hi))
 
     @property
     def handle(self):
