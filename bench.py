@@ -349,9 +349,11 @@ def main():
     e_ratings = 0
     prev = None
     t0 = time.perf_counter()
-    for _ in range(K):
-        b = next(stream_of_batches)               # host: RNG replay -> row ids + keep flags
-        m.train_on_batch(b, sync=False)           # pinned staging + H2D(row ids, flags) + kernels + D2H(metrics)
+    from omnidirectional_collaborative_filtering_b200.data_reader import Prefetcher
+    # generator thread (the reference's GeneratorEnqueuer): RNG replay -> row ids + uniform draws;
+    # main thread: flags + pinned staging + H2D + kernels + the D2H read of every step's metrics
+    for b in Prefetcher(stream_of_batches, K):
+        m.train_on_batch(b, sync=False)
         step_id = m.steps_logged() - 1
         if prev is not None:
             m.wait_metrics(prev)                  # read step i-1's result while step i runs

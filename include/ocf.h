@@ -91,6 +91,15 @@ int ocf_batch_destroy(ocf_batch* batch);
 int ocf_batch_fill_split(ocf_batch* batch, const ocf_store* store, const int32_t* row_ids,
                          int32_t n_rows, const uint8_t* keep_flags, int64_t n_flags,
                          int pass_through, float aux_var_value, void* stream);
+/* Same batch from the raw uniform draws instead of keep flags: u[k] is the k-th double the
+ * reference's np.random.choice calls consume (one per rating of the FULL rows, batch order),
+ * cdf0[r] = (1-s_r)/((1-s_r)+s_r) of batch row r; flag = (u >= cdf0) (data_reader.py:120,130).
+ * For a column shard, orig_pos[e] is the position of the shard's store entry e inside its full
+ * row and full_len[r] the full length of batch row r (both NULL for an unsharded store). */
+int ocf_batch_fill_split_uniform(ocf_batch* batch, const ocf_store* store, const int32_t* row_ids,
+                                 int32_t n_rows, const double* u, int64_t n_u, const double* cdf0,
+                                 const int32_t* orig_pos, const int64_t* full_len, int pass_through,
+                                 float aux_var_value, void* stream);
 /* build_sparse_batch_fixed_split, data_reader.py:202-298. */
 int ocf_batch_fill_fixed(ocf_batch* batch, const ocf_pair* pair, const int32_t* row_ids,
                          int32_t n_rows, float aux_var_value, void* stream);

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "ocf_batch_create": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(_P)]),
     "ocf_batch_destroy": (C.c_int, [_P]),
     "ocf_batch_fill_split": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, C.c_int, C.c_float, _P]),
+    "ocf_batch_fill_split_uniform": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_float, _P]),
     "ocf_batch_fill_fixed": (C.c_int, [_P, _P, _P, C.c_int32, C.c_float, _P]),
     "ocf_batch_regather": (C.c_int, [_P, _P]),
     "ocf_profile_enable": (C.c_int, [C.c_int]),

@@ -92,6 +92,7 @@ struct ocf_batch {
   float aux_value = -1.f;
   int64_t target_count = 0;
   size_t last_h2d = 0;
+  std::vector<uint8_t> flag_scratch;
   Arena mem;
 };
 
@@ -534,6 +535,36 @@ extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const 
   b->target_count = tc;
   b->pass_through = pass_through ? 1 : 0;
   return launch_gather(b, stream);
+}
+
+extern "C" int ocf_batch_fill_split_uniform(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows,
+                                            const double* u, int64_t n_u, const double* cdf0, const int32_t* orig_pos,
+                                            const int64_t* full_len, int pass_through, float aux_var_value, void* stream_) {
+  OCF_REQUIRE(b && store && row_ids && cdf0 && (u || n_u == 0), "ocf_batch_fill_split_uniform: null argument");
+  OCF_REQUIRE(n_rows > 0 && n_rows <= b->max_rows, "ocf_batch_fill_split_uniform: row count exceeds the batch capacity");
+  // keep flag of a rating = (its uniform draw >= cdf0 of its row): exactly what
+  // np.random.choice([0,1], n, p=[1-s, s]) returns for that draw (data_reader.py:130)
+  std::vector<uint8_t>& flags = b->flag_scratch;
+  int64_t total = 0, full_total = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    const int32_t row = row_ids[r];
+    OCF_REQUIRE(row >= 0 && row < store->n_rows, "ocf_batch_fill_split_uniform: row id out of range");
+    total += store->h_rowptr[row + 1] - store->h_rowptr[row];
+    full_total += full_len ? full_len[r] : store->h_rowptr[row + 1] - store->h_rowptr[row];
+  }
+  OCF_REQUIRE(full_total == n_u, "ocf_batch_fill_split_uniform: n_u must equal the total (full) length of the listed rows");
+  flags.resize((size_t)total);
+  int64_t k = 0, off = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    const int32_t row = row_ids[r];
+    const int64_t e0 = store->h_rowptr[row], n = store->h_rowptr[row + 1] - e0;
+    const double c0 = cdf0[r];
+    const double* ur = u + off;
+    if (orig_pos) for (int64_t j = 0; j < n; ++j) flags[k++] = ur[orig_pos[e0 + j]] >= c0;
+    else for (int64_t j = 0; j < n; ++j) flags[k++] = ur[j] >= c0;
+    off += full_len ? full_len[r] : n;
+  }
+  return ocf_batch_fill_split(b, store, row_ids, n_rows, flags.data(), total, pass_through, aux_var_value, stream_);
 }
 
 extern "C" int ocf_batch_fill_fixed(ocf_batch* b, const ocf_pair* pair, const int32_t* row_ids, int32_t n_rows,

@@ -54,7 +54,8 @@ class Batch(object):
         self.kind = kind                       # "split" | "fixed"
         self.source = source                   # RatingStore | StorePair
         self.rows = np.ascontiguousarray(rows, dtype=np.int32)
-        self.flags = flags
+        self._flags = flags                    # uint8 keep flags, or None while only (u, cdf0) are held
+        self.u = self.cdf0 = self.full_len = None
         self.pass_through = bool(pass_through)
         self.aux_type = aux_type
         self.aux_value = float(aux_value)
@@ -66,11 +67,32 @@ class Batch(object):
         self.n_ratings = int(n_ratings) if n_ratings is not None else self.n_entries   # of the full rows
         self._device = None
 
+    @property
+    def flags(self):
+        """uint8 keep flag per rating this batch holds (1 = input). Derived on demand from the
+        uniform draws; `upload` hands the draws to the library instead."""
+        if self._flags is None and self.kind == "split":
+            src = self.source
+            n_full = src.full_lengths[self.rows]
+            full = self.u >= np.repeat(self.cdf0, n_full)
+            if src.orig_pos is not None:        # a column shard keeps the flags of its own ratings
+                rp = src.csr.rowptr
+                loc = rp[self.rows + 1] - rp[self.rows]
+                full_off = np.cumsum(n_full) - n_full
+                loc_off = np.cumsum(loc) - loc
+                ent = np.repeat(rp[self.rows] - loc_off, loc) + np.arange(int(loc.sum()), dtype=np.int64)
+                full = full[np.repeat(full_off, loc) + src.orig_pos[ent]]
+            self._flags = full.astype(np.uint8)
+        return self._flags
+
     def upload(self, stream=None):
         """Stage + copy + gather (K1) into one of the reader's device batch buffers."""
         ring = self.reader._ring_for(self.n_rows, self.n_entries)
         dev = ring.next()
-        if self.kind == "split":
+        if self.kind == "split" and self._flags is None:
+            dev.fill_split_uniform(self.source, self.rows, self.u, self.cdf0, self.full_len, self.pass_through,
+                                   self.aux_value, stream)
+        elif self.kind == "split":
             dev.fill_split(self.source, self.rows, self.flags, self.pass_through, self.aux_value, stream)
         else:
             dev.fill_fixed(self.source, self.rows, self.aux_value, stream)
@@ -115,6 +137,41 @@ class Batch(object):
         if k == 2 and self.return_target_count:
             return self.target_count
         return self._as_tuple()[k]
+
+
+class Prefetcher(object):
+    """Pulls exactly `count` items from a generator on a background thread (bounded queue): the
+    role Keras' GeneratorEnqueuer (workers=1, max_q_size=10) plays for `fit_generator` in the
+    reference. NumPy releases the GIL inside `random_sample`, so the RNG
+    replay of batch i+1 overlaps the staging and kernel launches of batch i. Exactly `count`
+    items are drawn, so the NumPy global stream ends where synchronous consumption would leave
+    it; nothing else may draw from `np.random` while the thread runs."""
+
+    def __init__(self, generator, count, depth=10):
+        import queue
+        import threading
+        self.count = int(count)
+        self.queue = queue.Queue(maxsize=depth)
+        self.error = None
+
+        def work():
+            try:
+                for _ in range(self.count):
+                    self.queue.put(next(generator))
+            except BaseException as exc:          # surfaced on the consumer side
+                self.error = exc
+                self.queue.put(None)
+
+        self.thread = threading.Thread(target=work, daemon=True)
+        self.thread.start()
+
+    def __iter__(self):
+        for _ in range(self.count):
+            item = self.queue.get()
+            if self.error is not None:
+                raise self.error
+            yield item
+        self.thread.join()
 
 
 class data_reader(object):
@@ -297,18 +354,13 @@ class data_reader(object):
                 keep = np.random.uniform(low=data_sparsity[0], high=data_sparsity[1], size=batch_size)   # :120
                 u = np.random.random_sample(int(n_b.sum()))                                               # :130
                 p0 = 1 - keep
-                flags = (u >= np.repeat(p0 / (p0 + keep), n_b)).astype(np.uint8)
-                tcount = flags.size if pass_through_input_training else int(flags.size - flags.sum())
-                n_ratings = flags.size
-                if sharded:             # keep the flags of the ratings this column shard holds
-                    rp = src_split.csr.rowptr
-                    loc = rp[brow + 1] - rp[brow]
-                    full_off = np.cumsum(n_b) - n_b
-                    loc_off = np.cumsum(loc) - loc
-                    ent = np.repeat(rp[brow] - loc_off, loc) + np.arange(int(loc.sum()), dtype=np.int64)
-                    flags = flags[np.repeat(full_off, loc) + src_split.orig_pos[ent]]
-                yield Batch(self, "split", source, brow, flags, pass_through_input_training,
-                            auxilliary_mask_type, aux_var_value, tcount, False, n_ratings)
+                cdf0 = p0 / (p0 + keep)            # np.random.choice: cdf = cumsum(p) / cumsum(p)[-1]
+                tcount = int(u.size) if pass_through_input_training else -1   # split batches do not report it
+                batch = Batch(self, "split", source, brow, None, pass_through_input_training,
+                              auxilliary_mask_type, aux_var_value, tcount, False, int(u.size))
+                batch.u, batch.cdf0 = u, cdf0
+                batch.full_len = n_b if sharded else None
+                yield batch
             else:
                 tcount = int(source.tgt_store.full_lengths[brow].sum())                                   # :268
                 n_ratings = tcount + int(source.in_store.full_lengths[brow].sum())

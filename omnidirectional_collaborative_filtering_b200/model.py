@@ -216,16 +216,17 @@ class OmniNet(object):
             _lib.check(_lib.lib().ocf_model_read_metrics(self._handle, first, count, _lib.ptr(out), self.stream))
         return out
 
-    def _run(self, generator, steps, train):
-        """`steps` batches through train/eval steps. Steps are enqueued without a host sync (the
-        host builds batch i+1's row ids / flags while the device runs step i) and the metric
-        records, copied to pinned memory behind every step, are read back in chunks."""
+    def _run(self, generator, steps, train, workers=1):
+        """`steps` batches through train/eval steps. Steps are enqueued without a host sync and
+        the metric records, copied to pinned memory behind every step, are read back in chunks.
+        workers=1 (Keras' default) draws the batches on a prefetch thread, workers=0 inline."""
+        from .data_reader import Prefetcher
         steps = int(steps)
         rows = []
         first = None
         pending = 0
-        for _ in range(steps):
-            batch = next(generator)
+        source = Prefetcher(generator, steps) if workers else (next(generator) for _ in range(steps))
+        for batch in source:
             if batch is None:
                 raise StopIteration("generator ran out of batches (it yields None after floor(n/B) batches)")
             if first is None:
@@ -242,18 +243,18 @@ class OmniNet(object):
         return np.concatenate(rows, axis=0) if rows else np.zeros((0, _lib.N_METRICS), dtype=np.float32)
 
     def fit_generator(self, generator, steps_per_epoch, epochs=1, verbose=1, callbacks=None,
-                      validation_data=None, validation_steps=None, **_ignored):
+                      validation_data=None, validation_steps=None, workers=1, **_ignored):
         """`m.fit_generator(train_gen, steps, validation_data=valid_gen, validation_steps=...)`,
         train.py:157-158. Per-epoch value = mean of the per-batch values; training values are
         pre-update with dropout on, validation has dropout off (Keras semantics)."""
         hist = History()
         for epoch in range(int(epochs)):
-            recs = self._run(generator, steps_per_epoch, train=True)
+            recs = self._run(generator, steps_per_epoch, train=True, workers=workers)
             mean = recs[:, :6].astype(np.float64).mean(axis=0) if len(recs) else np.full(6, np.nan)
             for name, v in zip(METRIC_NAMES, mean):
                 hist.history.setdefault(name, []).append(float(v))
             if validation_data is not None:
-                vals = self.evaluate_generator(validation_data, validation_steps)
+                vals = self.evaluate_generator(validation_data, validation_steps, workers=workers)
                 for name, v in zip(METRIC_NAMES, vals):
                     hist.history.setdefault("val_" + name, []).append(float(v))
             hist.epoch.append(epoch)
@@ -261,9 +262,9 @@ class OmniNet(object):
                 print(" - ".join("%s: %.4f" % (k, v[-1]) for k, v in hist.history.items()))
         return hist
 
-    def evaluate_generator(self, generator, steps, **_ignored):
+    def evaluate_generator(self, generator, steps, workers=1, **_ignored):
         """train.py:208,218. Returns [loss, mae, accurate_MAE, nMAE, accurate_RMSE, accurate_MSE]."""
-        recs = self._run(generator, steps, train=False)
+        recs = self._run(generator, steps, train=False, workers=workers)
         return [float(v) for v in recs[:, :6].astype(np.float64).mean(axis=0)]
 
     def predict(self, batch, batch_size=None, verbose=0):

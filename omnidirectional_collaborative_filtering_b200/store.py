@@ -142,6 +142,19 @@ class DeviceBatch(object):
                                                    _lib.ptr(flags), flags.size, int(bool(pass_through)),
                                                    float(aux_value), stream))
 
+    def fill_split_uniform(self, store: RatingStore, rows: np.ndarray, u: np.ndarray, cdf0: np.ndarray,
+                           full_len, pass_through: bool, aux_value: float, stream=None):
+        """Like fill_split, from the raw uniform draws: the library derives the keep flags
+        (u >= cdf0 of the row) while it stages the batch."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        cdf0 = np.ascontiguousarray(cdf0, dtype=np.float64)
+        orig = None if store.orig_pos is None else np.ascontiguousarray(store.orig_pos, dtype=np.int32)
+        fl = None if full_len is None else np.ascontiguousarray(full_len, dtype=np.int64)
+        _lib.check(_lib.lib().ocf_batch_fill_split_uniform(self.handle, store.handle, _lib.ptr(rows), rows.size,
+                                                           _lib.ptr(u), u.size, _lib.ptr(cdf0), _lib.ptr(orig),
+                                                           _lib.ptr(fl), int(bool(pass_through)), float(aux_value), stream))
+
     def fill_fixed(self, pair: StorePair, rows: np.ndarray, aux_value: float, stream=None):
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         _lib.check(_lib.lib().ocf_batch_fill_fixed(self.handle, pair.handle, _lib.ptr(rows), rows.size,
