@@ -1,11 +1,13 @@
 // libocf_b200: the C ABI of include/ocf.h over the kernels in ocf_kernels.cuh.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "ocf_kernels.cuh"
+#include "ocf_score_tc.cuh"
 
 namespace ocf {
 
@@ -129,6 +131,11 @@ struct ocf_model {
   int4* col_tasks = nullptr;
   int* col_counters = nullptr;
   int sm_count = 148;
+  // tcgen05 scoring: TMA maps of the decoder kernel and of the top activation
+  CUtensorMap map_w{}, map_h{};
+  bool map_w_ok = false, map_h_ok = false;
+  int map_h_box = 0;
+  long long act_rows = 0;         // rows the activation buffers hold (max_rows padded to 256)
   // optimizer
   int opt_kind = OCF_OPT_ADAGRAD;
   float lr = 0.005f, p1 = 0.9f, p2 = 0.999f, eps = 1e-8f, decay = 0.f;
@@ -637,6 +644,8 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   m->cfg.max_entries = max_entries;
   m->max_items = max_items_for(max_rows, max_entries);
   const int L = m->L, Bm = max_rows;
+  m->act_rows = (long long)align_up((size_t)Bm, 256);   // whole TMA boxes of the scoring GEMM
+  m->map_h_ok = false;
   m->zsum.assign(L, nullptr); m->act.assign(L, nullptr); m->h.assign(L, nullptr);
   m->dscale.assign(L, nullptr); m->dz.assign(L, nullptr);
   const bool drop = m->cfg.dropout_p > 0.f;
@@ -644,7 +653,7 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   for (int l = 0; l < L; ++l) {
     const size_t n = (size_t)Bm * m->hp[l];
     OCF_TRY(ws.get(&m->zsum[l], n, true));
-    OCF_TRY(ws.get(&m->act[l], n, true));
+    OCF_TRY(ws.get(&m->act[l], (size_t)m->act_rows * m->hp[l], true));
     OCF_TRY(ws.get(&m->dz[l], n, true));
     if (drop) { OCF_TRY(ws.get(&m->h[l], n, true)); OCF_TRY(ws.get(&m->dscale[l], n, true)); }
     else m->h[l] = m->act[l];
@@ -689,7 +698,8 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
     if (l == 0) { ly.fan_in = m->nblk * N; ly.fan_out = cfg->widths[0]; ly.rows = m->nblk * N; ly.hp = m->hp[0]; ly.bias_len = m->hp[0]; }
     else if (l < L) { ly.fan_in = cfg->widths[l - 1]; ly.fan_out = cfg->widths[l]; ly.rows = m->hp[l - 1]; ly.hp = m->hp[l]; ly.bias_len = m->hp[l]; }
     else { ly.fan_in = cfg->widths[L - 1]; ly.fan_out = N; ly.rows = N; ly.hp = m->hp[L - 1]; ly.bias_len = N; }
-    st = m->mem.get(&ly.W, (size_t)ly.rows * ly.hp, true);
+    // the decoder kernel is padded (zeros) to whole 128-column tiles of the scoring GEMM
+    st = m->mem.get(&ly.W, (l == L ? align_up((size_t)ly.rows, tc::TILE_M) : (size_t)ly.rows) * ly.hp, true);
     if (!st) st = m->mem.get(&ly.b, (size_t)ly.bias_len, true);
   }
   if (st) return bail(st);
@@ -1193,9 +1203,26 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   }
   float* dst = out;
   if (!out_is_device) { OCF_TRY(ensure_dense(m)); dst = m->dense_out; }
-  GemmEpi ep{}; ep.kind = EPI_BIAS_COL; ep.C = dst; ep.ldc = m->cfg.n_cols; ep.aux0 = m->layers[L].b;
+  // decoder GEMM on the tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM (ocf_score_tc.cuh)
+  const Layer& dec = m->layers[L];
+  const int hpt = m->hp[L - 1];
+  static const bool trunc = std::getenv("OCF_TC_TRUNCATE") != nullptr;   // diagnostic: let the MMA truncate fp32 -> tf32
+  if (!m->map_w_ok) {
+    OCF_TRY(tc::make_map(&m->map_w, dec.W, hpt, (long long)align_up((size_t)m->cfg.n_cols, tc::TILE_M), tc::TILE_M, !trunc));
+    m->map_w_ok = true;
+  }
+  const int nb = tc::chunk_rows(B);
+  if (!m->map_h_ok || m->map_h_box != nb) {
+    OCF_TRY(tc::make_map(&m->map_h, m->act[L - 1], hpt, m->act_rows, nb, !trunc));
+    m->map_h_ok = true; m->map_h_box = nb;
+  }
+  tc::ScoreArgs sa{};
+  sa.bias = dec.b; sa.out = dst; sa.ldo = m->cfg.n_cols; sa.n_cols = m->cfg.n_cols; sa.n_rows = B;
+  sa.num_k = hpt / tc::BLOCK_K; sa.n_mtiles = (m->cfg.n_cols + tc::TILE_M - 1) / tc::TILE_M; sa.n_chunks = (B + nb - 1) / nb;
   g_prof.begin(4, st);
-  OCF_TRY(launch_gemm(false, true, m->act[L - 1], m->hp[L - 1], m->layers[L].W, m->hp[L - 1], B, m->cfg.n_cols, m->hp[L - 1], ep, st));
+  if (nb == 64) OCF_TRY(tc::launch_score_nb<64>(m->map_w, m->map_h, sa, m->sm_count, st));
+  else if (nb == 128) OCF_TRY(tc::launch_score_nb<128>(m->map_w, m->map_h, sa, m->sm_count, st));
+  else OCF_TRY(tc::launch_score_nb<256>(m->map_w, m->map_h, sa, m->sm_count, st));
   g_prof.end(4, st);
   if (!out_is_device) {
     OCF_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * (size_t)B * m->cfg.n_cols, cudaMemcpyDeviceToHost, st));
