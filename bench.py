@@ -63,6 +63,90 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak_tf32():
+    """Dense tf32 peak in TFLOP/s: kind::tf32 runs at half the bf16 rate (K = 8 instead of 16 per
+    tcgen05.mma of the same duration), so it is derived from the measured cuBLAS bf16 burst figure."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]) / 2.0, "measured bf16 burst / 2 (MEASURED_PEAKS.json)"
+    return 1590.0 / 2.0, "fallback bf16 / 2 (B200_PROFILING.md)"
+
+
+def scoring_run(lib, m, rd, w, aux, rows, reps, warm):
+    """Full-catalogue scoring (train.py:239 `predict` without the mask multiply) of `rows`
+    validation rows per call: device-timed with the scores left in HBM, then end to end through
+    `model.score` (host row ids in, [rows, N] float32 out)."""
+    import ctypes as C
+    import torch
+    from omnidirectional_collaborative_filtering_b200 import _lib
+    rows = min(rows, rd.val_set_size)
+    gen = rd.data_gen(rows, None, "valid", True, aux, w["aux_value"])
+    batches = []
+    while len(batches) < 4:
+        b = next(gen)
+        if b is None:
+            if not batches:
+                raise RuntimeError("validation set smaller than one scoring batch")
+            break
+        batches.append(b)
+    h = m._ensure(rows, max(b.n_entries for b in batches), aux, rd)
+    from omnidirectional_collaborative_filtering_b200.store import DeviceBatch
+    devs = []
+    for b in batches:
+        d = DeviceBatch(b.n_rows, b.n_entries)
+        d.fill_fixed(b.source, b.rows, b.aux_value, None)
+        devs.append(d)
+    N = m.owner.local_cols
+    out = torch.empty((rows, N), dtype=torch.float32, device="cuda")
+    optr = C.c_void_p(out.data_ptr())
+
+    def run(n, first=0):
+        for k in range(n):
+            d = devs[(first + k) % len(devs)]
+            _lib.check(lib.ocf_batch_regather(d.handle, None))
+            _lib.check(lib.ocf_score(h, d.handle, optr, 1, None))
+
+    run(warm)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.ocf_kernel_launches()
+    e0.record()
+    run(reps)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.ocf_kernel_launches() - l0
+    ms = e0.elapsed_time(e1) / reps
+    lib.ocf_profile_reset()
+    lib.ocf_profile_enable(1)
+    run(reps)
+    torch.cuda.synchronize()
+    lib.ocf_profile_enable(0)
+    tot, cnt = C.c_double(), C.c_int64()
+    _lib.check(lib.ocf_profile_read(4, C.byref(tot), C.byref(cnt)))
+    gemm_ms = tot.value / max(cnt.value, 1)
+    H = w["hidden"] if isinstance(w["hidden"], int) else w["hidden"][-1]
+    hp = (H + 127) // 128 * 128
+    flops = 2.0 * rows * hp * N                        # the padded contraction the tensor cores run
+    peak, src = tensor_peak_tf32()
+    # end to end: host batch -> scores in a host array, every call
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(reps, 5))
+    for k in range(n_e2e):
+        res = m.score(batches[k % len(batches)])
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    return {"rows_per_call": rows, "n_cols": int(N), "value": rows / (ms * 1e-3), "unit": "rows/s", "ms_per_call": ms,
+            "gpu_launches": int(launches),
+            "e2e": {"value": rows / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(devs[0].info()["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(res.nbytes), "ms_per_call": 1e3 * e2e_s,
+                    "note": "bounded by the PCIe read-back of the [rows, N] float32 score matrix"},
+            "roofline": {"kernel": "k_score_tc (tcgen05 kind::tf32)", "bound": "tensor", "achieved": flops / (gemm_ms * 1e-3) / 1e12,
+                         "peak": peak, "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                         "peak_source": src, "kernel_ms": gemm_ms, "share_of_step": gemm_ms / ms,
+                         "out_GBs": 4.0 * rows * N / (gemm_ms * 1e-3) / 1e9}}
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -203,6 +287,9 @@ def main():
     ap.add_argument("--batch-size", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "score"],
+                    help="score: full-catalogue scoring rows/s as the line's metric (the train line carries it under 'scoring')")
+    ap.add_argument("--score-rows", type=int, default=1024)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -249,6 +336,18 @@ def main():
     opt = {"adagrad": optimizers.Adagrad, "rmsprop": optimizers.RMSprop, "adam": optimizers.Adam}[w["opt"][0]](lr=w["opt"][1])
     m.compile(opt, "mean_squared_error", rating_range=fs.rating_range)
     K, W = args.steps, max(args.warmup, 3)
+
+    if args.mode == "score":
+        sampler = ClockSampler(0)
+        sc = scoring_run(lib, m, rd, w, aux, args.score_rows, K, W)
+        line = {"metric": "full-catalogue scoring rows/sec", "value": sc["value"], "unit": "rows/s", "n_gpus": 1, "steps": K,
+                "warmup": W, "ms_per_step": sc["ms_per_call"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32 operands, f32 accumulate", "data": "synthetic",
+                "config": dict(cfg, rows_per_call=sc["rows_per_call"], n_cols=sc["n_cols"],
+                               l2="outputs (%.0f MB per call) exceed the 126 MB L2" % (4e-6 * sc["rows_per_call"] * sc["n_cols"])),
+                "clocks": sampler.stop(), "e2e": sc["e2e"], "gpu_launches": sc["gpu_launches"], "roofline": sc["roofline"]}
+        print(json.dumps(line))
+        return 0
 
     def gen():
         return rd.data_gen(B, w["sparsity"], "train", True, aux, w["aux_value"], pass_through_input_training=w["pass_through"])
@@ -374,6 +473,10 @@ def main():
             "e2e": {"value": e_ratings / e2e_s, "unit": "ratings/s", "h2d_bytes_per_step": h2d / K,
                     "d2h_bytes_per_step": 4 * _lib.N_METRICS, "ms_per_step": 1e3 * e2e_s / K},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
+    try:
+        line["scoring"] = scoring_run(lib, m, rd, w, aux, args.score_rows, 10, 3)
+    except Exception as e:                                  # the train line must not depend on it
+        line["scoring"] = {"error": str(e)}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference(w, fs, B, 1000, 1, budget_s=args.cpu_seconds).items()
                                 if k in ("value", "unit", "cores", "kind", "sample", "overlapped_value")}
