@@ -131,6 +131,10 @@ struct ocf_model {
   int4* col_tasks = nullptr;
   int* col_counters = nullptr;
   int sm_count = 148;
+  // the column scan (K4a) needs only the gathered batch: it runs on a side stream beside K2/K3
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool scan_pending = false;
   // tcgen05 scoring: TMA maps of the decoder kernel and of the top activation
   CUtensorMap map_w{}, map_h{};
   bool map_w_ok = false, map_h_ok = false;
@@ -714,6 +718,10 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   for (int k = 0; k < 64; ++k)
     if (cudaEventCreateWithFlags(&m->step_ev[k], cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(OCF_ERR_CUDA, "ocf_model_create: event creation failed"));
+  if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess)
+    return bail(fail(OCF_ERR_CUDA, "ocf_model_create: side stream creation failed"));
   *out = m;
   st = ocf_model_set_optimizer(m, OCF_OPT_ADAGRAD, 0.005f, 0.9f, 0.999f, 1e-8f, 0.f);   // train.py:50-51
   if (st) { *out = nullptr; return bail(st); }
@@ -725,6 +733,9 @@ extern "C" int ocf_model_destroy(ocf_model* m) {
     m->mem.release(); m->opt_mem.release(); m->dense_mem.release(); m->ws_mem.release();
     if (m->h_rec) cudaFreeHost(m->h_rec);
     for (int k = 0; k < 64; ++k) if (m->step_ev[k]) cudaEventDestroy(m->step_ev[k]);
+    if (m->side) cudaStreamDestroy(m->side);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
   }
   return OCF_OK;
@@ -1049,6 +1060,72 @@ static int launch_row_update(int hp, int kind, int grid, const RowArgs& r, cudaS
   return OCF_OK;
 }
 
+// K4a: the store's CSC row ids against the batch's rows -> match list + update tasks.
+static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int dense, cudaStream_t st) {
+  if (!do_dec && !do_enc) return OCF_OK;
+  const BatchDev& bt = b->dev;
+  OCF_CUDA(cudaMemsetAsync(m->col_counters, 0, 2 * sizeof(int), st));
+  if (dense) OCF_CUDA(cudaMemsetAsync(m->col_seg, 0, sizeof(int2) * (size_t)m->cfg.n_cols, st));
+  if (bt.n_entries == 0 || b->store->dev.n_groups == 0) return OCF_OK;
+  ColArgs a{};
+  a.s = b->store->dev; a.bt = bt;
+  a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.dense = dense;
+  a.do_dec = do_dec; a.do_enc = do_enc;
+  a.err_flag = m->d_err; a.matches = m->col_matches; a.mcol = m->col_mcol; a.tasks = m->col_tasks;
+  a.colseg = m->col_seg; a.counters = m->col_counters; a.max_matches = (int)m->cfg.max_entries;
+  const int64_t words = (b->store->n_rows + 31) / 32;
+  a.bitmap_words = words <= 40 * 1024 ? (int)words : 0;             // <= 160 KB of shared memory
+  const size_t smem = (size_t)a.bitmap_words * 4;
+  if (smem > 40 * 1024) OCF_CUDA(cudaFuncSetAttribute(k_col_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (200 * 1024) / std::max<size_t>(smem + 16 * 1024, 1)));
+  const int grid = std::max(1, std::min(m->sm_count * per_sm, b->store->dev.n_groups));
+  g_prof.begin(3, st);
+  k_col_scan<<<grid, 256, smem, st>>>(a);
+  OCF_LAUNCHED();
+  g_prof.end(3, st);
+  return OCF_OK;
+}
+
+// K4b: one warp per (column, array) task: gradient row from the matches, fused optimizer update.
+static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int hpx, const OptDev& opt, cudaStream_t st) {
+  if (!do_dec && !do_enc) return OCF_OK;
+  const int L = m->L;
+  const bool drop = m->cfg.dropout_p > 0.f;
+  Layer& enc = m->layers[0];
+  Layer& dec = m->layers[L];
+  RowArgs r{};
+  r.matches = m->col_matches; r.tasks = m->col_tasks; r.colseg = m->col_seg; r.counters = m->col_counters;
+  r.hdec = drop ? m->h[L - 1] : m->act[L - 1]; r.dz0 = m->dz[0]; r.dy = m->dy;
+  r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
+  r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
+  r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.aux_val = b->aux_value; r.opt = opt;
+  r.dense = opt.dense; r.n_arr = 0;
+  if (do_dec) r.arr_map[r.n_arr++] = 0;
+  if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
+  g_prof.begin(5, st);
+  OCF_TRY(launch_row_update(hpx, opt.kind, m->sm_count * 6, r, st));
+  g_prof.end(5, st);
+  return OCF_OK;
+}
+
+// Start the column scan of a training step on the side stream, ordered after everything already
+// enqueued on `st` (the batch's gather, the previous step's update which reads the match list).
+static int fork_scan(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
+  m->scan_pending = false;
+  const int L = m->L;
+  if (m->hp[L - 1] != m->hp[0]) return OCF_OK;
+  const OptDev opt = make_opt(m);
+  if (b->dev.n_entries == 0 && !opt.dense) return OCF_OK;
+  const int do_dec = m->layers[L].trainable ? 1 : 0, do_enc = m->layers[0].trainable ? 1 : 0;
+  if (!do_dec && !do_enc) return OCF_OK;
+  OCF_CUDA(cudaEventRecord(m->ev_fork, st));
+  OCF_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+  OCF_TRY(launch_scan(m, b, do_dec, do_enc, opt.dense, m->side));
+  OCF_CUDA(cudaEventRecord(m->ev_join, m->side));
+  m->scan_pending = true;
+  return OCF_OK;
+}
+
 // phase 3 (training): backward through the hidden layers, fused updates, metrics
 static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* args, cudaStream_t st) {
   const BatchDev& bt = b->dev;
@@ -1085,47 +1162,19 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   Layer& enc = m->layers[0];
   Layer& dec = m->layers[L];
   const int hpd = m->hp[L - 1], hpe = m->hp[0];
-  auto col_update = [&](int do_dec, int do_enc, int hpx) -> int {
-    if (!do_dec && !do_enc) return OCF_OK;
-    OCF_CUDA(cudaMemsetAsync(m->col_counters, 0, 2 * sizeof(int), st));
-    if (opt.dense) OCF_CUDA(cudaMemsetAsync(m->col_seg, 0, sizeof(int2) * (size_t)m->cfg.n_cols, st));
-    ColArgs a{};
-    a.s = b->store->dev; a.bt = bt; a.dy = m->dy;
-    a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.dense = opt.dense;
-    a.do_dec = do_dec; a.do_enc = do_enc;
-    a.err_flag = m->d_err; a.matches = m->col_matches; a.mcol = m->col_mcol; a.tasks = m->col_tasks;
-    a.colseg = m->col_seg; a.counters = m->col_counters; a.max_matches = (int)m->cfg.max_entries;
-    const int64_t words = (b->store->n_rows + 31) / 32;
-    a.bitmap_words = words <= 40 * 1024 ? (int)words : 0;             // <= 160 KB of shared memory
-    const size_t smem = (size_t)a.bitmap_words * 4;
-    if (smem > 40 * 1024) OCF_CUDA(cudaFuncSetAttribute(k_col_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (200 * 1024) / std::max<size_t>(smem + 16 * 1024, 1)));
-    const int grid = std::max(1, std::min(m->sm_count * per_sm, b->store->dev.n_groups));
-    if (bt.n_entries > 0 && b->store->dev.n_groups > 0) {
-      g_prof.begin(3, st);
-      k_col_scan<<<grid, 256, smem, st>>>(a);
-      OCF_LAUNCHED();
-      g_prof.end(3, st);
-    }
-    RowArgs r{};
-    r.matches = m->col_matches; r.tasks = m->col_tasks; r.colseg = m->col_seg; r.counters = m->col_counters;
-    r.hdec = drop ? m->h[L - 1] : m->act[L - 1]; r.dz0 = m->dz[0];
-    r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
-    r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
-    r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.aux_val = b->aux_value; r.opt = opt;
-    r.dense = opt.dense; r.n_arr = 0;
-    if (do_dec) r.arr_map[r.n_arr++] = 0;
-    if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
-    g_prof.begin(5, st);
-    OCF_TRY(launch_row_update(hpx, opt.kind, m->sm_count * 6, r, st));
-    g_prof.end(5, st);
-    return OCF_OK;
-  };
   if (bt.n_entries > 0 || opt.dense) {
     // decoder and encoder rows share one padded width in the reference's architectures (one
     // num_hidden_units): one scan feeds both. A width list with different ends scans twice.
-    if (hpd == hpe) OCF_TRY(col_update(dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd));
-    else { OCF_TRY(col_update(dec.trainable ? 1 : 0, 0, hpd)); OCF_TRY(col_update(0, enc.trainable ? 1 : 0, hpe)); }
+    if (hpd == hpe) {
+      if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
+      else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, opt.dense, st));
+      OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd, opt, st));
+    } else {
+      OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, 0, opt.dense, st));
+      OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, 0, hpd, opt, st));
+      OCF_TRY(launch_scan(m, b, 0, enc.trainable ? 1 : 0, opt.dense, st));
+      OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st));
+    }
   }
   m->iterations += 1;
   return launch_metrics(m, B, args, n_reg, st);
@@ -1149,7 +1198,7 @@ extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* a
   cudaStream_t st = as_stream(stream_);
   const int phase = args ? args->phase : 0;
   OCF_REQUIRE(phase >= 0 && phase <= 3, "ocf_train_step: phase must be 0..3");
-  if (phase == 0 || phase == 1) OCF_TRY(phase_encode(m, b, st));
+  if (phase == 0 || phase == 1) { OCF_TRY(fork_scan(m, b, st)); OCF_TRY(phase_encode(m, b, st)); }
   if (phase == 0 || phase == 2) OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
   if (phase == 0 || phase == 3) { OCF_TRY(phase_update(m, b, args, st)); OCF_TRY(finish_step(m, host_metrics, st)); }
   return OCF_OK;

@@ -459,7 +459,7 @@ k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int 
 //              columns (<= SCAN_T entries, or one longer column) and tests every entry's row
 //              against a shared-memory bitmap of the batch's rows. The matches (~1 % of the
 //              entries) are compacted IN CSC ORDER (ballot words + prefix sum, no sorting, no
-//              float atomics) into a global match list as (batch row, code, value, dy) records,
+//              float atomics) into a global match list as (batch row, code, value, entry) records,
 //              so each column's matches are contiguous and deterministic. One task per weight row
 //              that must change is appended to a task list:
 //                array 0      decoder row  WdecT[c,:]  (+ b_dec[c])   needs a target entry
@@ -479,10 +479,9 @@ constexpr int SCAN_STAGE = 2048;          // matches of one group staged in shar
 
 struct ColArgs {
   StoreDev s; BatchDev bt;
-  const float* dy;
   int n_cols; int nblk; int3 bits; int dense; int do_dec; int do_enc;
   int* err_flag;
-  uint32_t* matches;      // [max_entries * 3]  b | code << 16, value bits, dy bits
+  uint32_t* matches;      // [max_entries * 3]  b | code << 16, value bits, batch entry index (-> dy)
   int32_t* mcol;          // [max_entries]      catalogue column of the match
   int4* tasks;            // sparse rules: (column, array, first match, match count)
   int2* colseg;           // dense rules:  per column (first match, match count), zeroed per step
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
         const size_t idx = (size_t)(base + running + t);
         a.matches[idx * 3] = b | ((uint32_t)a.bt.codes[p] << 16);
         a.matches[idx * 3 + 1] = __float_as_uint(a.bt.ent_val[p]);
-        a.matches[idx * 3 + 2] = __float_as_uint(a.dy[p]);
+        a.matches[idx * 3 + 2] = (uint32_t)p;   // the scan needs nothing of the forward pass: it runs beside it
         a.mcol[idx] = a.s.ccol[e];
       }
       running += block_total;
@@ -649,7 +648,7 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
 
 struct RowArgs {
   const uint32_t* matches; const int4* tasks; const int2* colseg; const int* counters;
-  const float* hdec; const float* dz0;
+  const float* hdec; const float* dz0; const float* dy;
   float* WdecT; float* Wd_s1; float* Wd_s2;
   float* bdec; float* bd_s1; float* bd_s2;
   float* Wenc; float* We_s1; float* We_s2;
@@ -697,7 +696,7 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
       if (i0 + lane < n) {
         const uint32_t* rec = a.matches + (size_t)(base + i0 + lane) * 3;
         bc = rec[0];
-        coef = arr == 0 ? __uint_as_float(rec[2]) : (arr == 1 ? __uint_as_float(rec[1]) : a.aux_val);
+        coef = arr == 0 ? __ldg(a.dy + rec[2]) : (arr == 1 ? __uint_as_float(rec[1]) : a.aux_val);
       }
       unsigned m = __ballot_sync(FULL, ((bc >> 16) & bit) != 0);
       while (m) {

@@ -93,7 +93,8 @@ def test_train_steps_match_oracle(golden_datasets, case):
     _close(om.model.test_on_batch(vb), ref.test_on_batch(vfeed, vt))
     _close(om.model.predict(vb), ref.predict(vfeed), rtol=1e-3, atol=1e-5)
     # tensor-core scoring rounds its operands to tf32 (2^-11): see tests/test_gpu_score.py
-    _close(om.model.score(vb), ref.score(vfeed), rtol=2e-3, atol=2e-3)
+    want_scores = ref.score(vfeed)
+    _close(om.model.score(vb), want_scores, rtol=2e-3, atol=2e-3 * max(1.0, float(np.abs(want_scores).max())))
     rd.close()
 
 
