@@ -360,6 +360,7 @@ def main():
         if b is None:
             g = gen()
             continue
+        b.flags                             # spend the batch's draws now (device RNG: upload + read back)
         plans.append(b)
     m._ensure(B, max(p.n_entries for p in plans), aux, rd)      # workspaces sized once for any batch of the set
     resident = []
@@ -431,27 +432,30 @@ def main():
                 "share_of_step": tag_ms[dom] / (ms / K)}
 
     # ---- e2e: the public API, host buffers in, metrics out, every step ---------------------------
-    def endless():
-        g = gen()
-        while True:
-            b = next(g)
-            if b is None:
-                g = gen()
-                continue
-            yield b
+    from omnidirectional_collaborative_filtering_b200.data_reader import Prefetcher
+    per_epoch = rd.train_set_size // B
 
-    stream_of_batches = endless()
-    for _ in range(W):
-        m.train_on_batch(next(stream_of_batches), sync=True)
+    def epochs(total):
+        """`total` batches, epoch by epoch like train.py:150-158: a fresh generator per epoch, drawn
+        on a generator thread (the reference's GeneratorEnqueuer), consumed in order."""
+        done = 0
+        while done < total:
+            n = min(total - done, per_epoch)
+            for b in Prefetcher(gen(), n):
+                yield b
+            done += n
+
+    for b in epochs(W):
+        m.train_on_batch(b, sync=True)
     torch.cuda.synchronize()
     h2d = 0
     e_ratings = 0
     prev = None
     t0 = time.perf_counter()
-    from omnidirectional_collaborative_filtering_b200.data_reader import Prefetcher
-    # generator thread (the reference's GeneratorEnqueuer): RNG replay -> row ids + uniform draws;
-    # main thread: flags + pinned staging + H2D + kernels + the D2H read of every step's metrics
-    for b in Prefetcher(stream_of_batches, K):
+    # generator thread: set order, row ids, the batch's place in the NumPy stream; main thread:
+    # pinned staging + H2D of the row ids + kernels (the random split is drawn on the device from
+    # the replayed MT19937 stream) + the D2H read of every step's metrics
+    for b in epochs(K):
         m.train_on_batch(b, sync=False)
         step_id = m.steps_logged() - 1
         if prev is not None:

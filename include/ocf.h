@@ -50,6 +50,7 @@ typedef struct ocf_store ocf_store;   /* device-resident rating store (CSR + CSC
 typedef struct ocf_pair ocf_pair;     /* (input store, target store) of a fixed-split set    */
 typedef struct ocf_batch ocf_batch;   /* one batch: row ids, keep-flags, gathered tiles      */
 typedef struct ocf_model ocf_model;   /* weights, optimizer state, workspaces                */
+typedef struct ocf_rng ocf_rng;       /* NumPy's MT19937 stream, resident on the device      */
 
 const char* ocf_last_error(void);
 int ocf_version(void);
@@ -100,6 +101,30 @@ int ocf_batch_fill_split_uniform(ocf_batch* batch, const ocf_store* store, const
                                  int32_t n_rows, const double* u, int64_t n_u, const double* cdf0,
                                  const int32_t* orig_pos, const int64_t* full_len, int pass_through,
                                  float aux_var_value, void* stream);
+/* The reference draws its reciprocal-dropout split from NumPy's global MT19937 stream
+ * (np.random.uniform at data_reader.py:120, np.random.choice at :130). An ocf_rng holds that
+ * stream on the device: set_state takes RandomState.get_state()[1:3] (key[624], pos), get_state
+ * returns them after waiting for the generator. The stream advances on its own CUDA stream, so the
+ * draws of the next batch are produced while the current step computes. */
+int ocf_rng_create(ocf_rng** out);
+int ocf_rng_destroy(ocf_rng* rng);
+int ocf_rng_set_state(ocf_rng* rng, const uint32_t* key, int32_t pos);
+int ocf_rng_get_state(ocf_rng* rng, uint32_t* key, int32_t* pos);
+/* Advances the stream by n_draws doubles (a batch the generator drew but nobody consumed). */
+int ocf_rng_skip(ocf_rng* rng, int64_t n_draws);
+/* Column shards: orig_pos[e] = position of the shard's store entry e inside its full row. */
+int ocf_store_set_orig_pos(ocf_store* store, const int32_t* orig_pos);
+/* build_sparse_batch (data_reader.py:95-200) with the random split drawn ON THE DEVICE, bit for
+ * bit what the reference draws: the stream's next n_rows doubles are
+ * np.random.uniform(lo, hi, size=n_rows) (:120), the following sum(len(row)) doubles are the
+ * rows' np.random.choice draws in batch order (:130). Nothing but the row ids crosses PCIe.
+ * full_len[r] (column shards, else NULL) = full length of batch row r. */
+int ocf_batch_fill_split_rng(ocf_batch* batch, const ocf_store* store, const int32_t* row_ids,
+                             int32_t n_rows, ocf_rng* rng, double lo, double hi,
+                             const int64_t* full_len, int pass_through, float aux_var_value,
+                             void* stream);
+/* The keep flags of a split batch as the device holds them (synchronises `stream`). */
+int ocf_batch_read_flags(ocf_batch* batch, uint8_t* out, int64_t count, void* stream);
 /* build_sparse_batch_fixed_split, data_reader.py:202-298. */
 int ocf_batch_fill_fixed(ocf_batch* batch, const ocf_pair* pair, const int32_t* row_ids,
                          int32_t n_rows, float aux_var_value, void* stream);

@@ -59,6 +59,14 @@ _SIGNATURES = {
     "ocf_batch_fill_split_uniform": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_float, _P]),
     "ocf_batch_fill_fixed": (C.c_int, [_P, _P, _P, C.c_int32, C.c_float, _P]),
     "ocf_batch_regather": (C.c_int, [_P, _P]),
+    "ocf_rng_create": (C.c_int, [C.POINTER(_P)]),
+    "ocf_rng_destroy": (C.c_int, [_P]),
+    "ocf_rng_set_state": (C.c_int, [_P, _P, C.c_int32]),
+    "ocf_rng_get_state": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
+    "ocf_rng_skip": (C.c_int, [_P, C.c_int64]),
+    "ocf_store_set_orig_pos": (C.c_int, [_P, _P]),
+    "ocf_batch_fill_split_rng": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, _P, C.c_int, C.c_float, _P]),
+    "ocf_batch_read_flags": (C.c_int, [_P, _P, C.c_int64, _P]),
     "ocf_profile_enable": (C.c_int, [C.c_int]),
     "ocf_profile_reset": (C.c_int, []),
     "ocf_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

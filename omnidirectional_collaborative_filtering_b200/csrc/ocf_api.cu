@@ -64,6 +64,15 @@ struct ocf_store {
   Arena mem;
 };
 
+// NumPy's MT19937 stream held on the device (624-word key + position), advanced by k_mt_words on
+// its own stream so that the draws of batch i+1 are generated while step i computes.
+struct ocf_rng {
+  uint32_t* d_state = nullptr;     // [625]
+  cudaStream_t stream = nullptr;
+  int device = 0;
+  Arena mem;
+};
+
 struct ocf_pair {
   const ocf_store* in = nullptr;
   const ocf_store* tg = nullptr;
@@ -95,6 +104,12 @@ struct ocf_batch {
   int64_t target_count = 0;
   size_t last_h2d = 0;
   std::vector<uint8_t> flag_scratch;
+  // device-RNG mode: this batch's slice of the MT19937 stream and the per-row cdf
+  uint32_t* d_words = nullptr;
+  int64_t words_cap = 0;           // in draws (2 words each)
+  double* d_cdf0 = nullptr;
+  cudaEvent_t words_ready = nullptr, gathered = nullptr;
+  bool rng_mode = false;
   Arena mem;
 };
 
@@ -389,14 +404,15 @@ static int max_items_for(int max_rows, int64_t max_entries) {
   return (int)std::min<int64_t>(max_entries / 32 + max_rows + 1, TARGET_ITEMS + max_rows + 1);
 }
 
-static size_t staging_layout(int B, int n_items, int64_t n_entries, size_t off[6]) {
+static size_t staging_layout(int B, int n_items, int64_t n_entries, size_t off[7]) {
   size_t o = 0;
   off[0] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // row_ids
   off[1] = o; o = align_up(o + sizeof(int32_t) * (B + 1), 16);       // ent_off
   off[2] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // in_len
   off[3] = o; o = align_up(o + sizeof(int32_t) * (B + 1), 16);       // item_ptr
   off[4] = o; o = align_up(o + sizeof(int4) * (size_t)n_items, 16);  // items
-  off[5] = o; o = align_up(o + (size_t)n_entries, 16);               // flags
+  off[5] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // draw_off (device-RNG mode)
+  off[6] = o; o = align_up(o + (size_t)n_entries, 16);               // flags (last: not uploaded when the device derives them)
   return o;
 }
 
@@ -408,7 +424,7 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
   ocf_batch* b = new ocf_batch();
   b->max_rows = max_rows; b->max_entries = max_entries;
   b->max_items = max_items_for(max_rows, max_entries);
-  size_t off[6];
+  size_t off[7];
   b->staging_bytes = staging_layout(max_rows, b->max_items, max_entries, off);
   auto bail = [&](int code) { b->mem.release(); if (b->h_staging) cudaFreeHost(b->h_staging); if (b->copied) cudaEventDestroy(b->copied); delete b; return code; };
   if (cudaMallocHost(reinterpret_cast<void**>(&b->h_staging), b->staging_bytes) != cudaSuccess)
@@ -429,6 +445,10 @@ extern "C" int ocf_batch_destroy(ocf_batch* b) {
     if (b->d_rowslot) cudaFree(b->d_rowslot);
     if (b->h_staging) cudaFreeHost(b->h_staging);
     if (b->copied) cudaEventDestroy(b->copied);
+    if (b->d_words) cudaFree(b->d_words);
+    if (b->d_cdf0) cudaFree(b->d_cdf0);
+    if (b->words_ready) cudaEventDestroy(b->words_ready);
+    if (b->gathered) cudaEventDestroy(b->gathered);
     delete b;
   }
   return OCF_OK;
@@ -442,9 +462,12 @@ static int pick_chunk(int64_t n_entries) {
   return (int)std::max<int64_t>(ch, 32);
 }
 
+// `draw_len` (device-RNG mode): draws each row consumes = its FULL length (a column shard passes
+// them; null = the store's own row lengths); `with_draws` stages the per-row draw offsets and
+// leaves the flags to the device.
 static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const std::vector<int64_t>& rp_a,
                        const std::vector<int64_t>* rp_b, int64_t n_store_rows, const uint8_t* flags,
-                       int64_t n_flags, cudaStream_t stream) {
+                       int64_t n_flags, cudaStream_t stream, bool with_draws = false, const int64_t* draw_len = nullptr) {
   OCF_REQUIRE(n_rows > 0 && n_rows <= b->max_rows, "batch fill: row count exceeds the batch capacity");
   if (b->copy_pending) { OCF_CUDA(cudaEventSynchronize(b->copied)); b->copy_pending = false; }
   // pass 1: lengths
@@ -466,26 +489,29 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
     n_items += (n + ch - 1) / ch;
   }
   OCF_REQUIRE(n_items <= b->max_items, "batch fill: too many work items");
-  size_t off[6];
-  const size_t bytes = staging_layout(n_rows, (int)n_items, total, off);
+  size_t off[7];
+  const size_t bytes_all = staging_layout(n_rows, (int)n_items, total, off);
+  const size_t bytes = flags != nullptr ? bytes_all : off[6];       // without host flags the flag slot is not copied
   uint8_t* hs = b->h_staging;
   int32_t* h_rows = reinterpret_cast<int32_t*>(hs + off[0]);
   int32_t* h_eoff = reinterpret_cast<int32_t*>(hs + off[1]);
   int32_t* h_inlen = reinterpret_cast<int32_t*>(hs + off[2]);
   int32_t* h_iptr = reinterpret_cast<int32_t*>(hs + off[3]);
   int4* h_items = reinterpret_cast<int4*>(hs + off[4]);
-  int64_t e = 0; int it = 0; int64_t tcount = 0;
+  int32_t* h_draw = reinterpret_cast<int32_t*>(hs + off[5]);
+  int64_t e = 0; int it = 0; int64_t tcount = 0; int64_t draw = n_rows;   // the first B draws are the rows' sparsities
   for (int r = 0; r < n_rows; ++r) {
     const int32_t row = row_ids[r];
     const int64_t na = rp_a[row + 1] - rp_a[row];
     const int64_t nb = rp_b ? (*rp_b)[row + 1] - (*rp_b)[row] : 0;
     h_rows[r] = row; h_eoff[r] = (int32_t)e; h_inlen[r] = (int32_t)na; h_iptr[r] = it;
+    if (with_draws) { h_draw[r] = (int32_t)draw; draw += draw_len ? draw_len[r] : na; }
     const int64_t n = na + nb;
     for (int64_t s0 = 0; s0 < n; s0 += ch) h_items[it++] = make_int4(r, (int)s0, (int)std::min<int64_t>(ch, n - s0), 0);
     e += n; tcount += nb;
   }
   h_eoff[n_rows] = (int32_t)e; h_iptr[n_rows] = it;
-  if (flags != nullptr && total > 0) std::memcpy(hs + off[5], flags, (size_t)total);
+  if (flags != nullptr && total > 0) std::memcpy(hs + off[6], flags, (size_t)total);
   OCF_CUDA(cudaMemcpyAsync(b->d_staging, hs, bytes, cudaMemcpyHostToDevice, stream));
   OCF_CUDA(cudaEventRecord(b->copied, stream));
   b->copy_pending = true;
@@ -498,7 +524,10 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
   d.in_len = reinterpret_cast<const int32_t*>(b->d_staging + off[2]);
   d.item_ptr = reinterpret_cast<const int32_t*>(b->d_staging + off[3]);
   d.items = reinterpret_cast<const int4*>(b->d_staging + off[4]);
-  d.flags = b->d_staging + off[5];
+  d.draw_off = reinterpret_cast<const int32_t*>(b->d_staging + off[5]);
+  d.flags = b->d_staging + off[6];
+  d.flags_out = b->d_staging + off[6];
+  d.words = b->d_words; d.cdf0 = b->d_cdf0;
   d.ent_col = b->d_ent_col; d.ent_val = b->d_ent_val; d.codes = b->d_codes;
   return OCF_OK;
 }
@@ -507,12 +536,15 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
 static int launch_gather(ocf_batch* b, cudaStream_t stream) {
   if (b->dev.n_items == 0) return OCF_OK;
   g_prof.begin(0, stream);
-  if (b->mode == 1) k_gather_split<<<b->dev.n_items, 128, 0, stream>>>(b->store->dev, b->dev, b->pass_through);
+  if (b->mode == 1 && b->rng_mode) k_gather_split<true><<<b->dev.n_items, 128, 0, stream>>>(b->store->dev, b->dev, b->pass_through);
+  else if (b->mode == 1) k_gather_split<false><<<b->dev.n_items, 128, 0, stream>>>(b->store->dev, b->dev, b->pass_through);
   else k_gather_fixed<<<b->dev.n_items, 128, 0, stream>>>(b->pair->in->dev, b->pair->tg->dev, b->pair->d_in_overlap, b->dev);
   OCF_LAUNCHED();
   g_prof.end(0, stream);
   return OCF_OK;
 }
+
+static int prepare_rowslot(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows, cudaStream_t stream, const char* who);
 
 extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows,
                                     const uint8_t* keep_flags, int64_t n_flags, int pass_through,
@@ -520,26 +552,11 @@ extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const 
   OCF_REQUIRE(b && store && row_ids, "ocf_batch_fill_split: null argument");
   OCF_REQUIRE(keep_flags != nullptr || n_flags == 0, "ocf_batch_fill_split: null keep_flags");
   cudaStream_t stream = as_stream(stream_);
-  {  // the row -> slot map needs distinct rows
-    std::vector<int32_t> tmp(row_ids, row_ids + std::max(n_rows, 0));
-    std::sort(tmp.begin(), tmp.end());
-    OCF_REQUIRE(std::adjacent_find(tmp.begin(), tmp.end()) == tmp.end(), "ocf_batch_fill_split: a row appears twice in the batch");
-  }
-  if (b->rowslot_rows < store->n_rows) {
-    if (b->d_rowslot) { OCF_CUDA(cudaStreamSynchronize(stream)); cudaFree(b->d_rowslot); b->d_rowslot = nullptr; }
-    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_rowslot), sizeof(uint32_t) * (size_t)std::max<int64_t>(store->n_rows, 1)));
-    b->rowslot_rows = store->n_rows;
-    b->tag = 0;
-  }
-  if (b->tag == 0 || b->tag >= (1u << (32 - SLOT_BITS)) - 1 || b->store != store) {
-    OCF_CUDA(cudaMemsetAsync(b->d_rowslot, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(b->rowslot_rows, 1), stream));
-    b->tag = 0;
-  }
-  b->tag += 1;
+  OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split"));
   OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, keep_flags, n_flags, stream));
   b->dev.rowslot = b->d_rowslot;
   b->dev.tag = b->tag;
-  b->mode = 1; b->store = store; b->aux_value = aux_var_value;
+  b->mode = 1; b->store = store; b->aux_value = aux_var_value; b->rng_mode = false;
   // in split mode every listed rating is a target when pass_through, else the flag-0 ones
   int64_t tc = 0;
   if (pass_through) tc = n_flags; else for (int64_t k = 0; k < n_flags; ++k) tc += keep_flags[k] == 0;
@@ -592,7 +609,140 @@ extern "C" int ocf_batch_fill_fixed(ocf_batch* b, const ocf_pair* pair, const in
 extern "C" int ocf_batch_regather(ocf_batch* b, void* stream_) {
   OCF_REQUIRE(b, "ocf_batch_regather: null argument");
   if (b->mode == 0) return fail(OCF_ERR_STATE, "ocf_batch_regather: the batch has not been filled");
+  b->rng_mode = false;            // the first gather left the flags in the device staging
   return launch_gather(b, as_stream(stream_));
+}
+
+// ---- NumPy MT19937 on the device ------------------------------------------------------------------
+extern "C" int ocf_rng_create(ocf_rng** out) {
+  OCF_REQUIRE(out != nullptr, "ocf_rng_create: null argument");
+  *out = nullptr;
+  ocf_rng* r = new ocf_rng();
+  if (cudaGetDevice(&r->device) != cudaSuccess) { cudaGetLastError(); delete r; return fail(OCF_ERR_CUDA, "ocf_rng_create: no CUDA device"); }
+  int st = r->mem.get(&r->d_state, 625, true);
+  if (st) { delete r; return st; }
+  if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) { r->mem.release(); delete r; return fail(OCF_ERR_CUDA, "ocf_rng_create: stream creation failed"); }
+  *out = r;
+  return OCF_OK;
+}
+
+extern "C" int ocf_rng_destroy(ocf_rng* r) {
+  if (r) { if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); } r->mem.release(); delete r; }
+  return OCF_OK;
+}
+
+extern "C" int ocf_rng_set_state(ocf_rng* r, const uint32_t* key, int32_t pos) {
+  OCF_REQUIRE(r && key && pos >= 0 && pos <= 624, "ocf_rng_set_state: bad argument");
+  uint32_t tmp[625];
+  std::memcpy(tmp, key, sizeof(uint32_t) * 624);
+  tmp[624] = (uint32_t)pos;
+  OCF_CUDA(cudaSetDevice(r->device));        // generator threads call this too
+  OCF_CUDA(cudaMemcpyAsync(r->d_state, tmp, sizeof(tmp), cudaMemcpyHostToDevice, r->stream));
+  OCF_CUDA(cudaStreamSynchronize(r->stream));
+  return OCF_OK;
+}
+
+extern "C" int ocf_rng_get_state(ocf_rng* r, uint32_t* key, int32_t* pos) {
+  OCF_REQUIRE(r && key && pos, "ocf_rng_get_state: null argument");
+  uint32_t tmp[625];
+  OCF_CUDA(cudaSetDevice(r->device));
+  OCF_CUDA(cudaMemcpyAsync(tmp, r->d_state, sizeof(tmp), cudaMemcpyDeviceToHost, r->stream));
+  OCF_CUDA(cudaStreamSynchronize(r->stream));
+  std::memcpy(key, tmp, sizeof(uint32_t) * 624);
+  *pos = (int32_t)tmp[624];
+  return OCF_OK;
+}
+
+extern "C" int ocf_rng_skip(ocf_rng* r, int64_t n_draws) {
+  OCF_REQUIRE(r && n_draws >= 0, "ocf_rng_skip: bad argument");
+  if (n_draws == 0) return OCF_OK;
+  OCF_CUDA(cudaSetDevice(r->device));
+  k_mt_words<<<1, 256, 0, r->stream>>>(r->d_state, 2 * (long long)n_draws, nullptr, 0, 0.0, 0.0, nullptr);
+  OCF_LAUNCHED();
+  return OCF_OK;
+}
+
+extern "C" int ocf_store_set_orig_pos(ocf_store* s, const int32_t* orig_pos) {
+  OCF_REQUIRE(s && (orig_pos || s->nnz == 0), "ocf_store_set_orig_pos: null argument");
+  int32_t* d = nullptr;
+  OCF_TRY(s->mem.get(&d, (size_t)s->nnz));
+  if (s->nnz) OCF_CUDA(cudaMemcpy(d, orig_pos, sizeof(int32_t) * s->nnz, cudaMemcpyHostToDevice));
+  s->dev.orig_pos = d;
+  return OCF_OK;
+}
+
+static int prepare_rowslot(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows, cudaStream_t stream, const char* who) {
+  {  // the row -> slot map needs distinct rows
+    std::vector<int32_t> tmp(row_ids, row_ids + std::max(n_rows, 0));
+    std::sort(tmp.begin(), tmp.end());
+    if (std::adjacent_find(tmp.begin(), tmp.end()) != tmp.end()) return fail(OCF_ERR_INVALID, std::string(who) + ": a row appears twice in the batch");
+  }
+  if (b->rowslot_rows < store->n_rows) {
+    if (b->d_rowslot) { OCF_CUDA(cudaStreamSynchronize(stream)); cudaFree(b->d_rowslot); b->d_rowslot = nullptr; }
+    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_rowslot), sizeof(uint32_t) * (size_t)std::max<int64_t>(store->n_rows, 1)));
+    b->rowslot_rows = store->n_rows;
+    b->tag = 0;
+  }
+  if (b->tag == 0 || b->tag >= (1u << (32 - SLOT_BITS)) - 1 || b->store != store) {
+    OCF_CUDA(cudaMemsetAsync(b->d_rowslot, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(b->rowslot_rows, 1), stream));
+    b->tag = 0;
+  }
+  b->tag += 1;
+  return OCF_OK;
+}
+
+extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows,
+                                        ocf_rng* rng, double lo, double hi, const int64_t* full_len, int pass_through,
+                                        float aux_var_value, void* stream_) {
+  OCF_REQUIRE(b && store && row_ids && rng, "ocf_batch_fill_split_rng: null argument");
+  OCF_REQUIRE(n_rows > 0 && n_rows <= b->max_rows, "ocf_batch_fill_split_rng: row count exceeds the batch capacity");
+  OCF_REQUIRE((full_len != nullptr) == (store->dev.orig_pos != nullptr), "ocf_batch_fill_split_rng: full_len goes with a store that has ocf_store_set_orig_pos");
+  cudaStream_t stream = as_stream(stream_);
+  int64_t draws = n_rows;
+  for (int r = 0; r < n_rows; ++r) {
+    const int32_t row = row_ids[r];
+    OCF_REQUIRE(row >= 0 && row < store->n_rows, "ocf_batch_fill_split_rng: row id out of range");
+    draws += full_len ? full_len[r] : store->h_rowptr[row + 1] - store->h_rowptr[row];
+  }
+  OCF_REQUIRE(draws < (int64_t(1) << 30), "ocf_batch_fill_split_rng: too many draws in one batch");
+  if (!b->words_ready) {
+    OCF_CUDA(cudaEventCreateWithFlags(&b->words_ready, cudaEventDisableTiming));
+    OCF_CUDA(cudaEventCreateWithFlags(&b->gathered, cudaEventDisableTiming));
+    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_cdf0), sizeof(double) * (size_t)b->max_rows));
+  }
+  if (draws > b->words_cap) {
+    if (b->d_words) { OCF_CUDA(cudaDeviceSynchronize()); cudaFree(b->d_words); b->d_words = nullptr; }
+    const int64_t cap = std::max<int64_t>(draws + draws / 4, b->max_rows + b->max_entries);
+    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_words), sizeof(uint32_t) * 2 * (size_t)cap));
+    b->words_cap = cap;
+  }
+  // the previous batch staged in this object may still be reading its words (no-op before the first gather)
+  OCF_CUDA(cudaStreamWaitEvent(rng->stream, b->gathered, 0));
+  // the stream's next `draws` doubles, generated beside whatever `stream` is running
+  k_mt_words<<<1, 256, 0, rng->stream>>>(rng->d_state, 2 * (long long)draws, b->d_words, n_rows, lo, hi - lo, b->d_cdf0);
+  OCF_LAUNCHED();
+  OCF_CUDA(cudaEventRecord(b->words_ready, rng->stream));
+  OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split_rng"));
+  OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, nullptr, -1, stream, true, full_len));
+  b->dev.rowslot = b->d_rowslot;
+  b->dev.tag = b->tag;
+  b->mode = 1; b->store = store; b->aux_value = aux_var_value; b->rng_mode = true;
+  b->pass_through = pass_through ? 1 : 0;
+  b->target_count = pass_through ? b->dev.n_entries : -1;      // the flags never visit the host
+  OCF_CUDA(cudaStreamWaitEvent(stream, b->words_ready, 0));
+  OCF_TRY(launch_gather(b, stream));
+  OCF_CUDA(cudaEventRecord(b->gathered, stream));
+  return OCF_OK;
+}
+
+extern "C" int ocf_batch_read_flags(ocf_batch* b, uint8_t* out, int64_t count, void* stream_) {
+  OCF_REQUIRE(b && (out || count == 0), "ocf_batch_read_flags: null argument");
+  if (b->mode != 1) return fail(OCF_ERR_STATE, "ocf_batch_read_flags: not a split batch");
+  OCF_REQUIRE(count == b->dev.n_entries, "ocf_batch_read_flags: count must equal the batch's entries");
+  cudaStream_t stream = as_stream(stream_);
+  if (count) OCF_CUDA(cudaMemcpyAsync(out, b->dev.flags, (size_t)count, cudaMemcpyDeviceToHost, stream));
+  OCF_CUDA(cudaStreamSynchronize(stream));
+  return OCF_OK;
 }
 
 extern "C" int ocf_batch_info(const ocf_batch* b, int64_t info[5]) {

@@ -65,6 +65,7 @@ struct StoreDev {
   const int32_t* crow;       //   row of the entry
   const int32_t* cj;         //   position of the entry inside its row
   const int32_t* ccol;       //   column of the entry (CSC expanded; read for matches only)
+  const int32_t* orig_pos;   // column shards: position of the entry inside its FULL row (null: the store holds full rows)
   const int2* groups;        //   scan schedule: groups of consecutive columns [x, y), <= scan_t entries each or one longer column; largest first
   int n_groups;
   int scan_t;                //   4096, 8192 or 16384: picked so that a scan is about one group per resident CTA
@@ -82,6 +83,10 @@ struct BatchDev {
   const int4* items;         // [n_items] (b, start, len, 0): a chunk of a row's entries
   const int32_t* item_ptr;   // [B+1] items of row b
   const uint8_t* flags;      // [n_entries] keep flags (split mode)
+  const int32_t* draw_off;   // [B] device-RNG mode: index of the row's first draw in the batch's slice of the stream
+  const uint32_t* words;     //     tempered MT19937 words of the batch's draws (2 per draw)
+  const double* cdf0;        // [B] (1-s)/((1-s)+s) of the row's sparsity draw
+  uint8_t* flags_out;        // [n_entries] == flags; written by K1 in device-RNG mode
   int32_t* ent_col;          // [n_entries]
   float* ent_val;            // [n_entries]
   uint8_t* codes;            // [n_entries]
@@ -172,6 +177,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     k.y += 0xBB67AE85u;
   }
   return c;
+}
+
+// NumPy's next_double for MT19937: 53 bits from two consecutive tempered words.
+__device__ __forceinline__ double mt_double(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

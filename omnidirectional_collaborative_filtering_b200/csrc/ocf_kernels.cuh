@@ -24,6 +24,11 @@ constexpr unsigned FULL = 0xffffffffu;
 // Replaces the per-rating Python loop of data_reader.py:122-170 / :226-268.
 // One CTA per work item (a chunk of <= CH ratings of one row); reads and writes are contiguous.
 // ============================================================================================
+// RNG = true: the keep flag of a rating is derived here from the batch's slice of the NumPy
+// MT19937 stream that k_mt_words left in HBM (draw d of the batch = words 2d, 2d+1), compared with
+// the row's cdf - what np.random.choice([0,1], n, p=[1-s, s]) returns (data_reader.py:130).
+// The flags are also written back so a caller can read them.
+template <bool RNG>
 __global__ void __launch_bounds__(128)
 k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
   const int4 it = bt.items[blockIdx.x];
@@ -32,11 +37,20 @@ k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
   const int64_t src0 = s.rowptr[row];
   const int p0 = bt.ent_off[b];
   if (start == 0 && threadIdx.x == 0) bt.rowslot[row] = (bt.tag << SLOT_BITS) | (uint32_t)b;
+  const int d0 = RNG ? bt.draw_off[b] : 0;
+  const double c0 = RNG ? bt.cdf0[b] : 0.0;
+  auto flag_of = [&](int j) -> uint8_t {
+    if (!RNG) return bt.flags[p0 + j];
+    const int d = d0 + (s.orig_pos != nullptr ? s.orig_pos[src0 + j] : j);
+    const uint2 w = *reinterpret_cast<const uint2*>(bt.words + 2 * (size_t)d);
+    return mt_double(w.x, w.y) >= c0 ? 1 : 0;
+  };
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
     const int j = start + i;
     const int64_t src = src0 + j;
     const int p = p0 + j;
-    const uint8_t f = bt.flags[p];
+    const uint8_t f = flag_of(j);
+    if (RNG) bt.flags_out[p] = f;
     bool in_live = f != 0;
     bool tg_live = (f == 0) || pass_through;
     bool obs_live = true;
@@ -44,7 +58,7 @@ k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
       int k = s.next_dup[src];
       while (k >= 0) {               // later ratings of the same column overwrite this one
         obs_live = false;
-        const uint8_t fk = bt.flags[p0 + k];
+        const uint8_t fk = flag_of(k);
         if (fk != 0) in_live = false;
         if (fk == 0 || pass_through) tg_live = false;
         k = s.next_dup[src0 + k];
@@ -53,6 +67,70 @@ k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
     bt.ent_col[p] = s.col[src];
     bt.ent_val[p] = s.val[src];
     bt.codes[p] = (uint8_t)((in_live ? CODE_IN : 0) | (obs_live ? CODE_OBS : 0) | (tg_live ? CODE_TGT : 0));
+  }
+}
+
+// ============================================================================================
+// NumPy's MT19937 stream on the device. One CTA owns the 624-word state: a regeneration is three
+// dependent sweeps of <= 227 independent words (word i needs i+1 and i+397 of the old array, or
+// i-227 of the new one), double-buffered in shared memory; the tempered words of the batch's
+// draws are written out in stream order. The first `n_rows` draws are the batch's
+// np.random.uniform(lo, hi, size=B) (data_reader.py:120): their cdf (what np.random.choice builds
+// from p=[1-s, s]) is computed here in IEEE double, operation by operation like the host code.
+// state[0..623] = key, state[624] = pos (RandomState.get_state()[1:3]).
+// ============================================================================================
+__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+  const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+  return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+__global__ void __launch_bounds__(256)
+k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict__ out, int n_rows,
+           double lo, double range, double* __restrict__ cdf0) {
+  __shared__ uint32_t mt[2][624];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 624; i += blockDim.x) mt[0][i] = state[i];
+  int pos = (int)state[624];
+  int cur = 0;
+  __syncthreads();
+  long long w = 0;
+  while (w < n_words) {
+    if (pos >= 624) {
+      const uint32_t* o = mt[cur];
+      uint32_t* n = mt[cur ^ 1];
+      if (tid < 227) n[tid] = mt_twist(o[tid], o[tid + 1], o[tid + 397]);
+      __syncthreads();
+      if (tid < 227) n[227 + tid] = mt_twist(o[227 + tid], o[228 + tid], n[tid]);
+      __syncthreads();
+      if (tid < 169) n[454 + tid] = mt_twist(o[454 + tid], o[455 + tid], n[227 + tid]);
+      else if (tid == 169) n[623] = mt_twist(o[623], n[0], n[396]);
+      __syncthreads();
+      cur ^= 1;
+      pos = 0;
+    }
+    const int take = (int)min((long long)(624 - pos), n_words - w);
+    if (out != nullptr)
+      for (int i = tid; i < take; i += blockDim.x) out[w + i] = mt_temper(mt[cur][pos + i]);
+    w += take;
+    pos += take;
+  }
+  __syncthreads();
+  for (int i = tid; i < 624; i += blockDim.x) state[i] = mt[cur][i];
+  if (tid == 0) state[624] = (uint32_t)pos;
+  if (out != nullptr && cdf0 != nullptr) {
+    for (int r = tid; r < n_rows; r += blockDim.x) {
+      const double u = mt_double(out[2 * r], out[2 * r + 1]);
+      const double keep = __dadd_rn(lo, __dmul_rn(range, u));        // random_uniform: lower + range * next_double
+      const double p0 = __dsub_rn(1.0, keep);
+      cdf0[r] = __ddiv_rn(p0, __dadd_rn(p0, keep));                  // cdf = cumsum(p) / cumsum(p)[-1]
+    }
   }
 }
 

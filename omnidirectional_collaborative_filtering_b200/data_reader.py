@@ -16,8 +16,11 @@ CUDA scatter kernel, so reference-style callers keep working.
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import pickle
+import threading
+from collections import OrderedDict
 from typing import Optional
 
 import numpy as np
@@ -45,6 +48,114 @@ def _csr_from_lists(lists, col_of, n_cols) -> Csr:
     return Csr(len(lists), n_cols, rowptr, col, val)
 
 
+class DeviceRng(object):
+    """`np.random`'s global MT19937 stream, lent to the GPU while split batches are drawn.
+
+    The reference draws `uniform(lo, hi, B)` + one `choice` per row from the global NumPy stream
+    for every training batch (`data_reader.py:120,130`). Replaying those ~10^5 doubles per batch on
+    the host bounds the whole step, so the stream itself moves: the generator hands out *tickets*
+    (how many doubles a batch consumes, in drawing order), the first upload pushes the host state
+    to the device (`ocf_rng_set_state`), every upload advances the device stream by exactly its
+    ticket (`ocf_batch_fill_split_rng`; tickets that were drawn but never uploaded are skipped in
+    order), and `release()` brings the state back into `np.random` before anything on the host
+    draws again. The result is bit-identical to host-side consumption at the generator's `next()`.
+    One instance per process, like the stream it stands in for."""
+
+    _instance = None
+
+    def __init__(self):
+        self.lock = threading.RLock()
+        self.handle = None
+        self.active = False                 # the device holds the current state
+        self.host_state = None              # np.random state at the first ticket since the last release
+        self.issued = 0
+        self.pending = OrderedDict()        # ticket -> draws, in drawing order
+
+    @classmethod
+    def get(cls):
+        if cls._instance is None:
+            cls._instance = DeviceRng()
+        return cls._instance
+
+    def ticket(self, draws):
+        with self.lock:
+            if self.host_state is None:
+                self.host_state = np.random.get_state()
+            t = self.issued
+            self.issued += 1
+            self.pending[t] = int(draws)
+            return t
+
+    def _activate(self):
+        if self.active:
+            return
+        lib = _lib.lib()
+        if self.handle is None:
+            _lib.require_gpu()
+            out = C.c_void_p()
+            _lib.check(lib.ocf_rng_create(C.byref(out)))
+            self.handle = out
+        key = np.ascontiguousarray(self.host_state[1], dtype=np.uint32)
+        _lib.check(lib.ocf_rng_set_state(self.handle, _lib.ptr(key), int(self.host_state[2])))
+        self.active = True
+
+    def consume(self, ticket):
+        """Called by the upload of a batch: positions the device stream at the batch's first draw
+        and returns the rng handle; the fill then advances it by the batch's draws."""
+        with self.lock:
+            if ticket not in self.pending:
+                raise RuntimeError("this batch's random draws were dropped: np.random was used on the host (a new "
+                                   "generator, a model initialisation) before the batch was uploaded")
+            self._activate()
+            lib = _lib.lib()
+            for t in list(self.pending):
+                if t >= ticket:
+                    break
+                _lib.check(lib.ocf_rng_skip(self.handle, self.pending.pop(t)))   # drawn, never uploaded
+            self.pending.pop(ticket)
+            return self.handle
+
+    def release(self):
+        """Hand the stream back to `np.random` (no-op when the host already owns it)."""
+        with self.lock:
+            if self.host_state is None:
+                return
+            cur, lent = np.random.get_state(), self.host_state
+            if not (cur[2] == lent[2] and cur[3] == lent[3] and cur[4] == lent[4] and np.array_equal(cur[1], lent[1])):
+                # np.random was reseeded (or drawn from) on the host while the stream was on loan:
+                # the host's stream is the current one, the device's copy and its open tickets lapse
+                self.pending.clear()
+                self.active = False
+                self.host_state = None
+                return
+            self._activate()
+            lib = _lib.lib()
+            for t in list(self.pending):
+                _lib.check(lib.ocf_rng_skip(self.handle, self.pending.pop(t)))
+            key = np.empty(624, dtype=np.uint32)
+            pos = C.c_int32()
+            _lib.check(lib.ocf_rng_get_state(self.handle, _lib.ptr(key), C.byref(pos)))
+            st = self.host_state
+            np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
+            self.active = False
+            self.host_state = None
+
+
+def sync_host_rng():
+    """Make `np.random` current again if the device holds its stream. Everything in this package
+    that draws from `np.random` calls this first; call it yourself before drawing from
+    `np.random` in between batches of a running generator."""
+    if DeviceRng._instance is not None:
+        DeviceRng._instance.release()
+
+
+def device_rng_available() -> bool:
+    try:
+        return _lib.lib().ocf_device_count() > 0
+    except _lib.OcfError:
+        return False
+
+
 class Batch(object):
     """One batch as (row ids, keep flags) + the stores they index. Host-only until uploaded."""
 
@@ -56,6 +167,9 @@ class Batch(object):
         self.rows = np.ascontiguousarray(rows, dtype=np.int32)
         self._flags = flags                    # uint8 keep flags, or None while only (u, cdf0) are held
         self.u = self.cdf0 = self.full_len = None
+        self.ticket = None                     # device-RNG mode: the batch's place in the NumPy stream
+        self.sparsity = None                   #   (lo, hi) of its np.random.uniform draw
+        self._dev_generation = -1
         self.pass_through = bool(pass_through)
         self.aux_type = aux_type
         self.aux_value = float(aux_value)
@@ -71,7 +185,14 @@ class Batch(object):
     def flags(self):
         """uint8 keep flag per rating this batch holds (1 = input). Derived on demand from the
         uniform draws; `upload` hands the draws to the library instead."""
-        if self._flags is None and self.kind == "split":
+        if self._flags is None and self.kind == "split" and self.ticket is not None:
+            if self._device is None:
+                self.upload(self.reader.stream)
+            if self._device.generation != self._dev_generation:
+                raise RuntimeError("the batch's device tiles were recycled before its keep flags were read; "
+                                   "read batch.flags before uploading later batches")
+            self._flags = self._device.read_flags(self.n_entries, self.reader.stream)
+        elif self._flags is None and self.kind == "split":
             src = self.source
             n_full = src.full_lengths[self.rows]
             full = self.u >= np.repeat(self.cdf0, n_full)
@@ -87,9 +208,16 @@ class Batch(object):
 
     def upload(self, stream=None):
         """Stage + copy + gather (K1) into one of the reader's device batch buffers."""
+        if self.kind == "split" and self.ticket is not None and self._flags is None and self._device is not None:
+            self.flags                          # second upload: the draws are spent, take the flags from the first
         ring = self.reader._ring_for(self.n_rows, self.n_entries)
         dev = ring.next()
-        if self.kind == "split" and self._flags is None:
+        if self.kind == "split" and self.ticket is not None and self._flags is None:
+            handle = DeviceRng.get().consume(self.ticket)
+            dev.fill_split_rng(self.source, self.rows, handle, self.sparsity[0], self.sparsity[1], self.full_len,
+                               self.pass_through, self.aux_value, stream)
+            self._dev_generation = dev.generation
+        elif self.kind == "split" and self._flags is None:
             dev.fill_split_uniform(self.source, self.rows, self.u, self.cdf0, self.full_len, self.pass_through,
                                    self.aux_value, stream)
         elif self.kind == "split":
@@ -185,7 +313,7 @@ class data_reader(object):
 
     def __init__(self, num_items, num_users, filepath, nonsequentialusers=False, use_json=True,
                  eval_mode="ablation", useTimestamps=False, reverse_user_item_data=False, data=None,
-                 stream=None, shard=None):
+                 stream=None, shard=None, rng_on_device=None):
         if useTimestamps:
             raise NotImplementedError("useTimestamps is broken in the reference (data_reader.py:132,359,409) "
                                       "and out of scope here")
@@ -198,6 +326,9 @@ class data_reader(object):
         self.eval_mode = eval_mode
         self.useTimestamps = useTimestamps
         self.stream = stream
+        # None: draw the random split on the GPU whenever one is present (DeviceRng); False keeps
+        # the NumPy stream on the host (one random_sample per batch)
+        self.rng_on_device = rng_on_device
         self._files = data if isinstance(data, dict) else None
         self._rings = {}
         self._stores = {}
@@ -281,6 +412,7 @@ class data_reader(object):
     def split_for_validation(self, val_split, seed=None):
         """`data_reader.py:300-312`."""
         self.val_split = val_split
+        sync_host_rng()
         if seed is not None:
             np.random.seed(seed)
         order = np.random.permutation(self.num_users)
@@ -338,8 +470,10 @@ class data_reader(object):
         else:
             rows = np.arange(len(order), dtype=np.int64)   # k-th key == k-th store row
             source = self._stores[train_val_test]
+        sync_host_rng()                     # np.random must be current before anything draws on the host
         if shuffle:
             rows = rows[np.random.permutation(len(order))]                          # :326-327
+        on_device = split_mode and (device_rng_available() if self.rng_on_device is None else bool(self.rng_on_device))
         batch_size = int(batch_size)
         num_batches = int(np.floor(n / batch_size))                                  # :329
         if split_mode and np.isscalar(data_sparsity):
@@ -349,8 +483,19 @@ class data_reader(object):
         sharded = split_mode and source.orig_pos is not None
         for i in range(num_batches):
             brow = rows[i * batch_size:(i + 1) * batch_size]
-            if split_mode:
+            if split_mode and on_device:
                 n_b = lengths[brow]
+                draws = int(n_b.sum())
+                tcount = draws if pass_through_input_training else -1
+                batch = Batch(self, "split", source, brow, None, pass_through_input_training,
+                              auxilliary_mask_type, aux_var_value, tcount, False, draws)
+                batch.ticket = DeviceRng.get().ticket(batch_size + draws)       # uniform(B) then one draw per rating
+                batch.sparsity = (float(data_sparsity[0]), float(data_sparsity[1]))
+                batch.full_len = n_b if sharded else None
+                yield batch
+            elif split_mode:
+                n_b = lengths[brow]
+                sync_host_rng()
                 keep = np.random.uniform(low=data_sparsity[0], high=data_sparsity[1], size=batch_size)   # :120
                 u = np.random.random_sample(int(n_b.sum()))                                               # :130
                 p0 = 1 - keep
@@ -368,6 +513,11 @@ class data_reader(object):
                             aux_var_value, tcount, return_target_count, n_ratings)
         while True:                                                                                        # :418-419
             yield None
+
+    @staticmethod
+    def sync_rng():
+        """Bring `np.random` up to date with the draws the GPU made for this process's batches."""
+        sync_host_rng()
 
     def close(self):
         for ring in self._rings.values():

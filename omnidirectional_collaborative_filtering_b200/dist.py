@@ -174,7 +174,11 @@ def bench_main(args, w, cfg, rank, world):
             yield b
 
     batches = endless()
-    plans = [next(batches) for _ in range(K + W)]
+    plans = []
+    for _ in range(K + W):
+        p = next(batches)
+        p.flags                             # spend the batch's draws before the next one is drawn
+        plans.append(p)
     m._ensure(B, max(p.n_entries for p in plans), aux, rd)
     resident = []
     for p in plans:

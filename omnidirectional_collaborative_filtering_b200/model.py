@@ -368,6 +368,8 @@ class omni_model(object):
         dims = [self.k_blocks * self.input_shape] + self.widths + [self.input_shape]
         full = []
         seeds = []
+        from .data_reader import sync_host_rng
+        sync_host_rng()                     # np.random may be on loan to the GPU (data_reader.DeviceRng)
         for l in range(self.numlayers + 1):
             seed = int(np.random.randint(10e6))
             lim = np.sqrt(6.0 / (dims[l] + dims[l + 1]))                # glorot_uniform
@@ -487,6 +489,8 @@ def load_model(path):
         cfg = ast.literal_eval(str(f["config"]))
         keys = sorted((k for k in f.files if k.startswith("arr_")), key=lambda k: int(k[4:]))
         weights = [f[k] for k in keys]
+    from .data_reader import sync_host_rng
+    sync_host_rng()
     state = np.random.get_state()                   # loading must not disturb the caller's stream
     om = omni_model(cfg["numlayers"], cfg["num_hidden_units"], cfg["input_shape"], cfg["batch_size"],
                     dense_activation=cfg["dense_activation"], use_causal_info=cfg["use_causal_info"],

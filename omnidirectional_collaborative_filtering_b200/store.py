@@ -62,6 +62,9 @@ class RatingStore(object):
                                                    _lib.ptr(col), _lib.ptr(val), int(self.build_csc),
                                                    C.byref(out)))
             self._handle = out
+            if self.orig_pos is not None:
+                op = np.ascontiguousarray(self.orig_pos, dtype=np.int32)
+                _lib.check(_lib.lib().ocf_store_set_orig_pos(out, _lib.ptr(op)))
         return self._handle
 
     def info(self):
@@ -133,6 +136,7 @@ class DeviceBatch(object):
         out = C.c_void_p()
         _lib.check(_lib.lib().ocf_batch_create(self.max_rows, self.max_entries, C.byref(out)))
         self.handle = out
+        self.generation = 0         # bumped by every fill: tells whether a Batch's tiles are still here
 
     def fill_split(self, store: RatingStore, rows: np.ndarray, flags: np.ndarray, pass_through: bool,
                    aux_value: float, stream=None):
@@ -141,6 +145,7 @@ class DeviceBatch(object):
         _lib.check(_lib.lib().ocf_batch_fill_split(self.handle, store.handle, _lib.ptr(rows), rows.size,
                                                    _lib.ptr(flags), flags.size, int(bool(pass_through)),
                                                    float(aux_value), stream))
+        self.generation += 1
 
     def fill_split_uniform(self, store: RatingStore, rows: np.ndarray, u: np.ndarray, cdf0: np.ndarray,
                            full_len, pass_through: bool, aux_value: float, stream=None):
@@ -154,11 +159,29 @@ class DeviceBatch(object):
         _lib.check(_lib.lib().ocf_batch_fill_split_uniform(self.handle, store.handle, _lib.ptr(rows), rows.size,
                                                            _lib.ptr(u), u.size, _lib.ptr(cdf0), _lib.ptr(orig),
                                                            _lib.ptr(fl), int(bool(pass_through)), float(aux_value), stream))
+        self.generation += 1
+
+    def fill_split_rng(self, store: RatingStore, rows: np.ndarray, rng_handle, lo: float, hi: float, full_len,
+                       pass_through: bool, aux_value: float, stream=None):
+        """Like fill_split, with the random split drawn on the device from the NumPy stream the
+        `DeviceRng` holds (only the row ids cross PCIe)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        fl = None if full_len is None else np.ascontiguousarray(full_len, dtype=np.int64)
+        _lib.check(_lib.lib().ocf_batch_fill_split_rng(self.handle, store.handle, _lib.ptr(rows), rows.size, rng_handle,
+                                                       float(lo), float(hi), _lib.ptr(fl), int(bool(pass_through)),
+                                                       float(aux_value), stream))
+        self.generation += 1
+
+    def read_flags(self, n_entries: int, stream=None) -> np.ndarray:
+        out = np.empty(int(n_entries), dtype=np.uint8)
+        _lib.check(_lib.lib().ocf_batch_read_flags(self.handle, _lib.ptr(out), out.size, stream))
+        return out
 
     def fill_fixed(self, pair: StorePair, rows: np.ndarray, aux_value: float, stream=None):
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         _lib.check(_lib.lib().ocf_batch_fill_fixed(self.handle, pair.handle, _lib.ptr(rows), rows.size,
                                                    float(aux_value), stream))
+        self.generation += 1
 
     def info(self):
         buf = (C.c_int64 * 5)()

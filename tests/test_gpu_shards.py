@@ -64,6 +64,8 @@ def test_two_shards_match_unsharded_oracle(golden_datasets, aux, layers, opt, pd
         np.random.seed(3)
         g = rd.data_gen(B, [0.3, 0.8], "train", True, aux, -1)
         gens.append([next(g) for _ in range(4)])           # drain each rank's stream separately
+        for b in gens[-1]:
+            b.flags        # one process plays both ranks here: spend rank r's draws before the stream is reseeded
     lib = _lib.lib()
     summer = _LocalSum([om.model.comm for om in models])
     for step in range(4):
