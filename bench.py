@@ -390,6 +390,12 @@ def main():
     torch.cuda.synchronize()
     launches = lib.ocf_kernel_launches() - launches0
     ms = e0.elapsed_time(e1)
+    # the timed region lasts a few ms, nvidia-smi samples every 100 ms: keep the same steps running
+    # for ~0.6 s so the clock / throttle record is taken under this load
+    t_hold = time.perf_counter()
+    while time.perf_counter() - t_hold < 0.6:
+        device_steps(resident[W:], W)
+        torch.cuda.synchronize()
     ratings = sum(p.n_entries for p in plans[W:])
     value = ratings / (ms * 1e-3)
 
