@@ -290,6 +290,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "score"],
                     help="score: full-catalogue scoring rows/s as the line's metric (the train line carries it under 'scoring')")
     ap.add_argument("--score-rows", type=int, default=1024)
+    ap.add_argument("--parallel", default="columns", choices=["columns", "rows"],
+                    help="N > 1: item-dimension sharding (default) or data parallelism with a gradient all-reduce")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

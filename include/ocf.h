@@ -51,6 +51,7 @@ typedef struct ocf_pair ocf_pair;     /* (input store, target store) of a fixed-
 typedef struct ocf_batch ocf_batch;   /* one batch: row ids, keep-flags, gathered tiles      */
 typedef struct ocf_model ocf_model;   /* weights, optimizer state, workspaces                */
 typedef struct ocf_rng ocf_rng;       /* NumPy's MT19937 stream, resident on the device      */
+typedef struct ocf_comm ocf_comm;     /* one rank of an NCCL communicator (one process per GPU) */
 
 const char* ocf_last_error(void);
 int ocf_version(void);
@@ -118,11 +119,21 @@ int ocf_store_set_orig_pos(ocf_store* store, const int32_t* orig_pos);
  * bit what the reference draws: the stream's next n_rows doubles are
  * np.random.uniform(lo, hi, size=n_rows) (:120), the following sum(len(row)) doubles are the
  * rows' np.random.choice draws in batch order (:130). Nothing but the row ids crosses PCIe.
- * full_len[r] (column shards, else NULL) = full length of batch row r. */
+ * full_len[r] (column shards, else NULL) = full length of batch row r.
+ * slice (row-parallel ranks, else NULL): the listed rows are rows [row0, row0 + n_rows) of a
+ * larger drawing unit of n_draw_rows rows (the global batch); draws_before = ratings of the
+ * unit's rows before row0, draws_total = n_draw_rows + all its ratings. Every rank advances its
+ * copy of the stream by the whole unit and reads its own rows' draws. */
+typedef struct {
+  int32_t n_draw_rows;
+  int32_t row0;
+  int64_t draws_before;
+  int64_t draws_total;
+} ocf_rng_slice;
 int ocf_batch_fill_split_rng(ocf_batch* batch, const ocf_store* store, const int32_t* row_ids,
                              int32_t n_rows, ocf_rng* rng, double lo, double hi,
                              const int64_t* full_len, int pass_through, float aux_var_value,
-                             void* stream);
+                             const ocf_rng_slice* slice, void* stream);
 /* The keep flags of a split batch as the device holds them (synchronises `stream`). */
 int ocf_batch_read_flags(ocf_batch* batch, uint8_t* out, int64_t count, void* stream);
 /* build_sparse_batch_fixed_split, data_reader.py:202-298. */
@@ -231,6 +242,23 @@ int ocf_model_read_metrics(ocf_model* model, int64_t first, int32_t count, float
 int ocf_model_wait_metrics(ocf_model* model, int64_t step, float* host);
 /* Number of steps logged so far (train + eval). */
 int64_t ocf_model_steps_logged(const ocf_model* model);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch -------------------------------
+ * (absent in the reference, train.py:125-129 runs one session on one GPU)
+ * Rank 0 draws a 128-byte id and ships it to the other ranks by any means (torch.distributed,
+ * MPI, a file); every rank then creates its communicator on its own device. libnccl.so.2 is
+ * loaded at run time, so single-GPU use does not need it. */
+int ocf_comm_unique_id(uint8_t id[128]);
+int ocf_comm_create(const uint8_t id[128], int32_t rank, int32_t world, ocf_comm** out);
+int ocf_comm_destroy(ocf_comm* comm);
+typedef enum {
+  OCF_PAR_COLUMNS = 1,   /* item-dimension sharding: the model holds columns [lo, hi) (created with sharded = 1);
+                            a phase-0 step runs phases 1..3 with the two activation all-reduces inside */
+  OCF_PAR_ROWS = 2       /* data parallel: replicated weights, every rank steps on its own rows of the global batch
+                            (ocf_step_args.row0 / rows_total); gradients are summed with one all-reduce and applied by
+                            a streaming optimizer pass; the metrics cover the global batch. comm may be NULL (world 1) */
+} ocf_parallel;
+int ocf_model_set_comm(ocf_model* model, ocf_comm* comm, int mode);
 
 /* OCF_BUF_STATS_DH: the row statistics [max_rows, 4] immediately followed by dL/dh [max_rows, hp];
  * a shard all-reduces its prefix of 4*max_rows + rows*hp floats with one collective. */

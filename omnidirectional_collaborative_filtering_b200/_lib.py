@@ -30,6 +30,10 @@ class ModelConfig(C.Structure):
     ]
 
 
+class RngSlice(C.Structure):
+    _fields_ = [("n_draw_rows", C.c_int32), ("row0", C.c_int32), ("draws_before", C.c_int64), ("draws_total", C.c_int64)]
+
+
 class StepArgs(C.Structure):
     _fields_ = [("dropout_seed", C.c_uint64), ("step", C.c_uint32), ("row0", C.c_int32),
                 ("rows_total", C.c_int32), ("phase", C.c_int32)]
@@ -41,6 +45,7 @@ LOSSES = {"mean_squared_error": 0, "mse": 0, "mean_absolute_error": 1, "mae": 1}
 OPTIMIZERS = {"sgd": 0, "adagrad": 1, "rmsprop": 2, "adam": 3}
 N_METRICS = 8
 BUF_Z, BUF_DH, BUF_ROWSTATS, BUF_STATS_DH = 0, 1, 2, 3
+PAR_COLUMNS, PAR_ROWS = 1, 2
 
 _P = C.c_void_p
 _SIGNATURES = {
@@ -65,7 +70,12 @@ _SIGNATURES = {
     "ocf_rng_get_state": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "ocf_rng_skip": (C.c_int, [_P, C.c_int64]),
     "ocf_store_set_orig_pos": (C.c_int, [_P, _P]),
-    "ocf_batch_fill_split_rng": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, _P, C.c_int, C.c_float, _P]),
+    "ocf_batch_fill_split_rng": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, _P, C.c_int, C.c_float,
+                                           C.POINTER(RngSlice), _P]),
+    "ocf_comm_unique_id": (C.c_int, [_P]),
+    "ocf_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "ocf_comm_destroy": (C.c_int, [_P]),
+    "ocf_model_set_comm": (C.c_int, [_P, _P, C.c_int]),
     "ocf_batch_read_flags": (C.c_int, [_P, _P, C.c_int64, _P]),
     "ocf_profile_enable": (C.c_int, [C.c_int]),
     "ocf_profile_reset": (C.c_int, []),

@@ -1,4 +1,7 @@
 // libocf_b200: the C ABI of include/ocf.h over the kernels in ocf_kernels.cuh.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -49,9 +52,50 @@ struct Arena {
   }
 };
 
+// NCCL is loaded at run time (the library must load, and every single-GPU path must work, on a
+// box without it): the copy PyTorch already mapped into the process when there is one, else the
+// system's libnccl.so.2.
+struct NcclApi {
+  decltype(&ncclGetUniqueId) getUniqueId = nullptr;
+  decltype(&ncclCommInitRank) commInitRank = nullptr;
+  decltype(&ncclCommDestroy) commDestroy = nullptr;
+  decltype(&ncclAllReduce) allReduce = nullptr;
+  decltype(&ncclAllGather) allGather = nullptr;
+  decltype(&ncclGetErrorString) getErrorString = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.getUniqueId = reinterpret_cast<decltype(a.getUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.commInitRank = reinterpret_cast<decltype(a.commInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.commDestroy = reinterpret_cast<decltype(a.commDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.allReduce = reinterpret_cast<decltype(a.allReduce)>(dlsym(h, "ncclAllReduce"));
+    a.allGather = reinterpret_cast<decltype(a.allGather)>(dlsym(h, "ncclAllGather"));
+    a.getErrorString = reinterpret_cast<decltype(a.getErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.ok = a.getUniqueId && a.commInitRank && a.commDestroy && a.allReduce && a.allGather && a.getErrorString;
+    return a;
+  }();
+  return api;
+}
+#define OCF_NCCL(expr)                                                                        \
+  do {                                                                                        \
+    ncclResult_t _r = (expr);                                                                 \
+    if (_r != ncclSuccess)                                                                    \
+      return ::ocf::fail(OCF_ERR_CUDA, std::string(#expr) + ": " + nccl_api().getErrorString(_r)); \
+  } while (0)
+
 }  // namespace ocf
 
 using namespace ocf;
+
+struct ocf_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+};
 
 // ============================================================================================
 // handles
@@ -108,6 +152,9 @@ struct ocf_batch {
   uint32_t* d_words = nullptr;
   int64_t words_cap = 0;           // in draws (2 words each)
   double* d_cdf0 = nullptr;
+  int64_t cdf0_cap = 0;
+  int64_t draw_base = 0;           // index of the batch's first per-rating draw in its slice of the stream
+  int cdf0_row0 = 0;               // row-parallel slice: index of the batch's first row among the sparsity draws
   cudaEvent_t words_ready = nullptr, gathered = nullptr;
   bool rng_mode = false;
   Arena mem;
@@ -150,6 +197,14 @@ struct ocf_model {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool scan_pending = false;
+  // multi-GPU (ocf_model_set_comm)
+  ocf_comm* comm = nullptr;
+  int par_mode = 0;               // 0 none, OCF_PAR_COLUMNS, OCF_PAR_ROWS
+  float* grads = nullptr;         // row-parallel mode: one arena, per layer [kernel | bias] like the parameters
+  size_t grads_count = 0;
+  std::vector<float*> gW, gb;
+  float* gathered_stats = nullptr;   // [world * max_rows * 4] row statistics of the global batch
+  Arena par_mem;
   // tcgen05 scoring: TMA maps of the decoder kernel and of the top activation
   CUtensorMap map_w{}, map_h{};
   bool map_w_ok = false, map_h_ok = false;
@@ -499,7 +554,7 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
   int32_t* h_iptr = reinterpret_cast<int32_t*>(hs + off[3]);
   int4* h_items = reinterpret_cast<int4*>(hs + off[4]);
   int32_t* h_draw = reinterpret_cast<int32_t*>(hs + off[5]);
-  int64_t e = 0; int it = 0; int64_t tcount = 0; int64_t draw = n_rows;   // the first B draws are the rows' sparsities
+  int64_t e = 0; int it = 0; int64_t tcount = 0; int64_t draw = b->draw_base;   // the sparsity draws come first
   for (int r = 0; r < n_rows; ++r) {
     const int32_t row = row_ids[r];
     const int64_t na = rp_a[row + 1] - rp_a[row];
@@ -527,7 +582,7 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
   d.draw_off = reinterpret_cast<const int32_t*>(b->d_staging + off[5]);
   d.flags = b->d_staging + off[6];
   d.flags_out = b->d_staging + off[6];
-  d.words = b->d_words; d.cdf0 = b->d_cdf0;
+  d.words = b->d_words; d.cdf0 = b->d_cdf0 ? b->d_cdf0 + b->cdf0_row0 : nullptr;
   d.ent_col = b->d_ent_col; d.ent_val = b->d_ent_val; d.codes = b->d_codes;
   return OCF_OK;
 }
@@ -693,7 +748,7 @@ static int prepare_rowslot(ocf_batch* b, const ocf_store* store, const int32_t* 
 
 extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows,
                                         ocf_rng* rng, double lo, double hi, const int64_t* full_len, int pass_through,
-                                        float aux_var_value, void* stream_) {
+                                        float aux_var_value, const ocf_rng_slice* slice, void* stream_) {
   OCF_REQUIRE(b && store && row_ids && rng, "ocf_batch_fill_split_rng: null argument");
   OCF_REQUIRE(n_rows > 0 && n_rows <= b->max_rows, "ocf_batch_fill_split_rng: row count exceeds the batch capacity");
   OCF_REQUIRE((full_len != nullptr) == (store->dev.orig_pos != nullptr), "ocf_batch_fill_split_rng: full_len goes with a store that has ocf_store_set_orig_pos");
@@ -704,11 +759,29 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
     OCF_REQUIRE(row >= 0 && row < store->n_rows, "ocf_batch_fill_split_rng: row id out of range");
     draws += full_len ? full_len[r] : store->h_rowptr[row + 1] - store->h_rowptr[row];
   }
+  int n_draw_rows = n_rows;
+  b->draw_base = n_rows; b->cdf0_row0 = 0;
+  if (slice != nullptr) {
+    // these rows are a slice of a larger drawing unit (a rank's rows of a global batch): the unit's
+    // sparsity draws come first, then the draws of the rows before this slice
+    OCF_REQUIRE(slice->n_draw_rows >= n_rows && slice->row0 >= 0 && slice->row0 + n_rows <= slice->n_draw_rows &&
+                slice->draws_before >= 0 && slice->draws_total >= slice->n_draw_rows + slice->draws_before + (draws - n_rows),
+                "ocf_batch_fill_split_rng: inconsistent slice");
+    n_draw_rows = slice->n_draw_rows;
+    b->draw_base = slice->n_draw_rows + slice->draws_before;
+    b->cdf0_row0 = slice->row0;
+    draws = slice->draws_total;
+  }
   OCF_REQUIRE(draws < (int64_t(1) << 30), "ocf_batch_fill_split_rng: too many draws in one batch");
   if (!b->words_ready) {
     OCF_CUDA(cudaEventCreateWithFlags(&b->words_ready, cudaEventDisableTiming));
     OCF_CUDA(cudaEventCreateWithFlags(&b->gathered, cudaEventDisableTiming));
-    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_cdf0), sizeof(double) * (size_t)b->max_rows));
+  }
+  if (n_draw_rows > b->cdf0_cap) {
+    if (b->d_cdf0) { OCF_CUDA(cudaDeviceSynchronize()); cudaFree(b->d_cdf0); b->d_cdf0 = nullptr; }
+    const int64_t cap = std::max<int64_t>(n_draw_rows, b->max_rows);
+    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_cdf0), sizeof(double) * (size_t)cap));
+    b->cdf0_cap = cap;
   }
   if (draws > b->words_cap) {
     if (b->d_words) { OCF_CUDA(cudaDeviceSynchronize()); cudaFree(b->d_words); b->d_words = nullptr; }
@@ -719,7 +792,7 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
   // the previous batch staged in this object may still be reading its words (no-op before the first gather)
   OCF_CUDA(cudaStreamWaitEvent(rng->stream, b->gathered, 0));
   // the stream's next `draws` doubles, generated beside whatever `stream` is running
-  k_mt_words<<<1, 256, 0, rng->stream>>>(rng->d_state, 2 * (long long)draws, b->d_words, n_rows, lo, hi - lo, b->d_cdf0);
+  k_mt_words<<<1, 256, 0, rng->stream>>>(rng->d_state, 2 * (long long)draws, b->d_words, n_draw_rows, lo, hi - lo, b->d_cdf0);
   OCF_LAUNCHED();
   OCF_CUDA(cudaEventRecord(b->words_ready, rng->stream));
   OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split_rng"));
@@ -880,7 +953,7 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
 
 extern "C" int ocf_model_destroy(ocf_model* m) {
   if (m) {
-    m->mem.release(); m->opt_mem.release(); m->dense_mem.release(); m->ws_mem.release();
+    m->mem.release(); m->opt_mem.release(); m->dense_mem.release(); m->ws_mem.release(); m->par_mem.release();
     if (m->h_rec) cudaFreeHost(m->h_rec);
     for (int k = 0; k < 64; ++k) if (m->step_ev[k]) cudaEventDestroy(m->step_ev[k]);
     if (m->side) cudaStreamDestroy(m->side);
@@ -1168,10 +1241,11 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   return OCF_OK;
 }
 
-static int launch_metrics(ocf_model* m, int B, const ocf_step_args* args, int n_reg, cudaStream_t st) {
+static int launch_metrics(ocf_model* m, int B, const ocf_step_args* args, int n_reg, cudaStream_t st,
+                          const float* stats = nullptr) {
   const int rows_total = (args && args->rows_total > 0) ? args->rows_total : B;
   float* rec = m->d_log + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
-  k_metrics<<<1, 32, 0, st>>>(m->rowstats, B, (float)rows_total, (float)m->cfg.n_cols_total, m->cfg.rating_range,
+  k_metrics<<<1, 32, 0, st>>>(stats ? stats : m->rowstats, B, (float)rows_total, (float)m->cfg.n_cols_total, m->cfg.rating_range,
                               m->cfg.loss, m->regparts, n_reg, m->cfg.l2 >= 0.f ? m->cfg.l2 : 0.f, rec);
   OCF_LAUNCHED();
   // every step's record goes back to pinned host memory right behind its kernels; readers wait
@@ -1199,6 +1273,7 @@ static int launch_row_update_nv(int kind, int grid, const RowArgs& r, cudaStream
     case OCF_OPT_SGD: k_row_update<NV, OCF_OPT_SGD><<<grid, 256, 0, st>>>(r); break;
     case OCF_OPT_ADAGRAD: k_row_update<NV, OCF_OPT_ADAGRAD><<<grid, 256, 0, st>>>(r); break;
     case OCF_OPT_RMSPROP: k_row_update<NV, OCF_OPT_RMSPROP><<<grid, 256, 0, st>>>(r); break;
+    case KIND_GRAD: k_row_update<NV, KIND_GRAD><<<grid, 256, 0, st>>>(r); break;
     default: k_row_update<NV, OCF_OPT_ADAM><<<grid, 256, 0, st>>>(r); break;
   }
   OCF_LAUNCHED();
@@ -1237,7 +1312,8 @@ static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
 }
 
 // K4b: one warp per (column, array) task: gradient row from the matches, fused optimizer update.
-static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int hpx, const OptDev& opt, cudaStream_t st) {
+static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int hpx, const OptDev& opt, cudaStream_t st,
+                       bool grad_mode = false) {
   if (!do_dec && !do_enc) return OCF_OK;
   const int L = m->L;
   const bool drop = m->cfg.dropout_p > 0.f;
@@ -1249,11 +1325,12 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
   r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
   r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.aux_val = b->aux_value; r.opt = opt;
-  r.dense = opt.dense; r.n_arr = 0;
+  r.dense = grad_mode ? 0 : opt.dense; r.n_arr = 0;
+  if (grad_mode) { r.Gdec = m->gW[L]; r.Genc = m->gW[0]; r.gbdec = m->gb[L]; }
   if (do_dec) r.arr_map[r.n_arr++] = 0;
   if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
   g_prof.begin(5, st);
-  OCF_TRY(launch_row_update(hpx, opt.kind, m->sm_count * 6, r, st));
+  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count * 6, r, st));
   g_prof.end(5, st);
   return OCF_OK;
 }
@@ -1265,30 +1342,38 @@ static int fork_scan(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
   const int L = m->L;
   if (m->hp[L - 1] != m->hp[0]) return OCF_OK;
   const OptDev opt = make_opt(m);
-  if (b->dev.n_entries == 0 && !opt.dense) return OCF_OK;
+  const int dense = m->par_mode == OCF_PAR_ROWS ? 0 : opt.dense;   // gradient rows exist for touched columns only
+  if (b->dev.n_entries == 0 && !dense) return OCF_OK;
   const int do_dec = m->layers[L].trainable ? 1 : 0, do_enc = m->layers[0].trainable ? 1 : 0;
   if (!do_dec && !do_enc) return OCF_OK;
   OCF_CUDA(cudaEventRecord(m->ev_fork, st));
   OCF_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-  OCF_TRY(launch_scan(m, b, do_dec, do_enc, opt.dense, m->side));
+  OCF_TRY(launch_scan(m, b, do_dec, do_enc, dense, m->side));
   OCF_CUDA(cudaEventRecord(m->ev_join, m->side));
   m->scan_pending = true;
   return OCF_OK;
 }
 
 // phase 3 (training): backward through the hidden layers, fused updates, metrics
-static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* args, cudaStream_t st) {
+// grad_mode (row-parallel): the same backward pass, but every gradient lands in the gradient arena
+// (zeroed first: untouched weight rows have no gradient) and nothing is applied or logged; the
+// caller all-reduces the arena and runs apply_gradients().
+static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* args, cudaStream_t st, bool grad_mode = false,
+                        int* n_reg_out = nullptr) {
   const BatchDev& bt = b->dev;
   const int L = m->L, B = bt.B;
   const bool drop = m->cfg.dropout_p > 0.f;
   const OptDev opt = make_opt(m);
   const int n_reg = launch_reg(m, st);          // L2 term of the reported loss uses pre-update weights
+  if (n_reg_out) *n_reg_out = n_reg;
+  if (grad_mode) OCF_CUDA(cudaMemsetAsync(m->grads, 0, sizeof(float) * m->grads_count, st));
   // top hidden layer: dz and its bias
   {
     const int l = L - 1;
     Layer& ly = m->layers[l];
     k_dz_bias<<<m->hp[l] / 32, 256, 0, st>>>(m->dh_top, m->act[l], drop ? m->dscale[l] : nullptr, B, m->hp[l],
-                                                     m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt, ly.trainable ? 1 : 0);
+                                                     m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt, ly.trainable ? 1 : 0,
+                                                     grad_mode ? m->gb[l] : nullptr);
     OCF_LAUNCHED();
   }
   for (int l = L - 1; l >= 1; --l) {
@@ -1299,11 +1384,13 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     OCF_TRY(launch_gemm(false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
     Layer& lo = m->layers[l - 1];
     k_dz_bias<<<m->hp[l - 1] / 32, 256, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
-                                                         m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0);
+                                                         m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0,
+                                                         grad_mode ? m->gb[l - 1] : nullptr);
     OCF_LAUNCHED();
     if (ly.trainable) {
       // dW_l = h_{l-1}^T . dz_l, fused with the update of W_l
       GemmEpi eu{}; eu.kind = EPI_UPDATE; eu.C = ly.W; eu.ldc = m->hp[l]; eu.s1 = ly.Ws1; eu.s2 = ly.Ws2; eu.opt = opt;
+      if (grad_mode) { eu.kind = EPI_STORE; eu.C = m->gW[l]; }
       const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
       OCF_TRY(launch_gemm(true, false, hin, m->hp[l - 1], m->dz[l], m->hp[l], m->hp[l - 1], m->hp[l], B, eu, st));
     }
@@ -1312,20 +1399,22 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   Layer& enc = m->layers[0];
   Layer& dec = m->layers[L];
   const int hpd = m->hp[L - 1], hpe = m->hp[0];
-  if (bt.n_entries > 0 || opt.dense) {
+  const int dense = grad_mode ? 0 : opt.dense;
+  if (bt.n_entries > 0 || dense) {
     // decoder and encoder rows share one padded width in the reference's architectures (one
     // num_hidden_units): one scan feeds both. A width list with different ends scans twice.
     if (hpd == hpe) {
       if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
-      else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, opt.dense, st));
-      OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd, opt, st));
+      else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, dense, st));
+      OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd, opt, st, grad_mode));
     } else {
-      OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, 0, opt.dense, st));
-      OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, 0, hpd, opt, st));
-      OCF_TRY(launch_scan(m, b, 0, enc.trainable ? 1 : 0, opt.dense, st));
-      OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st));
+      OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, 0, dense, st));
+      OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, 0, hpd, opt, st, grad_mode));
+      OCF_TRY(launch_scan(m, b, 0, enc.trainable ? 1 : 0, dense, st));
+      OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st, grad_mode));
     }
   }
+  if (grad_mode) return OCF_OK;
   m->iterations += 1;
   return launch_metrics(m, B, args, n_reg, st);
 }
@@ -1343,11 +1432,125 @@ static int finish_step(ocf_model* m, float* host_metrics, cudaStream_t) {
   return ocf_model_wait_metrics(m, m->steps_logged - 1, host_metrics);
 }
 
+// ---- multi-GPU ------------------------------------------------------------------------------------
+extern "C" int ocf_comm_unique_id(uint8_t* id) {
+  OCF_REQUIRE(id != nullptr, "ocf_comm_unique_id: null argument");
+  if (!nccl_api().ok) return fail(OCF_ERR_STATE, "NCCL (libnccl.so.2) could not be loaded");
+  ncclUniqueId u;
+  OCF_NCCL(nccl_api().getUniqueId(&u));
+  std::memcpy(id, u.internal, NCCL_UNIQUE_ID_BYTES);
+  return OCF_OK;
+}
+
+extern "C" int ocf_comm_create(const uint8_t* id, int32_t rank, int32_t world, ocf_comm** out) {
+  OCF_REQUIRE(id && out && world >= 1 && rank >= 0 && rank < world, "ocf_comm_create: bad argument");
+  *out = nullptr;
+  if (!nccl_api().ok) return fail(OCF_ERR_STATE, "NCCL (libnccl.so.2) could not be loaded");
+  ocf_comm* c = new ocf_comm();
+  c->rank = rank; c->world = world;
+  if (cudaGetDevice(&c->device) != cudaSuccess) { cudaGetLastError(); delete c; return fail(OCF_ERR_CUDA, "ocf_comm_create: no CUDA device"); }
+  ncclUniqueId u;
+  std::memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
+  ncclResult_t r = nccl_api().commInitRank(&c->comm, world, u, rank);
+  if (r != ncclSuccess) { delete c; return fail(OCF_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_api().getErrorString(r)); }
+  *out = c;
+  return OCF_OK;
+}
+
+extern "C" int ocf_comm_destroy(ocf_comm* c) {
+  if (c) { if (c->comm) nccl_api().commDestroy(c->comm); delete c; }
+  return OCF_OK;
+}
+
+extern "C" int ocf_model_set_comm(ocf_model* m, ocf_comm* comm, int mode) {
+  OCF_REQUIRE(m && (mode == OCF_PAR_COLUMNS || mode == OCF_PAR_ROWS), "ocf_model_set_comm: bad argument");
+  OCF_REQUIRE(mode != OCF_PAR_COLUMNS || (comm != nullptr && m->cfg.sharded), "ocf_model_set_comm: column mode needs a communicator and a model created with sharded = 1");
+  OCF_REQUIRE(mode != OCF_PAR_ROWS || !m->cfg.sharded, "ocf_model_set_comm: row mode needs an unsharded (replicated) model");
+  OCF_CUDA(cudaDeviceSynchronize());
+  m->comm = comm; m->par_mode = mode;
+  if (mode == OCF_PAR_ROWS && m->grads == nullptr) {
+    size_t total = 0;
+    for (const Layer& ly : m->layers) total += (size_t)ly.rows * ly.hp + (size_t)align_up((size_t)ly.bias_len, 4);
+    OCF_TRY(m->par_mem.get(&m->grads, total, true));
+    m->grads_count = total;
+    m->gW.clear(); m->gb.clear();
+    size_t off = 0;
+    for (const Layer& ly : m->layers) {
+      m->gW.push_back(m->grads + off); off += (size_t)ly.rows * ly.hp;
+      m->gb.push_back(m->grads + off); off += align_up((size_t)ly.bias_len, 4);
+    }
+    const int world = comm ? comm->world : 1;
+    OCF_TRY(m->par_mem.get(&m->gathered_stats, (size_t)world * MAX_BATCH_ROWS * ROWSTAT_W, true));
+  }
+  return OCF_OK;
+}
+
+// Row-parallel mode, after the gradient all-reduce: one streaming pass per parameter array.
+static int apply_gradients(ocf_model* m, cudaStream_t st) {
+  const OptDev opt = make_opt(m);
+  OptDev ob = opt; ob.l2x2 = 0.f;                 // Keras regularises kernels only
+  g_prof.begin(6, st);
+  for (int l = 0; l <= m->L; ++l) {
+    Layer& ly = m->layers[l];
+    if (!ly.trainable) continue;
+    const size_t n = (size_t)ly.rows * ly.hp;
+    const int grid = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)m->sm_count * 8);
+    k_dense_update<<<std::max(grid, 1), 256, 0, st>>>(ly.W, m->gW[l], ly.Ws1, ly.Ws2, n, opt);
+    OCF_LAUNCHED();
+    k_dense_update<<<std::max(1, std::min((ly.bias_len + 255) / 256, m->sm_count)), 256, 0, st>>>(ly.b, m->gb[l], ly.bs1, ly.bs2, (size_t)ly.bias_len, ob);
+    OCF_LAUNCHED();
+  }
+  g_prof.end(6, st);
+  m->iterations += 1;
+  return OCF_OK;
+}
+
+// Row statistics of the global batch (every rank's rows) for the metrics of a row-parallel step.
+static int gather_stats(ocf_model* m, int B, const ocf_step_args* args, const float** stats, int* rows, cudaStream_t st) {
+  *stats = m->rowstats; *rows = B;
+  if (m->comm == nullptr || m->comm->world == 1) return OCF_OK;
+  const int world = m->comm->world;
+  OCF_REQUIRE(args && args->rows_total == world * B, "row-parallel step: rows_total must be world x the rank's rows (equal slices)");
+  OCF_NCCL(nccl_api().allGather(m->rowstats, m->gathered_stats, (size_t)B * ROWSTAT_W, ncclFloat, m->comm->comm, st));
+  *stats = m->gathered_stats; *rows = world * B;
+  return OCF_OK;
+}
+
 extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
   OCF_TRY(check_step(m, b, true));
   cudaStream_t st = as_stream(stream_);
   const int phase = args ? args->phase : 0;
   OCF_REQUIRE(phase >= 0 && phase <= 3, "ocf_train_step: phase must be 0..3");
+  if (phase == 0 && m->par_mode == OCF_PAR_ROWS) {
+    // data parallel over rows: replicated weights, this rank's rows, gradients summed over ranks
+    OCF_TRY(fork_scan(m, b, st));
+    OCF_TRY(phase_encode(m, b, st));
+    OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
+    int n_reg = 0;
+    OCF_TRY(phase_update(m, b, args, st, true, &n_reg));
+    if (m->comm && m->comm->world > 1) {
+      g_prof.begin(7, st);
+      OCF_NCCL(nccl_api().allReduce(m->grads, m->grads, m->grads_count, ncclFloat, ncclSum, m->comm->comm, st));
+      g_prof.end(7, st);
+    }
+    const float* stats; int rows;
+    OCF_TRY(gather_stats(m, b->dev.B, args, &stats, &rows, st));
+    OCF_TRY(apply_gradients(m, st));
+    OCF_TRY(launch_metrics(m, rows, args, n_reg, st, stats));
+    return finish_step(m, host_metrics, st);
+  }
+  if (phase == 0 && m->par_mode == OCF_PAR_COLUMNS) {
+    // column shards: the three phases back to back with the two activation all-reduces between them
+    const int B = b->dev.B;
+    OCF_TRY(fork_scan(m, b, st));
+    OCF_TRY(phase_encode(m, b, st));
+    OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
+    OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
+    OCF_NCCL(nccl_api().allReduce(m->rowstats, m->rowstats, (size_t)m->cfg.max_rows * ROWSTAT_W + (size_t)B * m->hp[m->L - 1],
+                                  ncclFloat, ncclSum, m->comm->comm, st));
+    OCF_TRY(phase_update(m, b, args, st));
+    return finish_step(m, host_metrics, st);
+  }
   if (phase == 0 || phase == 1) { OCF_TRY(fork_scan(m, b, st)); OCF_TRY(phase_encode(m, b, st)); }
   if (phase == 0 || phase == 2) OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
   if (phase == 0 || phase == 3) { OCF_TRY(phase_update(m, b, args, st)); OCF_TRY(finish_step(m, host_metrics, st)); }
@@ -1359,12 +1562,42 @@ extern "C" int ocf_eval_step(ocf_model* m, ocf_batch* b, const ocf_step_args* ar
   cudaStream_t st = as_stream(stream_);
   const int phase = args ? args->phase : 0;
   OCF_REQUIRE(phase >= 0 && phase <= 3, "ocf_eval_step: phase must be 0..3");
+  if (phase == 0 && m->par_mode == OCF_PAR_ROWS) {
+    OCF_TRY(phase_encode(m, b, st));
+    OCF_TRY(phase_decode(m, b, false, args, nullptr, st));
+    const float* stats; int rows;
+    OCF_TRY(gather_stats(m, b->dev.B, args, &stats, &rows, st));
+    const int n_reg = launch_reg(m, st);
+    OCF_TRY(launch_metrics(m, rows, args, n_reg, st, stats));
+    return finish_step(m, host_metrics, st);
+  }
+  if (phase == 0 && m->par_mode == OCF_PAR_COLUMNS) {
+    const int B = b->dev.B;
+    OCF_TRY(phase_encode(m, b, st));
+    OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
+    OCF_TRY(phase_decode(m, b, false, args, nullptr, st));
+    OCF_NCCL(nccl_api().allReduce(m->rowstats, m->rowstats, (size_t)m->cfg.max_rows * ROWSTAT_W, ncclFloat, ncclSum, m->comm->comm, st));
+    const int n_reg = launch_reg(m, st);
+    OCF_TRY(launch_metrics(m, B, args, n_reg, st));
+    return finish_step(m, host_metrics, st);
+  }
   if (phase == 0 || phase == 1) OCF_TRY(phase_encode(m, b, st));
   if (phase == 0 || phase == 2) OCF_TRY(phase_decode(m, b, false, args, nullptr, st));
   if (phase == 0 || phase == 3) {
     const int n_reg = launch_reg(m, st);
     OCF_TRY(launch_metrics(m, b->dev.B, args, n_reg, st));
     OCF_TRY(finish_step(m, host_metrics, st));
+  }
+  return OCF_OK;
+}
+
+// Encoder pre-activations for predict / score. A column shard with a communicator reduces them
+// here; without one its caller has already run phase 1 and the z all-reduce.
+static int encode_for_output(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
+  if (!m->cfg.sharded) return phase_encode(m, b, st);
+  if (m->par_mode == OCF_PAR_COLUMNS) {
+    OCF_TRY(phase_encode(m, b, st));
+    OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)b->dev.B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
   }
   return OCF_OK;
 }
@@ -1381,7 +1614,7 @@ extern "C" int ocf_predict(ocf_model* m, ocf_batch* b, float* out, void* stream_
   OCF_TRY(ensure_dense(m));
   const size_t count = (size_t)b->dev.B * m->cfg.n_cols;
   OCF_CUDA(cudaMemsetAsync(m->dense_out, 0, sizeof(float) * count, st));
-  if (!m->cfg.sharded) OCF_TRY(phase_encode(m, b, st));   // a shard's caller has run phase 1 + the z all-reduce
+  OCF_TRY(encode_for_output(m, b, st));
   OCF_TRY(phase_decode(m, b, false, nullptr, m->dense_out, st));
   OCF_CUDA(cudaMemcpyAsync(out, m->dense_out, sizeof(float) * count, cudaMemcpyDeviceToHost, st));
   OCF_CUDA(cudaStreamSynchronize(st));
@@ -1393,7 +1626,7 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   OCF_REQUIRE(out != nullptr, "ocf_score: null output");
   cudaStream_t st = as_stream(stream_);
   const int L = m->L, B = b->dev.B;
-  if (!m->cfg.sharded) OCF_TRY(phase_encode(m, b, st));   // a shard's caller has run phase 1 + the z all-reduce
+  OCF_TRY(encode_for_output(m, b, st));
   OCF_TRY(launch_act(m, 0, B, false, nullptr, st));
   for (int l = 1; l < L; ++l) {
     GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];

@@ -409,7 +409,7 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
 __global__ void __launch_bounds__(256)
 k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float* __restrict__ dscale,
           int B, int HP, int act, int dh_is_dz, float* __restrict__ dz, float* __restrict__ bias,
-          float* __restrict__ s1, float* __restrict__ s2, OptDev o, int trainable) {
+          float* __restrict__ s1, float* __restrict__ s2, OptDev o, int trainable, float* __restrict__ gbias) {
   __shared__ float part[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = blockIdx.x * 32 + lane;
@@ -432,6 +432,7 @@ k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float
     g = part[0][lane];
 #pragma unroll
     for (int w = 1; w < 8; ++w) g += part[w][lane];
+    if (gbias != nullptr) { gbias[u] = g; return; }   // row-parallel mode: the gradient is reduced over ranks first
     o.l2x2 = 0.f;                     // Keras regularises kernels only (model.py:66,82)
     float w = bias[u], t1 = s1 ? s1[u] : 0.f, t2 = s2 ? s2[u] : 0.f;
     opt_apply(o, g, w, t1, t2);
@@ -730,14 +731,18 @@ struct RowArgs {
   float* WdecT; float* Wd_s1; float* Wd_s2;
   float* bdec; float* bd_s1; float* bd_s2;
   float* Wenc; float* We_s1; float* We_s2;
+  float* Gdec; float* Genc; float* gbdec;   // KIND_GRAD: gradient rows instead of updates (row-parallel mode)
   int n_cols; int3 bits; float aux_val;
   int dense; int n_arr; int arr_map[4];
   OptDev opt;
 };
 
+constexpr int KIND_GRAD = 4;              // k_row_update: store the gradient row, apply nothing
+
 template <int NV, int KIND>
 __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
   constexpr int HP = NV * 128;
+  constexpr bool LOAD_W = KIND != KIND_GRAD;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -758,8 +763,8 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
     float4 w[NV], t1[NV], t2[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      w[v] = *reinterpret_cast<const float4*>(Wrow + v * 128);
-      t1[v] = KIND != OCF_OPT_SGD ? *reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      w[v] = LOAD_W ? *reinterpret_cast<const float4*>(Wrow + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      t1[v] = (LOAD_W && KIND != OCF_OPT_SGD) ? *reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
       t2[v] = KIND == OCF_OPT_ADAM ? *reinterpret_cast<const float4*>(S2row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float* X = (arr == 0 ? a.hdec : a.dz0) + lane * 4;
@@ -787,6 +792,13 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
         cs += cf;
       }
     }
+    if (KIND == KIND_GRAD) {
+      float* Grow = (arr == 0 ? a.Gdec : a.Genc) + r + lane * 4;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) *reinterpret_cast<float4*>(Grow + v * 128) = g[v];
+      if (arr == 0 && lane == 0) a.gbdec[c] = cs;
+      continue;
+    }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       opt_apply_k<KIND>(a.opt, g[v].x, w[v].x, t1[v].x, t2[v].x);
@@ -805,6 +817,34 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
       if (KIND != OCF_OPT_SGD) a.bd_s1[c] = b1;
       if (KIND == OCF_OPT_ADAM) a.bd_s2[c] = b2;
     }
+  }
+}
+
+// Row-parallel (data-parallel) mode: the gradients of all ranks are summed by an all-reduce
+// first, so the optimizer runs as a plain stream over (parameter, gradient, state): 20 B/param
+// for Adagrad/RMSprop, 28 for Adam. n is a multiple of 4 for kernels; biases take the scalar tail.
+__global__ void __launch_bounds__(256)
+k_dense_update(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ s1, float* __restrict__ s2,
+               size_t n, OptDev o) {
+  const size_t n4 = n / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 wv = reinterpret_cast<float4*>(w)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 a = s1 ? reinterpret_cast<float4*>(s1)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 b = s2 ? reinterpret_cast<float4*>(s2)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    opt_apply(o, gv.x, wv.x, a.x, b.x); opt_apply(o, gv.y, wv.y, a.y, b.y);
+    opt_apply(o, gv.z, wv.z, a.z, b.z); opt_apply(o, gv.w, wv.w, a.w, b.w);
+    reinterpret_cast<float4*>(w)[i] = wv;
+    if (s1) reinterpret_cast<float4*>(s1)[i] = a;
+    if (s2) reinterpret_cast<float4*>(s2)[i] = b;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float wv = w[i], a = s1 ? s1[i] : 0.f, b = s2 ? s2[i] : 0.f;
+    opt_apply(o, g[i], wv, a, b);
+    w[i] = wv;
+    if (s1) s1[i] = a;
+    if (s2) s2[i] = b;
   }
 }
 

@@ -169,6 +169,9 @@ class Batch(object):
         self.u = self.cdf0 = self.full_len = None
         self.ticket = None                     # device-RNG mode: the batch's place in the NumPy stream
         self.sparsity = None                   #   (lo, hi) of its np.random.uniform draw
+        self.rng_slice = None                  #   row-parallel slice of a global batch (see row_slice)
+        self.row0 = 0                          # index of the first row inside the global batch
+        self.rows_total = 0                    # rows of the global batch (0: this batch is the whole of it)
         self._dev_generation = -1
         self.pass_through = bool(pass_through)
         self.aux_type = aux_type
@@ -215,7 +218,7 @@ class Batch(object):
         if self.kind == "split" and self.ticket is not None and self._flags is None:
             handle = DeviceRng.get().consume(self.ticket)
             dev.fill_split_rng(self.source, self.rows, handle, self.sparsity[0], self.sparsity[1], self.full_len,
-                               self.pass_through, self.aux_value, stream)
+                               self.pass_through, self.aux_value, stream, self.rng_slice)
             self._dev_generation = dev.generation
         elif self.kind == "split" and self._flags is None:
             dev.fill_split_uniform(self.source, self.rows, self.u, self.cdf0, self.full_len, self.pass_through,
@@ -226,6 +229,36 @@ class Batch(object):
             dev.fill_fixed(self.source, self.rows, self.aux_value, stream)
         self._device = dev
         return dev
+
+    def row_slice(self, rank, world):
+        """Rows [rank*B/world, (rank+1)*B/world) of this (global) batch as a batch of their own: what a
+        data-parallel rank steps on. The random split stays the global batch's: every rank replays the
+        whole batch's draws and reads its own rows' (on the device, or from the host draws)."""
+        if self.n_rows % world:
+            raise ValueError("a global batch of %d rows does not split over %d ranks" % (self.n_rows, world))
+        if self.source.orig_pos is not None if self.kind == "split" else False:
+            raise ValueError("row slices are taken from an unsharded reader")
+        per = self.n_rows // world
+        lo = rank * per
+        rows = self.rows[lo:lo + per]
+        if self.kind == "fixed":
+            tcount = int(self.source.tgt_store.full_lengths[rows].sum())
+            sub = Batch(self.reader, "fixed", self.source, rows, None, False, self.aux_type, self.aux_value, tcount,
+                        self.return_target_count, tcount + int(self.source.in_store.full_lengths[rows].sum()))
+        else:
+            lens = self.source.lengths[self.rows]
+            before, mine = int(lens[:lo].sum()), int(lens[lo:lo + per].sum())
+            sub = Batch(self.reader, "split", self.source, rows, None, self.pass_through, self.aux_type, self.aux_value,
+                        mine if self.pass_through else -1, False, mine)
+            if self.ticket is not None and self._flags is None:
+                sub.ticket, sub.sparsity = self.ticket, self.sparsity
+                sub.rng_slice = (self.n_rows, lo, before, self.n_rows + int(lens.sum()))
+            elif self._flags is None:
+                sub.u, sub.cdf0 = self.u[before:before + mine], self.cdf0[lo:lo + per]
+            else:
+                sub._flags = self._flags[before:before + mine]
+        sub.row0, sub.rows_total = lo, self.n_rows
+        return sub
 
     # -- reference-shaped view ---------------------------------------------------------------
     def to_dense(self, stream=None):

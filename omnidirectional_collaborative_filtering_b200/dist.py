@@ -1,4 +1,5 @@
-"""Multi-GPU: column (catalogue-dimension) sharding over one process per GPU.
+"""Multi-GPU, one process per GPU: column (catalogue-dimension) sharding, and row (data)
+parallelism with a gradient all-reduce.
 
 Why columns. At the reference's batch size the step is bound by the weight + optimizer-state
 stream, not by the batch, so replicating the weights and all-reducing
@@ -17,8 +18,18 @@ Hidden layers and biases are replicated and receive identical updates on every r
 is the single-GPU model at global batch `rows` (up to fp32 summation order), which is how a
 data-parallel run of G x per-GPU-batch is obtained here ("weak" scaling in bench.py).
 
-`torch.distributed` (NCCL over NVLink/NVSwitch on GPUs; gloo for the CPU tests of the host
-logic) is the plumbing: the collectives run on torch tensors that alias the library's buffers.
+Row parallelism (`row_parallel_model`, SURVEY.md section 8e first row) is the textbook scheme the
+north star names: replicated weights, rank g steps on rows [gB, (g+1)B) of every global batch,
+the gradients of all trainable parameters are summed with ONE NCCL all-reduce and applied by a
+streaming optimizer pass. It moves the whole parameter set over NVLink every step (66-440 MB on
+ML-10M shapes) and cannot fuse the update into the weight-gradient kernel, so it is provided for
+completeness and for small models; column sharding is the path that scales.
+
+The collectives of both schemes run INSIDE the C library (`ocf_comm_*`, `ocf_model_set_comm`:
+ncclAllReduce / ncclAllGather on the step's stream, one C call per step). `torch.distributed`
+only boots the ranks and ships the NCCL id; `ShardComm` (collectives on torch tensors aliasing the
+library's buffers, gloo-capable) remains for the CPU tests of the host logic and for runs without
+libnccl.
 """
 from __future__ import annotations
 
@@ -105,13 +116,50 @@ class ShardComm(object):
         self.dist.all_reduce(self.stats_dh[:n], group=self.group)
 
 
-def sharded_model(rank: int, world: int, numlayers, num_hidden_units, input_shape, batch_size, **kw):
+class NativeComm(object):
+    """This rank's NCCL communicator inside the C library (`ocf_comm_create`). The 128-byte NCCL
+    id is drawn on rank 0 and shipped over the already initialised torch.distributed group."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        lib = _lib.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ident = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            _lib.check(lib.ocf_comm_unique_id(ident))
+        box = [bytes(ident) if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        out = C.c_void_p()
+        _lib.check(lib.ocf_comm_create(ident, self.rank, self.world, C.byref(out)))
+        self.handle = out
+
+    def close(self):
+        if self.handle is not None:
+            _lib.lib().ocf_comm_destroy(self.handle)
+            self.handle = None
+
+
+def sharded_model(rank: int, world: int, numlayers, num_hidden_units, input_shape, batch_size, native=None, **kw):
     """`omni_model` for this rank's column slice. Every rank must call it with the same NumPy
-    global RNG state: the full glorot initialisation is drawn identically everywhere and sliced."""
+    global RNG state: the full glorot initialisation is drawn identically everywhere and sliced.
+    `native`: a NativeComm -> the step's two all-reduces run inside the C library."""
     from .model import omni_model
     lo, hi = col_range(int(input_shape), rank, world)
     om = omni_model(numlayers, num_hidden_units, input_shape, batch_size, local_cols=hi - lo, col_lo=lo, **kw)
     om.model.comm = ShardComm(om.model)
+    if native is not None:
+        om.model.native = (native, _lib.PAR_COLUMNS)
+    return om
+
+
+def row_parallel_model(native, numlayers, num_hidden_units, input_shape, batch_size, **kw):
+    """Replicated `omni_model` for data parallelism over rows (same NumPy stream on every rank ->
+    same initialisation). Feed it `batch.row_slice(rank, world)` of every global batch. `native`
+    None = a single rank (the gradient path without the all-reduce)."""
+    from .model import omni_model
+    om = omni_model(numlayers, num_hidden_units, input_shape, batch_size, **kw)
+    om.model.native = (native, _lib.PAR_ROWS)
     return om
 
 
@@ -144,18 +192,24 @@ def bench_main(args, w, cfg, rank, world):
     dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.lib()
     B = args.batch_size * world
+    rows_mode = getattr(args, "parallel", "columns") == "rows"
     fs = None
     if rank == 0:
         fs = bench.make_dataset(w)             # generate (or load the /tmp cache) once
     dist.barrier()
     if fs is None:
         fs = bench.make_dataset(w)
-    rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs, shard=(rank, world))
+    native = NativeComm()
+    rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs,
+                     shard=None if rows_mode else (rank, world))
     aux = w["aux"]
     np.random.seed(0)
-    om = sharded_model(rank, world, w["layers"], w["hidden"], fs.n_cols, B, dense_activation=w["act"],
-                       use_causal_info=aux is not None, use_both_masks=aux == "both",
-                       dropout_probability=w["dropout"], auxilliary_mask_type=aux)
+    mkw = dict(dense_activation=w["act"], use_causal_info=aux is not None, use_both_masks=aux == "both",
+               dropout_probability=w["dropout"], auxilliary_mask_type=aux)
+    if rows_mode:
+        om = row_parallel_model(native, w["layers"], w["hidden"], fs.n_cols, args.batch_size, **mkw)
+    else:
+        om = sharded_model(rank, world, w["layers"], w["hidden"], fs.n_cols, B, native=native, **mkw)
     m = om.model
     opt = {"adagrad": optimizers.Adagrad, "rmsprop": optimizers.RMSprop, "adam": optimizers.Adam}[w["opt"][0]](lr=w["opt"][1])
     m.compile(opt, "mean_squared_error", rating_range=fs.rating_range)
@@ -171,7 +225,7 @@ def bench_main(args, w, cfg, rank, world):
             if b is None:
                 g = gen()
                 continue
-            yield b
+            yield b.row_slice(rank, world) if rows_mode else b
 
     batches = endless()
     plans = []
@@ -179,7 +233,7 @@ def bench_main(args, w, cfg, rank, world):
         p = next(batches)
         p.flags                             # spend the batch's draws before the next one is drawn
         plans.append(p)
-    m._ensure(B, max(p.n_entries for p in plans), aux, rd)
+    m._ensure(plans[0].n_rows, max(p.n_entries for p in plans), aux, rd)
     resident = []
     for p in plans:
         dev = DeviceBatch(p.n_rows, p.n_entries)
@@ -189,7 +243,8 @@ def bench_main(args, w, cfg, rank, world):
     def device_steps(devs, first):
         for k, dev in enumerate(devs):
             _lib.check(lib.ocf_batch_regather(dev.handle, None))
-            m.step_on_device_batch(dev, B, first + k, train=True)
+            m.step_on_device_batch(dev, B // world if rows_mode else B, first + k, train=True,
+                                   row0=rank * (B // world) if rows_mode else 0, rows_total=B if rows_mode else 0)
 
     device_steps(resident[:W], 0)
     torch.cuda.synchronize()
@@ -214,7 +269,10 @@ def bench_main(args, w, cfg, rank, world):
         device_steps(resident[W:], W)
     torch.cuda.synchronize()
     dist.barrier()
-    ratings = sum(p.n_ratings for p in plans[W:])        # ratings of the global batches (all ranks together)
+    rt = torch.tensor([float(sum(p.n_ratings for p in plans[W:]))], device="cuda")
+    if rows_mode:
+        dist.all_reduce(rt)                              # every rank holds its own rows of the global batches
+    ratings = float(rt.item())                           # ratings of the global batches (all ranks together)
 
     # e2e through the public API on every rank: host RNG replay + H2D + phases/collectives + D2H
     for _ in range(W):
@@ -238,6 +296,10 @@ def bench_main(args, w, cfg, rank, world):
     dist.barrier()
     e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    if rows_mode:
+        er = torch.tensor([float(e_ratings)], device="cuda")
+        dist.all_reduce(er)
+        e_ratings = float(er.item())
     h2d_all = torch.tensor([float(h2d)], device="cuda")
     dist.all_reduce(h2d_all)
     clocks = sampler.stop() if sampler else None
@@ -245,7 +307,9 @@ def bench_main(args, w, cfg, rank, world):
         line = {"metric": "train ratings/sec", "value": ratings / (ms * 1e-3), "unit": "ratings/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(cfg, parallelism="column-sharded x%d, global batch %d rows (%d per GPU), 2 NCCL all-reduces of [rows, H] per step"
+                "config": dict(cfg, parallelism=("row-parallel x%d, global batch %d rows (%d per GPU), replicated weights, one NCCL all-reduce of all gradients per step"
+                                                 if rows_mode else
+                                                 "column-sharded x%d, global batch %d rows (%d per GPU), 2 NCCL all-reduces of [rows, H] per step")
                                % (world, B, args.batch_size), ratings_per_step=ratings / K,
                                l2="no flush: per-rank weights + optimizer state exceed the 126 MB L2"),
                 "clocks": clocks,

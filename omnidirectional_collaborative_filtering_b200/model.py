@@ -46,6 +46,7 @@ class OmniNet(object):
         self.metrics_names = list(METRIC_NAMES)
         self.stream = None
         self.comm = None                # dist.ShardComm when this model is a column shard
+        self.native = None              # (dist.NativeComm or None, _lib.PAR_*): collectives inside the C library
         self._step = 0
         self._compiled = False
 
@@ -85,6 +86,9 @@ class OmniNet(object):
             self._push_optimizer()
             for l, t in enumerate(o.trainable):
                 _lib.check(_lib.lib().ocf_model_set_trainable(self._handle, l, int(t)))
+            if self.native is not None:
+                comm, mode = self.native
+                _lib.check(_lib.lib().ocf_model_set_comm(self._handle, None if comm is None else comm.handle, int(mode)))
         elif rows > self._capacity[0] or entries > self._capacity[1]:
             _lib.check(_lib.lib().ocf_model_reserve(self._handle, rows, entries))
             self._capacity = (rows, entries)
@@ -148,8 +152,8 @@ class OmniNet(object):
         a = _lib.StepArgs()
         a.dropout_seed = self.owner.dropout_seed
         a.step = self._step & 0xFFFFFFFF
-        a.row0 = 0
-        a.rows_total = 0
+        a.row0 = int(getattr(batch, "row0", 0) or 0)
+        a.rows_total = int(getattr(batch, "rows_total", 0) or 0)
         a.phase = phase
         return a
 
@@ -160,7 +164,7 @@ class OmniNet(object):
         """One step through the C ABI; a column shard runs it as three phases with the two
         activation all-reduces between them (dist.py)."""
         fn = _lib.lib().ocf_train_step if train else _lib.lib().ocf_eval_step
-        if self.comm is None:
+        if self.comm is None or self.native is not None:
             args.phase = 0
             _lib.check(fn(h, dev_handle, C.byref(args), _lib.ptr(rec), self.stream))
             return
@@ -173,11 +177,12 @@ class OmniNet(object):
         args.phase = 3
         _lib.check(fn(h, dev_handle, C.byref(args), _lib.ptr(rec), self.stream))
 
-    def step_on_device_batch(self, dev, n_rows, step, train=True):
+    def step_on_device_batch(self, dev, n_rows, step, train=True, row0=0, rows_total=0):
         """A step on an already-filled DeviceBatch, no host sync (bench.py's device-timed loop)."""
         args = _lib.StepArgs()
         args.dropout_seed = self.owner.dropout_seed
         args.step = int(step) & 0xFFFFFFFF
+        args.row0, args.rows_total = int(row0), int(rows_total)
         self._run_step(self._handle, dev.handle, n_rows, args, None, train)
 
     def train_on_batch(self, batch, sync=True):
@@ -288,7 +293,7 @@ class OmniNet(object):
     def _shard_encode(self, h, dev, batch):
         """Column shards: encoder partial sums + their all-reduce before predict/score (this
         rank's output then holds its own columns)."""
-        if self.comm is None:
+        if self.comm is None or self.native is not None:
             return
         args = self._args(batch, phase=1, training=False)
         _lib.check(_lib.lib().ocf_eval_step(h, dev.handle, C.byref(args), None, self.stream))

@@ -162,14 +162,17 @@ class DeviceBatch(object):
         self.generation += 1
 
     def fill_split_rng(self, store: RatingStore, rows: np.ndarray, rng_handle, lo: float, hi: float, full_len,
-                       pass_through: bool, aux_value: float, stream=None):
+                       pass_through: bool, aux_value: float, stream=None, rng_slice=None):
         """Like fill_split, with the random split drawn on the device from the NumPy stream the
         `DeviceRng` holds (only the row ids cross PCIe)."""
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         fl = None if full_len is None else np.ascontiguousarray(full_len, dtype=np.int64)
+        sl = None
+        if rng_slice is not None:           # (rows of the drawing unit, first row, ratings before it, all draws)
+            sl = C.byref(_lib.RngSlice(int(rng_slice[0]), int(rng_slice[1]), int(rng_slice[2]), int(rng_slice[3])))
         _lib.check(_lib.lib().ocf_batch_fill_split_rng(self.handle, store.handle, _lib.ptr(rows), rows.size, rng_handle,
                                                        float(lo), float(hi), _lib.ptr(fl), int(bool(pass_through)),
-                                                       float(aux_value), stream))
+                                                       float(aux_value), sl, stream))
         self.generation += 1
 
     def read_flags(self, n_entries: int, stream=None) -> np.ndarray:

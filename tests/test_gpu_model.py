@@ -98,6 +98,33 @@ def test_train_steps_match_oracle(golden_datasets, case):
     rd.close()
 
 
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[3], CASES[6]], ids=["adagrad", "rmsprop-l2", "adam-mae", "widths"])
+def test_row_parallel_gradient_path_matches_oracle(golden_datasets, case):
+    """The data-parallel step of one rank (world 1: backward into the gradient arena, streaming
+    optimizer pass, no all-reduce) is the same math as the fused step."""
+    from omnidirectional_collaborative_filtering_b200 import _lib
+    aux, layers, width, act, l2, pdrop, opt, loss, pt = case
+    ds = golden_datasets["rev"]
+    om, ref = _pair(ds, aux, layers, width, act, l2, pdrop, opt, loss)
+    om.model.native = (None, _lib.PAR_ROWS)
+    rd = product_reader(ds, "fixed_split")
+    data = oracle_data(ds, "fixed_split")
+    np.random.seed(3)
+    gen = rd.data_gen(8, [0.2, 0.9], "train", True, aux, -1, pass_through_input_training=pt)
+    rgen = ref_batches.batch_stream(data, 8, [0.2, 0.9], "train", True, aux, -1, pass_through_input_training=pt,
+                                    rng=np.random.RandomState(3))
+    for step in range(5):
+        got = om.model.train_on_batch(next(gen))
+        feed, targets = next(rgen)
+        _close(got, ref.train_on_batch(feed, targets))
+    for g, w in zip(om.model.get_weights(), ref.get_weights()):
+        _close_weights(g, w, om.model.optimizer.lr)
+    vb = next(rd.data_gen(8, None, "valid", False, aux, -1))
+    vfeed, vt = next(ref_batches.batch_stream(data, 8, None, "valid", False, aux, -1, rng=np.random.RandomState(4)))
+    _close(om.model.test_on_batch(vb), ref.test_on_batch(vfeed, vt))
+    rd.close()
+
+
 def test_frozen_layers_and_transfer(golden_datasets):
     ds = golden_datasets["fwd"]
     N = ds["n_cols"]
