@@ -269,8 +269,9 @@ int ocf_model_buffer(ocf_model* model, int which, void** device_ptr, int64_t* co
  * for collectives over replicated parameters; count in floats. */
 int ocf_model_weight_device(ocf_model* model, int index, void** device_ptr, int64_t* count);
 /* Per-kernel timing with CUDA events recorded on the launching stream around the named kernels
- * (tag 0 = K1 gather, 1 = K2 encoder, 2 = K3 decoder/loss, 3 = K4 column update, 4 = scoring
- * GEMM). Off by default; ocf_profile_read synchronises the device and sums the elapsed times
+ * (tag 0 = K1 gather, 1 = K2 encoder, 2 = K3 decoder/loss, 3 = K4a column scan, 4 = scoring GEMM,
+ * 5 = K4b row update, 6 = first collective of a parallel step (z all-reduce / streaming optimizer
+ * pass), 7 = second collective (row statistics + dL/dh all-reduce / gradient all-reduce)). Off by default; ocf_profile_read synchronises the device and sums the elapsed times
  * of the launches recorded since the last reset. */
 int ocf_profile_enable(int on);
 int ocf_profile_reset(void);

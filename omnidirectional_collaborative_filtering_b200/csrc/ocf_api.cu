@@ -1544,10 +1544,14 @@ extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* a
     const int B = b->dev.B;
     OCF_TRY(fork_scan(m, b, st));
     OCF_TRY(phase_encode(m, b, st));
+    g_prof.begin(6, st);
     OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
+    g_prof.end(6, st);
     OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
+    g_prof.begin(7, st);
     OCF_NCCL(nccl_api().allReduce(m->rowstats, m->rowstats, (size_t)m->cfg.max_rows * ROWSTAT_W + (size_t)B * m->hp[m->L - 1],
                                   ncclFloat, ncclSum, m->comm->comm, st));
+    g_prof.end(7, st);
     OCF_TRY(phase_update(m, b, args, st));
     return finish_step(m, host_metrics, st);
   }

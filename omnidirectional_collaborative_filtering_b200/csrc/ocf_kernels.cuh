@@ -101,25 +101,43 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
   int cur = 0;
   __syncthreads();
   long long w = 0;
-  while (w < n_words) {
-    if (pos >= 624) {
-      const uint32_t* o = mt[cur];
-      uint32_t* n = mt[cur ^ 1];
-      if (tid < 227) n[tid] = mt_twist(o[tid], o[tid + 1], o[tid + 397]);
-      __syncthreads();
-      if (tid < 227) n[227 + tid] = mt_twist(o[227 + tid], o[228 + tid], n[tid]);
-      __syncthreads();
-      if (tid < 169) n[454 + tid] = mt_twist(o[454 + tid], o[455 + tid], n[227 + tid]);
-      else if (tid == 169) n[623] = mt_twist(o[623], n[0], n[396]);
-      __syncthreads();
-      cur ^= 1;
-      pos = 0;
-    }
-    const int take = (int)min((long long)(624 - pos), n_words - w);
+  // what is left of the current array
+  if (pos < 624) {
+    const int take = (int)min((long long)(624 - pos), n_words);
     if (out != nullptr)
-      for (int i = tid; i < take; i += blockDim.x) out[w + i] = mt_temper(mt[cur][pos + i]);
-    w += take;
+      for (int i = tid; i < take; i += blockDim.x) out[i] = mt_temper(mt[0][pos + i]);
+    w = take;
     pos += take;
+  }
+  // whole regenerations: the chain of dependent sweeps is the critical path (one barrier each), so
+  // every thread tempers and stores the word it has just produced instead of a separate output pass
+  while (w < n_words) {
+    const uint32_t* o = mt[cur];
+    uint32_t* n = mt[cur ^ 1];
+    const long long left = n_words - w;              // words of this array that belong to the batch
+    uint32_t* dst = out != nullptr ? out + w : nullptr;
+    if (tid < 227) {
+      const uint32_t v = mt_twist(o[tid], o[tid + 1], o[tid + 397]);
+      n[tid] = v;
+      if (dst != nullptr && tid < left) dst[tid] = mt_temper(v);
+    }
+    __syncthreads();
+    if (tid < 227) {
+      const uint32_t v = mt_twist(o[227 + tid], o[228 + tid], n[tid]);
+      n[227 + tid] = v;
+      if (dst != nullptr && 227 + tid < left) dst[227 + tid] = mt_temper(v);
+    }
+    __syncthreads();
+    if (tid < 170) {
+      const uint32_t v = tid < 169 ? mt_twist(o[454 + tid], o[455 + tid], n[227 + tid]) : mt_twist(o[623], n[0], n[396]);
+      n[454 + tid] = v;
+      if (dst != nullptr && 454 + tid < left) dst[454 + tid] = mt_temper(v);
+    }
+    __syncthreads();
+    cur ^= 1;
+    const int take = (int)min(624LL, left);
+    w += take;
+    pos = take;
   }
   __syncthreads();
   for (int i = tid; i < 624; i += blockDim.x) state[i] = mt[cur][i];

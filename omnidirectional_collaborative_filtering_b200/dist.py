@@ -269,6 +269,21 @@ def bench_main(args, w, cfg, rank, world):
         device_steps(resident[W:], W)
     torch.cuda.synchronize()
     dist.barrier()
+    # per-kernel / per-collective CUDA-event times of one more pass (this rank's view)
+    lib.ocf_profile_reset()
+    lib.ocf_profile_enable(1)
+    device_steps(resident[W:], W)
+    torch.cuda.synchronize()
+    lib.ocf_profile_enable(0)
+    dist.barrier()
+    names = {0: "k_gather_split (K1)", 1: "k_enc_fwd (K2)", 2: "k_dec_fwd (K3)", 3: "k_col_scan (K4a)", 5: "k_row_update (K4b)",
+             6: "streaming optimizer pass" if rows_mode else "ncclAllReduce z [rows, H]",
+             7: "ncclAllReduce gradients" if rows_mode else "ncclAllReduce row stats + dL/dh [rows, 4 + H]"}
+    kernels = {}
+    for tag, name in names.items():
+        tot, cnt = C.c_double(), C.c_int64()
+        _lib.check(lib.ocf_profile_read(tag, C.byref(tot), C.byref(cnt)))
+        kernels[name] = {"ms": tot.value / max(cnt.value, 1)}
     rt = torch.tensor([float(sum(p.n_ratings for p in plans[W:]))], device="cuda")
     if rows_mode:
         dist.all_reduce(rt)                              # every rank holds its own rows of the global batches
@@ -316,7 +331,7 @@ def bench_main(args, w, cfg, rank, world):
                 "e2e": {"value": e_ratings / float(e2e.item()), "unit": "ratings/s",
                         "h2d_bytes_per_step": float(h2d_all.item()) / K, "d2h_bytes_per_step": 4 * _lib.N_METRICS * world,
                         "ms_per_step": 1e3 * float(e2e.item()) / K},
-                "gpu_launches": int(launches)}
+                "gpu_launches": int(launches), "kernels_rank0": kernels}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
