@@ -131,10 +131,11 @@ def scoring_run(lib, m, rd, w, aux, rows, reps, warm):
     flops = 2.0 * rows * hp * N                        # the padded contraction the tensor cores run
     peak, src = tensor_peak_tf32()
     # end to end: host batch -> scores in a host array, every call
+    m.score(batches[0], reuse_output=True)            # allocates the page-locked destination (untimed)
     t0 = time.perf_counter()
     n_e2e = max(2, min(reps, 5))
     for k in range(n_e2e):
-        res = m.score(batches[k % len(batches)])
+        res = m.score(batches[k % len(batches)], reuse_output=True)     # page-locked destination
     e2e_s = (time.perf_counter() - t0) / n_e2e
     return {"rows_per_call": rows, "n_cols": int(N), "value": rows / (ms * 1e-3), "unit": "rows/s", "ms_per_call": ms,
             "gpu_launches": int(launches),

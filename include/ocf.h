@@ -57,6 +57,10 @@ const char* ocf_last_error(void);
 int ocf_version(void);
 /* Number of CUDA devices visible (0 without a GPU; never fails). */
 int ocf_device_count(void);
+/* Page-locked host memory for the [rows, n_cols] outputs of ocf_predict / ocf_score (a pageable
+ * destination makes the device->host copy several times slower). */
+int ocf_host_alloc(int64_t bytes, void** out);
+int ocf_host_free(void* ptr);
 
 /* ---- rating store ------------------------------------------------------------------------
  * Replaces the per-row (item, rating) lists the reader keeps after loading

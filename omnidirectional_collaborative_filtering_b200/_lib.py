@@ -53,6 +53,8 @@ _SIGNATURES = {
     "ocf_version": (C.c_int, []),
     "ocf_device_count": (C.c_int, []),
     "ocf_kernel_launches": (C.c_int64, []),
+    "ocf_host_alloc": (C.c_int, [C.c_int64, C.POINTER(_P)]),
+    "ocf_host_free": (C.c_int, [_P]),
     "ocf_store_create": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.c_int, C.POINTER(_P)]),
     "ocf_store_destroy": (C.c_int, [_P]),
     "ocf_store_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
@@ -140,6 +142,29 @@ def check(status):
 def require_gpu():
     if lib().ocf_device_count() < 1:
         raise OcfError("no CUDA device: the hot path is CUDA-only (sm_100a), there is no CPU fallback")
+
+
+class PinnedArray(object):
+    """A float32 NumPy array over page-locked host memory (freed with the object)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(x) for x in shape)
+        n = 1
+        for x in self.shape:
+            n *= x
+        self._ptr = C.c_void_p()
+        check(lib().ocf_host_alloc(4 * n, C.byref(self._ptr)))
+        import numpy as np
+        buf = (C.c_float * max(n, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float32, count=n).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self._ptr is not None and self._ptr.value:
+                lib().ocf_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
 
 
 def ptr(array):

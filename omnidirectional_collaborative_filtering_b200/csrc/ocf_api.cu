@@ -234,6 +234,22 @@ extern "C" int ocf_device_count(void) {
 }
 extern "C" int64_t ocf_kernel_launches(void) { return (int64_t)g_launches.load(); }
 
+// Page-locked host memory for buffers that cross PCIe every call (score / predict outputs):
+// copies to pageable memory are staged by the driver at a fraction of the link's bandwidth.
+extern "C" int ocf_host_alloc(int64_t bytes, void** out) {
+  OCF_REQUIRE(out != nullptr && bytes >= 0, "ocf_host_alloc: bad argument");
+  *out = nullptr;
+  if (cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 16)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(OCF_ERR_NOMEM, "ocf_host_alloc: cudaMallocHost(" + std::to_string(bytes) + ") failed");
+  }
+  return OCF_OK;
+}
+extern "C" int ocf_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+  return OCF_OK;
+}
+
 
 // ---- optional per-kernel timing with CUDA events on the launching stream -------------------
 namespace ocf {

@@ -47,6 +47,7 @@ class OmniNet(object):
         self.stream = None
         self.comm = None                # dist.ShardComm when this model is a column shard
         self.native = None              # (dist.NativeComm or None, _lib.PAR_*): collectives inside the C library
+        self._pinned = {}               # page-locked output buffers of predict / score, by shape
         self._step = 0
         self._compiled = False
 
@@ -272,21 +273,35 @@ class OmniNet(object):
         recs = self._run(generator, steps, train=False, workers=workers)
         return [float(v) for v in recs[:, :6].astype(np.float64).mean(axis=0)]
 
-    def predict(self, batch, batch_size=None, verbose=0):
+    def _out_buffer(self, rows, reuse):
+        """[rows, local_cols] float32 destination of predict / score. `reuse`: a page-locked buffer
+        owned by the model (the device->host copy then runs at PCIe speed; the returned array is
+        overwritten by the next call of the same shape), else a fresh pageable array."""
+        shape = (int(rows), int(self.owner.local_cols))
+        if not reuse:
+            return np.empty(shape, dtype=np.float32)
+        held = self._pinned.get(shape)
+        if held is None:
+            if len(self._pinned) >= 2:
+                self._pinned.clear()
+            held = self._pinned[shape] = _lib.PinnedArray(shape)
+        return held.array
+
+    def predict(self, batch, batch_size=None, verbose=0, reuse_output=False):
         """`best_m.predict(input_list)`, train.py:239: output_mask * full_predictions, [B, N] float32."""
         h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
         self._shard_encode(h, dev, batch)
-        out = np.empty((batch.n_rows, self.owner.local_cols), dtype=np.float32)
+        out = self._out_buffer(batch.n_rows, reuse_output)
         _lib.check(_lib.lib().ocf_predict(h, dev.handle, _lib.ptr(out), self.stream))
         return out
 
-    def score(self, batch):
+    def score(self, batch, reuse_output=False):
         """Full-catalogue scores `full_predictions` (model.py:82-84), [B, N] float32."""
         h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
         self._shard_encode(h, dev, batch)
-        out = np.empty((batch.n_rows, self.owner.local_cols), dtype=np.float32)
+        out = self._out_buffer(batch.n_rows, reuse_output)
         _lib.check(_lib.lib().ocf_score(h, dev.handle, _lib.ptr(out), 0, self.stream))
         return out
 

@@ -83,4 +83,6 @@ def test_score_rows_are_independent():
     a = om.model.score(big)
     b = om.model.score(small)
     assert np.array_equal(a[:8], b)
+    c = om.model.score(big, reuse_output=True)          # page-locked destination owned by the model
+    assert np.array_equal(a, c)
     rd.close()
