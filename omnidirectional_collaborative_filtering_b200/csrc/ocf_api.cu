@@ -728,7 +728,7 @@ extern "C" int ocf_rng_skip(ocf_rng* r, int64_t n_draws) {
   OCF_REQUIRE(r && n_draws >= 0, "ocf_rng_skip: bad argument");
   if (n_draws == 0) return OCF_OK;
   OCF_CUDA(cudaSetDevice(r->device));
-  k_mt_words<<<1, 256, 0, r->stream>>>(r->d_state, 2 * (long long)n_draws, nullptr, 0, 0.0, 0.0, nullptr);
+  k_mt_words<<<1, MT_THREADS, 0, r->stream>>>(r->d_state, 2 * (long long)n_draws, nullptr, 0, 0.0, 0.0, nullptr);
   OCF_LAUNCHED();
   return OCF_OK;
 }
@@ -808,7 +808,7 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
   // the previous batch staged in this object may still be reading its words (no-op before the first gather)
   OCF_CUDA(cudaStreamWaitEvent(rng->stream, b->gathered, 0));
   // the stream's next `draws` doubles, generated beside whatever `stream` is running
-  k_mt_words<<<1, 256, 0, rng->stream>>>(rng->d_state, 2 * (long long)draws, b->d_words, n_draw_rows, lo, hi - lo, b->d_cdf0);
+  k_mt_words<<<1, MT_THREADS, 0, rng->stream>>>(rng->d_state, 2 * (long long)draws, b->d_words, n_draw_rows, lo, hi - lo, b->d_cdf0);
   OCF_LAUNCHED();
   OCF_CUDA(cudaEventRecord(b->words_ready, rng->stream));
   OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split_rng"));
@@ -1257,20 +1257,32 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   return OCF_OK;
 }
 
-static int launch_metrics(ocf_model* m, int B, const ocf_step_args* args, int n_reg, cudaStream_t st,
-                          const float* stats = nullptr) {
+static MetricArgs metric_args(ocf_model* m, int B, const ocf_step_args* args, int n_reg, const float* stats = nullptr) {
   const int rows_total = (args && args->rows_total > 0) ? args->rows_total : B;
+  MetricArgs a{};
+  a.rowstats = stats ? stats : m->rowstats; a.rows = B; a.rows_total = (float)rows_total;
+  a.n_cols_total = (float)m->cfg.n_cols_total; a.rating_range = m->cfg.rating_range; a.loss_kind = m->cfg.loss;
+  a.regparts = m->regparts; a.n_reg = n_reg; a.l2 = m->cfg.l2 >= 0.f ? m->cfg.l2 : 0.f;
+  a.rec = m->d_log + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
+  return a;
+}
+
+// Every step's record goes back to pinned host memory right behind its kernels; readers wait on
+// the step's event instead of the whole stream.
+static int publish_metrics(ocf_model* m, cudaStream_t st) {
   float* rec = m->d_log + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
-  k_metrics<<<1, 32, 0, st>>>(stats ? stats : m->rowstats, B, (float)rows_total, (float)m->cfg.n_cols_total, m->cfg.rating_range,
-                              m->cfg.loss, m->regparts, n_reg, m->cfg.l2 >= 0.f ? m->cfg.l2 : 0.f, rec);
-  OCF_LAUNCHED();
-  // every step's record goes back to pinned host memory right behind its kernels; readers wait
-  // on the step's event instead of the whole stream
   float* hrec = m->h_rec + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
   OCF_CUDA(cudaMemcpyAsync(hrec, rec, sizeof(float) * LOG_W, cudaMemcpyDeviceToHost, st));
   OCF_CUDA(cudaEventRecord(m->step_ev[m->steps_logged % 64], st));
   m->steps_logged += 1;
   return OCF_OK;
+}
+
+static int launch_metrics(ocf_model* m, int B, const ocf_step_args* args, int n_reg, cudaStream_t st,
+                          const float* stats = nullptr) {
+  k_metrics<<<1, 32, 0, st>>>(metric_args(m, B, args, n_reg, stats));
+  OCF_LAUNCHED();
+  return publish_metrics(m, st);
 }
 
 static int launch_reg(ocf_model* m, cudaStream_t st) {
@@ -1387,9 +1399,13 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   {
     const int l = L - 1;
     Layer& ly = m->layers[l];
-    k_dz_bias<<<m->hp[l] / 32, 256, 0, st>>>(m->dh_top, m->act[l], drop ? m->dscale[l] : nullptr, B, m->hp[l],
+    // the fused step's metric record rides along as one extra CTA (a row-parallel step needs the
+    // other ranks' row statistics first and computes it after the gather)
+    MetricArgs met{};
+    if (!grad_mode) met = metric_args(m, B, args, n_reg);
+    k_dz_bias<<<m->hp[l] / 32 + (grad_mode ? 0 : 1), 1024, 0, st>>>(m->dh_top, m->act[l], drop ? m->dscale[l] : nullptr, B, m->hp[l],
                                                      m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt, ly.trainable ? 1 : 0,
-                                                     grad_mode ? m->gb[l] : nullptr);
+                                                     grad_mode ? m->gb[l] : nullptr, met);
     OCF_LAUNCHED();
   }
   for (int l = L - 1; l >= 1; --l) {
@@ -1399,9 +1415,9 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     ep.aux1 = drop ? m->dscale[l - 1] : nullptr; ep.act = m->cfg.activation;
     OCF_TRY(launch_gemm(false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
     Layer& lo = m->layers[l - 1];
-    k_dz_bias<<<m->hp[l - 1] / 32, 256, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
+    k_dz_bias<<<m->hp[l - 1] / 32, 1024, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
                                                          m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0,
-                                                         grad_mode ? m->gb[l - 1] : nullptr);
+                                                         grad_mode ? m->gb[l - 1] : nullptr, MetricArgs{});
     OCF_LAUNCHED();
     if (ly.trainable) {
       // dW_l = h_{l-1}^T . dz_l, fused with the update of W_l
@@ -1432,7 +1448,7 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   }
   if (grad_mode) return OCF_OK;
   m->iterations += 1;
-  return launch_metrics(m, B, args, n_reg, st);
+  return publish_metrics(m, st);
 }
 
 extern "C" int ocf_model_wait_metrics(ocf_model* m, int64_t step, float* host) {

@@ -71,12 +71,20 @@ k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
 }
 
 // ============================================================================================
-// NumPy's MT19937 stream on the device. One CTA owns the 624-word state: a regeneration is three
-// dependent sweeps of <= 227 independent words (word i needs i+1 and i+397 of the old array, or
-// i-227 of the new one), double-buffered in shared memory; the tempered words of the batch's
-// draws are written out in stream order. The first `n_rows` draws are the batch's
-// np.random.uniform(lo, hi, size=B) (data_reader.py:120): their cdf (what np.random.choice builds
-// from p=[1-s, s]) is computed here in IEEE double, operation by operation like the host code.
+// NumPy's MT19937 stream on the device. One CTA owns the 624-word state. The recurrence
+//   x[n] = x[n-227] ^ A(x[n-624], x[n-623])            (A = the "twist" of two neighbouring words)
+// only reaches 227 words back through a plain XOR, so inside one regeneration the chain can be
+// unrolled until it lands in the previous array: every new word is the XOR of at most three
+// twists of OLD words and one old word,
+//   i <  227 : new[i] = A(i) ^ old[i+397]
+//   i <  454 : new[i] = A(i) ^ A(i-227) ^ old[i+170]
+//   i <  623 : new[i] = A(i) ^ A(i-227) ^ A(i-454) ^ old[i-57]
+//   i == 623 : new[623] = A(old[623], new[0]) ^ new[396]
+// all 624 of them independent: one barrier per regeneration (double-buffered in shared memory)
+// instead of three dependent sweeps, and every thread tempers and stores the words it produced.
+// The first `n_rows` draws are the batch's np.random.uniform(lo, hi, size=B) (data_reader.py:120):
+// their cdf (what np.random.choice builds from p=[1-s, s]) is computed here in IEEE double,
+// operation by operation like the host code.
 // state[0..623] = key, state[624] = pos (RandomState.get_state()[1:3]).
 // ============================================================================================
 __device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
@@ -91,7 +99,14 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ uint32_t mt_a(uint32_t cur, uint32_t nxt) {
+  const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+  return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+constexpr int MT_THREADS = 320;            // 2 words per thread and regeneration
+
+__global__ void __launch_bounds__(MT_THREADS)
 k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict__ out, int n_rows,
            double lo, double range, double* __restrict__ cdf0) {
   __shared__ uint32_t mt[2][624];
@@ -109,29 +124,27 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
     w = take;
     pos += take;
   }
-  // whole regenerations: the chain of dependent sweeps is the critical path (one barrier each), so
-  // every thread tempers and stores the word it has just produced instead of a separate output pass
   while (w < n_words) {
     const uint32_t* o = mt[cur];
     uint32_t* n = mt[cur ^ 1];
     const long long left = n_words - w;              // words of this array that belong to the batch
     uint32_t* dst = out != nullptr ? out + w : nullptr;
-    if (tid < 227) {
-      const uint32_t v = mt_twist(o[tid], o[tid + 1], o[tid + 397]);
-      n[tid] = v;
-      if (dst != nullptr && tid < left) dst[tid] = mt_temper(v);
-    }
-    __syncthreads();
-    if (tid < 227) {
-      const uint32_t v = mt_twist(o[227 + tid], o[228 + tid], n[tid]);
-      n[227 + tid] = v;
-      if (dst != nullptr && 227 + tid < left) dst[227 + tid] = mt_temper(v);
-    }
-    __syncthreads();
-    if (tid < 170) {
-      const uint32_t v = tid < 169 ? mt_twist(o[454 + tid], o[455 + tid], n[227 + tid]) : mt_twist(o[623], n[0], n[396]);
-      n[454 + tid] = v;
-      if (dst != nullptr && 454 + tid < left) dst[454 + tid] = mt_temper(v);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * MT_THREADS;
+      if (i < 624) {
+        uint32_t v;
+        if (i < 227) v = mt_a(o[i], o[i + 1]) ^ o[i + 397];
+        else if (i < 454) v = mt_a(o[i], o[i + 1]) ^ mt_a(o[i - 227], o[i - 226]) ^ o[i + 170];
+        else if (i < 623) v = mt_a(o[i], o[i + 1]) ^ mt_a(o[i - 227], o[i - 226]) ^ mt_a(o[i - 454], o[i - 453]) ^ o[i - 57];
+        else {
+          const uint32_t new0 = mt_a(o[0], o[1]) ^ o[397];
+          const uint32_t new396 = mt_a(o[396], o[397]) ^ mt_a(o[169], o[170]) ^ o[566];
+          v = mt_a(o[623], new0) ^ new396;
+        }
+        n[i] = v;
+        if (dst != nullptr && i < left) dst[i] = mt_temper(v);
+      }
     }
     __syncthreads();
     cur ^= 1;
@@ -274,11 +287,23 @@ k_rowsum(const float4* __restrict__ P, const int32_t* __restrict__ item_ptr, int
   const int i0 = item_ptr[b], i1 = item_ptr[b + 1];
   if (hp4 > 0) {
     const int q = threadIdx.x / hp4, u = threadIdx.x - q * hp4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int it = i0 + q; it < i1; it += 4) {
+    // a heavy row has hundreds of items: four loads in flight per thread, summed in a fixed order
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s, s2 = s, s3 = s;
+    int it = i0 + q;
+    for (; it + 12 < i1; it += 16) {
+      const float4 p0 = P[(size_t)it * hp4 + u], p1 = P[(size_t)(it + 4) * hp4 + u];
+      const float4 p2 = P[(size_t)(it + 8) * hp4 + u], p3 = P[(size_t)(it + 12) * hp4 + u];
+      s.x += p0.x; s.y += p0.y; s.z += p0.z; s.w += p0.w;
+      s1.x += p1.x; s1.y += p1.y; s1.z += p1.z; s1.w += p1.w;
+      s2.x += p2.x; s2.y += p2.y; s2.z += p2.z; s2.w += p2.w;
+      s3.x += p3.x; s3.y += p3.y; s3.z += p3.z; s3.w += p3.w;
+    }
+    for (; it < i1; it += 4) {
       const float4 p = P[(size_t)it * hp4 + u];
       s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
     }
+    s.x = (s.x + s1.x) + (s2.x + s3.x); s.y = (s.y + s1.y) + (s2.y + s3.y);
+    s.z = (s.z + s1.z) + (s2.z + s3.z); s.w = (s.w + s1.w) + (s2.w + s3.w);
     rs_smem[q * hp4 + u] = s;
     __syncthreads();
     if (q == 0) {
@@ -421,19 +446,32 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
 }
 
 // dz = dh * dropout scale * act'(a) for one hidden layer, the bias gradient (column sum over the
-// batch) and the bias update. One CTA per 32 hidden units; its 8 warps deal the batch rows
-// round-robin and their partial column sums are added in warp order.
+// batch) and the bias update. One CTA per 32 hidden units; its 32 warps deal the batch rows
+// round-robin and their partial column sums are added in warp order. The launch may carry one
+// CTA more than there are unit groups: it writes the step's metric record (saves a launch on the
+// critical path of a training step).
 // dh_is_dz: the input already is dz (produced by the EPI_DZ GEMM epilogue).
-__global__ void __launch_bounds__(256)
+struct MetricArgs {            // the step's metric record, written by one extra CTA of k_dz_bias (null rec: none)
+  const float* rowstats; int rows; float rows_total; float n_cols_total; float rating_range; int loss_kind;
+  const float* regparts; int n_reg; float l2; float* rec;
+};
+__device__ void metrics_record(const MetricArgs& a, int lane);
+
+__global__ void __launch_bounds__(1024)
 k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float* __restrict__ dscale,
           int B, int HP, int act, int dh_is_dz, float* __restrict__ dz, float* __restrict__ bias,
-          float* __restrict__ s1, float* __restrict__ s2, OptDev o, int trainable, float* __restrict__ gbias) {
-  __shared__ float part[8][32];
+          float* __restrict__ s1, float* __restrict__ s2, OptDev o, int trainable, float* __restrict__ gbias,
+          MetricArgs met) {
+  __shared__ float part[32][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x * 32 >= HP) {           // the extra CTA: metrics of the step (train.py:102-121)
+    if (warp == 0 && met.rec != nullptr) metrics_record(met, lane);
+    return;
+  }
   const int u = blockIdx.x * 32 + lane;
   float g = 0.f;
   if (u < HP) {
-    for (int b = warp; b < B; b += 8) {
+    for (int b = warp; b < B; b += 32) {
       const size_t k = (size_t)b * HP + u;
       float d = dh[k];
       if (!dh_is_dz) {
@@ -449,7 +487,7 @@ k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float
   if (warp == 0 && u < HP && trainable) {
     g = part[0][lane];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) g += part[w][lane];
+    for (int w = 1; w < 32; ++w) g += part[w][lane];
     if (gbias != nullptr) { gbias[u] = g; return; }   // row-parallel mode: the gradient is reduced over ranks first
     o.l2x2 = 0.f;                     // Keras regularises kernels only (model.py:66,82)
     float w = bias[u], t1 = s1 ? s1[u] : 0.f, t2 = s2 ? s2[u] : 0.f;
@@ -884,32 +922,31 @@ __global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ w, size
 
 // Per-step metric record from the per-row statistics (train.py:102-121 + the Keras loss).
 // One warp, fixed summation order.
-__global__ void __launch_bounds__(32)
-k_metrics(const float* __restrict__ rowstats, int B, float rows_total, float n_cols_total,
-          float rating_range, int loss_kind, const float* __restrict__ regparts, int n_reg, float l2,
-          float* __restrict__ rec) {
-  const int lane = threadIdx.x;
+__device__ void metrics_record(const MetricArgs& a, int lane) {
   float sse = 0.f, sae = 0.f, cnt = 0.f, srt = 0.f, reg = 0.f;
-  for (int b = lane; b < B; b += 32) {
-    const float s = rowstats[b * ROWSTAT_W];
-    sse += s; sae += rowstats[b * ROWSTAT_W + 1]; cnt += rowstats[b * ROWSTAT_W + 2];
+  for (int b = lane; b < a.rows; b += 32) {
+    const float s = a.rowstats[b * ROWSTAT_W];
+    sse += s; sae += a.rowstats[b * ROWSTAT_W + 1]; cnt += a.rowstats[b * ROWSTAT_W + 2];
     srt += sqrtf(s);
   }
-  for (int k = lane; k < n_reg; k += 32) reg += regparts[k];
+  for (int k = lane; k < a.n_reg; k += 32) reg += a.regparts[k];
   sse = warp_sum(sse); sae = warp_sum(sae); cnt = warp_sum(cnt); srt = warp_sum(srt); reg = warp_sum(reg);
   if (lane == 0) {
-    const float bn = rows_total * n_cols_total;
+    float* rec = a.rec;
+    const float bn = a.rows_total * a.n_cols_total;
     const float mse = sse / bn, mae = sae / bn;
     const float acc_mae = sae / cnt;
-    rec[0] = (loss_kind == OCF_LOSS_MSE ? mse : mae) + (n_reg > 0 ? l2 * reg : 0.f);
+    rec[0] = (a.loss_kind == OCF_LOSS_MSE ? mse : mae) + (a.n_reg > 0 ? a.l2 * reg : 0.f);
     rec[1] = mae;
     rec[2] = acc_mae;
-    rec[3] = acc_mae / rating_range;
-    rec[4] = sqrtf(rows_total / cnt) * srt / rows_total;
+    rec[3] = acc_mae / a.rating_range;
+    rec[4] = sqrtf(a.rows_total / cnt) * srt / a.rows_total;
     rec[5] = sse / cnt;
     rec[6] = sse;
     rec[7] = cnt;
   }
 }
+
+__global__ void __launch_bounds__(32) k_metrics(MetricArgs a) { metrics_record(a, threadIdx.x); }
 
 }  // namespace ocf
