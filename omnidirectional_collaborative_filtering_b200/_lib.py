@@ -77,6 +77,7 @@ _SIGNATURES = {
     "ocf_comm_unique_id": (C.c_int, [_P]),
     "ocf_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "ocf_comm_destroy": (C.c_int, [_P]),
+    "ocf_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "ocf_model_set_comm": (C.c_int, [_P, _P, C.c_int]),
     "ocf_batch_read_flags": (C.c_int, [_P, _P, C.c_int64, _P]),
     "ocf_profile_enable": (C.c_int, [C.c_int]),

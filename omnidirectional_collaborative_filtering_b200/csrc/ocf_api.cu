@@ -11,6 +11,7 @@
 
 #include "ocf_kernels.cuh"
 #include "ocf_score_tc.cuh"
+#include "ocf_peer.cuh"
 
 namespace ocf {
 
@@ -95,6 +96,24 @@ using namespace ocf;
 struct ocf_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1, device = 0;
+  // one-shot all-reduce over peer memory (ocf_peer.cuh): [flags | slot 0 | slot 1] on every rank
+  bool p2p = false;
+  uint8_t* region = nullptr;                       // this rank's exchange region
+  uint8_t* peer_region[peer::MAX_PEERS] = {nullptr};   // every rank's region as mapped here (own: region)
+  size_t slot_floats = 0;
+  uint32_t epoch = 0;                              // exchanges done; the same on every rank
+  float* slot(int rank_, uint32_t e) const {
+    return reinterpret_cast<float*>(peer_region[rank_] + peer::FLAG_BYTES) + (size_t)(e & 1u) * slot_floats;
+  }
+  peer::PeerDev dev(uint32_t e) const {
+    peer::PeerDev d{};
+    for (int p = 0; p < world; ++p) {
+      d.slot[p] = reinterpret_cast<const float4*>(slot(p, e));
+      d.flags[p] = reinterpret_cast<uint32_t*>(peer_region[p]);
+    }
+    d.rank = rank; d.world = world; d.epoch = e;
+    return d;
+  }
 };
 
 // ============================================================================================
@@ -1174,7 +1193,7 @@ static int check_step(const ocf_model* m, const ocf_batch* b, bool train) {
 }
 
 // phase 1: encoder partial sums -> zsum[0]
-static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
+static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st, float* z_out = nullptr) {
   const BatchDev& bt = b->dev;
   const int hp0 = m->hp[0];
   if (bt.n_items > 0) {
@@ -1185,7 +1204,7 @@ static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
     g_prof.end(1, st);
   }
   k_rowsum<<<bt.B, hp0, (size_t)hp0 * 16, st>>>(reinterpret_cast<const float4*>(m->P1), bt.item_ptr, hp0 / 4,
-                                                reinterpret_cast<float4*>(m->zsum[0]), nullptr, nullptr);
+                                                reinterpret_cast<float4*>(z_out ? z_out : m->zsum[0]), nullptr, nullptr);
   OCF_LAUNCHED();
   return OCF_OK;
 }
@@ -1201,29 +1220,43 @@ static int launch_gemm(bool ta, bool tb, const float* A, int lda, const float* B
   return OCF_OK;
 }
 
+static ActArgs act_args(ocf_model* m, int l, int B, bool training, const ocf_step_args* args) {
+  const int hp = m->hp[l];
+  const bool drop = training && m->cfg.dropout_p > 0.f;
+  const uint64_t seed = args ? args->dropout_seed : 0;
+  ActArgs g{};
+  g.bias = reinterpret_cast<const float4*>(m->layers[l].b); g.B = B; g.H = m->cfg.widths[l]; g.hp4 = hp / 4;
+  g.act = m->cfg.activation;
+  g.a_out = reinterpret_cast<float4*>(m->act[l]);
+  g.h_out = reinterpret_cast<float4*>(drop ? m->h[l] : m->act[l]);
+  g.dscale = drop ? reinterpret_cast<float4*>(m->dscale[l]) : nullptr;
+  g.p_drop = m->cfg.dropout_p;
+  g.key = make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  g.step = args ? args->step : 0u; g.layer = (uint32_t)l; g.row0 = args ? args->row0 : 0;
+  return g;
+}
+
 // bias + activation (+ dropout) of layer l from zsum[l]
 static int launch_act(ocf_model* m, int l, int B, bool training, const ocf_step_args* args, cudaStream_t st) {
   const int hp = m->hp[l];
   const bool drop = training && m->cfg.dropout_p > 0.f;
   const int total = B * (hp / 4);
   const uint64_t seed = args ? args->dropout_seed : 0;
-  k_bias_act<<<(total + 255) / 256, 256, 0, st>>>(
-      reinterpret_cast<const float4*>(m->zsum[l]), reinterpret_cast<const float4*>(m->layers[l].b), B,
-      m->cfg.widths[l], hp / 4, m->cfg.activation, reinterpret_cast<float4*>(m->act[l]),
-      reinterpret_cast<float4*>(drop ? m->h[l] : m->act[l]), drop ? reinterpret_cast<float4*>(m->dscale[l]) : nullptr,
-      m->cfg.dropout_p, make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)), args ? args->step : 0u,
-      (uint32_t)l, args ? args->row0 : 0);
+  k_bias_act<<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(m->zsum[l]), act_args(m, l, B, training, args));
   OCF_LAUNCHED();
   return OCF_OK;
 }
 
 // phase 2: activations, hidden layers, decoder at the target entries, loss partials -> dh_top, rowstats
+// act0_done: the first layer's activations are already in place (fused into the peer exchange).
+// xslot: write the row statistics [B, 4] and dL/dh [B, hp] into this exchange slot instead of the
+// model's buffers (a peer all-reduce follows).
 static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args,
-                        float* dense_out, cudaStream_t st) {
+                        float* dense_out, cudaStream_t st, bool act0_done = false, float* xslot = nullptr) {
   const BatchDev& bt = b->dev;
   const int L = m->L, B = bt.B;
   const bool drop = training && m->cfg.dropout_p > 0.f;
-  OCF_TRY(launch_act(m, 0, B, training, args, st));
+  if (!act0_done) OCF_TRY(launch_act(m, 0, B, training, args, st));
   for (int l = 1; l < L; ++l) {
     GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];
     const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
@@ -1247,11 +1280,13 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
     OCF_LAUNCHED();
     g_prof.end(2, st);
   }
+  float* stats_out = xslot ? xslot : m->rowstats;
+  float* dh_out = xslot ? xslot + (size_t)B * ROWSTAT_W : m->dh_top;
   if (training) {
     k_rowsum<<<B, hpt, (size_t)hpt * 16, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, hpt / 4,
-                                               reinterpret_cast<float4*>(m->dh_top), m->itemstats, m->rowstats);
+                                               reinterpret_cast<float4*>(dh_out), m->itemstats, stats_out);
   } else {
-    k_rowsum<<<B, 32, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, 0, nullptr, m->itemstats, m->rowstats);
+    k_rowsum<<<B, 32, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, 0, nullptr, m->itemstats, stats_out);
   }
   OCF_LAUNCHED();
   return OCF_OK;
@@ -1474,6 +1509,56 @@ extern "C" int ocf_comm_unique_id(uint8_t* id) {
   return OCF_OK;
 }
 
+extern "C" int ocf_comm_destroy(ocf_comm* c);
+
+// Maps every rank's exchange region into this process (CUDA IPC; the handles travel through an
+// NCCL all-gather) unless OCF_NO_P2P is set or the ranks cannot all map each other - then the
+// step's exchanges stay on ncclAllReduce. All ranks take the same decision (all-reduced flag).
+static int comm_enable_p2p(ocf_comm* c) {
+  const bool want = c->world >= 2 && c->world <= peer::MAX_PEERS && std::getenv("OCF_NO_P2P") == nullptr;
+  c->slot_floats = (size_t)MAX_BATCH_ROWS * (MAX_HP + ROWSTAT_W);
+  const size_t bytes = peer::FLAG_BYTES + 2 * c->slot_floats * sizeof(float);
+  cudaIpcMemHandle_t mine{};
+  bool ok = want;
+  if (ok && cudaMalloc(reinterpret_cast<void**>(&c->region), bytes) != cudaSuccess) { cudaGetLastError(); c->region = nullptr; ok = false; }
+  if (ok && cudaMemset(c->region, 0, bytes) != cudaSuccess) ok = false;
+  if (ok && cudaIpcGetMemHandle(&mine, c->region) != cudaSuccess) { cudaGetLastError(); ok = false; }
+  // handles of all ranks (in-place all-gather on a small device buffer); a rank that failed so far
+  // still takes part in the collectives so that nobody hangs
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  uint8_t* d_h = nullptr;
+  OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_h), hb * c->world + sizeof(float)));
+  OCF_CUDA(cudaMemcpy(d_h + hb * c->rank, &mine, hb, cudaMemcpyHostToDevice));
+  OCF_NCCL(nccl_api().allGather(d_h + hb * c->rank, d_h, hb, ncclChar, c->comm, nullptr));
+  OCF_CUDA(cudaStreamSynchronize(nullptr));
+  std::vector<cudaIpcMemHandle_t> all((size_t)c->world);
+  OCF_CUDA(cudaMemcpy(all.data(), d_h, hb * c->world, cudaMemcpyDeviceToHost));
+  if (ok) {
+    for (int p = 0; p < c->world && ok; ++p) {
+      if (p == c->rank) { c->peer_region[p] = c->region; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+      c->peer_region[p] = static_cast<uint8_t*>(ptr);
+    }
+  }
+  float* d_flag = reinterpret_cast<float*>(d_h + hb * c->world);
+  const float f = ok ? 1.f : 0.f;
+  OCF_CUDA(cudaMemcpy(d_flag, &f, sizeof(float), cudaMemcpyHostToDevice));
+  OCF_NCCL(nccl_api().allReduce(d_flag, d_flag, 1, ncclFloat, ncclMin, c->comm, nullptr));
+  OCF_CUDA(cudaStreamSynchronize(nullptr));
+  float all_ok = 0.f;
+  OCF_CUDA(cudaMemcpy(&all_ok, d_flag, sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d_h);
+  c->p2p = want && all_ok == 1.f;
+  return OCF_OK;
+}
+
+extern "C" int ocf_comm_info(const ocf_comm* c, int32_t info[3]) {
+  OCF_REQUIRE(c && info, "ocf_comm_info: null argument");
+  info[0] = c->rank; info[1] = c->world; info[2] = c->p2p ? 1 : 0;
+  return OCF_OK;
+}
+
 extern "C" int ocf_comm_create(const uint8_t* id, int32_t rank, int32_t world, ocf_comm** out) {
   OCF_REQUIRE(id && out && world >= 1 && rank >= 0 && rank < world, "ocf_comm_create: bad argument");
   *out = nullptr;
@@ -1485,12 +1570,21 @@ extern "C" int ocf_comm_create(const uint8_t* id, int32_t rank, int32_t world, o
   std::memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
   ncclResult_t r = nccl_api().commInitRank(&c->comm, world, u, rank);
   if (r != ncclSuccess) { delete c; return fail(OCF_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_api().getErrorString(r)); }
+  int st = comm_enable_p2p(c);
+  if (st != OCF_OK) { ocf_comm_destroy(c); return st; }
   *out = c;
   return OCF_OK;
 }
 
 extern "C" int ocf_comm_destroy(ocf_comm* c) {
-  if (c) { if (c->comm) nccl_api().commDestroy(c->comm); delete c; }
+  if (c) {
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->world && p < peer::MAX_PEERS; ++p)
+      if (p != c->rank && c->peer_region[p]) cudaIpcCloseMemHandle(c->peer_region[p]);
+    if (c->comm) nccl_api().commDestroy(c->comm);      // after the peers' mappings are closed everywhere
+    if (c->region) cudaFree(c->region);
+    delete c;
+  }
   return OCF_OK;
 }
 
@@ -1514,6 +1608,60 @@ extern "C" int ocf_model_set_comm(ocf_model* m, ocf_comm* comm, int mode) {
     const int world = comm ? comm->world : 1;
     OCF_TRY(m->par_mem.get(&m->gathered_stats, (size_t)world * MAX_BATCH_ROWS * ROWSTAT_W, true));
   }
+  return OCF_OK;
+}
+
+// ---- the two exchanges of a column-sharded step ----------------------------------------------
+static bool use_peer(const ocf_model* m, int B) {
+  return m->comm && m->comm->p2p &&
+         (size_t)B * (std::max(m->hp[0], m->hp[m->L - 1]) + ROWSTAT_W) <= m->comm->slot_floats;
+}
+
+// phase 1 + exchange (+ first-layer activations when the peer path fuses them). *act0_done tells
+// the caller whether launch_act(0) is still due.
+static int encode_exchange(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args, cudaStream_t st,
+                           bool* act0_done) {
+  const int B = b->dev.B;
+  *act0_done = false;
+  if (use_peer(m, B)) {
+    ocf_comm* c = m->comm;
+    const uint32_t e = ++c->epoch;
+    OCF_TRY(phase_encode(m, b, st, c->slot(c->rank, e)));
+    g_prof.begin(6, st);
+    peer::k_allreduce_bias_act<<<peer::AR_CTAS, peer::AR_THREADS, 0, st>>>(c->dev(e), reinterpret_cast<float4*>(m->zsum[0]),
+                                                                            act_args(m, 0, B, training, args));
+    OCF_LAUNCHED();
+    g_prof.end(6, st);
+    *act0_done = true;
+    return OCF_OK;
+  }
+  OCF_TRY(phase_encode(m, b, st));
+  g_prof.begin(6, st);
+  OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
+  g_prof.end(6, st);
+  return OCF_OK;
+}
+
+// phase 2 + exchange of the row statistics (and dL/dh of the top hidden layer when training).
+static int decode_exchange(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args, cudaStream_t st,
+                           bool act0_done) {
+  const int B = b->dev.B, hpt = m->hp[m->L - 1];
+  if (use_peer(m, B)) {
+    ocf_comm* c = m->comm;
+    const uint32_t e = ++c->epoch;
+    OCF_TRY(phase_decode(m, b, training, args, nullptr, st, act0_done, c->slot(c->rank, e)));
+    g_prof.begin(7, st);
+    peer::k_allreduce_store<<<peer::AR_CTAS, peer::AR_THREADS, 0, st>>>(c->dev(e), B * ROWSTAT_W / 4, reinterpret_cast<float4*>(m->rowstats),
+                                                                         training ? B * hpt / 4 : 0, reinterpret_cast<float4*>(m->dh_top));
+    OCF_LAUNCHED();
+    g_prof.end(7, st);
+    return OCF_OK;
+  }
+  OCF_TRY(phase_decode(m, b, training, args, nullptr, st, act0_done));
+  g_prof.begin(7, st);
+  OCF_NCCL(nccl_api().allReduce(m->rowstats, m->rowstats, (size_t)m->cfg.max_rows * ROWSTAT_W + (training ? (size_t)B * hpt : 0),
+                                ncclFloat, ncclSum, m->comm->comm, st));
+  g_prof.end(7, st);
   return OCF_OK;
 }
 
@@ -1572,18 +1720,12 @@ extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* a
     return finish_step(m, host_metrics, st);
   }
   if (phase == 0 && m->par_mode == OCF_PAR_COLUMNS) {
-    // column shards: the three phases back to back with the two activation all-reduces between them
-    const int B = b->dev.B;
+    // column shards: the three phases back to back with the two activation exchanges between them
+    // (one-shot peer-memory all-reduce kernels fused with the next compute step, or ncclAllReduce)
+    bool act0 = false;
     OCF_TRY(fork_scan(m, b, st));
-    OCF_TRY(phase_encode(m, b, st));
-    g_prof.begin(6, st);
-    OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
-    g_prof.end(6, st);
-    OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
-    g_prof.begin(7, st);
-    OCF_NCCL(nccl_api().allReduce(m->rowstats, m->rowstats, (size_t)m->cfg.max_rows * ROWSTAT_W + (size_t)B * m->hp[m->L - 1],
-                                  ncclFloat, ncclSum, m->comm->comm, st));
-    g_prof.end(7, st);
+    OCF_TRY(encode_exchange(m, b, true, args, st, &act0));
+    OCF_TRY(decode_exchange(m, b, true, args, st, act0));
     OCF_TRY(phase_update(m, b, args, st));
     return finish_step(m, host_metrics, st);
   }
@@ -1608,13 +1750,11 @@ extern "C" int ocf_eval_step(ocf_model* m, ocf_batch* b, const ocf_step_args* ar
     return finish_step(m, host_metrics, st);
   }
   if (phase == 0 && m->par_mode == OCF_PAR_COLUMNS) {
-    const int B = b->dev.B;
-    OCF_TRY(phase_encode(m, b, st));
-    OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
-    OCF_TRY(phase_decode(m, b, false, args, nullptr, st));
-    OCF_NCCL(nccl_api().allReduce(m->rowstats, m->rowstats, (size_t)m->cfg.max_rows * ROWSTAT_W, ncclFloat, ncclSum, m->comm->comm, st));
+    bool act0 = false;
+    OCF_TRY(encode_exchange(m, b, false, args, st, &act0));
+    OCF_TRY(decode_exchange(m, b, false, args, st, act0));
     const int n_reg = launch_reg(m, st);
-    OCF_TRY(launch_metrics(m, B, args, n_reg, st));
+    OCF_TRY(launch_metrics(m, b->dev.B, args, n_reg, st));
     return finish_step(m, host_metrics, st);
   }
   if (phase == 0 || phase == 1) OCF_TRY(phase_encode(m, b, st));
@@ -1629,12 +1769,10 @@ extern "C" int ocf_eval_step(ocf_model* m, ocf_batch* b, const ocf_step_args* ar
 
 // Encoder pre-activations for predict / score. A column shard with a communicator reduces them
 // here; without one its caller has already run phase 1 and the z all-reduce.
-static int encode_for_output(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
+static int encode_for_output(ocf_model* m, const ocf_batch* b, cudaStream_t st, bool* act0_done) {
+  *act0_done = false;
   if (!m->cfg.sharded) return phase_encode(m, b, st);
-  if (m->par_mode == OCF_PAR_COLUMNS) {
-    OCF_TRY(phase_encode(m, b, st));
-    OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)b->dev.B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
-  }
+  if (m->par_mode == OCF_PAR_COLUMNS) return encode_exchange(m, b, false, nullptr, st, act0_done);
   return OCF_OK;
 }
 
@@ -1650,8 +1788,9 @@ extern "C" int ocf_predict(ocf_model* m, ocf_batch* b, float* out, void* stream_
   OCF_TRY(ensure_dense(m));
   const size_t count = (size_t)b->dev.B * m->cfg.n_cols;
   OCF_CUDA(cudaMemsetAsync(m->dense_out, 0, sizeof(float) * count, st));
-  OCF_TRY(encode_for_output(m, b, st));
-  OCF_TRY(phase_decode(m, b, false, nullptr, m->dense_out, st));
+  bool act0 = false;
+  OCF_TRY(encode_for_output(m, b, st, &act0));
+  OCF_TRY(phase_decode(m, b, false, nullptr, m->dense_out, st, act0));
   OCF_CUDA(cudaMemcpyAsync(out, m->dense_out, sizeof(float) * count, cudaMemcpyDeviceToHost, st));
   OCF_CUDA(cudaStreamSynchronize(st));
   return OCF_OK;
@@ -1662,8 +1801,9 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   OCF_REQUIRE(out != nullptr, "ocf_score: null output");
   cudaStream_t st = as_stream(stream_);
   const int L = m->L, B = b->dev.B;
-  OCF_TRY(encode_for_output(m, b, st));
-  OCF_TRY(launch_act(m, 0, B, false, nullptr, st));
+  bool act0 = false;
+  OCF_TRY(encode_for_output(m, b, st, &act0));
+  if (!act0) OCF_TRY(launch_act(m, 0, B, false, nullptr, st));
   for (int l = 1; l < L; ++l) {
     GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];
     OCF_TRY(launch_gemm(false, false, m->act[l - 1], m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));

@@ -323,29 +323,37 @@ k_rowsum(const float4* __restrict__ P, const int32_t* __restrict__ item_ptr, int
 // z + bias -> activation -> inverted dropout (model.py:66-73). Padded units are forced to 0.
 // a_out: activation before dropout (needed for the derivative), h_out: what the next layer sees,
 // dscale: 0 or 1/(1-p) per element (null when dropout is off).
-__global__ void __launch_bounds__(256)
-k_bias_act(const float4* __restrict__ zsum, const float4* __restrict__ bias, int B, int H, int hp4,
-           int act, float4* __restrict__ a_out, float4* __restrict__ h_out, float4* __restrict__ dscale,
-           float p_drop, uint2 key, uint32_t step, uint32_t layer, int row0) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * hp4) return;
-  const int b = idx / hp4, u4 = idx - b * hp4;
-  const float4 z = zsum[idx], bb = bias[u4];
+struct ActArgs {
+  const float4* bias; int B; int H; int hp4; int act;
+  float4* a_out; float4* h_out; float4* dscale;
+  float p_drop; uint2 key; uint32_t step; uint32_t layer; int row0;
+};
+
+__device__ __forceinline__ void bias_act_elem(const ActArgs& g, int idx, const float4 z) {
+  const int b = idx / g.hp4, u4 = idx - b * g.hp4;
+  const float4 bb = g.bias[u4];
   float a[4] = {z.x + bb.x, z.y + bb.y, z.z + bb.z, z.w + bb.w};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) a[k] = (u4 * 4 + k < H) ? act_fwd(act, a[k]) : 0.f;
-  a_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
-  if (dscale != nullptr) {
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)u4, (uint32_t)(b + row0), layer, step), key);
-    const uint32_t thresh = (uint32_t)floor((double)p_drop * 16777216.0);
-    const float inv = 1.0f / (1.0f - p_drop);
+  for (int k = 0; k < 4; ++k) a[k] = (u4 * 4 + k < g.H) ? act_fwd(g.act, a[k]) : 0.f;
+  g.a_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
+  if (g.dscale != nullptr) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)u4, (uint32_t)(b + g.row0), g.layer, g.step), g.key);
+    const uint32_t thresh = (uint32_t)floor((double)g.p_drop * 16777216.0);
+    const float inv = 1.0f / (1.0f - g.p_drop);
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
     float sc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { sc[k] = ((rr[k] >> 8) >= thresh) ? inv : 0.f; a[k] *= sc[k]; }
-    dscale[idx] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+    g.dscale[idx] = make_float4(sc[0], sc[1], sc[2], sc[3]);
   }
-  h_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
+  g.h_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+__global__ void __launch_bounds__(256)
+k_bias_act(const float4* __restrict__ zsum, ActArgs g) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.B * g.hp4) return;
+  bias_act_elem(g, idx, zsum[idx]);
 }
 
 // ============================================================================================

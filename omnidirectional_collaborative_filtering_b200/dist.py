@@ -133,6 +133,9 @@ class NativeComm(object):
         out = C.c_void_p()
         _lib.check(lib.ocf_comm_create(ident, self.rank, self.world, C.byref(out)))
         self.handle = out
+        info = (C.c_int32 * 3)()
+        _lib.check(lib.ocf_comm_info(out, info))
+        self.peer_memory = bool(info[2])     # exchanges run as one-shot all-reduce kernels over NVLink peer memory
 
     def close(self):
         if self.handle is not None:
@@ -277,8 +280,8 @@ def bench_main(args, w, cfg, rank, world):
     lib.ocf_profile_enable(0)
     dist.barrier()
     names = {0: "k_gather_split (K1)", 1: "k_enc_fwd (K2)", 2: "k_dec_fwd (K3)", 3: "k_col_scan (K4a)", 5: "k_row_update (K4b)",
-             6: "streaming optimizer pass" if rows_mode else "ncclAllReduce z [rows, H]",
-             7: "ncclAllReduce gradients" if rows_mode else "ncclAllReduce row stats + dL/dh [rows, 4 + H]"}
+             6: "streaming optimizer pass" if rows_mode else "exchange z [rows, H] (+ bias/act when over peer memory)",
+             7: "ncclAllReduce gradients" if rows_mode else "exchange row stats + dL/dh [rows, 4 + H]"}
     kernels = {}
     for tag, name in names.items():
         tot, cnt = C.c_double(), C.c_int64()
@@ -324,7 +327,9 @@ def bench_main(args, w, cfg, rank, world):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(cfg, parallelism=("row-parallel x%d, global batch %d rows (%d per GPU), replicated weights, one NCCL all-reduce of all gradients per step"
                                                  if rows_mode else
-                                                 "column-sharded x%d, global batch %d rows (%d per GPU), 2 NCCL all-reduces of [rows, H] per step")
+                                                 "column-sharded x%d, global batch %d rows (%d per GPU), 2 exchanges of [rows, H] per step as "
+                                                 + ("one-shot all-reduce kernels over NVLink peer memory fused with the next compute step"
+                                                    if native.peer_memory else "ncclAllReduce"))
                                % (world, B, args.batch_size), ratings_per_step=ratings / K,
                                l2="no flush: per-rank weights + optimizer state exceed the 126 MB L2"),
                 "clocks": clocks,
