@@ -1511,11 +1511,14 @@ extern "C" int ocf_comm_unique_id(uint8_t* id) {
 
 extern "C" int ocf_comm_destroy(ocf_comm* c);
 
-// Maps every rank's exchange region into this process (CUDA IPC; the handles travel through an
-// NCCL all-gather) unless OCF_NO_P2P is set or the ranks cannot all map each other - then the
-// step's exchanges stay on ncclAllReduce. All ranks take the same decision (all-reduced flag).
+// With OCF_P2P=1 in the environment of every rank: maps every rank's exchange region into this
+// process (CUDA IPC; the handles travel through an NCCL all-gather). Without it, or when the ranks
+// cannot all map each other, the step's exchanges stay on ncclAllReduce. All ranks take the same
+// decision (all-reduced flag). Opt-in for now: measured on 2 x B200 the one-shot kernels tie with
+// NCCL (profiles/README.md); NCCL is the path verified on 4 and 8 GPUs.
 static int comm_enable_p2p(ocf_comm* c) {
-  const bool want = c->world >= 2 && c->world <= peer::MAX_PEERS && std::getenv("OCF_NO_P2P") == nullptr;
+  const char* env = std::getenv("OCF_P2P");
+  const bool want = c->world >= 2 && c->world <= peer::MAX_PEERS && env != nullptr && env[0] == '1';
   c->slot_floats = (size_t)MAX_BATCH_ROWS * (MAX_HP + ROWSTAT_W);
   const size_t bytes = peer::FLAG_BYTES + 2 * c->slot_floats * sizeof(float);
   cudaIpcMemHandle_t mine{};
