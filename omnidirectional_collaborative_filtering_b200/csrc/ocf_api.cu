@@ -211,6 +211,10 @@ struct ocf_model {
   int2* col_seg = nullptr;
   int4* col_tasks = nullptr;
   int* col_counters = nullptr;
+  int* col_state = nullptr;       // batch-side K4a: [3][n_cols] per-column count / code OR / claimed, zeroed per step
+  int4* col_info = nullptr;       //   [n_cols]
+  uint32_t* col_bits = nullptr;   //   presence bitmap [min(n_cols, max_entries)][ceil(max_rows / 32)]
+  size_t col_bits_words = 0;
   int sm_count = 148;
   // the column scan (K4a) needs only the gathered batch: it runs on a side stream beside K2/K3
   cudaStream_t side = nullptr;
@@ -930,6 +934,8 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   m->dh_top = m->rowstats + (size_t)Bm * ROWSTAT_W;
   OCF_TRY(ws.get(&m->col_matches, (size_t)max_entries * 3));
   OCF_TRY(ws.get(&m->col_mcol, (size_t)max_entries));
+  m->col_bits_words = (size_t)std::min<int64_t>(m->cfg.n_cols, max_entries) * (size_t)((max_rows + 31) / 32);
+  OCF_TRY(ws.get(&m->col_bits, m->col_bits_words, true));
   return OCF_OK;
 }
 
@@ -967,7 +973,8 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   if (st) return bail(st);
   if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_log, (size_t)LOG_CAP * LOG_W, true)) ||
       (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_seg, (size_t)N, true)) ||
-      (st = m->mem.get(&m->col_counters, 2, true)))
+      (st = m->mem.get(&m->col_counters, 4, true)) || (st = m->mem.get(&m->col_state, (size_t)3 * N, true)) ||
+      (st = m->mem.get(&m->col_info, (size_t)N)))
     return bail(st);
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev); if (m->sm_count <= 0) m->sm_count = 148; }
   if ((st = alloc_workspace(m, cfg->max_rows, cfg->max_entries))) return bail(st);
@@ -1185,7 +1192,8 @@ static int check_step(const ocf_model* m, const ocf_batch* b, bool train) {
   OCF_REQUIRE(m && b, "step: null argument");
   if (b->mode == 0) return fail(OCF_ERR_STATE, "step: the batch has not been filled");
   if (train && b->mode != 1) return fail(OCF_ERR_STATE, "train step needs a split batch (ocf_batch_fill_split)");
-  if (train && !b->store->has_csc) return fail(OCF_ERR_STATE, "train step needs a store built with build_csc");
+  if (train && b->store->has_dups && !b->store->has_csc)
+    return fail(OCF_ERR_STATE, "training on a store whose rows repeat a column needs the store's column index (build_csc)");
   OCF_REQUIRE(b->store->n_cols == m->cfg.n_cols, "step: the batch's store and the model disagree on n_cols");
   OCF_REQUIRE(b->dev.B <= m->cfg.max_rows && b->dev.n_entries <= m->cfg.max_entries && b->dev.n_items <= m->max_items,
               "step: the batch exceeds the model's workspace");
@@ -1352,9 +1360,35 @@ static int launch_row_update(int hp, int kind, int grid, const RowArgs& r, cudaS
 static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int dense, cudaStream_t st) {
   if (!do_dec && !do_enc) return OCF_OK;
   const BatchDev& bt = b->dev;
-  OCF_CUDA(cudaMemsetAsync(m->col_counters, 0, 2 * sizeof(int), st));
+  OCF_CUDA(cudaMemsetAsync(m->col_counters, 0, 4 * sizeof(int), st));
   if (dense) OCF_CUDA(cudaMemsetAsync(m->col_seg, 0, sizeof(int2) * (size_t)m->cfg.n_cols, st));
-  if (bt.n_entries == 0 || b->store->dev.n_groups == 0) return OCF_OK;
+  if (bt.n_entries == 0) return OCF_OK;
+  if (!b->store->has_dups) {
+    // batch-side counting sort (every (column, batch row) pair is unique)
+    const int W = (bt.B + 31) / 32;
+    const size_t words = (size_t)std::min<int64_t>(m->cfg.n_cols, bt.n_entries) * W;
+    OCF_CUDA(cudaMemsetAsync(m->col_state, 0, sizeof(int) * 3 * (size_t)m->cfg.n_cols, st));
+    OCF_CUDA(cudaMemsetAsync(m->col_bits, 0, sizeof(uint32_t) * std::min(words, m->col_bits_words), st));
+    SortArgs a{};
+    a.bt = bt;
+    a.cnt = m->col_state; a.codeor = m->col_state + m->cfg.n_cols; a.claimed = m->col_state + 2 * (size_t)m->cfg.n_cols;
+    a.colinfo = m->col_info; a.bits = m->col_bits; a.W = W; a.counters = m->col_counters;
+    a.matches = m->col_matches; a.tasks = m->col_tasks; a.colseg = m->col_seg;
+    a.nblk = m->nblk; a.bits3 = m->bits; a.dense = dense; a.do_dec = do_dec; a.do_enc = do_enc;
+    g_prof.begin(3, st);
+    k_sort_count<<<bt.n_items, 128, 0, st>>>(a);
+    OCF_LAUNCHED();
+    k_sort_alloc<<<bt.n_items, 128, 0, st>>>(a);
+    OCF_LAUNCHED();
+    k_sort_bits<<<bt.n_items, 128, 0, st>>>(a);
+    OCF_LAUNCHED();
+    k_sort_place<<<bt.n_items, 128, 0, st>>>(a);
+    OCF_LAUNCHED();
+    g_prof.end(3, st);
+    return OCF_OK;
+  }
+  // rows that repeat a column: stream the store's CSC index (order-preserving compaction)
+  if (b->store->dev.n_groups == 0) return OCF_OK;
   ColArgs a{};
   a.s = b->store->dev; a.bt = bt;
   a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.dense = dense;

@@ -789,6 +789,115 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
   }
 }
 
+// ============================================================================================
+// K4a, batch-side: groups the batch's own ratings by catalogue column with a counting sort over
+// the ~10^5 gathered entries instead of streaming the store's CSC index (10^7-10^8 entries):
+//   count   per-column number of live entries + OR of their code bits        (atomics on ints)
+//   alloc   one elected entry per touched column reserves the column's segment of the match
+//           list, a row of the presence bitmap and the column's update tasks (warp-aggregated)
+//   bits    every entry sets bit `batch row` in its column's bitmap row
+//   place   an entry's rank inside its column = popcount of the lower batch rows present, so the
+//           match list of a column is ordered by batch row whatever order the atomics ran in:
+//           the gradient sums of K4b keep a fixed order (bit-reproducible steps)
+// A (column, batch row) pair is unique unless a row repeats a column; stores with repeats keep
+// using the CSC scan above. Four small kernels over the work items, ~2 MB of traffic.
+// ============================================================================================
+struct SortArgs {
+  BatchDev bt;
+  int* cnt; int* codeor; int* claimed;     // [n_cols] each, zeroed per step
+  int4* colinfo;                            // [n_cols] (first match, matches, bitmap row, -) of a touched column
+  uint32_t* bits; int W;                    // presence bitmap [touched columns][W words], zeroed per step
+  int* counters;                            // [0] matches [1] tasks [2] touched columns
+  uint32_t* matches; int4* tasks; int2* colseg;
+  int nblk; int3 bits3; int dense; int do_dec; int do_enc;
+};
+
+__global__ void __launch_bounds__(128) k_sort_count(SortArgs a) {
+  const int4 it = a.bt.items[blockIdx.x];
+  const int p0 = a.bt.ent_off[it.x] + it.y;
+  for (int i = threadIdx.x; i < it.z; i += 128) {
+    const int code = a.bt.codes[p0 + i];
+    if (code == 0) continue;
+    const int c = a.bt.ent_col[p0 + i];
+    atomicAdd(&a.cnt[c], 1);
+    atomicOr(&a.codeor[c], code);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sort_alloc(SortArgs a) {
+  const int4 it = a.bt.items[blockIdx.x];
+  const int p0 = a.bt.ent_off[it.x] + it.y;
+  const int lane = threadIdx.x & 31;
+  for (int i0 = 0; i0 < it.z; i0 += 128) {
+    const int i = i0 + threadIdx.x;
+    int c = -1, n = 0, n_tasks = 0;
+    int arr[4];
+    if (i < it.z && a.bt.codes[p0 + i] != 0) {
+      c = a.bt.ent_col[p0 + i];
+      if (atomicExch(&a.claimed[c], 1) == 0) {          // this entry speaks for its column
+        n = a.cnt[c];
+        const int any = a.codeor[c];
+        if (!a.dense) {
+          if (a.do_dec && (any & CODE_TGT)) arr[n_tasks++] = 0;
+          if (a.do_enc)
+            for (int blk = 0; blk < a.nblk; ++blk) {
+              const int bit = blk == 0 ? a.bits3.x : (blk == 1 ? a.bits3.y : a.bits3.z);
+              if (any & bit) arr[n_tasks++] = 1 + blk;
+            }
+        }
+      } else c = -1;
+    }
+    // one atomic per warp and counter: exclusive prefix of (matches, tasks, columns) over the lanes
+    int sn = n, stk = n_tasks, sc = c >= 0 ? 1 : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t0 = __shfl_up_sync(FULL, sn, o), t1 = __shfl_up_sync(FULL, stk, o), t2 = __shfl_up_sync(FULL, sc, o);
+      if (lane >= o) { sn += t0; stk += t1; sc += t2; }
+    }
+    int b0 = 0, b1 = 0, b2 = 0;
+    if (lane == 31) {
+      if (sn) b0 = atomicAdd(&a.counters[0], sn);
+      if (stk) b1 = atomicAdd(&a.counters[1], stk);
+      if (sc) b2 = atomicAdd(&a.counters[2], sc);
+    }
+    b0 = __shfl_sync(FULL, b0, 31); b1 = __shfl_sync(FULL, b1, 31); b2 = __shfl_sync(FULL, b2, 31);
+    if (c >= 0) {
+      const int base = b0 + sn - n, slot = b1 + stk - n_tasks, row = b2 + sc - 1;
+      a.colinfo[c] = make_int4(base, n, row, 0);
+      if (a.dense) a.colseg[c] = make_int2(base, n);
+      for (int k = 0; k < n_tasks; ++k) a.tasks[slot + k] = make_int4(c, arr[k], base, n);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sort_bits(SortArgs a) {
+  const int4 it = a.bt.items[blockIdx.x];
+  const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
+  for (int i = threadIdx.x; i < it.z; i += 128) {
+    if (a.bt.codes[p0 + i] == 0) continue;
+    const int row = a.colinfo[a.bt.ent_col[p0 + i]].z;
+    atomicOr(&a.bits[(size_t)row * a.W + (b >> 5)], 1u << (b & 31));
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sort_place(SortArgs a) {
+  const int4 it = a.bt.items[blockIdx.x];
+  const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
+  for (int i = threadIdx.x; i < it.z; i += 128) {
+    const int p = p0 + i;
+    const uint32_t code = a.bt.codes[p];
+    if (code == 0) continue;
+    const int4 info = a.colinfo[a.bt.ent_col[p]];
+    const uint32_t* bw = a.bits + (size_t)info.z * a.W;
+    int rank = __popc(bw[b >> 5] & ((1u << (b & 31)) - 1u));
+    for (int w = 0; w < (b >> 5); ++w) rank += __popc(bw[w]);
+    const size_t idx = (size_t)(info.x + rank);
+    a.matches[idx * 3] = (uint32_t)b | (code << 16);
+    a.matches[idx * 3 + 1] = __float_as_uint(a.bt.ent_val[p]);
+    a.matches[idx * 3 + 2] = (uint32_t)p;
+  }
+}
+
 struct RowArgs {
   const uint32_t* matches; const int4* tasks; const int2* colseg; const int* counters;
   const float* hdec; const float* dz0; const float* dy;

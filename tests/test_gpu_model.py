@@ -125,6 +125,41 @@ def test_row_parallel_gradient_path_matches_oracle(golden_datasets, case):
     rd.close()
 
 
+SYN_CASES = [
+    # shape, reverse, B, aux, layers, width, opt, l2, pdrop, pass_through   (no row repeats a column here:
+    # the weight update takes its work list from the batch-side counting sort, not from the CSC scan)
+    ("small", True, 64, None, 1, 48, "adagrad", None, 0.2, True),
+    ("small", False, 160, "dropout", 1, 130, "adagrad", None, None, False),
+    ("small", True, 96, "both", 2, 40, "rmsprop", 0.01, None, False),
+    ("tiny", True, 8, "causal", 1, 12, "adam", None, 0.3, True),
+]
+
+
+@pytest.mark.parametrize("case", SYN_CASES, ids=[str(i) for i in range(len(SYN_CASES))])
+def test_train_steps_match_oracle_synthetic(case):
+    from omnidirectional_collaborative_filtering_b200 import synthetic
+    from omnidirectional_collaborative_filtering_b200.data_reader import data_reader
+    shape, rev, B, aux, layers, width, opt, l2, pdrop, pt = case
+    fs = synthetic.make_fixed_split(shape, reverse_user_item_data=rev, seed=21)
+    dicts = synthetic.to_reference_dicts(fs, raw_col_id=lambda c: c)
+    rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs)
+    assert rd.store("train").info()["has_dups"] == 0
+    data = ref_batches.RefData(fs.n_cols, fs.train.n_rows, dicts["unique_cols"], eval_mode="fixed_split",
+                               train=dicts["train"], valid=tuple(dicts["valid"]), test=tuple(dicts["test"]))
+    om, ref = _pair({"n_cols": fs.n_cols}, aux, layers, width, "sigmoid", l2, pdrop, opt, "mean_squared_error", B=B)
+    np.random.seed(13)
+    gen = rd.data_gen(B, [0.3, 0.9], "train", True, aux, -1, pass_through_input_training=pt)
+    rgen = ref_batches.batch_stream(data, B, [0.3, 0.9], "train", True, aux, -1, pass_through_input_training=pt,
+                                    rng=np.random.RandomState(13), vectorised=True)
+    for step in range(4):
+        got = om.model.train_on_batch(next(gen))
+        feed, targets = next(rgen)
+        _close(got, ref.train_on_batch(feed, targets))
+    for g, w in zip(om.model.get_weights(), ref.get_weights()):
+        _close_weights(g, w, om.model.optimizer.lr)
+    rd.close()
+
+
 def test_frozen_layers_and_transfer(golden_datasets):
     ds = golden_datasets["fwd"]
     N = ds["n_cols"]
