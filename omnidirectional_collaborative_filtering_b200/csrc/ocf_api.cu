@@ -211,6 +211,7 @@ struct ocf_model {
   int2* col_seg = nullptr;
   int4* col_tasks = nullptr;
   int* col_counters = nullptr;
+  float* gemm_part = nullptr;     // split-K partials of the hidden-layer GEMMs
   int* col_state = nullptr;       // batch-side K4a: [3][n_cols] per-column count / code OR / claimed, zeroed per step
   int4* col_info = nullptr;       //   [n_cols]
   uint32_t* col_bits = nullptr;   //   presence bitmap [min(n_cols, max_entries)][ceil(max_rows / 32)]
@@ -1217,14 +1218,29 @@ static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st, float
   return OCF_OK;
 }
 
-static int launch_gemm(bool ta, bool tb, const float* A, int lda, const float* Bm, int ldb, int M, int N, int K,
-                       const GemmEpi& ep, cudaStream_t st) {
+constexpr size_t GEMM_PART_FLOATS = (size_t)8 * 512 * 1024;   // split-K scratch (16 MB), models with hidden-to-hidden layers only
+static float* g_gemm_part_of(ocf_model* m);
+
+static int launch_gemm(ocf_model* m, bool ta, bool tb, const float* A, int lda, const float* Bm, int ldb, int M, int N, int K,
+                       GemmEpi ep, cudaStream_t st) {
   dim3 grid((N + 63) / 64, (M + 63) / 64);
+  // few output tiles and a long contraction: split K over grid.z, reduce + epilogue in a second kernel
+  int S = 1;
+  while (S < 8 && (int)(grid.x * grid.y) * S * 2 <= m->sm_count * 2 && K / (S * 2) >= 64 &&
+         (size_t)(S * 2) * M * N <= GEMM_PART_FLOATS)
+    S *= 2;
+  ep.part = nullptr;
+  if (S > 1) { ep.part = g_gemm_part_of(m); if (ep.part == nullptr) S = 1; }
+  grid.z = S;
   if (!ta && !tb) k_sgemm<false, false><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
   else if (ta && !tb) k_sgemm<true, false><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
   else if (!ta && tb) k_sgemm<false, true><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
   else k_sgemm<true, true><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
   OCF_LAUNCHED();
+  if (S > 1) {
+    k_gemm_reduce<<<(M * N + 255) / 256, 256, 0, st>>>(M, N, S, ep);
+    OCF_LAUNCHED();
+  }
   return OCF_OK;
 }
 
@@ -1242,6 +1258,11 @@ static ActArgs act_args(ocf_model* m, int l, int B, bool training, const ocf_ste
   g.key = make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   g.step = args ? args->step : 0u; g.layer = (uint32_t)l; g.row0 = args ? args->row0 : 0;
   return g;
+}
+
+static float* g_gemm_part_of(ocf_model* m) {
+  if (m->gemm_part == nullptr && m->mem.get(&m->gemm_part, GEMM_PART_FLOATS) != OCF_OK) m->gemm_part = nullptr;
+  return m->gemm_part;
 }
 
 // bias + activation (+ dropout) of layer l from zsum[l]
@@ -1268,7 +1289,7 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   for (int l = 1; l < L; ++l) {
     GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];
     const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
-    OCF_TRY(launch_gemm(false, false, hin, m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
+    OCF_TRY(launch_gemm(m, false, false, hin, m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
     OCF_TRY(launch_act(m, l, B, training, args, st));
   }
   const float* htop = drop ? m->h[L - 1] : m->act[L - 1];
@@ -1482,7 +1503,7 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     // dz_{l-1} = (dz_l . W_l^T) * dropout scale * act'(a_{l-1})   (uses W_l before its update)
     GemmEpi ep{}; ep.kind = EPI_DZ; ep.C = m->dz[l - 1]; ep.ldc = m->hp[l - 1]; ep.aux0 = m->act[l - 1];
     ep.aux1 = drop ? m->dscale[l - 1] : nullptr; ep.act = m->cfg.activation;
-    OCF_TRY(launch_gemm(false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
+    OCF_TRY(launch_gemm(m, false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
     Layer& lo = m->layers[l - 1];
     k_dz_bias<<<m->hp[l - 1] / 32, 1024, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
                                                          m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0,
@@ -1493,7 +1514,7 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
       GemmEpi eu{}; eu.kind = EPI_UPDATE; eu.C = ly.W; eu.ldc = m->hp[l]; eu.s1 = ly.Ws1; eu.s2 = ly.Ws2; eu.opt = opt;
       if (grad_mode) { eu.kind = EPI_STORE; eu.C = m->gW[l]; }
       const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
-      OCF_TRY(launch_gemm(true, false, hin, m->hp[l - 1], m->dz[l], m->hp[l], m->hp[l - 1], m->hp[l], B, eu, st));
+      OCF_TRY(launch_gemm(m, true, false, hin, m->hp[l - 1], m->dz[l], m->hp[l], m->hp[l - 1], m->hp[l], B, eu, st));
     }
   }
   // catalogue-wide kernels: encoder rows and decoder rows of every touched column
@@ -1843,7 +1864,7 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   if (!act0) OCF_TRY(launch_act(m, 0, B, false, nullptr, st));
   for (int l = 1; l < L; ++l) {
     GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];
-    OCF_TRY(launch_gemm(false, false, m->act[l - 1], m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
+    OCF_TRY(launch_gemm(m, false, false, m->act[l - 1], m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
     OCF_TRY(launch_act(m, l, B, false, nullptr, st));
   }
   float* dst = out;

@@ -515,6 +515,7 @@ enum { EPI_STORE = 0, EPI_DZ = 1, EPI_UPDATE = 2, EPI_BIAS_COL = 3 };
 
 struct GemmEpi {
   int kind;
+  float* part;         // split-K: raw partial products [gridDim.z][M][N] (the epilogue runs in k_gemm_reduce)
   float* C; int ldc;
   const float* aux0;   // EPI_DZ: activation a [M, ldc];   EPI_BIAS_COL: bias [N]
   const float* aux1;   // EPI_DZ: dropout scale or null
@@ -536,7 +537,12 @@ k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  // split-K: slice blockIdx.z of the contraction (a batch of 128 rows gives a 2 x 8 grid of output
+  // tiles and a 64-step K loop otherwise: latency-bound on 16 CTAs)
+  const int kchunk = ((K + (int)gridDim.z - 1) / (int)gridDim.z + 15) / 16 * 16;
+  const int kbeg = blockIdx.z * kchunk;
+  K = min(K, kbeg + kchunk);
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int e = tid + r * 256;
@@ -576,6 +582,7 @@ k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int 
       if (gn >= N) continue;
       const size_t k = (size_t)gm * ep.ldc + gn;
       float v = acc[i][j];
+      if (gridDim.z > 1) { ep.part[((size_t)blockIdx.z * M + gm) * N + gn] = v; continue; }
       switch (ep.kind) {
         case EPI_STORE: ep.C[k] = v; break;
         case EPI_DZ:
@@ -592,6 +599,32 @@ k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int 
         default: ep.C[k] = v + ep.aux0[gn]; break;
       }
     }
+  }
+}
+
+// Sum of the split-K partials in slice order + the GEMM's epilogue.
+__global__ void __launch_bounds__(256)
+k_gemm_reduce(int M, int N, int S, GemmEpi ep) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int gm = idx / N, gn = idx - gm * N;
+  float v = ep.part[idx];
+  for (int z = 1; z < S; ++z) v += ep.part[(size_t)z * M * N + idx];
+  const size_t k = (size_t)gm * ep.ldc + gn;
+  switch (ep.kind) {
+    case EPI_STORE: ep.C[k] = v; break;
+    case EPI_DZ:
+      if (ep.aux1 != nullptr) v *= ep.aux1[k];
+      ep.C[k] = v * act_bwd(ep.act, ep.aux0[k]);
+      break;
+    case EPI_UPDATE: {
+      float w = ep.C[k], t1 = ep.s1 ? ep.s1[k] : 0.f, t2 = ep.s2 ? ep.s2[k] : 0.f;
+      opt_apply(ep.opt, v, w, t1, t2);
+      ep.C[k] = w;
+      if (ep.s1) ep.s1[k] = t1;
+      if (ep.s2) ep.s2[k] = t2;
+    } break;
+    default: ep.C[k] = v + ep.aux0[gn]; break;
   }
 }
 
