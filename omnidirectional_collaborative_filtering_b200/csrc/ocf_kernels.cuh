@@ -124,33 +124,37 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
     w = take;
     pos += take;
   }
-  while (w < n_words) {
+  // Whole regenerations. The single CTA is bound by instruction issue, so the twists A(i) are
+  // evaluated once into shared memory (first sweep) and combined by plain XORs (second sweep).
+  __shared__ uint32_t tw[624];
+  const int i0 = tid, i1 = tid + MT_THREADS;
+  long long left = n_words - w;                      // words still owed to the batch
+  uint32_t* dst = out != nullptr ? out + w : nullptr;
+  while (left > 0) {
     const uint32_t* o = mt[cur];
     uint32_t* n = mt[cur ^ 1];
-    const long long left = n_words - w;              // words of this array that belong to the batch
-    uint32_t* dst = out != nullptr ? out + w : nullptr;
+    tw[i0] = mt_a(o[i0], o[i0 + 1]);                 // i0 < 320 <= 622
+    if (i1 < 623) tw[i1] = mt_a(o[i1], o[i1 + 1]);
+    __syncthreads();
+    const int lim = left < 624 ? (int)left : 624;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const int i = tid + k * MT_THREADS;
+      const int i = k == 0 ? i0 : i1;
       if (i < 624) {
         uint32_t v;
-        if (i < 227) v = mt_a(o[i], o[i + 1]) ^ o[i + 397];
-        else if (i < 454) v = mt_a(o[i], o[i + 1]) ^ mt_a(o[i - 227], o[i - 226]) ^ o[i + 170];
-        else if (i < 623) v = mt_a(o[i], o[i + 1]) ^ mt_a(o[i - 227], o[i - 226]) ^ mt_a(o[i - 454], o[i - 453]) ^ o[i - 57];
-        else {
-          const uint32_t new0 = mt_a(o[0], o[1]) ^ o[397];
-          const uint32_t new396 = mt_a(o[396], o[397]) ^ mt_a(o[169], o[170]) ^ o[566];
-          v = mt_a(o[623], new0) ^ new396;
-        }
+        if (i < 227) v = tw[i] ^ o[i + 397];
+        else if (i < 454) v = tw[i] ^ tw[i - 227] ^ o[i + 170];
+        else if (i < 623) v = tw[i] ^ tw[i - 227] ^ tw[i - 454] ^ o[i - 57];
+        else v = mt_a(o[623], tw[0] ^ o[397]) ^ (tw[396] ^ tw[169] ^ o[566]);
         n[i] = v;
-        if (dst != nullptr && i < left) dst[i] = mt_temper(v);
+        if (dst != nullptr && i < lim) dst[i] = mt_temper(v);
       }
     }
     __syncthreads();
     cur ^= 1;
-    const int take = (int)min(624LL, left);
-    w += take;
-    pos = take;
+    pos = lim;
+    left -= lim;
+    if (dst != nullptr) dst += lim;
   }
   __syncthreads();
   for (int i = tid; i < 624; i += blockDim.x) state[i] = mt[cur][i];

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel totals of an `ncu --metrics gpu__time_duration.sum --csv` launch list, restricted to
-the launches of whole training steps (from one k_gather_split<false> to the next): kernel, launches
+the launches of whole device-timed training steps (k_gather_split<false> ... k_row_update): kernel, launches
 per step, mean duration, share of the summed kernel time of a step.
 
     python scripts/launch_summary.py gpurun_out/launches.csv > profiles/rNN_launch_summary.txt
@@ -21,7 +21,7 @@ for name, us, stream in launches:
         cur = []
     if cur is not None:
         cur.append((name, us, stream))
-        if name == "k_metrics":
+        if name.startswith("k_row_update"):
             steps.append(cur)
             cur = None
 tot = collections.defaultdict(float)
