@@ -170,8 +170,7 @@ struct ocf_batch {
   // device-RNG mode: this batch's slice of the MT19937 stream and the per-row cdf
   uint32_t* d_words = nullptr;
   int64_t words_cap = 0;           // in draws (2 words each)
-  double* d_cdf0 = nullptr;
-  int64_t cdf0_cap = 0;
+  double rng_lo = 0.0, rng_range = 0.0;
   int64_t draw_base = 0;           // index of the batch's first per-rating draw in its slice of the stream
   int cdf0_row0 = 0;               // row-parallel slice: index of the batch's first row among the sparsity draws
   cudaEvent_t words_ready = nullptr, gathered = nullptr;
@@ -541,7 +540,6 @@ extern "C" int ocf_batch_destroy(ocf_batch* b) {
     if (b->h_staging) cudaFreeHost(b->h_staging);
     if (b->copied) cudaEventDestroy(b->copied);
     if (b->d_words) cudaFree(b->d_words);
-    if (b->d_cdf0) cudaFree(b->d_cdf0);
     if (b->words_ready) cudaEventDestroy(b->words_ready);
     if (b->gathered) cudaEventDestroy(b->gathered);
     delete b;
@@ -622,7 +620,7 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
   d.draw_off = reinterpret_cast<const int32_t*>(b->d_staging + off[5]);
   d.flags = b->d_staging + off[6];
   d.flags_out = b->d_staging + off[6];
-  d.words = b->d_words; d.cdf0 = b->d_cdf0 ? b->d_cdf0 + b->cdf0_row0 : nullptr;
+  d.words = b->d_words; d.rng_lo = b->rng_lo; d.rng_range = b->rng_range; d.cdf_row0 = b->cdf0_row0;
   d.ent_col = b->d_ent_col; d.ent_val = b->d_ent_val; d.codes = b->d_codes;
   return OCF_OK;
 }
@@ -752,7 +750,7 @@ extern "C" int ocf_rng_skip(ocf_rng* r, int64_t n_draws) {
   OCF_REQUIRE(r && n_draws >= 0, "ocf_rng_skip: bad argument");
   if (n_draws == 0) return OCF_OK;
   OCF_CUDA(cudaSetDevice(r->device));
-  k_mt_words<<<1, MT_THREADS, 0, r->stream>>>(r->d_state, 2 * (long long)n_draws, nullptr, 0, 0.0, 0.0, nullptr);
+  k_mt_words<<<1, MT_THREADS, 0, r->stream>>>(r->d_state, 2 * (long long)n_draws, nullptr);
   OCF_LAUNCHED();
   return OCF_OK;
 }
@@ -799,7 +797,6 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
     OCF_REQUIRE(row >= 0 && row < store->n_rows, "ocf_batch_fill_split_rng: row id out of range");
     draws += full_len ? full_len[r] : store->h_rowptr[row + 1] - store->h_rowptr[row];
   }
-  int n_draw_rows = n_rows;
   b->draw_base = n_rows; b->cdf0_row0 = 0;
   if (slice != nullptr) {
     // these rows are a slice of a larger drawing unit (a rank's rows of a global batch): the unit's
@@ -807,7 +804,6 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
     OCF_REQUIRE(slice->n_draw_rows >= n_rows && slice->row0 >= 0 && slice->row0 + n_rows <= slice->n_draw_rows &&
                 slice->draws_before >= 0 && slice->draws_total >= slice->n_draw_rows + slice->draws_before + (draws - n_rows),
                 "ocf_batch_fill_split_rng: inconsistent slice");
-    n_draw_rows = slice->n_draw_rows;
     b->draw_base = slice->n_draw_rows + slice->draws_before;
     b->cdf0_row0 = slice->row0;
     draws = slice->draws_total;
@@ -817,22 +813,17 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
     OCF_CUDA(cudaEventCreateWithFlags(&b->words_ready, cudaEventDisableTiming));
     OCF_CUDA(cudaEventCreateWithFlags(&b->gathered, cudaEventDisableTiming));
   }
-  if (n_draw_rows > b->cdf0_cap) {
-    if (b->d_cdf0) { OCF_CUDA(cudaDeviceSynchronize()); cudaFree(b->d_cdf0); b->d_cdf0 = nullptr; }
-    const int64_t cap = std::max<int64_t>(n_draw_rows, b->max_rows);
-    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_cdf0), sizeof(double) * (size_t)cap));
-    b->cdf0_cap = cap;
-  }
+  b->rng_lo = lo; b->rng_range = hi - lo;
   if (draws > b->words_cap) {
     if (b->d_words) { OCF_CUDA(cudaDeviceSynchronize()); cudaFree(b->d_words); b->d_words = nullptr; }
     const int64_t cap = std::max<int64_t>(draws + draws / 4, b->max_rows + b->max_entries);
-    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_words), sizeof(uint32_t) * 2 * (size_t)cap));
+    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_words), sizeof(uint32_t) * (2 * (size_t)cap + MT_HDR + 4 + MT_SLACK)));
     b->words_cap = cap;
   }
   // the previous batch staged in this object may still be reading its words (no-op before the first gather)
   OCF_CUDA(cudaStreamWaitEvent(rng->stream, b->gathered, 0));
   // the stream's next `draws` doubles, generated beside whatever `stream` is running
-  k_mt_words<<<1, MT_THREADS, 0, rng->stream>>>(rng->d_state, 2 * (long long)draws, b->d_words, n_draw_rows, lo, hi - lo, b->d_cdf0);
+  k_mt_words<<<1, MT_THREADS, 0, rng->stream>>>(rng->d_state, 2 * (long long)draws, b->d_words);
   OCF_LAUNCHED();
   OCF_CUDA(cudaEventRecord(b->words_ready, rng->stream));
   OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split_rng"));
@@ -910,15 +901,15 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   m->cfg.max_rows = max_rows;
   m->cfg.max_entries = max_entries;
   m->max_items = max_items_for(max_rows, max_entries);
-  const int L = m->L, Bm = max_rows;
-  m->act_rows = (long long)align_up((size_t)Bm, 256);   // whole TMA boxes of the scoring GEMM
+  const int L = m->L;
+  m->act_rows = (long long)align_up((size_t)max_rows, 256);   // whole TMA boxes of the scoring GEMM
   m->map_h_ok = false;
   m->zsum.assign(L, nullptr); m->act.assign(L, nullptr); m->h.assign(L, nullptr);
   m->dscale.assign(L, nullptr); m->dz.assign(L, nullptr);
   const bool drop = m->cfg.dropout_p > 0.f;
   Arena& ws = m->ws_mem;
   for (int l = 0; l < L; ++l) {
-    const size_t n = (size_t)Bm * m->hp[l];
+    const size_t n = (size_t)max_rows * m->hp[l];
     OCF_TRY(ws.get(&m->zsum[l], n, true));
     OCF_TRY(ws.get(&m->act[l], (size_t)m->act_rows * m->hp[l], true));
     OCF_TRY(ws.get(&m->dz[l], n, true));
@@ -931,8 +922,8 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   OCF_TRY(ws.get(&m->dy, (size_t)max_entries, true));
   // [row statistics | dL/dh of the top hidden layer] share one allocation: a column shard
   // all-reduces both with a single collective over the prefix 4*max_rows + B*hp floats
-  OCF_TRY(ws.get(&m->rowstats, (size_t)Bm * ROWSTAT_W + (size_t)Bm * m->hp[L - 1], true));
-  m->dh_top = m->rowstats + (size_t)Bm * ROWSTAT_W;
+  OCF_TRY(ws.get(&m->rowstats, (size_t)max_rows * ROWSTAT_W + (size_t)max_rows * m->hp[L - 1], true));
+  m->dh_top = m->rowstats + (size_t)max_rows * ROWSTAT_W;
   OCF_TRY(ws.get(&m->col_matches, (size_t)max_entries * 3));
   OCF_TRY(ws.get(&m->col_mcol, (size_t)max_entries));
   m->col_bits_words = (size_t)std::min<int64_t>(m->cfg.n_cols, max_entries) * (size_t)((max_rows + 31) / 32);
@@ -957,7 +948,7 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   m->cfg = *cfg;
   m->L = cfg->n_layers;
   aux_bits(cfg->aux, m->nblk, m->bits);
-  const int L = m->L, N = cfg->n_cols, Bm = cfg->max_rows;
+  const int L = m->L, N = cfg->n_cols;
   for (int l = 0; l < L; ++l) m->hp.push_back(pad_h(cfg->widths[l]));
   m->layers.resize(L + 1);
   int st = OCF_OK;
@@ -1268,9 +1259,7 @@ static float* g_gemm_part_of(ocf_model* m) {
 // bias + activation (+ dropout) of layer l from zsum[l]
 static int launch_act(ocf_model* m, int l, int B, bool training, const ocf_step_args* args, cudaStream_t st) {
   const int hp = m->hp[l];
-  const bool drop = training && m->cfg.dropout_p > 0.f;
   const int total = B * (hp / 4);
-  const uint64_t seed = args ? args->dropout_seed : 0;
   k_bias_act<<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(m->zsum[l]), act_args(m, l, B, training, args));
   OCF_LAUNCHED();
   return OCF_OK;

@@ -84,8 +84,9 @@ struct BatchDev {
   const int32_t* item_ptr;   // [B+1] items of row b
   const uint8_t* flags;      // [n_entries] keep flags (split mode)
   const int32_t* draw_off;   // [B] device-RNG mode: index of the row's first draw in the batch's slice of the stream
-  const uint32_t* words;     //     tempered MT19937 words of the batch's draws (2 per draw)
-  const double* cdf0;        // [B] (1-s)/((1-s)+s) of the row's sparsity draw
+  const uint32_t* words;     //     k_mt_words output: header + tempered MT19937 words of the batch's draws (2 per draw)
+  double rng_lo, rng_range;  //     np.random.uniform(lo, hi) of the rows' sparsity draws (range = hi - lo)
+  int cdf_row0;              //     index of batch row 0 among the drawing unit's sparsity draws
   uint8_t* flags_out;        // [n_entries] == flags; written by K1 in device-RNG mode
   int32_t* ent_col;          // [n_entries]
   float* ent_val;            // [n_entries]

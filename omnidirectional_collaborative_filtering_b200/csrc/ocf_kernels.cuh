@@ -38,12 +38,26 @@ k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
   const int p0 = bt.ent_off[b];
   if (start == 0 && threadIdx.x == 0) bt.rowslot[row] = (bt.tag << SLOT_BITS) | (uint32_t)b;
   const int d0 = RNG ? bt.draw_off[b] : 0;
-  const double c0 = RNG ? bt.cdf0[b] : 0.0;
+  // the batch's slice of the stream: 4 header words (word 0 = alignment shift), then the draws
+  const uint32_t* W = RNG ? bt.words + 4 + bt.words[0] : nullptr;
+  __shared__ double s_c0;
+  if (RNG) {
+    if (threadIdx.x == 0) {
+      // the row's sparsity: draw (first row of the drawing unit + b) of np.random.uniform(lo, hi, size)
+      // (data_reader.py:120), then the cdf np.random.choice builds from p = [1-s, s] (:130)
+      const int r = bt.cdf_row0 + b;
+      const double u = mt_double(W[2 * r], W[2 * r + 1]);
+      const double keep = __dadd_rn(bt.rng_lo, __dmul_rn(bt.rng_range, u));   // random_uniform: lower + range * next_double
+      const double q0 = __dsub_rn(1.0, keep);
+      s_c0 = __ddiv_rn(q0, __dadd_rn(q0, keep));                             // cdf = cumsum(p) / cumsum(p)[-1]
+    }
+    __syncthreads();
+  }
+  const double c0 = RNG ? s_c0 : 0.0;
   auto flag_of = [&](int j) -> uint8_t {
     if (!RNG) return bt.flags[p0 + j];
-    const int d = d0 + (s.orig_pos != nullptr ? s.orig_pos[src0 + j] : j);
-    const uint2 w = *reinterpret_cast<const uint2*>(bt.words + 2 * (size_t)d);
-    return mt_double(w.x, w.y) >= c0 ? 1 : 0;
+    const size_t d = (size_t)(d0 + (s.orig_pos != nullptr ? s.orig_pos[src0 + j] : j));
+    return mt_double(W[2 * d], W[2 * d + 1]) >= c0 ? 1 : 0;
   };
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
     const int j = start + i;
@@ -82,9 +96,14 @@ k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
 //   i == 623 : new[623] = A(old[623], new[0]) ^ new[396]
 // all 624 of them independent: one barrier per regeneration (double-buffered in shared memory)
 // instead of three dependent sweeps, and every thread tempers and stores the words it produced.
-// The first `n_rows` draws are the batch's np.random.uniform(lo, hi, size=B) (data_reader.py:120):
-// their cdf (what np.random.choice builds from p=[1-s, s]) is computed here in IEEE double,
-// operation by operation like the host code.
+// The tempered words leave through a small ring in shared memory and TMA bulk stores
+// (cp.async.bulk shared -> global): ordinary global stores inside the loop made every barrier wait
+// for their acknowledgement (~0.3 us per regeneration, measured); the bulk copies run in the async
+// proxy and only the ring slot's reuse waits on them. `out` = 4 header words (word 0: the
+// alignment shift s in 0..3 that puts every regeneration on a 16-byte boundary), then word j of
+// the batch's draws at out[4 + s + j]; whole regenerations are stored, so `out` needs 1024 words of
+// slack. The batch's first draws are its np.random.uniform(lo, hi, size=B) (data_reader.py:120):
+// the gather kernel turns them into the rows' cdf.
 // state[0..623] = key, state[624] = pos (RandomState.get_state()[1:3]).
 // ============================================================================================
 __device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
@@ -105,38 +124,49 @@ __device__ __forceinline__ uint32_t mt_a(uint32_t cur, uint32_t nxt) {
 }
 
 constexpr int MT_THREADS = 320;            // 2 words per thread and regeneration
+constexpr int MT_RING = 4;                 // regenerations in flight towards HBM
+constexpr int MT_HDR = 4;                  // header words in front of the draws
+constexpr int MT_SLACK = 1024;             // words an output buffer holds beyond header + draws
 
 __global__ void __launch_bounds__(MT_THREADS)
-k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict__ out, int n_rows,
-           double lo, double range, double* __restrict__ cdf0) {
+k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict__ out) {
   __shared__ uint32_t mt[2][624];
+  __shared__ uint32_t tw[624];
+  __shared__ __align__(16) uint32_t ring[MT_RING][624];
   const int tid = threadIdx.x;
   for (int i = tid; i < 624; i += blockDim.x) mt[0][i] = state[i];
   int pos = (int)state[624];
   int cur = 0;
   __syncthreads();
-  long long w = 0;
-  // what is left of the current array
-  if (pos < 624) {
-    const int take = (int)min((long long)(624 - pos), n_words);
-    if (out != nullptr)
-      for (int i = tid; i < take; i += blockDim.x) out[i] = mt_temper(mt[0][pos + i]);
-    w = take;
+  long long left = n_words;
+  uint32_t* dst = nullptr;
+  // what is left of the current array (plain stores), shifted so that the regenerations that
+  // follow start on a 16-byte boundary
+  {
+    const int take = pos < 624 ? (int)min((long long)(624 - pos), n_words) : 0;
+    if (out != nullptr) {
+      const int shift = (4 - (take & 3)) & 3;
+      if (tid == 0) out[0] = (uint32_t)shift;
+      dst = out + MT_HDR + shift;
+      for (int i = tid; i < take; i += blockDim.x) dst[i] = mt_temper(mt[0][pos + i]);
+      dst += take;
+    }
+    left -= take;
     pos += take;
   }
-  // Whole regenerations. The single CTA is bound by instruction issue, so the twists A(i) are
-  // evaluated once into shared memory (first sweep) and combined by plain XORs (second sweep).
-  __shared__ uint32_t tw[624];
+  // Whole regenerations. The single CTA is bound by its barriers and by instruction issue: the
+  // twists A(i) are evaluated once into shared memory (first sweep) and combined by plain XORs
+  // (second sweep), and nothing in the loop waits on HBM.
   const int i0 = tid, i1 = tid + MT_THREADS;
-  long long left = n_words - w;                      // words still owed to the batch
-  uint32_t* dst = out != nullptr ? out + w : nullptr;
-  while (left > 0) {
+  for (int g = 0; left > 0; ++g) {
     const uint32_t* o = mt[cur];
     uint32_t* n = mt[cur ^ 1];
+    uint32_t* slot = ring[g % MT_RING];
     tw[i0] = mt_a(o[i0], o[i0 + 1]);                 // i0 < 320 <= 622
     if (i1 < 623) tw[i1] = mt_a(o[i1], o[i1 + 1]);
+    if (out != nullptr && tid == 0 && g >= MT_RING)  // the bulk store that last read this slot has its data
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(MT_RING - 1) : "memory");
     __syncthreads();
-    const int lim = left < 624 ? (int)left : 624;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int i = k == 0 ? i0 : i1;
@@ -147,26 +177,26 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
         else if (i < 623) v = tw[i] ^ tw[i - 227] ^ tw[i - 454] ^ o[i - 57];
         else v = mt_a(o[623], tw[0] ^ o[397]) ^ (tw[396] ^ tw[169] ^ o[566]);
         n[i] = v;
-        if (dst != nullptr && i < lim) dst[i] = mt_temper(v);
+        if (out != nullptr) slot[i] = mt_temper(v);
       }
     }
+    if (out != nullptr) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (out != nullptr && tid == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(slot)), "r"(624u * 4u) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    const int lim = left < 624 ? (int)left : 624;
     cur ^= 1;
     pos = lim;
     left -= lim;
-    if (dst != nullptr) dst += lim;
+    if (dst != nullptr) dst += 624;
   }
+  if (out != nullptr && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int i = tid; i < 624; i += blockDim.x) state[i] = mt[cur][i];
   if (tid == 0) state[624] = (uint32_t)pos;
-  if (out != nullptr && cdf0 != nullptr) {
-    for (int r = tid; r < n_rows; r += blockDim.x) {
-      const double u = mt_double(out[2 * r], out[2 * r + 1]);
-      const double keep = __dadd_rn(lo, __dmul_rn(range, u));        // random_uniform: lower + range * next_double
-      const double p0 = __dsub_rn(1.0, keep);
-      cdf0[r] = __ddiv_rn(p0, __dadd_rn(p0, keep));                  // cdf = cumsum(p) / cumsum(p)[-1]
-    }
-  }
 }
 
 // Fixed-split valid/test batches: a batch row is the input store's row followed by the target
