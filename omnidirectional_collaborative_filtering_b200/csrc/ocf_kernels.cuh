@@ -123,15 +123,23 @@ __device__ __forceinline__ uint32_t mt_a(uint32_t cur, uint32_t nxt) {
   return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
 
-constexpr int MT_THREADS = 320;            // 2 words per thread and regeneration
+constexpr int MT_THREADS = 160;            // 156 of them own 4 consecutive words of a regeneration
 constexpr int MT_RING = 4;                 // regenerations in flight towards HBM
 constexpr int MT_HDR = 4;                  // header words in front of the draws
 constexpr int MT_SLACK = 1024;             // words an output buffer holds beyond header + draws
 
+// One word of the new array from twists of the old one (see the derivation above). own = tw[i].
+__device__ __forceinline__ uint32_t mt_new_word(int i, uint32_t own, const uint32_t* __restrict__ o, const uint32_t* __restrict__ tw) {
+  if (i < 227) return own ^ o[i + 397];
+  if (i < 454) return own ^ tw[i - 227] ^ o[i + 170];
+  if (i < 623) return own ^ tw[i - 227] ^ tw[i - 454] ^ o[i - 57];
+  return mt_a(o[623], tw[0] ^ o[397]) ^ (tw[396] ^ tw[169] ^ o[566]);
+}
+
 __global__ void __launch_bounds__(MT_THREADS)
 k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict__ out) {
-  __shared__ uint32_t mt[2][624];
-  __shared__ uint32_t tw[624];
+  __shared__ __align__(16) uint32_t mt[2][624];
+  __shared__ __align__(16) uint32_t tw[624];
   __shared__ __align__(16) uint32_t ring[MT_RING][624];
   const int tid = threadIdx.x;
   for (int i = tid; i < 624; i += blockDim.x) mt[0][i] = state[i];
@@ -154,33 +162,35 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
     left -= take;
     pos += take;
   }
-  // Whole regenerations. The single CTA is bound by its barriers and by instruction issue: the
-  // twists A(i) are evaluated once into shared memory (first sweep) and combined by plain XORs
-  // (second sweep), and nothing in the loop waits on HBM.
-  const int i0 = tid, i1 = tid + MT_THREADS;
+  // Whole regenerations. A single CTA is bound by its two barriers, and a barrier pays for every
+  // shared-memory store still in flight: each thread owns 4 consecutive words, so a sweep ends
+  // in ONE 16-byte store per thread (5 warps), and nothing in the loop waits on HBM.
+  const int i = 4 * tid;
+  const bool active = i < 624;
   for (int g = 0; left > 0; ++g) {
     const uint32_t* o = mt[cur];
     uint32_t* n = mt[cur ^ 1];
     uint32_t* slot = ring[g % MT_RING];
-    tw[i0] = mt_a(o[i0], o[i0 + 1]);                 // i0 < 320 <= 622
-    if (i1 < 623) tw[i1] = mt_a(o[i1], o[i1 + 1]);
-    if (out != nullptr && tid == 0 && g >= MT_RING)  // the bulk store that last read this slot has its data
+    uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
+    if (active) {
+      const uint4 a = *reinterpret_cast<const uint4*>(o + i);
+      t4.x = mt_a(a.x, a.y); t4.y = mt_a(a.y, a.z); t4.z = mt_a(a.z, a.w);
+      if (i + 4 < 624) t4.w = mt_a(a.w, o[i + 4]);     // word 623 has no plain twist (it needs new[0])
+      *reinterpret_cast<uint4*>(tw + i) = t4;
+    }
+    if (out != nullptr && tid == 0 && g >= MT_RING)    // the bulk store that last read this slot has its data
       asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(MT_RING - 1) : "memory");
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int i = k == 0 ? i0 : i1;
-      if (i < 624) {
-        uint32_t v;
-        if (i < 227) v = tw[i] ^ o[i + 397];
-        else if (i < 454) v = tw[i] ^ tw[i - 227] ^ o[i + 170];
-        else if (i < 623) v = tw[i] ^ tw[i - 227] ^ tw[i - 454] ^ o[i - 57];
-        else v = mt_a(o[623], tw[0] ^ o[397]) ^ (tw[396] ^ tw[169] ^ o[566]);
-        n[i] = v;
-        if (out != nullptr) slot[i] = mt_temper(v);
+    if (active) {
+      uint4 v;
+      v.x = mt_new_word(i, t4.x, o, tw); v.y = mt_new_word(i + 1, t4.y, o, tw);
+      v.z = mt_new_word(i + 2, t4.z, o, tw); v.w = mt_new_word(i + 3, t4.w, o, tw);
+      *reinterpret_cast<uint4*>(n + i) = v;
+      if (out != nullptr) {
+        *reinterpret_cast<uint4*>(slot + i) = make_uint4(mt_temper(v.x), mt_temper(v.y), mt_temper(v.z), mt_temper(v.w));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
     }
-    if (out != nullptr) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (out != nullptr && tid == 0) {
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -195,7 +205,7 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
   }
   if (out != nullptr && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncthreads();
-  for (int i = tid; i < 624; i += blockDim.x) state[i] = mt[cur][i];
+  for (int k = tid; k < 624; k += blockDim.x) state[k] = mt[cur][k];
   if (tid == 0) state[624] = (uint32_t)pos;
 }
 
