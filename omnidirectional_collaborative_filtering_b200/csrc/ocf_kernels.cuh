@@ -123,7 +123,7 @@ __device__ __forceinline__ uint32_t mt_a(uint32_t cur, uint32_t nxt) {
   return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
 
-constexpr int MT_THREADS = 160;            // 156 of them own 4 consecutive words of a regeneration
+constexpr int MT_THREADS = 640;            // one word of a regeneration per thread (624 active)
 constexpr int MT_RING = 4;                 // regenerations in flight towards HBM
 constexpr int MT_HDR = 4;                  // header words in front of the draws
 constexpr int MT_SLACK = 1024;             // words an output buffer holds beyond header + draws
@@ -162,32 +162,25 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
     left -= take;
     pos += take;
   }
-  // Whole regenerations. A single CTA is bound by its two barriers, and a barrier pays for every
-  // shared-memory store still in flight: each thread owns 4 consecutive words, so a sweep ends
-  // in ONE 16-byte store per thread (5 warps), and nothing in the loop waits on HBM.
-  const int i = 4 * tid;
+  // Whole regenerations. A single CTA is bound by the latency of each thread's dependent
+  // instruction chain between the two barriers (measured: fewer, busier threads are slower), so
+  // every word gets its own thread and the shortest possible chain; nothing waits on HBM.
+  const int i = tid;
   const bool active = i < 624;
   for (int g = 0; left > 0; ++g) {
     const uint32_t* o = mt[cur];
     uint32_t* n = mt[cur ^ 1];
     uint32_t* slot = ring[g % MT_RING];
-    uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
-    if (active) {
-      const uint4 a = *reinterpret_cast<const uint4*>(o + i);
-      t4.x = mt_a(a.x, a.y); t4.y = mt_a(a.y, a.z); t4.z = mt_a(a.z, a.w);
-      if (i + 4 < 624) t4.w = mt_a(a.w, o[i + 4]);     // word 623 has no plain twist (it needs new[0])
-      *reinterpret_cast<uint4*>(tw + i) = t4;
-    }
+    uint32_t own = 0u;
+    if (i < 623) { own = mt_a(o[i], o[i + 1]); tw[i] = own; }     // word 623 has no plain twist (it needs new[0])
     if (out != nullptr && tid == 0 && g >= MT_RING)    // the bulk store that last read this slot has its data
       asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(MT_RING - 1) : "memory");
     __syncthreads();
     if (active) {
-      uint4 v;
-      v.x = mt_new_word(i, t4.x, o, tw); v.y = mt_new_word(i + 1, t4.y, o, tw);
-      v.z = mt_new_word(i + 2, t4.z, o, tw); v.w = mt_new_word(i + 3, t4.w, o, tw);
-      *reinterpret_cast<uint4*>(n + i) = v;
+      const uint32_t v = mt_new_word(i, own, o, tw);
+      n[i] = v;
       if (out != nullptr) {
-        *reinterpret_cast<uint4*>(slot + i) = make_uint4(mt_temper(v.x), mt_temper(v.y), mt_temper(v.z), mt_temper(v.w));
+        slot[i] = mt_temper(v);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
     }
