@@ -117,6 +117,8 @@ int ocf_rng_set_state(ocf_rng* rng, const uint32_t* key, int32_t pos);
 int ocf_rng_get_state(ocf_rng* rng, uint32_t* key, int32_t* pos);
 /* Advances the stream by n_draws doubles (a batch the generator drew but nobody consumed). */
 int ocf_rng_skip(ocf_rng* rng, int64_t n_draws);
+/* SM cycles and nanoseconds the generator kernel's last launch took (synchronises its stream). */
+int ocf_rng_last_timing(ocf_rng* rng, int64_t* sm_cycles, int64_t* nanoseconds);
 /* Column shards: orig_pos[e] = position of the shard's store entry e inside its full row. */
 int ocf_store_set_orig_pos(ocf_store* store, const int32_t* orig_pos);
 /* build_sparse_batch (data_reader.py:95-200) with the random split drawn ON THE DEVICE, bit for

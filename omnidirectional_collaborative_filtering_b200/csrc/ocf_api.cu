@@ -712,7 +712,7 @@ extern "C" int ocf_rng_create(ocf_rng** out) {
   *out = nullptr;
   ocf_rng* r = new ocf_rng();
   if (cudaGetDevice(&r->device) != cudaSuccess) { cudaGetLastError(); delete r; return fail(OCF_ERR_CUDA, "ocf_rng_create: no CUDA device"); }
-  int st = r->mem.get(&r->d_state, 625, true);
+  int st = r->mem.get(&r->d_state, 640, true);
   if (st) { delete r; return st; }
   if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) { r->mem.release(); delete r; return fail(OCF_ERR_CUDA, "ocf_rng_create: stream creation failed"); }
   *out = r;
@@ -743,6 +743,17 @@ extern "C" int ocf_rng_get_state(ocf_rng* r, uint32_t* key, int32_t* pos) {
   OCF_CUDA(cudaStreamSynchronize(r->stream));
   std::memcpy(key, tmp, sizeof(uint32_t) * 624);
   *pos = (int32_t)tmp[624];
+  return OCF_OK;
+}
+
+extern "C" int ocf_rng_last_timing(ocf_rng* r, int64_t* sm_cycles, int64_t* nanoseconds) {
+  OCF_REQUIRE(r && sm_cycles && nanoseconds, "ocf_rng_last_timing: null argument");
+  uint32_t tmp[4];
+  OCF_CUDA(cudaSetDevice(r->device));
+  OCF_CUDA(cudaMemcpyAsync(tmp, r->d_state + 626, sizeof(tmp), cudaMemcpyDeviceToHost, r->stream));
+  OCF_CUDA(cudaStreamSynchronize(r->stream));
+  *sm_cycles = (int64_t)(((uint64_t)tmp[1] << 32) | tmp[0]);
+  *nanoseconds = (int64_t)(((uint64_t)tmp[3] << 32) | tmp[2]);
   return OCF_OK;
 }
 

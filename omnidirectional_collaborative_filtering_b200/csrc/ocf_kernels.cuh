@@ -142,6 +142,9 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
   __shared__ __align__(16) uint32_t tw[624];
   __shared__ __align__(16) uint32_t ring[MT_RING][624];
   const int tid = threadIdx.x;
+  const long long clk0 = clock64();
+  unsigned long long ns0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
   for (int i = tid; i < 624; i += blockDim.x) mt[0][i] = state[i];
   int pos = (int)state[624];
   int cur = 0;
@@ -199,7 +202,15 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
   if (out != nullptr && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int k = tid; k < 624; k += blockDim.x) state[k] = mt[cur][k];
-  if (tid == 0) state[624] = (uint32_t)pos;
+  if (tid == 0) {
+    state[624] = (uint32_t)pos;
+    // diagnostics of the last launch: SM cycles and nanoseconds it took (ocf_rng_last_timing)
+    unsigned long long ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+    const unsigned long long cyc = (unsigned long long)(clock64() - clk0), ns = ns1 - ns0;
+    state[626] = (uint32_t)cyc; state[627] = (uint32_t)(cyc >> 32);
+    state[628] = (uint32_t)ns; state[629] = (uint32_t)(ns >> 32);
+  }
 }
 
 // Fixed-split valid/test batches: a batch row is the input store's row followed by the target

@@ -26,6 +26,10 @@ t0 = time.perf_counter()
 _lib.check(lib.ocf_rng_skip(rng, n))
 _lib.check(lib.ocf_rng_get_state(rng, _lib.ptr(out_key), C.byref(pos)))
 dt = time.perf_counter() - t0
+cyc, ns = C.c_int64(), C.c_int64()
+_lib.check(lib.ocf_rng_last_timing(rng, C.byref(cyc), C.byref(ns)))
+print("in-kernel: %d SM cycles, %.2f ms -> %.0f MHz, %.0f cycles per regeneration" %
+      (cyc.value, ns.value / 1e6, cyc.value / max(ns.value, 1) * 1e3, cyc.value / (2 * n / 624)))
 rs.random_sample(1000 + n)
 want = rs.get_state()
 ok = np.array_equal(want[1], out_key) and want[2] == pos.value
