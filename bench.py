@@ -436,8 +436,12 @@ def main():
     kernels = {tag_names[t]: {"ms": tag_ms[t], "algorithmic_bytes": alg[t], "GB/s": alg[t] / (tag_ms[t] * 1e-3) / 1e9 if tag_ms[t] > 0 else None}
                for t in range(5)}
     achieved = alg[dom] / (tag_ms[dom] * 1e-3) / 1e9
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel on this workload
+    traffic = 762.8e6 if (args.workload == "ml10m" and B == 128 and dom == 4) else None
     roofline = {"kernel": tag_names[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/r01_ncu_full_k_row_update_v2.txt (dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None,
+                "algorithmic_bytes": alg[dom], "peak_source": peak_src,
                 "share_of_step": tag_ms[dom] / (ms / K)}
 
     # ---- e2e: the public API, host buffers in, metrics out, every step ---------------------------
