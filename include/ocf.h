@@ -68,8 +68,8 @@ int ocf_host_free(void* ptr);
  * by the caller: `col` already holds dense columns). Rows keep their stored order: draw j of
  * the reciprocal dropout belongs to the j-th stored rating (data_reader.py:130-134).
  * Repeated columns inside a row are allowed and resolve last-write-wins like the dense fills
- * at data_reader.py:158-169. `build_csc` != 0 also builds the column-major index the training
- * update needs (stores that only feed evaluation can skip it).
+ * at data_reader.py:158-169. `build_csc` != 0 marks a store that will be trained on: if some row
+ * repeats a column, the column-major index the training update then needs is built too.
  * Limits: nnz < 2^31, n_cols < 2^31. */
 int ocf_store_create(int64_t n_rows, int64_t n_cols, const int64_t* rowptr, const int32_t* col,
                      const float* val, int build_csc, ocf_store** out);

@@ -380,7 +380,9 @@ extern "C" int ocf_store_create(int64_t n_rows, int64_t n_cols, const int64_t* r
       return bail(fail(OCF_ERR_CUDA, "ocf_store_create: upload failed"));
   }
   s->dev.rowptr = d_rowptr; s->dev.col = d_col; s->dev.val = d_val; s->dev.next_dup = d_nd;
-  if (build_csc) {
+  if (build_csc && s->has_dups) {
+    // (only stores whose rows repeat a column train through the CSC scan; all others build their
+    // update work list from the batch alone and never need the column-major index)
     // counting sort in CSR order: entries of a column come out ordered by (row, position)
     std::vector<int64_t> colptr((size_t)n_cols + 1, 0);
     for (int64_t e = 0; e < nnz; ++e) colptr[(size_t)col[e] + 1]++;
@@ -969,8 +971,8 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
     if (l == 0) { ly.fan_in = m->nblk * N; ly.fan_out = cfg->widths[0]; ly.rows = m->nblk * N; ly.hp = m->hp[0]; ly.bias_len = m->hp[0]; }
     else if (l < L) { ly.fan_in = cfg->widths[l - 1]; ly.fan_out = cfg->widths[l]; ly.rows = m->hp[l - 1]; ly.hp = m->hp[l]; ly.bias_len = m->hp[l]; }
     else { ly.fan_in = cfg->widths[L - 1]; ly.fan_out = N; ly.rows = N; ly.hp = m->hp[L - 1]; ly.bias_len = N; }
-    // the decoder kernel is padded (zeros) to whole 128-column tiles of the scoring GEMM
-    st = m->mem.get(&ly.W, (l == L ? align_up((size_t)ly.rows, tc::TILE_M) : (size_t)ly.rows) * ly.hp, true);
+    // the decoder kernel is padded (zeros) to whole 256-column pair tiles of the scoring GEMM
+    st = m->mem.get(&ly.W, (l == L ? align_up((size_t)ly.rows, 2 * tc::TILE_M) : (size_t)ly.rows) * ly.hp, true);
     if (!st) st = m->mem.get(&ly.b, (size_t)ly.bias_len, true);
   }
   if (st) return bail(st);
@@ -1873,22 +1875,30 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   const Layer& dec = m->layers[L];
   const int hpt = m->hp[L - 1];
   static const bool trunc = std::getenv("OCF_TC_TRUNCATE") != nullptr;   // diagnostic: let the MMA truncate fp32 -> tf32
+  static const bool single = std::getenv("OCF_TC_1CTA") != nullptr;     // diagnostic: the one-SM kernel instead of CTA pairs
   if (!m->map_w_ok) {
-    OCF_TRY(tc::make_map(&m->map_w, dec.W, hpt, (long long)align_up((size_t)m->cfg.n_cols, tc::TILE_M), tc::TILE_M, !trunc));
+    OCF_TRY(tc::make_map(&m->map_w, dec.W, hpt, (long long)align_up((size_t)m->cfg.n_cols, 2 * tc::TILE_M), tc::TILE_M, !trunc));
     m->map_w_ok = true;
   }
   const int nb = tc::chunk_rows(B);
-  if (!m->map_h_ok || m->map_h_box != nb) {
-    OCF_TRY(tc::make_map(&m->map_h, m->act[L - 1], hpt, m->act_rows, nb, !trunc));
-    m->map_h_ok = true; m->map_h_box = nb;
+  const int box = single ? nb : nb / 2;           // a CTA of a pair loads half of the batch-row operand
+  if (!m->map_h_ok || m->map_h_box != box) {
+    OCF_TRY(tc::make_map(&m->map_h, m->act[L - 1], hpt, m->act_rows, box, !trunc));
+    m->map_h_ok = true; m->map_h_box = box;
   }
   tc::ScoreArgs sa{};
   sa.bias = dec.b; sa.out = dst; sa.ldo = m->cfg.n_cols; sa.n_cols = m->cfg.n_cols; sa.n_rows = B;
   sa.num_k = hpt / tc::BLOCK_K; sa.n_mtiles = (m->cfg.n_cols + tc::TILE_M - 1) / tc::TILE_M; sa.n_chunks = (B + nb - 1) / nb;
   g_prof.begin(4, st);
-  if (nb == 64) OCF_TRY(tc::launch_score_nb<64>(m->map_w, m->map_h, sa, m->sm_count, st));
-  else if (nb == 128) OCF_TRY(tc::launch_score_nb<128>(m->map_w, m->map_h, sa, m->sm_count, st));
-  else OCF_TRY(tc::launch_score_nb<256>(m->map_w, m->map_h, sa, m->sm_count, st));
+  if (single) {
+    if (nb == 64) OCF_TRY(tc::launch_score_nb<64>(m->map_w, m->map_h, sa, m->sm_count, st));
+    else if (nb == 128) OCF_TRY(tc::launch_score_nb<128>(m->map_w, m->map_h, sa, m->sm_count, st));
+    else OCF_TRY(tc::launch_score_nb<256>(m->map_w, m->map_h, sa, m->sm_count, st));
+  } else {
+    if (nb == 64) OCF_TRY(tc::launch_score_pair_nb<64>(m->map_w, m->map_h, sa, m->sm_count, st));
+    else if (nb == 128) OCF_TRY(tc::launch_score_pair_nb<128>(m->map_w, m->map_h, sa, m->sm_count, st));
+    else OCF_TRY(tc::launch_score_pair_nb<256>(m->map_w, m->map_h, sa, m->sm_count, st));
+  }
   g_prof.end(4, st);
   if (!out_is_device) {
     OCF_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * (size_t)B * m->cfg.n_cols, cudaMemcpyDeviceToHost, st));

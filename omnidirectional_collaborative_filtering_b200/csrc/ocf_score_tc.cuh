@@ -238,6 +238,184 @@ k_score_tc(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
   }
 }
 
+// ============================================================================================
+// The same GEMM on CTA pairs (tcgen05 cta_group::2, thread-block cluster of 2): the two SMs of a
+// pair compute one 256-column x NB-row tile. Each CTA loads its own 128 catalogue columns of A
+// and HALF of the batch-row operand B; the pair's tensor cores read both halves, so the operand
+// bytes per MMA drop from 48 KB to 32 KB per SM and k-block - the single-CTA kernel is bound by
+// exactly that feed (profiles/r01_ncu_full_k_score_tc_v1.txt). Protocol:
+//   * TMA of both CTAs completes on the LEADER's (cluster rank 0) full barrier;
+//   * the leader's elected thread issues the MMAs for the pair and commits with a multicast
+//     arrive, which frees the smem stage in both CTAs and hands the accumulator to both epilogues;
+//   * each CTA drains its own 128 TMEM lanes; all 8 epilogue warps of the pair arrive on the
+//     leader's accumulator-empty barrier (the peer's through a cluster-mapped address).
+// ============================================================================================
+template <int NB>
+struct ScoreCfg2 {
+  static_assert(NB == 64 || NB == 128 || NB == 256, "batch chunk must be 64, 128 or 256 rows");
+  static constexpr int A_BYTES = TILE_M * BLOCK_K * 4;
+  static constexpr int B_BYTES = (NB / 2) * BLOCK_K * 4;                 // this CTA's half of the batch rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * NB;
+  // M = 256 over the pair, N = NB
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) |
+                                    ((uint32_t)((2 * TILE_M) >> 4) << 24);
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far are done.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <int NB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+k_score_tc2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h, ScoreArgs a) {
+  using C = ScoreCfg2<NB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                      // [STAGES] used in the leader: TMA of both CTAs -> MMA
+  uint64_t* empty = bars + C::STAGES;         // [STAGES] in each CTA: MMA -> this CTA's TMA
+  uint64_t* tfull = bars + 2 * C::STAGES;     // [2] in each CTA: MMA -> this CTA's epilogue
+  uint64_t* tempty = tfull + 2;               // [2] used in the leader: both epilogues -> MMA
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_ptiles = (a.n_mtiles + 1) / 2;              // 256-column tiles
+  const int total = n_ptiles * a.n_chunks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                      // both CTAs' barriers exist before anything arrives remotely
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_holder);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        const int m = t / a.n_chunks, n = t - m * a.n_chunks;
+        for (int k = 0; k < a.num_k; ++k) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          const uint32_t lbar = map_to_rank(&full[stage], 0);
+          if (leader) mbar_expect_tx(&full[stage], 2u * (uint32_t)C::STAGE_BYTES);   // this CTA's boxes + the peer's
+          tma_load_2d_pair(sa, &map_w, lbar, k * BLOCK_K, (2 * m + (int)rank) * TILE_M);
+          tma_load_2d_pair(sa + C::A_BYTES, &map_h, lbar, k * BLOCK_K, n * NB + (int)rank * (NB / 2));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NB);
+        for (int k = 0; k < a.num_k; ++k) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          const uint64_t da = make_desc(sa), db = make_desc(sa + C::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+            umma_tf32_pair(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), C::IDESC, (uint32_t)((k | kk) != 0));
+          umma_commit_pair(&empty[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&tfull[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = pair; t < total; t += n_pairs) {
+      const int m = t / a.n_chunks, n = t - m * a.n_chunks;
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
+      const int c = (2 * m + (int)rank) * TILE_M + q * 32 + lane;
+      const bool cok = c < a.n_cols;
+      const float bv = cok ? __ldg(a.bias + c) : 0.f;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NB);
+#pragma unroll 1
+      for (int j = 0; j < NB / 32; ++j) {
+        const int row0 = n * NB + j * 32;
+        if (row0 >= a.n_rows) break;          // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)(j * 32), r);
+        tmem_wait_ld();
+        float* dst = a.out + (long long)row0 * a.ldo + c;
+        const int nr = min(32, a.n_rows - row0);
+        if (cok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nr) __stcs(dst + (long long)i * a.ldo, __uint_as_float(r[i]) + bv);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_rank(&tempty[acc], 0));
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                      // the peer may still be reading this CTA's operands / signalling its barriers
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host side: tensor maps through the driver entry point (libcuda is not linked) -----------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -283,6 +461,21 @@ inline int launch_score_nb(const CUtensorMap& mw, const CUtensorMap& mh, const S
   const int total = a.n_mtiles * a.n_chunks;
   const int grid = total < sm_count ? total : sm_count;
   k_score_tc<NB><<<grid, NTHREADS, C::SMEM, st>>>(mw, mh, a);
+  OCF_LAUNCHED();
+  return OCF_OK;
+}
+
+template <int NB>
+inline int launch_score_pair_nb(const CUtensorMap& mw, const CUtensorMap& mh, const ScoreArgs& a, int sm_count, cudaStream_t st) {
+  using C = ScoreCfg2<NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCF_CUDA(cudaFuncSetAttribute(k_score_tc2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  const int total = ((a.n_mtiles + 1) / 2) * a.n_chunks;
+  const int pairs = total < sm_count / 2 ? total : sm_count / 2;
+  k_score_tc2<NB><<<2 * pairs, NTHREADS, C::SMEM, st>>>(mw, mh, a);
   OCF_LAUNCHED();
   return OCF_OK;
 }
