@@ -75,6 +75,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// One lane of a converged warp (the warp stays converged around the elected work, so the
+// barrier waits and loop counters run on the uniform datapath: a role loop written under
+// `if (lane == 0)` made the single issuing thread the bottleneck - ~1650 cycles per k-block of
+// scalarised descriptor moves against 512 cycles of tensor work, profiles/r01 score v2).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -161,42 +174,44 @@ k_score_tc(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_holder);
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int m = t / a.n_chunks, n = t - m * a.n_chunks;
-        for (int k = 0; k < a.num_k; ++k) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int m = t / a.n_chunks, n = t - m * a.n_chunks;
+      for (int k = 0; k < a.num_k; ++k) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           mbar_expect_tx(&full[stage], (uint32_t)C::STAGE_BYTES);
           tma_load_2d(sa, &map_w, &full[stage], k * BLOCK_K, m * TILE_M);
           tma_load_2d(sa + C::A_BYTES, &map_h, &full[stage], k * BLOCK_K, n * NB);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NB);
+      for (int k = 0; k < a.num_k; ++k) {
+        mbar_wait(&full[stage], phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NB);
-        for (int k = 0; k < a.num_k; ++k) {
-          mbar_wait(&full[stage], phase);
-          tcgen05_fence_after();
+        if (elect_one()) {
           const uint8_t* sa = smem + stage * C::STAGE_BYTES;
           const uint64_t da = make_desc(sa), db = make_desc(sa + C::A_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)   // +32 bytes along K inside the swizzle row
             umma_tf32(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), C::IDESC, (uint32_t)((k | kk) != 0));
           umma_commit(&empty[stage]);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          if (k == a.num_k - 1) umma_commit(&tfull[acc]);
         }
-        umma_commit(&tfull[acc]);
-        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     const int q = warp & 3;                   // the TMEM lane quarter this warp may read
@@ -338,23 +353,24 @@ k_score_tc2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_holder);
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = pair; t < total; t += n_pairs) {
-        const int m = t / a.n_chunks, n = t - m * a.n_chunks;
-        for (int k = 0; k < a.num_k; ++k) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = pair; t < total; t += n_pairs) {
+      const int m = t / a.n_chunks, n = t - m * a.n_chunks;
+      for (int k = 0; k < a.num_k; ++k) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           const uint32_t lbar = map_to_rank(&full[stage], 0);
           if (leader) mbar_expect_tx(&full[stage], 2u * (uint32_t)C::STAGE_BYTES);   // this CTA's boxes + the peer's
           tma_load_2d_pair(sa, &map_w, lbar, k * BLOCK_K, (2 * m + (int)rank) * TILE_M);
           tma_load_2d_pair(sa + C::A_BYTES, &map_h, lbar, k * BLOCK_K, n * NB + (int)rank * (NB / 2));
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = pair; t < total; t += n_pairs) {
@@ -364,15 +380,18 @@ k_score_tc2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
         for (int k = 0; k < a.num_k; ++k) {
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
-          const uint8_t* sa = smem + stage * C::STAGE_BYTES;
-          const uint64_t da = make_desc(sa), db = make_desc(sa + C::A_BYTES);
+          if (elect_one()) {
+            const uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            const uint64_t da = make_desc(sa), db = make_desc(sa + C::A_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-            umma_tf32_pair(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), C::IDESC, (uint32_t)((k | kk) != 0));
-          umma_commit_pair(&empty[stage]);
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+              umma_tf32_pair(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), C::IDESC, (uint32_t)((k | kk) != 0));
+            umma_commit_pair(&empty[stage]);
+            if (k == a.num_k - 1) umma_commit_pair(&tfull[acc]);
+          }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_pair(&tfull[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
