@@ -8,8 +8,8 @@
 // K-major in HBM already (WdecT [N, hp] and h [rows, hp], fp32 read as tf32), so TMA drops
 // 128-byte-swizzled [rows x 32] boxes straight into the layout the MMA descriptors name.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer
-// (one lane), warps 2..5 = epilogue (TMEM -> registers -> +bias -> HBM).  Two accumulator stages
+// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM owner + MMA
+// issuer (one elected lane), warps 2..9 = epilogue (TMEM -> registers -> +bias -> HBM).  Two accumulator stages
 // in TMEM let the epilogue of tile t overlap the MMAs of tile t+1; a ring of smem stages
 // decouples TMA from the MMAs.  Persistent: grid = min(#SM, tiles), tiles strided over the CTAs.
 #pragma once
@@ -24,7 +24,8 @@ namespace tc {
 constexpr int TILE_M = 128;    // catalogue columns per tile = UMMA M
 constexpr int BLOCK_K = 32;    // tf32 elements per 128-byte swizzle row
 constexpr int UMMA_K = 8;      // tf32 elements one tcgen05.mma consumes along K (32 bytes)
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 8;    // two warps per TMEM lane quarter, each draining every other 32-row chunk
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 
 template <int NB>
 struct ScoreCfg {
@@ -185,7 +186,7 @@ k_score_tc(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -249,7 +250,7 @@ k_score_tc(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
       const float bv = cok ? __ldg(a.bias + c) : 0.f;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NB);
 #pragma unroll 1
-      for (int j = 0; j < NB / 32; ++j) {
+      for (int j = (warp - 2) >> 2; j < NB / 32; j += EPI_WARPS / 4) {
         const int row0 = n * NB + j * 32;
         if (row0 >= a.n_rows) break;          // warp-uniform
         uint32_t r[32];
@@ -358,7 +359,7 @@ k_score_tc2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 2 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -425,7 +426,7 @@ k_score_tc2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
       const float bv = cok ? __ldg(a.bias + c) : 0.f;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NB);
 #pragma unroll 1
-      for (int j = 0; j < NB / 32; ++j) {
+      for (int j = (warp - 2) >> 2; j < NB / 32; j += EPI_WARPS / 4) {
         const int row0 = n * NB + j * 32;
         if (row0 >= a.n_rows) break;          // warp-uniform
         uint32_t r[32];
