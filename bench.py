@@ -142,8 +142,10 @@ def scoring_run(lib, m, rd, w, aux, rows, reps, warm):
             "e2e": {"value": rows / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(devs[0].info()["h2d_bytes"]),
                     "d2h_bytes_per_step": int(res.nbytes), "ms_per_call": 1e3 * e2e_s,
                     "note": "bounded by the PCIe read-back of the [rows, N] float32 score matrix"},
-            "roofline": {"kernel": "k_score_tc (tcgen05 kind::tf32)", "bound": "tensor", "achieved": flops / (gemm_ms * 1e-3) / 1e12,
-                         "peak": peak, "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak, "traffic": None,
+            "roofline": {"kernel": "k_score_tc2 (tcgen05 cta_group::2 kind::tf32)", "bound": "tensor", "achieved": flops / (gemm_ms * 1e-3) / 1e12,
+                         "peak": peak, "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak,
+                         # DRAM bytes per launch of the committed ncu --set full capture (profiles/r01_ncu_full_k_score_tc2_v3.txt)
+                         "traffic": 389.3e6 if (rows == 1024 and N == 71567 and hp == 512) else None,
                          "peak_source": src, "kernel_ms": gemm_ms, "share_of_step": gemm_ms / ms,
                          "out_GBs": 4.0 * rows * N / (gemm_ms * 1e-3) / 1e9}}
 
