@@ -137,7 +137,16 @@ def scoring_run(lib, m, rd, w, aux, rows, reps, warm):
     for k in range(n_e2e):
         res = m.score(batches[k % len(batches)], reuse_output=True)     # page-locked destination
     e2e_s = (time.perf_counter() - t0) / n_e2e
+    # top-k serving (k = 100, seen items excluded): selection on the device, k pairs per row back
+    m.recommend(batches[0], k=100)
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        top_cols, top_scores = m.recommend(batches[k % len(batches)], k=100, exclude_seen=True)
+    topk_s = (time.perf_counter() - t0) / n_e2e
     return {"rows_per_call": rows, "n_cols": int(N), "value": rows / (ms * 1e-3), "unit": "rows/s", "ms_per_call": ms,
+            "topk": {"k": 100, "e2e_value": rows / topk_s, "unit": "rows/s", "ms_per_call": 1e3 * topk_s,
+                     "d2h_bytes_per_step": int(top_cols.nbytes + top_scores.nbytes),
+                     "note": "ocf_score_topk through model.recommend: host row ids in, 100 (column, score) pairs per row out"},
             "gpu_launches": int(launches),
             "e2e": {"value": rows / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(devs[0].info()["h2d_bytes"]),
                     "d2h_bytes_per_step": int(res.nbytes), "ms_per_call": 1e3 * e2e_s,

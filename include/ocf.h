@@ -238,6 +238,14 @@ int ocf_predict(ocf_model* model, ocf_batch* batch, float* out, void* stream);
  * before the mask multiply). `out_is_device` != 0: out is a device pointer and the call does
  * not synchronise. */
 int ocf_score(ocf_model* model, ocf_batch* batch, float* out, int out_is_device, void* stream);
+/* Top-k serving epilogue on top of ocf_score: for every batch row the k
+ * (<= 512) highest full-catalogue scores and their columns, best first (ties: lower column first),
+ * selected on the device so that k pairs per row cross PCIe instead of n_cols scores.
+ * exclude_inputs != 0 drops the columns the row holds as inputs (what the user has rated already).
+ * out_cols int32[rows, k], out_scores float[rows, k] (host). Slots beyond the available columns
+ * hold column -1 / score -inf. Column shards return their own columns' top k (local ids). */
+int ocf_score_topk(ocf_model* model, ocf_batch* batch, int32_t k, int exclude_inputs,
+                   int32_t* out_cols, float* out_scores, void* stream);
 /* Copies `count` metric records starting at step slot `first` of the device log to the host
  * (synchronises `stream`). The log keeps the last 4096 steps. */
 int ocf_model_read_metrics(ocf_model* model, int64_t first, int32_t count, float* host,

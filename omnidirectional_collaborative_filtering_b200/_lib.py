@@ -102,6 +102,7 @@ _SIGNATURES = {
     "ocf_eval_step": (C.c_int, [_P, _P, C.POINTER(StepArgs), _P, _P]),
     "ocf_predict": (C.c_int, [_P, _P, _P, _P]),
     "ocf_score": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "ocf_score_topk": (C.c_int, [_P, _P, C.c_int32, C.c_int, _P, _P, _P]),
     "ocf_model_read_metrics": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "ocf_model_wait_metrics": (C.c_int, [_P, C.c_int64, _P]),
     "ocf_model_steps_logged": (C.c_int64, [_P]),

@@ -12,6 +12,7 @@
 #include "ocf_kernels.cuh"
 #include "ocf_score_tc.cuh"
 #include "ocf_peer.cuh"
+#include "ocf_topk.cuh"
 
 namespace ocf {
 
@@ -211,6 +212,9 @@ struct ocf_model {
   int4* col_tasks = nullptr;
   int* col_counters = nullptr;
   float* gemm_part = nullptr;     // split-K partials of the hidden-layer GEMMs
+  int32_t* topk_cols = nullptr;   // top-k epilogue outputs [max_rows, 512] (allocated with dense_out's arena)
+  float* topk_scores = nullptr;
+  size_t topk_cap = 0;
   int* col_state = nullptr;       // batch-side K4a: [3][n_cols] per-column count / code OR / claimed, zeroed per step
   int4* col_info = nullptr;       //   [n_cols]
   uint32_t* col_bits = nullptr;   //   presence bitmap [min(n_cols, max_entries)][ceil(max_rows / 32)]
@@ -911,6 +915,7 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   m->ws_mem.release();
   m->dense_mem.release();
   m->dense_out = nullptr;
+  m->topk_cols = nullptr; m->topk_scores = nullptr; m->topk_cap = 0;
   m->cfg.max_rows = max_rows;
   m->cfg.max_entries = max_entries;
   m->max_items = max_items_for(max_rows, max_entries);
@@ -1904,6 +1909,34 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
     OCF_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * (size_t)B * m->cfg.n_cols, cudaMemcpyDeviceToHost, st));
     OCF_CUDA(cudaStreamSynchronize(st));
   }
+  return OCF_OK;
+}
+
+extern "C" int ocf_score_topk(ocf_model* m, ocf_batch* b, int32_t k, int exclude_inputs, int32_t* out_cols, float* out_scores,
+                              void* stream_) {
+  OCF_TRY(check_step(m, b, false));
+  OCF_REQUIRE(out_cols && out_scores, "ocf_score_topk: null output");
+  OCF_REQUIRE(k >= 1 && k <= TOPK_MAX, "ocf_score_topk: k must be in 1..512");
+  cudaStream_t st = as_stream(stream_);
+  const int B = b->dev.B;
+  OCF_TRY(ensure_dense(m));
+  if (m->topk_cap < (size_t)m->cfg.max_rows * TOPK_MAX) {
+    OCF_TRY(m->dense_mem.get(&m->topk_cols, (size_t)m->cfg.max_rows * TOPK_MAX));
+    OCF_TRY(m->dense_mem.get(&m->topk_scores, (size_t)m->cfg.max_rows * TOPK_MAX));
+    m->topk_cap = (size_t)m->cfg.max_rows * TOPK_MAX;
+  }
+  OCF_TRY(ocf_score(m, b, m->dense_out, 1, stream_));          // full scores stay in HBM
+  if (exclude_inputs && b->dev.n_items > 0) {
+    k_exclude_inputs<<<b->dev.n_items, 128, 0, st>>>(b->dev, m->dense_out, (long long)m->cfg.n_cols);
+    OCF_LAUNCHED();
+  }
+  g_prof.begin(6, st);
+  k_topk<<<B, TOPK_THREADS, 0, st>>>(m->dense_out, (long long)m->cfg.n_cols, m->cfg.n_cols, k, m->topk_cols, m->topk_scores);
+  OCF_LAUNCHED();
+  g_prof.end(6, st);
+  OCF_CUDA(cudaMemcpyAsync(out_cols, m->topk_cols, sizeof(int32_t) * (size_t)B * k, cudaMemcpyDeviceToHost, st));
+  OCF_CUDA(cudaMemcpyAsync(out_scores, m->topk_scores, sizeof(float) * (size_t)B * k, cudaMemcpyDeviceToHost, st));
+  OCF_CUDA(cudaStreamSynchronize(st));
   return OCF_OK;
 }
 

@@ -305,6 +305,23 @@ class OmniNet(object):
         _lib.check(_lib.lib().ocf_score(h, dev.handle, _lib.ptr(out), 0, self.stream))
         return out
 
+    def recommend(self, batch, k=10, exclude_seen=True):
+        """The k best catalogue columns of every batch row by full-catalogue score, best first
+        (ties: lower column first), selected on the device: (columns int32 [B, k], scores float32
+        [B, k]). `exclude_seen` drops the columns a row holds as inputs. Slots beyond the available
+        columns hold column -1 / score -inf. A column shard returns the top k of its own columns
+        (global column ids); merging the shards' lists is the caller's k-way merge."""
+        h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
+        dev = batch.upload(self.stream)
+        self._shard_encode(h, dev, batch)
+        cols = np.empty((batch.n_rows, int(k)), dtype=np.int32)
+        scores = np.empty((batch.n_rows, int(k)), dtype=np.float32)
+        _lib.check(_lib.lib().ocf_score_topk(h, dev.handle, int(k), int(bool(exclude_seen)), _lib.ptr(cols),
+                                             _lib.ptr(scores), self.stream))
+        if self.owner.col_lo:
+            cols[cols >= 0] += self.owner.col_lo
+        return cols, scores
+
     def _shard_encode(self, h, dev, batch):
         """Column shards: encoder partial sums + their all-reduce before predict/score (this
         rank's output then holds its own columns)."""

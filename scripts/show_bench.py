@@ -20,6 +20,8 @@ if "scoring" in d:
         print("scoring: %.2f M rows/s (%d rows/call, %.3f ms) | gemm %.0f TFLOP/s = %.3f of %.0f | e2e %.0f rows/s" % (
             s["value"] / 1e6, s["rows_per_call"], s["ms_per_call"], s["roofline"]["achieved"], s["roofline"]["frac"],
             s["roofline"]["peak"], s["e2e"]["value"]))
+        if "topk" in s:
+            print("         top-%d e2e %.2f M rows/s (%.3f ms/call)" % (s["topk"]["k"], s["topk"]["e2e_value"] / 1e6, s["topk"]["ms_per_call"]))
 if "cpu_baseline" in d:
     print("cpu_baseline", d["cpu_baseline"])
 print("clocks", d.get("clocks"))
