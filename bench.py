@@ -341,7 +341,9 @@ def main():
     torch.cuda.set_device(0)
     lib = _lib.lib()
     fs = make_dataset(w)
-    rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):     # the reader prints the reference's "Finished loading data"
+        rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs)
     aux = w["aux"]
     np.random.seed(0)
     om = omni_model(w["layers"], w["hidden"], fs.n_cols, B, dense_activation=w["act"], use_causal_info=aux is not None,

@@ -203,8 +203,11 @@ def bench_main(args, w, cfg, rank, world):
     if fs is None:
         fs = bench.make_dataset(w)
     native = NativeComm()
-    rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs,
-                     shard=None if rows_mode else (rank, world))
+    import contextlib
+    import sys
+    with contextlib.redirect_stdout(sys.stderr):     # the reader prints the reference's "Finished loading data"
+        rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs,
+                         shard=None if rows_mode else (rank, world))
     aux = w["aux"]
     np.random.seed(0)
     mkw = dict(dense_activation=w["act"], use_causal_info=aux is not None, use_both_masks=aux == "both",
