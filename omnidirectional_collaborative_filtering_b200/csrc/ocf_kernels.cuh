@@ -1,15 +1,19 @@
 // Hand-written sm_100a kernels of the training / scoring hot path.
 //
 // Data layout in HBM:
-//   * rating store: CSR (rowptr i64, col i32, val f32) + CSC index (colptr i64, crow i32, cj i32)
+//   * rating store: CSR (rowptr i64, col i32, val f32); a CSC index (colptr i64, crow i32, cj i32)
+//     only for stores whose rows repeat a column
 //   * encoder kernel  Wenc  [k*N, HP]  (Keras layout, fan_out padded to a multiple of 128)
 //   * decoder kernel  WdecT [N, HP]    (TRANSPOSED Keras layout: one contiguous row per
 //     catalogue column, so the loss at an observed entry is one coalesced 4*HP-byte read)
 //   * activations [B, HP] fp32
 // Every catalogue-wide operation is therefore a gather of 4*HP-byte rows: row-centric kernels
-// (one work item = a chunk of one batch row's ratings) for the activation-side products,
-// a column-centric kernel (one warp per catalogue column) for the weight-side products fused
-// with the optimizer update. All reductions run in a fixed order (no float atomics).
+// (one work item = a chunk of one batch row's ratings) for the activation-side products, and for
+// the weight-side products a work list of (catalogue column, array) tasks - built from the batch
+// by a counting sort (k_sort_*) - that a persistent kernel (k_row_update, one warp per task)
+// turns into gradient rows fused with the optimizer update. All floating-point reductions run in
+// a fixed order (no float atomics). The tensor-core scoring GEMM, the peer-memory exchanges and
+// the top-k epilogue live in ocf_score_tc.cuh, ocf_peer.cuh and ocf_topk.cuh.
 #pragma once
 
 #include "ocf_common.cuh"
@@ -677,8 +681,10 @@ k_gemm_reduce(int M, int N, int S, GemmEpi ep) {
 }
 
 // ============================================================================================
-// K4: weight-side products fused with the optimizer update, in two kernels.
+// K4: weight-side products fused with the optimizer update: a work list, then the update.
 //
+// (work list)  normally built from the batch alone by k_sort_* further down; for stores whose
+//              rows repeat a column by k_col_scan:
 // k_col_scan   streams the store's CSC row ids once. A CTA owns a group of consecutive catalogue
 //              columns (<= SCAN_T entries, or one longer column) and tests every entry's row
 //              against a shared-memory bitmap of the batch's rows. The matches (~1 % of the
