@@ -229,6 +229,30 @@ def touched(batch, k_mask_blocks):
     return u_in, u_tg, int(f.sum()), int(cols.size if batch.pass_through else (~f).sum())
 
 
+def step_bytes(plans, w, nnz_store, n_obs_sample=8):
+    """Algorithmic bytes of one train step's kernels, mean over `plans`:
+    [K1, K2, K3, K4a, K4b]. K4b = S * 4 * (h_dec * U_target + h_enc * (k_in * U_input + k_obs * U_observed)) with
+    S = 2 * (1 + optimizer state arrays) words per parameter and U_* the distinct columns the batch touches."""
+    aux = w["aux"]
+    H = w["hidden"]
+    h_enc = H if isinstance(H, int) else H[0]
+    h_dec = H if isinstance(H, int) else H[-1]
+    k_in = 1 + (1 if aux in ("dropout", "both") else 0)          # encoder blocks selected by the input bit
+    k_obs = (1 if aux in ("causal", "both") else 0)
+    st = np.array([touched(p, 0) for p in plans], dtype=np.float64).mean(axis=0)   # u_in, u_tg, n_in, n_tg
+    u_obs = np.mean([np.unique(np.concatenate([p.source.csr.col[p.source.csr.rowptr[r]:p.source.csr.rowptr[r + 1]]
+                                               for r in p.rows])).size for p in plans[:n_obs_sample]])
+    n_all = float(np.mean([p.n_entries for p in plans]))
+    state_words = {"sgd": 2, "adagrad": 4, "rmsprop": 4, "adam": 6}[w["opt"][0]]
+    return [
+        9.0 * n_all * 2,                                                       # K1: read col,val,flag + write col,val,code
+        4.0 * h_enc * (st[2] * k_in + n_all * k_obs),                          # K2: one Wenc row per contributing entry
+        4.0 * h_dec * st[3],                                                   # K3: one WdecT row per target entry
+        40.0 * n_all,                                                          # K4a: counting sort over the batch's entries
+        4.0 * state_words * (h_dec * st[1] + h_enc * (st[0] * k_in + u_obs * k_obs)),   # K4b: W + state, read + write, touched rows
+    ]
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port (reference algorithm, per-rating Python loop + dense NumPy)
 # ------------------------------------------------------------------------------------------------
@@ -427,23 +451,8 @@ def main():
         tot, cnt = C.c_double(), C.c_int64()
         _lib.check(lib.ocf_profile_read(t, C.byref(tot), C.byref(cnt)))
         tag_ms.append(tot.value / max(cnt.value, 1))
-    H = w["hidden"] if isinstance(w["hidden"], int) else w["hidden"]
-    h_enc = H if isinstance(H, int) else H[0]
-    h_dec = H if isinstance(H, int) else H[-1]
-    k_in = 1 + (1 if aux in ("dropout", "both") else 0)          # encoder blocks selected by the input bit
-    k_obs = (1 if aux in ("causal", "both") else 0)
-    st = np.array([touched(p, 0) for p in plans[W:]], dtype=np.float64).mean(axis=0)   # u_in, u_tg, n_in, n_tg
-    u_obs = np.mean([np.unique(np.concatenate([p.source.csr.col[p.source.csr.rowptr[r]:p.source.csr.rowptr[r + 1]]
-                                               for r in p.rows])).size for p in plans[W:W + 8]])
-    n_all = ratings / K
     state_words = {"sgd": 2, "adagrad": 4, "rmsprop": 4, "adam": 6}[w["opt"][0]]
-    alg = [
-        9.0 * n_all * 2,                                                       # K1: read col,val,flag + write col,val,code
-        4.0 * h_enc * (st[2] * k_in + n_all * k_obs),                          # K2: one Wenc row per contributing entry
-        4.0 * h_dec * st[3],                                                   # K3: one WdecT row per target entry
-        4.0 * fs.train.nnz + 21.0 * n_all,                                     # K4a: CSC row ids of the store + the batch entries it matches
-        4.0 * state_words * (h_dec * st[1] + h_enc * (st[0] * k_in + u_obs * k_obs)),   # K4b: W + state, read + write, touched rows
-    ]
+    alg = step_bytes(plans[W:], w, fs.train.nnz)
     peak, peak_src = peaks()
     dom = int(np.argmax(tag_ms))
     kernels = {tag_names[t]: {"ms": tag_ms[t], "algorithmic_bytes": alg[t], "GB/s": alg[t] / (tag_ms[t] * 1e-3) / 1e9 if tag_ms[t] > 0 else None}

@@ -290,6 +290,21 @@ def bench_main(args, w, cfg, rank, world):
         tot, cnt = C.c_double(), C.c_int64()
         _lib.check(lib.ocf_profile_read(tag, C.byref(tot), C.byref(cnt)))
         kernels[name] = {"ms": tot.value / max(cnt.value, 1)}
+    # roofline of rank 0's dominant kernel (the fused row update): algorithmic bytes of the rank's own
+    # shard / CUDA-event time; never allowed to break the line
+    roofline = None
+    if not rows_mode:
+        try:
+            alg = bench.step_bytes(plans[W:], w, 0)
+            k4b_ms = kernels["k_row_update (K4b)"]["ms"]
+            peak, peak_src = bench.peaks()
+            if k4b_ms > 0:
+                ach = alg[4] / (k4b_ms * 1e-3) / 1e9
+                roofline = {"kernel": "k_row_update (K4b), rank 0's shard", "bound": "hbm", "achieved": ach, "peak": peak,
+                            "unit": "GB/s", "frac": ach / peak, "traffic": None, "algorithmic_bytes": alg[4],
+                            "peak_source": peak_src}
+        except Exception as exc:                      # pragma: no cover
+            roofline = {"error": str(exc)}
     rt = torch.tensor([float(sum(p.n_ratings for p in plans[W:]))], device="cuda")
     if rows_mode:
         dist.all_reduce(rt)                              # every rank holds its own rows of the global batches
@@ -339,7 +354,7 @@ def bench_main(args, w, cfg, rank, world):
                 "e2e": {"value": e_ratings / float(e2e.item()), "unit": "ratings/s",
                         "h2d_bytes_per_step": float(h2d_all.item()) / K, "d2h_bytes_per_step": 4 * _lib.N_METRICS * world,
                         "ms_per_step": 1e3 * float(e2e.item()) / K},
-                "gpu_launches": int(launches), "kernels_rank0": kernels}
+                "gpu_launches": int(launches), "roofline": roofline, "kernels_rank0": kernels}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
