@@ -21,7 +21,6 @@ import json
 import pickle
 import threading
 from collections import OrderedDict
-from typing import Optional
 
 import numpy as np
 

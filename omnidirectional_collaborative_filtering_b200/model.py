@@ -17,7 +17,7 @@ Differences from Keras that a caller can see:
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 
