@@ -186,8 +186,8 @@ def run(config: TrainConfig, reader: Optional[DataReader] = None, metadata: Opti
             batch = next(manual)
             # sum((mask*full - t)^2) over the batch == the step's sum of squared errors; the
             # dense predict()/subtract of train.py:239-249 is available as m.predict(batch)
-            rec = m.test_on_batch(batch, sync=False)
-            first = m.read_metrics(m_steps(m) - 1, 1)
+            m.test_on_batch(batch, sync=False)
+            first = m.read_metrics(m.steps_logged() - 1, 1)
             sse += float(first[0, 6])
             ratings_count += batch.target_count
         rmse = float(np.sqrt(sse / ratings_count)) if ratings_count else float("nan")
@@ -195,7 +195,3 @@ def run(config: TrainConfig, reader: Optional[DataReader] = None, metadata: Opti
         results["manual_test_rmse"] = rmse
     return results
 
-
-def m_steps(m):
-    from . import _lib
-    return _lib.lib().ocf_model_steps_logged(m._handle)
