@@ -71,3 +71,102 @@ def host_densify(batch):
             for c, v in zip(cols, vals):
                 mask_out[b, c] = a; t[b, c] = v; observed[b, c] = a
     return ref_batches.feed_list((mask_in, mask_out, x, t, observed), batch.aux_type), t
+
+
+class OracleNet(object):
+    """The surface `train.run` uses of `omni_model.model`, computed by the NumPy oracle on host-densified
+    product batches: lets the product's host logic (generators, RNG order, epoch loop, test procedures)
+    run end to end without a GPU. Test infrastructure only."""
+
+    def __init__(self, ref):
+        from oracle import ref_model
+        self.ref = ref
+        self.metrics_names = list(ref_model.METRIC_NAMES)
+        self.sse_log = []
+
+    def compile(self, optimizer=None, loss="mean_squared_error", rating_range=1.0):
+        from oracle import ref_model
+        self.ref.compile(ref_model.RefOptimizer(optimizer.kind, lr=optimizer.lr, epsilon=optimizer.epsilon,
+                                                decay=optimizer.decay), loss, rating_range=rating_range)
+
+    def get_weights(self):
+        return self.ref.get_weights()
+
+    def set_weights(self, w):
+        self.ref.set_weights(w)
+
+    def fit_generator(self, gen, steps, validation_data=None, validation_steps=None, verbose=0):
+        class _H(object):
+            pass
+        h = _H()
+        h.history = self.ref.fit_generator((host_densify(b) for b in gen), steps,
+                                           validation_data=(host_densify(b) for b in validation_data),
+                                           validation_steps=validation_steps)
+        return h
+
+    def evaluate_generator(self, gen, steps):
+        return self.ref.evaluate_generator((host_densify(b) for b in gen), steps)
+
+    def test_on_batch(self, batch, sync=True):
+        feed, t = host_densify(batch)
+        y = self.ref.predict(feed)
+        self.sse_log.append(float(np.sum(np.square(np.subtract(y, t, dtype=np.float64)))))
+
+    def steps_logged(self):
+        return len(self.sse_log)
+
+    def read_metrics(self, first, count):
+        rec = np.zeros((count, 8), dtype=np.float32)
+        rec[:, 6] = self.sse_log[first:first + count]
+        return rec
+
+
+def oracle_train_run(fs, cfg, seed, init_model):
+    """`train.py:147-177,215-254` driven through the oracle alone on one RandomState stream: the
+    per-epoch histories, the fixed-split test metrics and the manual test RMSE a `train.run` of the
+    same config must reproduce. `init_model()` builds the product model after `np.random.seed(seed)`
+    (its weights, dropout seed and the stream position it leaves are taken over)."""
+    from oracle import ref_model
+    from omnidirectional_collaborative_filtering_b200 import synthetic
+    c = cfg
+    dicts = synthetic.to_reference_dicts(fs, raw_col_id=lambda col: col)
+    data = ref_batches.RefData(fs.n_cols, fs.train.n_rows, dicts["unique_cols"], eval_mode="fixed_split",
+                               train=dicts["train"], valid=tuple(dicts["valid"]), test=tuple(dicts["test"]))
+    np.random.seed(seed)
+    twin = init_model()
+    rng = np.random.RandomState()
+    rng.set_state(np.random.get_state())          # the stream right after the model's initialisation
+    ref = ref_model.RefModel(c.numlayers, c.num_hidden_units, fs.n_cols, c.batch_size,
+                             dense_activation=c.activation_type, use_causal_info=c.use_causal_info,
+                             use_both_masks=c.auxilliary_mask_type == "both",
+                             l2_weight_regulatization=c.l2_weight_regulatization,
+                             dropout_probability=c.dropout_probability, dtype=np.float32,
+                             rng=np.random.RandomState(0))     # its own draws must not touch either stream
+    ref.set_weights(twin.model.get_weights())
+    ref.dropout_seed = twin.dropout_seed
+    ref.compile(ref_model.RefOptimizer("adagrad", lr=c.learning_rate), c.model_loss, rating_range=fs.rating_range)
+    B = c.batch_size
+
+    def gen(which, sparsity, **kw):
+        return ref_batches.batch_stream(data, B, sparsity, which, c.shuffle_data_every_epoch, c.auxilliary_mask_type,
+                                        c.aux_var_value, rng=rng, vectorised=True, **kw)
+
+    history, min_loss, best, best_weights = [], None, 0, None
+    for _ in range(c.max_epochs):          # callers pick max_epochs/patience so that no early stop happens
+        h = ref.fit_generator(gen("train", c.train_sparsity, pass_through_input_training=c.pass_through_input_training),
+                              np.floor(data.train_set_size / B) - 1, validation_data=gen("valid", c.train_sparsity),
+                              validation_steps=np.floor(data.val_set_size / B) - 1)
+        history.append({k: v[-1] for k, v in h.items()})
+        val = history[-1][c.early_stopping_metric]
+        if not best_weights or val < min_loss:        # train.py:161-169: strict improvement keeps the weights
+            min_loss, best, best_weights = val, len(history) - 1, ref.get_weights()
+    ref.set_weights(best_weights)                     # train.py:191: the best-validation model is tested
+    test = ref.evaluate_generator(gen("test", None), np.floor(data.test_set_size / B) - 1)
+    manual = gen("test", None, return_target_count=True)
+    sse, count = 0.0, 0
+    for _ in range(int(np.floor(data.test_set_size / B))):
+        feed, t, n = next(manual)
+        sse += float(np.sum(np.square(np.subtract(ref.predict(feed), t, dtype=np.float64))))
+        count += n
+    return {"history": history, "best_epoch": best, "test": dict(zip(ref_model.METRIC_NAMES, test)),
+            "manual_test_rmse": float(np.sqrt(sse / count))}
