@@ -287,6 +287,59 @@ int ocf_model_buffer(ocf_model* model, int which, void** device_ptr, int64_t* co
 /* Device pointer of a weight (kernel or bias, Keras index) in the library's internal layout,
  * for collectives over replicated parameters; count in floats. */
 int ocf_model_weight_device(ocf_model* model, int index, void** device_ptr, int64_t* count);
+/* ---- on-disk formats (host only; no CUDA device needed) --------------------------------------
+ * Ingest of the JSON files the reference's reader loads with json.load (data_reader.py:85-92) into
+ * CSR arrays, without a Python object per rating.
+ *
+ * ocf_vocab: `unique_items_list.json` / `unique_users_list.json` (data_reader.py:20-28) - a JSON list of
+ * ids (numbers or strings); position in the list = dense column. Ids compare like Python dict keys:
+ * 153 and 153.0 are the same id, "153" is another; a repeated id keeps its LAST position. */
+typedef struct ocf_vocab ocf_vocab;
+int ocf_vocab_load_json(const char* path, ocf_vocab** out);
+int ocf_vocab_size(const ocf_vocab* vocab, int64_t* n);
+int ocf_vocab_destroy(ocf_vocab* vocab);
+/* ocf_ratings: one rating-dict file.
+ *   paired = 0: {"row key": [[id, rating], ...], ...} - `ratingsBy*_dict.json` (data_reader.py:55) and
+ *               `ratingsBy*_dicts_train.json` (:67-68). Rows = keys in file order (json.load's dict order).
+ *   paired = 1: [input dict, target dict] - `ratingsBy*_dicts_{valid,test}.json` (:69-70). Rows = keys of
+ *               the TARGET dict in file order (:74-80); the input row of a key is the input dict's entry for
+ *               it, `null` = the reference's None (a zero input row, :234,253-254).
+ * Column ids are mapped through `cols` (data_reader.py:135; an unknown id fails with the KeyError the
+ * reference would raise). Ratings inside a row keep file order; a repeated row key keeps its first
+ * place and its last value, like a Python dict. Values are stored as float32.
+ * info = {rows, total bytes of the row keys (UTF-8), ratings of store 0, ratings of store 1}. */
+typedef struct ocf_ratings ocf_ratings;
+int ocf_ratings_load_json(const char* path, const ocf_vocab* cols, int paired, ocf_ratings** out);
+int ocf_ratings_info(const ocf_ratings* ratings, int64_t info[4]);
+/* Row keys, concatenated UTF-8 (bytes[info[1]]) + offsets[rows + 1]. */
+int ocf_ratings_keys(const ocf_ratings* ratings, char* bytes, int64_t* offsets);
+/* Copies store `which` (0 = the only / the input store, 1 = the target store of a paired file) into
+ * caller-owned arrays: rowptr[rows + 1], col[nnz], val[nnz], none[rows] (1 = the file held null; may be
+ * NULL). The arrays are what ocf_store_create takes. */
+int ocf_ratings_csr(const ocf_ratings* ratings, int which, int64_t* rowptr, int32_t* col, float* val, uint8_t* none);
+int ocf_ratings_destroy(ocf_ratings* ratings);
+
+/* The offline splitter (TrainValidTestSplit.py:31-219), native: ratings CSV -> per-rating train/valid/test
+ * split -> per-row dicts with paired inputs, written as the same files with the same bytes the reference's
+ * script writes (json.dump / DataFrame.to_csv formatting included).
+ *   ocf_csv_load    pandas.read_csv of the ratings file (:34): header line dropped, n_columns = 4
+ *                   (user, item, rating, timestamp) or 3 (the "netflix" schema, :64-69); per column int64 /
+ *                   float64 / string as pandas infers them.
+ *   ocf_split_write `order` = the caller's np.random.permutation(rows) (:74) - the NumPy stream stays the
+ *                   caller's; fractions = trainvalidtest_split; out_dir = output_filepath (with the trailing
+ *                   separator, the reverse_item-user/ part included, :27-29). Writes train_data_mml*.csv /
+ *                   test_data_mml*.csv (:91-96), ratingsByUser_dicts[_withtimestamps]_{train,valid,test}.json
+ *                   (:98-103,151-181) when build_data_for_omni, unique_{items,users}_list.json (:105-118) when
+ *                   save_users_and_items. cast_user_to_int = the "movielens" schema's str(int(userId)) keys;
+ *                   reverse_user_item_data swaps the first two columns' roles (:40-43). */
+typedef struct ocf_csv ocf_csv;
+int ocf_csv_load(const char* path, int n_columns, ocf_csv** out);
+int ocf_csv_rows(const ocf_csv* csv, int64_t* n);
+int ocf_csv_destroy(ocf_csv* csv);
+int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t n_order, const double fractions[3],
+                    const char* out_dir, int cast_user_to_int, int build_data_for_omni, int include_timestamps,
+                    int save_users_and_items, int reverse_user_item_data);
+
 /* Per-kernel timing with CUDA events recorded on the launching stream around the named kernels
  * (tag 0 = K1 gather, 1 = K2 encoder, 2 = K3 decoder/loss, 3 = K4a column scan, 4 = scoring GEMM,
  * 5 = K4b row update, 6 = first collective of a parallel step (z all-reduce / streaming optimizer

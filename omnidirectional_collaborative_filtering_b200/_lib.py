@@ -108,6 +108,19 @@ _SIGNATURES = {
     "ocf_model_steps_logged": (C.c_int64, [_P]),
     "ocf_model_buffer": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "ocf_model_weight_device": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "ocf_vocab_load_json": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "ocf_vocab_size": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "ocf_vocab_destroy": (C.c_int, [_P]),
+    "ocf_ratings_load_json": (C.c_int, [C.c_char_p, _P, C.c_int, C.POINTER(_P)]),
+    "ocf_ratings_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "ocf_ratings_keys": (C.c_int, [_P, _P, _P]),
+    "ocf_ratings_csr": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
+    "ocf_ratings_destroy": (C.c_int, [_P]),
+    "ocf_csv_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "ocf_csv_rows": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "ocf_csv_destroy": (C.c_int, [_P]),
+    "ocf_split_write": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_double), C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int]),
 }
 
 _lib = None

@@ -392,7 +392,8 @@ class data_reader(object):
 
     def _init_from_files(self, use_json, reverse):
         N = self.num_items
-        self.unique_items = self.load_data(self.filepath, "unique_users_list" if reverse else "unique_items_list", use_json)
+        cols_name = "unique_users_list" if reverse else "unique_items_list"
+        self.unique_items = self.load_data(self.filepath, cols_name, use_json)
         self.items_to_densevec = {item: i for i, item in enumerate(self.unique_items)}       # :24-28
         self.densevec_to_items = {i: item for i, item in enumerate(self.unique_items)}
         if self.nonsequentialusers:                                                           # :30-44
@@ -402,13 +403,38 @@ class data_reader(object):
         else:
             self.densevec_to_users = {i: i for i in range(self.num_users)}
         base = "ratingsByItem" if reverse else "ratingsByUser"                                # :46-49
+        # JSON files on disk go through the native parser (csrc/ocf_etl.cpp): no Python object per rating.
+        # In-memory `data=` dicts and pickles keep the per-rating Python loop (small / test inputs).
+        native = self._files is None and use_json
+        if native:
+            from . import ingest
+            vocab = ingest.Vocab(self.filepath + cols_name + ".json")
+            load = lambda name, paired: ingest.load_ratings(self.filepath + name + ".json", vocab, paired, N)
         if self.eval_mode == "ablation":
-            user_dict = self.load_data(self.filepath, base + "_dict", use_json)               # :55
-            lists = []
-            for i in range(self.num_users):
-                raw = self.densevec_to_users[i]
-                lists.append(user_dict[raw] if raw in user_dict else user_dict[str(raw)])
-            self._stores["train"] = RatingStore(_csr_from_lists(lists, self.items_to_densevec, N), build_csc=True)
+            if native:
+                keys, csr = load(base + "_dict", False)                                       # :55
+                row_of = {k: i for i, k in enumerate(keys)}
+                want = []
+                for i in range(self.num_users):
+                    raw = self.densevec_to_users[i]
+                    want.append(row_of[raw] if raw in row_of else row_of[str(raw)])
+                csr = csr.take_rows(np.asarray(want, dtype=np.int64))
+            else:
+                user_dict = self.load_data(self.filepath, base + "_dict", use_json)
+                lists = []
+                for i in range(self.num_users):
+                    raw = self.densevec_to_users[i]
+                    lists.append(user_dict[raw] if raw in user_dict else user_dict[str(raw)])
+                csr = _csr_from_lists(lists, self.items_to_densevec, N)
+            self._stores["train"] = RatingStore(csr, build_csc=True)
+        elif native:
+            self.train_set, train = load(base + "_dicts_train", False)                        # :67-70, :78-80
+            self.val_set, va_in, _, va_tg = load(base + "_dicts_valid", True)
+            self.test_set, te_in, _, te_tg = load(base + "_dicts_test", True)
+            self._set_sizes()
+            self._stores["train"] = RatingStore(train, build_csc=True)
+            self._stores["valid"] = StorePair(RatingStore(va_in), RatingStore(va_tg))
+            self._stores["test"] = StorePair(RatingStore(te_in), RatingStore(te_tg))
         else:
             train = self.load_data(self.filepath, base + "_dicts_train", use_json)            # :67-70
             valid = self.load_data(self.filepath, base + "_dicts_valid", use_json)
@@ -416,15 +442,18 @@ class data_reader(object):
             self.train_set = list(train.keys())                                               # :78-80
             self.val_set = list(valid[1].keys())
             self.test_set = list(test[1].keys())
-            self.train_set_size = len(self.train_set)                                         # :73-75
-            self.val_set_size = len(self.val_set)
-            self.test_set_size = len(self.test_set)
+            self._set_sizes()
             col_of = self.items_to_densevec
             self._stores["train"] = RatingStore(_csr_from_lists(list(train.values()), col_of, N), build_csc=True)
             for name, (ins, tgs), keys in (("valid", valid, self.val_set), ("test", test, self.test_set)):
                 pair = StorePair(RatingStore(_csr_from_lists([ins[k] for k in keys], col_of, N)),
                                  RatingStore(_csr_from_lists([tgs[k] for k in keys], col_of, N)))
                 self._stores[name] = pair
+
+    def _set_sizes(self):
+        self.train_set_size = len(self.train_set)                                             # :73-75
+        self.val_set_size = len(self.val_set)
+        self.test_set_size = len(self.test_set)
 
     def _init_from_split(self, fs: FixedSplit):
         if self.eval_mode != "fixed_split":

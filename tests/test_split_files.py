@@ -1,0 +1,264 @@
+"""The two file-format neighbours of the hot path, both native
+(`csrc/ocf_etl.cpp`) and both checked against files the REFERENCE's own scripts wrote
+(`tests/golden/make_split_golden.py`):
+
+  * splitter: `splitter.split_data` writes the same bytes as `TrainValidTestSplit.py` for the same CSV and
+    NumPy seed; `oracle/ref_split.py` (the pandas-free restatement) is pinned by the same files and then
+    serves as the checker for the cases the reference cannot finish under Python 3 and for random CSVs;
+  * ingest: `data_reader(..., use_json=True)` on the reference's files yields the batches the reference's
+    `data_reader.py` yields from them, bit for bit; the native parser agrees with `json.load` + the
+    per-rating Python path on every golden file and on adversarial JSON.
+No GPU needed: these entry points are host code."""
+import filecmp
+import json
+import os
+import shutil
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import ref_split
+from omnidirectional_collaborative_filtering_b200 import _lib, ingest, splitter
+from omnidirectional_collaborative_filtering_b200.data_reader import _csr_from_lists, data_reader
+from tests.conftest import GOLDEN
+from tests.helpers import host_densify
+
+SPLIT = os.path.join(GOLDEN, "split")
+with open(os.path.join(SPLIT, "cases.json")) as _f:
+    CASES = json.load(_f)
+
+
+def _golden_dir(case):
+    return os.path.join(SPLIT, case["name"], "reverse_item-user" if case["reverse_user_item_data"] else "")
+
+
+def _run(fn, case, out, **kw):
+    np.random.seed(case["seed"])
+    return fn(os.path.join(SPLIT, case["name"], "ratings.csv"), str(out) + "/", case["schema_type"],
+              include_timestamps=case["include_timestamps"], reverse_user_item_data=case["reverse_user_item_data"], **kw)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+@pytest.mark.parametrize("impl", ["native", "oracle"])
+def test_splitter_writes_the_reference_bytes(tmp_path, case, impl):
+    fn = splitter.split_data if impl == "native" else ref_split.split_data
+    if impl == "oracle":
+        os.makedirs(str(tmp_path) + ("/reverse_item-user" if case["reverse_user_item_data"] else ""), exist_ok=True)
+    out = _run(fn, case, tmp_path)
+    assert case["files"], "every case has at least the mymedialite CSVs"
+    for name in case["files"]:
+        assert filecmp.cmp(os.path.join(out, name), os.path.join(_golden_dir(case), name), shallow=False), name
+    stream_after = np.random.random_sample()
+    np.random.seed(case["seed"])
+    np.random.permutation(sum(1 for _ in open(os.path.join(SPLIT, case["name"], "ratings.csv"))) - 1)
+    assert stream_after == np.random.random_sample()          # one permutation drawn, nothing else
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_native_splitter_equals_oracle_everywhere(tmp_path, case):
+    """Including the files the reference dies in and the unique-id lists."""
+    a, b = tmp_path / "native", tmp_path / "oracle"
+    os.makedirs(str(b) + ("/reverse_item-user" if case["reverse_user_item_data"] else ""))
+    out_a = _run(splitter.split_data, case, a, save_users_and_items=True)
+    out_b = _run(ref_split.split_data, case, b, save_users_and_items=True)
+    names = sorted(os.listdir(out_b))
+    assert sorted(os.listdir(out_a)) == names and len(names) == 7
+    for name in names:
+        assert filecmp.cmp(os.path.join(out_a, name), os.path.join(out_b, name), shallow=False), name
+        if name.endswith(".json"):
+            with open(os.path.join(out_a, name)) as f:
+                json.load(f)
+
+
+_field = st.one_of(st.integers(-50, 5000).map(str), st.floats(-1e6, 1e6, allow_nan=False).map(repr),
+                   st.sampled_from(["0.5", "3", "1e-7", "2.50", "1E3", "12345678901234567890", "-0.0", ""]))
+_ident = st.one_of(st.integers(0, 30).map(str), st.sampled_from(["7.0", "7.5", "u1", "a,b", 'q"r', "é", "x y", "007"]))
+
+
+@settings(max_examples=100, deadline=None)
+@given(rows=st.lists(st.tuples(_ident, _ident, _field, st.integers(0, 10 ** 9).map(str)), min_size=1, max_size=40),
+       schema=st.sampled_from(["amazon", "netflix", "movielens", "yelp"]), ts=st.booleans(), rev=st.booleans(),
+       seed=st.integers(0, 10 ** 6), fr=st.sampled_from([(.8, .1, .1), (.5, .25, .25), (1.0, 0.0, 0.0), (.34, .33, .33)]))
+def test_native_splitter_equals_oracle_on_random_csvs(tmp_path_factory, rows, schema, ts, rev, seed, fr):
+    d = str(tmp_path_factory.mktemp("csv")) + "/"
+    ncol = 3 if schema == "netflix" else 4
+    ts = ts and ncol == 4
+
+    def q(s):
+        return '"' + s.replace('"', '""') + '"' if any(c in s for c in ',"\n') else s
+    with open(d + "r.csv", "w", encoding="utf-8") as f:
+        f.write(",".join(["a", "b", "c", "d"][:ncol]) + "\n")
+        for r in rows:
+            f.write(",".join(q(x) for x in r[:ncol]) + "\n")
+    os.makedirs(d + "n"), os.makedirs(d + "o" + ("/reverse_item-user" if rev else ""))
+    results = []
+    for fn, sub in ((splitter.split_data, "n/"), (ref_split.split_data, "o/")):
+        np.random.seed(seed)
+        try:
+            results.append(fn(d + "r.csv", d + sub, schema, fr, True, ts, True, rev))
+        except (ValueError, _lib.OcfError) as e:          # e.g. int('u1') under the movielens schema: both must refuse
+            results.append(type(e))
+    if isinstance(results[1], type):
+        assert isinstance(results[0], type)
+    else:
+        for name in sorted(os.listdir(results[1])):
+            assert filecmp.cmp(os.path.join(results[0], name), os.path.join(results[1], name), shallow=False), name
+    shutil.rmtree(d)
+
+
+# ---- ingest ------------------------------------------------------------------------------------------
+
+def _python_ingest(path, col_of, paired, n_cols):
+    with open(path) as f:
+        obj = json.load(f)
+    if not paired:
+        return list(obj.keys()), _csr_from_lists(list(obj.values()), col_of, n_cols)
+    ins, tgs = obj
+    keys = list(tgs.keys())
+    return keys, _csr_from_lists([ins[k] for k in keys], col_of, n_cols), np.array([ins[k] is None for k in keys]), \
+        _csr_from_lists([tgs[k] for k in keys], col_of, n_cols)
+
+
+def _same_csr(a, b):
+    assert a.n_rows == b.n_rows and np.array_equal(a.rowptr, b.rowptr)
+    assert np.array_equal(a.col, b.col) and np.array_equal(a.val, b.val, equal_nan=True) and a.val.dtype == b.val.dtype == np.float32
+
+
+def _check_file(path, vocab_path, paired):
+    with open(vocab_path) as f:
+        ids = json.load(f)
+    col_of = {x: i for i, x in enumerate(ids)}
+    got = ingest.load_ratings(path, ingest.Vocab(vocab_path), paired)
+    want = _python_ingest(path, col_of, paired, len(ids))
+    assert got[0] == want[0]
+    _same_csr(got[1], want[1])
+    if paired:
+        assert np.array_equal(got[2], want[2])
+        _same_csr(got[3], want[3])
+    return got
+
+
+@pytest.mark.parametrize("name", ["ml", "ml_rev", "amazon"])
+def test_native_ingest_equals_json_load_on_reference_files(tmp_path, name):
+    case = [c for c in CASES if c["name"] == name][0]
+    d = _golden_dir(case)
+    with open(os.path.join(d, "ratingsByUser_dicts_train.json")) as f:
+        train = json.load(f)
+    ids = []
+    for lst in train.values():
+        ids += [p[0] for p in lst]
+    for which in ("valid", "test"):
+        with open(os.path.join(d, "ratingsByUser_dicts_%s.json" % which)) as f:
+            for half in json.load(f):
+                for lst in half.values():
+                    ids += [p[0] for p in (lst or [])]
+    ids = list(dict.fromkeys(int(x) if isinstance(x, float) else x for x in ids))     # 153.0 in the rows, 153 in the list
+    vocab = str(tmp_path / "unique.json")
+    with open(vocab, "w") as f:
+        json.dump(ids, f)
+    keys, csr = _check_file(os.path.join(d, "ratingsByUser_dicts_train.json"), vocab, False)
+    assert csr.nnz > 150 and len(keys) > 20
+    for which in ("valid", "test"):
+        got = _check_file(os.path.join(d, "ratingsByUser_dicts_%s.json" % which), vocab, True)
+        assert got[3].nnz > 10
+
+
+def test_native_ingest_json_corner_cases(tmp_path):
+    vocab = str(tmp_path / "v.json")
+    with open(vocab, "w") as f:
+        f.write(' [ 153, 136.0, "x\\u00e9\\ud83d\\ude00", 7.5, 1e3, -0.0, "153", 153 , 9007199254740993]\n')
+    text = ('{ "a" : [[153.0, 4.5], ["x\\u00e9\\ud83d\\ude00", 3], [7.5, 1e0], [1000, 2.5E-1]],\n "b":[],\t"c":null,'
+            ' "k\\"\\\\\\n\\u0041": [[136, 2.5, "extra", {"x": [1, 2]}], [0, -1.5], ["153", 0.1]],'
+            ' "a": [[153, 1.0], [1.53e2, 2.0], [9007199254740993, 0.30000000000000004]], "b": [[-0, NaN]] }')
+    path = str(tmp_path / "t.json")
+    with open(path, "w") as f:
+        f.write(text)
+    keys, csr = _check_file(path, vocab, False)
+    assert keys == ["a", "b", "c", 'k"\\\nA']                    # repeated keys keep their first place, last value
+    assert csr.row(0)[0].tolist() == [7, 7, 8] and csr.row(1)[0].tolist() == [5]
+    with open(path, "w") as f:
+        f.write("[" + text + ", " + '{"c": [[153, 5]], "zz": [], "a": [[136, 1]]}' + "]")
+    with pytest.raises(_lib.OcfError, match="KeyError.*zz"):
+        ingest.load_ratings(path, ingest.Vocab(vocab), True)      # a target row the input dict does not hold
+    with open(path, "w") as f:
+        f.write("[" + text + ", " + '{"c": [[153, 5]], "b": [], "a": [[136, 1]]}' + "]")
+    keys, ins, none, tgs = _check_file(path, vocab, True)
+    assert keys == ["c", "b", "a"] and none.tolist() == [True, False, False]
+
+
+@pytest.mark.parametrize("text,message", [
+    ('{"a": [[99, 1.0]]}', "KeyError: 99"),
+    ('{"a": [["q", 1.0]]}', "KeyError: 'q'"),
+    ('{"a": [[153, 1.0]', "expected"),
+    ('{"a": [[153 1.0]]}', "expected ','"),
+    ('{"a": [[153, "5"]]}', "number"),
+    ('{"a": [[153, 1.0]]} x', "trailing"),
+    ('[[{}, {}], {}]', "_withtimestamps_"),
+])
+def test_native_ingest_errors(tmp_path, text, message):
+    vocab = str(tmp_path / "v.json")
+    with open(vocab, "w") as f:
+        json.dump([153, 136], f)
+    path = str(tmp_path / "t.json")
+    with open(path, "w") as f:
+        f.write(text)
+    with pytest.raises(_lib.OcfError, match=message):
+        ingest.load_ratings(path, ingest.Vocab(vocab), text.startswith("["))
+    with pytest.raises(_lib.OcfError, match="cannot open"):
+        ingest.load_ratings(path + ".missing", ingest.Vocab(vocab), False)
+
+
+_jid = st.one_of(st.integers(-5, 40), st.floats(-5, 40, allow_nan=False, width=32), st.sampled_from(["a", "é", "15", ""]))
+_jval = st.one_of(st.integers(-5, 5), st.floats(allow_nan=False, allow_infinity=False), st.floats(0.5, 5.0).map(lambda x: round(x, 1)))
+
+
+@settings(max_examples=100, deadline=None)
+@given(ids=st.lists(_jid, min_size=1, max_size=30),
+       rows=st.dictionaries(st.text(max_size=5), st.one_of(st.none(), st.lists(st.tuples(st.integers(0, 29), _jval), max_size=8)), max_size=8),
+       indent=st.sampled_from([None, 0, 2]), ascii_=st.booleans())
+def test_native_ingest_equals_json_load_on_random_files(tmp_path_factory, ids, rows, indent, ascii_):
+    d = str(tmp_path_factory.mktemp("json")) + "/"
+    with open(d + "v.json", "w") as f:
+        json.dump(ids, f, ensure_ascii=ascii_)
+    obj = {k: (None if l is None else [[ids[i % len(ids)], v] for i, v in l]) for k, l in rows.items()}
+    targets = {k: (l or []) for k, l in obj.items()}
+    with open(d + "s.json", "w") as f:
+        json.dump({k: l or [] for k, l in obj.items()}, f, indent=indent, ensure_ascii=ascii_)
+    with open(d + "p.json", "w") as f:
+        json.dump([obj, targets], f, indent=indent, ensure_ascii=ascii_)
+    _check_file(d + "s.json", d + "v.json", False)
+    _check_file(d + "p.json", d + "v.json", True)
+    shutil.rmtree(d)
+
+
+# ---- reference splitter output -> product reader, against the reference reader on the same files --------
+
+def test_reader_on_reference_files_yields_the_reference_batches():
+    d = os.path.join(SPLIT, "ml") + "/"
+    gold = np.load(os.path.join(SPLIT, "pipeline_batches.npz"))
+    rd = data_reader(int(gold["n_items"]), int(gold["n_rows"]), d, nonsequentialusers=False, use_json=True,
+                     eval_mode="fixed_split", useTimestamps=False, reverse_user_item_data=False, rng_on_device=False)
+    for which, sparsity, aux, seed in (("train", [0.3, 0.8], "dropout", 41), ("valid", None, None, 42), ("test", None, "both", 43)):
+        np.random.seed(seed)
+        gen = rd.data_gen(8, sparsity, train_val_test=which, shuffle=True, auxilliary_mask_type=aux, aux_var_value=-1,
+                          return_target_count=which != "train")
+        n = int(gold["%s/n_batches" % which])
+        assert n > 0
+        for b in range(n):
+            batch = next(gen)
+            feed, targets = host_densify(batch)
+            assert np.array_equal(targets, gold["%s/b%d/targets" % (which, b)])
+            for k, arr in enumerate(feed):
+                assert np.array_equal(arr, gold["%s/b%d/in%d" % (which, b, k)]), (which, b, k)
+            if which != "train":
+                assert batch.target_count == int(gold["%s/b%d/target_count" % (which, b)])
+        assert next(gen) is None
+    rd.close()
+
+
+def test_native_unique_lists_match_the_pipeline_fixture(tmp_path):
+    case = [c for c in CASES if c["name"] == "ml"][0]
+    out = _run(splitter.split_data, case, tmp_path, save_users_and_items=True)
+    for name in ("unique_items_list.json", "unique_users_list.json"):
+        assert filecmp.cmp(os.path.join(out, name), os.path.join(SPLIT, "ml", name), shallow=False)
