@@ -51,3 +51,33 @@ def test_no_cpu_fallback():
                         np.array([2.0], dtype=np.float32)))
     with pytest.raises(_lib.OcfError):
         s.handle
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ocf.h compiles as C99 (no C++ in the signatures) and a C program linked against the
+    library can call it: here the host-only ingest of a rating file, start to finish."""
+    import json
+    import os
+    src = tmp_path / "use.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "ocf.h"
+int main(int argc, char** argv) {
+  ocf_vocab* v = 0; ocf_ratings* r = 0; int64_t info[4];
+  if (ocf_version() != OCF_VERSION) return 2;
+  if (ocf_vocab_load_json(argv[1], &v)) { printf("%s\n", ocf_last_error()); return 3; }
+  if (ocf_ratings_load_json(argv[2], v, 0, &r)) { printf("%s\n", ocf_last_error()); return 4; }
+  if (ocf_ratings_info(r, info)) return 5;
+  printf("%lld rows %lld ratings\n", (long long)info[0], (long long)info[2]);
+  ocf_ratings_destroy(r); ocf_vocab_destroy(v);
+  return ocf_ratings_load_json("/nonexistent.json", 0, 0, &r) == OCF_ERR_INVALID ? 0 : 6;
+}
+''')
+    root = os.path.dirname(_lib.HEADER_PATH)
+    exe = str(tmp_path / "use")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", root, str(src), "-o", exe, _lib.SO_PATH,
+                    "-Wl,-rpath," + os.path.dirname(_lib.SO_PATH)], check=True)
+    (tmp_path / "v.json").write_text(json.dumps([10, 20, 30]))
+    (tmp_path / "t.json").write_text(json.dumps({"a": [[10, 1.0], [30.0, 2.5]], "b": [[20, 4]]}))
+    out = subprocess.run([exe, str(tmp_path / "v.json"), str(tmp_path / "t.json")], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "2 rows 3 ratings", (out.returncode, out.stdout, out.stderr)
