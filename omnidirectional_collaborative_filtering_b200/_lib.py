@@ -187,5 +187,5 @@ def ptr(array):
     """Host pointer of a C-contiguous NumPy array (None -> NULL)."""
     if array is None:
         return None
-    assert array.flags["C_CONTIGUOUS"]
-    return array.ctypes.data_as(C.c_void_p)
+    assert array.flags.c_contiguous
+    return C.c_void_p(array.ctypes.data)

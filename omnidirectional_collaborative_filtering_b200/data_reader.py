@@ -302,22 +302,29 @@ class Batch(object):
 class Prefetcher(object):
     """Pulls exactly `count` items from a generator on a background thread (bounded queue): the
     role Keras' GeneratorEnqueuer (workers=1, max_q_size=10) plays for `fit_generator` in the
-    reference. NumPy releases the GIL inside `random_sample`, so the RNG
-    replay of batch i+1 overlaps the staging and kernel launches of batch i. Exactly `count`
-    items are drawn, so the NumPy global stream ends where synchronous consumption would leave
-    it; nothing else may draw from `np.random` while the thread runs."""
+    reference. NumPy releases the GIL inside `random_sample` and ctypes
+    releases it inside the library, so drawing batch i+1 overlaps the staging and kernel launches of
+    batch i. Items cross the queue in chunks (a queue hand-off costs about as much as building a
+    device-drawn batch). Exactly `count` items are drawn, so the NumPy global stream ends where
+    synchronous consumption would leave it; nothing else may draw from `np.random` while the
+    thread runs."""
 
-    def __init__(self, generator, count, depth=10):
+    def __init__(self, generator, count, depth=10, chunk=8):
         import queue
-        import threading
         self.count = int(count)
         self.queue = queue.Queue(maxsize=depth)
         self.error = None
+        chunk = max(1, int(chunk))
 
         def work():
             try:
-                for _ in range(self.count):
-                    self.queue.put(next(generator))
+                left = self.count
+                first = True
+                while left:
+                    n = 1 if first else min(chunk, left)      # the first batch goes out at once
+                    first = False
+                    self.queue.put([next(generator) for _ in range(n)])
+                    left -= n
             except BaseException as exc:          # surfaced on the consumer side
                 self.error = exc
                 self.queue.put(None)
@@ -326,11 +333,14 @@ class Prefetcher(object):
         self.thread.start()
 
     def __iter__(self):
-        for _ in range(self.count):
-            item = self.queue.get()
-            if self.error is not None:
+        left = self.count
+        while left:
+            items = self.queue.get()
+            if items is None:
                 raise self.error
-            yield item
+            for item in items:
+                yield item
+            left -= len(items)
         self.thread.join()
 
 

@@ -21,6 +21,7 @@ class RatingStore(object):
         # row lengths (the RNG replay and target counts are defined on full rows)
         self.orig_pos = orig_pos
         self._full_lengths = full_lengths
+        self._lengths = None                # the store is immutable: row lengths are computed once
 
     @property
     def n_rows(self):
@@ -32,7 +33,9 @@ class RatingStore(object):
 
     @property
     def lengths(self):
-        return np.diff(self.csr.rowptr)
+        if self._lengths is None:
+            self._lengths = np.diff(self.csr.rowptr)
+        return self._lengths
 
     @property
     def full_lengths(self):
@@ -90,6 +93,7 @@ class StorePair(object):
         assert in_store.n_rows == tgt_store.n_rows and in_store.n_cols == tgt_store.n_cols
         self.in_store, self.tgt_store = in_store, tgt_store
         self._handle = None
+        self._lengths = None
 
     @property
     def n_rows(self):
@@ -101,7 +105,9 @@ class StorePair(object):
 
     @property
     def lengths(self):
-        return self.in_store.lengths + self.tgt_store.lengths
+        if self._lengths is None:
+            self._lengths = self.in_store.lengths + self.tgt_store.lengths
+        return self._lengths
 
     def column_shard(self, lo: int, hi: int) -> "StorePair":
         return StorePair(self.in_store.column_shard(lo, hi), self.tgt_store.column_shard(lo, hi))
