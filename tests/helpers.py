@@ -78,9 +78,12 @@ class OracleNet(object):
     product batches: lets the product's host logic (generators, RNG order, epoch loop, test procedures)
     run end to end without a GPU. Test infrastructure only."""
 
-    def __init__(self, ref):
+    _handle = None                       # what omni_model's helpers look at before talking to the library
+
+    def __init__(self, ref, owner=None):
         from oracle import ref_model
         self.ref = ref
+        self.owner = owner               # the product omni_model whose per-layer trainable flags apply
         self.metrics_names = list(ref_model.METRIC_NAMES)
         self.sse_log = []
 
@@ -99,6 +102,8 @@ class OracleNet(object):
         class _H(object):
             pass
         h = _H()
+        if self.owner is not None:
+            self.ref.trainable = list(self.owner.trainable)
         h.history = self.ref.fit_generator((host_densify(b) for b in gen), steps,
                                            validation_data=(host_densify(b) for b in validation_data),
                                            validation_steps=validation_steps)
@@ -114,6 +119,11 @@ class OracleNet(object):
 
     def steps_logged(self):
         return len(self.sse_log)
+
+    def save(self, path):
+        """The product's own `.npz` writer (it only needs `owner.config()` and `get_weights()`)."""
+        from omnidirectional_collaborative_filtering_b200.model import OmniNet
+        OmniNet.save(self, path)
 
     def read_metrics(self, first, count):
         rec = np.zeros((count, 8), dtype=np.float32)
@@ -144,6 +154,7 @@ def oracle_train_run(fs, cfg, seed, init_model):
                              rng=np.random.RandomState(0))     # its own draws must not touch either stream
     ref.set_weights(twin.model.get_weights())
     ref.dropout_seed = twin.dropout_seed
+    ref.trainable = list(twin.trainable)          # frozen layers of a nested denoising AE (model.py:158-170)
     ref.compile(ref_model.RefOptimizer("adagrad", lr=c.learning_rate), c.model_loss, rating_range=fs.rating_range)
     B = c.batch_size
 
@@ -169,4 +180,4 @@ def oracle_train_run(fs, cfg, seed, init_model):
         sse += float(np.sum(np.square(np.subtract(ref.predict(feed), t, dtype=np.float64))))
         count += n
     return {"history": history, "best_epoch": best, "test": dict(zip(ref_model.METRIC_NAMES, test)),
-            "manual_test_rmse": float(np.sqrt(sse / count))}
+            "manual_test_rmse": float(np.sqrt(sse / count)), "weights": ref.get_weights()}
