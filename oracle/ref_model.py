@@ -4,12 +4,21 @@ model, loss, metrics, optimizers and epoch loop.
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
 legs may import this module.
 
-Parity status: PARITY UNPINNED by the reference. The arithmetic of this path lives in
-Keras 2.0.4 on TensorFlow 1.3.0 (`/root/reference/README.md:17-23`), neither of which is in
-`/root/reference` nor installable offline, and the reference has no tests, golden vectors or
-logged results. This file restates the published algorithms of those releases at the
-reference's call sites; `tests/test_oracle_model.py` cross-checks it against an independent
-PyTorch-autograd implementation of the same formulas.
+Parity status: PARITY UNPINNED for the third-party arithmetic, pinned for everything the reference
+itself defines. The layer arithmetic, autodiff and optimizer rules of this path live in Keras 2.0.4
+on TensorFlow 1.3.0 (`/root/reference/README.md:17-23`), neither of which is in `/root/reference`
+nor installable offline, and the reference has no tests, golden vectors or logged results: Dense /
+activation / Dropout forward and backward and the Adagrad / RMSprop / Adam / SGD rules are restated
+from those releases' published algorithms, and `tests/test_oracle_model.py` cross-checks them against
+an independent PyTorch-autograd implementation of the same formulas. What the reference's OWN code
+defines is pinned by running that code here (fixtures under `tests/golden/`, each with the script
+that made it):
+  * the four custom metrics          train.py:102-121, closures cut out with `ast`     tests/test_reference_metrics.py
+  * graph structure, input order,    model.py:33-99 executed over a structural          tests/test_reference_structure.py
+    dropout placement, L2 placement  Keras stand-in
+  * the weight-transfer helpers      model.py:109-170, same run (88 cases)              tests/test_reference_structure.py
+  * epoch loop, early stopping,      train.py:147-255 executed over recording           tests/test_train_host.py
+    test procedures, manual RMSE     stand-ins (14 call traces)
 
 What is restated (reference file:line):
   RefModel.__init__/forward   graph of `omni_model`, `model.py:43-99`:
