@@ -639,9 +639,7 @@ void json_string(const std::string& s, std::string* out) {
 
 struct Column {
   enum Type : uint8_t { INT, FLT, STR } type = INT;
-  std::vector<int64_t> i;
-  std::vector<double> d;
-  std::vector<std::string> s;
+  std::vector<std::string> s;                          // STR columns only; numbers live in ocf_csv::packed
 };
 
 bool parse_int_field(const char* b, const char* e, int64_t* v) {
@@ -668,7 +666,88 @@ struct ocf_csv {
   int64_t n_rows = 0;
   Column col[4];
   uint8_t row_kind = RowKind::INT;   // what `ratings.iloc[i]` upcasts a row to (TrainValidTestSplit.py:125)
+  // the numeric columns of a row side by side (int64 or double bits, 4 slots per row): the writers visit rows
+  // in permuted order, so one cache line per rating instead of one per column
+  std::vector<uint64_t> packed;
+  int64_t int_at(int c, int64_t row) const { int64_t v; std::memcpy(&v, &packed[(size_t)row * 4 + c], 8); return v; }
+  double flt_at(int c, int64_t row) const { double v; std::memcpy(&v, &packed[(size_t)row * 4 + c], 8); return v; }
 };
+
+namespace {
+
+// One pass over the records of a CSV text (RFC 4180 quoting; header line dropped; blank lines skipped like
+// pandas' skip_blank_lines): cell(column, begin, end) per field. Returns the number of records or -1 (error set).
+template <typename Cell>
+int64_t scan_csv(const std::string& text, int n_columns, const char* path, Cell&& cell_cb) {
+  const char* p = text.data();
+  const char* end = p + text.size();
+  int64_t line = 0, records = 0;
+  std::string cell;
+  while (p < end) {
+    int c = 0;
+    bool any = false;
+    for (;;) {                                         // one record
+      const char* b = p;
+      const char* e;
+      if (p < end && *p == '"') {
+        cell.clear();
+        ++p;
+        for (;;) {
+          if (p >= end) { fail(OCF_ERR_INVALID, std::string(path) + ": unterminated quoted field"); return -1; }
+          if (*p == '"') {
+            if (p + 1 < end && p[1] == '"') { cell.push_back('"'); p += 2; continue; }
+            ++p;
+            break;
+          }
+          cell.push_back(*p++);
+        }
+        const char* t = p;
+        while (p < end && *p != ',' && *p != '\n' && *p != '\r') ++p;
+        cell.append(t, p);
+        b = cell.data();
+        e = b + cell.size();
+        any = true;
+      } else {
+        while (p < end && *p != ',' && *p != '\n' && *p != '\r') ++p;
+        e = p;
+        if (e > b) any = true;
+      }
+      const bool more = p < end && *p == ',';
+      if (line > 0 && (any || more || c > 0)) {
+        if (c >= n_columns) {
+          fail(OCF_ERR_INVALID, std::string(path) + ": line " + std::to_string(line + 1) + " has more than " +
+                                std::to_string(n_columns) + " fields");
+          return -1;
+        }
+        cell_cb(c, b, e);
+      }
+      ++c;
+      if (more) { ++p; any = true; continue; }
+      break;
+    }
+    if (p < end && *p == '\r') ++p;
+    if (p < end && *p == '\n') ++p;
+    const bool blank = !any && c == 1;
+    if (line > 0) {
+      if (!blank) {
+        if (c != n_columns) {
+          fail(OCF_ERR_INVALID, std::string(path) + ": line " + std::to_string(line + 1) + " has " + std::to_string(c) +
+                                " fields, expected " + std::to_string(n_columns));
+          return -1;
+        }
+        ++records;
+      }
+    } else if (c != n_columns) {
+      fail(OCF_ERR_INVALID, std::string(path) + ": the header has " + std::to_string(c) + " columns, the schema needs " +
+                            std::to_string(n_columns) + " (TrainValidTestSplit.py:39-69)");
+      return -1;
+    }
+    ++line;
+  }
+  return records;
+}
+
+}  // namespace
 
 extern "C" int ocf_csv_load(const char* path, int n_columns, ocf_csv** out) {
   if (!path || !out || (n_columns != 3 && n_columns != 4)) return fail(OCF_ERR_INVALID, "ocf_csv_load: bad argument");
@@ -677,89 +756,32 @@ extern "C" int ocf_csv_load(const char* path, int n_columns, ocf_csv** out) {
   if (int rc = read_file(path, &text)) return rc;
   auto csv = std::make_unique<ocf_csv>();
   csv->n_cols = n_columns;
-  // pass 1: split into fields (RFC 4180 quoting), header line dropped
-  std::vector<std::string> fields[4];
-  const char* p = text.data();
-  const char* end = p + text.size();
-  int64_t line = 0;
-  std::string cell;
-  while (p < end) {
-    int c = 0;
-    bool any = false;
-    for (;;) {                                         // one record
-      cell.clear();
-      if (p < end && *p == '"') {
-        ++p;
-        for (;;) {
-          if (p >= end) return fail(OCF_ERR_INVALID, std::string(path) + ": unterminated quoted field");
-          if (*p == '"') {
-            if (p + 1 < end && p[1] == '"') { cell.push_back('"'); p += 2; continue; }
-            ++p;
-            break;
-          }
-          cell.push_back(*p++);
-        }
-        any = true;
-      }
-      const char* b = p;
-      while (p < end && *p != ',' && *p != '\n' && *p != '\r') ++p;
-      cell.append(b, p);
-      if (p > b) any = true;
-      if (line > 0) {
-        if (c >= n_columns)
-          return fail(OCF_ERR_INVALID, std::string(path) + ": line " + std::to_string(line + 1) + " has more than " +
-                                       std::to_string(n_columns) + " fields");
-        fields[c].push_back(cell);
-      }
-      ++c;
-      if (p < end && *p == ',') { ++p; any = true; continue; }
-      break;
-    }
-    if (p < end && *p == '\r') ++p;
-    if (p < end && *p == '\n') ++p;
-    if (line > 0) {
-      if (!any && c == 1) {                            // blank line: skipped (pandas skip_blank_lines)
-        fields[0].pop_back();
-      } else if (c != n_columns) {
-        return fail(OCF_ERR_INVALID, std::string(path) + ": line " + std::to_string(line + 1) + " has " + std::to_string(c) +
-                                     " fields, expected " + std::to_string(n_columns));
-      }
-    } else if (c != n_columns) {
-      return fail(OCF_ERR_INVALID, std::string(path) + ": the header has " + std::to_string(c) + " columns, the schema needs " +
-                                   std::to_string(n_columns) + " (TrainValidTestSplit.py:39-69)");
-    }
-    ++line;
-  }
-  csv->n_rows = (int64_t)fields[0].size();
-  // pass 2: column types as pandas.read_csv infers them: int64 if every field is an integer, float64 if
-  // every field is a number (empty = NaN), else strings
+  // pass 1: column types as pandas.read_csv infers them - int64 if every field is an integer, float64 if every
+  // field is a number (empty = NaN), else strings. Nothing is stored: a Netflix-sized file has 4 * 10^8 fields.
+  bool all_int[4] = {true, true, true, true}, all_num[4] = {true, true, true, true};
+  int64_t rows = scan_csv(text, n_columns, path, [&](int c, const char* b, const char* e) {
+    int64_t iv; double dv;
+    if (all_int[c] && !parse_int_field(b, e, &iv)) all_int[c] = false;
+    if (!all_int[c] && all_num[c] && !parse_float_field(b, e, &dv)) all_num[c] = false;
+  });
+  if (rows < 0) return OCF_ERR_INVALID;
+  csv->n_rows = rows;
   for (int c = 0; c < n_columns; ++c) {
     Column& col = csv->col[c];
-    auto& f = fields[c];
-    bool all_int = true, all_num = true;
-    for (auto& s : f) {
-      int64_t iv; double dv;
-      const char* b = s.data();
-      const char* e = b + s.size();
-      if (all_int && !parse_int_field(b, e, &iv)) all_int = false;
-      if (!all_int && !parse_float_field(b, e, &dv)) { all_num = false; break; }
-    }
-    if (all_int) {
-      col.type = Column::INT;
-      col.i.resize(f.size());
-      for (size_t k = 0; k < f.size(); ++k) parse_int_field(f[k].data(), f[k].data() + f[k].size(), &col.i[k]);
-    } else if (all_num) {
-      col.type = Column::FLT;
-      col.d.resize(f.size());
-      for (size_t k = 0; k < f.size(); ++k) parse_float_field(f[k].data(), f[k].data() + f[k].size(), &col.d[k]);
-    } else {
-      col.type = Column::STR;
-      col.s.swap(f);
-    }
-    std::vector<std::string>().swap(f);
-    if (col.type == Column::STR) csv->row_kind = RowKind::STR;
+    col.type = all_int[c] ? Column::INT : (all_num[c] ? Column::FLT : Column::STR);
+    if (col.type == Column::STR) { csv->row_kind = RowKind::STR; col.s.reserve((size_t)rows); }
     else if (col.type == Column::FLT && csv->row_kind == RowKind::INT) csv->row_kind = RowKind::FLT;
   }
+  // pass 2: values into their typed homes
+  csv->packed.assign((size_t)rows * 4, 0);
+  int64_t r = 0;
+  scan_csv(text, n_columns, path, [&](int c, const char* b, const char* e) {
+    Column& col = csv->col[c];
+    if (col.type == Column::INT) { int64_t v = 0; parse_int_field(b, e, &v); std::memcpy(&csv->packed[(size_t)r * 4 + c], &v, 8); }
+    else if (col.type == Column::FLT) { double v = 0; parse_float_field(b, e, &v); std::memcpy(&csv->packed[(size_t)r * 4 + c], &v, 8); }
+    else col.s.emplace_back(b, e);
+    if (c == n_columns - 1) ++r;
+  });
   *out = csv.release();
   return OCF_OK;
 }
@@ -806,23 +828,10 @@ struct Splitter {
   std::vector<int32_t> uid;                            // per CSV row: id of its user KEY (the dict key string)
   std::vector<std::string> ukey;
   std::string error;
-  // the numeric columns of a row side by side (int64 or double bits): the writers visit rows in permuted
-  // order, so one cache line per rating instead of one per column
-  std::vector<uint64_t> packed;
 
-  Splitter(const ocf_csv& c, bool reverse, bool cast) : csv(c), user_col(reverse ? 1 : 0), item_col(reverse ? 0 : 1), cast_user_to_int(cast) {
-    packed.assign((size_t)csv.n_rows * 4, 0);
-    for (int k = 0; k < csv.n_cols; ++k) {
-      const Column& col = csv.col[k];
-      if (col.type == Column::INT)
-        for (int64_t r = 0; r < csv.n_rows; ++r) std::memcpy(&packed[(size_t)r * 4 + k], &col.i[(size_t)r], 8);
-      else if (col.type == Column::FLT)
-        for (int64_t r = 0; r < csv.n_rows; ++r) std::memcpy(&packed[(size_t)r * 4 + k], &col.d[(size_t)r], 8);
-    }
-  }
-  int64_t int_at(int c, int64_t row) const { int64_t v; std::memcpy(&v, &packed[(size_t)row * 4 + c], 8); return v; }
-  double flt_at(int c, int64_t row) const { double v; std::memcpy(&v, &packed[(size_t)row * 4 + c], 8); return v; }
-
+  Splitter(const ocf_csv& c, bool reverse, bool cast) : csv(c), user_col(reverse ? 1 : 0), item_col(reverse ? 0 : 1), cast_user_to_int(cast) {}
+  int64_t int_at(int c, int64_t row) const { return csv.int_at(c, row); }
+  double flt_at(int c, int64_t row) const { return csv.flt_at(c, row); }
   // one value of a row as json.dump prints it after the row went through `ratings.iloc[i]`
   void json_value(int c, int64_t row, std::string* out) const {
     const Column& col = csv.col[c];
@@ -863,17 +872,17 @@ struct Splitter {
         error = "ValueError: invalid literal for int(): '" + col.s[(size_t)row] + "' (schema 'movielens' casts user ids to int)";
         return false;
       }
-      if (col.type == Column::INT) { out->append(std::to_string(col.i[(size_t)row])); return true; }
-      double d = col.d[(size_t)row];
+      if (col.type == Column::INT) { out->append(std::to_string(int_at(user_col, row))); return true; }
+      double d = flt_at(user_col, row);
       if (std::isnan(d) || std::isinf(d)) { error = "ValueError: cannot convert float NaN/inf to integer (user id)"; return false; }
       out->append(std::to_string((int64_t)std::trunc(d)));
       return true;
     }
     if (col.type == Column::STR) { out->append(col.s[(size_t)row]); return true; }
     if (csv.row_kind == RowKind::FLT || col.type == Column::FLT)
-      py_float_repr(col.type == Column::INT ? (double)col.i[(size_t)row] : col.d[(size_t)row], out, "nan", "inf");
+      py_float_repr(col.type == Column::INT ? (double)int_at(user_col, row) : flt_at(user_col, row), out, "nan", "inf");
     else
-      out->append(std::to_string(col.i[(size_t)row]));
+      out->append(std::to_string(int_at(user_col, row)));
     return true;
   }
   bool index_users() {
@@ -884,14 +893,14 @@ struct Splitter {
     std::string key;
     for (int64_t r = 0; r < csv.n_rows; ++r) {
       if (col.type == Column::INT) {
-        auto it = by_int.find(col.i[(size_t)r]);
+        auto it = by_int.find(csv.int_at(user_col, r));
         if (it != by_int.end()) { uid[(size_t)r] = it->second; continue; }
       }
       if (!user_key(r, &key)) return false;
       auto ins = by_key.emplace(key, (int32_t)ukey.size());
       if (ins.second) ukey.push_back(key);
       uid[(size_t)r] = ins.first->second;
-      if (col.type == Column::INT) by_int.emplace(col.i[(size_t)r], ins.first->second);
+      if (col.type == Column::INT) by_int.emplace(csv.int_at(user_col, r), ins.first->second);
     }
     return true;
   }
@@ -1091,12 +1100,12 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
         for (int64_t r = 0; r < n; ++r) if (seen.emplace(col.s[(size_t)r], 1).second) firsts.push_back(r);
       } else if (col.type == Column::INT) {
         std::unordered_map<int64_t, char> seen;
-        for (int64_t r = 0; r < n; ++r) if (seen.emplace(col.i[(size_t)r], 1).second) firsts.push_back(r);
+        for (int64_t r = 0; r < n; ++r) if (seen.emplace(csv->int_at(c, r), 1).second) firsts.push_back(r);
       } else {
         std::unordered_map<uint64_t, char> seen;
         bool nan_seen = false;
         for (int64_t r = 0; r < n; ++r) {
-          double d = col.d[(size_t)r];
+          double d = csv->flt_at(c, r);
           if (std::isnan(d)) { if (!nan_seen) { nan_seen = true; firsts.push_back(r); } continue; }
           if (d == 0.0) d = 0.0;                       // -0.0 and 0.0 are one value
           uint64_t b; std::memcpy(&b, &d, 8);
@@ -1113,8 +1122,8 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
       first = false;
       const Column& col = csv->col[sp.item_col];
       if (col.type == Column::STR) json_string(col.s[(size_t)r], &items.buf);
-      else if (col.type == Column::INT) items.buf.append(std::to_string(col.i[(size_t)r]));
-      else py_float_repr(col.d[(size_t)r], &items.buf, "NaN", "Infinity");
+      else if (col.type == Column::INT) items.buf.append(std::to_string(csv->int_at(sp.item_col, r)));
+      else py_float_repr(csv->flt_at(sp.item_col, r), &items.buf, "NaN", "Infinity");
       items.tick();
     }
     items.buf.push_back(']');
@@ -1130,12 +1139,13 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
       if (col.type == Column::STR) {
         if (cast_user_to_int) return fail(OCF_ERR_INVALID, "ValueError: invalid literal for int(): '" + col.s[(size_t)r] + "'");
         key = col.s[(size_t)r];
-      } else if (col.type == Column::INT) key = std::to_string(col.i[(size_t)r]);
+      } else if (col.type == Column::INT) key = std::to_string(csv->int_at(sp.user_col, r));
       else if (cast_user_to_int) {
-        if (std::isnan(col.d[(size_t)r]) || std::isinf(col.d[(size_t)r]))
+        const double d = csv->flt_at(sp.user_col, r);
+        if (std::isnan(d) || std::isinf(d))
           return fail(OCF_ERR_INVALID, "ValueError: cannot convert float NaN/inf to integer (user id)");
-        key = std::to_string((int64_t)std::trunc(col.d[(size_t)r]));
-      } else py_float_repr(col.d[(size_t)r], &key, "nan", "inf");
+        key = std::to_string((int64_t)std::trunc(d));
+      } else py_float_repr(csv->flt_at(sp.user_col, r), &key, "nan", "inf");
       json_string(key, &users.buf);
       users.tick();
     }
