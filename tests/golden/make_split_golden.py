@@ -148,6 +148,35 @@ def main():
             n += 1
         store["%s/n_batches" % which] = np.asarray(n)
         print("pipeline", which, "batches:", n)
+    # ablation mode from disk: `ratingsByUser_dict.json` (data_reader.py:55; no script of the reference writes it - it
+    # has the layout of the train file) + a `unique_users_list.json` in another order than the dict's keys
+    a = os.path.join(OUT, "ml_ablation") + "/"
+    os.makedirs(a)
+    shutil.copy(d + "ratingsByUser_dicts_train.json", a + "ratingsByUser_dict.json")
+    shutil.copy(d + "unique_items_list.json", a + "unique_items_list.json")
+    with open(a + "ratingsByUser_dict.json") as f:
+        users = sorted(json.load(f).keys(), key=lambda k: (len(k), k))[::-1]
+    with open(a + "unique_users_list.json", "w") as f:
+        json.dump(users, f)
+    rd = ref.data_reader(n_items, len(users), a, nonsequentialusers=True, use_json=True, eval_mode="ablation",
+                         useTimestamps=False, reverse_user_item_data=False)
+    np.random.seed(51)
+    rd.split_for_validation([0.6, 0.2, 0.2])
+    store["ablation/n_users"] = np.asarray(len(users))
+    for which, sparsity, seed in (("train", [0.2, 0.7], 52), ("test", [0.5, 0.5], 53)):
+        np.random.seed(seed)
+        gen = rd.data_gen(4, sparsity, train_val_test=which, shuffle=True, auxilliary_mask_type="causal", aux_var_value=-1)
+        n = 0
+        while True:
+            item = next(gen)
+            if item is None:
+                break
+            for k, arr in enumerate(item[0]):
+                store["ablation/%s/b%d/in%d" % (which, n, k)] = np.asarray(arr, dtype=np.float64)
+            store["ablation/%s/b%d/targets" % (which, n)] = np.asarray(item[1], dtype=np.float64)
+            n += 1
+        store["ablation/%s/n_batches" % which] = np.asarray(n)
+        print("ablation", which, "batches:", n)
     np.savez_compressed(os.path.join(OUT, "pipeline_batches.npz"), **store)
 
 

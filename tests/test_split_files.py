@@ -257,6 +257,28 @@ def test_reader_on_reference_files_yields_the_reference_batches():
     rd.close()
 
 
+def test_reader_in_ablation_mode_on_files_yields_the_reference_batches():
+    """`ratingsByUser_dict.json` + `unique_users_list.json` (rows follow the LIST's order, data_reader.py:30-44,124-128)."""
+    d = os.path.join(SPLIT, "ml_ablation") + "/"
+    gold = np.load(os.path.join(SPLIT, "pipeline_batches.npz"))
+    rd = data_reader(int(gold["n_items"]), int(gold["ablation/n_users"]), d, nonsequentialusers=True, use_json=True,
+                     eval_mode="ablation", useTimestamps=False, reverse_user_item_data=False, rng_on_device=False)
+    np.random.seed(51)
+    rd.split_for_validation([0.6, 0.2, 0.2])
+    for which, sparsity, seed in (("train", [0.2, 0.7], 52), ("test", [0.5, 0.5], 53)):
+        np.random.seed(seed)
+        gen = rd.data_gen(4, sparsity, train_val_test=which, shuffle=True, auxilliary_mask_type="causal", aux_var_value=-1)
+        n = int(gold["ablation/%s/n_batches" % which])
+        assert n > 0
+        for b in range(n):
+            feed, targets = host_densify(next(gen))
+            assert np.array_equal(targets, gold["ablation/%s/b%d/targets" % (which, b)])
+            for k, arr in enumerate(feed):
+                assert np.array_equal(arr, gold["ablation/%s/b%d/in%d" % (which, b, k)]), (which, b, k)
+        assert next(gen) is None
+    rd.close()
+
+
 def test_native_unique_lists_match_the_pipeline_fixture(tmp_path):
     case = [c for c in CASES if c["name"] == "ml"][0]
     out = _run(splitter.split_data, case, tmp_path, save_users_and_items=True)
