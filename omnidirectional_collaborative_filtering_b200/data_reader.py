@@ -413,6 +413,14 @@ class data_reader(object):
         else:
             self.densevec_to_users = {i: i for i in range(self.num_users)}
         base = "ratingsByItem" if reverse else "ratingsByUser"                                # :46-49
+        if reverse and self._files is None:
+            # the reference's splitter writes `ratingsByUser*` even for reversed data (TrainValidTestSplit.py:153-157)
+            # while its reader asks for `ratingsByItem*`: take whichever is on disk
+            import os
+            probe = "_dict" if self.eval_mode == "ablation" else "_dicts_train"
+            ext = ".json" if use_json else ".p"
+            if not os.path.exists(self.filepath + base + probe + ext) and os.path.exists(self.filepath + "ratingsByUser" + probe + ext):
+                base = "ratingsByUser"
         # JSON files on disk go through the native parser (csrc/ocf_etl.cpp): no Python object per rating.
         # In-memory `data=` dicts and pickles keep the per-rating Python loop (small / test inputs).
         native = self._files is None and use_json

@@ -279,6 +279,41 @@ def test_reader_in_ablation_mode_on_files_yields_the_reference_batches():
     rd.close()
 
 
+def test_reversed_data_is_found_under_either_file_name(tmp_path):
+    """reverse_user_item_data=True: the reader asks for `ratingsByItem_*` (data_reader.py:46-49) but the reference's
+    splitter writes `ratingsByUser_*` into reverse_item-user/ (TrainValidTestSplit.py:153-157); both are accepted, and
+    the column vocabulary is `unique_users_list` (data_reader.py:20-23)."""
+    case = [c for c in CASES if c["name"] == "ml_rev"][0]
+    src = _golden_dir(case)
+    with open(os.path.join(src, "ratingsByUser_dicts_train.json")) as f:
+        train = json.load(f)
+    cols = []
+    for which in ("train", "valid", "test"):
+        with open(os.path.join(src, "ratingsByUser_dicts_%s.json" % which)) as f:
+            obj = json.load(f)
+        for half in (obj if which != "train" else [obj]):
+            for lst in half.values():
+                cols += [int(p[0]) for p in (lst or [])]
+    cols = list(dict.fromkeys(cols))
+    readers = []
+    for name in ("ratingsByUser", "ratingsByItem"):
+        d = str(tmp_path / name) + "/"
+        os.makedirs(d)
+        for which in ("train", "valid", "test"):
+            shutil.copy(os.path.join(src, "ratingsByUser_dicts_%s.json" % which), d + "%s_dicts_%s.json" % (name, which))
+        with open(d + "unique_users_list.json", "w") as f:
+            json.dump(cols, f)
+        readers.append(data_reader(len(cols), len(train), d, use_json=True, eval_mode="fixed_split",
+                                   reverse_user_item_data=True, rng_on_device=False))
+    a, b = readers
+    assert a.train_set == b.train_set == list(train.keys()) and a.val_set == b.val_set
+    for which in ("train",):
+        _same_csr(a.store(which).csr, b.store(which).csr)
+    assert a.store("train").csr.nnz == sum(len(l) for l in train.values())
+    for r in readers:
+        r.close()
+
+
 def test_native_unique_lists_match_the_pipeline_fixture(tmp_path):
     case = [c for c in CASES if c["name"] == "ml"][0]
     out = _run(splitter.split_data, case, tmp_path, save_users_and_items=True)
