@@ -219,13 +219,19 @@ def make_dataset(w, seed=0):
     return fs
 
 
+def n_unique(a):
+    """Number of distinct values (sort + compare; NumPy 2.3's hash-based np.unique is ~50x slower on these sizes)."""
+    a = np.sort(np.asarray(a).ravel())
+    return int(np.count_nonzero(a[1:] != a[:-1]) + 1) if a.size else 0
+
+
 def touched(batch, k_mask_blocks):
     """Unique catalogue columns the batch touches as inputs / as targets (for algorithmic bytes)."""
     csr = batch.source.csr
     cols = np.concatenate([csr.col[csr.rowptr[r]:csr.rowptr[r + 1]] for r in batch.rows])
     f = batch.flags.astype(bool)
-    u_in = np.unique(cols[f]).size
-    u_tg = np.unique(cols if batch.pass_through else cols[~f]).size
+    u_in = n_unique(cols[f])
+    u_tg = n_unique(cols if batch.pass_through else cols[~f])
     return u_in, u_tg, int(f.sum()), int(cols.size if batch.pass_through else (~f).sum())
 
 
@@ -240,8 +246,8 @@ def step_bytes(plans, w, nnz_store, n_obs_sample=8):
     k_in = 1 + (1 if aux in ("dropout", "both") else 0)          # encoder blocks selected by the input bit
     k_obs = (1 if aux in ("causal", "both") else 0)
     st = np.array([touched(p, 0) for p in plans], dtype=np.float64).mean(axis=0)   # u_in, u_tg, n_in, n_tg
-    u_obs = np.mean([np.unique(np.concatenate([p.source.csr.col[p.source.csr.rowptr[r]:p.source.csr.rowptr[r + 1]]
-                                               for r in p.rows])).size for p in plans[:n_obs_sample]])
+    u_obs = np.mean([n_unique(np.concatenate([p.source.csr.col[p.source.csr.rowptr[r]:p.source.csr.rowptr[r + 1]]
+                                              for r in p.rows])) for p in plans[:n_obs_sample]])
     n_all = float(np.mean([p.n_entries for p in plans]))
     state_words = {"sgd": 2, "adagrad": 4, "rmsprop": 4, "adam": 6}[w["opt"][0]]
     return [
