@@ -131,6 +131,49 @@ class OracleNet(object):
         return rec
 
 
+def oracle_train_run_ablation(user_dict, unique_cols, unique_rows, cfg, seed, init_model, rating_range):
+    """The ablation branch of the script (train.py:85-86,147-177,202-213): rows split 80/10/10 by one permutation
+    drawn BEFORE the model is built, every set goes through the random reciprocal split, the test set once per
+    entry of `test_sparsities`."""
+    from oracle import ref_model
+    c = cfg
+    data = ref_batches.RefData(len(unique_cols), len(unique_rows), unique_cols, eval_mode="ablation", user_dict=user_dict,
+                               nonsequentialusers=True, unique_rows=unique_rows)
+    np.random.seed(seed)
+    ref_batches.split_rows(data, c.val_split, rng=np.random)          # train.py:86 (global stream, before the model)
+    twin = init_model()
+    rng = np.random.RandomState()
+    rng.set_state(np.random.get_state())
+    ref = ref_model.RefModel(c.numlayers, c.num_hidden_units, len(unique_cols), c.batch_size,
+                             dense_activation=c.activation_type, use_causal_info=c.use_causal_info,
+                             use_both_masks=c.auxilliary_mask_type == "both", dropout_probability=c.dropout_probability,
+                             dtype=np.float32, rng=np.random.RandomState(0))
+    ref.set_weights(twin.model.get_weights())
+    ref.dropout_seed = twin.dropout_seed
+    ref.compile(ref_model.RefOptimizer("adagrad", lr=c.learning_rate), c.model_loss, rating_range=rating_range)
+    B = c.batch_size
+
+    def gen(which, sparsity, **kw):
+        return ref_batches.batch_stream(data, B, sparsity, which, c.shuffle_data_every_epoch, c.auxilliary_mask_type,
+                                        c.aux_var_value, rng=rng, vectorised=True, **kw)
+
+    history, min_loss, best, best_weights = [], None, 0, None
+    for _ in range(c.max_epochs):
+        h = ref.fit_generator(gen("train", c.train_sparsity, pass_through_input_training=c.pass_through_input_training),
+                              np.floor(data.train_set_size / B) - 1, validation_data=gen("valid", c.train_sparsity),
+                              validation_steps=np.floor(data.val_set_size / B) - 1)
+        history.append({k: v[-1] for k, v in h.items()})
+        val = history[-1][c.early_stopping_metric]
+        if not best_weights or val < min_loss:
+            min_loss, best, best_weights = val, len(history) - 1, ref.get_weights()
+    ref.set_weights(best_weights)
+    test = {}
+    for s in c.test_sparsities:                                         # train.py:204-213
+        vals = ref.evaluate_generator(gen("test", [s, s]), np.floor(data.test_set_size / B) - 1)
+        test[s] = dict(zip(ref_model.METRIC_NAMES, vals))
+    return {"history": history, "best_epoch": best, "test": test}
+
+
 def oracle_train_run(fs, cfg, seed, init_model):
     """`train.py:147-177,215-254` driven through the oracle alone on one RandomState stream: the
     per-epoch histories, the fixed-split test metrics and the manual test RMSE a `train.run` of the

@@ -76,3 +76,40 @@ def test_train_run_host_logic_is_the_oracle_loop(monkeypatch, name):
     want = oracle_train_run(fs, cfg, 5, init_model_for(cfg, fs.n_cols))
     assert_same_run(got, want, rtol=0)
     rd.close()
+
+
+def test_train_run_ablation_mode_is_the_oracle_loop(monkeypatch, golden_datasets):
+    """eval_mode='ablation' (train.py:85-86,202-213): the row split is drawn before the model is built, validation
+    and test batches go through the random split too, one evaluation per test sparsity (scalars accepted)."""
+    from tests.helpers import oracle_train_run_ablation, product_reader
+    ds = golden_datasets["rev"]
+    rd = product_reader(ds, "ablation")
+    rd.rng_on_device = False
+    cfg = train_config("omni", eval_mode="ablation", batch_size=4, num_hidden_units=10, test_sparsities=[0.0, 0.5, 0.9],
+                       val_split=[0.6, 0.2, 0.2])
+    N = ds["n_cols"]
+    real_omni = ocf_train.omni_model
+
+    def oracle_backed(*a, **k):
+        om = real_omni(*a, **k)
+        ref = ref_model.RefModel(cfg.numlayers, cfg.num_hidden_units, N, cfg.batch_size, dense_activation=cfg.activation_type,
+                                 use_causal_info=cfg.use_causal_info, dropout_probability=cfg.dropout_probability,
+                                 dtype=np.float32, rng=np.random.RandomState(0))
+        ref.set_weights(om.model.get_weights())
+        ref.dropout_seed = om.dropout_seed
+        om.model = OracleNet(ref, owner=om)
+        return om
+
+    monkeypatch.setattr(ocf_train, "omni_model", oracle_backed)
+    np.random.seed(9)
+    got = ocf_train.run(cfg, reader=rd, rating_range=4.0, save_models=False, verbose=0)
+    monkeypatch.setattr(ocf_train, "omni_model", real_omni)
+    want = oracle_train_run_ablation(ds["ablation"], ds["unique_cols"], ds["unique_rows"], cfg, 9,
+                                     init_model_for(cfg, N), 4.0)
+    assert got["best_epoch"] == want["best_epoch"] and len(got["history"]) == len(want["history"])
+    for g, w in zip(got["history"], want["history"]):
+        assert g == w
+    assert set(got["test"]) == set(want["test"])
+    for s, vals in want["test"].items():
+        assert got["test"][s] == vals
+    rd.close()
