@@ -284,7 +284,15 @@ struct Json {
     return true;
   }
 
+  int depth = 0;
+  struct Nest {                                         // bounds the recursion of skip_value on hostile input
+    Json* j;
+    explicit Nest(Json* js) : j(js) { ++j->depth; }
+    ~Nest() { --j->depth; }
+  };
   bool skip_value() {
+    Nest nest(this);
+    if (depth > 256) return bad("nesting deeper than 256 levels");
     char c = peek();
     if (c == '"') { std::string s; return string(&s); }
     if (c == '{') {

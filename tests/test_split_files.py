@@ -195,6 +195,7 @@ def test_native_ingest_json_corner_cases(tmp_path):
     ('{"a": [[153, "5"]]}', "number"),
     ('{"a": [[153, 1.0]]} x', "trailing"),
     ('[[{}, {}], {}]', "_withtimestamps_"),
+    ('{"a": [[153, 1.0, ' + "[" * 100000 + ']]}', "nesting"),
 ])
 def test_native_ingest_errors(tmp_path, text, message):
     vocab = str(tmp_path / "v.json")
