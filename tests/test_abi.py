@@ -81,3 +81,22 @@ int main(int argc, char** argv) {
     (tmp_path / "t.json").write_text(json.dumps({"a": [[10, 1.0], [30.0, 2.5]], "b": [[20, 4]]}))
     out = subprocess.run([exe, str(tmp_path / "v.json"), str(tmp_path / "t.json")], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "2 rows 3 ratings", (out.returncode, out.stdout, out.stderr)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package imports it, and importing the whole package
+    leaves `oracle` out of sys.modules (a product path routed through the oracle would void every parity claim)."""
+    import os
+    import sys
+    pkg = os.path.dirname(_lib.HERE + "/")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                with open(os.path.join(root, f), errors="replace") as fh:
+                    text = fh.read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+    code = ("import sys; sys.path.insert(0, %r); "
+            "import omnidirectional_collaborative_filtering_b200 as p; "
+            "from omnidirectional_collaborative_filtering_b200 import data_reader, model, train, dist, ingest, splitter, store, synthetic, optimizers; "
+            "assert not [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]" % os.path.dirname(pkg))
+    subprocess.run([sys.executable, "-c", code], check=True)
