@@ -95,7 +95,8 @@ struct Vocab {
     if (ints.empty()) return;
     int64_t mn = INT64_MAX, mx = INT64_MIN;
     for (auto& kv : ints) { mn = std::min(mn, kv.first); mx = std::max(mx, kv.first); }
-    if (mx - mn < (int64_t)(1 << 28) && mx - mn < 64 * (int64_t)ints.size() + 1024) {
+    const uint64_t span = (uint64_t)mx - (uint64_t)mn;          // no signed overflow for ids near +-2^63
+    if (span < (uint64_t)(1 << 28) && span < 64 * (uint64_t)ints.size() + 1024) {
       lo = mn;
       window.assign((size_t)(mx - mn + 1), -1);
       for (auto& kv : ints) window[(size_t)(kv.first - mn)] = kv.second;
@@ -1034,6 +1035,8 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
     }
   }
   const std::string dir(out_dir);
+  for (int k = 0; k < 3; ++k)
+    if (!(fractions[k] >= 0.0 && fractions[k] <= 1.0)) return fail(OCF_ERR_INVALID, "ocf_split_write: a split fraction is outside [0, 1]");
   const int64_t n_tr = (int64_t)((double)n * fractions[0]);                  // :76-78 int(num_ratings * f)
   const int64_t n_va = (int64_t)((double)n * fractions[1]);
   if (n_tr + n_va > n) return fail(OCF_ERR_INVALID, "ocf_split_write: split fractions exceed 1");

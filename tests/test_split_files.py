@@ -315,6 +315,26 @@ def test_reversed_data_is_found_under_either_file_name(tmp_path):
         r.close()
 
 
+def test_splitter_rejects_bad_arguments(tmp_path):
+    csv = os.path.join(SPLIT, "ml", "ratings.csv")
+    for bad in ((1.2, 0.1, 0.1), (-0.1, 0.5, 0.5), (0.7, 0.7, 0.1), (float("nan"), 0.1, 0.1)):
+        with pytest.raises(_lib.OcfError, match="fraction"):
+            splitter.split_data(csv, str(tmp_path) + "/", "movielens", bad, include_timestamps=False)
+    with pytest.raises(_lib.OcfError, match="header has 4 columns"):
+        splitter.split_data(csv, str(tmp_path) + "/", "netflix", include_timestamps=False)
+    with pytest.raises(_lib.OcfError, match="timestamp"):
+        splitter.split_data(os.path.join(SPLIT, "netflix_int", "ratings.csv"), str(tmp_path) + "/", "netflix", include_timestamps=True)
+    with pytest.raises(ValueError):
+        splitter.split_data(csv, str(tmp_path) + "/", "lastfm")
+    # ids at the ends of the int64 range do not upset the id -> column window
+    v = tmp_path / "v.json"
+    v.write_text("[9223372036854775807, -9223372036854775807, 5]")
+    t = tmp_path / "t.json"
+    t.write_text('{"a": [[-9223372036854775807, 1.5], [5, 2], [9223372036854775807, 3]]}')
+    keys, csr = ingest.load_ratings(str(t), ingest.Vocab(str(v)), False)
+    assert csr.col.tolist() == [1, 2, 0]
+
+
 def test_native_unique_lists_match_the_pipeline_fixture(tmp_path):
     case = [c for c in CASES if c["name"] == "ml"][0]
     out = _run(splitter.split_data, case, tmp_path, save_users_and_items=True)
