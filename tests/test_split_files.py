@@ -107,6 +107,33 @@ def test_native_splitter_equals_oracle_on_random_csvs(tmp_path_factory, rows, sc
     shutil.rmtree(d)
 
 
+def test_float_formatting_matches_python_repr_over_the_double_range(tmp_path):
+    """json.dump / to_csv print floats with float.__repr__: shortest round-trip digits, fixed notation for
+    1e-4 <= |x| < 1e16, else exponent form. 4 000 ratings spread over every binade (+ the notation boundaries,
+    subnormals, the largest double) go through the native splitter and the Python oracle."""
+    import random
+    import struct
+    rnd = random.Random(1)
+    vals = [1e16, 9999999999999998.0, 1e15, 0.0001, 0.00009999, 5e-324, 1.7976931348623157e308, 2.2250738585072014e-308,
+            1e22, 1e23, 0.1, 0.30000000000000004, 1 / 3, 100.0, 1e-7, 2.675, 1e21, -0.0, -1e-320, 12345678901234567.0]
+    while len(vals) < 4000:
+        v = struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(64)))[0]
+        if v == v and abs(v) != float("inf"):
+            vals.append(v)
+            vals.append(round(rnd.uniform(-1000, 1000), rnd.randint(0, 6)))
+    d = str(tmp_path) + "/"
+    with open(d + "r.csv", "w") as f:
+        f.write("u,i,r,t\n")
+        for k, v in enumerate(vals):
+            f.write("%d,%s,%s,%d\n" % (k % 50, repr(float(k % 97) + 0.25 * (k % 3)), repr(v), k))
+    os.makedirs(d + "n"), os.makedirs(d + "o")
+    for fn, sub in ((splitter.split_data, "n/"), (ref_split.split_data, "o/")):
+        np.random.seed(0)
+        fn(d + "r.csv", d + sub, "amazon", (.8, .1, .1), True, True, True, False)
+    for name in sorted(os.listdir(d + "o")):
+        assert filecmp.cmp(d + "n/" + name, d + "o/" + name, shallow=False), name
+
+
 # ---- ingest ------------------------------------------------------------------------------------------
 
 def _python_ingest(path, col_of, paired, n_cols):
