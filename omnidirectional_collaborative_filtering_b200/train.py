@@ -77,8 +77,14 @@ def compute_full_RMSE(predictions, targets, ratings_count):
 
 
 def run(config: TrainConfig, reader: Optional[DataReader] = None, metadata: Optional[dict] = None,
-        rating_range: Optional[float] = None, save_models: bool = True, verbose: int = 1) -> dict:
-    """The body of `train.py`. Returns a dict with the history, the best epoch and test results."""
+        rating_range: Optional[float] = None, save_models: bool = True, verbose: int = 1,
+        reference_first_epoch_fallback: bool = False) -> dict:
+    """The body of `train.py`. Returns a dict with the history, the best epoch and test results.
+
+    `reference_first_epoch_fallback`: the reference never saves epoch 1 (train.py:164-165), so when epoch 1 stays
+    the best its reload of "the best model" fails and it tests the LIVE model, i.e. the last epoch's weights
+    (train.py:194-197). False (default) tests epoch 1's weights, which is what the script means to do; True
+    reproduces what it does."""
     c = config
     if c.useTimestamps or c.use_sparse_representation or c.use_experimental_sparse_masking_layer:
         raise NotImplementedError("timestamps / sparse representation / experimental masking layer are out of scope")
@@ -156,7 +162,8 @@ def run(config: TrainConfig, reader: Optional[DataReader] = None, metadata: Opti
             print("Val history: ", val_history)
             break
     # Testing (train.py:181-199): the best-validation weights, optimizer state dropped
-    m.set_weights(best_weights)
+    if not (reference_first_epoch_fallback and best_epoch == 0):
+        m.set_weights(best_weights)
     if save_models:
         m.save(os.path.join(c.model_save_path, save_name + "_bestValidScore"))
     print("Testing model from epoch: ", best_epoch + 1)

@@ -211,3 +211,9 @@ def test_train_run_follows_the_reference_loop(monkeypatch, tmp_path, case):
         assert want["tested"] == "live"
     if case["eval_mode"] == "fixed_split":
         assert res["manual_test_rmse"] == pytest.approx(want["manual_rmse"], rel=1e-6)
+    # with the fallback switched on the reference's accident is reproduced: nothing is restored, the live model is tested
+    net2 = _RecordingNet(case["script"], [])
+    _Owner.model = net2
+    rd2 = _RecordingReader(case["sizes"], len(case["script"]) * 7 + case["patience"], [])
+    ocf_train.run(cfg, reader=rd2, rating_range=4.0, verbose=0, reference_first_epoch_fallback=True)
+    assert net2.weights_set == (None if want["tested"] == "live" else want["best_epoch"] + 1)
