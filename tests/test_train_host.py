@@ -217,3 +217,37 @@ def test_train_run_follows_the_reference_loop(monkeypatch, tmp_path, case):
     rd2 = _RecordingReader(case["sizes"], len(case["script"]) * 7 + case["patience"], [])
     ocf_train.run(cfg, reader=rd2, rating_range=4.0, verbose=0, reference_first_epoch_fallback=True)
     assert net2.weights_set == (None if want["tested"] == "live" else want["best_epoch"] + 1)
+
+
+def test_parameter_surface_is_the_reference_scripts():
+    """`TrainConfig` = the module-level parameters of train.py:22-59 (names, defaults, the save-name expression);
+    `splitter.split_data` = those of TrainValidTestSplit.py:17-25. The fixture is read out of the reference's source
+    with `ast` (tests/golden/make_params_golden.py)."""
+    import dataclasses
+    import inspect
+    from omnidirectional_collaborative_filtering_b200 import splitter
+    with open(os.path.join(GOLDEN, "script_params.json")) as f:
+        gold = json.load(f)
+    fields = {f.name: f for f in dataclasses.fields(ocf_train.TrainConfig)}
+    want = dict(gold["train"])
+    want.pop("model_save_name")                              # an expression of the others: checked below
+    assert set(fields) == set(want)
+    cfg = ocf_train.TrainConfig()
+    for name, spec in want.items():
+        if "value" in spec:
+            assert getattr(cfg, name) == spec["value"], name
+        else:                                                # optimizer = Adagrad(lr=learning_rate, epsilon=1e-08, decay=0.0)
+            assert name == "optimizer" and spec["source"] == "Adagrad(lr=learning_rate, epsilon=1e-08, decay=0.0)"
+            assert cfg.optimizer is None                     # run() builds exactly that one
+    assert cfg.model_save_name() == gold["default_model_save_name_prefix"]
+    cfg2 = ocf_train.TrainConfig(train_sparsity=[0.5, 0.5], numlayers=2, l2_weight_regulatization=0.01, auxilliary_mask_type="both",
+                                 reverse_user_item_data=False, dataset="netflix")
+    assert cfg2.model_save_name() == ("stackedDenoising_WITHfinetuning_[0.5, 0.5]trainSparsity_128bs_2lay_512hu_0.005lr_"
+                                      "0.01regul_both_sigmoid_netflix_")
+    sig = inspect.signature(splitter.split_data)
+    assert list(sig.parameters) == ["full_data_filepath", "output_filepath", "schema_type", "trainvalidtest_split",
+                                    "build_data_for_omni", "include_timestamps", "save_users_and_items", "reverse_user_item_data"]
+    assert set(sig.parameters) == set(gold["split"])
+    for name, spec in gold["split"].items():
+        default = sig.parameters[name].default
+        assert (list(default) if isinstance(default, tuple) else default) == spec["value"], name
