@@ -251,3 +251,25 @@ def test_parameter_surface_is_the_reference_scripts():
     for name, spec in gold["split"].items():
         default = sig.parameters[name].default
         assert (list(default) if isinstance(default, tuple) else default) == spec["value"], name
+
+
+def test_class_signatures_are_the_reference_classes():
+    """`data_reader(...)`, `.data_gen(...)`, `.split_for_validation(...)`, `omni_model(...)` and its helpers take the
+    reference's parameters in the reference's order with the reference's defaults (data_reader.py:12,300,314;
+    model.py:34-35,102-170); extra keyword parameters may only follow them."""
+    import inspect
+    from omnidirectional_collaborative_filtering_b200.data_reader import data_reader
+    from omnidirectional_collaborative_filtering_b200.model import omni_model
+    with open(os.path.join(GOLDEN, "script_params.json")) as f:
+        sigs = json.load(f)["signatures"]
+    assert len(sigs) == 10
+    for qual, params in sigs.items():
+        cls, fn = qual.split(".")
+        got = list(inspect.signature(getattr({"data_reader": data_reader, "omni_model": omni_model}[cls], fn)).parameters.values())[1:]
+        assert [p.name for p in got[:len(params)]] == [n for n, _ in params], qual
+        for p, (n, d) in zip(got, params):
+            assert (p.default is inspect.Parameter.empty) == (d == "<required>"), (qual, n)
+            if d != "<required>":
+                assert p.default == d, (qual, n)
+        for extra in got[len(params):]:
+            assert extra.default is not inspect.Parameter.empty, (qual, extra.name)     # additions are optional
