@@ -13,8 +13,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -1047,10 +1049,27 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
   Splitter sp(*csv, reverse_user_item_data != 0, cast_user_to_int != 0);
   const char* suffix = include_timestamps ? "_withtimestamps" : "";
 
+  // The output files are independent of each other: each is produced by its own thread (a task returns its
+  // error message, empty = ok; the first one is reported). Only the per-row dicts wait for the user index.
+  std::vector<std::thread> threads;
+  std::vector<std::unique_ptr<std::string>> errors;
+  auto spawn = [&](std::function<std::string()> task) {
+    errors.emplace_back(new std::string());
+    std::string* slot = errors.back().get();
+    threads.emplace_back([task, slot] { *slot = task(); });
+  };
+  auto join_all = [&]() -> int {
+    for (auto& t : threads) t.join();
+    threads.clear();
+    for (auto& e : errors)
+      if (!e->empty()) return fail(OCF_ERR_INVALID, *e);
+    return OCF_OK;
+  };
+
   // convert_and_save_mml (:213-219): train+valid and test as userId,itemId,rating[,timestamp] lines
-  auto save_mml = [&](const int64_t* rows, int64_t count, const std::string& name) -> bool {
+  auto save_mml = [&sp, &dir, include_timestamps](const int64_t* rows, int64_t count, const std::string& name) -> std::string {
     Out o;
-    if (!o.open(dir + name)) return false;
+    if (!o.open(dir + name)) return "cannot write " + dir + name;
     for (int64_t k = 0; k < count; ++k) {
       sp.csv_value(sp.user_col, rows[k], &o.buf); o.buf.push_back(',');
       sp.csv_value(sp.item_col, rows[k], &o.buf); o.buf.push_back(',');
@@ -1059,32 +1078,32 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
       o.buf.push_back('\n');
       o.tick();
     }
-    return o.close();
+    return o.close() ? "" : "write failed: " + dir + name;
   };
-  if (!save_mml(order, n_in, std::string("train_data_mml") + suffix + ".csv") ||
-      !save_mml(te, n_te, std::string("test_data_mml") + suffix + ".csv"))
-    return fail(OCF_ERR_INVALID, "cannot write the mymedialite CSVs under " + dir);
+  spawn([&] { return save_mml(order, n_in, std::string("train_data_mml") + suffix + ".csv"); });
+  spawn([&] { return save_mml(te, n_te, std::string("test_data_mml") + suffix + ".csv"); });
 
+  Groups g_tr, g_va, g_te, g_in;
   if (build_data_for_omni) {
-    if (!sp.index_users()) return fail(OCF_ERR_INVALID, sp.error);
-    Groups g_tr, g_va, g_te, g_in;
-    g_tr.build(sp, tr, n_tr);
-    g_va.build(sp, va, n_va);
-    g_te.build(sp, te, n_te);
-    g_in.build(sp, order, n_in);                        // :102 a fresh dict of train+valid, in split order
-    auto path = [&](const char* which) { return dir + "ratingsByUser_dicts" + suffix + "_" + which + ".json"; };
+    if (!sp.index_users()) { join_all(); return fail(OCF_ERR_INVALID, sp.error); }
+    {
+      std::thread a([&] { g_tr.build(sp, tr, n_tr); }), b([&] { g_va.build(sp, va, n_va); }), c([&] { g_te.build(sp, te, n_te); });
+      g_in.build(sp, order, n_in);                      // :102 a fresh dict of train+valid, in split order
+      a.join(); b.join(); c.join();
+    }
+    auto path = [dir, suffix](const char* which) { return dir + "ratingsByUser_dicts" + suffix + "_" + which + ".json"; };
     const bool ts = include_timestamps != 0;
-    {                                                   // train: the dict, or (ratings, timestamps) (:162-166)
+    spawn([&, path, ts]() -> std::string {              // train: the dict, or (ratings, timestamps) (:162-166)
       Out o;
-      if (!o.open(path("train"))) return fail(OCF_ERR_INVALID, "cannot write " + path("train"));
+      if (!o.open(path("train"))) return "cannot write " + path("train");
       if (ts) o.buf.push_back('[');
       write_dict(sp, g_tr, sp.rating_col, &o);
       if (ts) { o.buf.append(", "); write_dict(sp, g_tr, sp.ts_col, &o); o.buf.push_back(']'); }
-      if (!o.close()) return fail(OCF_ERR_INVALID, "write failed: " + path("train"));
-    }
-    auto paired = [&](const char* which, const Groups& tg, const Groups& in) -> int {   // :167-175
+      return o.close() ? "" : "write failed: " + path("train");
+    });
+    auto paired = [&sp, path, ts](const char* which, const Groups& tg, const Groups& in) -> std::string {   // :167-175
       Out o;
-      if (!o.open(path(which))) return fail(OCF_ERR_INVALID, "cannot write " + path(which));
+      if (!o.open(path(which))) return "cannot write " + path(which);
       o.buf.push_back('[');
       if (ts) o.buf.push_back('[');
       write_paired_inputs(sp, tg, in, sp.rating_col, &o);
@@ -1092,12 +1111,12 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
       write_dict(sp, tg, sp.rating_col, &o);
       if (ts) { o.buf.append("], "); write_merged_timestamps(sp, in, tg, &o); }
       o.buf.push_back(']');
-      if (!o.close()) return fail(OCF_ERR_INVALID, "write failed: " + path(which));
-      return OCF_OK;
+      return o.close() ? "" : "write failed: " + path(which);
     };
-    if (int rc = paired("valid", g_va, g_tr)) return rc;
-    if (int rc = paired("test", g_te, g_in)) return rc;
+    spawn([&, paired] { return paired("valid", g_va, g_tr); });
+    spawn([&, paired] { return paired("test", g_te, g_in); });
   }
+  if (int rc = join_all()) return rc;
 
   if (save_users_and_items) {                           // :105-118, ids in first-appearance order of the file
     Out items, users;

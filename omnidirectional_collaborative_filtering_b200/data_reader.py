@@ -446,9 +446,14 @@ class data_reader(object):
                 csr = _csr_from_lists(lists, self.items_to_densevec, N)
             self._stores["train"] = RatingStore(csr, build_csc=True)
         elif native:
-            self.train_set, train = load(base + "_dicts_train", False)                        # :67-70, :78-80
-            self.val_set, va_in, _, va_tg = load(base + "_dicts_valid", True)
-            self.test_set, te_in, _, te_tg = load(base + "_dicts_test", True)
+            # the three files parse concurrently (ctypes releases the GIL inside the library)
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=3) as pool:
+                jobs = [pool.submit(load, base + "_dicts_train", False), pool.submit(load, base + "_dicts_valid", True),
+                        pool.submit(load, base + "_dicts_test", True)]
+                self.train_set, train = jobs[0].result()                                      # :67-70, :78-80
+                self.val_set, va_in, _, va_tg = jobs[1].result()
+                self.test_set, te_in, _, te_tg = jobs[2].result()
             self._set_sizes()
             self._stores["train"] = RatingStore(train, build_csc=True)
             self._stores["valid"] = StorePair(RatingStore(va_in), RatingStore(va_tg))

@@ -48,7 +48,9 @@ def main():
     d = tempfile.mkdtemp(prefix="ocf_etl_") + "/"
     write_csv(d + "ratings.csv", u, i, r, n)
     out = {"workload": "ml1m-shaped synthetic CSV, %d ratings, schema movielens, include_timestamps=False" % n,
-           "cores": 1}
+           "cores": {"native_splitter": "1 thread for the CSV parse and the user index, then one thread per output file (5)",
+                     "reference_splitter": 1, "native_ingest": "1 (files one after the other); the reader parses its 3 files on 3 threads",
+                     "python_ingest": 1}}
     np.random.seed(1)
     t0 = time.perf_counter()
     quiet(splitter.split_data, d + "ratings.csv", d + "native/", "movielens", include_timestamps=False,
@@ -95,6 +97,12 @@ def main():
     t = time.perf_counter() - t0
     out["python_ingest"] = {"seconds": t, "ratings_per_s": total / t, "what": "json.load + per-rating dict lookup (data_reader.py:85-92,134-136)"}
     out["ingest_speedup"] = out["python_ingest"]["seconds"] / out["native_ingest"]["seconds"]
+    from concurrent.futures import ThreadPoolExecutor
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        list(pool.map(lambda a: ingest.load_ratings(d + "native/" + a[0] + ".json", vocab, a[1]), files))
+    t = time.perf_counter() - t0
+    out["native_ingest_3_threads"] = {"seconds": t, "ratings_per_s": total / t}
     print(json.dumps(out, indent=1))
 
 

@@ -15,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORK = "/tmp/ocf_etl_fuzz"
 os.makedirs(WORK, exist_ok=True)
-subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-w", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", WORK + "/drv",
+subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-w", "-pthread", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", WORK + "/drv",
                 os.path.join(ROOT, "scripts", "etl_fuzz_driver.cpp")], check=True)
 os.chdir(WORK)
 random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
