@@ -166,6 +166,44 @@ def row_parallel_model(native, numlayers, num_hidden_units, input_shape, batch_s
     return om
 
 
+def merge_topk(parts: Sequence, k: int):
+    """The k best columns per row over the whole catalogue from the shards' own top-k lists
+    (`model.recommend` of a column shard returns global column ids): (columns int32 [B, k], scores float32 [B, k]),
+    best first, ties broken by the lower column - the order `recommend` itself uses. Empty slots (column -1,
+    score -inf) sort last."""
+    cols = np.concatenate([np.asarray(c, dtype=np.int32) for c, _ in parts], axis=1)
+    scores = np.concatenate([np.asarray(v, dtype=np.float32) for _, v in parts], axis=1)
+    empty = cols < 0
+    # lexsort: last key is primary. Primary: empty slots last; then score descending; then column ascending
+    order = np.lexsort((cols, -scores.astype(np.float64), empty), axis=1)[:, :int(k)]
+    rows = np.arange(cols.shape[0])[:, None]
+    out_c, out_s = cols[rows, order], scores[rows, order]
+    if out_c.shape[1] < k:                           # fewer candidates than k: pad like recommend does
+        pad = int(k) - out_c.shape[1]
+        out_c = np.concatenate([out_c, np.full((out_c.shape[0], pad), -1, dtype=np.int32)], axis=1)
+        out_s = np.concatenate([out_s, np.full((out_s.shape[0], pad), -np.inf, dtype=np.float32)], axis=1)
+    return out_c, out_s
+
+
+def all_gather_topk(cols, scores, k: int, group=None):
+    """`merge_topk` over the ranks of a column-sharded model: every rank gets the catalogue-wide top k."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    packed = torch.from_numpy(np.concatenate([np.asarray(cols, dtype=np.int32).view(np.float32),
+                                              np.asarray(scores, dtype=np.float32)], axis=1).copy())
+    if dist.get_backend(group) == "nccl":
+        packed = packed.cuda()
+    bucket = [torch.empty_like(packed) for _ in range(world)]
+    dist.all_gather(bucket, packed, group=group)
+    kk = np.asarray(cols).shape[1]
+    parts = []
+    for t in bucket:
+        a = t.cpu().numpy()
+        parts.append((a[:, :kk].copy().view(np.int32), a[:, kk:]))
+    return merge_topk(parts, k)
+
+
 def gather_full_weights(om, group=None) -> List[np.ndarray]:
     """Full Keras-layout weight list assembled from all ranks (every rank gets it)."""
     import torch.distributed as dist

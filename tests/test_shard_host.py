@@ -89,6 +89,13 @@ def _gloo_worker(rank, world, port, ds, out):
         dist.all_gather_object(parts, ocf_dist.slice_weights(full, 1, N, lo, hi))
         merged = ocf_dist.merge_weights(parts, 1, N)
         assert all(np.array_equal(a, b) for a, b in zip(merged, full))
+        # catalogue-wide top-k from the shards' own lists (what follows model.recommend on a column shard)
+        from oracle import ref_topk
+        scores = np.round(np.random.RandomState(9).normal(size=(B, N)), 1).astype(np.float32)
+        c, v = ref_topk.topk(scores[:, lo:hi], 5)
+        got_c, got_v = ocf_dist.all_gather_topk(np.where(c >= 0, c + lo, -1).astype(np.int32), v, 5)
+        want_c, want_v = ref_topk.topk(scores, 5)
+        assert np.array_equal(got_c, want_c) and np.array_equal(got_v, want_v)
         out.put((rank, "ok"))
     except Exception as exc:                                   # pragma: no cover
         out.put((rank, repr(exc)))
@@ -108,3 +115,26 @@ def test_collectives_over_gloo_world2(golden_datasets):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def test_merge_topk_equals_topk_of_the_whole_catalogue():
+    """Shard-local top-k lists merged on the host = the oracle's top-k over all columns (score descending, ties by the
+    lower column, -1 / -inf padding last), including rows with fewer than k candidates."""
+    from oracle import ref_topk
+    from omnidirectional_collaborative_filtering_b200.dist import merge_topk
+    rs = np.random.RandomState(3)
+    B, N, k, world = 6, 50, 8, 4
+    scores = np.round(rs.normal(size=(B, N)), 1).astype(np.float32)          # rounded: plenty of ties
+    seen = rs.random_sample((B, N)) < 0.3
+    seen[5, 3:] = True                                                       # a row with 3 candidates only
+    bounds = [N * r // world for r in range(world + 1)]
+    parts = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        c, v = ref_topk.topk(scores[:, lo:hi], k, seen=[np.flatnonzero(row) for row in seen[:, lo:hi]])
+        c = np.where(c >= 0, c + lo, -1).astype(np.int32)
+        parts.append((c, v))
+    got_c, got_v = merge_topk(parts, k)
+    want_c, want_v = ref_topk.topk(scores, k, seen=[np.flatnonzero(row) for row in seen])
+    assert np.array_equal(got_c, want_c) and np.array_equal(got_v, want_v)
+    assert got_c[5, 3:].tolist() == [-1] * (k - 3)
