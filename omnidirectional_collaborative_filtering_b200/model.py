@@ -310,7 +310,7 @@ class OmniNet(object):
         (ties: lower column first), selected on the device: (columns int32 [B, k], scores float32
         [B, k]). `exclude_seen` drops the columns a row holds as inputs. Slots beyond the available
         columns hold column -1 / score -inf. A column shard returns the top k of its own columns
-        (global column ids); merging the shards' lists is the caller's k-way merge."""
+        (global column ids); `dist.all_gather_topk` merges the shards' lists into the catalogue-wide top k."""
         h = self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
         dev = batch.upload(self.stream)
         self._shard_encode(h, dev, batch)
