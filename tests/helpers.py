@@ -174,7 +174,7 @@ def oracle_train_run_ablation(user_dict, unique_cols, unique_rows, cfg, seed, in
     return {"history": history, "best_epoch": best, "test": test}
 
 
-def oracle_train_run(fs, cfg, seed, init_model):
+def oracle_train_run(fs, cfg, seed, init_model, data=None, n_cols=None, rating_range=None):
     """`train.py:147-177,215-254` driven through the oracle alone on one RandomState stream: the
     per-epoch histories, the fixed-split test metrics and the manual test RMSE a `train.run` of the
     same config must reproduce. `init_model()` builds the product model after `np.random.seed(seed)`
@@ -182,14 +182,16 @@ def oracle_train_run(fs, cfg, seed, init_model):
     from oracle import ref_model
     from omnidirectional_collaborative_filtering_b200 import synthetic
     c = cfg
-    dicts = synthetic.to_reference_dicts(fs, raw_col_id=lambda col: col)
-    data = ref_batches.RefData(fs.n_cols, fs.train.n_rows, dicts["unique_cols"], eval_mode="fixed_split",
-                               train=dicts["train"], valid=tuple(dicts["valid"]), test=tuple(dicts["test"]))
+    if data is None:                               # a synthetic FixedSplit; else a ready RefData (e.g. loaded from files)
+        dicts = synthetic.to_reference_dicts(fs, raw_col_id=lambda col: col)
+        data = ref_batches.RefData(fs.n_cols, fs.train.n_rows, dicts["unique_cols"], eval_mode="fixed_split",
+                                   train=dicts["train"], valid=tuple(dicts["valid"]), test=tuple(dicts["test"]))
+        n_cols, rating_range = fs.n_cols, fs.rating_range
     np.random.seed(seed)
     twin = init_model()
     rng = np.random.RandomState()
     rng.set_state(np.random.get_state())          # the stream right after the model's initialisation
-    ref = ref_model.RefModel(c.numlayers, c.num_hidden_units, fs.n_cols, c.batch_size,
+    ref = ref_model.RefModel(c.numlayers, c.num_hidden_units, n_cols, c.batch_size,
                              dense_activation=c.activation_type, use_causal_info=c.use_causal_info,
                              use_both_masks=c.auxilliary_mask_type == "both",
                              l2_weight_regulatization=c.l2_weight_regulatization,
@@ -198,7 +200,7 @@ def oracle_train_run(fs, cfg, seed, init_model):
     ref.set_weights(twin.model.get_weights())
     ref.dropout_seed = twin.dropout_seed
     ref.trainable = list(twin.trainable)          # frozen layers of a nested denoising AE (model.py:158-170)
-    ref.compile(ref_model.RefOptimizer("adagrad", lr=c.learning_rate), c.model_loss, rating_range=fs.rating_range)
+    ref.compile(ref_model.RefOptimizer("adagrad", lr=c.learning_rate), c.model_loss, rating_range=rating_range)
     B = c.batch_size
 
     def gen(which, sparsity, **kw):
@@ -224,3 +226,24 @@ def oracle_train_run(fs, cfg, seed, init_model):
         count += n
     return {"history": history, "best_epoch": best, "test": dict(zip(ref_model.METRIC_NAMES, test)),
             "manual_test_rmse": float(np.sqrt(sse / count)), "weights": ref.get_weights()}
+
+
+def files_pipeline(tmp_dir, seed=3):
+    """CSV -> the product's splitter -> the reference's file layout on disk. Returns (directory, n_items, n_rows,
+    RefData over the same files read with json.load, as the reference's reader would)."""
+    import json
+    import os
+    from omnidirectional_collaborative_filtering_b200 import splitter
+    csv = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "split", "ml", "ratings.csv")
+    np.random.seed(seed)
+    d = splitter.split_data(csv, str(tmp_dir) + "/", "movielens", include_timestamps=False, save_users_and_items=True)
+
+    def load(name):
+        with open(d + name + ".json") as f:
+            return json.load(f)
+
+    items = load("unique_items_list")
+    train = load("ratingsByUser_dicts_train")
+    data = ref_batches.RefData(len(items), len(train), items, eval_mode="fixed_split", train=train,
+                               valid=tuple(load("ratingsByUser_dicts_valid")), test=tuple(load("ratingsByUser_dicts_test")))
+    return d, len(items), len(train), data

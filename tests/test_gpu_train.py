@@ -25,3 +25,24 @@ def test_train_run_matches_oracle(name):
     rd.close()
     want = oracle_train_run(fs, cfg, 5, init_model_for(cfg, fs.n_cols))
     assert_same_run(got, want, rtol=1e-3)
+
+
+def test_csv_to_metrics_pipeline_matches_oracle(tmp_path):
+    """Ratings CSV -> native splitter -> the reference's files -> native ingest -> `train.run` on the GPU -> top-k
+    recommendations; per-epoch metrics against the oracle loop over the same files read with json.load."""
+    from tests.helpers import files_pipeline
+    d, n_items, n_rows, data = files_pipeline(tmp_path)
+    cfg = train_config("autorec", batch_size=8, num_hidden_units=16, max_epochs=2, reverse_user_item_data=False)
+    rd = data_reader(n_items, n_rows, d, use_json=True, eval_mode="fixed_split")
+    np.random.seed(5)
+    got = ocf_train.run(cfg, reader=rd, rating_range=4.5, save_models=False, verbose=0)
+    want = oracle_train_run(None, cfg, 5, init_model_for(cfg, n_items), data=data, n_cols=n_items, rating_range=4.5)
+    assert_same_run(got, want, rtol=1e-3)
+    # serving on the trained model: 5 unseen items per user of a validation batch
+    batch = next(rd.data_gen(8, None, "valid", False, None, -1))
+    cols, scores = got["model"].model.recommend(batch, k=5, exclude_seen=True)
+    assert cols.shape == (8, 5) and (cols >= 0).all() and (np.diff(scores, axis=1) <= 0).all()
+    seen = rd.store("valid").in_store.csr
+    for b, row in enumerate(batch.rows):
+        assert not set(cols[b].tolist()) & set(seen.row(int(row))[0].tolist())
+    rd.close()

@@ -113,3 +113,32 @@ def test_train_run_ablation_mode_is_the_oracle_loop(monkeypatch, golden_datasets
     for s, vals in want["test"].items():
         assert got["test"][s] == vals
     rd.close()
+
+
+def test_csv_to_metrics_pipeline_is_the_oracle_loop(monkeypatch, tmp_path):
+    """The whole drop-in story without a GPU: ratings CSV -> `splitter.split_data` -> the reference's files ->
+    `data_reader(use_json=True)` (native ingest) -> `train.run`; against the oracle loop over the same files read
+    with json.load. `tests/test_gpu_train.py` has the CUDA twin."""
+    from tests.helpers import files_pipeline
+    d, n_items, n_rows, data = files_pipeline(tmp_path)
+    cfg = train_config("autorec", batch_size=8, num_hidden_units=16, max_epochs=2, reverse_user_item_data=False)
+    rd = data_reader(n_items, n_rows, d, use_json=True, eval_mode="fixed_split", rng_on_device=False)
+    real_omni = ocf_train.omni_model
+
+    def oracle_backed(*a, **k):
+        om = real_omni(*a, **k)
+        ref = ref_model.RefModel(cfg.numlayers, cfg.num_hidden_units, n_items, cfg.batch_size, dense_activation=cfg.activation_type,
+                                 use_causal_info=cfg.use_causal_info, dropout_probability=cfg.dropout_probability,
+                                 dtype=np.float32, rng=np.random.RandomState(0))
+        ref.set_weights(om.model.get_weights())
+        ref.dropout_seed = om.dropout_seed
+        om.model = OracleNet(ref, owner=om)
+        return om
+
+    monkeypatch.setattr(ocf_train, "omni_model", oracle_backed)
+    np.random.seed(5)
+    got = ocf_train.run(cfg, reader=rd, rating_range=4.5, save_models=False, verbose=0)
+    monkeypatch.setattr(ocf_train, "omni_model", real_omni)
+    want = oracle_train_run(None, cfg, 5, init_model_for(cfg, n_items), data=data, n_cols=n_items, rating_range=4.5)
+    assert_same_run(got, want, rtol=0)
+    rd.close()
