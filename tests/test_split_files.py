@@ -362,6 +362,32 @@ def test_splitter_rejects_bad_arguments(tmp_path):
     assert csr.col.tolist() == [1, 2, 0]
 
 
+def test_pickle_files_give_the_same_stores_as_json_files(tmp_path):
+    """`use_json=False`: the reference's other on-disk format (`.p` pickles of the same objects, data_reader.py:88-91).
+    Tuples inside pickles (the splitter's in-memory `(item, rating)` pairs) are accepted like lists."""
+    import pickle
+    src = os.path.join(SPLIT, "ml") + "/"
+    d = str(tmp_path) + "/"
+    for name in ("unique_items_list", "ratingsByUser_dicts_train", "ratingsByUser_dicts_valid", "ratingsByUser_dicts_test"):
+        with open(src + name + ".json") as f:
+            obj = json.load(f)
+        if name.endswith("train"):
+            obj = {k: [tuple(p) for p in v] for k, v in obj.items()}
+        elif "dicts" in name:
+            obj = tuple({k: (None if v is None else [tuple(p) for p in v]) for k, v in half.items()} for half in obj)
+        with open(d + name + ".p", "wb") as f:
+            pickle.dump(obj, f, protocol=2)
+    gold = np.load(os.path.join(SPLIT, "pipeline_batches.npz"))
+    a = data_reader(int(gold["n_items"]), int(gold["n_rows"]), src, use_json=True, eval_mode="fixed_split", rng_on_device=False)
+    b = data_reader(int(gold["n_items"]), int(gold["n_rows"]), d, use_json=False, eval_mode="fixed_split", rng_on_device=False)
+    assert a.train_set == b.train_set and a.val_set == b.val_set and a.test_set == b.test_set
+    _same_csr(a.store("train").csr, b.store("train").csr)
+    for which in ("valid", "test"):
+        _same_csr(a.store(which).in_store.csr, b.store(which).in_store.csr)
+        _same_csr(a.store(which).tgt_store.csr, b.store(which).tgt_store.csr)
+    a.close(), b.close()
+
+
 def test_native_unique_lists_match_the_pipeline_fixture(tmp_path):
     case = [c for c in CASES if c["name"] == "ml"][0]
     out = _run(splitter.split_data, case, tmp_path, save_users_and_items=True)
