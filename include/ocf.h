@@ -340,6 +340,23 @@ int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t n_order, c
                     const char* out_dir, int cast_user_to_int, int build_data_for_omni, int include_timestamps,
                     int save_users_and_items, int reverse_user_item_data);
 
+/* The same split without the files: CSV -> the row stores the reader would build from the splitter's output
+ * (ocf_split_write followed by ocf_ratings_load_json, minus two passes over the JSON text). `csv` must outlive the
+ * handle. Columns = the distinct items in first-appearance order of the file (the order of unique_items_list.json).
+ *   info[0] = columns; for set s in {0 train, 1 valid, 2 test}: info[1+4s] = rows (the set's row keys in dict order),
+ *   info[2+4s] = bytes of its keys, info[3+4s] = ratings of part 0, info[4+4s] = ratings of part 1.
+ *   part 0 = the set's input rows (train: its own ratings; valid: the train rows of the same users; test: their
+ *   train+valid rows; none[k] = 1 where the reference stores None), part 1 = the set's target rows (valid / test). */
+typedef struct ocf_split ocf_split;
+int ocf_split_build(const ocf_csv* csv, const int64_t* order, int64_t n_order, const double fractions[3],
+                    int cast_user_to_int, int reverse_user_item_data, ocf_split** out);
+int ocf_split_info(const ocf_split* split, int64_t info[13]);
+int ocf_split_keys(const ocf_split* split, int set, char* bytes, int64_t* offsets);
+int ocf_split_csr(const ocf_split* split, int set, int part, int64_t* rowptr, int32_t* col, float* val, uint8_t* none);
+/* The column ids as the text of unique_items_list.json: *needed = its length; copied into buf when cap suffices. */
+int ocf_split_columns_json(const ocf_split* split, char* buf, int64_t cap, int64_t* needed);
+int ocf_split_destroy(ocf_split* split);
+
 /* Per-kernel timing with CUDA events recorded on the launching stream around the named kernels
  * (tag 0 = K1 gather, 1 = K2 encoder, 2 = K3 decoder/loss, 3 = K4a column scan, 4 = scoring GEMM,
  * 5 = K4b row update, 6 = first collective of a parallel step (z all-reduce / streaming optimizer

@@ -121,6 +121,12 @@ _SIGNATURES = {
     "ocf_csv_destroy": (C.c_int, [_P]),
     "ocf_split_write": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_double), C.c_char_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int]),
+    "ocf_split_build": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(_P)]),
+    "ocf_split_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "ocf_split_keys": (C.c_int, [_P, C.c_int, _P, _P]),
+    "ocf_split_csr": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "ocf_split_columns_json": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "ocf_split_destroy": (C.c_int, [_P]),
 }
 
 _lib = None

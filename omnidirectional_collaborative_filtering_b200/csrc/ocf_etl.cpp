@@ -1020,6 +1020,41 @@ void write_merged_timestamps(const Splitter& sp, const Groups& in, const Groups&
 
 }  // namespace
 
+namespace {
+
+// ratings[col].unique(): the rows where a value of column c appears for the first time, in file order. With
+// `dense`, also the position of every row's value in that list (the dense id data_reader.py:24-28 would give it).
+std::vector<int64_t> unique_first_rows(const ocf_csv& csv, int c, std::vector<int32_t>* dense) {
+  std::vector<int64_t> firsts;
+  const Column& col = csv.col[c];
+  const int64_t n = csv.n_rows;
+  if (dense) dense->resize((size_t)n);
+  auto visit = [&](auto& seen, const auto& key, int64_t r) {
+    auto ins = seen.emplace(key, (int32_t)firsts.size());
+    if (ins.second) firsts.push_back(r);
+    if (dense) (*dense)[(size_t)r] = ins.first->second;
+  };
+  if (col.type == Column::STR) {
+    std::unordered_map<std::string, int32_t> seen;
+    for (int64_t r = 0; r < n; ++r) visit(seen, col.s[(size_t)r], r);
+  } else if (col.type == Column::INT) {
+    std::unordered_map<int64_t, int32_t> seen;
+    for (int64_t r = 0; r < n; ++r) visit(seen, csv.int_at(c, r), r);
+  } else {
+    std::unordered_map<uint64_t, int32_t> seen;
+    for (int64_t r = 0; r < n; ++r) {
+      double d = csv.flt_at(c, r);
+      if (std::isnan(d)) d = std::nan("");              // every NaN is one value
+      if (d == 0.0) d = 0.0;                           // -0.0 and 0.0 are one value
+      uint64_t b; std::memcpy(&b, &d, 8);
+      visit(seen, b, r);
+    }
+  }
+  return firsts;
+}
+
+}  // namespace
+
 extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t n_order, const double fractions[3],
                                const char* out_dir, int cast_user_to_int, int build_data_for_omni,
                                int include_timestamps, int save_users_and_items, int reverse_user_item_data) {
@@ -1122,28 +1157,7 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
     Out items, users;
     if (!items.open(dir + "unique_items_list.json") || !users.open(dir + "unique_users_list.json"))
       return fail(OCF_ERR_INVALID, "cannot write the unique lists under " + dir);
-    auto unique_rows = [&](int c) {
-      std::vector<int64_t> firsts;
-      const Column& col = csv->col[c];
-      if (col.type == Column::STR) {
-        std::unordered_map<std::string, char> seen;
-        for (int64_t r = 0; r < n; ++r) if (seen.emplace(col.s[(size_t)r], 1).second) firsts.push_back(r);
-      } else if (col.type == Column::INT) {
-        std::unordered_map<int64_t, char> seen;
-        for (int64_t r = 0; r < n; ++r) if (seen.emplace(csv->int_at(c, r), 1).second) firsts.push_back(r);
-      } else {
-        std::unordered_map<uint64_t, char> seen;
-        bool nan_seen = false;
-        for (int64_t r = 0; r < n; ++r) {
-          double d = csv->flt_at(c, r);
-          if (std::isnan(d)) { if (!nan_seen) { nan_seen = true; firsts.push_back(r); } continue; }
-          if (d == 0.0) d = 0.0;                       // -0.0 and 0.0 are one value
-          uint64_t b; std::memcpy(&b, &d, 8);
-          if (seen.emplace(b, 1).second) firsts.push_back(r);
-        }
-      }
-      return firsts;
-    };
+    auto unique_rows = [&](int c) { return unique_first_rows(*csv, c, nullptr); };
     // json.dump(list(ratings["itemId"].unique())): the column's own dtype
     items.buf.push_back('[');
     bool first = true;
@@ -1182,5 +1196,142 @@ extern "C" int ocf_split_write(const ocf_csv* csv, const int64_t* order, int64_t
     users.buf.push_back(']');
     if (!items.close() || !users.close()) return fail(OCF_ERR_INVALID, "write failed: unique lists under " + dir);
   }
+  return OCF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same split without the files: CSV -> the stores the reader builds from the splitter's output
+// (what ocf_split_write + ocf_ratings_load_json give together, minus 2 x the JSON text).
+// ---------------------------------------------------------------------------------------------
+struct ocf_split {
+  std::unique_ptr<Splitter> sp;
+  Groups g[4];                        // train, valid targets, test targets, test inputs (= train + valid)
+  std::vector<int32_t> item_dense;    // per CSV row: dense column of its item (first-appearance order of the file)
+  int64_t n_cols = 0;
+  const ocf_csv* csv = nullptr;
+};
+
+extern "C" int ocf_split_build(const ocf_csv* csv, const int64_t* order, int64_t n_order, const double fractions[3],
+                               int cast_user_to_int, int reverse_user_item_data, ocf_split** out) {
+  if (!csv || !order || !fractions || !out) return fail(OCF_ERR_INVALID, "ocf_split_build: bad argument");
+  *out = nullptr;
+  const int64_t n = csv->n_rows;
+  if (n_order != n) return fail(OCF_ERR_INVALID, "ocf_split_build: the rating order must be a permutation of all rows");
+  {
+    std::vector<uint8_t> seen((size_t)n, 0);
+    for (int64_t k = 0; k < n; ++k) {
+      if (order[k] < 0 || order[k] >= n || seen[(size_t)order[k]])
+        return fail(OCF_ERR_INVALID, "ocf_split_build: the rating order is not a permutation");
+      seen[(size_t)order[k]] = 1;
+    }
+  }
+  for (int k = 0; k < 3; ++k)
+    if (!(fractions[k] >= 0.0 && fractions[k] <= 1.0)) return fail(OCF_ERR_INVALID, "ocf_split_build: a split fraction is outside [0, 1]");
+  const int64_t n_tr = (int64_t)((double)n * fractions[0]);
+  const int64_t n_va = (int64_t)((double)n * fractions[1]);
+  if (n_tr + n_va > n) return fail(OCF_ERR_INVALID, "ocf_split_build: split fractions exceed 1");
+  if (csv->col[2].type == Column::STR) return fail(OCF_ERR_INVALID, "ocf_split_build: the rating column is not numeric");
+  auto s = std::make_unique<ocf_split>();
+  s->csv = csv;
+  s->sp = std::make_unique<Splitter>(*csv, reverse_user_item_data != 0, cast_user_to_int != 0);
+  if (!s->sp->index_users()) return fail(OCF_ERR_INVALID, s->sp->error);
+  s->n_cols = (int64_t)unique_first_rows(*csv, s->sp->item_col, &s->item_dense).size();
+  s->g[0].build(*s->sp, order, n_tr);
+  s->g[1].build(*s->sp, order + n_tr, n_va);
+  s->g[2].build(*s->sp, order + n_tr + n_va, n - n_tr - n_va);
+  s->g[3].build(*s->sp, order, n_tr + n_va);
+  *out = s.release();
+  return OCF_OK;
+}
+
+namespace {
+// (targets, inputs) groups of a set: train has no inputs of its own
+inline const Groups& split_targets(const ocf_split* s, int set) { return s->g[set]; }
+inline const Groups* split_inputs(const ocf_split* s, int set) { return set == 1 ? &s->g[0] : (set == 2 ? &s->g[3] : nullptr); }
+}  // namespace
+
+extern "C" int ocf_split_info(const ocf_split* s, int64_t info[13]) {
+  if (!s || !info) return fail(OCF_ERR_INVALID, "ocf_split_info: bad argument");
+  info[0] = s->n_cols;
+  for (int set = 0; set < 3; ++set) {
+    const Groups& tg = split_targets(s, set);
+    const Groups* in = split_inputs(s, set);
+    int64_t key_bytes = 0, n_in = 0;
+    for (int32_t u : tg.users) {
+      key_bytes += (int64_t)s->sp->ukey[(size_t)u].size();
+      if (in) { int32_t gi = in->group_of[(size_t)u]; if (gi >= 0) n_in += in->start[(size_t)gi + 1] - in->start[(size_t)gi]; }
+    }
+    info[1 + 4 * set] = (int64_t)tg.users.size();
+    info[2 + 4 * set] = key_bytes;
+    info[3 + 4 * set] = in ? n_in : (int64_t)tg.rows.size();       // train: its ratings are store 0
+    info[4 + 4 * set] = in ? (int64_t)tg.rows.size() : 0;
+  }
+  return OCF_OK;
+}
+
+extern "C" int ocf_split_keys(const ocf_split* s, int set, char* bytes, int64_t* offsets) {
+  if (!s || !bytes || !offsets || set < 0 || set > 2) return fail(OCF_ERR_INVALID, "ocf_split_keys: bad argument");
+  const Groups& tg = split_targets(s, set);
+  int64_t at = 0;
+  for (size_t k = 0; k < tg.users.size(); ++k) {
+    const std::string& key = s->sp->ukey[(size_t)tg.users[k]];
+    offsets[k] = at;
+    std::memcpy(bytes + at, key.data(), key.size());
+    at += (int64_t)key.size();
+  }
+  offsets[tg.users.size()] = at;
+  return OCF_OK;
+}
+
+extern "C" int ocf_split_csr(const ocf_split* s, int set, int part, int64_t* rowptr, int32_t* col, float* val, uint8_t* none) {
+  if (!s || !rowptr || !col || !val || set < 0 || set > 2 || part < 0 || part > 1 || (set == 0 && part == 1))
+    return fail(OCF_ERR_INVALID, "ocf_split_csr: bad argument");
+  const Groups& tg = split_targets(s, set);
+  const Groups* in = split_inputs(s, set);
+  const Groups& src = (in && part == 0) ? *in : tg;
+  const ocf_csv& csv = *s->csv;
+  const int rc = s->sp->rating_col;
+  const bool as_int = csv.col[rc].type == Column::INT;
+  int64_t at = 0;
+  for (size_t k = 0; k < tg.users.size(); ++k) {
+    rowptr[k] = at;
+    int32_t g = (in && part == 0) ? in->group_of[(size_t)tg.users[k]] : (int32_t)k;
+    if (none) none[k] = g < 0 ? 1 : 0;
+    if (g < 0) continue;
+    for (int64_t j = src.start[(size_t)g]; j < src.start[(size_t)g + 1]; ++j) {
+      const int64_t row = src.rows[(size_t)j];
+      col[at] = s->item_dense[(size_t)row];
+      val[at] = as_int ? (float)(double)csv.int_at(rc, row) : (float)csv.flt_at(rc, row);
+      ++at;
+    }
+  }
+  rowptr[tg.users.size()] = at;
+  return OCF_OK;
+}
+
+// The column ids as the JSON list `unique_items_list.json` would hold (json.dump formatting): returns the text's
+// length in *needed; copies it when cap is large enough.
+extern "C" int ocf_split_columns_json(const ocf_split* s, char* buf, int64_t cap, int64_t* needed) {
+  if (!s || !needed) return fail(OCF_ERR_INVALID, "ocf_split_columns_json: bad argument");
+  const ocf_csv& csv = *s->csv;
+  const int c = s->sp->item_col;
+  const Column& col = csv.col[c];
+  std::string out = "[";
+  bool first = true;
+  for (int64_t r : unique_first_rows(csv, c, nullptr)) {
+    if (!first) out.append(", ");
+    first = false;
+    if (col.type == Column::STR) json_string(col.s[(size_t)r], &out);
+    else if (col.type == Column::INT) out.append(std::to_string(csv.int_at(c, r)));
+    else py_float_repr(csv.flt_at(c, r), &out, "NaN", "Infinity");
+  }
+  out.push_back(']');
+  *needed = (int64_t)out.size();
+  if (buf && cap >= (int64_t)out.size()) std::memcpy(buf, out.data(), out.size());
+  return OCF_OK;
+}
+
+extern "C" int ocf_split_destroy(ocf_split* s) {
+  delete s;
   return OCF_OK;
 }

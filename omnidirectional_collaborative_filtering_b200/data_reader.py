@@ -374,8 +374,11 @@ class data_reader(object):
         self._files = data if isinstance(data, dict) else None
         self._rings = {}
         self._stores = {}
+        from .ingest import LoadedSplit
         if isinstance(data, FixedSplit):
             self._init_from_split(data)
+        elif isinstance(data, LoadedSplit):
+            self._init_from_loaded(data)
         else:
             self._init_from_files(use_json, reverse_user_item_data)
         # column shard (rank, world): this process keeps catalogue columns [lo, hi) of every set;
@@ -472,6 +475,29 @@ class data_reader(object):
                 pair = StorePair(RatingStore(_csr_from_lists([ins[k] for k in keys], col_of, N)),
                                  RatingStore(_csr_from_lists([tgs[k] for k in keys], col_of, N)))
                 self._stores[name] = pair
+
+    def _init_from_loaded(self, ls):
+        """Keys + CSR stores (ingest.LoadedSplit: parsed files, or splitter.split_in_memory)."""
+        if self.eval_mode != "fixed_split":
+            raise ValueError("a LoadedSplit only serves eval_mode='fixed_split'")
+        if ls.n_cols > self.num_items:
+            raise ValueError("num_items (%d) is smaller than the split's column count (%d)" % (self.num_items, ls.n_cols))
+        self.unique_items = list(range(ls.n_cols)) if ls.unique_items is None else list(ls.unique_items)
+        self.items_to_densevec = {item: i for i, item in enumerate(self.unique_items)}
+        self.densevec_to_items = {i: item for i, item in enumerate(self.unique_items)}
+        self.densevec_to_users = {i: i for i in range(self.num_users)}
+        N = self.num_items
+
+        def widen(csr):                    # the reader's arrays are num_items wide whatever the data uses (:13,109-118)
+            return Csr(csr.n_rows, N, csr.rowptr, csr.col, csr.val)
+
+        self.train_set, train = ls.train
+        self.val_set, va_in, _, va_tg = ls.valid
+        self.test_set, te_in, _, te_tg = ls.test
+        self._set_sizes()
+        self._stores["train"] = RatingStore(widen(train), build_csc=True)
+        self._stores["valid"] = StorePair(RatingStore(widen(va_in)), RatingStore(widen(va_tg)))
+        self._stores["test"] = StorePair(RatingStore(widen(te_in)), RatingStore(widen(te_tg)))
 
     def _set_sizes(self):
         self.train_set_size = len(self.train_set)                                             # :73-75

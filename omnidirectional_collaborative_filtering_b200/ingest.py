@@ -12,6 +12,15 @@ from . import _lib
 from .synthetic import Csr
 
 
+class LoadedSplit(object):
+    """What `eval_mode="fixed_split"` needs, as keys + CSR stores: train = (keys, csr); valid / test = (keys, input
+    csr, none flags, target csr) with aligned rows. Produced by the native file parser (`load_split`) or straight
+    from a ratings CSV (`splitter.split_in_memory`); `data_reader(..., data=LoadedSplit)` consumes it."""
+
+    def __init__(self, n_cols, train, valid, test, unique_items=None):
+        self.n_cols, self.train, self.valid, self.test, self.unique_items = int(n_cols), train, valid, test, unique_items
+
+
 class Vocab(object):
     """`unique_items_list.json` / `unique_users_list.json`: id -> dense column (data_reader.py:24-28)."""
 

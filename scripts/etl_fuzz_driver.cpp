@@ -32,6 +32,25 @@ int main(int argc, char** argv) {
       int rc = ocf_split_write(c, order.data(), n, fr, argv[4], cast, 1, ts, 1, rev);
       if (rc) printf("split err: %s\n", ocf::last_error().c_str());
     }
+    for (int rev = 0; rev < 2; ++rev) for (int cast = 0; cast < 2; ++cast) {
+      ocf_split* sp = nullptr;
+      if (ocf_split_build(c, order.data(), n, fr, cast, rev, &sp)) { printf("build err: %s\n", ocf::last_error().c_str()); continue; }
+      int64_t info[13]; ocf_split_info(sp, info);
+      for (int set = 0; set < 3; ++set) {
+        std::vector<char> kb(info[2 + 4 * set] + 1); std::vector<int64_t> off(info[1 + 4 * set] + 1);
+        ocf_split_keys(sp, set, kb.data(), off.data());
+        for (int part = 0; part < (set ? 2 : 1); ++part) {
+          int64_t nnz = info[3 + 4 * set + part];
+          std::vector<int64_t> rp(info[1 + 4 * set] + 1); std::vector<int32_t> cc(nnz + 1); std::vector<float> vv(nnz + 1); std::vector<uint8_t> none(info[1 + 4 * set] + 1);
+          ocf_split_csr(sp, set, part, rp.data(), cc.data(), vv.data(), none.data());
+          if (rp[info[1 + 4 * set]] != nnz) { printf("BUG split nnz mismatch\n"); return 1; }
+          for (int64_t k = 0; k < nnz; ++k) if (cc[k] < 0 || cc[k] >= info[0]) { printf("BUG column out of range\n"); return 1; }
+        }
+      }
+      int64_t need = 0; ocf_split_columns_json(sp, nullptr, 0, &need);
+      std::vector<char> txt(need + 1); ocf_split_columns_json(sp, txt.data(), need, &need);
+      ocf_split_destroy(sp);
+    }
     printf("ok rows %lld\n", (long long)n);
     ocf_csv_destroy(c);
   }

@@ -388,6 +388,69 @@ def test_pickle_files_give_the_same_stores_as_json_files(tmp_path):
     a.close(), b.close()
 
 
+def _readers_agree(csv, schema, rev, seed, tmp, fractions=(.8, .1, .1)):
+    """split_in_memory == split_data (files) + native ingest, store by store."""
+    np.random.seed(seed)
+    try:
+        ls = splitter.split_in_memory(csv, schema, fractions, rev)
+    except _lib.OcfError as e:
+        ls = e
+    np.random.seed(seed)
+    try:
+        d = splitter.split_data(csv, str(tmp) + "/", schema, fractions, True, False, True, rev)
+        vocab = ingest.Vocab(d + "unique_items_list.json")
+        files = (ingest.load_ratings(d + "ratingsByUser_dicts_train.json", vocab, False, vocab.size),
+                 ingest.load_ratings(d + "ratingsByUser_dicts_valid.json", vocab, True, vocab.size),
+                 ingest.load_ratings(d + "ratingsByUser_dicts_test.json", vocab, True, vocab.size))
+    except _lib.OcfError as e:
+        files = e
+    if isinstance(files, Exception) or isinstance(ls, Exception):
+        assert isinstance(files, Exception) and isinstance(ls, Exception), (files, ls)
+        return None
+    with open(d + "unique_items_list.json") as f:
+        assert ls.unique_items == json.load(f) and ls.n_cols == vocab.size
+    assert ls.train[0] == files[0][0]
+    _same_csr(ls.train[1], files[0][1])
+    for got, want in ((ls.valid, files[1]), (ls.test, files[2])):
+        assert got[0] == want[0] and np.array_equal(got[2], want[2])
+        _same_csr(got[1], want[1])
+        _same_csr(got[3], want[3])
+    return ls
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_split_in_memory_equals_the_path_through_files(tmp_path, case):
+    csv = os.path.join(SPLIT, case["name"], "ratings.csv")
+    ls = _readers_agree(csv, case["schema_type"], case["reverse_user_item_data"], case["seed"], tmp_path)
+    assert ls is not None and ls.train[1].nnz > 100
+    rd = data_reader(ls.n_cols + 3, len(ls.train[0]), "", eval_mode="fixed_split", data=ls, rng_on_device=False)
+    assert rd.store("train").n_cols == ls.n_cols + 3 and rd.train_set == ls.train[0]       # arrays are num_items wide
+    np.random.seed(1)
+    batch = next(rd.data_gen(4, [0.5, 0.5], "train", True, "dropout", -1))
+    feed, targets = host_densify(batch)
+    assert targets.shape == (4, ls.n_cols + 3) and np.count_nonzero(feed[0]) + np.count_nonzero(targets) > 0
+    rd.close()
+
+
+@settings(max_examples=60, deadline=None)
+@given(rows=st.lists(st.tuples(_ident, _ident, _field, st.integers(0, 10 ** 9).map(str)), min_size=1, max_size=40),
+       schema=st.sampled_from(["amazon", "netflix", "movielens"]), rev=st.booleans(), seed=st.integers(0, 10 ** 6),
+       fr=st.sampled_from([(.8, .1, .1), (.5, .25, .25), (1.0, 0.0, 0.0)]))
+def test_split_in_memory_equals_the_path_through_files_on_random_csvs(tmp_path_factory, rows, schema, rev, seed, fr):
+    d = str(tmp_path_factory.mktemp("mem")) + "/"
+    ncol = 3 if schema == "netflix" else 4
+
+    def q(s):
+        return '"' + s.replace('"', '""') + '"' if any(c in s for c in ',"\n') else s
+    with open(d + "r.csv", "w", encoding="utf-8") as f:
+        f.write(",".join(["a", "b", "c", "d"][:ncol]) + "\n")
+        for r in rows:
+            f.write(",".join(q(x) for x in r[:ncol]) + "\n")
+    os.makedirs(d + "out")
+    _readers_agree(d + "r.csv", schema, rev, seed, d + "out", fr)
+    shutil.rmtree(d)
+
+
 def test_native_unique_lists_match_the_pipeline_fixture(tmp_path):
     case = [c for c in CASES if c["name"] == "ml"][0]
     out = _run(splitter.split_data, case, tmp_path, save_users_and_items=True)
