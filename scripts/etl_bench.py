@@ -103,6 +103,13 @@ def main():
         list(pool.map(lambda a: ingest.load_ratings(d + "native/" + a[0] + ".json", vocab, a[1]), files))
     t = time.perf_counter() - t0
     out["native_ingest_3_threads"] = {"seconds": t, "ratings_per_s": total / t}
+    np.random.seed(1)
+    t0 = time.perf_counter()
+    ls = splitter.split_in_memory(d + "ratings.csv", "movielens")
+    t = time.perf_counter() - t0
+    out["native_split_in_memory"] = {"seconds": t, "ratings_per_s": n / t,
+                                     "what": "CSV -> the reader's train / valid / test stores, no files (%d + %d + %d + %d + %d ratings)"
+                                     % (ls.train[1].nnz, ls.valid[1].nnz, ls.valid[3].nnz, ls.test[1].nnz, ls.test[3].nnz)}
     print(json.dumps(out, indent=1))
 
 
