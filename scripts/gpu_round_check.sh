@@ -15,6 +15,7 @@ for cfg in autorec omni; do python scripts/train_check.py $cfg > $out/${tag}_tra
 python bench.py > $out/${tag}_bench_ml10m.json 2> $out/${tag}_bench_ml10m.err || exit 1
 tail -c 600 $out/${tag}_bench_ml10m.json
 for w in ml1m jester ml20m; do python bench.py --workload $w > $out/${tag}_bench_$w.json 2> $out/${tag}_bench_$w.err; done
+( time timeout 900 python bench.py --workload netflix --steps 20 --no-cpu-baseline > $out/${tag}_bench_netflix.json ) 2> $out/${tag}_bench_netflix.err
 python bench.py --mode score > $out/${tag}_bench_score.json 2> $out/${tag}_bench_score.err
 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \

@@ -247,3 +247,79 @@ def files_pipeline(tmp_dir, seed=3):
     data = ref_batches.RefData(len(items), len(train), items, eval_mode="fixed_split", train=train,
                                valid=tuple(load("ratingsByUser_dicts_valid")), test=tuple(load("ratingsByUser_dicts_test")))
     return d, len(items), len(train), data
+
+
+# ---------------------------------------------------------------------------------------------------
+# Full-size workloads: reference-shaped dicts over a FixedSplit WITHOUT one Python list per rating
+# ---------------------------------------------------------------------------------------------------
+class CsrRows(object):
+    """Read-only dict {row index: [[column, rating], ...] or None} over a `synthetic.Csr`, rows built on
+    demand (what `json.load` of a ratingsBy*_dicts file gives the reference, `data_reader.py:67-70`; a
+    Netflix-sized dict of Python lists would need ~20 GB). Keys are the CSR row numbers in store order."""
+
+    def __init__(self, csr, none=None):
+        self.csr, self.none = csr, none
+
+    def keys(self):
+        return range(self.csr.n_rows)
+
+    def __len__(self):
+        return self.csr.n_rows
+
+    def __iter__(self):
+        return iter(range(self.csr.n_rows))
+
+    def __contains__(self, k):
+        return 0 <= int(k) < self.csr.n_rows
+
+    def __getitem__(self, k):
+        k = int(k)
+        if self.none is not None and self.none[k]:
+            return None
+        c, v = self.csr.row(k)
+        return [[int(ci), float(vi)] for ci, vi in zip(c, v)]
+
+
+def oracle_data_from_split(fs):
+    """`ref_batches.RefData` over a FixedSplit with lazily built rows: same keys order, same pairing, same
+    RNG consumption as the dict files of the same data (keys are ints here; only their count matters to
+    `np.random.permutation`)."""
+    return ref_batches.RefData(fs.n_cols, fs.train.n_rows, range(fs.n_cols), eval_mode="fixed_split",
+                               train=CsrRows(fs.train),
+                               valid=(CsrRows(fs.valid_in, fs.valid_none), CsrRows(fs.valid_tg)),
+                               test=(CsrRows(fs.test_in, fs.test_none), CsrRows(fs.test_tg)))
+
+
+def cached_split(shape, reverse, seed=0):
+    """`synthetic.make_fixed_split`, cached on disk under /tmp with bench.py's file names so one box builds
+    each full-size data set once for the tests and the bench."""
+    import os
+    import pickle
+    from omnidirectional_collaborative_filtering_b200 import synthetic
+    path = "/tmp/ocf_b200_%s_%d_%d.pkl" % (shape, int(reverse), seed)
+    if os.path.exists(path):
+        try:
+            with open(path, "rb") as f:
+                return pickle.load(f)
+        except Exception:
+            pass
+    fs = synthetic.make_fixed_split(shape, reverse_user_item_data=reverse, seed=seed)
+    try:
+        tmp = path + ".%d.tmp" % os.getpid()
+        with open(tmp, "wb") as f:
+            pickle.dump(fs, f, protocol=4)
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return fs
+
+
+def mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0

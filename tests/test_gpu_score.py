@@ -86,3 +86,48 @@ def test_score_rows_are_independent():
     c = om.model.score(big, reuse_output=True)          # page-locked destination owned by the model
     assert np.array_equal(a, c)
     rd.close()
+
+
+# Multi-tile shapes: the persistent kernel gives every CTA pair several (256-column x row-chunk) tiles, so the
+# TMEM accumulator ping-pong (tfull / tempty phases), the smem ring wrapping across tiles and the tile scheduler all
+# run for more than one round: 10 677 columns x 1 024 rows = 42 x 4 = 168 pair tiles, 71 567 x 1 024 (bench.py's
+# scoring shape) = 280 x 4 = 1 120 pair tiles, over 74 CTA pairs.
+@pytest.mark.parametrize("reverse", [False, True], ids=["ml10m_users_168_tiles", "ml10m_items_1120_tiles"])
+def test_scores_match_oracle_on_many_tiles_per_cta_pair(reverse):
+    from tests.helpers import cached_split
+    fs = cached_split("ml10m", reverse)
+    rows = 1024
+    rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs)
+    assert rd.val_set_size >= rows
+    om, ref = _models(fs.n_cols, 1, 512, rows, "sigmoid", "dropout", seed=5)
+    n_pair_tiles = ((fs.n_cols + 255) // 256) * ((rows + 255) // 256)
+    assert n_pair_tiles >= 2 * 74                      # every CTA pair of a 148-SM part gets at least two tiles
+    np.random.seed(9)
+    batch = next(rd.data_gen(rows, None, "valid", True, "dropout", -1))
+    got = om.model.score(batch).astype(np.float64)
+    again = om.model.score(batch)
+    feed, targets = batch
+    _, want, acts, _, _ = ref.forward(feed)
+    assert got.shape == want.shape == (rows, fs.n_cols)
+    assert np.array_equal(got.astype(np.float32), again)          # same bits on a second call
+    scale = np.abs(acts[-1]) @ np.abs(ref.get_weights()[-2]) + 1.0
+    err = got - want
+    assert np.max(np.abs(err) / scale) <= 2e-3
+    assert abs(err.mean()) <= 2e-5 * max(1.0, np.abs(want).mean())
+    # every 256-column tile and every row chunk carries its own data (a stale or swapped accumulator stage would
+    # put one tile's scores under another tile's columns): per-tile RMS error stays at tf32 level everywhere
+    ncol = fs.n_cols // 256 * 256
+    tile_rms = np.sqrt((err[:, :ncol] ** 2).reshape(rows // 256, 256, ncol // 256, 256).mean(axis=(1, 3)))
+    ref_rms = np.sqrt((want[:, :ncol] ** 2).reshape(rows // 256, 256, ncol // 256, 256).mean(axis=(1, 3)))
+    assert np.all(tile_rms <= 2e-3 * (ref_rms + 1.0))
+    mask, obs = feed[-1], targets != 0
+    rm_got = np.sqrt((((mask * got) - targets)[obs] ** 2).mean())
+    rm_want = np.sqrt((((mask * want) - targets)[obs] ** 2).mean())
+    assert abs(rm_got - rm_want) <= 1e-3 * rm_want
+    # top-k over the same multi-tile scores: exact selection on the device's own scores
+    cols, scores = om.model.recommend(batch, k=50, exclude_seen=False)
+    order = np.lexsort((np.arange(fs.n_cols)[None, :].repeat(8, 0), -again[:8]), axis=1)[:, :50]
+    assert np.array_equal(cols[:8], order.astype(np.int32))
+    assert np.array_equal(scores[:8], np.take_along_axis(again[:8], order, axis=1))
+    om.model.close()
+    rd.close()
