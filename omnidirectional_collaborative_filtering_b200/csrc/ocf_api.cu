@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "ocf_kernels.cuh"
@@ -145,10 +147,12 @@ struct ocf_pair {
 };
 
 struct ocf_batch {
+  uint64_t uid = 0;               // never reused: captured steps are keyed by it
   int max_rows = 0;
   int64_t max_entries = 0;
   int max_items = 0;
   size_t staging_bytes = 0;
+  size_t off[8] = {0};            // fixed layout of the staging buffer (staging_layout)
   uint8_t* h_staging = nullptr;   // pinned
   uint8_t* d_staging = nullptr;
   cudaEvent_t copied = nullptr;
@@ -201,8 +205,18 @@ struct ocf_model {
   float* dh_top = nullptr;
   float* dense_out = nullptr;
   float* regparts = nullptr;
-  float* d_log = nullptr;
-  float* h_rec = nullptr;         // pinned
+  float* h_rec = nullptr;         // page-locked, mapped: the metric log, written by the kernels, read by the host
+  float* h_rec_dev = nullptr;     //   its device address
+  StepDev* d_step = nullptr;      // device-resident step scalars (dropout counter, log slot, lr)
+  StepDev step_mirror{};          //   what the device holds once everything enqueued so far has run
+  bool step_mirror_valid = false;
+  TailBuf tail{};                 // row-tail counters and group sums of K2 / K3
+  // captured steps (CUDA graphs), keyed by batch object / rows / kind; dropped whenever anything they
+  // bake in changes (workspaces, optimizer, trainable flags, ...)
+  struct StepGraph { cudaGraphExec_t exec = nullptr; int kernels = 0; int seen = 0; bool failed = false; };
+  std::map<std::tuple<uint64_t, int, int, int, int>, StepGraph> graphs;
+  cudaStream_t cap = nullptr;     // capture stream
+  bool capturing = false;
   int* d_err = nullptr;
   int64_t steps_logged = 0;
   cudaEvent_t step_ev[64] = {nullptr};
@@ -245,9 +259,13 @@ struct ocf_model {
   Arena mem, opt_mem, dense_mem, ws_mem;
 };
 
-constexpr int LOG_CAP = 4096;
-constexpr int LOG_W = OCF_N_METRICS;
 constexpr int N_REGPART = 64;
+
+static void drop_graphs(ocf_model* m) {
+  for (auto& kv : m->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
+}
 
 // ============================================================================================
 // misc
@@ -504,17 +522,23 @@ static int max_items_for(int max_rows, int64_t max_entries) {
   return (int)std::min<int64_t>(max_entries / 32 + max_rows + 1, TARGET_ITEMS + max_rows + 1);
 }
 
-static size_t staging_layout(int B, int n_items, int64_t n_entries, size_t off[7]) {
+// Fixed for the life of a batch object (sized by its capacity), so that every device pointer a kernel
+// gets is the same for every fill: [header | row_ids | ent_off | in_len | item_ptr | items | draw_off | flags].
+// One copy uploads the prefix up to the flags (or through them when the host supplies the flags).
+static size_t staging_layout(int max_rows, int max_items, int64_t max_entries, size_t off[8]) {
   size_t o = 0;
-  off[0] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // row_ids
-  off[1] = o; o = align_up(o + sizeof(int32_t) * (B + 1), 16);       // ent_off
-  off[2] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // in_len
-  off[3] = o; o = align_up(o + sizeof(int32_t) * (B + 1), 16);       // item_ptr
-  off[4] = o; o = align_up(o + sizeof(int4) * (size_t)n_items, 16);  // items
-  off[5] = o; o = align_up(o + sizeof(int32_t) * B, 16);             // draw_off (device-RNG mode)
-  off[6] = o; o = align_up(o + (size_t)n_entries, 16);               // flags (last: not uploaded when the device derives them)
+  off[0] = o; o = align_up(o + sizeof(BatchHdr), 64);                        // header
+  off[1] = o; o = align_up(o + sizeof(int32_t) * max_rows, 16);              // row_ids
+  off[2] = o; o = align_up(o + sizeof(int32_t) * (max_rows + 1), 16);        // ent_off
+  off[3] = o; o = align_up(o + sizeof(int32_t) * max_rows, 16);              // in_len
+  off[4] = o; o = align_up(o + sizeof(int32_t) * (max_rows + 1), 16);        // item_ptr
+  off[5] = o; o = align_up(o + sizeof(int4) * (size_t)max_items, 16);        // items
+  off[6] = o; o = align_up(o + sizeof(int32_t) * max_rows, 16);              // draw_off (device-RNG mode)
+  off[7] = o; o = align_up(o + (size_t)max_entries, 16);                     // flags (last: not uploaded when the device derives them)
   return o;
 }
+
+static std::atomic<uint64_t> g_batch_uid{0};
 
 extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch** out) {
   OCF_REQUIRE(out != nullptr, "ocf_batch_create: null argument");
@@ -523,9 +547,9 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
   OCF_REQUIRE(max_entries >= 0 && max_entries < (int64_t(1) << 31), "ocf_batch_create: bad max_entries");
   ocf_batch* b = new ocf_batch();
   b->max_rows = max_rows; b->max_entries = max_entries;
+  b->uid = ++g_batch_uid;
   b->max_items = max_items_for(max_rows, max_entries);
-  size_t off[7];
-  b->staging_bytes = staging_layout(max_rows, b->max_items, max_entries, off);
+  b->staging_bytes = staging_layout(max_rows, b->max_items, max_entries, b->off);
   auto bail = [&](int code) { b->mem.release(); if (b->h_staging) cudaFreeHost(b->h_staging); if (b->copied) cudaEventDestroy(b->copied); delete b; return code; };
   if (cudaMallocHost(reinterpret_cast<void**>(&b->h_staging), b->staging_bytes) != cudaSuccess)
     return bail(fail(OCF_ERR_NOMEM, "ocf_batch_create: pinned allocation failed"));
@@ -535,6 +559,19 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
   if ((st = b->mem.get(&b->d_staging, b->staging_bytes)) || (st = b->mem.get(&b->d_ent_col, (size_t)max_entries)) ||
       (st = b->mem.get(&b->d_ent_val, (size_t)max_entries)) || (st = b->mem.get(&b->d_codes, (size_t)max_entries)))
     return bail(st);
+  std::memset(b->h_staging, 0, b->staging_bytes);
+  BatchDev& d = b->dev;
+  const size_t* off = b->off;
+  d.hdr = reinterpret_cast<const BatchHdr*>(b->d_staging + off[0]);
+  d.row_ids = reinterpret_cast<const int32_t*>(b->d_staging + off[1]);
+  d.ent_off = reinterpret_cast<const int32_t*>(b->d_staging + off[2]);
+  d.in_len = reinterpret_cast<const int32_t*>(b->d_staging + off[3]);
+  d.item_ptr = reinterpret_cast<const int32_t*>(b->d_staging + off[4]);
+  d.items = reinterpret_cast<const int4*>(b->d_staging + off[5]);
+  d.draw_off = reinterpret_cast<const int32_t*>(b->d_staging + off[6]);
+  d.flags = b->d_staging + off[7];
+  d.flags_out = b->d_staging + off[7];
+  d.ent_col = b->d_ent_col; d.ent_val = b->d_ent_val; d.codes = b->d_codes;
   *out = b;
   return OCF_OK;
 }
@@ -566,7 +603,8 @@ static int pick_chunk(int64_t n_entries) {
 // leaves the flags to the device.
 static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const std::vector<int64_t>& rp_a,
                        const std::vector<int64_t>* rp_b, int64_t n_store_rows, const uint8_t* flags,
-                       int64_t n_flags, cudaStream_t stream, bool with_draws = false, const int64_t* draw_len = nullptr) {
+                       int64_t n_flags, cudaStream_t stream, uint32_t hdr_tag, int hdr_pass_through, float hdr_aux,
+                       bool with_draws = false, const int64_t* draw_len = nullptr) {
   OCF_REQUIRE(n_rows > 0 && n_rows <= b->max_rows, "batch fill: row count exceeds the batch capacity");
   if (b->copy_pending) { OCF_CUDA(cudaEventSynchronize(b->copied)); b->copy_pending = false; }
   // pass 1: lengths
@@ -585,19 +623,19 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
     const int32_t row = row_ids[r];
     int64_t n = rp_a[row + 1] - rp_a[row];
     if (rp_b) n += (*rp_b)[row + 1] - (*rp_b)[row];
-    n_items += (n + ch - 1) / ch;
+    n_items += std::max<int64_t>(1, (n + ch - 1) / ch);          // an empty row still gets one (empty) item: its row tail
   }
   OCF_REQUIRE(n_items <= b->max_items, "batch fill: too many work items");
-  size_t off[7];
-  const size_t bytes_all = staging_layout(n_rows, (int)n_items, total, off);
-  const size_t bytes = flags != nullptr ? bytes_all : off[6];       // without host flags the flag slot is not copied
+  const size_t* off = b->off;
+  const size_t bytes = flags != nullptr ? off[7] + (size_t)total : off[7];       // without host flags the flag slot is not copied
   uint8_t* hs = b->h_staging;
-  int32_t* h_rows = reinterpret_cast<int32_t*>(hs + off[0]);
-  int32_t* h_eoff = reinterpret_cast<int32_t*>(hs + off[1]);
-  int32_t* h_inlen = reinterpret_cast<int32_t*>(hs + off[2]);
-  int32_t* h_iptr = reinterpret_cast<int32_t*>(hs + off[3]);
-  int4* h_items = reinterpret_cast<int4*>(hs + off[4]);
-  int32_t* h_draw = reinterpret_cast<int32_t*>(hs + off[5]);
+  BatchHdr* h_hdr = reinterpret_cast<BatchHdr*>(hs + off[0]);
+  int32_t* h_rows = reinterpret_cast<int32_t*>(hs + off[1]);
+  int32_t* h_eoff = reinterpret_cast<int32_t*>(hs + off[2]);
+  int32_t* h_inlen = reinterpret_cast<int32_t*>(hs + off[3]);
+  int32_t* h_iptr = reinterpret_cast<int32_t*>(hs + off[4]);
+  int4* h_items = reinterpret_cast<int4*>(hs + off[5]);
+  int32_t* h_draw = reinterpret_cast<int32_t*>(hs + off[6]);
   int64_t e = 0; int it = 0; int64_t tcount = 0; int64_t draw = b->draw_base;   // the sparsity draws come first
   for (int r = 0; r < n_rows; ++r) {
     const int32_t row = row_ids[r];
@@ -606,11 +644,15 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
     h_rows[r] = row; h_eoff[r] = (int32_t)e; h_inlen[r] = (int32_t)na; h_iptr[r] = it;
     if (with_draws) { h_draw[r] = (int32_t)draw; draw += draw_len ? draw_len[r] : na; }
     const int64_t n = na + nb;
+    if (n == 0) h_items[it++] = make_int4(r, 0, 0, 0);
     for (int64_t s0 = 0; s0 < n; s0 += ch) h_items[it++] = make_int4(r, (int)s0, (int)std::min<int64_t>(ch, n - s0), 0);
     e += n; tcount += nb;
   }
   h_eoff[n_rows] = (int32_t)e; h_iptr[n_rows] = it;
-  if (flags != nullptr && total > 0) std::memcpy(hs + off[6], flags, (size_t)total);
+  h_hdr->B = n_rows; h_hdr->n_items = (int)n_items; h_hdr->n_entries = (int)total;
+  h_hdr->tag = hdr_tag; h_hdr->cdf_row0 = b->cdf0_row0; h_hdr->pass_through = hdr_pass_through;
+  h_hdr->rng_lo = b->rng_lo; h_hdr->rng_range = b->rng_range; h_hdr->aux_value = hdr_aux;
+  if (flags != nullptr && total > 0) std::memcpy(hs + off[7], flags, (size_t)total);
   OCF_CUDA(cudaMemcpyAsync(b->d_staging, hs, bytes, cudaMemcpyHostToDevice, stream));
   OCF_CUDA(cudaEventRecord(b->copied, stream));
   b->copy_pending = true;
@@ -618,16 +660,7 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
   b->target_count = tcount;
   BatchDev& d = b->dev;
   d.B = n_rows; d.n_items = (int)n_items; d.n_entries = (int)total;
-  d.row_ids = reinterpret_cast<const int32_t*>(b->d_staging + off[0]);
-  d.ent_off = reinterpret_cast<const int32_t*>(b->d_staging + off[1]);
-  d.in_len = reinterpret_cast<const int32_t*>(b->d_staging + off[2]);
-  d.item_ptr = reinterpret_cast<const int32_t*>(b->d_staging + off[3]);
-  d.items = reinterpret_cast<const int4*>(b->d_staging + off[4]);
-  d.draw_off = reinterpret_cast<const int32_t*>(b->d_staging + off[5]);
-  d.flags = b->d_staging + off[6];
-  d.flags_out = b->d_staging + off[6];
   d.words = b->d_words; d.rng_lo = b->rng_lo; d.rng_range = b->rng_range; d.cdf_row0 = b->cdf0_row0;
-  d.ent_col = b->d_ent_col; d.ent_val = b->d_ent_val; d.codes = b->d_codes;
   return OCF_OK;
 }
 
@@ -635,8 +668,8 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
 static int launch_gather(ocf_batch* b, cudaStream_t stream) {
   if (b->dev.n_items == 0) return OCF_OK;
   g_prof.begin(0, stream);
-  if (b->mode == 1 && b->rng_mode) k_gather_split<true><<<b->dev.n_items, 128, 0, stream>>>(b->store->dev, b->dev, b->pass_through);
-  else if (b->mode == 1) k_gather_split<false><<<b->dev.n_items, 128, 0, stream>>>(b->store->dev, b->dev, b->pass_through);
+  if (b->mode == 1 && b->rng_mode) k_gather_split<true><<<b->dev.n_items, 128, 0, stream>>>(b->store->dev, b->dev);
+  else if (b->mode == 1) k_gather_split<false><<<b->dev.n_items, 128, 0, stream>>>(b->store->dev, b->dev);
   else k_gather_fixed<<<b->dev.n_items, 128, 0, stream>>>(b->pair->in->dev, b->pair->tg->dev, b->pair->d_in_overlap, b->dev);
   OCF_LAUNCHED();
   g_prof.end(0, stream);
@@ -652,7 +685,8 @@ extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const 
   OCF_REQUIRE(keep_flags != nullptr || n_flags == 0, "ocf_batch_fill_split: null keep_flags");
   cudaStream_t stream = as_stream(stream_);
   OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split"));
-  OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, keep_flags, n_flags, stream));
+  OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, keep_flags, n_flags, stream,
+                      b->tag, pass_through ? 1 : 0, aux_var_value));
   b->dev.rowslot = b->d_rowslot;
   b->dev.tag = b->tag;
   b->mode = 1; b->store = store; b->aux_value = aux_var_value; b->rng_mode = false;
@@ -698,7 +732,8 @@ extern "C" int ocf_batch_fill_fixed(ocf_batch* b, const ocf_pair* pair, const in
                                     float aux_var_value, void* stream_) {
   OCF_REQUIRE(b && pair && row_ids, "ocf_batch_fill_fixed: null argument");
   cudaStream_t stream = as_stream(stream_);
-  OCF_TRY(batch_stage(b, row_ids, n_rows, pair->in->h_rowptr, &pair->tg->h_rowptr, pair->in->n_rows, nullptr, -1, stream));
+  OCF_TRY(batch_stage(b, row_ids, n_rows, pair->in->h_rowptr, &pair->tg->h_rowptr, pair->in->n_rows, nullptr, -1, stream,
+                      0u, 0, aux_var_value));
   b->dev.rowslot = nullptr; b->dev.tag = 0;
   b->mode = 2; b->store = pair->tg; b->aux_value = aux_var_value;
   b->pair = pair;
@@ -844,7 +879,8 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
   OCF_LAUNCHED();
   OCF_CUDA(cudaEventRecord(b->words_ready, rng->stream));
   OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split_rng"));
-  OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, nullptr, -1, stream, true, full_len));
+  OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, nullptr, -1, stream,
+                      b->tag, pass_through ? 1 : 0, aux_var_value, true, full_len));
   b->dev.rowslot = b->d_rowslot;
   b->dev.tag = b->tag;
   b->mode = 1; b->store = store; b->aux_value = aux_var_value; b->rng_mode = true;
@@ -912,6 +948,7 @@ static void aux_bits(int aux, int& nblk, int3& bits) {
 
 // Batch-sized buffers (activations, work-item partials, per-entry gradients).
 static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
+  drop_graphs(m);
   m->ws_mem.release();
   m->dense_mem.release();
   m->dense_out = nullptr;
@@ -937,6 +974,16 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   OCF_TRY(ws.get(&m->P1, (size_t)m->max_items * m->hp[0]));
   OCF_TRY(ws.get(&m->P2, (size_t)m->max_items * m->hp[L - 1]));
   OCF_TRY(ws.get(&m->itemstats, (size_t)m->max_items * ROWSTAT_W));
+  {
+    int hpmax = 0;
+    for (int l = 0; l < L; ++l) hpmax = std::max(hpmax, m->hp[l]);
+    float* G = nullptr;
+    OCF_TRY(ws.get(&G, (size_t)m->max_items * hpmax));
+    m->tail.G = reinterpret_cast<float4*>(G);
+    OCF_TRY(ws.get(&m->tail.Gs, (size_t)m->max_items * ROWSTAT_W));
+    OCF_TRY(ws.get(&m->tail.tick_grp, (size_t)m->max_items, true));      // self-resetting arrival counters
+    OCF_TRY(ws.get(&m->tail.tick_row, (size_t)max_rows, true));
+  }
   OCF_TRY(ws.get(&m->dy, (size_t)max_entries, true));
   // [row statistics | dL/dh of the top hidden layer] share one allocation: a column shard
   // all-reduces both with a single collective over the prefix 4*max_rows + B*hp floats
@@ -981,19 +1028,22 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
     if (!st) st = m->mem.get(&ly.b, (size_t)ly.bias_len, true);
   }
   if (st) return bail(st);
-  if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_log, (size_t)LOG_CAP * LOG_W, true)) ||
+  if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_step, 1, true)) ||
       (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_seg, (size_t)N, true)) ||
       (st = m->mem.get(&m->col_counters, 4, true)) || (st = m->mem.get(&m->col_state, (size_t)3 * N, true)) ||
       (st = m->mem.get(&m->col_info, (size_t)N)))
     return bail(st);
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev); if (m->sm_count <= 0) m->sm_count = 148; }
   if ((st = alloc_workspace(m, cfg->max_rows, cfg->max_entries))) return bail(st);
-  if (cudaMallocHost(reinterpret_cast<void**>(&m->h_rec), sizeof(float) * LOG_CAP * LOG_W) != cudaSuccess)
+  if (cudaHostAlloc(reinterpret_cast<void**>(&m->h_rec), sizeof(float) * LOG_CAP * LOG_W, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->h_rec_dev), m->h_rec, 0) != cudaSuccess)
     return bail(fail(OCF_ERR_NOMEM, "ocf_model_create: pinned allocation failed"));
+  std::memset(m->h_rec, 0, sizeof(float) * LOG_CAP * LOG_W);
   for (int k = 0; k < 64; ++k)
     if (cudaEventCreateWithFlags(&m->step_ev[k], cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(OCF_ERR_CUDA, "ocf_model_create: event creation failed"));
   if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->cap, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(OCF_ERR_CUDA, "ocf_model_create: side stream creation failed"));
@@ -1005,10 +1055,13 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
 
 extern "C" int ocf_model_destroy(ocf_model* m) {
   if (m) {
+    cudaDeviceSynchronize();
     m->mem.release(); m->opt_mem.release(); m->dense_mem.release(); m->ws_mem.release(); m->par_mem.release();
     if (m->h_rec) cudaFreeHost(m->h_rec);
     for (int k = 0; k < 64; ++k) if (m->step_ev[k]) cudaEventDestroy(m->step_ev[k]);
+    drop_graphs(m);
     if (m->side) cudaStreamDestroy(m->side);
+    if (m->cap) cudaStreamDestroy(m->cap);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
@@ -1107,6 +1160,8 @@ extern "C" int ocf_model_set_optimizer(ocf_model* m, int kind, float lr, float p
   OCF_REQUIRE(m, "ocf_model_set_optimizer: null argument");
   OCF_REQUIRE(kind >= OCF_OPT_SGD && kind <= OCF_OPT_ADAM, "ocf_model_set_optimizer: bad kind");
   OCF_CUDA(cudaDeviceSynchronize());
+  drop_graphs(m);
+  m->step_mirror_valid = false;
   const bool s1 = kind != OCF_OPT_SGD, s2 = kind == OCF_OPT_ADAM;
   if (s1 != m->has_s1 || s2 != m->has_s2) {
     m->opt_mem.release();
@@ -1123,6 +1178,7 @@ extern "C" int ocf_model_set_optimizer(ocf_model* m, int kind, float lr, float p
 
 extern "C" int ocf_model_set_loss(ocf_model* m, int loss, float rating_range) {
   OCF_REQUIRE(m && (loss == OCF_LOSS_MSE || loss == OCF_LOSS_MAE), "ocf_model_set_loss: bad argument");
+  if (m->cfg.loss != loss || m->cfg.rating_range != rating_range) drop_graphs(m);
   m->cfg.loss = loss;
   m->cfg.rating_range = rating_range;
   return OCF_OK;
@@ -1133,12 +1189,14 @@ extern "C" int ocf_model_set_aux(ocf_model* m, int aux) {
   int nblk; int3 bits;
   aux_bits(aux, nblk, bits);
   OCF_REQUIRE(nblk == m->nblk, "ocf_model_set_aux: this mask type feeds a different number of input blocks than the model has");
+  if (m->cfg.aux != aux) drop_graphs(m);
   m->cfg.aux = aux; m->bits = bits;
   return OCF_OK;
 }
 
 extern "C" int ocf_model_set_trainable(ocf_model* m, int layer, int trainable) {
   OCF_REQUIRE(m && layer >= 0 && layer <= m->L, "ocf_model_set_trainable: bad argument");
+  if (m->layers[layer].trainable != (trainable != 0)) drop_graphs(m);
   m->layers[layer].trainable = trainable != 0;
   return OCF_OK;
 }
@@ -1195,6 +1253,7 @@ static OptDev make_opt(const ocf_model* m) {
   o.eps = m->eps;
   o.l2x2 = m->cfg.l2 >= 0.f ? (float)(2.0 * (double)m->cfg.l2) : 0.f;
   o.dense = (m->opt_kind == OCF_OPT_RMSPROP || m->opt_kind == OCF_OPT_ADAM || o.l2x2 != 0.f) ? 1 : 0;
+  o.st = m->d_step;                 // the kernels read this step's lr there (sync_step_state keeps it current)
   return o;
 }
 
@@ -1210,20 +1269,60 @@ static int check_step(const ocf_model* m, const ocf_batch* b, bool train) {
   return OCF_OK;
 }
 
-// phase 1: encoder partial sums -> zsum[0]
-static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st, float* z_out = nullptr) {
+// Makes the device-resident step scalars what this step needs: the caller's dropout counter / seed,
+// the host's log slot and this step's learning rate. The kernels advance step and log_slot themselves,
+// so a plain training loop never rewrites them (Adam and `decay` change lr every step and do).
+static int sync_step_state(ocf_model* m, const ocf_step_args* args, cudaStream_t st) {
+  StepDev want{};
+  want.step = args ? args->step : 0u;
+  want.log_slot = (int32_t)(m->steps_logged % LOG_CAP);
+  want.lr = make_opt(m).lr;
+  const uint64_t seed = args ? args->dropout_seed : 0;
+  want.seed_lo = (uint32_t)(seed & 0xffffffffu); want.seed_hi = (uint32_t)(seed >> 32);
+  const StepDev& have = m->step_mirror;
+  if (m->step_mirror_valid && have.step == want.step && have.log_slot == want.log_slot && have.lr == want.lr &&
+      have.seed_lo == want.seed_lo && have.seed_hi == want.seed_hi)
+    return OCF_OK;
+  k_set_step<<<1, 1, 0, st>>>(m->d_step, want);
+  OCF_LAUNCHED();
+  m->step_mirror = want;
+  m->step_mirror_valid = true;
+  return OCF_OK;
+}
+
+// Work-item grids: a captured step must cover any later fill of the same batch object, so it
+// launches the batch's item capacity (CTAs beyond the header's n_items return at once).
+static inline int item_grid(const ocf_model* m, const ocf_batch* b) {
+  return m->capturing ? std::min(b->max_items, m->max_items) : b->dev.n_items;
+}
+
+static ActArgs act_args(ocf_model* m, int l, int B, bool training, const ocf_step_args* args) {
+  const int hp = m->hp[l];
+  const bool drop = training && m->cfg.dropout_p > 0.f;
+  ActArgs g{};
+  g.bias = reinterpret_cast<const float4*>(m->layers[l].b); g.B = B; g.H = m->cfg.widths[l]; g.hp4 = hp / 4;
+  g.act = m->cfg.activation;
+  g.a_out = reinterpret_cast<float4*>(m->act[l]);
+  g.h_out = reinterpret_cast<float4*>(drop ? m->h[l] : m->act[l]);
+  g.dscale = drop ? reinterpret_cast<float4*>(m->dscale[l]) : nullptr;
+  g.p_drop = m->cfg.dropout_p;
+  g.st = m->d_step; g.layer = (uint32_t)l; g.row0 = args ? args->row0 : 0;
+  return g;
+}
+
+// phase 1: encoder partial sums; the row tails leave either z (z_out, or zsum[0]) or, with `fuse_act`,
+// the first layer's activations (bias + activation + dropout applied by the row's last CTA).
+static int phase_encode(ocf_model* m, const ocf_batch* b, cudaStream_t st, float* z_out, bool fuse_act, bool training,
+                        const ocf_step_args* args) {
   const BatchDev& bt = b->dev;
   const int hp0 = m->hp[0];
-  if (bt.n_items > 0) {
-    g_prof.begin(1, st);
-    OCF_NV_SWITCH(hp0, k_enc_fwd<NV><<<bt.n_items, 128, 0, st>>>(bt, m->layers[0].W, m->cfg.n_cols, m->nblk, m->bits,
-                                                                b->aux_value, reinterpret_cast<float4*>(m->P1)));
-    OCF_LAUNCHED();
-    g_prof.end(1, st);
-  }
-  k_rowsum<<<bt.B, hp0, (size_t)hp0 * 16, st>>>(reinterpret_cast<const float4*>(m->P1), bt.item_ptr, hp0 / 4,
-                                                reinterpret_cast<float4*>(z_out ? z_out : m->zsum[0]), nullptr, nullptr);
+  const ActArgs act = act_args(m, 0, bt.B, training, args);
+  float4* z = reinterpret_cast<float4*>(z_out ? z_out : m->zsum[0]);
+  g_prof.begin(1, st);
+  OCF_NV_SWITCH(hp0, k_enc_fwd<NV><<<item_grid(m, b), 128, 0, st>>>(bt, m->layers[0].W, m->cfg.n_cols, m->nblk, m->bits,
+                                                                     reinterpret_cast<float4*>(m->P1), m->tail, z, fuse_act ? 1 : 0, act));
   OCF_LAUNCHED();
+  g_prof.end(1, st);
   return OCF_OK;
 }
 
@@ -1247,30 +1346,14 @@ static int launch_gemm(ocf_model* m, bool ta, bool tb, const float* A, int lda, 
   else k_sgemm<true, true><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, M, N, K, ep);
   OCF_LAUNCHED();
   if (S > 1) {
-    k_gemm_reduce<<<(M * N + 255) / 256, 256, 0, st>>>(M, N, S, ep);
+    k_gemm_reduce<<<(M * ((N + 3) / 4) + 255) / 256, 256, 0, st>>>(M, N, S, ep);
     OCF_LAUNCHED();
   }
   return OCF_OK;
 }
 
-static ActArgs act_args(ocf_model* m, int l, int B, bool training, const ocf_step_args* args) {
-  const int hp = m->hp[l];
-  const bool drop = training && m->cfg.dropout_p > 0.f;
-  const uint64_t seed = args ? args->dropout_seed : 0;
-  ActArgs g{};
-  g.bias = reinterpret_cast<const float4*>(m->layers[l].b); g.B = B; g.H = m->cfg.widths[l]; g.hp4 = hp / 4;
-  g.act = m->cfg.activation;
-  g.a_out = reinterpret_cast<float4*>(m->act[l]);
-  g.h_out = reinterpret_cast<float4*>(drop ? m->h[l] : m->act[l]);
-  g.dscale = drop ? reinterpret_cast<float4*>(m->dscale[l]) : nullptr;
-  g.p_drop = m->cfg.dropout_p;
-  g.key = make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
-  g.step = args ? args->step : 0u; g.layer = (uint32_t)l; g.row0 = args ? args->row0 : 0;
-  return g;
-}
-
 static float* g_gemm_part_of(ocf_model* m) {
-  if (m->gemm_part == nullptr && m->mem.get(&m->gemm_part, GEMM_PART_FLOATS) != OCF_OK) m->gemm_part = nullptr;
+  if (m->gemm_part == nullptr && !m->capturing && m->mem.get(&m->gemm_part, GEMM_PART_FLOATS) != OCF_OK) m->gemm_part = nullptr;
   return m->gemm_part;
 }
 
@@ -1284,7 +1367,8 @@ static int launch_act(ocf_model* m, int l, int B, bool training, const ocf_step_
 }
 
 // phase 2: activations, hidden layers, decoder at the target entries, loss partials -> dh_top, rowstats
-// act0_done: the first layer's activations are already in place (fused into the peer exchange).
+// act0_done: the first layer's activations are already in place (fused into the encoder's row tails or
+// into the peer exchange).
 // xslot: write the row statistics [B, 4] and dL/dh [B, hp] into this exchange slot instead of the
 // model's buffers (a peer all-reduce follows).
 static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args,
@@ -1294,66 +1378,58 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   const bool drop = training && m->cfg.dropout_p > 0.f;
   if (!act0_done) OCF_TRY(launch_act(m, 0, B, training, args, st));
   for (int l = 1; l < L; ++l) {
-    GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];
+    // hidden layer: product + bias + activation + dropout in the GEMM's epilogue
+    GemmEpi ep{}; ep.kind = EPI_BIAS_ACT; ep.C = m->zsum[l]; ep.ldc = m->hp[l]; ep.actargs = act_args(m, l, B, training, args);
     const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
     OCF_TRY(launch_gemm(m, false, false, hin, m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
-    OCF_TRY(launch_act(m, l, B, training, args, st));
   }
   const float* htop = drop ? m->h[L - 1] : m->act[L - 1];
   const int hpt = m->hp[L - 1];
   const int rows_total = (args && args->rows_total > 0) ? args->rows_total : B;
   const double bn = (double)rows_total * (double)m->cfg.n_cols_total;
   const float gscale = (float)((m->cfg.loss == OCF_LOSS_MSE ? 2.0 : 1.0) / bn);
-  if (bt.n_items > 0) {
-    g_prof.begin(2, st);
-    if (training) {
-      OCF_NV_SWITCH(hpt, k_dec_fwd<NV, true><<<bt.n_items, 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, b->aux_value, gscale,
-                                                                          m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2), m->itemstats, dense_out, m->cfg.n_cols));
-    } else {
-      OCF_NV_SWITCH(hpt, k_dec_fwd<NV, false><<<bt.n_items, 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, b->aux_value, gscale,
-                                                                           m->cfg.loss, nullptr, nullptr, m->itemstats, dense_out, m->cfg.n_cols));
-    }
-    OCF_LAUNCHED();
-    g_prof.end(2, st);
-  }
   float* stats_out = xslot ? xslot : m->rowstats;
-  float* dh_out = xslot ? xslot + (size_t)B * ROWSTAT_W : m->dh_top;
+  float4* dh_out = reinterpret_cast<float4*>(xslot ? xslot + (size_t)B * ROWSTAT_W : m->dh_top);
+  g_prof.begin(2, st);
   if (training) {
-    k_rowsum<<<B, hpt, (size_t)hpt * 16, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, hpt / 4,
-                                               reinterpret_cast<float4*>(dh_out), m->itemstats, stats_out);
+    OCF_NV_SWITCH(hpt, k_dec_fwd<NV, true><<<item_grid(m, b), 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, gscale,
+                                                                        m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2), m->itemstats, dense_out, m->cfg.n_cols,
+                                                                        m->tail, dh_out, stats_out));
   } else {
-    k_rowsum<<<B, 32, 0, st>>>(reinterpret_cast<const float4*>(m->P2), bt.item_ptr, 0, nullptr, m->itemstats, stats_out);
+    OCF_NV_SWITCH(hpt, k_dec_fwd<NV, false><<<item_grid(m, b), 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, gscale,
+                                                                         m->cfg.loss, nullptr, nullptr, m->itemstats, dense_out, m->cfg.n_cols,
+                                                                         m->tail, nullptr, stats_out));
   }
   OCF_LAUNCHED();
+  g_prof.end(2, st);
   return OCF_OK;
 }
 
-static MetricArgs metric_args(ocf_model* m, int B, const ocf_step_args* args, int n_reg, const float* stats = nullptr) {
+static MetricArgs metric_args(ocf_model* m, int B, const ocf_step_args* args, int n_reg, bool advance_step, const float* stats = nullptr) {
   const int rows_total = (args && args->rows_total > 0) ? args->rows_total : B;
   MetricArgs a{};
   a.rowstats = stats ? stats : m->rowstats; a.rows = B; a.rows_total = (float)rows_total;
   a.n_cols_total = (float)m->cfg.n_cols_total; a.rating_range = m->cfg.rating_range; a.loss_kind = m->cfg.loss;
   a.regparts = m->regparts; a.n_reg = n_reg; a.l2 = m->cfg.l2 >= 0.f ? m->cfg.l2 : 0.f;
-  a.rec = m->d_log + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
+  a.log = m->h_rec_dev; a.st = m->d_step; a.advance_step = advance_step ? 1 : 0;
   return a;
 }
 
-// Every step's record goes back to pinned host memory right behind its kernels; readers wait on
-// the step's event instead of the whole stream.
-static int publish_metrics(ocf_model* m, cudaStream_t st) {
-  float* rec = m->d_log + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
-  float* hrec = m->h_rec + (size_t)(m->steps_logged % LOG_CAP) * LOG_W;
-  OCF_CUDA(cudaMemcpyAsync(hrec, rec, sizeof(float) * LOG_W, cudaMemcpyDeviceToHost, st));
+// A step's record is written into page-locked host memory by its own kernel; readers wait on the step's
+// event instead of the whole stream. Also advances the host's mirror of the device-side step scalars.
+static int publish_metrics(ocf_model* m, bool trained, cudaStream_t st) {
   OCF_CUDA(cudaEventRecord(m->step_ev[m->steps_logged % 64], st));
   m->steps_logged += 1;
+  m->step_mirror.log_slot = (int32_t)(m->steps_logged % LOG_CAP);
+  if (trained) m->step_mirror.step += 1u;
   return OCF_OK;
 }
 
-static int launch_metrics(ocf_model* m, int B, const ocf_step_args* args, int n_reg, cudaStream_t st,
+static int launch_metrics(ocf_model* m, int B, const ocf_step_args* args, int n_reg, bool trained, cudaStream_t st,
                           const float* stats = nullptr) {
-  k_metrics<<<1, 32, 0, st>>>(metric_args(m, B, args, n_reg, stats));
+  k_metrics<<<1, 32, 0, st>>>(metric_args(m, B, args, n_reg, trained, stats));
   OCF_LAUNCHED();
-  return publish_metrics(m, st);
+  return OCF_OK;
 }
 
 static int launch_reg(ocf_model* m, cudaStream_t st) {
@@ -1384,39 +1460,40 @@ static int launch_row_update(int hp, int kind, int grid, const RowArgs& r, cudaS
   return OCF_OK;
 }
 
-// K4a: the store's CSC row ids against the batch's rows -> match list + update tasks.
+// K4a: the batch's ratings grouped by catalogue column -> match list + update tasks.
 static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int dense, cudaStream_t st) {
   if (!do_dec && !do_enc) return OCF_OK;
   const BatchDev& bt = b->dev;
   OCF_CUDA(cudaMemsetAsync(m->col_counters, 0, 4 * sizeof(int), st));
   if (dense) OCF_CUDA(cudaMemsetAsync(m->col_seg, 0, sizeof(int2) * (size_t)m->cfg.n_cols, st));
-  if (bt.n_entries == 0) return OCF_OK;
   if (!b->store->has_dups) {
     // batch-side counting sort (every (column, batch row) pair is unique)
     const int W = (bt.B + 31) / 32;
-    const size_t words = (size_t)std::min<int64_t>(m->cfg.n_cols, bt.n_entries) * W;
+    // (a captured step clears the whole bitmap: its size must not depend on the fill)
+    const size_t words = m->capturing ? m->col_bits_words : (size_t)std::min<int64_t>(m->cfg.n_cols, bt.n_entries) * W;
     OCF_CUDA(cudaMemsetAsync(m->col_state, 0, sizeof(int) * 3 * (size_t)m->cfg.n_cols, st));
-    OCF_CUDA(cudaMemsetAsync(m->col_bits, 0, sizeof(uint32_t) * std::min(words, m->col_bits_words), st));
+    OCF_CUDA(cudaMemsetAsync(m->col_bits, 0, sizeof(uint32_t) * std::max<size_t>(std::min(words, m->col_bits_words), 4), st));
     SortArgs a{};
     a.bt = bt;
     a.cnt = m->col_state; a.codeor = m->col_state + m->cfg.n_cols; a.claimed = m->col_state + 2 * (size_t)m->cfg.n_cols;
     a.colinfo = m->col_info; a.bits = m->col_bits; a.W = W; a.counters = m->col_counters;
     a.matches = m->col_matches; a.tasks = m->col_tasks; a.colseg = m->col_seg;
     a.nblk = m->nblk; a.bits3 = m->bits; a.dense = dense; a.do_dec = do_dec; a.do_enc = do_enc;
+    const int grid = item_grid(m, b);
     g_prof.begin(3, st);
-    k_sort_count<<<bt.n_items, 128, 0, st>>>(a);
+    k_sort_count<<<grid, 128, 0, st>>>(a);
     OCF_LAUNCHED();
-    k_sort_alloc<<<bt.n_items, 128, 0, st>>>(a);
+    k_sort_alloc<<<grid, 128, 0, st>>>(a);
     OCF_LAUNCHED();
-    k_sort_bits<<<bt.n_items, 128, 0, st>>>(a);
+    k_sort_bits<<<grid, 128, 0, st>>>(a);
     OCF_LAUNCHED();
-    k_sort_place<<<bt.n_items, 128, 0, st>>>(a);
+    k_sort_place<<<grid, 128, 0, st>>>(a);
     OCF_LAUNCHED();
     g_prof.end(3, st);
     return OCF_OK;
   }
   // rows that repeat a column: stream the store's CSC index (order-preserving compaction)
-  if (b->store->dev.n_groups == 0) return OCF_OK;
+  if (b->store->dev.n_groups == 0 || bt.n_entries == 0) return OCF_OK;
   ColArgs a{};
   a.s = b->store->dev; a.bt = bt;
   a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.dense = dense;
@@ -1449,7 +1526,7 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   r.hdec = drop ? m->h[L - 1] : m->act[L - 1]; r.dz0 = m->dz[0]; r.dy = m->dy;
   r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
   r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
-  r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.aux_val = b->aux_value; r.opt = opt;
+  r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.bt_hdr = b->dev.hdr; r.opt = opt;
   r.dense = grad_mode ? 0 : opt.dense; r.n_arr = 0;
   if (grad_mode) { r.Gdec = m->gW[L]; r.Genc = m->gW[0]; r.gbdec = m->gb[L]; }
   if (do_dec) r.arr_map[r.n_arr++] = 0;
@@ -1460,7 +1537,7 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   return OCF_OK;
 }
 
-// Start the column scan of a training step on the side stream, ordered after everything already
+// Start the column grouping of a training step on the side stream, ordered after everything already
 // enqueued on `st` (the batch's gather, the previous step's update which reads the match list).
 static int fork_scan(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
   m->scan_pending = false;
@@ -1468,7 +1545,6 @@ static int fork_scan(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
   if (m->hp[L - 1] != m->hp[0]) return OCF_OK;
   const OptDev opt = make_opt(m);
   const int dense = m->par_mode == OCF_PAR_ROWS ? 0 : opt.dense;   // gradient rows exist for touched columns only
-  if (b->dev.n_entries == 0 && !dense) return OCF_OK;
   const int do_dec = m->layers[L].trainable ? 1 : 0, do_enc = m->layers[0].trainable ? 1 : 0;
   if (!do_dec && !do_enc) return OCF_OK;
   OCF_CUDA(cudaEventRecord(m->ev_fork, st));
@@ -1499,7 +1575,7 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     // the fused step's metric record rides along as one extra CTA (a row-parallel step needs the
     // other ranks' row statistics first and computes it after the gather)
     MetricArgs met{};
-    if (!grad_mode) met = metric_args(m, B, args, n_reg);
+    if (!grad_mode) met = metric_args(m, B, args, n_reg, true);
     k_dz_bias<<<m->hp[l] / 32 + (grad_mode ? 0 : 1), 1024, 0, st>>>(m->dh_top, m->act[l], drop ? m->dscale[l] : nullptr, B, m->hp[l],
                                                      m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt, ly.trainable ? 1 : 0,
                                                      grad_mode ? m->gb[l] : nullptr, met);
@@ -1529,23 +1605,19 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   Layer& dec = m->layers[L];
   const int hpd = m->hp[L - 1], hpe = m->hp[0];
   const int dense = grad_mode ? 0 : opt.dense;
-  if (bt.n_entries > 0 || dense) {
-    // decoder and encoder rows share one padded width in the reference's architectures (one
-    // num_hidden_units): one scan feeds both. A width list with different ends scans twice.
-    if (hpd == hpe) {
-      if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
-      else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, dense, st));
-      OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd, opt, st, grad_mode));
-    } else {
-      OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, 0, dense, st));
-      OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, 0, hpd, opt, st, grad_mode));
-      OCF_TRY(launch_scan(m, b, 0, enc.trainable ? 1 : 0, dense, st));
-      OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st, grad_mode));
-    }
+  // decoder and encoder rows share one padded width in the reference's architectures (one
+  // num_hidden_units): one grouping pass feeds both. A width list with different ends groups twice.
+  if (hpd == hpe) {
+    if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
+    else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, dense, st));
+    OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd, opt, st, grad_mode));
+  } else {
+    OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, 0, dense, st));
+    OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, 0, hpd, opt, st, grad_mode));
+    OCF_TRY(launch_scan(m, b, 0, enc.trainable ? 1 : 0, dense, st));
+    OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st, grad_mode));
   }
-  if (grad_mode) return OCF_OK;
-  m->iterations += 1;
-  return publish_metrics(m, st);
+  return OCF_OK;
 }
 
 extern "C" int ocf_model_wait_metrics(ocf_model* m, int64_t step, float* host) {
@@ -1658,6 +1730,7 @@ extern "C" int ocf_model_set_comm(ocf_model* m, ocf_comm* comm, int mode) {
   OCF_REQUIRE(mode != OCF_PAR_COLUMNS || (comm != nullptr && m->cfg.sharded), "ocf_model_set_comm: column mode needs a communicator and a model created with sharded = 1");
   OCF_REQUIRE(mode != OCF_PAR_ROWS || !m->cfg.sharded, "ocf_model_set_comm: row mode needs an unsharded (replicated) model");
   OCF_CUDA(cudaDeviceSynchronize());
+  drop_graphs(m);
   m->comm = comm; m->par_mode = mode;
   if (mode == OCF_PAR_ROWS && m->grads == nullptr) {
     size_t total = 0;
@@ -1691,7 +1764,7 @@ static int encode_exchange(ocf_model* m, const ocf_batch* b, bool training, cons
   if (use_peer(m, B)) {
     ocf_comm* c = m->comm;
     const uint32_t e = ++c->epoch;
-    OCF_TRY(phase_encode(m, b, st, c->slot(c->rank, e)));
+    OCF_TRY(phase_encode(m, b, st, c->slot(c->rank, e), false, training, args));
     g_prof.begin(6, st);
     peer::k_allreduce_bias_act<<<peer::AR_CTAS, peer::AR_THREADS, 0, st>>>(c->dev(e), reinterpret_cast<float4*>(m->zsum[0]),
                                                                             act_args(m, 0, B, training, args));
@@ -1700,7 +1773,7 @@ static int encode_exchange(ocf_model* m, const ocf_batch* b, bool training, cons
     *act0_done = true;
     return OCF_OK;
   }
-  OCF_TRY(phase_encode(m, b, st));
+  OCF_TRY(phase_encode(m, b, st, nullptr, false, training, args));
   g_prof.begin(6, st);
   OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
   g_prof.end(6, st);
@@ -1761,6 +1834,84 @@ static int gather_stats(ocf_model* m, int B, const ocf_step_args* args, const fl
   return OCF_OK;
 }
 
+// ---- one step = one body of kernel launches; replayed as a CUDA graph once it has been seen twice ----
+// Bodies only enqueue work on `st` (and the side stream forked from it): no allocation, no
+// synchronisation, no host-visible bookkeeping, so that they can run under stream capture.
+static int train_body(ocf_model* m, ocf_batch* b, const ocf_step_args* args, cudaStream_t st) {
+  if (m->par_mode == OCF_PAR_COLUMNS) {
+    // column shards: the three phases back to back with the two activation exchanges between them
+    // (one-shot peer-memory all-reduce kernels fused with the next compute step, or ncclAllReduce)
+    bool act0 = false;
+    OCF_TRY(fork_scan(m, b, st));
+    OCF_TRY(encode_exchange(m, b, true, args, st, &act0));
+    OCF_TRY(decode_exchange(m, b, true, args, st, act0));
+    return phase_update(m, b, args, st);
+  }
+  OCF_TRY(fork_scan(m, b, st));
+  OCF_TRY(phase_encode(m, b, st, nullptr, true, true, args));
+  OCF_TRY(phase_decode(m, b, true, args, nullptr, st, true));
+  return phase_update(m, b, args, st);
+}
+
+static int eval_body(ocf_model* m, ocf_batch* b, const ocf_step_args* args, cudaStream_t st) {
+  if (m->par_mode == OCF_PAR_COLUMNS) {
+    bool act0 = false;
+    OCF_TRY(encode_exchange(m, b, false, args, st, &act0));
+    OCF_TRY(decode_exchange(m, b, false, args, st, act0));
+  } else {
+    OCF_TRY(phase_encode(m, b, st, nullptr, true, false, args));
+    OCF_TRY(phase_decode(m, b, false, args, nullptr, st, true));
+  }
+  const int n_reg = launch_reg(m, st);
+  return launch_metrics(m, b->dev.B, args, n_reg, false, st);
+}
+
+static bool graphs_enabled() {
+  static const bool on = [] { const char* e = std::getenv("OCF_NO_GRAPH"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
+// Runs a whole step (phase 0) of a single-GPU or column-sharded model. The first time a (batch object,
+// rows, kind) combination is seen the body runs as plain launches (lazy allocations happen there), the
+// second time it is captured into a CUDA graph, from then on the graph is replayed: one launch per step,
+// every size and scalar that changes from step to step is read from device memory (BatchHdr, StepDev).
+static int run_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, bool train, cudaStream_t st) {
+  OCF_TRY(sync_step_state(m, args, st));
+  auto body = [&](cudaStream_t s) { return train ? train_body(m, b, args, s) : eval_body(m, b, args, s); };
+  const bool peer = m->par_mode == OCF_PAR_COLUMNS && use_peer(m, b->dev.B);     // exchange epochs are launch arguments
+  bool done = false;
+  if (graphs_enabled() && !g_prof.on && !b->store->has_dups && !peer) {
+    const auto key = std::make_tuple(b->uid, b->dev.B, train ? 1 : 0, args ? args->rows_total : 0, args ? args->row0 : 0);
+    ocf_model::StepGraph& g = m->graphs[key];
+    if (g.exec == nullptr && !g.failed && g.seen++ >= 1) {
+      const long long launched = g_launches.load();
+      m->capturing = true;
+      cudaGraph_t graph = nullptr;
+      int rc = OCF_OK;
+      if (cudaStreamBeginCapture(m->cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); rc = OCF_ERR_CUDA; }
+      else {
+        rc = body(m->cap);
+        if (cudaStreamEndCapture(m->cap, &graph) != cudaSuccess) { cudaGetLastError(); rc = OCF_ERR_CUDA; graph = nullptr; }
+      }
+      m->capturing = false;
+      m->scan_pending = false;
+      g.kernels = (int)(g_launches.load() - launched);
+      g_launches.store(launched);
+      if (rc == OCF_OK && graph != nullptr && cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; }
+      if (graph) cudaGraphDestroy(graph);
+      if (g.exec == nullptr) g.failed = true;          // this combination keeps running as plain launches
+    }
+    if (g.exec != nullptr) {
+      OCF_CUDA(cudaGraphLaunch(g.exec, st));
+      g_launches.fetch_add(g.kernels, std::memory_order_relaxed);
+      done = true;
+    }
+  }
+  if (!done) OCF_TRY(body(st));
+  if (train) m->iterations += 1;
+  return publish_metrics(m, train, st);
+}
+
 extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
   OCF_TRY(check_step(m, b, true));
   cudaStream_t st = as_stream(stream_);
@@ -1768,9 +1919,10 @@ extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* a
   OCF_REQUIRE(phase >= 0 && phase <= 3, "ocf_train_step: phase must be 0..3");
   if (phase == 0 && m->par_mode == OCF_PAR_ROWS) {
     // data parallel over rows: replicated weights, this rank's rows, gradients summed over ranks
+    OCF_TRY(sync_step_state(m, args, st));
     OCF_TRY(fork_scan(m, b, st));
-    OCF_TRY(phase_encode(m, b, st));
-    OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
+    OCF_TRY(phase_encode(m, b, st, nullptr, true, true, args));
+    OCF_TRY(phase_decode(m, b, true, args, nullptr, st, true));
     int n_reg = 0;
     OCF_TRY(phase_update(m, b, args, st, true, &n_reg));
     if (m->comm && m->comm->world > 1) {
@@ -1781,22 +1933,24 @@ extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* a
     const float* stats; int rows;
     OCF_TRY(gather_stats(m, b->dev.B, args, &stats, &rows, st));
     OCF_TRY(apply_gradients(m, st));
-    OCF_TRY(launch_metrics(m, rows, args, n_reg, st, stats));
+    OCF_TRY(launch_metrics(m, rows, args, n_reg, true, st, stats));
+    OCF_TRY(publish_metrics(m, true, st));
     return finish_step(m, host_metrics, st);
   }
-  if (phase == 0 && m->par_mode == OCF_PAR_COLUMNS) {
-    // column shards: the three phases back to back with the two activation exchanges between them
-    // (one-shot peer-memory all-reduce kernels fused with the next compute step, or ncclAllReduce)
-    bool act0 = false;
-    OCF_TRY(fork_scan(m, b, st));
-    OCF_TRY(encode_exchange(m, b, true, args, st, &act0));
-    OCF_TRY(decode_exchange(m, b, true, args, st, act0));
+  if (phase == 0) {
+    OCF_TRY(run_step(m, b, args, true, st));
+    return finish_step(m, host_metrics, st);
+  }
+  // a step driven phase by phase (a caller that runs the shard exchanges itself between the phases)
+  OCF_TRY(sync_step_state(m, args, st));
+  if (phase == 1) { OCF_TRY(fork_scan(m, b, st)); OCF_TRY(phase_encode(m, b, st, nullptr, false, true, args)); }
+  if (phase == 2) OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
+  if (phase == 3) {
     OCF_TRY(phase_update(m, b, args, st));
-    return finish_step(m, host_metrics, st);
+    m->iterations += 1;
+    OCF_TRY(publish_metrics(m, true, st));
+    OCF_TRY(finish_step(m, host_metrics, st));
   }
-  if (phase == 0 || phase == 1) { OCF_TRY(fork_scan(m, b, st)); OCF_TRY(phase_encode(m, b, st)); }
-  if (phase == 0 || phase == 2) OCF_TRY(phase_decode(m, b, true, args, nullptr, st));
-  if (phase == 0 || phase == 3) { OCF_TRY(phase_update(m, b, args, st)); OCF_TRY(finish_step(m, host_metrics, st)); }
   return OCF_OK;
 }
 
@@ -1806,27 +1960,27 @@ extern "C" int ocf_eval_step(ocf_model* m, ocf_batch* b, const ocf_step_args* ar
   const int phase = args ? args->phase : 0;
   OCF_REQUIRE(phase >= 0 && phase <= 3, "ocf_eval_step: phase must be 0..3");
   if (phase == 0 && m->par_mode == OCF_PAR_ROWS) {
-    OCF_TRY(phase_encode(m, b, st));
-    OCF_TRY(phase_decode(m, b, false, args, nullptr, st));
+    OCF_TRY(sync_step_state(m, args, st));
+    OCF_TRY(phase_encode(m, b, st, nullptr, true, false, args));
+    OCF_TRY(phase_decode(m, b, false, args, nullptr, st, true));
     const float* stats; int rows;
     OCF_TRY(gather_stats(m, b->dev.B, args, &stats, &rows, st));
     const int n_reg = launch_reg(m, st);
-    OCF_TRY(launch_metrics(m, rows, args, n_reg, st, stats));
+    OCF_TRY(launch_metrics(m, rows, args, n_reg, false, st, stats));
+    OCF_TRY(publish_metrics(m, false, st));
     return finish_step(m, host_metrics, st);
   }
-  if (phase == 0 && m->par_mode == OCF_PAR_COLUMNS) {
-    bool act0 = false;
-    OCF_TRY(encode_exchange(m, b, false, args, st, &act0));
-    OCF_TRY(decode_exchange(m, b, false, args, st, act0));
-    const int n_reg = launch_reg(m, st);
-    OCF_TRY(launch_metrics(m, b->dev.B, args, n_reg, st));
+  if (phase == 0) {
+    OCF_TRY(run_step(m, b, args, false, st));
     return finish_step(m, host_metrics, st);
   }
-  if (phase == 0 || phase == 1) OCF_TRY(phase_encode(m, b, st));
-  if (phase == 0 || phase == 2) OCF_TRY(phase_decode(m, b, false, args, nullptr, st));
-  if (phase == 0 || phase == 3) {
+  OCF_TRY(sync_step_state(m, args, st));
+  if (phase == 1) OCF_TRY(phase_encode(m, b, st, nullptr, false, false, args));
+  if (phase == 2) OCF_TRY(phase_decode(m, b, false, args, nullptr, st));
+  if (phase == 3) {
     const int n_reg = launch_reg(m, st);
-    OCF_TRY(launch_metrics(m, b->dev.B, args, n_reg, st));
+    OCF_TRY(launch_metrics(m, b->dev.B, args, n_reg, false, st));
+    OCF_TRY(publish_metrics(m, false, st));
     OCF_TRY(finish_step(m, host_metrics, st));
   }
   return OCF_OK;
@@ -1836,7 +1990,8 @@ extern "C" int ocf_eval_step(ocf_model* m, ocf_batch* b, const ocf_step_args* ar
 // here; without one its caller has already run phase 1 and the z all-reduce.
 static int encode_for_output(ocf_model* m, const ocf_batch* b, cudaStream_t st, bool* act0_done) {
   *act0_done = false;
-  if (!m->cfg.sharded) return phase_encode(m, b, st);
+  OCF_TRY(sync_step_state(m, nullptr, st));
+  if (!m->cfg.sharded) { *act0_done = true; return phase_encode(m, b, st, nullptr, true, false, nullptr); }
   if (m->par_mode == OCF_PAR_COLUMNS) return encode_exchange(m, b, false, nullptr, st, act0_done);
   return OCF_OK;
 }

@@ -71,9 +71,40 @@ struct StoreDev {
   int scan_t;                //   4096, 8192 or 16384: picked so that a scan is about one group per resident CTA
 };
 
+// What changes from one fill of a batch object to the next, as the device sees it: the first bytes of
+// the batch's staging buffer, uploaded with the row ids. Kernels of a captured step (CUDA graph) read
+// their sizes here, so a replayed graph needs no per-step parameter update; every pointer in BatchDev
+// is fixed for the life of the batch object.
+struct BatchHdr {
+  int B;
+  int n_items;
+  int n_entries;
+  uint32_t tag;              // rowslot tag of this fill
+  int cdf_row0;              // device-RNG mode: index of batch row 0 among the drawing unit's sparsity draws
+  int pass_through;
+  double rng_lo, rng_range;  // np.random.uniform(lo, hi) of the rows' sparsity draws (range = hi - lo)
+  float aux_value;
+  int pad[5];
+};
+static_assert(sizeof(BatchHdr) == 64, "BatchHdr is one 64-byte block at the head of the staging buffer");
+
+// Per-step scalars of a model, resident in device memory so that a captured step replays unchanged:
+// the dropout counter, the slot of the metric log the step writes, the step's learning rate (decay /
+// Adam bias correction folded in). The step's last kernel advances step and log_slot; the host keeps a
+// mirror and rewrites the struct (k_set_step) only when a caller's arguments differ from it.
+struct StepDev {
+  uint32_t step;
+  int32_t log_slot;
+  float lr;
+  uint32_t seed_lo, seed_hi;
+  int32_t pad[3];
+};
+
 // Device view of one batch. The first group is uploaded by the host in one copy, the second
-// is written by K1.
+// is written by K1. B / n_items / n_entries are the host's copy of the current fill (for host logic
+// and for kernels launched outside captured steps); captured kernels use hdr.
 struct BatchDev {
+  const BatchHdr* hdr;
   int B;
   int n_items;
   int n_entries;
@@ -97,7 +128,7 @@ struct BatchDev {
 
 struct OptDev {
   int kind;          // ocf_optimizer
-  float lr;          // learning rate of this step (decay and Adam bias correction folded in)
+  float lr;          // host's copy of this step's learning rate; kernels use st->lr (passed to opt_apply as `lr`)
   float p1;          // rho / beta_1
   float one_m_p1;    // 1 - rho / 1 - beta_1 (computed in double on the host, like Keras)
   float p2;          // beta_2
@@ -105,6 +136,7 @@ struct OptDev {
   float eps;
   float l2x2;        // 2 * lambda, 0 without regularisation
   int dense;         // 1: every parameter changes every step (RMSprop, Adam, L2)
+  const StepDev* st; // kernels take this step's lr from st->lr (the value above is the host's copy)
 };
 
 // sqrt / divide of the update rules use the MUFU approximations (<= 2 ulp): the IEEE-rounded
@@ -116,29 +148,29 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 }
 
 template <int KIND>
-__device__ __forceinline__ void opt_apply_k(const OptDev& o, float g, float& w, float& s1, float& s2) {
+__device__ __forceinline__ void opt_apply_k(const OptDev& o, const float lr, float g, float& w, float& s1, float& s2) {
   g = fmaf(o.l2x2, w, g);
   if (KIND == OCF_OPT_SGD) {
-    w = fmaf(-o.lr, g, w);
+    w = fmaf(-lr, g, w);
   } else if (KIND == OCF_OPT_ADAGRAD) {
     s1 = fmaf(g, g, s1);
-    w -= __fdividef(o.lr * g, fast_sqrt(s1) + o.eps);
+    w -= __fdividef(lr * g, fast_sqrt(s1) + o.eps);
   } else if (KIND == OCF_OPT_RMSPROP) {
     s1 = fmaf(o.one_m_p1 * g, g, o.p1 * s1);
-    w -= __fdividef(o.lr * g, fast_sqrt(s1) + o.eps);
+    w -= __fdividef(lr * g, fast_sqrt(s1) + o.eps);
   } else {  // Adam
     s1 = fmaf(o.one_m_p1, g, o.p1 * s1);
     s2 = fmaf(o.one_m_p2 * g, g, o.p2 * s2);
-    w -= __fdividef(o.lr * s1, fast_sqrt(s2) + o.eps);
+    w -= __fdividef(lr * s1, fast_sqrt(s2) + o.eps);
   }
 }
 
-__device__ __forceinline__ void opt_apply(const OptDev& o, float g, float& w, float& s1, float& s2) {
+__device__ __forceinline__ void opt_apply(const OptDev& o, const float lr, float g, float& w, float& s1, float& s2) {
   switch (o.kind) {
-    case OCF_OPT_SGD: opt_apply_k<OCF_OPT_SGD>(o, g, w, s1, s2); break;
-    case OCF_OPT_ADAGRAD: opt_apply_k<OCF_OPT_ADAGRAD>(o, g, w, s1, s2); break;
-    case OCF_OPT_RMSPROP: opt_apply_k<OCF_OPT_RMSPROP>(o, g, w, s1, s2); break;
-    default: opt_apply_k<OCF_OPT_ADAM>(o, g, w, s1, s2); break;
+    case OCF_OPT_SGD: opt_apply_k<OCF_OPT_SGD>(o, lr, g, w, s1, s2); break;
+    case OCF_OPT_ADAGRAD: opt_apply_k<OCF_OPT_ADAGRAD>(o, lr, g, w, s1, s2); break;
+    case OCF_OPT_RMSPROP: opt_apply_k<OCF_OPT_RMSPROP>(o, lr, g, w, s1, s2); break;
+    default: opt_apply_k<OCF_OPT_ADAM>(o, lr, g, w, s1, s2); break;
   }
 }
 

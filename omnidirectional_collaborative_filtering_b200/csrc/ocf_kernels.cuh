@@ -34,13 +34,16 @@ constexpr unsigned FULL = 0xffffffffu;
 // The flags are also written back so a caller can read them.
 template <bool RNG>
 __global__ void __launch_bounds__(128)
-k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
+k_gather_split(StoreDev s, BatchDev bt) {
+  const BatchHdr hd = *bt.hdr;
+  if ((int)blockIdx.x >= hd.n_items) return;
+  const int pass_through = hd.pass_through;
   const int4 it = bt.items[blockIdx.x];
   const int b = it.x, start = it.y, len = it.z;
   const int row = bt.row_ids[b];
   const int64_t src0 = s.rowptr[row];
   const int p0 = bt.ent_off[b];
-  if (start == 0 && threadIdx.x == 0) bt.rowslot[row] = (bt.tag << SLOT_BITS) | (uint32_t)b;
+  if (start == 0 && threadIdx.x == 0 && bt.rowslot != nullptr) bt.rowslot[row] = (hd.tag << SLOT_BITS) | (uint32_t)b;
   const int d0 = RNG ? bt.draw_off[b] : 0;
   // the batch's slice of the stream: 4 header words (word 0 = alignment shift), then the draws
   const uint32_t* W = RNG ? bt.words + 4 + bt.words[0] : nullptr;
@@ -49,9 +52,9 @@ k_gather_split(StoreDev s, BatchDev bt, int pass_through) {
     if (threadIdx.x == 0) {
       // the row's sparsity: draw (first row of the drawing unit + b) of np.random.uniform(lo, hi, size)
       // (data_reader.py:120), then the cdf np.random.choice builds from p = [1-s, s] (:130)
-      const int r = bt.cdf_row0 + b;
+      const int r = hd.cdf_row0 + b;
       const double u = mt_double(W[2 * r], W[2 * r + 1]);
-      const double keep = __dadd_rn(bt.rng_lo, __dmul_rn(bt.rng_range, u));   // random_uniform: lower + range * next_double
+      const double keep = __dadd_rn(hd.rng_lo, __dmul_rn(hd.rng_range, u));   // random_uniform: lower + range * next_double
       const double q0 = __dsub_rn(1.0, keep);
       s_c0 = __ddiv_rn(q0, __dadd_rn(q0, keep));                             // cdf = cumsum(p) / cumsum(p)[-1]
     }
@@ -222,6 +225,7 @@ k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict
 // (the missing-data mask is then carried by the target entry only).
 __global__ void __launch_bounds__(128)
 k_gather_fixed(StoreDev sin, StoreDev stg, const uint8_t* __restrict__ in_overlap, BatchDev bt) {
+  if ((int)blockIdx.x >= bt.hdr->n_items) return;
   const int4 it = bt.items[blockIdx.x];
   const int b = it.x, start = it.y, len = it.z;
   const int row = bt.row_ids[b];
@@ -270,18 +274,169 @@ __global__ void k_densify(BatchDev bt, int which, double aux_val, int n_cols, do
 }
 
 // ============================================================================================
+// z + bias -> activation -> inverted dropout (model.py:66-73). Padded units are forced to 0.
+// a_out: activation before dropout (needed for the derivative), h_out: what the next layer sees,
+// dscale: 0 or 1/(1-p) per element (null when dropout is off). The dropout counter (step) and key
+// come from the model's device-resident StepDev.
+// ============================================================================================
+struct ActArgs {
+  const float4* bias; int B; int H; int hp4; int act;
+  float4* a_out; float4* h_out; float4* dscale;
+  float p_drop; const StepDev* st; uint32_t layer; int row0;
+};
+
+__device__ __forceinline__ void bias_act_elem(const ActArgs& g, int idx, const float4 z) {
+  const int b = idx / g.hp4, u4 = idx - b * g.hp4;
+  const float4 bb = g.bias[u4];
+  float a[4] = {z.x + bb.x, z.y + bb.y, z.z + bb.z, z.w + bb.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = (u4 * 4 + k < g.H) ? act_fwd(g.act, a[k]) : 0.f;
+  g.a_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
+  if (g.dscale != nullptr) {
+    const uint32_t step = g.st->step;
+    const uint2 key = make_uint2(g.st->seed_lo, g.st->seed_hi);
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)u4, (uint32_t)(b + g.row0), g.layer, step), key);
+    const uint32_t thresh = (uint32_t)floor((double)g.p_drop * 16777216.0);
+    const float inv = 1.0f / (1.0f - g.p_drop);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    float sc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sc[k] = ((rr[k] >> 8) >= thresh) ? inv : 0.f; a[k] *= sc[k]; }
+    g.dscale[idx] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+  }
+  g.h_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+__global__ void __launch_bounds__(256)
+k_bias_act(const float4* __restrict__ zsum, ActArgs g) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.B * g.hp4) return;
+  bias_act_elem(g, idx, zsum[idx]);
+}
+
+// ============================================================================================
+// Row tail of the row-centric kernels (K2, K3). A batch row's ratings are spread over work items
+// (one CTA each); the row's result is the sum of its items' partial rows. Instead of a separate
+// reduction kernel, the CTAs of a row count their arrivals and the LAST one to arrive sums the
+// partials - always in item order, so the result does not depend on which CTA that is. Rows with
+// more than TAIL_FAN items reduce in two levels (groups of TAIL_FAN consecutive items, then the
+// groups), which bounds the serial part of a heavy row (hundreds of items) to two short sums.
+// Counters reset themselves; every batch row has at least one item (an empty row has one item of
+// length 0), so every row gets its tail.
+// ============================================================================================
+constexpr int TAIL_FAN = 16;
+
+struct TailBuf {
+  int* tick_grp;      // [max_items] arrivals of a group, indexed by the group's first item
+  int* tick_row;      // [max_rows]  arrivals of a row's groups
+  float4* G;          // [max_items, hp4] group sums, indexed by the group's first item
+  float* Gs;          // [max_items, ROWSTAT_W] group sums of the loss statistics
+};
+
+// sum of `count` partial rows P[(first + k * step) * hp4 + u], k = 0..count-1, fixed order, 4 accumulators
+__device__ __forceinline__ float4 tail_sum4(const float4* P, int first, int step, int count, int hp4, int u) {
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  int k = 0;
+  for (; k + 8 <= count; k += 8) {
+    float4 p[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) p[q] = __ldcg(P + (size_t)(first + (k + q) * step) * hp4 + u);
+#pragma unroll
+    for (int q = 0; q < 8; q += 4) {
+      a0.x += p[q].x; a0.y += p[q].y; a0.z += p[q].z; a0.w += p[q].w;
+      a1.x += p[q + 1].x; a1.y += p[q + 1].y; a1.z += p[q + 1].z; a1.w += p[q + 1].w;
+      a2.x += p[q + 2].x; a2.y += p[q + 2].y; a2.z += p[q + 2].z; a2.w += p[q + 2].w;
+      a3.x += p[q + 3].x; a3.y += p[q + 3].y; a3.z += p[q + 3].z; a3.w += p[q + 3].w;
+    }
+  }
+  for (; k < count; ++k) {
+    const float4 p = __ldcg(P + (size_t)(first + k * step) * hp4 + u);
+    float4& a = (k & 3) == 0 ? a0 : ((k & 3) == 1 ? a1 : ((k & 3) == 2 ? a2 : a3));
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+  }
+  return make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                     (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+}
+
+// Runs at the end of a row-centric CTA (all threads, after the CTA's own partial row / statistics are
+// in global memory). `finish(u, sum)` receives the row's summed float4 column u (u < hp4; hp4 = 0: no
+// row data), `finish_stat(k, sum)` the row's summed statistic k when `stats` is given.
+template <typename F, typename FS>
+__device__ __forceinline__ void row_tail(const BatchDev& bt, int item, int b, const float4* P, int hp4,
+                                         const float* stats, const TailBuf& tb, F&& finish, FS&& finish_stat) {
+  __shared__ int s_last;
+  const int i0 = bt.item_ptr[b], i1 = bt.item_ptr[b + 1];
+  const int n = i1 - i0;
+  const int nthreads = blockDim.x;
+  if (n == 1) {                                   // the CTA's own partial is the row (bar.sync orders the CTA's global writes)
+    __syncthreads();
+    for (int u = threadIdx.x; u < hp4; u += nthreads) finish(u, P[(size_t)item * hp4 + u]);
+    if (stats != nullptr && threadIdx.x < ROWSTAT_W) finish_stat((int)threadIdx.x, stats[(size_t)item * ROWSTAT_W + threadIdx.x]);
+    return;
+  }
+  const int g_first = i0 + (item - i0) / TAIL_FAN * TAIL_FAN;
+  const int g_count = min(TAIL_FAN, i1 - g_first);
+  const int n_groups = (n + TAIL_FAN - 1) / TAIL_FAN;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&tb.tick_grp[g_first], 1);
+    s_last = t == g_count - 1;
+    if (s_last) tb.tick_grp[g_first] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (n_groups == 1) {
+    for (int u = threadIdx.x; u < hp4; u += nthreads) finish(u, tail_sum4(P, g_first, 1, g_count, hp4, u));
+    if (stats != nullptr && threadIdx.x < ROWSTAT_W) {
+      float s = 0.f;
+      for (int k = 0; k < g_count; ++k) s += __ldcg(stats + (size_t)(g_first + k) * ROWSTAT_W + threadIdx.x);
+      finish_stat((int)threadIdx.x, s);
+    }
+    return;
+  }
+  for (int u = threadIdx.x; u < hp4; u += nthreads) tb.G[(size_t)g_first * hp4 + u] = tail_sum4(P, g_first, 1, g_count, hp4, u);
+  if (stats != nullptr && threadIdx.x < ROWSTAT_W) {
+    float s = 0.f;
+    for (int k = 0; k < g_count; ++k) s += __ldcg(stats + (size_t)(g_first + k) * ROWSTAT_W + threadIdx.x);
+    tb.Gs[(size_t)g_first * ROWSTAT_W + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&tb.tick_row[b], 1);
+    s_last = t == n_groups - 1;
+    if (s_last) tb.tick_row[b] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int u = threadIdx.x; u < hp4; u += nthreads) finish(u, tail_sum4(tb.G, i0, TAIL_FAN, n_groups, hp4, u));
+  if (stats != nullptr && threadIdx.x < ROWSTAT_W) {
+    float s = 0.f;
+    for (int k = 0; k < n_groups; ++k) s += __ldcg(tb.Gs + (size_t)(i0 + k * TAIL_FAN) * ROWSTAT_W + threadIdx.x);
+    finish_stat((int)threadIdx.x, s);
+  }
+}
+
+// ============================================================================================
 // K2: encoder, sparse-row x dense Wenc (SpMM). Work item = chunk of one batch row; the 4 warps of
 // the CTA split the chunk's ratings, each warp accumulates full HP-wide rows (NV float4 per
 // lane, 512-byte coalesced segments), then the warps are summed in a fixed order.
 // x0 = [data | aux | second] (model.py:47-56) is never formed: block k of the concatenation is
 // rows [k*N, (k+1)*N) of Wenc, selected by the entry's code bits.
+// The row's last CTA (row_tail) sums the row and either stores the pre-activation z (a column shard
+// all-reduces it first) or applies bias + activation + dropout right there (fuse_act).
 // ============================================================================================
 template <int NV>
 __global__ void __launch_bounds__(128)
 k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int3 bits,
-          float aux_val, float4* __restrict__ P) {
+          float4* __restrict__ P, TailBuf tb, float4* __restrict__ z_out, int fuse_act, ActArgs act) {
   constexpr int HP = NV * 128;
   __shared__ float4 red[4][HP / 4];
+  if ((int)blockIdx.x >= bt.hdr->n_items) return;
+  const float aux_val = bt.hdr->aux_value;
   const int4 it = bt.items[blockIdx.x];
   const int len = it.z;
   const int p0 = bt.ent_off[it.x] + it.y;
@@ -326,86 +481,13 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
     s.z = ((s.z + a.z) + b2.z) + c2.z; s.w = ((s.w + a.w) + b2.w) + c2.w;
     P[(size_t)blockIdx.x * (HP / 4) + u] = s;
   }
-}
-
-// Sum of the work-item partials of each batch row in a fixed order: the row's items are dealt
-// round-robin to 4 thread groups, the 4 group sums are added in group order. Also sums the
-// per-item loss statistics into per-row statistics when given. blockDim = 4 * hp4.
-__global__ void __launch_bounds__(1024)
-k_rowsum(const float4* __restrict__ P, const int32_t* __restrict__ item_ptr, int hp4,
-         float4* __restrict__ out, const float* __restrict__ itemstats, float* __restrict__ rowstats) {
-  extern __shared__ float4 rs_smem[];      // [4][hp4]
-  const int b = blockIdx.x;
-  const int i0 = item_ptr[b], i1 = item_ptr[b + 1];
-  if (hp4 > 0) {
-    const int q = threadIdx.x / hp4, u = threadIdx.x - q * hp4;
-    // a heavy row has hundreds of items: four loads in flight per thread, summed in a fixed order
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s, s2 = s, s3 = s;
-    int it = i0 + q;
-    for (; it + 12 < i1; it += 16) {
-      const float4 p0 = P[(size_t)it * hp4 + u], p1 = P[(size_t)(it + 4) * hp4 + u];
-      const float4 p2 = P[(size_t)(it + 8) * hp4 + u], p3 = P[(size_t)(it + 12) * hp4 + u];
-      s.x += p0.x; s.y += p0.y; s.z += p0.z; s.w += p0.w;
-      s1.x += p1.x; s1.y += p1.y; s1.z += p1.z; s1.w += p1.w;
-      s2.x += p2.x; s2.y += p2.y; s2.z += p2.z; s2.w += p2.w;
-      s3.x += p3.x; s3.y += p3.y; s3.z += p3.z; s3.w += p3.w;
-    }
-    for (; it < i1; it += 4) {
-      const float4 p = P[(size_t)it * hp4 + u];
-      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
-    }
-    s.x = (s.x + s1.x) + (s2.x + s3.x); s.y = (s.y + s1.y) + (s2.y + s3.y);
-    s.z = (s.z + s1.z) + (s2.z + s3.z); s.w = (s.w + s1.w) + (s2.w + s3.w);
-    rs_smem[q * hp4 + u] = s;
-    __syncthreads();
-    if (q == 0) {
-      const float4 a = rs_smem[hp4 + u], b2 = rs_smem[2 * hp4 + u], c2 = rs_smem[3 * hp4 + u];
-      s.x = ((s.x + a.x) + b2.x) + c2.x; s.y = ((s.y + a.y) + b2.y) + c2.y;
-      s.z = ((s.z + a.z) + b2.z) + c2.z; s.w = ((s.w + a.w) + b2.w) + c2.w;
-      out[(size_t)b * hp4 + u] = s;
-    }
-  }
-  if (itemstats != nullptr && threadIdx.x < ROWSTAT_W) {
-    float s = 0.f;
-    for (int it = i0; it < i1; ++it) s += itemstats[(size_t)it * ROWSTAT_W + threadIdx.x];
-    rowstats[(size_t)b * ROWSTAT_W + threadIdx.x] = s;
-  }
-}
-
-// z + bias -> activation -> inverted dropout (model.py:66-73). Padded units are forced to 0.
-// a_out: activation before dropout (needed for the derivative), h_out: what the next layer sees,
-// dscale: 0 or 1/(1-p) per element (null when dropout is off).
-struct ActArgs {
-  const float4* bias; int B; int H; int hp4; int act;
-  float4* a_out; float4* h_out; float4* dscale;
-  float p_drop; uint2 key; uint32_t step; uint32_t layer; int row0;
-};
-
-__device__ __forceinline__ void bias_act_elem(const ActArgs& g, int idx, const float4 z) {
-  const int b = idx / g.hp4, u4 = idx - b * g.hp4;
-  const float4 bb = g.bias[u4];
-  float a[4] = {z.x + bb.x, z.y + bb.y, z.z + bb.z, z.w + bb.w};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) a[k] = (u4 * 4 + k < g.H) ? act_fwd(g.act, a[k]) : 0.f;
-  g.a_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
-  if (g.dscale != nullptr) {
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)u4, (uint32_t)(b + g.row0), g.layer, g.step), g.key);
-    const uint32_t thresh = (uint32_t)floor((double)g.p_drop * 16777216.0);
-    const float inv = 1.0f / (1.0f - g.p_drop);
-    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-    float sc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { sc[k] = ((rr[k] >> 8) >= thresh) ? inv : 0.f; a[k] *= sc[k]; }
-    g.dscale[idx] = make_float4(sc[0], sc[1], sc[2], sc[3]);
-  }
-  g.h_out[idx] = make_float4(a[0], a[1], a[2], a[3]);
-}
-
-__global__ void __launch_bounds__(256)
-k_bias_act(const float4* __restrict__ zsum, ActArgs g) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= g.B * g.hp4) return;
-  bias_act_elem(g, idx, zsum[idx]);
+  const int b = it.x;
+  row_tail(bt, (int)blockIdx.x, b, P, HP / 4, nullptr, tb,
+           [&](int u, const float4 z) {
+             const int idx = b * (HP / 4) + u;
+             if (fuse_act) bias_act_elem(act, idx, z); else z_out[idx] = z;
+           },
+           [&](int, float) {});
 }
 
 // ============================================================================================
@@ -414,16 +496,20 @@ k_bias_act(const float4* __restrict__ zsum, ActArgs g) {
 // reconstruction (model.py:82-86) is never formed.
 //   full = h . WdecT[c] + b[c];  y = m * full (m = aux_var_value);  e = y - t
 //   dL/dfull = m * 2e/(B N)   (mean_squared_error)   or   m * sign(e)/(B N)   (mean_absolute_error)
+// The row's last CTA (row_tail) leaves the row's loss statistics in rowstats[b] and, when training,
+// dL/dh of the row in dh_out[b].
 // ============================================================================================
 template <int NV, bool TRAIN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, NV <= 4 ? 5 : 3)
 k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict__ bdec,
-          const float* __restrict__ h, float aux_val, float gscale, int loss_kind,
+          const float* __restrict__ h, float gscale, int loss_kind,
           float* __restrict__ dy, float4* __restrict__ P2, float* __restrict__ itemstats,
-          float* __restrict__ dense_out, int n_cols) {
+          float* __restrict__ dense_out, int n_cols, TailBuf tb, float4* __restrict__ dh_out, float* __restrict__ rowstats) {
   constexpr int HP = NV * 128;
   __shared__ float4 red[TRAIN ? 4 : 1][HP / 4];
   __shared__ float sred[4][3];
+  if ((int)blockIdx.x >= bt.hdr->n_items) return;
+  const float aux_val = bt.hdr->aux_value;
   const int4 it = bt.items[blockIdx.x];
   const int b = it.x, len = it.z;
   const int p0 = bt.ent_off[b] + it.y;
@@ -503,6 +589,9 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
     itemstats[(size_t)blockIdx.x * ROWSTAT_W + threadIdx.x] =
         ((sred[0][threadIdx.x] + sred[1][threadIdx.x]) + sred[2][threadIdx.x]) + sred[3][threadIdx.x];
   if (threadIdx.x == 3) itemstats[(size_t)blockIdx.x * ROWSTAT_W + 3] = 0.f;
+  row_tail(bt, (int)blockIdx.x, b, P2, TRAIN ? HP / 4 : 0, itemstats, tb,
+           [&](int u, const float4 s) { dh_out[(size_t)b * (HP / 4) + u] = s; },
+           [&](int k, float s) { rowstats[(size_t)b * ROWSTAT_W + k] = s; });
 }
 
 // dz = dh * dropout scale * act'(a) for one hidden layer, the bias gradient (column sum over the
@@ -511,9 +600,15 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
 // CTA more than there are unit groups: it writes the step's metric record (saves a launch on the
 // critical path of a training step).
 // dh_is_dz: the input already is dz (produced by the EPI_DZ GEMM epilogue).
-struct MetricArgs {            // the step's metric record, written by one extra CTA of k_dz_bias (null rec: none)
+constexpr int LOG_CAP = 4096;             // steps the metric log holds
+constexpr int LOG_W = OCF_N_METRICS;
+
+struct MetricArgs {            // the step's metric record, written by one extra CTA of k_dz_bias (null log: none)
   const float* rowstats; int rows; float rows_total; float n_cols_total; float rating_range; int loss_kind;
-  const float* regparts; int n_reg; float l2; float* rec;
+  const float* regparts; int n_reg; float l2;
+  float* log;                  // [LOG_CAP, LOG_W] page-locked host memory, written straight from the kernel
+  StepDev* st;                 // the record goes to slot st->log_slot, which then advances
+  int advance_step;            // training: the dropout counter advances too
 };
 __device__ void metrics_record(const MetricArgs& a, int lane);
 
@@ -525,7 +620,7 @@ k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float
   __shared__ float part[32][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x * 32 >= HP) {           // the extra CTA: metrics of the step (train.py:102-121)
-    if (warp == 0 && met.rec != nullptr) metrics_record(met, lane);
+    if (warp == 0 && met.log != nullptr) metrics_record(met, lane);
     return;
   }
   const int u = blockIdx.x * 32 + lane;
@@ -551,7 +646,7 @@ k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float
     if (gbias != nullptr) { gbias[u] = g; return; }   // row-parallel mode: the gradient is reduced over ranks first
     o.l2x2 = 0.f;                     // Keras regularises kernels only (model.py:66,82)
     float w = bias[u], t1 = s1 ? s1[u] : 0.f, t2 = s2 ? s2[u] : 0.f;
-    opt_apply(o, g, w, t1, t2);
+    opt_apply(o, o.st->lr, g, w, t1, t2);
     bias[u] = w;
     if (s1) s1[u] = t1;
     if (s2) s2[u] = t2;
@@ -563,7 +658,7 @@ k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float
 //   C[M,N] = A'[M,K] * B'[K,N],  A'(m,k) = TA ? A[k*lda+m] : A[m*lda+k],
 //                                B'(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
 // ============================================================================================
-enum { EPI_STORE = 0, EPI_DZ = 1, EPI_UPDATE = 2, EPI_BIAS_COL = 3 };
+enum { EPI_STORE = 0, EPI_DZ = 1, EPI_UPDATE = 2, EPI_BIAS_COL = 3, EPI_BIAS_ACT = 4 };
 
 struct GemmEpi {
   int kind;
@@ -574,7 +669,35 @@ struct GemmEpi {
   float* s1; float* s2;  // EPI_UPDATE: optimizer state, same layout as C (C = the weight)
   int act;
   OptDev opt;
+  ActArgs actargs;     // EPI_BIAS_ACT: bias + activation + dropout of a hidden layer's forward product (N = its padded width)
 };
+
+// One output element group (4 consecutive columns of one row) through the GEMM's epilogue.
+__device__ __forceinline__ void gemm_epilogue4(const GemmEpi& ep, const float lr, int gm, int gn, int ncols, const float v[4]) {
+  if (ep.kind == EPI_BIAS_ACT) {            // ncols == 4 always: the width is padded to 128
+    bias_act_elem(ep.actargs, gm * ep.actargs.hp4 + (gn >> 2), make_float4(v[0], v[1], v[2], v[3]));
+    return;
+  }
+  for (int j = 0; j < ncols; ++j) {
+    const size_t k = (size_t)gm * ep.ldc + gn + j;
+    float x = v[j];
+    switch (ep.kind) {
+      case EPI_STORE: ep.C[k] = x; break;
+      case EPI_DZ:
+        if (ep.aux1 != nullptr) x *= ep.aux1[k];
+        ep.C[k] = x * act_bwd(ep.act, ep.aux0[k]);
+        break;
+      case EPI_UPDATE: {
+        float w = ep.C[k], t1 = ep.s1 ? ep.s1[k] : 0.f, t2 = ep.s2 ? ep.s2[k] : 0.f;
+        opt_apply(ep.opt, lr, x, w, t1, t2);
+        ep.C[k] = w;
+        if (ep.s1) ep.s1[k] = t1;
+        if (ep.s2) ep.s2[k] = t2;
+      } break;
+      default: ep.C[k] = x + ep.aux0[gn + j]; break;
+    }
+  }
+}
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
@@ -624,60 +747,39 @@ k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int 
     }
     __syncthreads();
   }
+  const float lr = ep.kind == EPI_UPDATE ? ep.opt.st->lr : 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int gm = m0 + ty * 4 + i;
     if (gm >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
-      if (gn >= N) continue;
-      const size_t k = (size_t)gm * ep.ldc + gn;
-      float v = acc[i][j];
-      if (gridDim.z > 1) { ep.part[((size_t)blockIdx.z * M + gm) * N + gn] = v; continue; }
-      switch (ep.kind) {
-        case EPI_STORE: ep.C[k] = v; break;
-        case EPI_DZ:
-          if (ep.aux1 != nullptr) v *= ep.aux1[k];
-          ep.C[k] = v * act_bwd(ep.act, ep.aux0[k]);
-          break;
-        case EPI_UPDATE: {
-          float w = ep.C[k], t1 = ep.s1 ? ep.s1[k] : 0.f, t2 = ep.s2 ? ep.s2[k] : 0.f;
-          opt_apply(ep.opt, v, w, t1, t2);
-          ep.C[k] = w;
-          if (ep.s1) ep.s1[k] = t1;
-          if (ep.s2) ep.s2[k] = t2;
-        } break;
-        default: ep.C[k] = v + ep.aux0[gn]; break;
-      }
+    const int gn = n0 + tx * 4;
+    if (gn >= N) continue;
+    const int ncols = min(4, N - gn);
+    if (gridDim.z > 1) {
+      for (int j = 0; j < ncols; ++j) ep.part[((size_t)blockIdx.z * M + gm) * N + gn + j] = acc[i][j];
+      continue;
     }
+    gemm_epilogue4(ep, lr, gm, gn, ncols, acc[i]);
   }
 }
 
 // Sum of the split-K partials in slice order + the GEMM's epilogue.
 __global__ void __launch_bounds__(256)
 k_gemm_reduce(int M, int N, int S, GemmEpi ep) {
+  const int n4 = (N + 3) / 4;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * N) return;
-  const int gm = idx / N, gn = idx - gm * N;
-  float v = ep.part[idx];
-  for (int z = 1; z < S; ++z) v += ep.part[(size_t)z * M * N + idx];
-  const size_t k = (size_t)gm * ep.ldc + gn;
-  switch (ep.kind) {
-    case EPI_STORE: ep.C[k] = v; break;
-    case EPI_DZ:
-      if (ep.aux1 != nullptr) v *= ep.aux1[k];
-      ep.C[k] = v * act_bwd(ep.act, ep.aux0[k]);
-      break;
-    case EPI_UPDATE: {
-      float w = ep.C[k], t1 = ep.s1 ? ep.s1[k] : 0.f, t2 = ep.s2 ? ep.s2[k] : 0.f;
-      opt_apply(ep.opt, v, w, t1, t2);
-      ep.C[k] = w;
-      if (ep.s1) ep.s1[k] = t1;
-      if (ep.s2) ep.s2[k] = t2;
-    } break;
-    default: ep.C[k] = v + ep.aux0[gn]; break;
+  if (idx >= M * n4) return;
+  const int gm = idx / n4, gn = (idx - gm * n4) * 4;
+  const int ncols = min(4, N - gn);
+  const float lr = ep.kind == EPI_UPDATE ? ep.opt.st->lr : 0.f;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < ncols; ++j) {
+    const size_t e = (size_t)gm * N + gn + j;
+    float x = ep.part[e];
+    for (int z = 1; z < S; ++z) x += ep.part[(size_t)z * M * N + e];
+    v[j] = x;
   }
+  gemm_epilogue4(ep, lr, gm, gn, ncols, v);
 }
 
 // ============================================================================================
@@ -734,7 +836,7 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
   if (a.bitmap_words > 0) {
     for (int i = threadIdx.x; i < a.bitmap_words; i += blockDim.x) bitmap[i] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < a.bt.B; i += blockDim.x) {
+    for (int i = threadIdx.x; i < a.bt.hdr->B; i += blockDim.x) {
       const int r = a.bt.row_ids[i];
       atomicOr(&bitmap[r >> 5], 1u << (r & 31));
     }
@@ -761,7 +863,7 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
           // only stores with too many rows for shared memory fall back to the row -> slot map
           bool match = row[i] >= 0;
           if (match) match = a.bitmap_words > 0 ? ((bitmap[row[i] >> 5] >> (row[i] & 31)) & 1u) != 0
-                                                : (a.bt.rowslot[row[i]] >> SLOT_BITS) == a.bt.tag;
+                                                : (a.bt.rowslot[row[i]] >> SLOT_BITS) == a.bt.hdr->tag;
           const unsigned m = __ballot_sync(FULL, match);
           if (lane == 0) words[sb * (SCAN_SUB / 32) + warp + 8 * i] = m;
         }
@@ -900,6 +1002,7 @@ struct SortArgs {
 };
 
 __global__ void __launch_bounds__(128) k_sort_count(SortArgs a) {
+  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
   const int4 it = a.bt.items[blockIdx.x];
   const int p0 = a.bt.ent_off[it.x] + it.y;
   for (int i = threadIdx.x; i < it.z; i += 128) {
@@ -912,6 +1015,7 @@ __global__ void __launch_bounds__(128) k_sort_count(SortArgs a) {
 }
 
 __global__ void __launch_bounds__(128) k_sort_alloc(SortArgs a) {
+  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
   const int4 it = a.bt.items[blockIdx.x];
   const int p0 = a.bt.ent_off[it.x] + it.y;
   const int lane = threadIdx.x & 31;
@@ -958,6 +1062,7 @@ __global__ void __launch_bounds__(128) k_sort_alloc(SortArgs a) {
 }
 
 __global__ void __launch_bounds__(128) k_sort_bits(SortArgs a) {
+  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
   const int4 it = a.bt.items[blockIdx.x];
   const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
   for (int i = threadIdx.x; i < it.z; i += 128) {
@@ -968,6 +1073,7 @@ __global__ void __launch_bounds__(128) k_sort_bits(SortArgs a) {
 }
 
 __global__ void __launch_bounds__(128) k_sort_place(SortArgs a) {
+  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
   const int4 it = a.bt.items[blockIdx.x];
   const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
   for (int i = threadIdx.x; i < it.z; i += 128) {
@@ -992,7 +1098,7 @@ struct RowArgs {
   float* bdec; float* bd_s1; float* bd_s2;
   float* Wenc; float* We_s1; float* We_s2;
   float* Gdec; float* Genc; float* gbdec;   // KIND_GRAD: gradient rows instead of updates (row-parallel mode)
-  int n_cols; int3 bits; float aux_val;
+  int n_cols; int3 bits; const BatchHdr* bt_hdr;
   int dense; int n_arr; int arr_map[4];
   OptDev opt;
 };
@@ -1000,7 +1106,7 @@ struct RowArgs {
 constexpr int KIND_GRAD = 4;              // k_row_update: store the gradient row, apply nothing
 
 template <int NV, int KIND>
-__global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
+__global__ void __launch_bounds__(256, KIND == OCF_OPT_ADAM ? (NV <= 4 ? 2 : 1) : (NV <= 4 ? 3 : 2)) k_row_update(RowArgs a) {
   constexpr int HP = NV * 128;
   constexpr bool LOAD_W = KIND != KIND_GRAD;
   const int lane = threadIdx.x & 31;
@@ -1039,7 +1145,7 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
       if (i0 + lane < n) {
         const uint32_t* rec = a.matches + (size_t)(base + i0 + lane) * 3;
         bc = rec[0];
-        coef = arr == 0 ? __ldg(a.dy + rec[2]) : (arr == 1 ? __uint_as_float(rec[1]) : a.aux_val);
+        coef = arr == 0 ? __ldg(a.dy + rec[2]) : (arr == 1 ? __uint_as_float(rec[1]) : __ldg(&a.bt_hdr->aux_value));
       }
       unsigned m = __ballot_sync(FULL, ((bc >> 16) & bit) != 0);
       while (m) {
@@ -1059,12 +1165,13 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
       if (arr == 0 && lane == 0) a.gbdec[c] = cs;
       continue;
     }
+    const float lr = __ldg(&a.opt.st->lr);      // this step's learning rate (device-resident: a replayed graph carries no scalars)
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      opt_apply_k<KIND>(a.opt, g[v].x, w[v].x, t1[v].x, t2[v].x);
-      opt_apply_k<KIND>(a.opt, g[v].y, w[v].y, t1[v].y, t2[v].y);
-      opt_apply_k<KIND>(a.opt, g[v].z, w[v].z, t1[v].z, t2[v].z);
-      opt_apply_k<KIND>(a.opt, g[v].w, w[v].w, t1[v].w, t2[v].w);
+      opt_apply_k<KIND>(a.opt, lr, g[v].x, w[v].x, t1[v].x, t2[v].x);
+      opt_apply_k<KIND>(a.opt, lr, g[v].y, w[v].y, t1[v].y, t2[v].y);
+      opt_apply_k<KIND>(a.opt, lr, g[v].z, w[v].z, t1[v].z, t2[v].z);
+      opt_apply_k<KIND>(a.opt, lr, g[v].w, w[v].w, t1[v].w, t2[v].w);
       *reinterpret_cast<float4*>(Wrow + v * 128) = w[v];
       if (KIND != OCF_OPT_SGD) *reinterpret_cast<float4*>(S1row + r + lane * 4 + v * 128) = t1[v];
       if (KIND == OCF_OPT_ADAM) *reinterpret_cast<float4*>(S2row + r + lane * 4 + v * 128) = t2[v];
@@ -1072,7 +1179,7 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
     if (arr == 0 && lane == 0) {          // decoder bias: column-local gradient sum_b dy[b,c]
       OptDev ob = a.opt; ob.l2x2 = 0.f;   // Keras regularises kernels only
       float wb = a.bdec[c], b1 = KIND != OCF_OPT_SGD ? a.bd_s1[c] : 0.f, b2 = KIND == OCF_OPT_ADAM ? a.bd_s2[c] : 0.f;
-      opt_apply_k<KIND>(ob, cs, wb, b1, b2);
+      opt_apply_k<KIND>(ob, lr, cs, wb, b1, b2);
       a.bdec[c] = wb;
       if (KIND != OCF_OPT_SGD) a.bd_s1[c] = b1;
       if (KIND == OCF_OPT_ADAM) a.bd_s2[c] = b2;
@@ -1086,6 +1193,7 @@ __global__ void __launch_bounds__(256) k_row_update(RowArgs a) {
 __global__ void __launch_bounds__(256)
 k_dense_update(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ s1, float* __restrict__ s2,
                size_t n, OptDev o) {
+  const float lr = o.st->lr;
   const size_t n4 = n / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -1093,15 +1201,15 @@ k_dense_update(float* __restrict__ w, const float* __restrict__ g, float* __rest
     const float4 gv = reinterpret_cast<const float4*>(g)[i];
     float4 a = s1 ? reinterpret_cast<float4*>(s1)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 b = s2 ? reinterpret_cast<float4*>(s2)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    opt_apply(o, gv.x, wv.x, a.x, b.x); opt_apply(o, gv.y, wv.y, a.y, b.y);
-    opt_apply(o, gv.z, wv.z, a.z, b.z); opt_apply(o, gv.w, wv.w, a.w, b.w);
+    opt_apply(o, lr, gv.x, wv.x, a.x, b.x); opt_apply(o, lr, gv.y, wv.y, a.y, b.y);
+    opt_apply(o, lr, gv.z, wv.z, a.z, b.z); opt_apply(o, lr, gv.w, wv.w, a.w, b.w);
     reinterpret_cast<float4*>(w)[i] = wv;
     if (s1) reinterpret_cast<float4*>(s1)[i] = a;
     if (s2) reinterpret_cast<float4*>(s2)[i] = b;
   }
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float wv = w[i], a = s1 ? s1[i] : 0.f, b = s2 ? s2[i] : 0.f;
-    opt_apply(o, g[i], wv, a, b);
+    opt_apply(o, lr, g[i], wv, a, b);
     w[i] = wv;
     if (s1) s1[i] = a;
     if (s2) s2[i] = b;
@@ -1136,7 +1244,8 @@ __device__ void metrics_record(const MetricArgs& a, int lane) {
   for (int k = lane; k < a.n_reg; k += 32) reg += a.regparts[k];
   sse = warp_sum(sse); sae = warp_sum(sae); cnt = warp_sum(cnt); srt = warp_sum(srt); reg = warp_sum(reg);
   if (lane == 0) {
-    float* rec = a.rec;
+    const int slot = a.st->log_slot;
+    float* rec = a.log + (size_t)slot * LOG_W;
     const float bn = a.rows_total * a.n_cols_total;
     const float mse = sse / bn, mae = sae / bn;
     const float acc_mae = sae / cnt;
@@ -1148,8 +1257,15 @@ __device__ void metrics_record(const MetricArgs& a, int lane) {
     rec[5] = sse / cnt;
     rec[6] = sse;
     rec[7] = cnt;
+    __threadfence_system();
+    a.st->log_slot = slot + 1 == LOG_CAP ? 0 : slot + 1;
+    if (a.advance_step) a.st->step += 1u;
   }
 }
+
+// Rewrites the model's device-resident step scalars (only when a caller's step arguments differ
+// from what the device would use next).
+__global__ void k_set_step(StepDev* st, StepDev v) { *st = v; }
 
 __global__ void __launch_bounds__(32) k_metrics(MetricArgs a) { metrics_record(a, threadIdx.x); }
 
