@@ -490,7 +490,7 @@ def main():
                 yield b
             done += n
 
-    for b in epochs(W):
+    for b in epochs(max(W, 9)):              # three rounds of the reader's ring of 3 batch buffers: plain, capture, replay
         m.train_on_batch(b, sync=True)
     torch.cuda.synchronize()
     h2d = 0

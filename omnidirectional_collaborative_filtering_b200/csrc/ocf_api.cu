@@ -1042,8 +1042,13 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   for (int k = 0; k < 64; ++k)
     if (cudaEventCreateWithFlags(&m->step_ev[k], cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(OCF_ERR_CUDA, "ocf_model_create: event creation failed"));
-  if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&m->cap, cudaStreamNonBlocking) != cudaSuccess ||
+  // the column grouping (K4a) runs beside K2/K3 at the LOWEST priority: its small latency-bound CTAs take the
+  // slots the row-centric kernels leave, instead of pushing those into a second wave; the capture stream carries
+  // the highest priority so that captured steps keep the same order of preference
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&m->cap, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(OCF_ERR_CUDA, "ocf_model_create: side stream creation failed"));
@@ -1442,21 +1447,22 @@ static int launch_reg(ocf_model* m, cudaStream_t st) {
   return N_REGPART * (m->L + 1);
 }
 
-template <int NV>
+template <int NV, bool WIDE>
 static int launch_row_update_nv(int kind, int grid, const RowArgs& r, cudaStream_t st) {
   switch (kind) {
-    case OCF_OPT_SGD: k_row_update<NV, OCF_OPT_SGD><<<grid, 256, 0, st>>>(r); break;
-    case OCF_OPT_ADAGRAD: k_row_update<NV, OCF_OPT_ADAGRAD><<<grid, 256, 0, st>>>(r); break;
-    case OCF_OPT_RMSPROP: k_row_update<NV, OCF_OPT_RMSPROP><<<grid, 256, 0, st>>>(r); break;
-    case KIND_GRAD: k_row_update<NV, KIND_GRAD><<<grid, 256, 0, st>>>(r); break;
-    default: k_row_update<NV, OCF_OPT_ADAM><<<grid, 256, 0, st>>>(r); break;
+    case OCF_OPT_SGD: k_row_update<NV, OCF_OPT_SGD, WIDE><<<grid, 256, 0, st>>>(r); break;
+    case OCF_OPT_ADAGRAD: k_row_update<NV, OCF_OPT_ADAGRAD, WIDE><<<grid, 256, 0, st>>>(r); break;
+    case OCF_OPT_RMSPROP: k_row_update<NV, OCF_OPT_RMSPROP, WIDE><<<grid, 256, 0, st>>>(r); break;
+    case KIND_GRAD: k_row_update<NV, KIND_GRAD, false><<<grid, 256, 0, st>>>(r); break;
+    default: k_row_update<NV, OCF_OPT_ADAM, WIDE><<<grid, 256, 0, st>>>(r); break;
   }
   OCF_LAUNCHED();
   return OCF_OK;
 }
 
-static int launch_row_update(int hp, int kind, int grid, const RowArgs& r, cudaStream_t st) {
-  OCF_NV_SWITCH(hp, return launch_row_update_nv<NV>(kind, grid, r, st));
+static int launch_row_update(int hp, int kind, int grid, bool wide, const RowArgs& r, cudaStream_t st) {
+  if (wide) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, true>(kind, grid, r, st))); }
+  else { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false>(kind, grid, r, st))); }
   return OCF_OK;
 }
 
@@ -1532,7 +1538,9 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   if (do_dec) r.arr_map[r.n_arr++] = 0;
   if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
   g_prof.begin(5, st);
-  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count * 6, r, st));
+  // small catalogues (weights + state within reach of the 126 MB L2): latency-bound, wide walk; else HBM-bound
+  const bool wide = !grad_mode && (size_t)m->cfg.n_cols * (size_t)hpx <= ((size_t)8 << 20);
+  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count * (wide ? 4 : 6), wide, r, st));
   g_prof.end(5, st);
   return OCF_OK;
 }

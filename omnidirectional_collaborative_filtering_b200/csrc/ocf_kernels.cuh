@@ -1105,8 +1105,12 @@ struct RowArgs {
 
 constexpr int KIND_GRAD = 4;              // k_row_update: store the gradient row, apply nothing
 
-template <int NV, int KIND>
-__global__ void __launch_bounds__(256, KIND == OCF_OPT_ADAM ? (NV <= 4 ? 2 : 1) : (NV <= 4 ? 3 : 2)) k_row_update(RowArgs a) {
+// WIDE: two matched activation rows in flight per step of a task's walk (more registers, fewer resident warps): for
+// catalogues whose weights sit in L2, where the kernel is bound by the longest column's chain of dependent L2 round
+// trips instead of by HBM.
+template <int NV, int KIND, bool WIDE>
+__global__ void __launch_bounds__(256, WIDE ? (NV <= 4 ? 2 : 1) : (KIND == OCF_OPT_ADAM ? (NV <= 4 ? 2 : 1) : (NV <= 4 ? 3 : 2)))
+k_row_update(RowArgs a) {
   constexpr int HP = NV * 128;
   constexpr bool LOAD_W = KIND != KIND_GRAD;
   const int lane = threadIdx.x & 31;
@@ -1148,7 +1152,7 @@ __global__ void __launch_bounds__(256, KIND == OCF_OPT_ADAM ? (NV <= 4 ? 2 : 1) 
         coef = arr == 0 ? __ldg(a.dy + rec[2]) : (arr == 1 ? __uint_as_float(rec[1]) : __ldg(&a.bt_hdr->aux_value));
       }
       unsigned m = __ballot_sync(FULL, ((bc >> 16) & bit) != 0);
-      while (m) {
+      while (!WIDE && m) {
         const int j = __ffs(m) - 1; m &= m - 1;
         const uint32_t b = __shfl_sync(FULL, bc, j) & 0xffffu;
         const float cf = __shfl_sync(FULL, coef, j);
@@ -1156,6 +1160,24 @@ __global__ void __launch_bounds__(256, KIND == OCF_OPT_ADAM ? (NV <= 4 ? 2 : 1) 
 #pragma unroll
         for (int v = 0; v < NV; ++v) fma4(g[v], cf, ldg4(x + v * 128));
         cs += cf;
+      }
+      while (WIDE && m) {
+        // (a popular column has as many matches as the batch has rows: one dependent L2 round trip per match was the
+        // tail of this kernel on small catalogues); the sums keep their order: match j0 is added before match j1
+        const int j0 = __ffs(m) - 1; m &= m - 1;
+        const bool two = m != 0;
+        const int j1 = two ? __ffs(m) - 1 : j0; m &= m - 1;
+        const uint32_t b0 = __shfl_sync(FULL, bc, j0) & 0xffffu, b1 = __shfl_sync(FULL, bc, j1) & 0xffffu;
+        const float cf0 = __shfl_sync(FULL, coef, j0);
+        const float cf1 = two ? __shfl_sync(FULL, coef, j1) : 0.f;
+        const float* x0 = X + (size_t)b0 * HP;
+        const float* x1 = X + (size_t)b1 * HP;
+        float4 a0[NV], a1[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { a0[v] = ldg4(x0 + v * 128); a1[v] = ldg4(x1 + v * 128); }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { fma4(g[v], cf0, a0[v]); fma4(g[v], cf1, a1[v]); }
+        cs += cf0; cs += cf1;
       }
     }
     if (KIND == KIND_GRAD) {

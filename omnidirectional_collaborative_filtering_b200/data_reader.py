@@ -35,15 +35,26 @@ def _csr_from_lists(lists, col_of, n_cols) -> Csr:
     rowptr = np.zeros(len(lists) + 1, dtype=np.int64)
     np.cumsum(lens, out=rowptr[1:])
     col = np.empty(int(rowptr[-1]), dtype=np.int32)
-    val = np.empty(int(rowptr[-1]), dtype=np.float32)
+    val64 = np.empty(int(rowptr[-1]), dtype=np.float64)
     k = 0
     for l in lists:
         if not l:
             continue
         for pair in l:
             col[k] = col_of[pair[0]]           # data_reader.py:135 (KeyError like the reference)
-            val[k] = pair[1]
+            val64[k] = pair[1]
             k += 1
+    # The store is float32 (the model's dtype; the reference's float64 batch arrays are cast to float32 at the
+    # feed). Dyadic ratings (k/2, integers) are exact; others round to the nearest float32 (~6e-8 relative) and the
+    # dense view `Batch.to_dense` returns those rounded values. A finite rating beyond float32's range becomes inf,
+    # as in the native parser (csrc/ocf_etl.cpp) and in the reference's own float32 feed - said out loud here.
+    with np.errstate(over="ignore"):
+        val = val64.astype(np.float32)
+    overflow = np.isfinite(val64) & ~np.isfinite(val)
+    if overflow.any():
+        import warnings
+        warnings.warn("%d rating(s) exceed float32's range and are stored as inf (first: %r)"
+                      % (int(overflow.sum()), float(val64[np.flatnonzero(overflow)[0]])), RuntimeWarning, stacklevel=2)
     return Csr(len(lists), n_cols, rowptr, col, val)
 
 
@@ -122,7 +133,15 @@ class DeviceRng(object):
             cur, lent = np.random.get_state(), self.host_state
             if not (cur[2] == lent[2] and cur[3] == lent[3] and cur[4] == lent[4] and np.array_equal(cur[1], lent[1])):
                 # np.random was reseeded (or drawn from) on the host while the stream was on loan:
-                # the host's stream is the current one, the device's copy and its open tickets lapse
+                # the host's stream is the current one, the device's copy and its open tickets lapse.
+                # Draws the device already made are then NOT reflected in np.random: say so unless the host
+                # clearly reseeded (a fresh seed puts the position at 624 with a new key).
+                if self.active and cur[2] != 624:
+                    import warnings
+                    warnings.warn("np.random was drawn from on the host while its stream was lent to the GPU "
+                                  "(data_reader.DeviceRng): the draws the GPU made for uploaded batches are dropped from "
+                                  "the host stream. Call data_reader.sync_rng() before drawing from np.random between "
+                                  "batches, or construct the reader with rng_on_device=False.", RuntimeWarning, stacklevel=3)
                 self.pending.clear()
                 self.active = False
                 self.host_state = None
@@ -311,7 +330,7 @@ class Prefetcher(object):
 
     def __init__(self, generator, count, depth=10, chunk=8):
         import queue
-        self.count = int(count)
+        self.count = max(int(count), 0)          # Keras runs zero steps for steps <= 0 (sets smaller than one batch)
         self.queue = queue.Queue(maxsize=depth)
         self.error = None
         chunk = max(1, int(chunk))

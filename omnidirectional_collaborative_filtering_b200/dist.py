@@ -352,7 +352,7 @@ def bench_main(args, w, cfg, rank, world):
     ratings = float(rt.item())                           # ratings of the global batches (all ranks together)
 
     # e2e through the public API on every rank: host RNG replay + H2D + phases/collectives + D2H
-    for _ in range(W):
+    for _ in range(max(W, 9)):               # three rounds of the ring of 3 batch buffers: plain, capture, replay
         m.train_on_batch(next(batches), sync=True)
     dist.barrier()
     torch.cuda.synchronize()

@@ -10,8 +10,9 @@ Arithmetic runs in `csrc/` kernels; nothing here co
 Differences from Keras that a caller can see:
   * generators yield `data_reader.Batch` objects, not dense arrays
   * `num_hidden_units` may be a list of widths (superset; the reference uses one width)
-  * `save`/`load` use `.npz` (h5py is not available); optimizer state is not saved, matching
-    what `train.py:183-189` strips before testing
+  * `save` / `load_model` keep the reference's file names and write Keras-layout HDF5 when h5py is importable,
+    `.npz` bytes otherwise (`checkpoint.py`); optimizer state is not saved, matching what `train.py:183-189`
+    strips before testing
   * dropout masks come from Philox (oracle/philox.py defines the spec), not TensorFlow's RNG
 """
 from __future__ import annotations
@@ -227,14 +228,14 @@ class OmniNet(object):
         the metric records, copied to pinned memory behind every step, are read back in chunks.
         workers=1 (Keras' default) draws the batches on a prefetch thread, workers=0 inline."""
         from .data_reader import Prefetcher
-        steps = int(steps)
+        steps = max(int(steps), 0)              # train.py passes floor(n/B) - 1: -1 for sets smaller than a batch; Keras runs none
         rows = []
         first = None
         pending = 0
         source = Prefetcher(generator, steps) if workers else (next(generator) for _ in range(steps))
         for batch in source:
             if batch is None:
-                raise StopIteration("generator ran out of batches (it yields None after floor(n/B) batches)")
+                raise RuntimeError("generator ran out of batches (it yields None after floor(n/B) batches)")
             if first is None:
                 self._ensure(batch.n_rows, batch.n_entries, batch.aux_type, batch.reader)
                 first = _lib.lib().ocf_model_steps_logged(self._handle)
@@ -332,18 +333,19 @@ class OmniNet(object):
         self.comm.reduce_z(batch.n_rows)
 
     def save(self, path):
-        """`m.save(...)`, train.py:169 (weights + architecture as .npz; no optimizer state)."""
-        o = self.owner
-        np.savez(path if path.endswith(".npz") else path + ".npz", *self.get_weights(),
-                 config=np.array(repr(o.config())))
+        """`m.save(...)`, train.py:169: weights + architecture under exactly `path` (the reference's names carry no
+        extension), as Keras-layout HDF5 when h5py is importable, else as .npz bytes; no optimizer state, which
+        train.py:183-189 strips anyway. See `checkpoint.py`."""
+        from . import checkpoint
+        checkpoint.save(path, self.get_weights(), self.owner.config())
 
     def save_weights(self, path):
-        np.savez(path if path.endswith(".npz") else path + ".npz", *self.get_weights())
+        from . import checkpoint
+        checkpoint.save(path, self.get_weights(), None)
 
     def load_weights(self, path):
-        with np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False) as f:
-            keys = sorted((k for k in f.files if k.startswith("arr_")), key=lambda k: int(k[4:]))
-            self.set_weights([f[k] for k in keys])
+        from . import checkpoint
+        self.set_weights(checkpoint.load(path)[1])
 
     def close(self):
         if self._handle is not None:
@@ -461,9 +463,25 @@ class omni_model(object):
         return [[w[2 * l], w[2 * l + 1]] for l in range(self.numlayers + 1)]
 
     def _set_dense(self, l, pair):
-        w = self.model.get_weights()
-        w[2 * l], w[2 * l + 1] = pair[0], pair[1]
-        self.model.set_weights(w)
+        """Kernel + bias of dense layer l (only these two arrays move; no round trip of the other layers)."""
+        shapes = self.weight_shapes()
+        arrs = []
+        for k in (0, 1):
+            a = np.ascontiguousarray(pair[k], dtype=np.float32)
+            if tuple(a.shape) != tuple(shapes[2 * l + k]):
+                raise ValueError("weight shape %s does not match %s" % (a.shape, shapes[2 * l + k]))
+            arrs.append(a)
+        net = self.model
+        if getattr(net, "_handle", None) is None:
+            if self._host_weights is not None and type(net).__name__ == "OmniNet":
+                self._host_weights[2 * l], self._host_weights[2 * l + 1] = arrs[0].copy(), arrs[1].copy()
+            else:                                   # a stand-in model (tests): go through its own setter
+                w = net.get_weights()
+                w[2 * l], w[2 * l + 1] = arrs[0], arrs[1]
+                net.set_weights(w)
+            return
+        for k in (0, 1):
+            _lib.check(_lib.lib().ocf_model_set_weight(net._handle, 2 * l + k, _lib.ptr(arrs[k]), arrs[k].size))
 
     def _set_trainable(self, l, flag):
         self.trainable[l] = bool(flag)
@@ -520,12 +538,12 @@ def _donor_pairs(donor):
 
 
 def load_model(path):
-    """`keras.models.load_model(...)` stand-in for files written by `OmniNet.save` (train.py:139,191)."""
-    import ast
-    with np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False) as f:
-        cfg = ast.literal_eval(str(f["config"]))
-        keys = sorted((k for k in f.files if k.startswith("arr_")), key=lambda k: int(k[4:]))
-        weights = [f[k] for k in keys]
+    """`keras.models.load_model(...)` (train.py:139,191): a model file written by `OmniNet.save` or, with h5py
+    installed, by Keras itself (the reference's donors); format told by the file's first bytes (`checkpoint.py`)."""
+    from . import checkpoint
+    cfg, weights = checkpoint.load(path)
+    if cfg is None:
+        raise ValueError("%s holds weights only (save_weights); build the model and call load_weights" % path)
     from .data_reader import sync_host_rng
     sync_host_rng()
     state = np.random.get_state()                   # loading must not disturb the caller's stream

@@ -1,5 +1,5 @@
 """Checkpoints and donor models on the host (train.py:136-145,164-169,181-199): `m.save` /
-`load_model` / `save_weights` / `load_weights` round trips in the `.npz` format, and the two-stage nested
+`load_model` / `save_weights` / `load_weights` round trips (`.npz` bytes under the reference's file names: h5py is absent here), and the two-stage nested
 denoising autoencoder of BASELINE configs[3] through `train.run` - stage 1 saves its best model, stage 2
 (`load_weights_from`, deeper, outer layers frozen; or `perform_finetuning`) starts from it. The arithmetic is
 the oracle's (`helpers.OracleNet`), so everything here runs without a GPU and must match the oracle loop exactly."""
@@ -71,9 +71,9 @@ def test_two_stage_training_from_a_saved_donor(monkeypatch, tmp_path, finetune):
     monkeypatch.setattr(ocf_train, "omni_model", _oracle_backed(cfg1, fs.n_cols))
     np.random.seed(5)
     first = ocf_train.run(cfg1, reader=rd, rating_range=fs.rating_range, save_models=True, verbose=0)
-    saved = sorted(glob.glob(save_dir + "*_bestValidScore.npz"), key=os.path.getmtime)
-    assert saved and saved[-1].endswith(first["save_name"] + "_bestValidScore.npz")
-    donor_name = os.path.basename(saved[-1])[:-len(".npz")]
+    saved = sorted(glob.glob(save_dir + "*_bestValidScore"), key=os.path.getmtime)
+    assert saved and saved[-1].endswith(first["save_name"] + "_bestValidScore")       # the reference's name, no extension
+    donor_name = os.path.basename(saved[-1])
     donor_weights = load_model(save_dir + donor_name).get_weights()
     for a, b in zip(donor_weights, first["model"].model.get_weights()):
         assert np.array_equal(a, b)                       # the tested (best) weights are the saved ones

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _newest(save_dir, pattern):
-    found = sorted(glob.glob(save_dir + pattern), key=os.path.getmtime)
+    found = sorted(glob.glob(glob.escape(save_dir) + pattern), key=os.path.getmtime)
     assert found, "no checkpoint written under %s" % save_dir
     return found[-1]
 
@@ -34,7 +34,7 @@ def test_best_model_saved_reloaded_and_continued_on_the_device(tmp_path, finetun
                         num_hidden_units=24, model_save_path=save_dir)
     np.random.seed(5)
     first = ocf_train.run(cfg1, reader=rd, rating_range=fs.rating_range, save_models=True, verbose=0)
-    path = _newest(save_dir, first["save_name"] + "_bestValidScore*")
+    path = _newest(save_dir, glob.escape(first["save_name"]) + "_bestValidScore*")
     live = first["model"].model                           # holds the best weights (train.py:191: the tested model)
     # ---- reload: same bits on the device, same test metrics ---------------------------------------------------
     back = load_model(path)
@@ -94,7 +94,7 @@ def test_best_model_saved_reloaded_and_continued_on_the_device(tmp_path, finetun
     want = oracle_train_run(fs, cfg2, 6, init)
     assert_same_run(got, want, rtol=1e-3)
     # the second stage's own best model is on disk too and reloads to the tested weights
-    path2 = _newest(save_dir, got["save_name"] + "_bestValidScore*")
+    path2 = _newest(save_dir, glob.escape(got["save_name"]) + "_bestValidScore*")
     for a, b in zip(load_model(path2).get_weights(), final):
         assert np.array_equal(a, b)
     rd.close()
