@@ -235,6 +235,23 @@ def touched(batch, k_mask_blocks):
     return u_in, u_tg, int(f.sum()), int(cols.size if batch.pass_through else (~f).sum())
 
 
+def state_words_of(w):
+    return {"sgd": 2, "adagrad": 4, "rmsprop": 4, "adam": 6}[w["opt"][0]]
+
+
+def ncu_traffic(workload, kernel_key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel from the committed
+    `ncu --set full` summary of the CURRENT round for this workload, or None: profiles/traffic.json is written by
+    scripts/ncu_summary.py from the raw capture, so the number is never a literal in this file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(workload, {}).get(kernel_key)
+        return (float(e["dram_bytes"]), e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 def step_bytes(plans, w, nnz_store, n_obs_sample=8):
     """Algorithmic bytes of one train step's kernels, mean over `plans`:
     [K1, K2, K3, K4a, K4b]. K4b = S * 4 * (h_dec * U_target + h_enc * (k_in * U_input + k_obs * U_observed)) with
@@ -264,11 +281,14 @@ def step_bytes(plans, w, nnz_store, n_obs_sample=8):
 # ------------------------------------------------------------------------------------------------
 def cpu_reference(w, fs, batch_size, steps, warmup, budget_s=None, seed=0):
     from oracle import ref_batches, ref_model
+    # every host core for the dense NumPy step, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for N > 1)
+    threads = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        from threadpoolctl import threadpool_info, threadpool_limits
+        cpu_reference._limit = threadpool_limits(limits=threads)          # kept alive for the whole run
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [threads])
     except Exception:
-        threads = os.cpu_count() or 1
+        threads = int(os.environ.get("OMP_NUM_THREADS", threads))
     rs = np.random.RandomState(seed)
     n_batches = steps + warmup
     rows = rs.permutation(fs.train.n_rows)[:n_batches * batch_size]
@@ -318,6 +338,25 @@ def cpu_reference(w, fs, batch_size, steps, warmup, budget_s=None, seed=0):
             "overlapped_value": ratings / max(t_batch, t_model, 1e-9)}
 
 
+def other_workloads(names, args, gpus=1):
+    """The remaining BASELINE configs, each in its own process (own CUDA context, a failure cannot take the headline
+    line down): value / e2e / ms_per_step / roofline / per-kernel times of `bench.py --workload X`."""
+    out = {}
+    for name in names:
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(max(10, min(args.steps, 30))),
+               "--warmup", str(args.warmup), "--no-cpu-baseline", "--no-scoring", "--others", "none", "--batch-size", str(args.batch_size)]
+        t0 = time.perf_counter()
+        try:
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+            d = json.loads(res.stdout.strip().splitlines()[-1])
+            out[name] = {k: d.get(k) for k in ("value", "unit", "ms_per_step", "steps", "e2e", "roofline", "kernels", "gpu_launches", "config",
+                                               "l2", "ratings_per_step", "target_ratings_per_s", "clocks")}
+            out[name]["wall_s"] = time.perf_counter() - t0
+        except Exception as e:
+            out[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -334,6 +373,10 @@ def main():
     ap.add_argument("--score-rows", type=int, default=1024)
     ap.add_argument("--parallel", default="columns", choices=["columns", "rows"],
                     help="N > 1: item-dimension sharding (default) or data parallelism with a gradient all-reduce")
+    ap.add_argument("--others", default=None,
+                    help="comma-separated workloads whose value / e2e / roofline ride along under 'other_workloads' "
+                         "(default: the other four BASELINE configs when the workload is the default one; 'none' to skip)")
+    ap.add_argument("--no-scoring", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -347,7 +390,7 @@ def main():
         if rank != 0:
             return 0
         fs = make_dataset(w)
-        warm = max(1, min(args.warmup, 2))
+        warm = max(args.warmup, 0)
         res = cpu_reference(w, fs, B, args.steps, warm, budget_s=150.0)
         line = {"impl": "reference", "metric": "train ratings/sec", "value": res["value"], "unit": "ratings/s",
                 "n_gpus": args.gpus, "steps": res["steps"], "warmup": warm, "ms_per_step": res["ms_per_step"],
@@ -448,6 +491,15 @@ def main():
         torch.cuda.synchronize()
     ratings = sum(p.n_entries for p in plans[W:])
     value = ratings / (ms * 1e-3)
+    # SURVEY 8(d) counts a rating as one observed TARGET entry of a step; `value` counts every stored rating of the
+    # batch rows (each is gathered, split and consumed). Both are reported.
+    targets = sum(p.n_entries if p.pass_through else int((np.asarray(p.flags) == 0).sum()) for p in plans[W:])
+    working_set = (sum(np.prod(sh) for sh in om.weight_shapes()) * 4 * state_words_of(w) / 2 + fs.train.nnz * 9) / 1e6
+    if working_set > 2 * 126:
+        l2_note = "no flush: weights + optimizer state + store (%.0f MB) exceed the 126 MB L2 several times over" % working_set
+    else:
+        l2_note = ("no flush, and weights + optimizer state + store (%.0f MB) fit or nearly fit the 126 MB L2: the kernels of this "
+                   "workload run from L2, an HBM fraction is not meaningful for it (roofline.bound says 'l2')" % working_set)
 
     # ---- roofline: instrumented pass over the same resident batches ------------------------------
     lib.ocf_profile_reset()
@@ -461,7 +513,7 @@ def main():
         tot, cnt = C.c_double(), C.c_int64()
         _lib.check(lib.ocf_profile_read(t, C.byref(tot), C.byref(cnt)))
         tag_ms.append(tot.value / max(cnt.value, 1))
-    state_words = {"sgd": 2, "adagrad": 4, "rmsprop": 4, "adam": 6}[w["opt"][0]]
+    state_words = state_words_of(w)
     alg = step_bytes(plans[W:], w, fs.train.nnz)
     peak, peak_src = peaks()
     dom = int(np.argmax(tag_ms))
@@ -469,12 +521,13 @@ def main():
                for t in range(5)}
     achieved = alg[dom] / (tag_ms[dom] * 1e-3) / 1e9
     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel on this workload
-    traffic = 762.8e6 if (args.workload == "ml10m" and B == 128 and dom == 4) else None
-    roofline = {"kernel": tag_names[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "profiles/r01_ncu_full_k_row_update_v2.txt (dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None,
+    traffic, traffic_src = ncu_traffic(args.workload, tag_names[dom].split(" ")[0]) if B == 128 else (None, None)
+    roofline = {"kernel": tag_names[dom], "bound": "hbm" if working_set > 2 * 126 else "l2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": alg[dom], "peak_source": peak_src,
-                "share_of_step": tag_ms[dom] / (ms / K)}
+                "share_of_step": tag_ms[dom] / (ms / K),
+                # the whole step against the same roofline: every kernel's algorithmic bytes / the step's device time
+                "step_frac": sum(alg) / (ms / K * 1e-3) / 1e9 / peak, "step_algorithmic_bytes": sum(alg)}
 
     # ---- e2e: the public API, host buffers in, metrics out, every step ---------------------------
     from omnidirectional_collaborative_filtering_b200.data_reader import Prefetcher
@@ -515,17 +568,24 @@ def main():
 
     line = {"metric": "train ratings/sec", "value": value, "unit": "ratings/s", "n_gpus": 1, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(cfg, l2="no flush: weights+optimizer state+store (%.0f MB) exceed the 126 MB L2"
-                                                % ((sum(np.prod(s) for s in om.weight_shapes()) * 4 * state_words / 2 + fs.train.nnz * 16) / 1e6),
-                                                ratings_per_step=ratings / K),
+            "data": "synthetic", "config": cfg, "l2": l2_note, "ratings_per_step": ratings / K,
+            "target_ratings_per_step": targets / K, "target_ratings_per_s": targets / (ms * 1e-3),
             "clocks": clocks,
             "e2e": {"value": e_ratings / e2e_s, "unit": "ratings/s", "h2d_bytes_per_step": h2d / K,
                     "d2h_bytes_per_step": 4 * _lib.N_METRICS, "ms_per_step": 1e3 * e2e_s / K},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
-    try:
-        line["scoring"] = scoring_run(lib, m, rd, w, aux, args.score_rows, 10, 3)
-    except Exception as e:                                  # the train line must not depend on it
-        line["scoring"] = {"error": str(e)}
+    if not args.no_scoring:
+        try:
+            line["scoring"] = scoring_run(lib, m, rd, w, aux, args.score_rows, 10, 3)
+        except Exception as e:                                  # the train line must not depend on it
+            line["scoring"] = {"error": str(e)}
+    others = args.others
+    if others is None:
+        others = "ml1m,jester,ml20m,netflix" if args.workload == "ml10m" else "none"
+    if others != "none":
+        # release this workload's device memory before the others run in their own processes
+        m.close(); rd.close(); del resident
+        line["other_workloads"] = other_workloads([x for x in others.split(",") if x], args)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference(w, fs, B, 1000, 1, budget_s=args.cpu_seconds).items()
                                 if k in ("value", "unit", "cores", "kind", "sample", "overlapped_value")}

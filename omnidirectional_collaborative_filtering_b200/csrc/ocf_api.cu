@@ -229,9 +229,9 @@ struct ocf_model {
   int32_t* topk_cols = nullptr;   // top-k epilogue outputs [max_rows, 512] (allocated with dense_out's arena)
   float* topk_scores = nullptr;
   size_t topk_cap = 0;
-  int* col_state = nullptr;       // batch-side K4a: [3][n_cols] per-column count / code OR / claimed, zeroed per step
-  int4* col_info = nullptr;       //   [n_cols]
-  uint32_t* col_bits = nullptr;   //   presence bitmap [min(n_cols, max_entries)][ceil(max_rows / 32)]
+  int* col_state = nullptr;       // batch-side K4a: [2][n_cols] per-column count / code OR, zeroed per step
+  int2* col_info = nullptr;       //   [n_cols] (first match, matches)
+  uint32_t* col_bits = nullptr;   //   presence bitmap [n_cols][ceil(max_rows / 32)]
   size_t col_bits_words = 0;
   int sm_count = 148;
   // the column scan (K4a) needs only the gathered batch: it runs on a side stream beside K2/K3
@@ -991,7 +991,7 @@ static int alloc_workspace(ocf_model* m, int max_rows, int64_t max_entries) {
   m->dh_top = m->rowstats + (size_t)max_rows * ROWSTAT_W;
   OCF_TRY(ws.get(&m->col_matches, (size_t)max_entries * 3));
   OCF_TRY(ws.get(&m->col_mcol, (size_t)max_entries));
-  m->col_bits_words = (size_t)std::min<int64_t>(m->cfg.n_cols, max_entries) * (size_t)((max_rows + 31) / 32);
+  m->col_bits_words = (size_t)m->cfg.n_cols * (size_t)((max_rows + 31) / 32);
   OCF_TRY(ws.get(&m->col_bits, m->col_bits_words, true));
   return OCF_OK;
 }
@@ -1030,7 +1030,7 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   if (st) return bail(st);
   if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_step, 1, true)) ||
       (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_seg, (size_t)N, true)) ||
-      (st = m->mem.get(&m->col_counters, 4, true)) || (st = m->mem.get(&m->col_state, (size_t)3 * N, true)) ||
+      (st = m->mem.get(&m->col_counters, 4, true)) || (st = m->mem.get(&m->col_state, (size_t)2 * N, true)) ||
       (st = m->mem.get(&m->col_info, (size_t)N)))
     return bail(st);
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev); if (m->sm_count <= 0) m->sm_count = 148; }
@@ -1475,23 +1475,20 @@ static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   if (!b->store->has_dups) {
     // batch-side counting sort (every (column, batch row) pair is unique)
     const int W = (bt.B + 31) / 32;
-    // (a captured step clears the whole bitmap: its size must not depend on the fill)
-    const size_t words = m->capturing ? m->col_bits_words : (size_t)std::min<int64_t>(m->cfg.n_cols, bt.n_entries) * W;
-    OCF_CUDA(cudaMemsetAsync(m->col_state, 0, sizeof(int) * 3 * (size_t)m->cfg.n_cols, st));
-    OCF_CUDA(cudaMemsetAsync(m->col_bits, 0, sizeof(uint32_t) * std::max<size_t>(std::min(words, m->col_bits_words), 4), st));
+    const size_t N = (size_t)m->cfg.n_cols;
+    OCF_CUDA(cudaMemsetAsync(m->col_state, 0, sizeof(int) * 2 * N, st));
+    OCF_CUDA(cudaMemsetAsync(m->col_bits, 0, sizeof(uint32_t) * N * W, st));
     SortArgs a{};
     a.bt = bt;
-    a.cnt = m->col_state; a.codeor = m->col_state + m->cfg.n_cols; a.claimed = m->col_state + 2 * (size_t)m->cfg.n_cols;
+    a.cnt = m->col_state; a.codeor = m->col_state + N;
     a.colinfo = m->col_info; a.bits = m->col_bits; a.W = W; a.counters = m->col_counters;
     a.matches = m->col_matches; a.tasks = m->col_tasks; a.colseg = m->col_seg;
-    a.nblk = m->nblk; a.bits3 = m->bits; a.dense = dense; a.do_dec = do_dec; a.do_enc = do_enc;
+    a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits3 = m->bits; a.dense = dense; a.do_dec = do_dec; a.do_enc = do_enc;
     const int grid = item_grid(m, b);
     g_prof.begin(3, st);
     k_sort_count<<<grid, 128, 0, st>>>(a);
     OCF_LAUNCHED();
-    k_sort_alloc<<<grid, 128, 0, st>>>(a);
-    OCF_LAUNCHED();
-    k_sort_bits<<<grid, 128, 0, st>>>(a);
+    k_sort_alloc<<<(m->cfg.n_cols + 255) / 256, 256, 0, st>>>(a);
     OCF_LAUNCHED();
     k_sort_place<<<grid, 128, 0, st>>>(a);
     OCF_LAUNCHED();

@@ -435,6 +435,8 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
           float4* __restrict__ P, TailBuf tb, float4* __restrict__ z_out, int fuse_act, ActArgs act) {
   constexpr int HP = NV * 128;
   __shared__ float4 red[4][HP / 4];
+  __shared__ int2 s_list[128 * 3];          // (weight row, coefficient bits) of the row loads of 128 entries
+  __shared__ int s_cnt[3][4];
   if ((int)blockIdx.x >= bt.hdr->n_items) return;
   const float aux_val = bt.hdr->aux_value;
   const int4 it = bt.items[blockIdx.x];
@@ -445,31 +447,45 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int base = warp * 32; base < len; base += 128) {
-    const int i = base + lane;
+  // The chunk's (entry, input block) pairs that really load a weight row are compacted into one list in shared
+  // memory (entry order within a block, blocks in order), and the four warps deal that list in pairs: every warp
+  // gets the same number of row loads whatever the keep flags look like. (Dealing the ENTRIES to the warps left a
+  // third of the warp time waiting at the barrier for the warp that drew the most inputs.)
+  for (int tile = 0; tile < len; tile += 128) {
+    const int i = tile + (int)threadIdx.x;
     int c = 0, code = 0; float val = 0.f;
     if (i < len) { c = bt.ent_col[p0 + i]; val = bt.ent_val[p0 + i]; code = bt.codes[p0 + i]; }
-    for (int blk = 0; blk < nblk; ++blk) {
+    unsigned bal[3];
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
       const int bit = blk == 0 ? bits.x : (blk == 1 ? bits.y : bits.z);
-      const float coef = blk == 0 ? val : aux_val;
-      unsigned m = __ballot_sync(FULL, (code & bit) != 0);
-      const float* Wb = Wenc + (size_t)blk * n_cols * HP + lane * 4;
-      while (m) {
-        const int j0 = __ffs(m) - 1; m &= m - 1;
-        const bool two = m != 0;
-        const int j1 = two ? __ffs(m) - 1 : j0; m &= m - 1;
-        const int c0 = __shfl_sync(FULL, c, j0), c1 = __shfl_sync(FULL, c, j1);
-        const float f0 = __shfl_sync(FULL, coef, j0);
-        const float f1 = two ? __shfl_sync(FULL, coef, j1) : 0.f;
-        const float* r0 = Wb + (size_t)c0 * HP;
-        const float* r1 = Wb + (size_t)c1 * HP;
-        float4 w0[NV], w1[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) { w0[v] = ldg4(r0 + v * 128); w1[v] = ldg4(r1 + v * 128); }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) { fma4(acc[v], f0, w0[v]); fma4(acc[v], f1, w1[v]); }
-      }
+      bal[blk] = blk < nblk ? __ballot_sync(FULL, (code & bit) != 0) : 0u;
+      if (lane == 0) s_cnt[blk][warp] = __popc(bal[blk]);
     }
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+      int mine = total;
+#pragma unroll
+      for (int w2 = 0; w2 < 4; ++w2) { const int n = s_cnt[blk][w2]; if (w2 < warp) mine += n; total += n; }
+      if ((bal[blk] >> lane) & 1u)
+        s_list[mine + __popc(bal[blk] & ((1u << lane) - 1u))] = make_int2(blk * n_cols + c, __float_as_int(blk == 0 ? val : aux_val));
+    }
+    __syncthreads();
+    for (int j = warp * 2; j < total; j += 8) {
+      const bool two = j + 1 < total;
+      const int2 e0 = s_list[j], e1 = s_list[two ? j + 1 : j];
+      const float f0 = __int_as_float(e0.y), f1 = two ? __int_as_float(e1.y) : 0.f;
+      const float* r0 = Wenc + (size_t)e0.x * HP + lane * 4;
+      const float* r1 = Wenc + (size_t)e1.x * HP + lane * 4;
+      float4 w0[NV], w1[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { w0[v] = ldg4(r0 + v * 128); w1[v] = ldg4(r1 + v * 128); }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { fma4(acc[v], f0, w0[v]); fma4(acc[v], f1, w1[v]); }
+    }
+    if (tile + 128 < len) __syncthreads();          // the list is rebuilt for the next 128 entries
   }
 #pragma unroll
   for (int v = 0; v < NV; ++v) red[warp][v * 32 + lane] = acc[v];
@@ -508,6 +524,9 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
   constexpr int HP = NV * 128;
   __shared__ float4 red[TRAIN ? 4 : 1][HP / 4];
   __shared__ float sred[4][3];
+  __shared__ int2 s_list[128];              // (column, entry) of the target entries of 128 entries
+  __shared__ float s_t[128];
+  __shared__ int s_cnt[4];
   if ((int)blockIdx.x >= bt.hdr->n_items) return;
   const float aux_val = bt.hdr->aux_value;
   const int4 it = bt.items[blockIdx.x];
@@ -522,18 +541,26 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
   }
   float sse = 0.f, sae = 0.f, cnt = 0.f;
 
-  for (int base = warp * 32; base < len; base += 128) {
-    const int i = base + lane;
+  // target entries compacted into a list in shared memory, dealt to the four warps in pairs (see k_enc_fwd)
+  for (int tile = 0; tile < len; tile += 128) {
+    const int i = tile + (int)threadIdx.x;
     int c = 0, code = 0; float t = 0.f;
     if (i < len) { c = bt.ent_col[p0 + i]; t = bt.ent_val[p0 + i]; code = bt.codes[p0 + i]; }
-    unsigned m = __ballot_sync(FULL, (code & CODE_TGT) != 0);
-    if (TRAIN && i < len && !(code & CODE_TGT)) dy[p0 + i] = 0.f;
-    while (m) {
-      const int j0 = __ffs(m) - 1; m &= m - 1;
-      const bool two = m != 0;
-      const int j1 = two ? __ffs(m) - 1 : j0; m &= m - 1;
-      const int c0 = __shfl_sync(FULL, c, j0), c1 = __shfl_sync(FULL, c, j1);
-      const float t0 = __shfl_sync(FULL, t, j0), t1 = __shfl_sync(FULL, t, j1);
+    const bool tgt = (code & CODE_TGT) != 0;
+    if (TRAIN && i < len && !tgt) dy[p0 + i] = 0.f;
+    const unsigned bal = __ballot_sync(FULL, tgt);
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int mine = 0, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < 4; ++w2) { const int n = s_cnt[w2]; if (w2 < warp) mine += n; total += n; }
+    if (tgt) { const int pos = mine + __popc(bal & ((1u << lane) - 1u)); s_list[pos] = make_int2(c, i); s_t[pos] = t; }
+    __syncthreads();
+    for (int j = warp * 2; j < total; j += 8) {
+      const bool two = j + 1 < total;
+      const int2 e0 = s_list[j], e1 = s_list[two ? j + 1 : j];
+      const int c0 = e0.x, c1 = e1.x;
+      const float t0 = s_t[j], t1 = s_t[two ? j + 1 : j];
       const float* r0 = WdecT + (size_t)c0 * HP + lane * 4;
       const float* r1 = WdecT + (size_t)c1 * HP + lane * 4;
       float4 w0[NV], w1[NV];
@@ -551,7 +578,7 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
         if (TRAIN) {
           const float ge = loss_kind == OCF_LOSS_MSE ? gscale * e : gscale * (float)((e > 0.f) - (e < 0.f));
           const float dyv = aux_val * ge;
-          if (lane == 0) dy[p0 + base + j0] = dyv;
+          if (lane == 0) dy[p0 + e0.y] = dyv;
 #pragma unroll
           for (int v = 0; v < NV; ++v) fma4(dh[v], dyv, w0[v]);
         }
@@ -563,12 +590,13 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
         if (TRAIN) {
           const float ge = loss_kind == OCF_LOSS_MSE ? gscale * e : gscale * (float)((e > 0.f) - (e < 0.f));
           const float dyv = aux_val * ge;
-          if (lane == 0) dy[p0 + base + j1] = dyv;
+          if (lane == 0) dy[p0 + e1.y] = dyv;
 #pragma unroll
           for (int v = 0; v < NV; ++v) fma4(dh[v], dyv, w1[v]);
         }
       }
     }
+    if (tile + 128 < len) __syncthreads();
   }
   if (lane == 0) { sred[warp][0] = sse; sred[warp][1] = sae; sred[warp][2] = cnt; }
   if (TRAIN) {
@@ -981,94 +1009,77 @@ __global__ void __launch_bounds__(256) k_col_scan(ColArgs a) {
 // ============================================================================================
 // K4a, batch-side: groups the batch's own ratings by catalogue column with a counting sort over
 // the ~10^5 gathered entries instead of streaming the store's CSC index (10^7-10^8 entries):
-//   count   per-column number of live entries + OR of their code bits        (atomics on ints)
-//   alloc   one elected entry per touched column reserves the column's segment of the match
-//           list, a row of the presence bitmap and the column's update tasks (warp-aggregated)
-//   bits    every entry sets bit `batch row` in its column's bitmap row
-//   place   an entry's rank inside its column = popcount of the lower batch rows present, so the
-//           match list of a column is ordered by batch row whatever order the atomics ran in:
-//           the gradient sums of K4b keep a fixed order (bit-reproducible steps)
+//   count   per entry: the column's live-entry count, the OR of its code bits (int atomics) and bit
+//           `batch row` of the column's row of the presence bitmap [n_cols][W words]
+//   alloc   per COLUMN (a coalesced sweep over the count array): a touched column reserves its segment of
+//           the match list and its update tasks; one atomic per warp and counter (warp-aggregated), and
+//           the tasks come out in column order inside a warp: neighbouring tasks touch neighbouring
+//           weight rows
+//   place   per entry: rank inside its column = popcount of the lower batch rows present, so a column's
+//           matches are ordered by batch row whatever order the atomics ran in: the gradient sums of K4b
+//           keep a fixed order (bit-reproducible steps)
 // A (column, batch row) pair is unique unless a row repeats a column; stores with repeats keep
-// using the CSC scan above. Four small kernels over the work items, ~2 MB of traffic.
+// using the CSC scan above. Three small kernels beside K2 / K3 on a low-priority stream.
 // ============================================================================================
 struct SortArgs {
   BatchDev bt;
-  int* cnt; int* codeor; int* claimed;     // [n_cols] each, zeroed per step
-  int4* colinfo;                            // [n_cols] (first match, matches, bitmap row, -) of a touched column
-  uint32_t* bits; int W;                    // presence bitmap [touched columns][W words], zeroed per step
-  int* counters;                            // [0] matches [1] tasks [2] touched columns
+  int* cnt; int* codeor;                    // [n_cols] each, zeroed per step
+  int2* colinfo;                            // [n_cols] (first match, matches) of a touched column
+  uint32_t* bits; int W;                    // presence bitmap [n_cols][W words], zeroed per step
+  int* counters;                            // [0] matches [1] tasks
   uint32_t* matches; int4* tasks; int2* colseg;
-  int nblk; int3 bits3; int dense; int do_dec; int do_enc;
+  int n_cols; int nblk; int3 bits3; int dense; int do_dec; int do_enc;
 };
 
 __global__ void __launch_bounds__(128) k_sort_count(SortArgs a) {
   if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
   const int4 it = a.bt.items[blockIdx.x];
-  const int p0 = a.bt.ent_off[it.x] + it.y;
+  const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
   for (int i = threadIdx.x; i < it.z; i += 128) {
     const int code = a.bt.codes[p0 + i];
     if (code == 0) continue;
     const int c = a.bt.ent_col[p0 + i];
     atomicAdd(&a.cnt[c], 1);
     atomicOr(&a.codeor[c], code);
+    atomicOr(&a.bits[(size_t)c * a.W + (b >> 5)], 1u << (b & 31));
   }
 }
 
-__global__ void __launch_bounds__(128) k_sort_alloc(SortArgs a) {
-  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
-  const int4 it = a.bt.items[blockIdx.x];
-  const int p0 = a.bt.ent_off[it.x] + it.y;
+__global__ void __launch_bounds__(256) k_sort_alloc(SortArgs a) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  for (int i0 = 0; i0 < it.z; i0 += 128) {
-    const int i = i0 + threadIdx.x;
-    int c = -1, n = 0, n_tasks = 0;
-    int arr[4];
-    if (i < it.z && a.bt.codes[p0 + i] != 0) {
-      c = a.bt.ent_col[p0 + i];
-      if (atomicExch(&a.claimed[c], 1) == 0) {          // this entry speaks for its column
-        n = a.cnt[c];
-        const int any = a.codeor[c];
-        if (!a.dense) {
-          if (a.do_dec && (any & CODE_TGT)) arr[n_tasks++] = 0;
-          if (a.do_enc)
-            for (int blk = 0; blk < a.nblk; ++blk) {
-              const int bit = blk == 0 ? a.bits3.x : (blk == 1 ? a.bits3.y : a.bits3.z);
-              if (any & bit) arr[n_tasks++] = 1 + blk;
-            }
+  int n = 0, n_tasks = 0;
+  int arr[4];
+  if (c < a.n_cols) {
+    n = a.cnt[c];
+    if (n > 0 && !a.dense) {
+      const int any = a.codeor[c];
+      if (a.do_dec && (any & CODE_TGT)) arr[n_tasks++] = 0;
+      if (a.do_enc)
+        for (int blk = 0; blk < a.nblk; ++blk) {
+          const int bit = blk == 0 ? a.bits3.x : (blk == 1 ? a.bits3.y : a.bits3.z);
+          if (any & bit) arr[n_tasks++] = 1 + blk;
         }
-      } else c = -1;
-    }
-    // one atomic per warp and counter: exclusive prefix of (matches, tasks, columns) over the lanes
-    int sn = n, stk = n_tasks, sc = c >= 0 ? 1 : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t0 = __shfl_up_sync(FULL, sn, o), t1 = __shfl_up_sync(FULL, stk, o), t2 = __shfl_up_sync(FULL, sc, o);
-      if (lane >= o) { sn += t0; stk += t1; sc += t2; }
-    }
-    int b0 = 0, b1 = 0, b2 = 0;
-    if (lane == 31) {
-      if (sn) b0 = atomicAdd(&a.counters[0], sn);
-      if (stk) b1 = atomicAdd(&a.counters[1], stk);
-      if (sc) b2 = atomicAdd(&a.counters[2], sc);
-    }
-    b0 = __shfl_sync(FULL, b0, 31); b1 = __shfl_sync(FULL, b1, 31); b2 = __shfl_sync(FULL, b2, 31);
-    if (c >= 0) {
-      const int base = b0 + sn - n, slot = b1 + stk - n_tasks, row = b2 + sc - 1;
-      a.colinfo[c] = make_int4(base, n, row, 0);
-      if (a.dense) a.colseg[c] = make_int2(base, n);
-      for (int k = 0; k < n_tasks; ++k) a.tasks[slot + k] = make_int4(c, arr[k], base, n);
     }
   }
-}
-
-__global__ void __launch_bounds__(128) k_sort_bits(SortArgs a) {
-  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
-  const int4 it = a.bt.items[blockIdx.x];
-  const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
-  for (int i = threadIdx.x; i < it.z; i += 128) {
-    if (a.bt.codes[p0 + i] == 0) continue;
-    const int row = a.colinfo[a.bt.ent_col[p0 + i]].z;
-    atomicOr(&a.bits[(size_t)row * a.W + (b >> 5)], 1u << (b & 31));
+  if (__ballot_sync(FULL, n > 0) == 0u) return;
+  int sn = n, stk = n_tasks;                 // inclusive prefix over the lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t0 = __shfl_up_sync(FULL, sn, o), t1 = __shfl_up_sync(FULL, stk, o);
+    if (lane >= o) { sn += t0; stk += t1; }
+  }
+  int b0 = 0, b1 = 0;
+  if (lane == 31) {
+    b0 = atomicAdd(&a.counters[0], sn);
+    if (stk) b1 = atomicAdd(&a.counters[1], stk);
+  }
+  b0 = __shfl_sync(FULL, b0, 31); b1 = __shfl_sync(FULL, b1, 31);
+  if (n > 0) {
+    const int base = b0 + sn - n, slot = b1 + stk - n_tasks;
+    a.colinfo[c] = make_int2(base, n);
+    if (a.dense) a.colseg[c] = make_int2(base, n);
+    for (int k = 0; k < n_tasks; ++k) a.tasks[slot + k] = make_int4(c, arr[k], base, n);
   }
 }
 
@@ -1080,8 +1091,9 @@ __global__ void __launch_bounds__(128) k_sort_place(SortArgs a) {
     const int p = p0 + i;
     const uint32_t code = a.bt.codes[p];
     if (code == 0) continue;
-    const int4 info = a.colinfo[a.bt.ent_col[p]];
-    const uint32_t* bw = a.bits + (size_t)info.z * a.W;
+    const int c = a.bt.ent_col[p];
+    const int2 info = a.colinfo[c];
+    const uint32_t* bw = a.bits + (size_t)c * a.W;
     int rank = __popc(bw[b >> 5] & ((1u << (b & 31)) - 1u));
     for (int w = 0; w < (b >> 5); ++w) rank += __popc(bw[w]);
     const size_t idx = (size_t)(info.x + rank);
