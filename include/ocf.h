@@ -109,16 +109,31 @@ int ocf_batch_fill_split_uniform(ocf_batch* batch, const ocf_store* store, const
 /* The reference draws its reciprocal-dropout split from NumPy's global MT19937 stream
  * (np.random.uniform at data_reader.py:120, np.random.choice at :130). An ocf_rng holds that
  * stream on the device: set_state takes RandomState.get_state()[1:3] (key[624], pos), get_state
- * returns them after waiting for the generator. The stream advances on its own CUDA stream, so the
- * draws of the next batch are produced while the current step computes. */
-int ocf_rng_create(ocf_rng** out);
+ * returns them at the consumers' position. The stream is produced ahead of its consumers, in blocks of
+ * `block_regens` regenerations of the 624-word array, by `workers` generator CTAs on their own CUDA
+ * streams: worker j makes blocks j, j + workers, ... and skips the others' blocks with a GF(2)
+ * polynomial jump - bit for bit the sequential stream, at `workers` times the rate of one chain.
+ * The blocks live in a ring of at least ring_words_min words (+ room for the blocks in flight); a
+ * batch larger than the ring makes it grow. */
+int ocf_rng_create(ocf_rng** out);                        /* workers = $OCF_RNG_WORKERS or 2, blocks of 256 regenerations */
+int ocf_rng_configure(ocf_rng* rng, int32_t workers, int32_t block_regens, int64_t ring_words_min);   /* <= 0: keep; keeps the stream state */
 int ocf_rng_destroy(ocf_rng* rng);
 int ocf_rng_set_state(ocf_rng* rng, const uint32_t* key, int32_t pos);
 int ocf_rng_get_state(ocf_rng* rng, uint32_t* key, int32_t* pos);
-/* Advances the stream by n_draws doubles (a batch the generator drew but nobody consumed). */
+/* Advances the consumers' position by n_draws doubles (a batch the generator drew but nobody consumed). */
 int ocf_rng_skip(ocf_rng* rng, int64_t n_draws);
-/* SM cycles and nanoseconds the generator kernel's last launch took (synchronises its stream). */
+/* Makes sure the blocks holding the next n_draws doubles are being generated (as far as the ring has room). */
+int ocf_rng_prefetch(ocf_rng* rng, int64_t n_draws);
+/* info[0..5] = workers, block_regens, ring blocks, ring words, consumers' position (words), blocks enqueued. */
+int ocf_rng_info(const ocf_rng* rng, int64_t info[6]);
+/* SM cycles and nanoseconds the last block-generation kernel took (synchronises the workers). */
 int ocf_rng_last_timing(ocf_rng* rng, int64_t* sm_cycles, int64_t* nanoseconds);
+/* Host side of the jump (no GPU needed): poly624 = x^n_words mod phi(x) as 624 32-bit words (phi = the
+ * characteristic polynomial of MT19937's word recurrence, recovered by Berlekamp-Massey), and the array n_words
+ * further down the stream than key624, computed the way the device kernel does (word 0 exact in its top bit only,
+ * the only bit of it MT19937 reads). */
+int ocf_mt_jump_poly(int64_t n_words, uint32_t* poly624);
+int ocf_mt_jump_apply_host(const uint32_t* key624, const uint32_t* poly624, uint32_t* out624);
 /* Column shards: orig_pos[e] = position of the shard's store entry e inside its full row. */
 int ocf_store_set_orig_pos(ocf_store* store, const int32_t* orig_pos);
 /* build_sparse_batch (data_reader.py:95-200) with the random split drawn ON THE DEVICE, bit for

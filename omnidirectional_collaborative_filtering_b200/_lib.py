@@ -71,6 +71,11 @@ _SIGNATURES = {
     "ocf_rng_set_state": (C.c_int, [_P, _P, C.c_int32]),
     "ocf_rng_get_state": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "ocf_rng_skip": (C.c_int, [_P, C.c_int64]),
+    "ocf_rng_prefetch": (C.c_int, [_P, C.c_int64]),
+    "ocf_rng_configure": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64]),
+    "ocf_rng_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "ocf_mt_jump_poly": (C.c_int, [C.c_int64, _P]),
+    "ocf_mt_jump_apply_host": (C.c_int, [_P, _P, _P]),
     "ocf_rng_last_timing": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ocf_store_set_orig_pos": (C.c_int, [_P, _P]),
     "ocf_batch_fill_split_rng": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, _P, C.c_int, C.c_float,

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "ocf_kernels.cuh"
+#include "ocf_mtjump.h"
 #include "ocf_score_tc.cuh"
 #include "ocf_peer.cuh"
 #include "ocf_topk.cuh"
@@ -130,13 +131,33 @@ struct ocf_store {
   Arena mem;
 };
 
-// NumPy's MT19937 stream held on the device (624-word key + position), advanced by k_mt_words on
-// its own stream so that the draws of batch i+1 are generated while step i computes.
+// NumPy's MT19937 stream as a service on the device. The stream is addressed by absolute word position u, counted
+// from the start of the ORIGIN array (the 624-word key of the last set_state; its words are u = 0..623, the stream
+// continues at u = pos). Regeneration g >= 1 of the origin array is words [624 g, 624 g + 624). Blocks of C
+// regenerations (block k = regenerations 1 + kC .. (k+1)C) are produced by M worker CTAs: worker k % M makes block k
+// on its own CUDA stream and then jumps its array over the other workers' M - 1 blocks (k_mt_jump_apply). All words
+// land in one ring of R blocks, addressed (u mod ring words). The host only keeps positions: which blocks are
+// enqueued, how far the consumers have read, which event guards which ring slot.
 struct ocf_rng {
-  uint32_t* d_state = nullptr;     // [625]
-  cudaStream_t stream = nullptr;
   int device = 0;
+  int M = 1, C = 256, R = 16;                   // workers, regenerations per block, ring blocks
+  int64_t BW = 0, RW = 0;                       // words per block / in the ring
+  uint32_t* d_ring = nullptr;
+  uint32_t* d_arrays = nullptr;                 // [M][2][640] worker arrays (double-buffered by the jumps) + timing words
+  uint32_t* d_seq = nullptr;                    // [M][33 * 624] sequence a jump reads
+  uint32_t* d_poly = nullptr;                   // [2][624]: x^(624 C) (placement), x^(624 C (M-1)) (steady state)
+  std::vector<cudaStream_t> wstream;
+  std::vector<cudaEvent_t> block_ev, slot_free;
+  std::vector<char> slot_free_valid;
+  std::vector<int> cur;                         // which of its two array buffers worker j holds
+  cudaEvent_t placed = nullptr;
+  int64_t next_block = 0;                       // first block not enqueued yet
+  int64_t pos_u = 0;                            // consumers' position (absolute word)
+  uint32_t origin[624] = {0};
+  bool have_state = false;
+  int last_worker = 0;
   Arena mem;
+  uint32_t* array_of(int j, int which) const { return d_arrays + ((size_t)j * 2 + which) * 640; }
 };
 
 struct ocf_pair {
@@ -172,13 +193,12 @@ struct ocf_batch {
   int64_t target_count = 0;
   size_t last_h2d = 0;
   std::vector<uint8_t> flag_scratch;
-  // device-RNG mode: this batch's slice of the MT19937 stream and the per-row cdf
-  uint32_t* d_words = nullptr;
-  int64_t words_cap = 0;           // in draws (2 words each)
+  // device-RNG mode: where this batch's draws sit in the generator's stream ring, and the per-row cdf
+  const uint32_t* d_words = nullptr;   // the ring (owned by the ocf_rng)
+  uint32_t word_base = 0, ring_words = 0;
   double rng_lo = 0.0, rng_range = 0.0;
   int64_t draw_base = 0;           // index of the batch's first per-rating draw in its slice of the stream
   int cdf0_row0 = 0;               // row-parallel slice: index of the batch's first row among the sparsity draws
-  cudaEvent_t words_ready = nullptr, gathered = nullptr;
   bool rng_mode = false;
   Arena mem;
 };
@@ -582,9 +602,6 @@ extern "C" int ocf_batch_destroy(ocf_batch* b) {
     if (b->d_rowslot) cudaFree(b->d_rowslot);
     if (b->h_staging) cudaFreeHost(b->h_staging);
     if (b->copied) cudaEventDestroy(b->copied);
-    if (b->d_words) cudaFree(b->d_words);
-    if (b->words_ready) cudaEventDestroy(b->words_ready);
-    if (b->gathered) cudaEventDestroy(b->gathered);
     delete b;
   }
   return OCF_OK;
@@ -652,6 +669,7 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
   h_hdr->B = n_rows; h_hdr->n_items = (int)n_items; h_hdr->n_entries = (int)total;
   h_hdr->tag = hdr_tag; h_hdr->cdf_row0 = b->cdf0_row0; h_hdr->pass_through = hdr_pass_through;
   h_hdr->rng_lo = b->rng_lo; h_hdr->rng_range = b->rng_range; h_hdr->aux_value = hdr_aux;
+  h_hdr->word_base = b->word_base; h_hdr->ring_words = b->ring_words;
   if (flags != nullptr && total > 0) std::memcpy(hs + off[7], flags, (size_t)total);
   OCF_CUDA(cudaMemcpyAsync(b->d_staging, hs, bytes, cudaMemcpyHostToDevice, stream));
   OCF_CUDA(cudaEventRecord(b->copied, stream));
@@ -748,51 +766,187 @@ extern "C" int ocf_batch_regather(ocf_batch* b, void* stream_) {
 }
 
 // ---- NumPy MT19937 on the device ------------------------------------------------------------------
+static void rng_release(ocf_rng* r) {
+  for (cudaStream_t st : r->wstream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (cudaEvent_t e : r->block_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : r->slot_free) cudaEventDestroy(e);
+  if (r->placed) cudaEventDestroy(r->placed);
+  r->wstream.clear(); r->block_ev.clear(); r->slot_free.clear(); r->placed = nullptr;
+  r->mem.release();
+  r->d_ring = r->d_arrays = r->d_seq = r->d_poly = nullptr;
+}
+
+// (Re)builds the service: `workers` generator CTAs, blocks of `block_regens` regenerations, a ring of at least
+// `ring_words_min` words. Drops whatever stream state the object held (set_state must follow).
+static int rng_setup(ocf_rng* r, int workers, int block_regens, int64_t ring_words_min) {
+  OCF_REQUIRE(workers >= 1 && workers <= 32 && block_regens >= 1 && block_regens <= (1 << 16), "ocf_rng_configure: workers must be 1..32, block_regens 1..65536");
+  OCF_CUDA(cudaSetDevice(r->device));
+  rng_release(r);
+  r->M = workers; r->C = block_regens;
+  r->BW = (int64_t)block_regens * 624;
+  // room for the batch being read, the batch being generated and every worker's block in flight
+  const int64_t want = std::max<int64_t>(ring_words_min, 4 * r->BW) + (int64_t)(2 * workers + 2) * r->BW;
+  r->R = (int)((want + r->BW - 1) / r->BW);
+  r->RW = (int64_t)r->R * r->BW;
+  OCF_REQUIRE(r->RW < (int64_t(1) << 31), "ocf_rng_configure: ring too large");
+  if (workers > 1) {
+    OCF_REQUIRE(mtj::phi_ok(), "ocf_rng_configure: could not recover MT19937's characteristic polynomial");
+    uint32_t poly[2][624];
+    mtj::to_words(mtj::x_pow((uint64_t)r->BW), poly[0]);
+    mtj::to_words(mtj::x_pow((uint64_t)r->BW * (uint64_t)(workers - 1)), poly[1]);
+    OCF_TRY(r->mem.get(&r->d_poly, 2 * 624));
+    OCF_CUDA(cudaMemcpy(r->d_poly, poly, sizeof(poly), cudaMemcpyHostToDevice));
+    OCF_TRY(r->mem.get(&r->d_seq, (size_t)workers * MT_SEQ_REGENS * 624));
+  }
+  OCF_TRY(r->mem.get(&r->d_ring, (size_t)r->RW));
+  OCF_TRY(r->mem.get(&r->d_arrays, (size_t)workers * 2 * 640, true));
+  r->wstream.resize(workers); r->cur.assign(workers, 0);
+  for (int j = 0; j < workers; ++j) OCF_CUDA(cudaStreamCreateWithFlags(&r->wstream[j], cudaStreamNonBlocking));
+  r->block_ev.resize(r->R); r->slot_free.resize(r->R); r->slot_free_valid.assign(r->R, 0);
+  for (int k = 0; k < r->R; ++k) {
+    OCF_CUDA(cudaEventCreateWithFlags(&r->block_ev[k], cudaEventDisableTiming));
+    OCF_CUDA(cudaEventCreateWithFlags(&r->slot_free[k], cudaEventDisableTiming));
+  }
+  OCF_CUDA(cudaEventCreateWithFlags(&r->placed, cudaEventDisableTiming));
+  r->have_state = false; r->next_block = 0; r->pos_u = 0;
+  return OCF_OK;
+}
+
 extern "C" int ocf_rng_create(ocf_rng** out) {
   OCF_REQUIRE(out != nullptr, "ocf_rng_create: null argument");
   *out = nullptr;
   ocf_rng* r = new ocf_rng();
   if (cudaGetDevice(&r->device) != cudaSuccess) { cudaGetLastError(); delete r; return fail(OCF_ERR_CUDA, "ocf_rng_create: no CUDA device"); }
-  int st = r->mem.get(&r->d_state, 640, true);
-  if (st) { delete r; return st; }
-  if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) { r->mem.release(); delete r; return fail(OCF_ERR_CUDA, "ocf_rng_create: stream creation failed"); }
+  int workers = 2;
+  if (const char* e = std::getenv("OCF_RNG_WORKERS")) workers = std::max(1, std::min(32, std::atoi(e)));
+  const int st = rng_setup(r, workers, 256, 0);
+  if (st) { rng_release(r); delete r; return st; }
   *out = r;
   return OCF_OK;
 }
 
+extern "C" int ocf_rng_configure(ocf_rng* r, int32_t workers, int32_t block_regens, int64_t ring_words_min) {
+  OCF_REQUIRE(r != nullptr, "ocf_rng_configure: null argument");
+  if (workers <= 0) workers = r->M;
+  if (block_regens <= 0) block_regens = r->C;
+  // nothing to do when the current ring already satisfies the request
+  if (workers == r->M && block_regens == r->C && std::max<int64_t>(ring_words_min, 4 * r->BW) + (int64_t)(2 * workers + 2) * r->BW <= r->RW)
+    return OCF_OK;
+  uint32_t key[624]; int32_t pos = 0;
+  const bool keep = r->have_state;
+  if (keep) OCF_TRY(ocf_rng_get_state(r, key, &pos));
+  OCF_TRY(rng_setup(r, workers, block_regens, ring_words_min));
+  if (keep) OCF_TRY(ocf_rng_set_state(r, key, pos));
+  return OCF_OK;
+}
+
+extern "C" int ocf_rng_info(const ocf_rng* r, int64_t info[6]) {
+  OCF_REQUIRE(r && info, "ocf_rng_info: null argument");
+  info[0] = r->M; info[1] = r->C; info[2] = r->R; info[3] = r->RW; info[4] = r->pos_u; info[5] = r->next_block;
+  return OCF_OK;
+}
+
 extern "C" int ocf_rng_destroy(ocf_rng* r) {
-  if (r) { if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); } r->mem.release(); delete r; }
+  if (r) { cudaSetDevice(r->device); rng_release(r); delete r; }
+  return OCF_OK;
+}
+
+// array `src` of worker j jumped by polynomial `which` into its other buffer, on stream st
+static int rng_jump(ocf_rng* r, int j, const uint32_t* src, uint32_t* dst, int which, cudaStream_t st) {
+  uint32_t* seq = r->d_seq + (size_t)j * MT_SEQ_REGENS * 624;
+  OCF_CUDA(cudaMemcpyAsync(seq, src, 624 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  OCF_CUDA(cudaMemcpyAsync(dst, src, 624 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));      // scratch copy the block kernel advances
+  k_mt_block<false><<<1, MT_THREADS, 0, st>>>(dst, MT_SEQ_REGENS - 1, seq, (uint32_t)(MT_SEQ_REGENS * 624), 624u);
+  OCF_LAUNCHED();
+  OCF_CUDA(cudaMemsetAsync(dst, 0, 624 * sizeof(uint32_t), st));
+  k_mt_jump_apply<<<MT_JUMP_CTAS, MT_THREADS, 0, st>>>(seq, r->d_poly + (size_t)which * 624, dst);
+  OCF_LAUNCHED();
   return OCF_OK;
 }
 
 extern "C" int ocf_rng_set_state(ocf_rng* r, const uint32_t* key, int32_t pos) {
   OCF_REQUIRE(r && key && pos >= 0 && pos <= 624, "ocf_rng_set_state: bad argument");
-  uint32_t tmp[625];
-  std::memcpy(tmp, key, sizeof(uint32_t) * 624);
-  tmp[624] = (uint32_t)pos;
   OCF_CUDA(cudaSetDevice(r->device));        // generator threads call this too
-  OCF_CUDA(cudaMemcpyAsync(r->d_state, tmp, sizeof(tmp), cudaMemcpyHostToDevice, r->stream));
-  OCF_CUDA(cudaStreamSynchronize(r->stream));
+  for (cudaStream_t st : r->wstream) OCF_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(r->origin, key, sizeof(r->origin));
+  r->pos_u = pos; r->next_block = 0; r->have_state = true;
+  std::fill(r->slot_free_valid.begin(), r->slot_free_valid.end(), 0);
+  std::fill(r->cur.begin(), r->cur.end(), 0);
+  // the origin array's own (tempered) words are stream words 0..623
+  uint32_t tempered[624];
+  for (int i = 0; i < 624; ++i) tempered[i] = mtj::temper(key[i]);
+  cudaStream_t s0 = r->wstream[0];
+  OCF_CUDA(cudaMemcpyAsync(r->d_ring, tempered, sizeof(tempered), cudaMemcpyHostToDevice, s0));
+  OCF_CUDA(cudaMemcpyAsync(r->array_of(0, 0), key, 624 * sizeof(uint32_t), cudaMemcpyHostToDevice, s0));
+  // worker j starts C regenerations after worker j - 1
+  for (int j = 1; j < r->M; ++j) OCF_TRY(rng_jump(r, j, r->array_of(j - 1, 0), r->array_of(j, 0), 0, s0));
+  OCF_CUDA(cudaStreamSynchronize(s0));       // `tempered` / `key` are stack / caller memory
   return OCF_OK;
+}
+
+// Enqueues the generation of every block up to `upto` (inclusive) that the ring has room for. A block's slot is
+// reused once the consumers have read past the block that last lived in it.
+static int rng_enqueue_blocks(ocf_rng* r, int64_t upto) {
+  while (r->next_block <= upto) {
+    const int64_t k = r->next_block;
+    const int64_t evicted_end = 624 + (k - r->R + 1) * r->BW;       // end of the block this one overwrites
+    if (k >= r->R && evicted_end > r->pos_u) break;                 // its words are not consumed yet
+    const int j = (int)(k % r->M), slot = (int)(k % r->R);
+    cudaStream_t st = r->wstream[j];
+    if (r->slot_free_valid[slot]) OCF_CUDA(cudaStreamWaitEvent(st, r->slot_free[slot], 0));
+    uint32_t* arr = r->array_of(j, r->cur[j]);
+    const uint32_t off = (uint32_t)((624 + k * r->BW) % r->RW);
+    k_mt_block<true><<<1, MT_THREADS, 0, st>>>(arr, r->C, r->d_ring, (uint32_t)r->RW, off);
+    OCF_LAUNCHED();
+    OCF_CUDA(cudaEventRecord(r->block_ev[slot], st));
+    if (r->M > 1) {                                                 // over the other workers' blocks
+      OCF_TRY(rng_jump(r, j, arr, r->array_of(j, r->cur[j] ^ 1), 1, st));
+      r->cur[j] ^= 1;
+    }
+    r->last_worker = j;
+    r->next_block += 1;
+  }
+  return OCF_OK;
+}
+
+static inline int64_t rng_block_of(const ocf_rng* r, int64_t u) { return u < 624 ? -1 : (u - 624) / r->BW; }
+
+extern "C" int ocf_rng_prefetch(ocf_rng* r, int64_t n_draws) {
+  OCF_REQUIRE(r && n_draws >= 0, "ocf_rng_prefetch: bad argument");
+  if (!r->have_state) return fail(OCF_ERR_STATE, "ocf_rng_prefetch: no stream state (ocf_rng_set_state first)");
+  OCF_CUDA(cudaSetDevice(r->device));
+  return rng_enqueue_blocks(r, rng_block_of(r, r->pos_u + 2 * n_draws));
 }
 
 extern "C" int ocf_rng_get_state(ocf_rng* r, uint32_t* key, int32_t* pos) {
   OCF_REQUIRE(r && key && pos, "ocf_rng_get_state: null argument");
-  uint32_t tmp[625];
+  if (!r->have_state) return fail(OCF_ERR_STATE, "ocf_rng_get_state: no stream state");
   OCF_CUDA(cudaSetDevice(r->device));
-  OCF_CUDA(cudaMemcpyAsync(tmp, r->d_state, sizeof(tmp), cudaMemcpyDeviceToHost, r->stream));
-  OCF_CUDA(cudaStreamSynchronize(r->stream));
-  std::memcpy(key, tmp, sizeof(uint32_t) * 624);
-  *pos = (int32_t)tmp[624];
+  int64_t g = r->pos_u / 624;
+  int32_t p = (int32_t)(r->pos_u % 624);
+  if (p == 0 && g > 0) { g -= 1; p = 624; }          // NumPy regenerates lazily: "array g - 1, exhausted"
+  *pos = p;
+  if (g == 0) { std::memcpy(key, r->origin, sizeof(r->origin)); return OCF_OK; }
+  const int64_t k = (g - 1) / r->C;                  // the block regeneration g lives in
+  OCF_TRY(rng_enqueue_blocks(r, k));
+  if (r->next_block <= k) return fail(OCF_ERR_STATE, "ocf_rng_get_state: the stream position lies beyond the ring");
+  const int slot = (int)(k % r->R);
+  OCF_CUDA(cudaEventSynchronize(r->block_ev[slot]));
+  uint32_t tmp[624];
+  OCF_CUDA(cudaMemcpy(tmp, r->d_ring + (size_t)((624 * g) % r->RW), sizeof(tmp), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 624; ++i) key[i] = mtj::untemper(tmp[i]);
   return OCF_OK;
 }
 
 extern "C" int ocf_rng_last_timing(ocf_rng* r, int64_t* sm_cycles, int64_t* nanoseconds) {
   OCF_REQUIRE(r && sm_cycles && nanoseconds, "ocf_rng_last_timing: null argument");
-  uint32_t tmp[4];
   OCF_CUDA(cudaSetDevice(r->device));
-  OCF_CUDA(cudaMemcpyAsync(tmp, r->d_state + 626, sizeof(tmp), cudaMemcpyDeviceToHost, r->stream));
-  OCF_CUDA(cudaStreamSynchronize(r->stream));
+  for (cudaStream_t st : r->wstream) OCF_CUDA(cudaStreamSynchronize(st));
+  // a worker's timing words sit in the buffer its last block kernel ran on
+  const int j = r->last_worker;
+  uint32_t tmp[4];
+  const int which = r->M > 1 ? r->cur[j] ^ 1 : r->cur[j];
+  OCF_CUDA(cudaMemcpy(tmp, r->array_of(j, which) + 626, sizeof(tmp), cudaMemcpyDeviceToHost));
   *sm_cycles = (int64_t)(((uint64_t)tmp[1] << 32) | tmp[0]);
   *nanoseconds = (int64_t)(((uint64_t)tmp[3] << 32) | tmp[2]);
   return OCF_OK;
@@ -800,10 +954,21 @@ extern "C" int ocf_rng_last_timing(ocf_rng* r, int64_t* sm_cycles, int64_t* nano
 
 extern "C" int ocf_rng_skip(ocf_rng* r, int64_t n_draws) {
   OCF_REQUIRE(r && n_draws >= 0, "ocf_rng_skip: bad argument");
-  if (n_draws == 0) return OCF_OK;
-  OCF_CUDA(cudaSetDevice(r->device));
-  k_mt_words<<<1, MT_THREADS, 0, r->stream>>>(r->d_state, 2 * (long long)n_draws, nullptr);
-  OCF_LAUNCHED();
+  if (!r->have_state) return fail(OCF_ERR_STATE, "ocf_rng_skip: no stream state");
+  r->pos_u += 2 * n_draws;                           // positions only: the workers produce every block anyway
+  return OCF_OK;
+}
+
+// host-side helpers of the jump (tests pin the polynomial arithmetic against NumPy without a GPU)
+extern "C" int ocf_mt_jump_poly(int64_t n_words, uint32_t* poly624) {
+  OCF_REQUIRE(n_words >= 0 && poly624, "ocf_mt_jump_poly: bad argument");
+  OCF_REQUIRE(mtj::phi_ok(), "ocf_mt_jump_poly: could not recover MT19937's characteristic polynomial");
+  mtj::to_words(mtj::x_pow((uint64_t)n_words), poly624);
+  return OCF_OK;
+}
+extern "C" int ocf_mt_jump_apply_host(const uint32_t* key624, const uint32_t* poly624, uint32_t* out624) {
+  OCF_REQUIRE(key624 && poly624 && out624, "ocf_mt_jump_apply_host: null argument");
+  mtj::apply_host(key624, poly624, out624);
   return OCF_OK;
 }
 
@@ -861,23 +1026,16 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
     draws = slice->draws_total;
   }
   OCF_REQUIRE(draws < (int64_t(1) << 30), "ocf_batch_fill_split_rng: too many draws in one batch");
-  if (!b->words_ready) {
-    OCF_CUDA(cudaEventCreateWithFlags(&b->words_ready, cudaEventDisableTiming));
-    OCF_CUDA(cudaEventCreateWithFlags(&b->gathered, cudaEventDisableTiming));
-  }
+  if (!rng->have_state) return fail(OCF_ERR_STATE, "ocf_batch_fill_split_rng: the generator has no stream state (ocf_rng_set_state first)");
+  OCF_CUDA(cudaSetDevice(rng->device));
   b->rng_lo = lo; b->rng_range = hi - lo;
-  if (draws > b->words_cap) {
-    if (b->d_words) { OCF_CUDA(cudaDeviceSynchronize()); cudaFree(b->d_words); b->d_words = nullptr; }
-    const int64_t cap = std::max<int64_t>(draws + draws / 4, b->max_rows + b->max_entries);
-    OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_words), sizeof(uint32_t) * (2 * (size_t)cap + MT_HDR + 4 + MT_SLACK)));
-    b->words_cap = cap;
-  }
-  // the previous batch staged in this object may still be reading its words (no-op before the first gather)
-  OCF_CUDA(cudaStreamWaitEvent(rng->stream, b->gathered, 0));
-  // the stream's next `draws` doubles, generated beside whatever `stream` is running
-  k_mt_words<<<1, MT_THREADS, 0, rng->stream>>>(rng->d_state, 2 * (long long)draws, b->d_words);
-  OCF_LAUNCHED();
-  OCF_CUDA(cudaEventRecord(b->words_ready, rng->stream));
+  // this batch's words are [u0, u1) of the stream; grow the ring if one batch does not fit it comfortably
+  if (4 * draws + (int64_t)(2 * rng->M + 2) * rng->BW > rng->RW) OCF_TRY(ocf_rng_configure(rng, rng->M, rng->C, 6 * draws));
+  const int64_t u0 = rng->pos_u, u1 = u0 + 2 * draws;
+  const int64_t kb0 = rng_block_of(rng, u0), kb1 = rng_block_of(rng, u1 - 1);
+  OCF_TRY(rng_enqueue_blocks(rng, kb1));
+  if (rng->next_block <= kb1) return fail(OCF_ERR_STATE, "ocf_batch_fill_split_rng: the stream ring is too small for this batch");
+  b->d_words = rng->d_ring; b->word_base = (uint32_t)(u0 % rng->RW); b->ring_words = (uint32_t)rng->RW;
   OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split_rng"));
   OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, nullptr, -1, stream,
                       b->tag, pass_through ? 1 : 0, aux_var_value, true, full_len));
@@ -886,9 +1044,16 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
   b->mode = 1; b->store = store; b->aux_value = aux_var_value; b->rng_mode = true;
   b->pass_through = pass_through ? 1 : 0;
   b->target_count = pass_through ? b->dev.n_entries : -1;      // the flags never visit the host
-  OCF_CUDA(cudaStreamWaitEvent(stream, b->words_ready, 0));
+  // the gather waits for the blocks it reads; the ring slots it read are free again once it has run
+  for (int64_t k = std::max<int64_t>(kb0, 0); k <= kb1; ++k) OCF_CUDA(cudaStreamWaitEvent(stream, rng->block_ev[k % rng->R], 0));
   OCF_TRY(launch_gather(b, stream));
-  OCF_CUDA(cudaEventRecord(b->gathered, stream));
+  for (int64_t k = std::max<int64_t>(kb0, 0); k <= kb1; ++k) {
+    OCF_CUDA(cudaEventRecord(rng->slot_free[k % rng->R], stream));
+    rng->slot_free_valid[k % rng->R] = 1;
+  }
+  rng->pos_u = u1;
+  // keep the workers one round of blocks ahead of the consumers
+  OCF_TRY(rng_enqueue_blocks(rng, kb1 + rng->M));
   return OCF_OK;
 }
 

@@ -84,7 +84,9 @@ struct BatchHdr {
   int pass_through;
   double rng_lo, rng_range;  // np.random.uniform(lo, hi) of the rows' sparsity draws (range = hi - lo)
   float aux_value;
-  int pad[5];
+  uint32_t word_base;        // device-RNG mode: ring position of the batch's first stream word
+  uint32_t ring_words;       //   size of the stream ring in words
+  int pad[3];
 };
 static_assert(sizeof(BatchHdr) == 64, "BatchHdr is one 64-byte block at the head of the staging buffer");
 
@@ -115,7 +117,7 @@ struct BatchDev {
   const int32_t* item_ptr;   // [B+1] items of row b
   const uint8_t* flags;      // [n_entries] keep flags (split mode)
   const int32_t* draw_off;   // [B] device-RNG mode: index of the row's first draw in the batch's slice of the stream
-  const uint32_t* words;     //     k_mt_words output: header + tempered MT19937 words of the batch's draws (2 per draw)
+  const uint32_t* words;     //     the generator's stream ring (tempered MT19937 words; 2 per draw)
   double rng_lo, rng_range;  //     np.random.uniform(lo, hi) of the rows' sparsity draws (range = hi - lo)
   int cdf_row0;              //     index of batch row 0 among the drawing unit's sparsity draws
   uint8_t* flags_out;        // [n_entries] == flags; written by K1 in device-RNG mode

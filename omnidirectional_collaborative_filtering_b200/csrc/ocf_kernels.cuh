@@ -29,7 +29,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // One CTA per work item (a chunk of <= CH ratings of one row); reads and writes are contiguous.
 // ============================================================================================
 // RNG = true: the keep flag of a rating is derived here from the batch's slice of the NumPy
-// MT19937 stream that k_mt_words left in HBM (draw d of the batch = words 2d, 2d+1), compared with
+// MT19937 stream the generator workers left in the stream ring (draw d of the batch = its words 2d, 2d+1), compared with
 // the row's cdf - what np.random.choice([0,1], n, p=[1-s, s]) returns (data_reader.py:130).
 // The flags are also written back so a caller can read them.
 template <bool RNG>
@@ -45,15 +45,22 @@ k_gather_split(StoreDev s, BatchDev bt) {
   const int p0 = bt.ent_off[b];
   if (start == 0 && threadIdx.x == 0 && bt.rowslot != nullptr) bt.rowslot[row] = (hd.tag << SLOT_BITS) | (uint32_t)b;
   const int d0 = RNG ? bt.draw_off[b] : 0;
-  // the batch's slice of the stream: 4 header words (word 0 = alignment shift), then the draws
-  const uint32_t* W = RNG ? bt.words + 4 + bt.words[0] : nullptr;
+  // the stream lives in a ring addressed by absolute position: word j of the batch's draws is ring word
+  // (word_base + j) mod ring_words (a batch is shorter than the ring, so one conditional subtraction wraps)
+  const uint32_t* W = RNG ? bt.words : nullptr;
+  auto draw = [&](size_t d) -> double {
+    uint32_t x0 = hd.word_base + 2u * (uint32_t)d, x1 = x0 + 1u;
+    if (x0 >= hd.ring_words) x0 -= hd.ring_words;
+    if (x1 >= hd.ring_words) x1 -= hd.ring_words;
+    return mt_double(W[x0], W[x1]);
+  };
   __shared__ double s_c0;
   if (RNG) {
     if (threadIdx.x == 0) {
       // the row's sparsity: draw (first row of the drawing unit + b) of np.random.uniform(lo, hi, size)
       // (data_reader.py:120), then the cdf np.random.choice builds from p = [1-s, s] (:130)
       const int r = hd.cdf_row0 + b;
-      const double u = mt_double(W[2 * r], W[2 * r + 1]);
+      const double u = draw((size_t)r);
       const double keep = __dadd_rn(hd.rng_lo, __dmul_rn(hd.rng_range, u));   // random_uniform: lower + range * next_double
       const double q0 = __dsub_rn(1.0, keep);
       s_c0 = __ddiv_rn(q0, __dadd_rn(q0, keep));                             // cdf = cumsum(p) / cumsum(p)[-1]
@@ -64,7 +71,7 @@ k_gather_split(StoreDev s, BatchDev bt) {
   auto flag_of = [&](int j) -> uint8_t {
     if (!RNG) return bt.flags[p0 + j];
     const size_t d = (size_t)(d0 + (s.orig_pos != nullptr ? s.orig_pos[src0 + j] : j));
-    return mt_double(W[2 * d], W[2 * d + 1]) >= c0 ? 1 : 0;
+    return draw(d) >= c0 ? 1 : 0;
   };
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
     const int j = start + i;
@@ -92,7 +99,7 @@ k_gather_split(StoreDev s, BatchDev bt) {
 }
 
 // ============================================================================================
-// NumPy's MT19937 stream on the device. One CTA owns the 624-word state. The recurrence
+// NumPy's MT19937 stream on the device. A worker CTA owns a 624-word array. The recurrence
 //   x[n] = x[n-227] ^ A(x[n-624], x[n-623])            (A = the "twist" of two neighbouring words)
 // only reaches 227 words back through a plain XOR, so inside one regeneration the chain can be
 // unrolled until it lands in the previous array: every new word is the XOR of at most three
@@ -101,17 +108,16 @@ k_gather_split(StoreDev s, BatchDev bt) {
 //   i <  454 : new[i] = A(i) ^ A(i-227) ^ old[i+170]
 //   i <  623 : new[i] = A(i) ^ A(i-227) ^ A(i-454) ^ old[i-57]
 //   i == 623 : new[623] = A(old[623], new[0]) ^ new[396]
-// all 624 of them independent: one barrier per regeneration (double-buffered in shared memory)
-// instead of three dependent sweeps, and every thread tempers and stores the words it produced.
-// The tempered words leave through a small ring in shared memory and TMA bulk stores
-// (cp.async.bulk shared -> global): ordinary global stores inside the loop made every barrier wait
-// for their acknowledgement (~0.3 us per regeneration, measured); the bulk copies run in the async
-// proxy and only the ring slot's reuse waits on them. `out` = 4 header words (word 0: the
-// alignment shift s in 0..3 that puts every regeneration on a 16-byte boundary), then word j of
-// the batch's draws at out[4 + s + j]; whole regenerations are stored, so `out` needs 1024 words of
-// slack. The batch's first draws are its np.random.uniform(lo, hi, size=B) (data_reader.py:120):
-// the gather kernel turns them into the rows' cdf.
-// state[0..623] = key, state[624] = pos (RandomState.get_state()[1:3]).
+// all 624 of them independent: two barriers per regeneration (twists evaluated once into shared
+// memory), and every thread tempers and stores the word it produced. The tempered words leave
+// through a small ring of slots in shared memory and TMA bulk stores (cp.async.bulk shared ->
+// global): ordinary global stores inside the loop made every barrier wait for their
+// acknowledgement; the bulk copies run in the async proxy and only a slot's reuse waits on them.
+// One CTA tops out at ~0.84 G draws/s (one dependency chain). The stream is therefore produced in
+// BLOCKS of a fixed number of regenerations by several worker CTAs side by side: worker j makes
+// blocks j, j + M, j + 2M, ... and between two of its blocks JUMPS over the others' blocks with
+// k_mt_jump_apply (GF(2) polynomial jump-ahead, ocf_mtjump.h). The result is the sequential
+// stream, bit for bit. Consumers (k_gather_split) address the ring by absolute stream position.
 // ============================================================================================
 __device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
   const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
@@ -132,8 +138,7 @@ __device__ __forceinline__ uint32_t mt_a(uint32_t cur, uint32_t nxt) {
 
 constexpr int MT_THREADS = 640;            // one word of a regeneration per thread (624 active)
 constexpr int MT_RING = 4;                 // regenerations in flight towards HBM
-constexpr int MT_HDR = 4;                  // header words in front of the draws
-constexpr int MT_SLACK = 1024;             // words an output buffer holds beyond header + draws
+constexpr int MT_SEQ_REGENS = 33;          // arrays a jump reads: 33 * 624 >= 19937 + 624 words of the worker's own sequence
 
 // One word of the new array from twists of the old one (see the derivation above). own = tw[i].
 __device__ __forceinline__ uint32_t mt_new_word(int i, uint32_t own, const uint32_t* __restrict__ o, const uint32_t* __restrict__ tw) {
@@ -143,81 +148,91 @@ __device__ __forceinline__ uint32_t mt_new_word(int i, uint32_t own, const uint3
   return mt_a(o[623], tw[0] ^ o[397]) ^ (tw[396] ^ tw[169] ^ o[566]);
 }
 
+// A block of the stream: `n_regen` regenerations continuing the 624-word array `state` (left at the array after
+// the last one). TEMPER: the tempered words (what NumPy hands out) go to the ring buffer `ring` of `ring_words`
+// words at word offset `off0` (a multiple of 4, every regeneration 16-byte aligned; a regeneration never straddles
+// the ring's end because ring_words is a multiple of 624) through shared-memory slots and TMA bulk stores. Without
+// TEMPER the raw arrays are appended to `ring` from off0 (the sequence a jump correlates with its polynomial).
+// state[626..629]: SM cycles and nanoseconds of the launch (ocf_rng_last_timing).
+template <bool TEMPER>
 __global__ void __launch_bounds__(MT_THREADS)
-k_mt_words(uint32_t* __restrict__ state, long long n_words, uint32_t* __restrict__ out) {
+k_mt_block(uint32_t* __restrict__ state, int n_regen, uint32_t* __restrict__ ring, uint32_t ring_words, uint32_t off0) {
   __shared__ __align__(16) uint32_t mt[2][624];
   __shared__ __align__(16) uint32_t tw[624];
-  __shared__ __align__(16) uint32_t ring[MT_RING][624];
+  __shared__ __align__(16) uint32_t slots[MT_RING][624];
   const int tid = threadIdx.x;
   const long long clk0 = clock64();
   unsigned long long ns0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
   for (int i = tid; i < 624; i += blockDim.x) mt[0][i] = state[i];
-  int pos = (int)state[624];
   int cur = 0;
   __syncthreads();
-  long long left = n_words;
-  uint32_t* dst = nullptr;
-  // what is left of the current array (plain stores), shifted so that the regenerations that
-  // follow start on a 16-byte boundary
-  {
-    const int take = pos < 624 ? (int)min((long long)(624 - pos), n_words) : 0;
-    if (out != nullptr) {
-      const int shift = (4 - (take & 3)) & 3;
-      if (tid == 0) out[0] = (uint32_t)shift;
-      dst = out + MT_HDR + shift;
-      for (int i = tid; i < take; i += blockDim.x) dst[i] = mt_temper(mt[0][pos + i]);
-      dst += take;
-    }
-    left -= take;
-    pos += take;
-  }
-  // Whole regenerations. A single CTA is bound by the latency of each thread's dependent
-  // instruction chain between the two barriers (measured: fewer, busier threads are slower), so
-  // every word gets its own thread and the shortest possible chain; nothing waits on HBM.
+  uint32_t off = off0;
+  // A single CTA is bound by the latency of each thread's dependent instruction chain between the two barriers
+  // (measured: fewer, busier threads are slower), so every word gets its own thread and the shortest chain.
   const int i = tid;
   const bool active = i < 624;
-  for (int g = 0; left > 0; ++g) {
+  for (int g = 0; g < n_regen; ++g) {
     const uint32_t* o = mt[cur];
     uint32_t* n = mt[cur ^ 1];
-    uint32_t* slot = ring[g % MT_RING];
+    uint32_t* slot = slots[g % MT_RING];
     uint32_t own = 0u;
     if (i < 623) { own = mt_a(o[i], o[i + 1]); tw[i] = own; }     // word 623 has no plain twist (it needs new[0])
-    if (out != nullptr && tid == 0 && g >= MT_RING)    // the bulk store that last read this slot has its data
+    if (tid == 0 && g >= MT_RING)                                  // the bulk store that last read this slot has its data
       asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(MT_RING - 1) : "memory");
     __syncthreads();
     if (active) {
       const uint32_t v = mt_new_word(i, own, o, tw);
       n[i] = v;
-      if (out != nullptr) {
-        slot[i] = mt_temper(v);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      }
+      slot[i] = TEMPER ? mt_temper(v) : v;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (out != nullptr && tid == 0) {
+    if (tid == 0) {
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                   ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(slot)), "r"(624u * 4u) : "memory");
+                   ::"l"(ring + off), "r"((uint32_t)__cvta_generic_to_shared(slot)), "r"(624u * 4u) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    const int lim = left < 624 ? (int)left : 624;
+    off += 624u;
+    if (off >= ring_words) off -= ring_words;
     cur ^= 1;
-    pos = lim;
-    left -= lim;
-    if (dst != nullptr) dst += 624;
   }
-  if (out != nullptr && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int k = tid; k < 624; k += blockDim.x) state[k] = mt[cur][k];
   if (tid == 0) {
-    state[624] = (uint32_t)pos;
-    // diagnostics of the last launch: SM cycles and nanoseconds it took (ocf_rng_last_timing)
     unsigned long long ns1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
     const unsigned long long cyc = (unsigned long long)(clock64() - clk0), ns = ns1 - ns0;
     state[626] = (uint32_t)cyc; state[627] = (uint32_t)(cyc >> 32);
     state[628] = (uint32_t)ns; state[629] = (uint32_t)(ns >> 32);
   }
+}
+
+// Jump of a worker's array by J words, J fixed by the polynomial g = x^J mod phi (ocf_mtjump.h):
+//   out[k] = XOR over the set bits i of g of seq[i + k],   seq = the worker's own untempered sequence
+// (seq[0..623] = its current array, then MT_SEQ_REGENS - 1 further arrays from k_mt_block<false>). CTA c takes bits
+// [624 c, 624 c + 624) of g with its slice of the sequence staged in shared memory; the partial arrays are combined
+// with integer XOR atomics (order-independent, so the result is exact and reproducible). out must be zeroed.
+constexpr int MT_JUMP_CTAS = 32;           // 32 * 624 = 19968 >= 19937 polynomial bits
+
+__global__ void __launch_bounds__(MT_THREADS)
+k_mt_jump_apply(const uint32_t* __restrict__ seq, const uint32_t* __restrict__ poly, uint32_t* __restrict__ out) {
+  __shared__ uint32_t s_seq[1248];
+  __shared__ uint32_t s_poly[20];            // 624 bits from bit0 (bit0 % 32 is 0 or 16) lie in exactly 20 words
+  const int tid = threadIdx.x;
+  const int bit0 = blockIdx.x * 624;
+  for (int k = tid; k < 1248; k += blockDim.x) s_seq[k] = seq[bit0 + k];
+  if (tid < 20) s_poly[tid] = (bit0 >> 5) + tid < 624 ? poly[(bit0 >> 5) + tid] : 0u;
+  __syncthreads();
+  if (tid >= 624) return;
+  uint32_t acc = 0u;
+  const int sh = bit0 & 31;
+  for (int b = 0; b < 624; ++b) {
+    const int pos = sh + b;
+    if ((s_poly[pos >> 5] >> (pos & 31)) & 1u) acc ^= s_seq[b + tid];
+  }
+  if (acc) atomicXor(&out[tid], acc);
 }
 
 // Fixed-split valid/test batches: a batch row is the input store's row followed by the target

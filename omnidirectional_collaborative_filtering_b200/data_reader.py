@@ -105,9 +105,32 @@ class DeviceRng(object):
             out = C.c_void_p()
             _lib.check(lib.ocf_rng_create(C.byref(out)))
             self.handle = out
+            # generator CTAs: one chain makes ~0.84 G draws/s; a rank of a multi-GPU run replays the whole global
+            # batch's draws, so it gets more workers ($OCF_RNG_WORKERS overrides)
+            import os
+            workers = os.environ.get("OCF_RNG_WORKERS")
+            if workers is None and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+                _lib.check(lib.ocf_rng_configure(self.handle, 8, 256, 0))
         key = np.ascontiguousarray(self.host_state[1], dtype=np.uint32)
         _lib.check(lib.ocf_rng_set_state(self.handle, _lib.ptr(key), int(self.host_state[2])))
         self.active = True
+
+    def configure(self, workers=0, block_regens=0, ring_words_min=0):
+        """Generator layout of the device stream (`ocf_rng_configure`): worker CTAs, regenerations per block, minimum
+        ring size in words; 0 keeps a value. The stream's state and position are kept."""
+        with self.lock:
+            lib = _lib.lib()
+            if self.handle is None:
+                _lib.require_gpu()
+                out = C.c_void_p()
+                _lib.check(lib.ocf_rng_create(C.byref(out)))
+                self.handle = out
+            _lib.check(lib.ocf_rng_configure(self.handle, int(workers), int(block_regens), int(ring_words_min)))
+
+    def info(self):
+        buf = (C.c_int64 * 6)()
+        _lib.check(_lib.lib().ocf_rng_info(self.handle, buf))
+        return dict(zip(("workers", "block_regens", "ring_blocks", "ring_words", "position_words", "blocks_enqueued"), list(buf)))
 
     def consume(self, ticket):
         """Called by the upload of a batch: positions the device stream at the batch's first draw
@@ -122,7 +145,9 @@ class DeviceRng(object):
                 if t >= ticket:
                     break
                 _lib.check(lib.ocf_rng_skip(self.handle, self.pending.pop(t)))   # drawn, never uploaded
-            self.pending.pop(ticket)
+            mine = self.pending.pop(ticket)
+            # the tickets already drawn tell how far the workers may run ahead of this batch
+            _lib.check(lib.ocf_rng_prefetch(self.handle, mine + sum(self.pending.values())))
             return self.handle
 
     def release(self):

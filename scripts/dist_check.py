@@ -43,13 +43,18 @@ def check(mode, native, rank, world):
                                train=dicts["train"], valid=tuple(dicts["valid"]), test=tuple(dicts["test"]))
     np.random.seed(7)
     gen = rd.data_gen(B, [0.4, 0.9], "train", True, "dropout", -1)
-    rgen = ref_batches.batch_stream(data, B, [0.4, 0.9], "train", True, "dropout", -1, rng=np.random.RandomState(7),
-                                    vectorised=True)
+    rng7 = np.random.RandomState(7)
+    rgen = ref_batches.batch_stream(data, B, [0.4, 0.9], "train", True, "dropout", -1, rng=rng7, vectorised=True)
     worst = 0.0
-    for step in range(5):
-        b = next(gen)
+    for step in range(9):          # ring of 3 batch buffers: plain launches, captured steps (NCCL inside the graph), replays
+        b, rb = next(gen), next(rgen)
+        if b is None:                  # the epoch is over (on both sides): a new generator each, like train.py:153
+            assert rb is None
+            gen = rd.data_gen(B, [0.4, 0.9], "train", True, "dropout", -1)
+            rgen = ref_batches.batch_stream(data, B, [0.4, 0.9], "train", True, "dropout", -1, rng=rng7, vectorised=True)
+            b, rb = next(gen), next(rgen)
         got = om.model.train_on_batch(b.row_slice(rank, world) if rows_mode else b)
-        feed, targets = next(rgen)
+        feed, targets = rb
         want = ref.train_on_batch(feed, targets)
         worst = max(worst, float(np.max(np.abs(np.array(got) - np.array(want)) / np.maximum(np.abs(want), 1e-6))))
     full = om.model.get_weights() if rows_mode else ocf_dist.gather_full_weights(om)

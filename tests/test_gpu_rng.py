@@ -1,4 +1,4 @@
-"""GPU parity of the device-resident NumPy stream (`k_mt_words` + `k_gather_split<RNG>`):
+"""GPU parity of the device-resident NumPy stream (block generator workers + polynomial jump-ahead + `k_gather_split<RNG>`):
 the keep flags a generator's batches get when MT19937 is replayed on the GPU are bit-identical to
 the ones `np.random.uniform` / `np.random.choice` give on the host (data_reader.py:120,130), and
 `np.random` ends in the same state."""
@@ -92,3 +92,44 @@ def test_reseeding_on_the_host_wins():
     bh = next(rh.data_gen(16, [0.2, 0.8], "train", True, None, -1))
     assert np.array_equal(got_rows, bh.rows) and np.array_equal(got_flags, bh.flags)
     rh.close()
+
+
+@pytest.mark.parametrize("workers,block_regens", [(1, 1), (2, 1), (3, 2), (4, 5), (8, 3), (8, 256), (5, 64)])
+def test_parallel_generator_workers_give_the_sequential_stream(workers, block_regens):
+    """The stream is cut into blocks of `block_regens` regenerations made by `workers` CTAs that jump over each other's
+    blocks (GF(2) polynomial jump-ahead). Tiny blocks and a small ring make every batch cross many blocks, every worker
+    jump many times and the ring wrap many times; the flags and the final np.random state must not notice."""
+    from omnidirectional_collaborative_filtering_b200.data_reader import DeviceRng
+    fs = synthetic.make_fixed_split("small", reverse_user_item_data=True, seed=6)
+    sync_host_rng()
+    DeviceRng.get().configure(workers, block_regens, 1)
+    try:
+        dev, dev_tail = _flags_of_epochs(fs, True, 64, [0.1, 0.9], False, seed=workers * 100 + block_regens, skip_every=4)
+        info = DeviceRng.get().info()
+        assert info["workers"] == workers and info["block_regens"] == block_regens
+        host, host_tail = _flags_of_epochs(fs, False, 64, [0.1, 0.9], False, seed=workers * 100 + block_regens, skip_every=4)
+        assert len(dev) == len(host) and len(dev) > 4
+        for (r0, f0), (r1, f1) in zip(dev, host):
+            assert np.array_equal(r0, r1) and np.array_equal(f0, f1)
+        assert np.array_equal(dev_tail, host_tail)
+        if block_regens <= 5:
+            assert info["blocks_enqueued"] > 3 * info["ring_blocks"]          # the ring wrapped several times
+    finally:
+        sync_host_rng()
+        DeviceRng.get().configure(2, 256, 0)
+
+
+def test_ring_grows_for_a_batch_larger_than_the_ring():
+    from omnidirectional_collaborative_filtering_b200.data_reader import DeviceRng
+    fs = synthetic.make_fixed_split("ml1m", reverse_user_item_data=True, seed=0)
+    sync_host_rng()
+    DeviceRng.get().configure(4, 2, 1)                    # ring of a few thousand words; a batch needs ~10^5
+    try:
+        dev, dev_tail = _flags_of_epochs(fs, True, 128, [0.3, 0.6], False, seed=3, epochs=1)
+        host, host_tail = _flags_of_epochs(fs, False, 128, [0.3, 0.6], False, seed=3, epochs=1)
+        for (r0, f0), (r1, f1) in zip(dev, host):
+            assert np.array_equal(r0, r1) and np.array_equal(f0, f1)
+        assert np.array_equal(dev_tail, host_tail)
+    finally:
+        sync_host_rng()
+        DeviceRng.get().configure(2, 256, 0)
