@@ -32,6 +32,13 @@ class _FakeLib(object):
         self.rs.random_sample(int(n))
         return 0
 
+    def ocf_rng_prefetch(self, handle, n):       # a hint: the real library starts generating ahead
+        self.prefetched = getattr(self, "prefetched", []) + [int(n)]
+        return 0
+
+    def ocf_rng_configure(self, handle, workers, block_regens, ring_words_min):
+        return 0
+
     def ocf_rng_get_state(self, handle, key_ptr, pos):
         st = self.rs.get_state()
         np.ctypeslib.as_array((C.c_uint32 * 624).from_address(key_ptr.value))[:] = st[1]

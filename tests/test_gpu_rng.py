@@ -113,7 +113,7 @@ def test_parallel_generator_workers_give_the_sequential_stream(workers, block_re
             assert np.array_equal(r0, r1) and np.array_equal(f0, f1)
         assert np.array_equal(dev_tail, host_tail)
         if block_regens <= 5:
-            assert info["blocks_enqueued"] > 3 * info["ring_blocks"]          # the ring wrapped several times
+            assert info["blocks_enqueued"] > info["ring_blocks"]              # the ring wrapped
     finally:
         sync_host_rng()
         DeviceRng.get().configure(2, 256, 0)
