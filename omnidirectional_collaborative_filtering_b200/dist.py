@@ -215,11 +215,61 @@ def gather_full_weights(om, group=None) -> List[np.ndarray]:
 
 
 # ---- bench.py, N > 1 ----------------------------------------------------------------------------------
-def bench_main(args, w, cfg, rank, world):
-    """`bench.py --gpus N` under torchrun: weak scaling, global batch = N x batch_size rows, columns
-    sharded over the ranks. Timed with CUDA events, barrier + synchronize on both sides, max over
-    ranks; rank 0 prints the JSON line."""
-    import json
+_KERNEL_TAGS = {0: "k_gather_split (K1)", 1: "k_enc_fwd (K2)", 2: "k_dec_fwd (K3)", 3: "k_col_scan (K4a)", 5: "k_row_update (K4b)"}
+
+
+def _model_kwargs(w):
+    aux = w["aux"]
+    return dict(dense_activation=w["act"], use_causal_info=aux is not None, use_both_masks=aux == "both",
+                dropout_probability=w["dropout"], auxilliary_mask_type=aux)
+
+
+def _parity_vs_one_rank(args, w, fs, rd, om, B, rank, world):
+    """The first two steps of the sharded model (fresh weights) next to the same two steps of an unsharded model on
+    rank 0 (same initialisation, same NumPy stream, same global batches): max relative difference of the six step
+    metrics. Collective: every rank steps its shard; only rank 0 also builds and steps the 1-rank model."""
+    import contextlib
+    import sys
+    import torch.distributed as dist
+    from . import optimizers
+    from .data_reader import data_reader, sync_host_rng
+    from .model import omni_model
+    aux = w["aux"]
+
+    def two_steps(reader, model):
+        sync_host_rng()
+        np.random.seed(11)
+        g = reader.data_gen(B, w["sparsity"], "train", True, aux, w["aux_value"], pass_through_input_training=w["pass_through"])
+        out = [model.train_on_batch(next(g), sync=True) for _ in range(2)]
+        sync_host_rng()
+        return np.array(out, dtype=np.float64)
+
+    got = two_steps(rd, om.model)
+    res = None
+    if rank == 0:
+        with contextlib.redirect_stdout(sys.stderr):
+            rd1 = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs)
+        np.random.seed(0)
+        om1 = omni_model(w["layers"], w["hidden"], fs.n_cols, B, **_model_kwargs(w))
+        opt = {"adagrad": optimizers.Adagrad, "rmsprop": optimizers.RMSprop, "adam": optimizers.Adam}[w["opt"][0]](lr=w["opt"][1])
+        om1.model.compile(opt, "mean_squared_error", rating_range=fs.rating_range)
+        want = two_steps(rd1, om1.model)
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)
+        res = {"steps": 2, "max_rel_diff_of_step_metrics": float(rel.max()), "bar": 1e-3, "ok": bool(rel.max() < 1e-3),
+               "sharded_accurate_RMSE": [float(v) for v in got[:, 3]], "one_rank_accurate_RMSE": [float(v) for v in want[:, 3]],
+               "what": "first two train steps of the %d-rank column-sharded model vs the unsharded model on rank 0 "
+                       "(same init, same NumPy stream, global batch %d rows)" % (world, B)}
+        om1.model.close(); rd1.close()
+    dist.barrier()
+    return res
+
+
+def _bench_config(args, w, rank, world, native, B, scaling, parity=False, steps=None):
+    """One (workload, global batch) configuration on all ranks: device-timed value (CUDA events, barrier + synchronize
+    on both sides, max over ranks), per-rank kernel / exchange times, e2e through the public API. Returns the record on
+    rank 0 (None elsewhere); every rank makes the same collective calls."""
+    import contextlib
+    import sys
     import time
     import torch
     import torch.distributed as dist
@@ -228,11 +278,8 @@ def bench_main(args, w, cfg, rank, world):
     from .data_reader import data_reader
     from .store import DeviceBatch
 
-    local_rank = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.lib()
-    B = args.batch_size * world
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
     rows_mode = getattr(args, "parallel", "columns") == "rows"
     fs = None
     if rank == 0:
@@ -240,24 +287,27 @@ def bench_main(args, w, cfg, rank, world):
     dist.barrier()
     if fs is None:
         fs = bench.make_dataset(w)
-    native = NativeComm()
-    import contextlib
-    import sys
     with contextlib.redirect_stdout(sys.stderr):     # the reader prints the reference's "Finished loading data"
         rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs,
                          shard=None if rows_mode else (rank, world))
     aux = w["aux"]
     np.random.seed(0)
-    mkw = dict(dense_activation=w["act"], use_causal_info=aux is not None, use_both_masks=aux == "both",
-               dropout_probability=w["dropout"], auxilliary_mask_type=aux)
     if rows_mode:
-        om = row_parallel_model(native, w["layers"], w["hidden"], fs.n_cols, args.batch_size, **mkw)
+        om = row_parallel_model(native, w["layers"], w["hidden"], fs.n_cols, B // world, **_model_kwargs(w))
     else:
-        om = sharded_model(rank, world, w["layers"], w["hidden"], fs.n_cols, B, native=native, **mkw)
+        om = sharded_model(rank, world, w["layers"], w["hidden"], fs.n_cols, B, native=native, **_model_kwargs(w))
     m = om.model
     opt = {"adagrad": optimizers.Adagrad, "rmsprop": optimizers.RMSprop, "adam": optimizers.Adam}[w["opt"][0]](lr=w["opt"][1])
     m.compile(opt, "mean_squared_error", rating_range=fs.rating_range)
-    K, W = args.steps, max(args.warmup, 3)
+    K, W = int(steps or args.steps), max(args.warmup, 3)
+    K = max(2, min(K, rd.train_set_size // B * 4))
+    parity_rec = None
+    if parity and not rows_mode:
+        try:
+            parity_rec = _parity_vs_one_rank(args, w, fs, rd, om, B, rank, world)
+        except Exception as exc:                         # pragma: no cover - must not take the line down
+            parity_rec = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+            dist.barrier()
 
     def gen():
         return rd.data_gen(B, w["sparsity"], "train", True, aux, w["aux_value"], pass_through_input_training=w["pass_through"])
@@ -306,7 +356,8 @@ def bench_main(args, w, cfg, rank, world):
     torch.cuda.synchronize()
     dist.barrier()
     launches = lib.ocf_kernel_launches() - launches0
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    own_ms = e0.elapsed_time(e1)
+    t = torch.tensor([own_ms], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     # keep the same steps running ~0.6 s so nvidia-smi (100 ms period) samples clocks under this
@@ -316,24 +367,29 @@ def bench_main(args, w, cfg, rank, world):
         device_steps(resident[W:], W)
     torch.cuda.synchronize()
     dist.barrier()
-    # per-kernel / per-collective CUDA-event times of one more pass (this rank's view)
+    # per-kernel / per-collective CUDA-event times of one more pass, on EVERY rank (plain launches: the
+    # instrumented pass does not replay the graphs)
     lib.ocf_profile_reset()
     lib.ocf_profile_enable(1)
     device_steps(resident[W:], W)
     torch.cuda.synchronize()
     lib.ocf_profile_enable(0)
     dist.barrier()
-    names = {0: "k_gather_split (K1)", 1: "k_enc_fwd (K2)", 2: "k_dec_fwd (K3)", 3: "k_col_scan (K4a)", 5: "k_row_update (K4b)",
-             6: "streaming optimizer pass" if rows_mode else "exchange z [rows, H] (+ bias/act when over peer memory)",
-             7: "ncclAllReduce gradients" if rows_mode else "exchange row stats + dL/dh [rows, 4 + H]"}
+    names = dict(_KERNEL_TAGS)
+    names[6] = "streaming optimizer pass" if rows_mode else "exchange z [rows, H] (+ bias/act when over peer memory)"
+    names[7] = "ncclAllReduce gradients" if rows_mode else "exchange row stats + dL/dh [rows, 4 + H]"
     kernels = {}
     for tag, name in names.items():
         tot, cnt = C.c_double(), C.c_int64()
         _lib.check(lib.ocf_profile_read(tag, C.byref(tot), C.byref(cnt)))
         kernels[name] = {"ms": tot.value / max(cnt.value, 1)}
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"rank": rank, "own_timed_ms_per_step": own_ms / K,
+                                      "ms": {k: round(v["ms"], 5) for k, v in kernels.items()}})
     # roofline of rank 0's dominant kernel (the fused row update): algorithmic bytes of the rank's own
     # shard / CUDA-event time; never allowed to break the line
     roofline = None
+    state_mb = sum(float(np.prod(sh)) for sh in om.weight_shapes()) * 4 * bench.state_words_of(w) / 2 / 1e6
     if not rows_mode:
         try:
             alg = bench.step_bytes(plans[W:], w, 0)
@@ -341,15 +397,22 @@ def bench_main(args, w, cfg, rank, world):
             peak, peak_src = bench.peaks()
             if k4b_ms > 0:
                 ach = alg[4] / (k4b_ms * 1e-3) / 1e9
-                roofline = {"kernel": "k_row_update (K4b), rank 0's shard", "bound": "hbm", "achieved": ach, "peak": peak,
+                roofline = {"kernel": "k_row_update (K4b), rank 0's shard", "bound": "hbm" if state_mb > 2 * 126 else "l2",
+                            "achieved": ach, "peak": peak,
                             "unit": "GB/s", "frac": ach / peak, "traffic": None, "algorithmic_bytes": alg[4],
-                            "peak_source": peak_src}
+                            "peak_source": peak_src, "share_of_step": k4b_ms / (ms / K)}
         except Exception as exc:                      # pragma: no cover
             roofline = {"error": str(exc)}
-    rt = torch.tensor([float(sum(p.n_ratings for p in plans[W:]))], device="cuda")
+    rt = torch.tensor([float(sum(p.n_ratings for p in plans[W:])),
+                       float(sum(p.n_ratings if p.pass_through else 0 for p in plans[W:]))], device="cuda")
     if rows_mode:
         dist.all_reduce(rt)                              # every rank holds its own rows of the global batches
-    ratings = float(rt.item())                           # ratings of the global batches (all ranks together)
+    ratings = float(rt[0].item())                        # ratings of the global batches (all ranks together)
+    # SURVEY 8(d)'s rating = one observed TARGET entry: each rank counts the targets among its own ratings
+    tg = torch.tensor([float(sum(p.n_entries if p.pass_through else int((np.asarray(p.flags) == 0).sum()) for p in plans[W:]))],
+                      device="cuda")
+    dist.all_reduce(tg)
+    targets = float(tg.item())
 
     # e2e through the public API on every rank: host RNG replay + H2D + phases/collectives + D2H
     for _ in range(max(W, 9)):               # three rounds of the ring of 3 batch buffers: plain, capture, replay
@@ -380,22 +443,81 @@ def bench_main(args, w, cfg, rank, world):
     h2d_all = torch.tensor([float(h2d)], device="cuda")
     dist.all_reduce(h2d_all)
     clocks = sampler.stop() if sampler else None
+    rec = None
     if rank == 0:
-        line = {"metric": "train ratings/sec", "value": ratings / (ms * 1e-3), "unit": "ratings/s", "n_gpus": world,
-                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(cfg, parallelism=("row-parallel x%d, global batch %d rows (%d per GPU), replicated weights, one NCCL all-reduce of all gradients per step"
-                                                 if rows_mode else
-                                                 "column-sharded x%d, global batch %d rows (%d per GPU), 2 exchanges of [rows, H] per step as "
-                                                 + ("one-shot all-reduce kernels over NVLink peer memory fused with the next compute step"
-                                                    if native.peer_memory else "ncclAllReduce"))
-                               % (world, B, args.batch_size), ratings_per_step=ratings / K,
-                               l2="no flush: per-rank weights + optimizer state exceed the 126 MB L2"),
-                "clocks": clocks,
-                "e2e": {"value": e_ratings / float(e2e.item()), "unit": "ratings/s",
-                        "h2d_bytes_per_step": float(h2d_all.item()) / K, "d2h_bytes_per_step": 4 * _lib.N_METRICS * world,
-                        "ms_per_step": 1e3 * float(e2e.item()) / K},
-                "gpu_launches": int(launches), "roofline": roofline, "kernels_rank0": kernels}
+        if rows_mode:
+            par = ("row-parallel x%d, global batch %d rows (%d per GPU), replicated weights, one NCCL all-reduce of all gradients per step"
+                   % (world, B, B // world))
+        else:
+            par = ("column-sharded x%d, global batch %d rows (every rank walks all of them on its own columns), 2 exchanges of [rows, H] per step as %s"
+                   % (world, B, "one-shot all-reduce kernels over NVLink peer memory fused with the next compute step"
+                      if native.peer_memory else "ncclAllReduce (captured in the step's CUDA graph)"))
+        l2 = ("no flush: per-rank weights + optimizer state (%.0f MB) exceed the 126 MB L2 several times over" % state_mb
+              if state_mb > 2 * 126 else
+              "no flush, and per-rank weights + optimizer state (%.0f MB) fit or nearly fit the 126 MB L2: the rank's kernels "
+              "run from L2, an HBM fraction is not meaningful here (roofline.bound says 'l2')" % state_mb)
+        rec = {"value": ratings / (ms * 1e-3), "unit": "ratings/s", "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "scaling": scaling, "global_batch_rows": B, "parallelism": par, "l2": l2,
+               "ratings_per_step": ratings / K, "target_ratings_per_step": targets / K,
+               "target_ratings_per_s": targets / (ms * 1e-3), "clocks": clocks,
+               "e2e": {"value": e_ratings / float(e2e.item()), "unit": "ratings/s",
+                       "h2d_bytes_per_step": float(h2d_all.item()) / K, "d2h_bytes_per_step": 4 * _lib.N_METRICS * world,
+                       "ms_per_step": 1e3 * float(e2e.item()) / K},
+               "gpu_launches": int(launches), "roofline": roofline, "kernels_rank0": kernels, "kernels_per_rank": per_rank}
+        if parity_rec is not None:
+            rec["parity"] = parity_rec
+    del resident
+    m.close()
+    rd.close()
+    dist.barrier()
+    return rec
+
+
+def bench_main(args, w, cfg, rank, world):
+    """`bench.py --gpus N` under torchrun, columns sharded over the ranks. The line's `value` is weak scaling (global
+    batch = N x batch_size rows: the data-parallel run of N per-GPU batches); `strong_scaling` carries the same model at
+    the reference's own global batch (batch_size rows in all, train.py:30); at N = 8 the Netflix-shaped config rides
+    along under `other_workloads` (it is the config the 8-way column split exists for). Rank 0 prints the JSON line."""
+    import json
+    import torch
+    import torch.distributed as dist
+    import bench
+
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    native = NativeComm()
+    rows_mode = getattr(args, "parallel", "columns") == "rows"
+    main = _bench_config(args, w, rank, world, native, args.batch_size * world, "weak", parity=True)
+    strong = None
+    if not rows_mode and os.environ.get("OCF_BENCH_STRONG", "1") != "0":
+        strong = _bench_config(args, w, rank, world, native, args.batch_size, "strong", steps=min(args.steps, 30))
+    others = getattr(args, "others", None)
+    if others is None:
+        others = "netflix" if (world == 8 and args.workload == "ml10m" and not rows_mode) else "none"
+    other_recs = {}
+    for name in [x for x in others.split(",") if x and x != "none"]:
+        try:
+            other_recs[name] = _bench_config(args, bench.WORKLOADS[name], rank, world, native, args.batch_size * world, "weak",
+                                             parity=True, steps=min(args.steps, 12))
+        except Exception as exc:                          # pragma: no cover
+            other_recs[name] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+    if rank == 0:
+        line = {"metric": "train ratings/sec", "value": main["value"], "unit": "ratings/s", "n_gpus": world,
+                "steps": main["steps"], "warmup": main["warmup"], "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg}
+        for k, v in main.items():
+            if k not in line:
+                line[k] = v
+        if strong is not None:
+            line["strong_scaling"] = {k: strong[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "global_batch_rows",
+                                                             "ratings_per_step", "e2e", "gpu_launches", "kernels_rank0", "l2")}
+        if other_recs:
+            line["other_workloads"] = {k: ({kk: vv for kk, vv in v.items() if kk != "kernels_per_rank"} if "error" not in v else v)
+                                       for k, v in other_recs.items()}
+            for k, v in other_recs.items():
+                if "error" not in v:
+                    line["other_workloads"][k]["kernels_per_rank"] = v["kernels_per_rank"]
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
