@@ -509,16 +509,29 @@ def main():
     lib.ocf_profile_enable(0)
     tag_names = ["k_gather_split (K1)", "k_enc_fwd (K2)", "k_dec_fwd (K3)", "k_col_scan (K4a)", "k_row_update (K4b)"]
     tag_ms = []
+    n_prof_steps = 1
     for t in (0, 1, 2, 3, 5):
         tot, cnt = C.c_double(), C.c_int64()
         _lib.check(lib.ocf_profile_read(t, C.byref(tot), C.byref(cnt)))
-        tag_ms.append(tot.value / max(cnt.value, 1))
+        if t == 1:
+            n_prof_steps = max(cnt.value, 1)
+        # per step: a width list launches the row update twice (decoder rows, encoder rows)
+        tag_ms.append(tot.value / max(cnt.value, 1) if t != 5 else tot.value / n_prof_steps)
     state_words = state_words_of(w)
     alg = step_bytes(plans[W:], w, fs.train.nnz)
+    if w["layers"] > 1:
+        # hidden [H1, H2] layers: three tcgen05 contractions each per step (forward, backward, gradient + update)
+        tot, cnt = C.c_double(), C.c_int64()
+        _lib.check(lib.ocf_profile_read(8, C.byref(tot), C.byref(cnt)))
+        widths = w["hidden"] if isinstance(w["hidden"], (list, tuple)) else [w["hidden"]] * w["layers"]
+        hid_bytes = sum(4.0 * a * b * (2 + state_words) for a, b in zip(widths[:-1], widths[1:]))   # W read twice + W/state read+write
+        tag_names.append("k_gemm_tc x%d (hidden layers, tcgen05 3xTF32)" % (cnt.value // n_prof_steps))
+        tag_ms.append(tot.value / n_prof_steps)
+        alg = list(alg) + [hid_bytes]
     peak, peak_src = peaks()
     dom = int(np.argmax(tag_ms))
     kernels = {tag_names[t]: {"ms": tag_ms[t], "algorithmic_bytes": alg[t], "GB/s": alg[t] / (tag_ms[t] * 1e-3) / 1e9 if tag_ms[t] > 0 else None}
-               for t in range(5)}
+               for t in range(len(tag_names))}
     achieved = alg[dom] / (tag_ms[dom] * 1e-3) / 1e9
     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel on this workload
     traffic, traffic_src = ncu_traffic(args.workload, tag_names[dom].split(" ")[0]) if B == 128 else (None, None)

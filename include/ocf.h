@@ -261,6 +261,15 @@ int ocf_score(ocf_model* model, ocf_batch* batch, float* out, int out_is_device,
  * hold column -1 / score -inf. Column shards return their own columns' top k (local ids). */
 int ocf_score_topk(ocf_model* model, ocf_batch* batch, int32_t k, int exclude_inputs,
                    int32_t* out_cols, float* out_scores, void* stream);
+/* The dense contraction kernel of the training step (tcgen05 kind::tf32 with fp32 operands split hi/lo, TMEM
+ * accumulators, split-K over a thread-block cluster reduced through distributed shared memory;
+ * csrc/ocf_gemm_tc.cuh: hidden layers of model.py:64-71 forward / backward / weight gradient), on host arrays:
+ *   out[n, m] = sum_k A(m, k) * B(n, k)        out is [n_len, m_len] row-major
+ * a_mn != 0: A is stored [k_len, m_len] (m contiguous), else [m_len, k_len]; b_mn likewise for B with n_len.
+ * m_len, n_len, k_len multiples of 4. terms: 3 = fp32-grade (hi*hi + hi*lo + lo*hi), 1 = plain tf32.
+ * split: 0 = the library's choice, else the cluster size along the contraction (1, 2, 4 or 8). */
+int ocf_gemm_tc(const float* a, int a_mn, const float* b, int b_mn, int32_t m_len, int32_t n_len, int32_t k_len,
+                int terms, int split, float* out);
 /* Copies `count` metric records starting at step slot `first` of the device log to the host
  * (synchronises `stream`). The log keeps the last 4096 steps. */
 int ocf_model_read_metrics(ocf_model* model, int64_t first, int32_t count, float* host,

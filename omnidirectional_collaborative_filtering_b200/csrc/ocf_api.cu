@@ -14,6 +14,7 @@
 #include "ocf_kernels.cuh"
 #include "ocf_mtjump.h"
 #include "ocf_score_tc.cuh"
+#include "ocf_gemm_tc.cuh"
 #include "ocf_peer.cuh"
 #include "ocf_topk.cuh"
 
@@ -318,7 +319,7 @@ extern "C" int ocf_host_free(void* p) {
 
 // ---- optional per-kernel timing with CUDA events on the launching stream -------------------
 namespace ocf {
-constexpr int N_TAGS = 8;
+constexpr int N_TAGS = 10;
 struct Profiler {
   bool on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[N_TAGS];
@@ -854,11 +855,9 @@ extern "C" int ocf_rng_destroy(ocf_rng* r) {
 // array `src` of worker j jumped by polynomial `which` into its other buffer, on stream st
 static int rng_jump(ocf_rng* r, int j, const uint32_t* src, uint32_t* dst, int which, cudaStream_t st) {
   uint32_t* seq = r->d_seq + (size_t)j * MT_SEQ_REGENS * 624;
-  OCF_CUDA(cudaMemcpyAsync(seq, src, 624 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-  OCF_CUDA(cudaMemcpyAsync(dst, src, 624 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));      // scratch copy the block kernel advances
-  k_mt_block<false><<<1, MT_THREADS, 0, st>>>(dst, MT_SEQ_REGENS - 1, seq, (uint32_t)(MT_SEQ_REGENS * 624), 624u);
+  // the worker's own sequence from `src` on (src itself stays as it is), dst zeroed for the XOR accumulation
+  k_mt_block<false><<<1, MT_THREADS, 0, st>>>(dst, MT_SEQ_REGENS - 1, seq, (uint32_t)(MT_SEQ_REGENS * 624), 624u, src, dst);
   OCF_LAUNCHED();
-  OCF_CUDA(cudaMemsetAsync(dst, 0, 624 * sizeof(uint32_t), st));
   k_mt_jump_apply<<<MT_JUMP_CTAS, MT_THREADS, 0, st>>>(seq, r->d_poly + (size_t)which * 624, dst);
   OCF_LAUNCHED();
   return OCF_OK;
@@ -1536,6 +1535,55 @@ static int launch_act(ocf_model* m, int l, int B, bool training, const ocf_step_
   return OCF_OK;
 }
 
+// ---- hidden [H1, H2] layers on the tensor cores (ocf_gemm_tc.cuh); OCF_NO_TC_HIDDEN=1 keeps the SIMT k_sgemm path ----
+static bool tc_hidden() {
+  static const bool on = [] { const char* e = std::getenv("OCF_NO_TC_HIDDEN"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
+// a_l = act(h_{l-1} . W_l + b_l) (+ dropout): D[n, b] = sum_k W[k, n] h[b, k]
+static int hidden_fwd_tc(ocf_model* m, int l, int B, const float* hin, const ActArgs& act, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  OCF_TRY(gtc::make_map_mn(&ma, m->layers[l].W, m->hp[l], m->hp[l], m->hp[l - 1]));
+  OCF_TRY(gtc::make_map_k(&mb, hin, m->hp[l - 1], m->hp[l - 1], B));
+  gtc::GemmTcArgs g{};
+  g.kind = gtc::GEPI_FWD; g.a_mn = 1; g.b_mn = 0; g.actargs = act;
+  g_prof.begin(8, st);
+  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l], B, m->hp[l - 1], st));
+  g_prof.end(8, st);
+  return OCF_OK;
+}
+
+// dz_{l-1} = (dz_l . W_l^T) * dropout scale * act'(a_{l-1}): D[k, b] = sum_n W[k, n] dz[b, n]
+static int hidden_dz_tc(ocf_model* m, int l, int B, bool drop, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  OCF_TRY(gtc::make_map_k(&ma, m->layers[l].W, m->hp[l], m->hp[l], m->hp[l - 1]));
+  OCF_TRY(gtc::make_map_k(&mb, m->dz[l], m->hp[l], m->hp[l], B));
+  gtc::GemmTcArgs g{};
+  g.kind = gtc::GEPI_DZ; g.a_mn = 0; g.b_mn = 0;
+  g.C = m->dz[l - 1]; g.ldc = m->hp[l - 1]; g.aux0 = m->act[l - 1]; g.aux1 = drop ? m->dscale[l - 1] : nullptr; g.act = m->cfg.activation;
+  g_prof.begin(8, st);
+  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l - 1], B, m->hp[l], st));
+  g_prof.end(8, st);
+  return OCF_OK;
+}
+
+// dW_l = h_{l-1}^T . dz_l fused with the update of W_l (or stored, row-parallel mode): D[n, k] = sum_b dz[b, n] h[b, k]
+static int hidden_dw_tc(ocf_model* m, int l, int B, const float* hin, const OptDev& opt, float* grad_out, cudaStream_t st) {
+  Layer& ly = m->layers[l];
+  CUtensorMap ma, mb;
+  OCF_TRY(gtc::make_map_mn(&ma, m->dz[l], m->hp[l], m->hp[l], B));
+  OCF_TRY(gtc::make_map_mn(&mb, hin, m->hp[l - 1], m->hp[l - 1], B));
+  gtc::GemmTcArgs g{};
+  g.a_mn = 1; g.b_mn = 1; g.ldc = m->hp[l];
+  if (grad_out) { g.kind = gtc::GEPI_STORE; g.C = grad_out; }
+  else { g.kind = gtc::GEPI_UPDATE; g.C = ly.W; g.s1 = ly.Ws1; g.s2 = ly.Ws2; g.opt = opt; }
+  g_prof.begin(8, st);
+  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l], m->hp[l - 1], B, st));
+  g_prof.end(8, st);
+  return OCF_OK;
+}
+
 // phase 2: activations, hidden layers, decoder at the target entries, loss partials -> dh_top, rowstats
 // act0_done: the first layer's activations are already in place (fused into the encoder's row tails or
 // into the peer exchange).
@@ -1551,7 +1599,8 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
     // hidden layer: product + bias + activation + dropout in the GEMM's epilogue
     GemmEpi ep{}; ep.kind = EPI_BIAS_ACT; ep.C = m->zsum[l]; ep.ldc = m->hp[l]; ep.actargs = act_args(m, l, B, training, args);
     const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
-    OCF_TRY(launch_gemm(m, false, false, hin, m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
+    if (tc_hidden()) OCF_TRY(hidden_fwd_tc(m, l, B, hin, ep.actargs, st));
+    else OCF_TRY(launch_gemm(m, false, false, hin, m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
   }
   const float* htop = drop ? m->h[L - 1] : m->act[L - 1];
   const int hpt = m->hp[L - 1];
@@ -1683,7 +1732,7 @@ static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
 
 // K4b: one warp per (column, array) task: gradient row from the matches, fused optimizer update.
 static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int hpx, const OptDev& opt, cudaStream_t st,
-                       bool grad_mode = false) {
+                       bool grad_mode = false, int only = 0) {
   if (!do_dec && !do_enc) return OCF_OK;
   const int L = m->L;
   const bool drop = m->cfg.dropout_p > 0.f;
@@ -1695,7 +1744,7 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
   r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
   r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.bt_hdr = b->dev.hdr; r.opt = opt;
-  r.dense = grad_mode ? 0 : opt.dense; r.n_arr = 0;
+  r.dense = grad_mode ? 0 : opt.dense; r.n_arr = 0; r.only = only;
   if (grad_mode) { r.Gdec = m->gW[L]; r.Genc = m->gW[0]; r.gbdec = m->gb[L]; }
   if (do_dec) r.arr_map[r.n_arr++] = 0;
   if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
@@ -1712,7 +1761,6 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
 static int fork_scan(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
   m->scan_pending = false;
   const int L = m->L;
-  if (m->hp[L - 1] != m->hp[0]) return OCF_OK;
   const OptDev opt = make_opt(m);
   const int dense = m->par_mode == OCF_PAR_ROWS ? 0 : opt.dense;   // gradient rows exist for touched columns only
   const int do_dec = m->layers[L].trainable ? 1 : 0, do_enc = m->layers[0].trainable ? 1 : 0;
@@ -1756,7 +1804,8 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     // dz_{l-1} = (dz_l . W_l^T) * dropout scale * act'(a_{l-1})   (uses W_l before its update)
     GemmEpi ep{}; ep.kind = EPI_DZ; ep.C = m->dz[l - 1]; ep.ldc = m->hp[l - 1]; ep.aux0 = m->act[l - 1];
     ep.aux1 = drop ? m->dscale[l - 1] : nullptr; ep.act = m->cfg.activation;
-    OCF_TRY(launch_gemm(m, false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
+    if (tc_hidden()) OCF_TRY(hidden_dz_tc(m, l, B, drop, st));
+    else OCF_TRY(launch_gemm(m, false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
     Layer& lo = m->layers[l - 1];
     k_dz_bias<<<m->hp[l - 1] / 32, 1024, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
                                                          m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0,
@@ -1767,7 +1816,8 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
       GemmEpi eu{}; eu.kind = EPI_UPDATE; eu.C = ly.W; eu.ldc = m->hp[l]; eu.s1 = ly.Ws1; eu.s2 = ly.Ws2; eu.opt = opt;
       if (grad_mode) { eu.kind = EPI_STORE; eu.C = m->gW[l]; }
       const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
-      OCF_TRY(launch_gemm(m, true, false, hin, m->hp[l - 1], m->dz[l], m->hp[l], m->hp[l - 1], m->hp[l], B, eu, st));
+      if (tc_hidden()) OCF_TRY(hidden_dw_tc(m, l, B, hin, opt, grad_mode ? m->gW[l] : nullptr, st));
+      else OCF_TRY(launch_gemm(m, true, false, hin, m->hp[l - 1], m->dz[l], m->hp[l], m->hp[l - 1], m->hp[l], B, eu, st));
     }
   }
   // catalogue-wide kernels: encoder rows and decoder rows of every touched column
@@ -1776,16 +1826,15 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   const int hpd = m->hp[L - 1], hpe = m->hp[0];
   const int dense = grad_mode ? 0 : opt.dense;
   // decoder and encoder rows share one padded width in the reference's architectures (one
-  // num_hidden_units): one grouping pass feeds both. A width list with different ends groups twice.
+  // num_hidden_units). A width list with different ends shares the grouping too: its task list holds both kinds of
+  // rows and each of the two launches (one per width) takes its own.
+  if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
+  else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, dense, st));
   if (hpd == hpe) {
-    if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
-    else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, dense, st));
     OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd, opt, st, grad_mode));
   } else {
-    OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, 0, dense, st));
-    OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, 0, hpd, opt, st, grad_mode));
-    OCF_TRY(launch_scan(m, b, 0, enc.trainable ? 1 : 0, dense, st));
-    OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st, grad_mode));
+    OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, 0, hpd, opt, st, grad_mode, 1));
+    OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st, grad_mode, 2));
   }
   return OCF_OK;
 }
@@ -2195,6 +2244,7 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   OCF_TRY(encode_for_output(m, b, st, &act0));
   if (!act0) OCF_TRY(launch_act(m, 0, B, false, nullptr, st));
   for (int l = 1; l < L; ++l) {
+    if (tc_hidden()) { OCF_TRY(hidden_fwd_tc(m, l, B, m->act[l - 1], act_args(m, l, B, false, nullptr), st)); continue; }
     GemmEpi ep{}; ep.kind = EPI_STORE; ep.C = m->zsum[l]; ep.ldc = m->hp[l];
     OCF_TRY(launch_gemm(m, false, false, m->act[l - 1], m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
     OCF_TRY(launch_act(m, l, B, false, nullptr, st));
@@ -2262,6 +2312,32 @@ extern "C" int ocf_score_topk(ocf_model* m, ocf_batch* b, int32_t k, int exclude
   OCF_CUDA(cudaMemcpyAsync(out_cols, m->topk_cols, sizeof(int32_t) * (size_t)B * k, cudaMemcpyDeviceToHost, st));
   OCF_CUDA(cudaMemcpyAsync(out_scores, m->topk_scores, sizeof(float) * (size_t)B * k, cudaMemcpyDeviceToHost, st));
   OCF_CUDA(cudaStreamSynchronize(st));
+  return OCF_OK;
+}
+
+extern "C" int ocf_gemm_tc(const float* a, int a_mn, const float* b, int b_mn, int32_t m_len, int32_t n_len, int32_t k_len,
+                           int terms, int split, float* out) {
+  OCF_REQUIRE(a && b && out && m_len > 0 && n_len > 0 && k_len > 0, "ocf_gemm_tc: bad argument");
+  OCF_REQUIRE(m_len % 4 == 0 && n_len % 4 == 0 && k_len % 4 == 0, "ocf_gemm_tc: sizes must be multiples of 4 (16-byte rows for TMA)");
+  OCF_REQUIRE(terms == 1 || terms == 3, "ocf_gemm_tc: terms must be 1 or 3");
+  OCF_REQUIRE(split == 0 || split == 1 || split == 2 || split == 4 || split == 8, "ocf_gemm_tc: split must be 0, 1, 2, 4 or 8");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return fail(OCF_ERR_CUDA, "ocf_gemm_tc: no CUDA device"); }
+  Arena mem;
+  struct Release { Arena& a; ~Release() { a.release(); } } release_on_exit{mem};
+  float *da = nullptr, *db = nullptr, *dc = nullptr;
+  const size_t na = (size_t)m_len * k_len, nb = (size_t)n_len * k_len, nc = (size_t)m_len * n_len;
+  OCF_TRY(mem.get(&da, na)); OCF_TRY(mem.get(&db, nb)); OCF_TRY(mem.get(&dc, nc, true));
+  OCF_CUDA(cudaMemcpy(da, a, na * sizeof(float), cudaMemcpyHostToDevice));
+  OCF_CUDA(cudaMemcpy(db, b, nb * sizeof(float), cudaMemcpyHostToDevice));
+  CUtensorMap ma, mb;
+  if (a_mn) OCF_TRY(gtc::make_map_mn(&ma, da, m_len, m_len, k_len)); else OCF_TRY(gtc::make_map_k(&ma, da, k_len, k_len, m_len));
+  if (b_mn) OCF_TRY(gtc::make_map_mn(&mb, db, n_len, n_len, k_len)); else OCF_TRY(gtc::make_map_k(&mb, db, k_len, k_len, n_len));
+  gtc::GemmTcArgs g{};
+  g.kind = gtc::GEPI_RAW; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0; g.C = dc; g.ldc = m_len; g.terms = terms;
+  OCF_TRY(gtc::launch(ma, mb, g, m_len, n_len, k_len, nullptr, split));
+  OCF_CUDA(cudaDeviceSynchronize());
+  OCF_CUDA(cudaMemcpy(out, dc, nc * sizeof(float), cudaMemcpyDeviceToHost));
   return OCF_OK;
 }
 

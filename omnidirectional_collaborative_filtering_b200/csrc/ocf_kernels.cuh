@@ -153,10 +153,13 @@ __device__ __forceinline__ uint32_t mt_new_word(int i, uint32_t own, const uint3
 // words at word offset `off0` (a multiple of 4, every regeneration 16-byte aligned; a regeneration never straddles
 // the ring's end because ring_words is a multiple of 624) through shared-memory slots and TMA bulk stores. Without
 // TEMPER the raw arrays are appended to `ring` from off0 (the sequence a jump correlates with its polynomial).
+// One launch per block and two per jump: every launch costs the host ~3 us, and a rank of an 8-GPU run makes
+// ~10 blocks per step (profiles/r02: 0.29 ms of API calls per step with the 8-call version of block + jump).
 // state[626..629]: SM cycles and nanoseconds of the launch (ocf_rng_last_timing).
 template <bool TEMPER>
 __global__ void __launch_bounds__(MT_THREADS)
-k_mt_block(uint32_t* __restrict__ state, int n_regen, uint32_t* __restrict__ ring, uint32_t ring_words, uint32_t off0) {
+k_mt_block(uint32_t* __restrict__ state, int n_regen, uint32_t* __restrict__ ring, uint32_t ring_words, uint32_t off0,
+           const uint32_t* __restrict__ src = nullptr, uint32_t* __restrict__ clear = nullptr) {
   __shared__ __align__(16) uint32_t mt[2][624];
   __shared__ __align__(16) uint32_t tw[624];
   __shared__ __align__(16) uint32_t slots[MT_RING][624];
@@ -164,7 +167,13 @@ k_mt_block(uint32_t* __restrict__ state, int n_regen, uint32_t* __restrict__ rin
   const long long clk0 = clock64();
   unsigned long long ns0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
-  for (int i = tid; i < 624; i += blockDim.x) mt[0][i] = state[i];
+  // src (a jump's sequence pass): start from `src` and leave it alone - its raw words open the sequence at
+  // ring[off0 - 624 ..), nothing is written back; `clear` (the jump's output array) is zeroed on the way out.
+  for (int i = tid; i < 624; i += blockDim.x) {
+    const uint32_t v = src != nullptr ? src[i] : state[i];
+    mt[0][i] = v;
+    if (src != nullptr) ring[off0 - 624u + i] = v;
+  }
   int cur = 0;
   __syncthreads();
   uint32_t off = off0;
@@ -199,6 +208,8 @@ k_mt_block(uint32_t* __restrict__ state, int n_regen, uint32_t* __restrict__ rin
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (clear != nullptr) for (int k = tid; k < 624; k += blockDim.x) clear[k] = 0u;
+  if (src != nullptr) return;
   for (int k = tid; k < 624; k += blockDim.x) state[k] = mt[cur][k];
   if (tid == 0) {
     unsigned long long ns1;
@@ -1127,6 +1138,7 @@ struct RowArgs {
   float* Gdec; float* Genc; float* gbdec;   // KIND_GRAD: gradient rows instead of updates (row-parallel mode)
   int n_cols; int3 bits; const BatchHdr* bt_hdr;
   int dense; int n_arr; int arr_map[4];
+  int only;                                 // task list shared by two launches (decoder and encoder rows of different widths): 1 = decoder tasks only, 2 = encoder tasks only
   OptDev opt;
 };
 
@@ -1151,6 +1163,7 @@ k_row_update(RowArgs a) {
       const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
     } else {
       const int4 task = a.tasks[t]; c = task.x; arr = task.y; base = task.z; n = task.w;
+      if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
     }
     const size_t r = arr == 0 ? (size_t)c * HP : ((size_t)(arr - 1) * a.n_cols + c) * HP;
     float* Wrow = (arr == 0 ? a.WdecT : a.Wenc) + r + lane * 4;

@@ -80,6 +80,7 @@ class DeviceRng(object):
         self.host_state = None              # np.random state at the first ticket since the last release
         self.issued = 0
         self.pending = OrderedDict()        # ticket -> draws, in drawing order
+        self.layout = None                  # (workers, regenerations per block) this object asked for last
 
     @classmethod
     def get(cls):
@@ -105,19 +106,14 @@ class DeviceRng(object):
             out = C.c_void_p()
             _lib.check(lib.ocf_rng_create(C.byref(out)))
             self.handle = out
-            # generator CTAs: one chain makes ~0.84 G draws/s; a rank of a multi-GPU run replays the whole global
-            # batch's draws, so it gets more workers ($OCF_RNG_WORKERS overrides)
-            import os
-            workers = os.environ.get("OCF_RNG_WORKERS")
-            if workers is None and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-                _lib.check(lib.ocf_rng_configure(self.handle, 8, 256, 0))
         key = np.ascontiguousarray(self.host_state[1], dtype=np.uint32)
         _lib.check(lib.ocf_rng_set_state(self.handle, _lib.ptr(key), int(self.host_state[2])))
         self.active = True
 
-    def configure(self, workers=0, block_regens=0, ring_words_min=0):
+    def configure(self, workers=0, block_regens=0, ring_words_min=0, pin=True):
         """Generator layout of the device stream (`ocf_rng_configure`): worker CTAs, regenerations per block, minimum
-        ring size in words; 0 keeps a value. The stream's state and position are kept."""
+        ring size in words; 0 keeps a value. The stream's state and position are kept. A layout set here stays
+        (`pin`); without a pinned layout the object sizes the blocks to the batches it sees (`_tune`)."""
         with self.lock:
             lib = _lib.lib()
             if self.handle is None:
@@ -126,6 +122,31 @@ class DeviceRng(object):
                 _lib.check(lib.ocf_rng_create(C.byref(out)))
                 self.handle = out
             _lib.check(lib.ocf_rng_configure(self.handle, int(workers), int(block_regens), int(ring_words_min)))
+            self.pinned = bool(pin)
+            self.layout = None              # re-read on the next _tune
+
+    def _tune(self, draws):
+        """Generator layout for batches of `draws` doubles. One chain (CTA) makes ~0.8 G draws/s, and every block
+        costs the host four launches (block, event, the jump's two kernels). A rank of a multi-GPU run replays the
+        whole global batch's draws, so it gets 8 workers (16 for multi-million-draw batches), and blocks grow with
+        the batch so that a batch stays a handful of blocks (8 ranks x 10 blocks of 256 regenerations per step was
+        0.29 ms of API calls per 0.24 ms step, profiles/r02). Only ever grows; $OCF_RNG_WORKERS pins the workers."""
+        if getattr(self, "pinned", False):
+            return
+        import os
+        if self.layout is None:
+            inf = self.info()
+            self.layout = (int(inf["workers"]), int(inf["block_regens"]))
+        fixed = os.environ.get("OCF_RNG_WORKERS")
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        workers = int(fixed) if fixed else (2 if world == 1 else (8 if draws <= 3000000 else 16))
+        regens = 256
+        while regens < 4096 and regens * 624 * workers < 2 * draws:
+            regens *= 2
+        want = (max(workers, self.layout[0]), max(regens, self.layout[1]))
+        if want != self.layout:
+            _lib.check(_lib.lib().ocf_rng_configure(self.handle, want[0], want[1], 0))
+            self.layout = want
 
     def info(self):
         buf = (C.c_int64 * 6)()
@@ -146,6 +167,7 @@ class DeviceRng(object):
                     break
                 _lib.check(lib.ocf_rng_skip(self.handle, self.pending.pop(t)))   # drawn, never uploaded
             mine = self.pending.pop(ticket)
+            self._tune(mine)
             # the tickets already drawn tell how far the workers may run ahead of this batch
             _lib.check(lib.ocf_rng_prefetch(self.handle, mine + sum(self.pending.values())))
             return self.handle

@@ -37,6 +37,13 @@ class _FakeLib(object):
         return 0
 
     def ocf_rng_configure(self, handle, workers, block_regens, ring_words_min):
+        self.layout = (int(workers), int(block_regens))
+        return 0
+
+    def ocf_rng_info(self, handle, buf):
+        w, c = getattr(self, "layout", (2, 256))
+        for k, v in enumerate((w, c, 16, 16 * 624 * c, 0, 0)):
+            buf[k] = v
         return 0
 
     def ocf_rng_get_state(self, handle, key_ptr, pos):

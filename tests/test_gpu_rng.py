@@ -116,7 +116,7 @@ def test_parallel_generator_workers_give_the_sequential_stream(workers, block_re
             assert info["blocks_enqueued"] > info["ring_blocks"]              # the ring wrapped
     finally:
         sync_host_rng()
-        DeviceRng.get().configure(2, 256, 0)
+        DeviceRng.get().configure(2, 256, 0, pin=False)
 
 
 def test_ring_grows_for_a_batch_larger_than_the_ring():
@@ -132,4 +132,4 @@ def test_ring_grows_for_a_batch_larger_than_the_ring():
         assert np.array_equal(dev_tail, host_tail)
     finally:
         sync_host_rng()
-        DeviceRng.get().configure(2, 256, 0)
+        DeviceRng.get().configure(2, 256, 0, pin=False)
