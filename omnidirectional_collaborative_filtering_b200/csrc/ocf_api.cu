@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -281,6 +282,23 @@ struct ocf_model {
 };
 
 constexpr int N_REGPART = 64;
+
+// Launch with the programmatic-stream-serialization attribute (PDL, ocf_common.cuh): only for kernels that call
+// pdl_wait() before they touch memory, and only when the previous operation in the stream is a kernel.
+static bool pdl_on() {
+  static const bool on = [] { const char* e = std::getenv("OCF_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (pdl && pdl_on()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 static void drop_graphs(ocf_model* m) {
   for (auto& kv : m->graphs)
@@ -1542,20 +1560,20 @@ static bool tc_hidden() {
 }
 
 // a_l = act(h_{l-1} . W_l + b_l) (+ dropout): D[n, b] = sum_k W[k, n] h[b, k]
-static int hidden_fwd_tc(ocf_model* m, int l, int B, const float* hin, const ActArgs& act, cudaStream_t st) {
+static int hidden_fwd_tc(ocf_model* m, int l, int B, const float* hin, const ActArgs& act, cudaStream_t st, bool pdl = false) {
   CUtensorMap ma, mb;
   OCF_TRY(gtc::make_map_mn(&ma, m->layers[l].W, m->hp[l], m->hp[l], m->hp[l - 1]));
   OCF_TRY(gtc::make_map_k(&mb, hin, m->hp[l - 1], m->hp[l - 1], B));
   gtc::GemmTcArgs g{};
   g.kind = gtc::GEPI_FWD; g.a_mn = 1; g.b_mn = 0; g.actargs = act;
   g_prof.begin(8, st);
-  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l], B, m->hp[l - 1], st));
+  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l], B, m->hp[l - 1], st, 0, pdl && pdl_on() && !g_prof.on));
   g_prof.end(8, st);
   return OCF_OK;
 }
 
 // dz_{l-1} = (dz_l . W_l^T) * dropout scale * act'(a_{l-1}): D[k, b] = sum_n W[k, n] dz[b, n]
-static int hidden_dz_tc(ocf_model* m, int l, int B, bool drop, cudaStream_t st) {
+static int hidden_dz_tc(ocf_model* m, int l, int B, bool drop, cudaStream_t st, bool pdl = false) {
   CUtensorMap ma, mb;
   OCF_TRY(gtc::make_map_k(&ma, m->layers[l].W, m->hp[l], m->hp[l], m->hp[l - 1]));
   OCF_TRY(gtc::make_map_k(&mb, m->dz[l], m->hp[l], m->hp[l], B));
@@ -1563,13 +1581,13 @@ static int hidden_dz_tc(ocf_model* m, int l, int B, bool drop, cudaStream_t st) 
   g.kind = gtc::GEPI_DZ; g.a_mn = 0; g.b_mn = 0;
   g.C = m->dz[l - 1]; g.ldc = m->hp[l - 1]; g.aux0 = m->act[l - 1]; g.aux1 = drop ? m->dscale[l - 1] : nullptr; g.act = m->cfg.activation;
   g_prof.begin(8, st);
-  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l - 1], B, m->hp[l], st));
+  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l - 1], B, m->hp[l], st, 0, pdl && pdl_on() && !g_prof.on));
   g_prof.end(8, st);
   return OCF_OK;
 }
 
 // dW_l = h_{l-1}^T . dz_l fused with the update of W_l (or stored, row-parallel mode): D[n, k] = sum_b dz[b, n] h[b, k]
-static int hidden_dw_tc(ocf_model* m, int l, int B, const float* hin, const OptDev& opt, float* grad_out, cudaStream_t st) {
+static int hidden_dw_tc(ocf_model* m, int l, int B, const float* hin, const OptDev& opt, float* grad_out, cudaStream_t st, bool pdl = false) {
   Layer& ly = m->layers[l];
   CUtensorMap ma, mb;
   OCF_TRY(gtc::make_map_mn(&ma, m->dz[l], m->hp[l], m->hp[l], B));
@@ -1579,7 +1597,7 @@ static int hidden_dw_tc(ocf_model* m, int l, int B, const float* hin, const OptD
   if (grad_out) { g.kind = gtc::GEPI_STORE; g.C = grad_out; }
   else { g.kind = gtc::GEPI_UPDATE; g.C = ly.W; g.s1 = ly.Ws1; g.s2 = ly.Ws2; g.opt = opt; }
   g_prof.begin(8, st);
-  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l], m->hp[l - 1], B, st));
+  OCF_TRY(gtc::launch(ma, mb, g, m->hp[l], m->hp[l - 1], B, st, 0, pdl && pdl_on() && !g_prof.on));
   g_prof.end(8, st);
   return OCF_OK;
 }
@@ -1589,18 +1607,21 @@ static int hidden_dw_tc(ocf_model* m, int l, int B, const float* hin, const OptD
 // into the peer exchange).
 // xslot: write the row statistics [B, 4] and dL/dh [B, hp] into this exchange slot instead of the
 // model's buffers (a peer all-reduce follows).
+// after_kernel: the previous operation in the stream is a kernel (the phase's first launch may be a dependent launch)
 static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args,
-                        float* dense_out, cudaStream_t st, bool act0_done = false, float* xslot = nullptr) {
+                        float* dense_out, cudaStream_t st, bool act0_done = false, float* xslot = nullptr, bool after_kernel = false) {
   const BatchDev& bt = b->dev;
   const int L = m->L, B = bt.B;
   const bool drop = training && m->cfg.dropout_p > 0.f;
-  if (!act0_done) OCF_TRY(launch_act(m, 0, B, training, args, st));
+  bool dep = after_kernel && !g_prof.on;       // instrumented passes record events between the kernels
+  if (!act0_done) { OCF_TRY(launch_act(m, 0, B, training, args, st)); dep = !g_prof.on; }
   for (int l = 1; l < L; ++l) {
     // hidden layer: product + bias + activation + dropout in the GEMM's epilogue
     GemmEpi ep{}; ep.kind = EPI_BIAS_ACT; ep.C = m->zsum[l]; ep.ldc = m->hp[l]; ep.actargs = act_args(m, l, B, training, args);
     const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
-    if (tc_hidden()) OCF_TRY(hidden_fwd_tc(m, l, B, hin, ep.actargs, st));
+    if (tc_hidden()) OCF_TRY(hidden_fwd_tc(m, l, B, hin, ep.actargs, st, dep));
     else OCF_TRY(launch_gemm(m, false, false, hin, m->hp[l - 1], m->layers[l].W, m->hp[l], B, m->hp[l], m->hp[l - 1], ep, st));
+    dep = !g_prof.on;
   }
   const float* htop = drop ? m->h[L - 1] : m->act[L - 1];
   const int hpt = m->hp[L - 1];
@@ -1611,13 +1632,13 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   float4* dh_out = reinterpret_cast<float4*>(xslot ? xslot + (size_t)B * ROWSTAT_W : m->dh_top);
   g_prof.begin(2, st);
   if (training) {
-    OCF_NV_SWITCH(hpt, k_dec_fwd<NV, true><<<item_grid(m, b), 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, gscale,
-                                                                        m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2), m->itemstats, dense_out, m->cfg.n_cols,
-                                                                        m->tail, dh_out, stats_out));
+    OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, k_dec_fwd<NV, true>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
+                                           (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2),
+                                           m->itemstats, dense_out, m->cfg.n_cols, m->tail, dh_out, stats_out)));
   } else {
-    OCF_NV_SWITCH(hpt, k_dec_fwd<NV, false><<<item_grid(m, b), 128, 0, st>>>(bt, m->layers[L].W, m->layers[L].b, htop, gscale,
-                                                                         m->cfg.loss, nullptr, nullptr, m->itemstats, dense_out, m->cfg.n_cols,
-                                                                         m->tail, nullptr, stats_out));
+    OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, k_dec_fwd<NV, false>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
+                                           (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, (float*)nullptr, (float4*)nullptr,
+                                           m->itemstats, dense_out, m->cfg.n_cols, m->tail, (float4*)nullptr, stats_out)));
   }
   OCF_LAUNCHED();
   g_prof.end(2, st);
@@ -1662,21 +1683,22 @@ static int launch_reg(ocf_model* m, cudaStream_t st) {
 }
 
 template <int NV, bool WIDE>
-static int launch_row_update_nv(int kind, int grid, const RowArgs& r, cudaStream_t st) {
+static int launch_row_update_nv(int kind, int grid, const RowArgs& r, cudaStream_t st, bool dep) {
+  const dim3 g(grid), b(256);
   switch (kind) {
-    case OCF_OPT_SGD: k_row_update<NV, OCF_OPT_SGD, WIDE><<<grid, 256, 0, st>>>(r); break;
-    case OCF_OPT_ADAGRAD: k_row_update<NV, OCF_OPT_ADAGRAD, WIDE><<<grid, 256, 0, st>>>(r); break;
-    case OCF_OPT_RMSPROP: k_row_update<NV, OCF_OPT_RMSPROP, WIDE><<<grid, 256, 0, st>>>(r); break;
-    case KIND_GRAD: k_row_update<NV, KIND_GRAD, false><<<grid, 256, 0, st>>>(r); break;
-    default: k_row_update<NV, OCF_OPT_ADAM, WIDE><<<grid, 256, 0, st>>>(r); break;
+    case OCF_OPT_SGD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_SGD, WIDE>, g, b, st, r)); break;
+    case OCF_OPT_ADAGRAD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_ADAGRAD, WIDE>, g, b, st, r)); break;
+    case OCF_OPT_RMSPROP: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_RMSPROP, WIDE>, g, b, st, r)); break;
+    case KIND_GRAD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, KIND_GRAD, false>, g, b, st, r)); break;
+    default: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_ADAM, WIDE>, g, b, st, r)); break;
   }
   OCF_LAUNCHED();
   return OCF_OK;
 }
 
-static int launch_row_update(int hp, int kind, int grid, bool wide, const RowArgs& r, cudaStream_t st) {
-  if (wide) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, true>(kind, grid, r, st))); }
-  else { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false>(kind, grid, r, st))); }
+static int launch_row_update(int hp, int kind, int grid, bool wide, const RowArgs& r, cudaStream_t st, bool dep) {
+  if (wide) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, true>(kind, grid, r, st, dep))); }
+  else { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false>(kind, grid, r, st, dep))); }
   return OCF_OK;
 }
 
@@ -1702,9 +1724,9 @@ static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
     g_prof.begin(3, st);
     k_sort_count<<<grid, 128, 0, st>>>(a);
     OCF_LAUNCHED();
-    k_sort_alloc<<<(m->cfg.n_cols + 255) / 256, 256, 0, st>>>(a);
+    OCF_CUDA(launch_pdl(!g_prof.on, k_sort_alloc, dim3((m->cfg.n_cols + 255) / 256), dim3(256), st, a));
     OCF_LAUNCHED();
-    k_sort_place<<<grid, 128, 0, st>>>(a);
+    OCF_CUDA(launch_pdl(!g_prof.on, k_sort_place, dim3(grid), dim3(128), st, a));
     OCF_LAUNCHED();
     g_prof.end(3, st);
     return OCF_OK;
@@ -1751,7 +1773,8 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   g_prof.begin(5, st);
   // small catalogues (weights + state within reach of the 126 MB L2): latency-bound, wide walk; else HBM-bound
   const bool wide = !grad_mode && (size_t)m->cfg.n_cols * (size_t)hpx <= ((size_t)8 << 20);
-  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count * (wide ? 4 : 6), wide, r, st));
+  // a dependent launch: its predecessor in this stream is a kernel (the backward pass, or the first of two row updates)
+  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count * (wide ? 4 : 6), wide, r, st, !g_prof.on));
   g_prof.end(5, st);
   return OCF_OK;
 }
@@ -1778,7 +1801,7 @@ static int fork_scan(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
 // (zeroed first: untouched weight rows have no gradient) and nothing is applied or logged; the
 // caller all-reduces the arena and runs apply_gradients().
 static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* args, cudaStream_t st, bool grad_mode = false,
-                        int* n_reg_out = nullptr) {
+                        int* n_reg_out = nullptr, bool after_kernel = false) {
   const BatchDev& bt = b->dev;
   const int L = m->L, B = bt.B;
   const bool drop = m->cfg.dropout_p > 0.f;
@@ -1786,6 +1809,8 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   const int n_reg = launch_reg(m, st);          // L2 term of the reported loss uses pre-update weights
   if (n_reg_out) *n_reg_out = n_reg;
   if (grad_mode) OCF_CUDA(cudaMemsetAsync(m->grads, 0, sizeof(float) * m->grads_count, st));
+  // dependent launches (PDL) from here on whenever the previous operation in the stream is a kernel
+  bool dep = (after_kernel || n_reg > 0) && !grad_mode && !g_prof.on;
   // top hidden layer: dz and its bias
   {
     const int l = L - 1;
@@ -1794,29 +1819,30 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     // other ranks' row statistics first and computes it after the gather)
     MetricArgs met{};
     if (!grad_mode) met = metric_args(m, B, args, n_reg, true);
-    k_dz_bias<<<m->hp[l] / 32 + (grad_mode ? 0 : 1), 1024, 0, st>>>(m->dh_top, m->act[l], drop ? m->dscale[l] : nullptr, B, m->hp[l],
-                                                     m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt, ly.trainable ? 1 : 0,
-                                                     grad_mode ? m->gb[l] : nullptr, met);
+    OCF_CUDA(launch_pdl(dep, k_dz_bias, dim3(m->hp[l] / 32 + (grad_mode ? 0 : 1)), dim3(1024), st, (const float*)m->dh_top, (const float*)m->act[l],
+                        (const float*)(drop ? m->dscale[l] : nullptr), B, m->hp[l], m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt,
+                        ly.trainable ? 1 : 0, grad_mode ? m->gb[l] : (float*)nullptr, met));
     OCF_LAUNCHED();
+    dep = !g_prof.on;
   }
   for (int l = L - 1; l >= 1; --l) {
     Layer& ly = m->layers[l];
     // dz_{l-1} = (dz_l . W_l^T) * dropout scale * act'(a_{l-1})   (uses W_l before its update)
     GemmEpi ep{}; ep.kind = EPI_DZ; ep.C = m->dz[l - 1]; ep.ldc = m->hp[l - 1]; ep.aux0 = m->act[l - 1];
     ep.aux1 = drop ? m->dscale[l - 1] : nullptr; ep.act = m->cfg.activation;
-    if (tc_hidden()) OCF_TRY(hidden_dz_tc(m, l, B, drop, st));
+    if (tc_hidden()) OCF_TRY(hidden_dz_tc(m, l, B, drop, st, dep));
     else OCF_TRY(launch_gemm(m, false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
     Layer& lo = m->layers[l - 1];
-    k_dz_bias<<<m->hp[l - 1] / 32, 1024, 0, st>>>(m->dz[l - 1], nullptr, nullptr, B, m->hp[l - 1], m->cfg.activation, 1,
-                                                         m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0,
-                                                         grad_mode ? m->gb[l - 1] : nullptr, MetricArgs{});
+    OCF_CUDA(launch_pdl(dep, k_dz_bias, dim3(m->hp[l - 1] / 32), dim3(1024), st, (const float*)m->dz[l - 1], (const float*)nullptr, (const float*)nullptr,
+                        B, m->hp[l - 1], m->cfg.activation, 1, m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0,
+                        grad_mode ? m->gb[l - 1] : (float*)nullptr, MetricArgs{}));
     OCF_LAUNCHED();
     if (ly.trainable) {
       // dW_l = h_{l-1}^T . dz_l, fused with the update of W_l
       GemmEpi eu{}; eu.kind = EPI_UPDATE; eu.C = ly.W; eu.ldc = m->hp[l]; eu.s1 = ly.Ws1; eu.s2 = ly.Ws2; eu.opt = opt;
       if (grad_mode) { eu.kind = EPI_STORE; eu.C = m->gW[l]; }
       const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
-      if (tc_hidden()) OCF_TRY(hidden_dw_tc(m, l, B, hin, opt, grad_mode ? m->gW[l] : nullptr, st));
+      if (tc_hidden()) OCF_TRY(hidden_dw_tc(m, l, B, hin, opt, grad_mode ? m->gW[l] : nullptr, st, dep));
       else OCF_TRY(launch_gemm(m, true, false, hin, m->hp[l - 1], m->dz[l], m->hp[l], m->hp[l - 1], m->hp[l], B, eu, st));
     }
   }
@@ -2068,8 +2094,8 @@ static int train_body(ocf_model* m, ocf_batch* b, const ocf_step_args* args, cud
   }
   OCF_TRY(fork_scan(m, b, st));
   OCF_TRY(phase_encode(m, b, st, nullptr, true, true, args));
-  OCF_TRY(phase_decode(m, b, true, args, nullptr, st, true));
-  return phase_update(m, b, args, st);
+  OCF_TRY(phase_decode(m, b, true, args, nullptr, st, true, nullptr, true));
+  return phase_update(m, b, args, st, false, nullptr, true);
 }
 
 static int eval_body(ocf_model* m, ocf_batch* b, const ocf_step_args* args, cudaStream_t st) {
@@ -2079,7 +2105,7 @@ static int eval_body(ocf_model* m, ocf_batch* b, const ocf_step_args* args, cuda
     OCF_TRY(decode_exchange(m, b, false, args, st, act0));
   } else {
     OCF_TRY(phase_encode(m, b, st, nullptr, true, false, args));
-    OCF_TRY(phase_decode(m, b, false, args, nullptr, st, true));
+    OCF_TRY(phase_decode(m, b, false, args, nullptr, st, true, nullptr, true));
   }
   const int n_reg = launch_reg(m, st);
   return launch_metrics(m, b->dev.B, args, n_reg, false, st);
@@ -2118,7 +2144,12 @@ static int run_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, bool 
       g_launches.store(launched);
       if (rc == OCF_OK && graph != nullptr && cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; }
       if (graph) cudaGraphDestroy(graph);
-      if (g.exec == nullptr) g.failed = true;          // this combination keeps running as plain launches
+      if (g.exec == nullptr) {                         // this combination keeps running as plain launches
+        g.failed = true;
+        if (std::getenv("OCF_DEBUG_GRAPH")) std::fprintf(stderr, "[ocf] step graph capture failed (rc %d): plain launches from here on\n", rc);
+      } else if (std::getenv("OCF_DEBUG_GRAPH")) {
+        std::fprintf(stderr, "[ocf] step graph captured: %d kernels\n", g.kernels);
+      }
     }
     if (g.exec != nullptr) {
       OCF_CUDA(cudaGraphLaunch(g.exec, st));

@@ -219,6 +219,15 @@ __device__ __forceinline__ double mt_double(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// Programmatic dependent launch (PDL). A kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream still runs: `pdl_trigger` (first statement) lets the NEXT
+// kernel do so as soon as every CTA of this grid has started, `pdl_wait` blocks until the PREVIOUS grid has
+// completed and its writes are visible - nothing the predecessor produces may be read before it. Between two
+// dependent small kernels this hides the launch latency and the prologue (a training step of the small catalogues
+// is a chain of 9-13 such kernels). Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

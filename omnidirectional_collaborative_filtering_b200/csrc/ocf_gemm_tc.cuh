@@ -189,6 +189,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* tfull = bars + 3 * STAGES;    // [1] MMA -> epilogue
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull + 1);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GM;             // first output row (lane dimension) of the tile
   const int c0 = blockIdx.y * NB;             // first output column
@@ -208,6 +209,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_holder);
+  pdl_wait();                                 // barriers and TMEM are set up while the previous kernel drains
 
   if (warp == 0) {
     // ---- TMA producer: raw fp32 tiles into the hi halves of the stage ------------------------------------
@@ -414,7 +416,7 @@ inline int pick_split(int total_k_blocks, int tiles) {
 
 // D[m_len, n_len] over a contraction of k_len elements (a multiple of 32 after zero fill).
 inline int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmTcArgs g, int m_len, int n_len, int k_len, cudaStream_t st,
-                  int want_split = 0) {
+                  int want_split = 0, bool pdl = false) {
   static bool attr_set = false;
   if (!attr_set) {
     OCF_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -438,10 +440,12 @@ inline int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmTcArgs g, in
   cfg.blockDim = dim3(NTHREADS, 1, 1);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)split;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
   OCF_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc, ma, mb, g));
   OCF_LAUNCHED();
   return OCF_OK;

@@ -459,6 +459,8 @@ template <int NV>
 __global__ void __launch_bounds__(128)
 k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int3 bits,
           float4* __restrict__ P, TailBuf tb, float4* __restrict__ z_out, int fuse_act, ActArgs act) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int HP = NV * 128;
   __shared__ float4 red[4][HP / 4];
   __shared__ int2 s_list[128 * 3];          // (weight row, coefficient bits) of the row loads of 128 entries
@@ -547,6 +549,8 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
           const float* __restrict__ h, float gscale, int loss_kind,
           float* __restrict__ dy, float4* __restrict__ P2, float* __restrict__ itemstats,
           float* __restrict__ dense_out, int n_cols, TailBuf tb, float4* __restrict__ dh_out, float* __restrict__ rowstats) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int HP = NV * 128;
   __shared__ float4 red[TRAIN ? 4 : 1][HP / 4];
   __shared__ float sred[4][3];
@@ -671,6 +675,8 @@ k_dz_bias(const float* __restrict__ dh, const float* __restrict__ a, const float
           int B, int HP, int act, int dh_is_dz, float* __restrict__ dz, float* __restrict__ bias,
           float* __restrict__ s1, float* __restrict__ s2, OptDev o, int trainable, float* __restrict__ gbias,
           MetricArgs met) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[32][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x * 32 >= HP) {           // the extra CTA: metrics of the step (train.py:102-121)
@@ -1072,6 +1078,8 @@ __global__ void __launch_bounds__(128) k_sort_count(SortArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_sort_alloc(SortArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * 256 + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int n = 0, n_tasks = 0;
@@ -1110,6 +1118,8 @@ __global__ void __launch_bounds__(256) k_sort_alloc(SortArgs a) {
 }
 
 __global__ void __launch_bounds__(128) k_sort_place(SortArgs a) {
+  pdl_trigger();
+  pdl_wait();
   if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
   const int4 it = a.bt.items[blockIdx.x];
   const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
@@ -1150,6 +1160,8 @@ constexpr int KIND_GRAD = 4;              // k_row_update: store the gradient ro
 template <int NV, int KIND, bool WIDE>
 __global__ void __launch_bounds__(256, WIDE ? (NV <= 4 ? 2 : 1) : (KIND == OCF_OPT_ADAM ? (NV <= 4 ? 2 : 1) : (NV <= 4 ? 3 : 2)))
 k_row_update(RowArgs a) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int HP = NV * 128;
   constexpr bool LOAD_W = KIND != KIND_GRAD;
   const int lane = threadIdx.x & 31;

@@ -1,0 +1,12 @@
+#!/bin/bash
+# round 2, call s: programmatic dependent launches across the step: parity suite, then the five workloads with PDL on / off
+out=gpurun_out; tag=${1:-r02s}
+mkdir -p $out
+timeout 1200 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_model.py tests/test_gpu_train.py tests/test_gpu_score.py tests/test_gpu_shards.py tests/test_gpu_checkpoint.py tests/test_gpu_full_configs.py tests/test_gpu_xl_sizes.py -q -m gpu -k "not netflix" > $out/${tag}_tests.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_tests.log
+tail -6 $out/${tag}_tests.log
+for w in ${WORKLOADS:-jester ml1m ml20m ml10m}; do
+  OCF_DEBUG_GRAPH=1 timeout 600 python bench.py --workload $w --steps 30 --no-cpu-baseline --no-scoring > $out/${tag}_bench_$w.json 2> $out/${tag}_bench_$w.err
+  grep -c "graph captured" $out/${tag}_bench_$w.err; grep "capture failed" $out/${tag}_bench_$w.err | head -2
+  OCF_NO_PDL=1 timeout 600 python bench.py --workload $w --steps 30 --no-cpu-baseline --no-scoring > $out/${tag}_bench_${w}_nopdl.json 2> $out/${tag}_bench_${w}_nopdl.err
+done
+python scripts/show_quick.py $tag "" _nopdl 2>/dev/null | grep -v "ERR\|GB/s"
