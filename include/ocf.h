@@ -270,6 +270,12 @@ int ocf_score_topk(ocf_model* model, ocf_batch* batch, int32_t k, int exclude_in
  * split: 0 = the library's choice, else the cluster size along the contraction (1, 2, 4 or 8). */
 int ocf_gemm_tc(const float* a, int a_mn, const float* b, int b_mn, int32_t m_len, int32_t n_len, int32_t k_len,
                 int terms, int split, float* out);
+/* Diagnostic twin (scripts/gemm_tc_bench.py): `reps` back-to-back launches of the kernel on zeroed device operands with
+ * epilogue `kind` (1 = backward, 2 = gradient + Adagrad update, 3 = store); CUDA-event milliseconds per launch and
+ * eight %globaltimer stamps (ns from kernel entry) of one CTA: entry, set-up done, first operands landed, products
+ * done, tile parked + cluster barrier, epilogue done, second cluster barrier, exit. */
+int ocf_gemm_tc_profile(int a_mn, int b_mn, int32_t m_len, int32_t n_len, int32_t k_len, int split, int kind, int reps,
+                        float* ms_per_launch, int64_t stamps_ns[8]);
 /* Copies `count` metric records starting at step slot `first` of the device log to the host
  * (synchronises `stream`). The log keeps the last 4096 steps. */
 int ocf_model_read_metrics(ocf_model* model, int64_t first, int32_t count, float* host,

@@ -109,6 +109,8 @@ _SIGNATURES = {
     "ocf_score": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "ocf_score_topk": (C.c_int, [_P, _P, C.c_int32, C.c_int, _P, _P, _P]),
     "ocf_gemm_tc": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, _P]),
+    "ocf_gemm_tc_profile": (C.c_int, [C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "ocf_model_read_metrics": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "ocf_model_wait_metrics": (C.c_int, [_P, C.c_int64, _P]),
     "ocf_model_steps_logged": (C.c_int64, [_P]),

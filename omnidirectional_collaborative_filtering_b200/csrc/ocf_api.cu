@@ -246,6 +246,7 @@ struct ocf_model {
   int32_t* col_mcol = nullptr;
   int2* col_seg = nullptr;
   int4* col_tasks = nullptr;
+  int4* col_heavy = nullptr;      // tasks with more than HEAVY_N matches (batch-side K4a only), same capacity as col_tasks
   int* col_counters = nullptr;
   float* gemm_part = nullptr;     // split-K partials of the hidden-layer GEMMs
   int32_t* topk_cols = nullptr;   // top-k epilogue outputs [max_rows, 512] (allocated with dense_out's arena)
@@ -1211,7 +1212,7 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   }
   if (st) return bail(st);
   if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_step, 1, true)) ||
-      (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_seg, (size_t)N, true)) ||
+      (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_heavy, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_seg, (size_t)N, true)) ||
       (st = m->mem.get(&m->col_counters, 4, true)) || (st = m->mem.get(&m->col_state, (size_t)2 * N, true)) ||
       (st = m->mem.get(&m->col_info, (size_t)N)))
     return bail(st);
@@ -1682,24 +1683,35 @@ static int launch_reg(ocf_model* m, cudaStream_t st) {
   return N_REGPART * (m->L + 1);
 }
 
-template <int NV, bool WIDE>
+template <int NV, bool WIDE, bool HEAVY>
 static int launch_row_update_nv(int kind, int grid, const RowArgs& r, cudaStream_t st, bool dep) {
   const dim3 g(grid), b(256);
   switch (kind) {
-    case OCF_OPT_SGD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_SGD, WIDE>, g, b, st, r)); break;
-    case OCF_OPT_ADAGRAD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_ADAGRAD, WIDE>, g, b, st, r)); break;
-    case OCF_OPT_RMSPROP: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_RMSPROP, WIDE>, g, b, st, r)); break;
-    case KIND_GRAD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, KIND_GRAD, false>, g, b, st, r)); break;
-    default: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_ADAM, WIDE>, g, b, st, r)); break;
+    case OCF_OPT_SGD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_SGD, WIDE, HEAVY>, g, b, st, r)); break;
+    case OCF_OPT_ADAGRAD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_ADAGRAD, WIDE, HEAVY>, g, b, st, r)); break;
+    case OCF_OPT_RMSPROP: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_RMSPROP, WIDE, HEAVY>, g, b, st, r)); break;
+    case KIND_GRAD: OCF_CUDA(launch_pdl(dep, k_row_update<NV, KIND_GRAD, false, false>, g, b, st, r)); break;
+    default: OCF_CUDA(launch_pdl(dep, k_row_update<NV, OCF_OPT_ADAM, WIDE, HEAVY>, g, b, st, r)); break;
   }
   OCF_LAUNCHED();
   return OCF_OK;
 }
 
-static int launch_row_update(int hp, int kind, int grid, bool wide, const RowArgs& r, cudaStream_t st, bool dep) {
-  if (wide) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, true>(kind, grid, r, st, dep))); }
-  else { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false>(kind, grid, r, st, dep))); }
+static int launch_row_update(int hp, int kind, int grid, bool wide, bool heavy, const RowArgs& r, cudaStream_t st, bool dep) {
+  if (wide) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, true, true>(kind, grid, r, st, dep))); }
+  else if (heavy) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false, true>(kind, grid, r, st, dep))); }
+  else { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false, false>(kind, grid, r, st, dep))); }
   return OCF_OK;
+}
+
+static bool heavy_rows() {            // OCF_NO_HEAVY=1: every update task is one warp's, whatever its length
+  static const bool on = [] { const char* e = std::getenv("OCF_NO_HEAVY"); return !(e && e[0] == '1'); }();
+  return on;
+}
+// Catalogues whose weights are within reach of the 126 MB L2 (n_cols x hp <= 32 M floats): the update is bound by its
+// longest chain of dependent L2 round trips, so long chains are split over a CTA; beyond that it is HBM-bound.
+static bool heavy_model(const ocf_model* m) {
+  return heavy_rows() && (size_t)m->cfg.n_cols * (size_t)std::max(m->hp[0], m->hp[m->L - 1]) <= ((size_t)32 << 20);
 }
 
 // K4a: the batch's ratings grouped by catalogue column -> match list + update tasks.
@@ -1718,7 +1730,7 @@ static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
     a.bt = bt;
     a.cnt = m->col_state; a.codeor = m->col_state + N;
     a.colinfo = m->col_info; a.bits = m->col_bits; a.W = W; a.counters = m->col_counters;
-    a.matches = m->col_matches; a.tasks = m->col_tasks; a.colseg = m->col_seg;
+    a.matches = m->col_matches; a.tasks = m->col_tasks; a.colseg = m->col_seg; a.heavy = heavy_model(m) ? m->col_heavy : nullptr;
     a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits3 = m->bits; a.dense = dense; a.do_dec = do_dec; a.do_enc = do_enc;
     const int grid = item_grid(m, b);
     g_prof.begin(3, st);
@@ -1762,6 +1774,10 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   Layer& dec = m->layers[L];
   RowArgs r{};
   r.matches = m->col_matches; r.tasks = m->col_tasks; r.colseg = m->col_seg; r.counters = m->col_counters;
+  // small catalogues (weights + state within reach of the 126 MB L2): latency-bound, wide walk; else HBM-bound
+  const bool wide = !grad_mode && (size_t)m->cfg.n_cols * (size_t)hpx <= ((size_t)8 << 20);
+  const bool heavy = (wide || heavy_model(m)) && heavy_rows() && !b->store->has_dups && !grad_mode;
+  r.heavy = heavy ? m->col_heavy : nullptr;      // the batch-side K4a lists them; the CSC scan does not
   r.hdec = drop ? m->h[L - 1] : m->act[L - 1]; r.dz0 = m->dz[0]; r.dy = m->dy;
   r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
   r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
@@ -1771,10 +1787,8 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   if (do_dec) r.arr_map[r.n_arr++] = 0;
   if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
   g_prof.begin(5, st);
-  // small catalogues (weights + state within reach of the 126 MB L2): latency-bound, wide walk; else HBM-bound
-  const bool wide = !grad_mode && (size_t)m->cfg.n_cols * (size_t)hpx <= ((size_t)8 << 20);
   // a dependent launch: its predecessor in this stream is a kernel (the backward pass, or the first of two row updates)
-  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count * (wide ? 4 : 6), wide, r, st, !g_prof.on));
+  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count * (wide ? 4 : 6), wide, heavy, r, st, !g_prof.on));
   g_prof.end(5, st);
   return OCF_OK;
 }
@@ -2369,6 +2383,44 @@ extern "C" int ocf_gemm_tc(const float* a, int a_mn, const float* b, int b_mn, i
   OCF_TRY(gtc::launch(ma, mb, g, m_len, n_len, k_len, nullptr, split));
   OCF_CUDA(cudaDeviceSynchronize());
   OCF_CUDA(cudaMemcpy(out, dc, nc * sizeof(float), cudaMemcpyDeviceToHost));
+  return OCF_OK;
+}
+
+// Diagnostic twin of ocf_gemm_tc: `reps` launches of the update-kind contraction (read-modify-write epilogue) on
+// device-resident random operands, CUDA-event time per launch and the phase stamps of CTA (0,0,0) of the last launch.
+extern "C" int ocf_gemm_tc_profile(int a_mn, int b_mn, int32_t m_len, int32_t n_len, int32_t k_len, int split, int kind, int reps,
+                                   float* ms_per_launch, int64_t stamps_ns[8]) {
+  OCF_REQUIRE(ms_per_launch && stamps_ns && reps > 0, "ocf_gemm_tc_profile: bad argument");
+  Arena mem;
+  struct Release { Arena& a; ~Release() { a.release(); } } release_on_exit{mem};
+  float *da = nullptr, *db = nullptr, *dc = nullptr, *ds = nullptr, *dx = nullptr;
+  unsigned long long* dbg = nullptr;
+  const size_t na = (size_t)m_len * k_len, nb = (size_t)n_len * k_len, nc = (size_t)m_len * n_len;
+  OCF_TRY(mem.get(&da, na, true)); OCF_TRY(mem.get(&db, nb, true)); OCF_TRY(mem.get(&dc, nc, true)); OCF_TRY(mem.get(&ds, nc, true));
+  OCF_TRY(mem.get(&dx, nc, true)); OCF_TRY(mem.get(&dbg, 8, true));
+  StepDev* dstep = nullptr;
+  OCF_TRY(mem.get(&dstep, 1, true));
+  CUtensorMap ma, mb;
+  if (a_mn) OCF_TRY(gtc::make_map_mn(&ma, da, m_len, m_len, k_len)); else OCF_TRY(gtc::make_map_k(&ma, da, k_len, k_len, m_len));
+  if (b_mn) OCF_TRY(gtc::make_map_mn(&mb, db, n_len, n_len, k_len)); else OCF_TRY(gtc::make_map_k(&mb, db, k_len, k_len, n_len));
+  gtc::GemmTcArgs g{};
+  g.kind = kind; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0; g.C = dc; g.ldc = m_len; g.terms = 3; g.dbg = dbg;
+  g.s1 = ds; g.aux0 = dx; g.act = OCF_ACT_SIGMOID;
+  g.opt.kind = OCF_OPT_ADAGRAD; g.opt.eps = 1e-8f; g.opt.st = dstep;
+  cudaEvent_t e0, e1;
+  OCF_CUDA(cudaEventCreate(&e0)); OCF_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) OCF_TRY(gtc::launch(ma, mb, g, m_len, n_len, k_len, nullptr, split));
+  OCF_CUDA(cudaEventRecord(e0, nullptr));
+  for (int i = 0; i < reps; ++i) OCF_TRY(gtc::launch(ma, mb, g, m_len, n_len, k_len, nullptr, split));
+  OCF_CUDA(cudaEventRecord(e1, nullptr));
+  OCF_CUDA(cudaDeviceSynchronize());
+  float ms = 0.f;
+  OCF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_launch = ms / reps;
+  unsigned long long h[8];
+  OCF_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; ++i) stamps_ns[i] = (int64_t)(h[i] - h[0]);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return OCF_OK;
 }
 

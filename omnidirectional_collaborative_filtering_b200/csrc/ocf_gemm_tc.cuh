@@ -23,8 +23,8 @@
 // a cluster barrier every CTA sums a 1/S slice of the tile's columns over all ranks IN RANK ORDER through distributed
 // shared memory (ld.shared::cluster) and runs the epilogue on it. Bit-reproducible.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = operand splitter
-// during the main loop, then epilogue (one TMEM lane quarter each).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = operand splitters
+// during the main loop, then epilogue (two warps per TMEM lane quarter, alternating column groups).
 #pragma once
 
 #include <cuda.h>
@@ -41,7 +41,8 @@ using tc::smem_u32;
 constexpr int GM = 128;            // accumulator rows = TMEM lanes = UMMA M
 constexpr int NB = 128;            // accumulator columns per tile = UMMA N
 constexpr int BK = 32;             // contraction elements per stage (one 128-byte swizzle row)
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter; also the operand splitters of the main loop
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int TILE_BYTES = GM * BK * 4;              // 16 KB: one operand tile of a stage (A and B are both 128 x 32)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A hi | B hi | A lo | B lo
 constexpr int STAGES = 3;
@@ -66,7 +67,16 @@ struct GemmTcArgs {
   int act;
   OptDev opt;
   ActArgs actargs;       // FWD: bias + activation + dropout of the layer (a_out / h_out / dscale are [b, hp4 * 4])
+  unsigned long long* dbg;   // diagnostic (scripts/gemm_tc_bench.py): 8 %globaltimer stamps of CTA (0,0,0), else null
 };
+
+__device__ __forceinline__ void stamp(const GemmTcArgs& g, int slot) {
+  if (g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.dbg[slot] = t;
+  }
+}
 
 // instruction descriptor (kind::tf32): D = f32, A = B = tf32, M = 128, N = NB; bits 15 / 16 = A / B is MN-major
 __host__ __device__ constexpr uint32_t idesc_of(bool a_mn, bool b_mn) {
@@ -117,7 +127,29 @@ struct EpiRegs {            // per-thread constants of the epilogue, read once
   float lr; float bias; uint32_t drop_step; uint2 drop_key; uint32_t drop_thresh; float drop_inv;
 };
 
-__device__ __forceinline__ void epi_batch(const GemmTcArgs& g, const EpiRegs& e, int m, int c_first, int n_ok, const float (&v)[EB]) {
+struct EpiPre { float a[EB], b[EB], c[EB]; };      // what the batch's epilogue reads from global memory
+
+// issued before the distributed-shared-memory reduction of the batch, so both latencies overlap
+__device__ __forceinline__ void epi_prefetch(const GemmTcArgs& g, int m, int c_first, int n_ok, EpiPre& p) {
+  if (g.kind == GEPI_DZ) {
+#pragma unroll
+    for (int j = 0; j < EB; ++j) {
+      const size_t idx = (size_t)(c_first + j) * g.ldc + m;
+      p.a[j] = j < n_ok ? __ldcg(g.aux0 + idx) : 0.f;
+      p.b[j] = (j < n_ok && g.aux1 != nullptr) ? __ldcg(g.aux1 + idx) : 1.f;
+    }
+  } else if (g.kind == GEPI_UPDATE) {
+#pragma unroll
+    for (int j = 0; j < EB; ++j) {
+      const size_t idx = (size_t)(c_first + j) * g.ldc + m;
+      p.a[j] = j < n_ok ? __ldcg(g.C + idx) : 0.f;
+      p.b[j] = (j < n_ok && g.s1 != nullptr) ? __ldcg(g.s1 + idx) : 0.f;
+      p.c[j] = (j < n_ok && g.s2 != nullptr) ? __ldcg(g.s2 + idx) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_apply(const GemmTcArgs& g, const EpiRegs& e, int m, int c_first, int n_ok, const float (&v)[EB], EpiPre& p) {
   switch (g.kind) {
     case GEPI_FWD: {            // m = hidden unit n, columns = batch rows b
       const ActArgs& a = g.actargs;
@@ -139,37 +171,22 @@ __device__ __forceinline__ void epi_batch(const GemmTcArgs& g, const EpiRegs& e,
         reinterpret_cast<float*>(a.h_out)[idx] = z;
       }
     } break;
-    case GEPI_DZ: {             // m = unit k of the layer below, columns = batch rows b
-      float av[EB], sc[EB];
-#pragma unroll
-      for (int j = 0; j < EB; ++j) {
-        const size_t idx = (size_t)(c_first + j) * g.ldc + m;
-        av[j] = j < n_ok ? __ldcg(g.aux0 + idx) : 0.f;
-        sc[j] = (j < n_ok && g.aux1 != nullptr) ? __ldcg(g.aux1 + idx) : 1.f;
-      }
+    case GEPI_DZ:               // m = unit k of the layer below, columns = batch rows b
 #pragma unroll
       for (int j = 0; j < EB; ++j)
-        if (j < n_ok) g.C[(size_t)(c_first + j) * g.ldc + m] = v[j] * sc[j] * act_bwd(g.act, av[j]);
-    } break;
-    case GEPI_UPDATE: {         // m = fan-out n, columns = fan-in k: W[k, n]
-      float w[EB], t1[EB], t2[EB];
-#pragma unroll
-      for (int j = 0; j < EB; ++j) {
-        const size_t idx = (size_t)(c_first + j) * g.ldc + m;
-        w[j] = j < n_ok ? __ldcg(g.C + idx) : 0.f;
-        t1[j] = (j < n_ok && g.s1 != nullptr) ? __ldcg(g.s1 + idx) : 0.f;
-        t2[j] = (j < n_ok && g.s2 != nullptr) ? __ldcg(g.s2 + idx) : 0.f;
-      }
+        if (j < n_ok) g.C[(size_t)(c_first + j) * g.ldc + m] = v[j] * p.b[j] * act_bwd(g.act, p.a[j]);
+      break;
+    case GEPI_UPDATE:           // m = fan-out n, columns = fan-in k: W[k, n]
 #pragma unroll
       for (int j = 0; j < EB; ++j) {
         if (j >= n_ok) break;
         const size_t idx = (size_t)(c_first + j) * g.ldc + m;
-        opt_apply(g.opt, e.lr, v[j], w[j], t1[j], t2[j]);
-        g.C[idx] = w[j];
-        if (g.s1) g.s1[idx] = t1[j];
-        if (g.s2) g.s2[idx] = t2[j];
+        opt_apply(g.opt, e.lr, v[j], p.a[j], p.b[j], p.c[j]);
+        g.C[idx] = p.a[j];
+        if (g.s1) g.s1[idx] = p.b[j];
+        if (g.s2) g.s2[idx] = p.c[j];
       }
-    } break;
+      break;
     default:                    // STORE / RAW: out[c, m]
 #pragma unroll
       for (int j = 0; j < EB; ++j)
@@ -190,6 +207,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull + 1);
 
   pdl_trigger();
+  stamp(g, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GM;             // first output row (lane dimension) of the tile
   const int c0 = blockIdx.y * NB;             // first output column
@@ -197,7 +215,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const uint32_t rank = g.split > 1 ? tc::cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&ready[s], 4); tc::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&ready[s], EPI_WARPS); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -210,6 +228,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_holder);
   pdl_wait();                                 // barriers and TMEM are set up while the previous kernel drains
+  stamp(g, 1);
 
   if (warp == 0) {
     // ---- TMA producer: raw fp32 tiles into the hi halves of the stage ------------------------------------
@@ -263,14 +282,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
   } else {
     // ---- operand splitter: x -> hi = tf32(x) (round to nearest, in place), lo = x - hi (exact) ----------
-    const int t = threadIdx.x - 64;        // 0..127
+    const int t = threadIdx.x - 64;        // 0..255
     int stage = 0; uint32_t phase = 0;
     for (int k = 0; k < g.k_blocks; ++k) {
       tc::mbar_wait(&full[stage], phase);
+      if (k == 0) stamp(g, 2);
       float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
       float4* lo = hi + 2 * TILE_BYTES / 16;
 #pragma unroll 4
-      for (int i = t; i < 2 * TILE_BYTES / 16; i += 128) {
+      for (int i = t; i < 2 * TILE_BYTES / 16; i += 32 * EPI_WARPS) {
         const float4 x = hi[i];
         float4 h, l;
         h.x = __uint_as_float((__float_as_uint(x.x) + 0x1000u) & 0xFFFFE000u); l.x = x.x - h.x;
@@ -289,6 +309,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   // ---- epilogue -------------------------------------------------------------------------------------------
   const int q = warp & 3;                      // TMEM lane quarter of an epilogue warp
+  const int half = warp >= 6 ? 1 : 0;          // the two warps of a quarter alternate column groups
   const int ml = q * 32 + lane;                // row of the tile this thread owns
   const int m = m0 + ml;
   EpiRegs e{};
@@ -302,23 +323,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
     tc::mbar_wait(tfull, 0);
     tc::tcgen05_fence_after();
+    stamp(g, 3);
   }
   if (g.split == 1) {
     if (warp >= 2) {
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int j = 0; j < NB / 32; ++j) {
+      for (int j = half; j < NB / 32; j += 2) {
         if (c0 + j * 32 >= g.n_valid) break;
         uint32_t r[32];
         tc::tmem_ld32(tbase + (uint32_t)(j * 32), r);
         tc::tmem_wait_ld();
 #pragma unroll
         for (int i0 = 0; i0 < 32; i0 += EB) {
-          float v[EB];
-#pragma unroll
-          for (int i = 0; i < EB; ++i) v[i] = __uint_as_float(r[i0 + i]);
           const int cf = c0 + j * 32 + i0;
-          if (m < g.m_valid && cf < g.n_valid) epi_batch(g, e, m, cf, min(EB, g.n_valid - cf), v);
+          if (m < g.m_valid && cf < g.n_valid) {
+            const int n_ok = min(EB, g.n_valid - cf);
+            EpiPre pre;
+            epi_prefetch(g, m, cf, n_ok, pre);
+            float v[EB];
+#pragma unroll
+            for (int i = 0; i < EB; ++i) v[i] = __uint_as_float(r[i0 + i]);
+            epi_apply(g, e, m, cf, n_ok, v, pre);
+          }
         }
       }
     }
@@ -328,7 +355,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (warp >= 2) {
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int j = 0; j < NB / 32; ++j) {
+      for (int j = half; j < NB / 32; j += 2) {
         uint32_t r[32];
         tc::tmem_ld32(tbase + (uint32_t)(j * 32), r);
         tc::tmem_wait_ld();
@@ -337,41 +364,54 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       }
     }
     tc::cluster_sync_all();
+    stamp(g, 4);
     if (warp >= 2) {
-      const int cps = NB / g.split;              // columns this CTA reduces and finishes (16, 32 or 64: multiples of EB)
+      const int cps = NB / g.split;              // columns this CTA reduces and finishes (16, 32 or 64: multiples of 2 * EB)
       uint32_t base[MAX_SPLIT];
 #pragma unroll
       for (int r = 0; r < MAX_SPLIT; ++r) base[r] = tc::map_to_rank(part, (uint32_t)(r < g.split ? r : 0));
 #pragma unroll 1
-      for (int i0 = 0; i0 < cps; i0 += EB) {
+      for (int i0 = half * EB; i0 < cps; i0 += 2 * EB) {
         const int cl = (int)rank * cps + i0;
         const int cf = c0 + cl;
         if (cf >= g.n_valid) break;
+        const int n_ok = min(EB, g.n_valid - cf);
+        EpiPre pre;
+        if (m < g.m_valid) epi_prefetch(g, m, cf, n_ok, pre);
         const uint32_t off = (uint32_t)((cl * GM + ml) * 4);
-        float v[EB];
+        // every rank's values of the batch first (one round trip over the cluster), then the sums in rank order
+        float u[MAX_SPLIT][EB];
 #pragma unroll
-        for (int i = 0; i < EB; ++i) v[i] = ld_dsmem(base[0] + off + (uint32_t)(i * GM * 4));
-#pragma unroll
-        for (int r = 1; r < MAX_SPLIT; ++r) {          // rank order, whatever the arrival order was
+        for (int r = 0; r < MAX_SPLIT; ++r) {
           if (r < g.split) {
-            float u[EB];
 #pragma unroll
-            for (int i = 0; i < EB; ++i) u[i] = ld_dsmem(base[r] + off + (uint32_t)(i * GM * 4));
-#pragma unroll
-            for (int i = 0; i < EB; ++i) v[i] += u[i];
+            for (int i = 0; i < EB; ++i) u[r][i] = ld_dsmem(base[r] + off + (uint32_t)(i * GM * 4));
           }
         }
-        if (m < g.m_valid) epi_batch(g, e, m, cf, min(EB, g.n_valid - cf), v);
+        float v[EB];
+#pragma unroll
+        for (int i = 0; i < EB; ++i) v[i] = u[0][i];
+#pragma unroll
+        for (int r = 1; r < MAX_SPLIT; ++r) {
+          if (r < g.split) {
+#pragma unroll
+            for (int i = 0; i < EB; ++i) v[i] += u[r][i];
+          }
+        }
+        if (m < g.m_valid) epi_apply(g, e, m, cf, n_ok, v, pre);
       }
     }
+    stamp(g, 5);
     tc::cluster_sync_all();                      // nobody leaves while a peer still reads its tile
   }
+  stamp(g, 6);
   tc::tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc::tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)NB) : "memory");
   }
+  stamp(g, 7);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------

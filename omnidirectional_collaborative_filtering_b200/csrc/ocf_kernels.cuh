@@ -1058,8 +1058,9 @@ struct SortArgs {
   int* cnt; int* codeor;                    // [n_cols] each, zeroed per step
   int2* colinfo;                            // [n_cols] (first match, matches) of a touched column
   uint32_t* bits; int W;                    // presence bitmap [n_cols][W words], zeroed per step
-  int* counters;                            // [0] matches [1] tasks
+  int* counters;                            // [0] matches [1] tasks [2] heavy tasks
   uint32_t* matches; int4* tasks; int2* colseg;
+  int4* heavy;                              // (column, array, first match, matches) of every task with more than HEAVY_N matches (null: none recorded)
   int n_cols; int nblk; int3 bits3; int dense; int do_dec; int do_enc;
 };
 
@@ -1077,23 +1078,29 @@ __global__ void __launch_bounds__(128) k_sort_count(SortArgs a) {
   }
 }
 
+// A column matched by more than HEAVY_N batch rows is a "heavy" task: one warp walking its matches is a chain of that
+// many dependent L2 round trips and becomes the tail of the whole update kernel (popular items of a user-row batch are
+// matched by half of its 128 rows). Heavy tasks are listed separately and each is walked by a whole CTA.
+constexpr int HEAVY_N = 24;
+
 __global__ void __launch_bounds__(256) k_sort_alloc(SortArgs a) {
   pdl_trigger();
   pdl_wait();
   const int c = blockIdx.x * 256 + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  int n = 0, n_tasks = 0;
+  int n = 0, n_tasks = 0, n_arr = 0;
   int arr[4];
   if (c < a.n_cols) {
     n = a.cnt[c];
-    if (n > 0 && !a.dense) {
-      const int any = a.codeor[c];
-      if (a.do_dec && (any & CODE_TGT)) arr[n_tasks++] = 0;
+    if (n > 0) {
+      const int any = a.dense ? 0xff : a.codeor[c];      // dense updates touch every array of every column
+      if (a.do_dec && (any & CODE_TGT)) arr[n_arr++] = 0;
       if (a.do_enc)
         for (int blk = 0; blk < a.nblk; ++blk) {
           const int bit = blk == 0 ? a.bits3.x : (blk == 1 ? a.bits3.y : a.bits3.z);
-          if (any & bit) arr[n_tasks++] = 1 + blk;
+          if (any & bit) arr[n_arr++] = 1 + blk;
         }
+      if (!a.dense) n_tasks = n_arr;
     }
   }
   if (__ballot_sync(FULL, n > 0) == 0u) return;
@@ -1114,6 +1121,10 @@ __global__ void __launch_bounds__(256) k_sort_alloc(SortArgs a) {
     a.colinfo[c] = make_int2(base, n);
     if (a.dense) a.colseg[c] = make_int2(base, n);
     for (int k = 0; k < n_tasks; ++k) a.tasks[slot + k] = make_int4(c, arr[k], base, n);
+    if (n > HEAVY_N && a.heavy != nullptr && n_arr > 0) {
+      const int h0 = atomicAdd(&a.counters[2], n_arr);
+      for (int k = 0; k < n_arr; ++k) a.heavy[h0 + k] = make_int4(c, arr[k], base, n);
+    }
   }
 }
 
@@ -1148,6 +1159,7 @@ struct RowArgs {
   float* Gdec; float* Genc; float* gbdec;   // KIND_GRAD: gradient rows instead of updates (row-parallel mode)
   int n_cols; int3 bits; const BatchHdr* bt_hdr;
   int dense; int n_arr; int arr_map[4];
+  const int4* heavy;                        // tasks with more than HEAVY_N matches, walked by whole CTAs (null: every task is a warp's)
   int only;                                 // task list shared by two launches (decoder and encoder rows of different widths): 1 = decoder tasks only, 2 = encoder tasks only
   OptDev opt;
 };
@@ -1157,48 +1169,41 @@ constexpr int KIND_GRAD = 4;              // k_row_update: store the gradient ro
 // WIDE: two matched activation rows in flight per step of a task's walk (more registers, fewer resident warps): for
 // catalogues whose weights sit in L2, where the kernel is bound by the longest column's chain of dependent L2 round
 // trips instead of by HBM.
-template <int NV, int KIND, bool WIDE>
+// HEAVY: the CTA-cooperative walk of heavy tasks is compiled in (catalogues whose weights are within reach of L2, where
+// the longest chain is the kernel's tail; the HBM-bound catalogues keep the lean kernel: no shared memory, 80 registers).
+template <int NV, int KIND, bool WIDE, bool HEAVY>
 __global__ void __launch_bounds__(256, WIDE ? (NV <= 4 ? 2 : 1) : (KIND == OCF_OPT_ADAM ? (NV <= 4 ? 2 : 1) : (NV <= 4 ? 3 : 2)))
 k_row_update(RowArgs a) {
   pdl_trigger();
   pdl_wait();
   constexpr int HP = NV * 128;
   constexpr bool LOAD_W = KIND != KIND_GRAD;
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const long long n_tasks = a.dense ? (long long)a.n_cols * a.n_arr : (long long)a.counters[1];
-  for (long long t = gwarp; t < n_tasks; t += nwarps) {
-    int c, arr, base, n;
-    if (a.dense) {
-      c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
-      const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
-    } else {
-      const int4 task = a.tasks[t]; c = task.x; arr = task.y; base = task.z; n = task.w;
-      if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
-    }
-    const size_t r = arr == 0 ? (size_t)c * HP : ((size_t)(arr - 1) * a.n_cols + c) * HP;
-    float* Wrow = (arr == 0 ? a.WdecT : a.Wenc) + r + lane * 4;
-    float* S1row = (arr == 0 ? a.Wd_s1 : a.We_s1);
-    float* S2row = (arr == 0 ? a.Wd_s2 : a.We_s2);
-    // the row and its state first: these are the HBM loads, everything below overlaps them
-    float4 w[NV], t1[NV], t2[NV];
+  __shared__ float4 hpart[HEAVY ? 8 : 1][HEAVY ? HP / 4 : 1];       // heavy tasks: the eight warps' partial gradient rows
+  __shared__ float hcs[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // where a task's row lives
+  auto row_of = [&](int c, int arr) -> size_t { return arr == 0 ? (size_t)c * HP : ((size_t)(arr - 1) * a.n_cols + c) * HP; };
+  // the row and its state: these are the HBM loads, issued before the match walk so that it overlaps them
+  auto load_row = [&](int arr, size_t r, float4 (&w)[NV], float4 (&t1)[NV], float4 (&t2)[NV]) {
+    const float* Wrow = (arr == 0 ? a.WdecT : a.Wenc) + r + lane * 4;
+    const float* S1row = (arr == 0 ? a.Wd_s1 : a.We_s1);
+    const float* S2row = (arr == 0 ? a.Wd_s2 : a.We_s2);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       w[v] = LOAD_W ? *reinterpret_cast<const float4*>(Wrow + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
       t1[v] = (LOAD_W && KIND != OCF_OPT_SGD) ? *reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
       t2[v] = KIND == OCF_OPT_ADAM ? *reinterpret_cast<const float4*>(S2row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  // g += sum over matches [i_begin, i_end) of the task of coef * X[b, :], in match order
+  auto walk = [&](int arr, int base, int i_begin, int i_end, float4 (&g)[NV], float& cs) {
     const float* X = (arr == 0 ? a.hdec : a.dz0) + lane * 4;
     const uint32_t bit = arr == 0 ? CODE_TGT : (arr == 1 ? a.bits.x : (arr == 2 ? a.bits.y : a.bits.z));
-    float4 g[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float cs = 0.f;
-    for (int i0 = 0; i0 < n; i0 += 32) {
+    for (int i0 = i_begin; i0 < i_end; i0 += 32) {
       // lanes fetch up to 32 match records, then the warp walks them in order
       uint32_t bc = 0; float coef = 0.f;
-      if (i0 + lane < n) {
+      if (i0 + lane < i_end) {
         const uint32_t* rec = a.matches + (size_t)(base + i0 + lane) * 3;
         bc = rec[0];
         coef = arr == 0 ? __ldg(a.dy + rec[2]) : (arr == 1 ? __uint_as_float(rec[1]) : __ldg(&a.bt_hdr->aux_value));
@@ -1214,8 +1219,7 @@ k_row_update(RowArgs a) {
         cs += cf;
       }
       while (WIDE && m) {
-        // (a popular column has as many matches as the batch has rows: one dependent L2 round trip per match was the
-        // tail of this kernel on small catalogues); the sums keep their order: match j0 is added before match j1
+        // two matched rows in flight; the sums keep their order: match j0 is added before match j1
         const int j0 = __ffs(m) - 1; m &= m - 1;
         const bool two = m != 0;
         const int j1 = two ? __ffs(m) - 1 : j0; m &= m - 1;
@@ -1232,13 +1236,19 @@ k_row_update(RowArgs a) {
         cs += cf0; cs += cf1;
       }
     }
+  };
+  // gradient row g (and the column's dy sum cs) -> stored (KIND_GRAD) or applied through the optimizer
+  auto finish = [&](int c, int arr, size_t r, float4 (&g)[NV], float cs, float4 (&w)[NV], float4 (&t1)[NV], float4 (&t2)[NV]) {
     if (KIND == KIND_GRAD) {
       float* Grow = (arr == 0 ? a.Gdec : a.Genc) + r + lane * 4;
 #pragma unroll
       for (int v = 0; v < NV; ++v) *reinterpret_cast<float4*>(Grow + v * 128) = g[v];
       if (arr == 0 && lane == 0) a.gbdec[c] = cs;
-      continue;
+      return;
     }
+    float* Wrow = (arr == 0 ? a.WdecT : a.Wenc) + r + lane * 4;
+    float* S1row = (arr == 0 ? a.Wd_s1 : a.We_s1);
+    float* S2row = (arr == 0 ? a.Wd_s2 : a.We_s2);
     const float lr = __ldg(&a.opt.st->lr);      // this step's learning rate (device-resident: a replayed graph carries no scalars)
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -1258,6 +1268,65 @@ k_row_update(RowArgs a) {
       if (KIND != OCF_OPT_SGD) a.bd_s1[c] = b1;
       if (KIND == OCF_OPT_ADAM) a.bd_s2[c] = b2;
     }
+  };
+
+  // ---- heavy tasks first (they are the long poles): one CTA each, its eight warps split the match list -------
+  const int n_heavy = (HEAVY && a.heavy != nullptr) ? a.counters[2] : 0;
+  for (int h = blockIdx.x; HEAVY && h < n_heavy; h += gridDim.x) {
+    const int4 task = a.heavy[h];
+    const int c = task.x, arr = task.y, base = task.z, n = task.w;
+    if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;            // CTA-uniform
+    const size_t r = row_of(c, arr);
+    float4 w[NV], t1[NV], t2[NV], g[NV];
+    if (warp == 0) load_row(arr, r, w, t1, t2);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cs = 0.f;
+    const int per = (n + 7) >> 3;
+    walk(arr, base, min(n, warp * per), min(n, (warp + 1) * per), g, cs);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) hpart[warp][v * 32 + lane] = g[v];
+    if (lane == 0) hcs[warp] = cs;
+    __syncthreads();
+    if (warp == 0) {
+      cs = hcs[0];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) g[v] = hpart[0][v * 32 + lane];
+      for (int k = 1; k < 8; ++k) {                                    // warp order = match order of the eight segments
+        cs += hcs[k];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float4 p = hpart[k][v * 32 + lane];
+          g[v].x += p.x; g[v].y += p.y; g[v].z += p.z; g[v].w += p.w;
+        }
+      }
+      finish(c, arr, r, g, cs, w, t1, t2);
+    }
+    __syncthreads();
+  }
+
+  // ---- every other task: one warp each ------------------------------------------------------------------------
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const long long n_tasks = a.dense ? (long long)a.n_cols * a.n_arr : (long long)a.counters[1];
+  for (long long t = gwarp; t < n_tasks; t += nwarps) {
+    int c, arr, base, n;
+    if (a.dense) {
+      c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
+      const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
+    } else {
+      const int4 task = a.tasks[t]; c = task.x; arr = task.y; base = task.z; n = task.w;
+      if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
+    }
+    if (HEAVY && a.heavy != nullptr && n > HEAVY_N) continue;            // done above by a whole CTA
+    const size_t r = row_of(c, arr);
+    float4 w[NV], t1[NV], t2[NV], g[NV];
+    load_row(arr, r, w, t1, t2);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cs = 0.f;
+    walk(arr, base, 0, n, g, cs);
+    finish(c, arr, r, g, cs, w, t1, t2);
   }
 }
 
