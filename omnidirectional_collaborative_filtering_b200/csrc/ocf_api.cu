@@ -180,6 +180,12 @@ struct ocf_batch {
   uint8_t* d_staging = nullptr;
   cudaEvent_t copied = nullptr;
   bool copy_pending = false;
+  // A fill (staging copy + gather kernel K1) runs on the batch's own stream, so that it overlaps the step the
+  // caller's stream is still executing (K1 and its H2D copy were ~10 % of a small catalogue's step). `gathered`
+  // orders every consumer after the fill, `consumed` orders the next fill after the last consumer.
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t gathered = nullptr, consumed = nullptr;
+  bool gathered_valid = false, consumed_valid = false;
   int32_t* d_ent_col = nullptr;
   float* d_ent_val = nullptr;
   uint8_t* d_codes = nullptr;
@@ -557,9 +563,17 @@ extern "C" int ocf_pair_destroy(ocf_pair* p) {
 // ============================================================================================
 // Upper bound of the work items of any batch within (max_rows, max_entries): pick_chunk() keeps
 // the chunk length >= ceil(entries / TARGET_ITEMS), so items <= TARGET_ITEMS + rows.
-constexpr int64_t TARGET_ITEMS = 148 * 6;
+constexpr int64_t TARGET_ITEMS_DEFAULT = 148 * 6;
+static int64_t target_items() {          // $OCF_TARGET_ITEMS: experiments with the work-item granularity
+  static const int64_t v = [] {
+    const char* e = std::getenv("OCF_TARGET_ITEMS");
+    const long long x = e ? std::atoll(e) : 0;
+    return (int64_t)(x >= 148 && x <= 148 * 64 ? x : TARGET_ITEMS_DEFAULT);
+  }();
+  return v;
+}
 static int max_items_for(int max_rows, int64_t max_entries) {
-  return (int)std::min<int64_t>(max_entries / 32 + max_rows + 1, TARGET_ITEMS + max_rows + 1);
+  return (int)std::min<int64_t>(max_entries / 32 + max_rows + 1, std::max(target_items(), TARGET_ITEMS_DEFAULT) + max_rows + 1);
 }
 
 // Fixed for the life of a batch object (sized by its capacity), so that every device pointer a kernel
@@ -590,11 +604,22 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
   b->uid = ++g_batch_uid;
   b->max_items = max_items_for(max_rows, max_entries);
   b->staging_bytes = staging_layout(max_rows, b->max_items, max_entries, b->off);
-  auto bail = [&](int code) { b->mem.release(); if (b->h_staging) cudaFreeHost(b->h_staging); if (b->copied) cudaEventDestroy(b->copied); delete b; return code; };
+  auto bail = [&](int code) {
+    b->mem.release(); if (b->h_staging) cudaFreeHost(b->h_staging); if (b->copied) cudaEventDestroy(b->copied);
+    if (b->gstream) cudaStreamDestroy(b->gstream); if (b->gathered) cudaEventDestroy(b->gathered); if (b->consumed) cudaEventDestroy(b->consumed);
+    delete b; return code; };
   if (cudaMallocHost(reinterpret_cast<void**>(&b->h_staging), b->staging_bytes) != cudaSuccess)
     return bail(fail(OCF_ERR_NOMEM, "ocf_batch_create: pinned allocation failed"));
   if (cudaEventCreateWithFlags(&b->copied, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(OCF_ERR_CUDA, "ocf_batch_create: event creation failed"));
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&b->gstream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->gathered, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->consumed, cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(OCF_ERR_CUDA, "ocf_batch_create: stream / event creation failed"));
+  }
   int st;
   if ((st = b->mem.get(&b->d_staging, b->staging_bytes)) || (st = b->mem.get(&b->d_ent_col, (size_t)max_entries)) ||
       (st = b->mem.get(&b->d_ent_val, (size_t)max_entries)) || (st = b->mem.get(&b->d_codes, (size_t)max_entries)))
@@ -618,6 +643,9 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
 
 extern "C" int ocf_batch_destroy(ocf_batch* b) {
   if (b) {
+    if (b->gstream) { cudaStreamSynchronize(b->gstream); cudaStreamDestroy(b->gstream); }
+    if (b->gathered) cudaEventDestroy(b->gathered);
+    if (b->consumed) cudaEventDestroy(b->consumed);
     b->mem.release();
     if (b->d_rowslot) cudaFree(b->d_rowslot);
     if (b->h_staging) cudaFreeHost(b->h_staging);
@@ -630,7 +658,7 @@ extern "C" int ocf_batch_destroy(ocf_batch* b) {
 // Work items: chunks of <= CH ratings of one row, CH sized so that the row-centric kernels get
 // a few CTAs per SM whatever the batch looks like.
 static int pick_chunk(int64_t n_entries) {
-  int64_t ch = (n_entries + TARGET_ITEMS - 1) / TARGET_ITEMS;
+  int64_t ch = (n_entries + target_items() - 1) / target_items();
   ch = (int64_t)align_up((size_t)std::max<int64_t>(ch, 1), 32);
   return (int)std::max<int64_t>(ch, 32);
 }
@@ -714,6 +742,32 @@ static int launch_gather(ocf_batch* b, cudaStream_t stream) {
   return OCF_OK;
 }
 
+static bool async_gather() {          // OCF_SYNC_GATHER=1: fills run on the caller's stream, in its order
+  static const bool on = [] { const char* e = std::getenv("OCF_SYNC_GATHER"); return !(e && e[0] == '1'); }();
+  return on;
+}
+// The stream a fill of `b` runs on, ordered after the last consumer of the batch's tiles.
+static cudaStream_t fill_begin(ocf_batch* b, cudaStream_t user) {
+  if (!async_gather() || b->gstream == nullptr) return user;
+  if (b->consumed_valid) cudaStreamWaitEvent(b->gstream, b->consumed, 0);
+  return b->gstream;
+}
+static int fill_end(ocf_batch* b, cudaStream_t user, cudaStream_t used) {
+  b->gathered_valid = false;
+  if (used != user) { OCF_CUDA(cudaEventRecord(b->gathered, used)); b->gathered_valid = true; }
+  return OCF_OK;
+}
+// Consumers of a batch's tiles (steps, predict / score, densify, flag read-back) on stream `st`.
+static int batch_acquire(const ocf_batch* b, cudaStream_t st) {
+  if (b->gathered_valid) OCF_CUDA(cudaStreamWaitEvent(st, b->gathered, 0));
+  return OCF_OK;
+}
+static int batch_release(const ocf_batch* cb, cudaStream_t st) {
+  ocf_batch* b = const_cast<ocf_batch*>(cb);
+  if (async_gather() && b->gstream != nullptr) { OCF_CUDA(cudaEventRecord(b->consumed, st)); b->consumed_valid = true; }
+  return OCF_OK;
+}
+
 static int prepare_rowslot(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows, cudaStream_t stream, const char* who);
 
 extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows,
@@ -721,7 +775,8 @@ extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const 
                                     float aux_var_value, void* stream_) {
   OCF_REQUIRE(b && store && row_ids, "ocf_batch_fill_split: null argument");
   OCF_REQUIRE(keep_flags != nullptr || n_flags == 0, "ocf_batch_fill_split: null keep_flags");
-  cudaStream_t stream = as_stream(stream_);
+  cudaStream_t user = as_stream(stream_);
+  cudaStream_t stream = fill_begin(b, user);
   OCF_TRY(prepare_rowslot(b, store, row_ids, n_rows, stream, "ocf_batch_fill_split"));
   OCF_TRY(batch_stage(b, row_ids, n_rows, store->h_rowptr, nullptr, store->n_rows, keep_flags, n_flags, stream,
                       b->tag, pass_through ? 1 : 0, aux_var_value));
@@ -733,7 +788,8 @@ extern "C" int ocf_batch_fill_split(ocf_batch* b, const ocf_store* store, const 
   if (pass_through) tc = n_flags; else for (int64_t k = 0; k < n_flags; ++k) tc += keep_flags[k] == 0;
   b->target_count = tc;
   b->pass_through = pass_through ? 1 : 0;
-  return launch_gather(b, stream);
+  OCF_TRY(launch_gather(b, stream));
+  return fill_end(b, user, stream);
 }
 
 extern "C" int ocf_batch_fill_split_uniform(ocf_batch* b, const ocf_store* store, const int32_t* row_ids, int32_t n_rows,
@@ -769,20 +825,26 @@ extern "C" int ocf_batch_fill_split_uniform(ocf_batch* b, const ocf_store* store
 extern "C" int ocf_batch_fill_fixed(ocf_batch* b, const ocf_pair* pair, const int32_t* row_ids, int32_t n_rows,
                                     float aux_var_value, void* stream_) {
   OCF_REQUIRE(b && pair && row_ids, "ocf_batch_fill_fixed: null argument");
-  cudaStream_t stream = as_stream(stream_);
+  cudaStream_t user = as_stream(stream_);
+  cudaStream_t stream = fill_begin(b, user);
   OCF_TRY(batch_stage(b, row_ids, n_rows, pair->in->h_rowptr, &pair->tg->h_rowptr, pair->in->n_rows, nullptr, -1, stream,
                       0u, 0, aux_var_value));
   b->dev.rowslot = nullptr; b->dev.tag = 0;
   b->mode = 2; b->store = pair->tg; b->aux_value = aux_var_value;
   b->pair = pair;
-  return launch_gather(b, stream);
+  OCF_TRY(launch_gather(b, stream));
+  return fill_end(b, user, stream);
 }
 
 extern "C" int ocf_batch_regather(ocf_batch* b, void* stream_) {
   OCF_REQUIRE(b, "ocf_batch_regather: null argument");
   if (b->mode == 0) return fail(OCF_ERR_STATE, "ocf_batch_regather: the batch has not been filled");
   b->rng_mode = false;            // the first gather left the flags in the device staging
-  return launch_gather(b, as_stream(stream_));
+  cudaStream_t user = as_stream(stream_);
+  cudaStream_t stream = fill_begin(b, user);
+  if (stream != user && b->gathered_valid) OCF_CUDA(cudaStreamWaitEvent(stream, b->gathered, 0));   // same stream: already in order
+  OCF_TRY(launch_gather(b, stream));
+  return fill_end(b, user, stream);
 }
 
 // ---- NumPy MT19937 on the device ------------------------------------------------------------------
@@ -1025,7 +1087,8 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
   OCF_REQUIRE(b && store && row_ids && rng, "ocf_batch_fill_split_rng: null argument");
   OCF_REQUIRE(n_rows > 0 && n_rows <= b->max_rows, "ocf_batch_fill_split_rng: row count exceeds the batch capacity");
   OCF_REQUIRE((full_len != nullptr) == (store->dev.orig_pos != nullptr), "ocf_batch_fill_split_rng: full_len goes with a store that has ocf_store_set_orig_pos");
-  cudaStream_t stream = as_stream(stream_);
+  cudaStream_t user = as_stream(stream_);
+  cudaStream_t stream = fill_begin(b, user);
   int64_t draws = n_rows;
   for (int r = 0; r < n_rows; ++r) {
     const int32_t row = row_ids[r];
@@ -1072,7 +1135,7 @@ extern "C" int ocf_batch_fill_split_rng(ocf_batch* b, const ocf_store* store, co
   rng->pos_u = u1;
   // keep the workers one round of blocks ahead of the consumers
   OCF_TRY(rng_enqueue_blocks(rng, kb1 + rng->M));
-  return OCF_OK;
+  return fill_end(b, user, stream);
 }
 
 extern "C" int ocf_batch_read_flags(ocf_batch* b, uint8_t* out, int64_t count, void* stream_) {
@@ -1080,6 +1143,7 @@ extern "C" int ocf_batch_read_flags(ocf_batch* b, uint8_t* out, int64_t count, v
   if (b->mode != 1) return fail(OCF_ERR_STATE, "ocf_batch_read_flags: not a split batch");
   OCF_REQUIRE(count == b->dev.n_entries, "ocf_batch_read_flags: count must equal the batch's entries");
   cudaStream_t stream = as_stream(stream_);
+  OCF_TRY(batch_acquire(b, stream));
   if (count) OCF_CUDA(cudaMemcpyAsync(out, b->dev.flags, (size_t)count, cudaMemcpyDeviceToHost, stream));
   OCF_CUDA(cudaStreamSynchronize(stream));
   return OCF_OK;
@@ -1101,7 +1165,8 @@ extern "C" int ocf_batch_densify(const ocf_batch* b, int which, double* out, voi
   const size_t count = (size_t)b->dev.B * (size_t)n_cols;
   double* d_out = nullptr;
   OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_out), count * sizeof(double)));
-  cudaError_t e = cudaMemsetAsync(d_out, 0, count * sizeof(double), stream);
+  cudaError_t e = b->gathered_valid ? cudaStreamWaitEvent(stream, b->gathered, 0) : cudaSuccess;
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, count * sizeof(double), stream);
   if (e == cudaSuccess && b->dev.n_entries > 0) {
     k_densify<<<(b->dev.n_entries + 255) / 256, 256, 0, stream>>>(b->dev, which, (double)b->aux_value, (int)n_cols, d_out);
     g_launches.fetch_add(1);
@@ -2176,7 +2241,14 @@ static int run_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, bool 
   return publish_metrics(m, train, st);
 }
 
+static int ocf_train_step_impl(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_);
 extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
+  if (b) OCF_TRY(batch_acquire(b, as_stream(stream_)));          // the batch's fill runs on its own stream
+  const int rc = ocf_train_step_impl(m, b, args, host_metrics, stream_);
+  if (b && rc == OCF_OK) OCF_TRY(batch_release(b, as_stream(stream_)));
+  return rc;
+}
+static int ocf_train_step_impl(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
   OCF_TRY(check_step(m, b, true));
   cudaStream_t st = as_stream(stream_);
   const int phase = args ? args->phase : 0;
@@ -2218,7 +2290,14 @@ extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* a
   return OCF_OK;
 }
 
+static int ocf_eval_step_impl(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_);
 extern "C" int ocf_eval_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
+  if (b) OCF_TRY(batch_acquire(b, as_stream(stream_)));          // the batch's fill runs on its own stream
+  const int rc = ocf_eval_step_impl(m, b, args, host_metrics, stream_);
+  if (b && rc == OCF_OK) OCF_TRY(batch_release(b, as_stream(stream_)));
+  return rc;
+}
+static int ocf_eval_step_impl(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
   OCF_TRY(check_step(m, b, false));
   cudaStream_t st = as_stream(stream_);
   const int phase = args ? args->phase : 0;
@@ -2265,7 +2344,14 @@ static int ensure_dense(ocf_model* m) {
   return m->dense_mem.get(&m->dense_out, (size_t)m->cfg.max_rows * m->cfg.n_cols);
 }
 
+static int ocf_predict_impl(ocf_model* m, ocf_batch* b, float* out, void* stream_);
 extern "C" int ocf_predict(ocf_model* m, ocf_batch* b, float* out, void* stream_) {
+  if (b) OCF_TRY(batch_acquire(b, as_stream(stream_)));          // the batch's fill runs on its own stream
+  const int rc = ocf_predict_impl(m, b, out, stream_);
+  if (b && rc == OCF_OK) OCF_TRY(batch_release(b, as_stream(stream_)));
+  return rc;
+}
+static int ocf_predict_impl(ocf_model* m, ocf_batch* b, float* out, void* stream_) {
   OCF_TRY(check_step(m, b, false));
   OCF_REQUIRE(out != nullptr, "ocf_predict: null output");
   cudaStream_t st = as_stream(stream_);
@@ -2280,7 +2366,14 @@ extern "C" int ocf_predict(ocf_model* m, ocf_batch* b, float* out, void* stream_
   return OCF_OK;
 }
 
+static int ocf_score_impl(ocf_model* m, ocf_batch* b, float* out, int out_is_device, void* stream_);
 extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_device, void* stream_) {
+  if (b) OCF_TRY(batch_acquire(b, as_stream(stream_)));          // the batch's fill runs on its own stream
+  const int rc = ocf_score_impl(m, b, out, out_is_device, stream_);
+  if (b && rc == OCF_OK) OCF_TRY(batch_release(b, as_stream(stream_)));
+  return rc;
+}
+static int ocf_score_impl(ocf_model* m, ocf_batch* b, float* out, int out_is_device, void* stream_) {
   OCF_TRY(check_step(m, b, false));
   OCF_REQUIRE(out != nullptr, "ocf_score: null output");
   cudaStream_t st = as_stream(stream_);
@@ -2332,7 +2425,16 @@ extern "C" int ocf_score(ocf_model* m, ocf_batch* b, float* out, int out_is_devi
   return OCF_OK;
 }
 
+static int ocf_score_topk_impl(ocf_model* m, ocf_batch* b, int32_t k, int exclude_inputs, int32_t* out_cols, float* out_scores,
+                              void* stream_);
 extern "C" int ocf_score_topk(ocf_model* m, ocf_batch* b, int32_t k, int exclude_inputs, int32_t* out_cols, float* out_scores,
+                              void* stream_) {
+  if (b) OCF_TRY(batch_acquire(b, as_stream(stream_)));
+  const int rc = ocf_score_topk_impl(m, b, k, exclude_inputs, out_cols, out_scores, stream_);
+  if (b && rc == OCF_OK) OCF_TRY(batch_release(b, as_stream(stream_)));
+  return rc;
+}
+static int ocf_score_topk_impl(ocf_model* m, ocf_batch* b, int32_t k, int exclude_inputs, int32_t* out_cols, float* out_scores,
                               void* stream_) {
   OCF_TRY(check_step(m, b, false));
   OCF_REQUIRE(out_cols && out_scores, "ocf_score_topk: null output");
