@@ -30,6 +30,7 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 std::atomic<long long> g_launches{0};
+static std::atomic<int> g_comms_alive{0};      // NCCL communicators of this process (ocf_comm_create / _destroy)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -615,7 +616,8 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&b->gstream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+    static const bool normal_prio = [] { const char* e = std::getenv("OCF_GATHER_PRIO"); return e && e[0] == '0'; }();
+    if (cudaStreamCreateWithPriority(&b->gstream, cudaStreamNonBlocking, normal_prio ? lo : hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->gathered, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->consumed, cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(OCF_ERR_CUDA, "ocf_batch_create: stream / event creation failed"));
@@ -841,7 +843,13 @@ extern "C" int ocf_batch_regather(ocf_batch* b, void* stream_) {
   if (b->mode == 0) return fail(OCF_ERR_STATE, "ocf_batch_regather: the batch has not been filled");
   b->rng_mode = false;            // the first gather left the flags in the device staging
   cudaStream_t user = as_stream(stream_);
-  cudaStream_t stream = fill_begin(b, user);
+  // A re-gather has no host copy to hide. On its own stream it still overlaps the previous step (Jester: 71 -> 66 us per
+  // step), but beside a step that holds NCCL collectives it costs more than it hides (2 GPUs: 785 vs 855 M ratings/s,
+  // gpurun_out/r03a-b), so a process with a communicator keeps it on the caller's stream. OCF_REGATHER_SYNC=0|1 forces.
+  static const int forced = [] { const char* e = std::getenv("OCF_REGATHER_SYNC"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+  const bool regather_sync = forced >= 0 ? forced == 1 : g_comms_alive.load() > 0;
+  cudaStream_t stream = regather_sync ? user : fill_begin(b, user);
+  if (regather_sync) OCF_TRY(batch_acquire(b, user));
   if (stream != user && b->gathered_valid) OCF_CUDA(cudaStreamWaitEvent(stream, b->gathered, 0));   // same stream: already in order
   OCF_TRY(launch_gather(b, stream));
   return fill_end(b, user, stream);
@@ -2031,6 +2039,7 @@ extern "C" int ocf_comm_create(const uint8_t* id, int32_t rank, int32_t world, o
   std::memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
   ncclResult_t r = nccl_api().commInitRank(&c->comm, world, u, rank);
   if (r != ncclSuccess) { delete c; return fail(OCF_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_api().getErrorString(r)); }
+  g_comms_alive.fetch_add(1);
   int st = comm_enable_p2p(c);
   if (st != OCF_OK) { ocf_comm_destroy(c); return st; }
   *out = c;
@@ -2042,7 +2051,7 @@ extern "C" int ocf_comm_destroy(ocf_comm* c) {
     cudaDeviceSynchronize();
     for (int p = 0; p < c->world && p < peer::MAX_PEERS; ++p)
       if (p != c->rank && c->peer_region[p]) cudaIpcCloseMemHandle(c->peer_region[p]);
-    if (c->comm) nccl_api().commDestroy(c->comm);      // after the peers' mappings are closed everywhere
+    if (c->comm) { nccl_api().commDestroy(c->comm); g_comms_alive.fetch_sub(1); }      // after the peers' mappings are closed everywhere
     if (c->region) cudaFree(c->region);
     delete c;
   }

@@ -414,16 +414,29 @@ def _bench_config(args, w, rank, world, native, B, scaling, parity=False, steps=
     dist.all_reduce(tg)
     targets = float(tg.item())
 
-    # e2e through the public API on every rank: host RNG replay + H2D + phases/collectives + D2H
-    for _ in range(max(W, 9)):               # three rounds of the ring of 3 batch buffers: plain, capture, replay
-        m.train_on_batch(next(batches), sync=True)
+    # e2e through the public API on every rank: generator thread (row ids, the batch's place in the NumPy stream),
+    # H2D of the row ids, device-side draw of the random split, phases / collectives, D2H of the step's metrics
+    from .data_reader import Prefetcher
+    per_epoch = max(rd.train_set_size // B, 1)
+
+    def epochs(total):
+        """`total` batches epoch by epoch like train.py:150-158 (a fresh generator per epoch), drawn on a generator
+        thread like Keras' GeneratorEnqueuer; every rank draws the same batches in the same order."""
+        done = 0
+        while done < total:
+            n = min(total - done, per_epoch)
+            for bt in Prefetcher(gen(), n):
+                yield bt.row_slice(rank, world) if rows_mode else bt
+            done += n
+
+    for b in epochs(max(W, 9)):              # three rounds of the ring of 3 batch buffers: plain, capture, replay
+        m.train_on_batch(b, sync=True)
     dist.barrier()
     torch.cuda.synchronize()
     h2d = e_ratings = 0
     prev = None
     t0 = time.perf_counter()
-    for _ in range(K):
-        b = next(batches)
+    for b in epochs(K):
         m.train_on_batch(b, sync=False)
         sid = m.steps_logged() - 1
         if prev is not None:
