@@ -561,20 +561,22 @@ def main():
     torch.cuda.synchronize()
     h2d = 0
     e_ratings = 0
-    prev = None
+    from collections import deque
+    in_flight = deque()
+    lag = max(1, int(os.environ.get("OCF_BENCH_LAG", "2")))      # steps enqueued ahead of the metrics read-back (the reader holds 3 batch buffers)
     t0 = time.perf_counter()
     # generator thread: set order, row ids, the batch's place in the NumPy stream; main thread:
     # pinned staging + H2D of the row ids + kernels (the random split is drawn on the device from
-    # the replayed MT19937 stream) + the D2H read of every step's metrics
+    # the replayed MT19937 stream) + the D2H read of EVERY step's metrics, `lag` steps behind the enqueue
     for b in epochs(K):
         m.train_on_batch(b, sync=False)
-        step_id = m.steps_logged() - 1
-        if prev is not None:
-            m.wait_metrics(prev)                  # read step i-1's result while step i runs
-        prev = step_id
+        in_flight.append(m.steps_logged() - 1)
+        if len(in_flight) > lag:
+            m.wait_metrics(in_flight.popleft())   # read step i-lag's result while the later steps run
         e_ratings += b.n_entries
         h2d += b._device.info()["h2d_bytes"]
-    m.wait_metrics(prev)
+    while in_flight:
+        m.wait_metrics(in_flight.popleft())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()

@@ -434,17 +434,19 @@ def _bench_config(args, w, rank, world, native, B, scaling, parity=False, steps=
     dist.barrier()
     torch.cuda.synchronize()
     h2d = e_ratings = 0
-    prev = None
+    from collections import deque
+    in_flight = deque()
+    lag = max(1, int(os.environ.get("OCF_BENCH_LAG", "2")))      # like bench.py's 1-GPU loop: every step's metrics are read, `lag` steps behind
     t0 = time.perf_counter()
     for b in epochs(K):
         m.train_on_batch(b, sync=False)
-        sid = m.steps_logged() - 1
-        if prev is not None:
-            m.wait_metrics(prev)
-        prev = sid
+        in_flight.append(m.steps_logged() - 1)
+        if len(in_flight) > lag:
+            m.wait_metrics(in_flight.popleft())
         e_ratings += b.n_ratings
         h2d += b._device.info()["h2d_bytes"]
-    m.wait_metrics(prev)
+    while in_flight:
+        m.wait_metrics(in_flight.popleft())
     torch.cuda.synchronize()
     dist.barrier()
     e2e = torch.tensor([time.perf_counter() - t0], device="cuda")

@@ -86,7 +86,7 @@ class OmniNet(object):
             self._push_weights(o._host_weights)
             o._host_weights = None
             self._push_optimizer()
-            for l, t in enumerate(o.trainable):
+            for l, t in enumerate(o._compiled_trainable):
                 _lib.check(_lib.lib().ocf_model_set_trainable(self._handle, l, int(t)))
             if self.native is not None:
                 comm, mode = self.native
@@ -118,6 +118,8 @@ class OmniNet(object):
         if rating_range is not None:
             self.rating_range = float(rating_range)
         self._compiled = True
+        for l in range(len(self.owner.trainable)):        # compile collects the trainable weights (both modes)
+            self.owner._apply_trainable(l)
         if self._handle is not None:
             self._push_optimizer()
 
@@ -400,7 +402,13 @@ class omni_model(object):
         self.set_aux_kind(auxilliary_mask_type)
         self.local_cols = self.input_shape if local_cols is None else int(local_cols)
         self.sharded = self.local_cols != self.input_shape
-        self.trainable = [True] * (self.numlayers + 1)
+        self.trainable = [True] * (self.numlayers + 1)         # layer.trainable, as the caller set it
+        # What the optimizer honours. "at_once" (default): a flag set after compile() takes effect immediately - what
+        # the reference's transfer flows intend (model.py:109-170 called after m.compile, train.py:131-145).
+        # "on_compile": the Keras 2.0.4 the reference pins collects the trainable weights at compile time, so a flag
+        # set afterwards is ignored until the next compile() (the reference's own comment, model.py:137).
+        self.trainable_applies = "at_once"
+        self._compiled_trainable = list(self.trainable)
         # Keras draws one seed per kernel initializer and per Dropout layer from the global NumPy
         # RNG while the graph is built; keep that stream position.
         self.col_lo = int(col_lo)
@@ -485,8 +493,13 @@ class omni_model(object):
 
     def _set_trainable(self, l, flag):
         self.trainable[l] = bool(flag)
-        if self.model._handle is not None:
-            _lib.check(_lib.lib().ocf_model_set_trainable(self.model._handle, l, int(bool(flag))))
+        if self.trainable_applies != "on_compile":
+            self._apply_trainable(l)
+
+    def _apply_trainable(self, l):
+        self._compiled_trainable[l] = self.trainable[l]
+        if getattr(self.model, "_handle", None) is not None:
+            _lib.check(_lib.lib().ocf_model_set_trainable(self.model._handle, l, int(self.trainable[l])))
 
     def replace_dense_layer_weights(self, donor_model, layers_to_replace, make_layers_trainable=False):
         donor = _donor_pairs(donor_model)

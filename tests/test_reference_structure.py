@@ -119,3 +119,22 @@ def test_graph_structure_matches_the_reference(case):
     if lam is not None:
         expect = lam * sum(float(np.sum(np.square(w.astype(np.float64)))) for w in ref.get_weights()[0::2])
         assert float(ref._reg()) == pytest.approx(expect, rel=1e-5)
+
+
+def test_trainable_flags_after_compile_both_keras_behaviours():
+    """model.py:109-170 set layer.trainable AFTER m.compile (train.py:131-145). Default: the flags count at once (the
+    flows' intent). trainable_applies = "on_compile": Keras 2.0.4 collected the trainable weights at compile time, so the
+    flags wait for the next compile (model.py:137's own remark)."""
+    from omnidirectional_collaborative_filtering_b200.model import omni_model
+    np.random.seed(3)
+    donor = omni_model(1, 8, 12, 4, use_causal_info=False)
+    for mode, after_helper, after_compile in (("at_once", [False, True, False], [False, True, False]),
+                                              ("on_compile", [True, True, True], [False, True, False])):
+        om = omni_model(2, 8, 12, 4, use_causal_info=False)
+        om.trainable_applies = mode
+        om.model.compile("adagrad", "mean_squared_error")
+        om.load_and_fix_for_denoising_autoencoders(donor)
+        assert om.trainable == [False, True, False]                   # layer.trainable as the helper left it
+        assert om._compiled_trainable == after_helper
+        om.model.compile("adagrad", "mean_squared_error")
+        assert om._compiled_trainable == after_compile
