@@ -18,6 +18,7 @@
 #include "ocf_gemm_tc.cuh"
 #include "ocf_peer.cuh"
 #include "ocf_topk.cuh"
+#include "ocf_staged.cuh"
 
 namespace ocf {
 
@@ -170,6 +171,29 @@ struct ocf_pair {
   Arena mem;
 };
 
+// K4a's product for one batch: what K4b walks. The model owns one (filled inside the step, on a side stream);
+// a batch object owns another when its column grouping runs AHEAD of the step on the batch's own stream.
+struct WorkList {
+  uint32_t* matches = nullptr;    // [3 * entries] (batch row | code << 16, value, entry)
+  int32_t* mcol = nullptr;        // [entries] CSC scan only
+  int2* seg = nullptr;            // [n_cols] dense mode: (first match, matches) of every column
+  int4* tasks = nullptr;          // [(nblk + 1) * n_cols]
+  int4* heavy = nullptr;          //   tasks with more than HEAVY_N matches
+  int* counters = nullptr;        // [8]: matches, tasks, heavy tasks, K4b's task cursors (two launches may share a list)
+  int* state = nullptr;           // [2][n_cols] per-column count / code OR
+  int2* info = nullptr;           // [n_cols] (first match, matches) of a touched column
+  uint32_t* bits = nullptr;       // presence bitmap [n_cols][ceil(rows / 32)]
+};
+
+// What a work list depends on besides the batch's own tiles.
+struct WorkSig {
+  int n_cols = 0, nblk = 0, b0 = 0, b1 = 0, b2 = 0, do_dec = 0, do_enc = 0, dense = 0, heavy = 0, B = 0;
+  bool operator==(const WorkSig& o) const {
+    return n_cols == o.n_cols && nblk == o.nblk && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && do_dec == o.do_dec &&
+           do_enc == o.do_enc && dense == o.dense && heavy == o.heavy && B == o.B;
+  }
+};
+
 struct ocf_batch {
   uint64_t uid = 0;               // never reused: captured steps are keyed by it
   int max_rows = 0;
@@ -209,6 +233,20 @@ struct ocf_batch {
   int64_t draw_base = 0;           // index of the batch's first per-rating draw in its slice of the stream
   int cdf0_row0 = 0;               // row-parallel slice: index of the batch's first row among the sparsity draws
   bool rng_mode = false;
+  // The batch's own update work list (K4a): grouped by catalogue column right behind the gather, on the batch's
+  // stream, so that it runs under an EARLIER step instead of beside this step's K2 / K3 (which it slowed from 31
+  // to 48 us on the ML-10M shape). One zeroed region [counters | state | bits | seg], one memset.
+  WorkList wl{};
+  Arena wl_mem;
+  uint8_t* wl_zero = nullptr; size_t wl_zero_bytes = 0, wl_zero_dense_bytes = 0;
+  int wl_cols = 0, wl_nblk = 0;   // what the allocation was sized for
+  WorkSig wl_sig{};               // what the list in `wl` was built for ...
+  uint64_t fill_seq = 0, wl_seq = 0;   // ... and for which fill (0: none)
+  cudaEvent_t wl_ready = nullptr;
+  cudaGraphExec_t wl_graph = nullptr;  // memset + the three K4a kernels of `wl_graph_sig`, one launch
+  WorkSig wl_graph_sig{};
+  int wl_graph_kernels = 0;
+  bool wl_graph_failed = false;
   Arena mem;
 };
 
@@ -296,6 +334,16 @@ constexpr int N_REGPART = 64;
 static bool pdl_on() {
   static const bool on = [] { const char* e = std::getenv("OCF_NO_PDL"); return !(e && e[0] == '1'); }();
   return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_smem(bool pdl, size_t smem, void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (pdl && pdl_on()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
@@ -608,6 +656,7 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
   auto bail = [&](int code) {
     b->mem.release(); if (b->h_staging) cudaFreeHost(b->h_staging); if (b->copied) cudaEventDestroy(b->copied);
     if (b->gstream) cudaStreamDestroy(b->gstream); if (b->gathered) cudaEventDestroy(b->gathered); if (b->consumed) cudaEventDestroy(b->consumed);
+    if (b->wl_ready) cudaEventDestroy(b->wl_ready);
     delete b; return code; };
   if (cudaMallocHost(reinterpret_cast<void**>(&b->h_staging), b->staging_bytes) != cudaSuccess)
     return bail(fail(OCF_ERR_NOMEM, "ocf_batch_create: pinned allocation failed"));
@@ -619,6 +668,7 @@ extern "C" int ocf_batch_create(int32_t max_rows, int64_t max_entries, ocf_batch
     static const bool normal_prio = [] { const char* e = std::getenv("OCF_GATHER_PRIO"); return e && e[0] == '0'; }();
     if (cudaStreamCreateWithPriority(&b->gstream, cudaStreamNonBlocking, normal_prio ? lo : hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->gathered, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->wl_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->consumed, cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(OCF_ERR_CUDA, "ocf_batch_create: stream / event creation failed"));
   }
@@ -648,6 +698,9 @@ extern "C" int ocf_batch_destroy(ocf_batch* b) {
     if (b->gstream) { cudaStreamSynchronize(b->gstream); cudaStreamDestroy(b->gstream); }
     if (b->gathered) cudaEventDestroy(b->gathered);
     if (b->consumed) cudaEventDestroy(b->consumed);
+    if (b->wl_ready) cudaEventDestroy(b->wl_ready);
+    if (b->wl_graph) cudaGraphExecDestroy(b->wl_graph);
+    b->wl_mem.release();
     b->mem.release();
     if (b->d_rowslot) cudaFree(b->d_rowslot);
     if (b->h_staging) cudaFreeHost(b->h_staging);
@@ -755,6 +808,7 @@ static cudaStream_t fill_begin(ocf_batch* b, cudaStream_t user) {
   return b->gstream;
 }
 static int fill_end(ocf_batch* b, cudaStream_t user, cudaStream_t used) {
+  b->fill_seq += 1;               // a work list built for an earlier fill is stale
   b->gathered_valid = false;
   if (used != user) { OCF_CUDA(cudaEventRecord(b->gathered, used)); b->gathered_valid = true; }
   return OCF_OK;
@@ -1286,7 +1340,7 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   if (st) return bail(st);
   if ((st = m->mem.get(&m->regparts, (size_t)N_REGPART * (L + 1), true)) || (st = m->mem.get(&m->d_step, 1, true)) ||
       (st = m->mem.get(&m->d_err, 1, true)) || (st = m->mem.get(&m->col_tasks, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_heavy, (size_t)N * (m->nblk + 1))) || (st = m->mem.get(&m->col_seg, (size_t)N, true)) ||
-      (st = m->mem.get(&m->col_counters, 4, true)) || (st = m->mem.get(&m->col_state, (size_t)2 * N, true)) ||
+      (st = m->mem.get(&m->col_counters, 8, true)) || (st = m->mem.get(&m->col_state, (size_t)2 * N, true)) ||
       (st = m->mem.get(&m->col_info, (size_t)N)))
     return bail(st);
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev); if (m->sm_count <= 0) m->sm_count = 148; }
@@ -1682,6 +1736,14 @@ static int hidden_dw_tc(ocf_model* m, int l, int B, const float* hin, const OptD
 // xslot: write the row statistics [B, 4] and dL/dh [B, hp] into this exchange slot instead of the
 // model's buffers (a peer all-reduce follows).
 // after_kernel: the previous operation in the stream is a kernel (the phase's first launch may be a dependent launch)
+// K3 through shared memory (ocf_staged.cuh) when the batch object's work items are short: decided by the object's
+// capacity, so that a captured step keeps its kernel whatever a later fill holds. OCF_DEC_STAGED=0|1 forces.
+static bool dec_staged(const ocf_batch* b) {
+  static const int forced = [] { const char* e = std::getenv("OCF_DEC_STAGED"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+  if (forced >= 0) return forced == 1;
+  return pick_chunk(b->max_entries) <= 256;
+}
+
 static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args,
                         float* dense_out, cudaStream_t st, bool act0_done = false, float* xslot = nullptr, bool after_kernel = false) {
   const BatchDev& bt = b->dev;
@@ -1705,7 +1767,18 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   float* stats_out = xslot ? xslot : m->rowstats;
   float4* dh_out = reinterpret_cast<float4*>(xslot ? xslot + (size_t)B * ROWSTAT_W : m->dh_top);
   g_prof.begin(2, st);
-  if (training) {
+  if (dec_staged(b)) {
+    // short work items: the rows come through shared memory (copy engine), ocf_staged.cuh
+    if (training) {
+      OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, st::k_dec_fwd_st<NV, true>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
+                                             (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2),
+                                             m->itemstats, dense_out, m->cfg.n_cols, m->tail, dh_out, stats_out)));
+    } else {
+      OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, st::k_dec_fwd_st<NV, false>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
+                                             (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, (float*)nullptr, (float4*)nullptr,
+                                             m->itemstats, dense_out, m->cfg.n_cols, m->tail, (float4*)nullptr, stats_out)));
+    }
+  } else if (training) {
     OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, k_dec_fwd<NV, true>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
                                            (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2),
                                            m->itemstats, dense_out, m->cfg.n_cols, m->tail, dh_out, stats_out)));
@@ -1770,7 +1843,39 @@ static int launch_row_update_nv(int kind, int grid, const RowArgs& r, cudaStream
   return OCF_OK;
 }
 
-static int launch_row_update(int hp, int kind, int grid, bool wide, bool heavy, const RowArgs& r, cudaStream_t st, bool dep) {
+// K4b with the rows staged through shared memory by the copy engine (ocf_staged.cuh): the lean variant's job,
+// i.e. catalogues far beyond L2. OCF_UPD_STAGED=0 keeps the register version.
+static bool upd_staged() {
+  static const bool on = [] { const char* e = std::getenv("OCF_UPD_STAGED"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <int NV, int KIND>
+static int launch_row_update_st(int sm_count, const RowArgs& r, cudaStream_t st, bool dep) {
+  using C = st::UpdCfg<NV, KIND>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCF_CUDA(cudaFuncSetAttribute(st::k_row_update_st<NV, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  OCF_CUDA(launch_pdl_smem(dep, (size_t)C::SMEM, st::k_row_update_st<NV, KIND>, dim3(sm_count * C::CTAS_PER_SM), dim3(C::WARPS * 32), st, r));
+  OCF_LAUNCHED();
+  return OCF_OK;
+}
+template <int NV>
+static int launch_row_update_st_nv(int kind, int sm_count, const RowArgs& r, cudaStream_t st, bool dep) {
+  switch (kind) {
+    case OCF_OPT_SGD: return launch_row_update_st<NV, OCF_OPT_SGD>(sm_count, r, st, dep);
+    case OCF_OPT_ADAGRAD: return launch_row_update_st<NV, OCF_OPT_ADAGRAD>(sm_count, r, st, dep);
+    case OCF_OPT_RMSPROP: return launch_row_update_st<NV, OCF_OPT_RMSPROP>(sm_count, r, st, dep);
+    default: return launch_row_update_st<NV, OCF_OPT_ADAM>(sm_count, r, st, dep);
+  }
+}
+
+static int launch_row_update(int hp, int kind, int sm_count, bool wide, bool heavy, const RowArgs& r, cudaStream_t st, bool dep) {
+  if (!wide && !heavy && kind != KIND_GRAD && upd_staged()) {
+    OCF_NV_SWITCH(hp, return (launch_row_update_st_nv<NV>(kind, sm_count, r, st, dep)));
+  }
+  const int grid = sm_count * (wide ? 4 : 6);
   if (wide) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, true, true>(kind, grid, r, st, dep))); }
   else if (heavy) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false, true>(kind, grid, r, st, dep))); }
   else { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false, false>(kind, grid, r, st, dep))); }
@@ -1787,23 +1892,51 @@ static bool heavy_model(const ocf_model* m) {
   return heavy_rows() && (size_t)m->cfg.n_cols * (size_t)std::max(m->hp[0], m->hp[m->L - 1]) <= ((size_t)32 << 20);
 }
 
+// The model's own work list (filled inside the step).
+static WorkList model_wl(const ocf_model* m) {
+  WorkList w;
+  w.matches = m->col_matches; w.mcol = m->col_mcol; w.seg = m->col_seg; w.tasks = m->col_tasks; w.heavy = m->col_heavy;
+  w.counters = m->col_counters; w.state = m->col_state; w.info = m->col_info; w.bits = m->col_bits;
+  return w;
+}
+
+static WorkSig work_sig(const ocf_model* m, const ocf_batch* b) {
+  WorkSig s;
+  s.n_cols = m->cfg.n_cols; s.nblk = m->nblk; s.b0 = m->bits.x; s.b1 = m->bits.y; s.b2 = m->bits.z;
+  s.do_dec = m->layers[m->L].trainable ? 1 : 0; s.do_enc = m->layers[0].trainable ? 1 : 0;
+  s.dense = make_opt(m).dense; s.heavy = heavy_model(m) ? 1 : 0; s.B = b->dev.B;
+  return s;
+}
+// The batch carries the work list of its current fill, built for this model's settings.
+static bool wl_current(const ocf_model* m, const ocf_batch* b) {
+  return m->par_mode == 0 && b->wl_seq != 0 && b->wl_seq == b->fill_seq && b->wl_sig == work_sig(m, b);
+}
+// The list this step's update walks.
+static WorkList step_wl(const ocf_model* m, const ocf_batch* b) { return wl_current(m, b) ? b->wl : model_wl(m); }
+
 // K4a: the batch's ratings grouped by catalogue column -> match list + update tasks.
-static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int dense, cudaStream_t st) {
+// zeroed: the caller has already cleared the list's counters / per-column state (one memset over the batch's own list).
+static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int dense, cudaStream_t st, const WorkList& wl,
+                       bool zeroed = false) {
   if (!do_dec && !do_enc) return OCF_OK;
   const BatchDev& bt = b->dev;
-  OCF_CUDA(cudaMemsetAsync(m->col_counters, 0, 4 * sizeof(int), st));
-  if (dense) OCF_CUDA(cudaMemsetAsync(m->col_seg, 0, sizeof(int2) * (size_t)m->cfg.n_cols, st));
+  if (!zeroed) {
+    OCF_CUDA(cudaMemsetAsync(wl.counters, 0, 8 * sizeof(int), st));
+    if (dense) OCF_CUDA(cudaMemsetAsync(wl.seg, 0, sizeof(int2) * (size_t)m->cfg.n_cols, st));
+  }
   if (!b->store->has_dups) {
     // batch-side counting sort (every (column, batch row) pair is unique)
     const int W = (bt.B + 31) / 32;
     const size_t N = (size_t)m->cfg.n_cols;
-    OCF_CUDA(cudaMemsetAsync(m->col_state, 0, sizeof(int) * 2 * N, st));
-    OCF_CUDA(cudaMemsetAsync(m->col_bits, 0, sizeof(uint32_t) * N * W, st));
+    if (!zeroed) {
+      OCF_CUDA(cudaMemsetAsync(wl.state, 0, sizeof(int) * 2 * N, st));
+      OCF_CUDA(cudaMemsetAsync(wl.bits, 0, sizeof(uint32_t) * N * W, st));
+    }
     SortArgs a{};
     a.bt = bt;
-    a.cnt = m->col_state; a.codeor = m->col_state + N;
-    a.colinfo = m->col_info; a.bits = m->col_bits; a.W = W; a.counters = m->col_counters;
-    a.matches = m->col_matches; a.tasks = m->col_tasks; a.colseg = m->col_seg; a.heavy = heavy_model(m) ? m->col_heavy : nullptr;
+    a.cnt = wl.state; a.codeor = wl.state + N;
+    a.colinfo = wl.info; a.bits = wl.bits; a.W = W; a.counters = wl.counters;
+    a.matches = wl.matches; a.tasks = wl.tasks; a.colseg = wl.seg; a.heavy = heavy_model(m) ? wl.heavy : nullptr;
     a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits3 = m->bits; a.dense = dense; a.do_dec = do_dec; a.do_enc = do_enc;
     const int grid = item_grid(m, b);
     g_prof.begin(3, st);
@@ -1822,8 +1955,8 @@ static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   a.s = b->store->dev; a.bt = bt;
   a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits = m->bits; a.dense = dense;
   a.do_dec = do_dec; a.do_enc = do_enc;
-  a.err_flag = m->d_err; a.matches = m->col_matches; a.mcol = m->col_mcol; a.tasks = m->col_tasks;
-  a.colseg = m->col_seg; a.counters = m->col_counters; a.max_matches = (int)m->cfg.max_entries;
+  a.err_flag = m->d_err; a.matches = wl.matches; a.mcol = wl.mcol; a.tasks = wl.tasks;
+  a.colseg = wl.seg; a.counters = wl.counters; a.max_matches = (int)m->cfg.max_entries;
   const int64_t words = (b->store->n_rows + 31) / 32;
   a.bitmap_words = words <= 40 * 1024 ? (int)words : 0;             // <= 160 KB of shared memory
   const size_t smem = (size_t)a.bitmap_words * 4;
@@ -1846,11 +1979,12 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   Layer& enc = m->layers[0];
   Layer& dec = m->layers[L];
   RowArgs r{};
-  r.matches = m->col_matches; r.tasks = m->col_tasks; r.colseg = m->col_seg; r.counters = m->col_counters;
+  const WorkList wl = step_wl(m, b);
+  r.matches = wl.matches; r.tasks = wl.tasks; r.colseg = wl.seg; r.counters = wl.counters;
   // small catalogues (weights + state within reach of the 126 MB L2): latency-bound, wide walk; else HBM-bound
   const bool wide = !grad_mode && (size_t)m->cfg.n_cols * (size_t)hpx <= ((size_t)8 << 20);
-  const bool heavy = (wide || heavy_model(m)) && heavy_rows() && !b->store->has_dups && !grad_mode;
-  r.heavy = heavy ? m->col_heavy : nullptr;      // the batch-side K4a lists them; the CSC scan does not
+  const bool heavy = heavy_model(m) && !b->store->has_dups && !grad_mode;      // exactly when K4a lists heavy tasks
+  r.heavy = heavy ? wl.heavy : nullptr;          // the batch-side K4a lists them; the CSC scan does not
   r.hdec = drop ? m->h[L - 1] : m->act[L - 1]; r.dz0 = m->dz[0]; r.dy = m->dy;
   r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
   r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
@@ -1861,7 +1995,7 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
   g_prof.begin(5, st);
   // a dependent launch: its predecessor in this stream is a kernel (the backward pass, or the first of two row updates)
-  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count * (wide ? 4 : 6), wide, heavy, r, st, !g_prof.on));
+  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count, wide, heavy, r, st, !g_prof.on));
   g_prof.end(5, st);
   return OCF_OK;
 }
@@ -1870,6 +2004,7 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
 // enqueued on `st` (the batch's gather, the previous step's update which reads the match list).
 static int fork_scan(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
   m->scan_pending = false;
+  if (wl_current(m, b)) return OCF_OK;          // grouped ahead of the step on the batch's stream (prepare_worklist)
   const int L = m->L;
   const OptDev opt = make_opt(m);
   const int dense = m->par_mode == OCF_PAR_ROWS ? 0 : opt.dense;   // gradient rows exist for touched columns only
@@ -1877,7 +2012,7 @@ static int fork_scan(ocf_model* m, const ocf_batch* b, cudaStream_t st) {
   if (!do_dec && !do_enc) return OCF_OK;
   OCF_CUDA(cudaEventRecord(m->ev_fork, st));
   OCF_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-  OCF_TRY(launch_scan(m, b, do_dec, do_enc, dense, m->side));
+  OCF_TRY(launch_scan(m, b, do_dec, do_enc, dense, m->side, model_wl(m)));
   OCF_CUDA(cudaEventRecord(m->ev_join, m->side));
   m->scan_pending = true;
   return OCF_OK;
@@ -1941,8 +2076,9 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   // decoder and encoder rows share one padded width in the reference's architectures (one
   // num_hidden_units). A width list with different ends shares the grouping too: its task list holds both kinds of
   // rows and each of the two launches (one per width) takes its own.
-  if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
-  else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, dense, st));
+  if (wl_current(m, b)) {}                        // the batch brought its list along
+  else if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
+  else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, dense, st, model_wl(m)));
   if (hpd == hpe) {
     OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd, opt, st, grad_mode));
   } else {
@@ -2204,6 +2340,102 @@ static bool graphs_enabled() {
   return on;
 }
 
+// ---- K4a ahead of the step --------------------------------------------------------------------------
+// The column grouping needs nothing but the gathered batch, so a single-GPU training step runs it on the batch's
+// own stream right behind the gather: it executes under whatever step the device is still busy with (the host
+// enqueues a step or two ahead) instead of beside this step's K2 / K3. OCF_NO_AHEAD=1: back inside the step.
+static bool ahead_enabled() {
+  static const bool on = [] { const char* e = std::getenv("OCF_NO_AHEAD"); return !(e && e[0] == '1'); }();
+  return on;
+}
+static bool ahead_ok(const ocf_model* m, const ocf_batch* b, const ocf_step_args* args) {
+  return ahead_enabled() && m->par_mode == 0 && m->comm == nullptr && (args == nullptr || args->phase == 0) && b->mode == 1 &&
+         b->store != nullptr && !b->store->has_dups && b->gstream != nullptr && b->gathered_valid &&
+         (m->layers[0].trainable || m->layers[m->L].trainable) && b->dev.B <= b->max_rows;
+}
+
+// [seg | counters | state | bits] is one region: a single memset clears what K4a counts into.
+static int worklist_alloc(ocf_batch* b, const ocf_model* m) {
+  const size_t N = (size_t)m->cfg.n_cols;
+  if (b->wl_cols == m->cfg.n_cols && b->wl_nblk == m->nblk) return OCF_OK;
+  if (b->wl_cols != 0) {
+    // another catalogue / input layout: steps captured with the old pointers are stale, the batch takes a new identity
+    OCF_CUDA(cudaDeviceSynchronize());
+    b->wl_mem.release();
+    if (b->wl_graph) { cudaGraphExecDestroy(b->wl_graph); b->wl_graph = nullptr; }
+    b->wl_graph_failed = false;
+    b->uid = ++g_batch_uid;
+    b->wl_cols = 0; b->wl_seq = 0;
+  }
+  const size_t Wcap = (size_t)(b->max_rows + 31) / 32;
+  const size_t seg_b = sizeof(int2) * N, cnt_b = 32, state_b = sizeof(int) * 2 * N, bits_b = sizeof(uint32_t) * N * Wcap;
+  uint8_t* z = nullptr;
+  OCF_TRY(b->wl_mem.get(&z, seg_b + cnt_b + state_b + bits_b, true));
+  b->wl_zero = z;
+  b->wl.seg = reinterpret_cast<int2*>(z);
+  b->wl.counters = reinterpret_cast<int*>(z + seg_b);
+  b->wl.state = reinterpret_cast<int*>(z + seg_b + cnt_b);
+  b->wl.bits = reinterpret_cast<uint32_t*>(z + seg_b + cnt_b + state_b);
+  OCF_TRY(b->wl_mem.get(&b->wl.tasks, N * (size_t)(m->nblk + 1)));
+  OCF_TRY(b->wl_mem.get(&b->wl.heavy, N * (size_t)(m->nblk + 1)));
+  OCF_TRY(b->wl_mem.get(&b->wl.info, N));
+  OCF_TRY(b->wl_mem.get(&b->wl.matches, (size_t)std::max<int64_t>(b->max_entries, 1) * 3));
+  b->wl.mcol = nullptr;
+  b->wl_cols = m->cfg.n_cols; b->wl_nblk = m->nblk;
+  return OCF_OK;
+}
+
+static int worklist_enqueue(ocf_model* m, ocf_batch* b, const WorkSig& sig, cudaStream_t s) {
+  const size_t N = (size_t)sig.n_cols, W = (size_t)(sig.B + 31) / 32;
+  uint8_t* z0 = sig.dense ? b->wl_zero : reinterpret_cast<uint8_t*>(b->wl.counters);
+  const size_t bytes = (sig.dense ? sizeof(int2) * N : 0) + 32 + sizeof(int) * 2 * N + sizeof(uint32_t) * N * W;
+  OCF_CUDA(cudaMemsetAsync(z0, 0, bytes, s));
+  return launch_scan(m, b, sig.do_dec, sig.do_enc, sig.dense, s, b->wl, true);
+}
+
+static int prepare_worklist(ocf_model* m, ocf_batch* b, cudaStream_t user) {
+  const WorkSig sig = work_sig(m, b);
+  if (b->wl_seq != 0 && b->wl_seq == b->fill_seq && b->wl_sig == sig) {
+    // a second step on the same fill walks the same list: only K4b's task cursors start over
+    OCF_CUDA(cudaMemsetAsync(b->wl.counters + 3, 0, 2 * sizeof(int), user));
+    return OCF_OK;
+  }
+  OCF_TRY(worklist_alloc(b, m));
+  cudaStream_t gs = b->gstream;                                                        // the fill ran here: in order behind it
+  if (b->consumed_valid) OCF_CUDA(cudaStreamWaitEvent(gs, b->consumed, 0));            // the list's previous reader
+  bool done = false;
+  if (graphs_enabled() && !g_prof.on) {
+    if (b->wl_graph != nullptr && !(b->wl_graph_sig == sig)) { cudaGraphExecDestroy(b->wl_graph); b->wl_graph = nullptr; b->wl_graph_failed = false; }
+    if (b->wl_graph == nullptr && !b->wl_graph_failed) {
+      const long long launched = g_launches.load();
+      const bool was_capturing = m->capturing;
+      m->capturing = true;                         // grids sized to the batch object's capacity (item_grid)
+      cudaGraph_t graph = nullptr;
+      int rc = OCF_OK;
+      if (cudaStreamBeginCapture(m->cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); rc = OCF_ERR_CUDA; }
+      else {
+        rc = worklist_enqueue(m, b, sig, m->cap);
+        if (cudaStreamEndCapture(m->cap, &graph) != cudaSuccess) { cudaGetLastError(); rc = OCF_ERR_CUDA; graph = nullptr; }
+      }
+      m->capturing = was_capturing;
+      b->wl_graph_kernels = (int)(g_launches.load() - launched);
+      g_launches.store(launched);
+      if (rc == OCF_OK && graph != nullptr && cudaGraphInstantiate(&b->wl_graph, graph, 0) != cudaSuccess) { cudaGetLastError(); b->wl_graph = nullptr; }
+      if (graph) cudaGraphDestroy(graph);
+      if (b->wl_graph == nullptr) b->wl_graph_failed = true; else b->wl_graph_sig = sig;
+    }
+    if (b->wl_graph != nullptr) {
+      OCF_CUDA(cudaGraphLaunch(b->wl_graph, gs));
+      g_launches.fetch_add(b->wl_graph_kernels, std::memory_order_relaxed);
+      done = true;
+    }
+  }
+  if (!done) OCF_TRY(worklist_enqueue(m, b, sig, gs));
+  OCF_CUDA(cudaEventRecord(b->wl_ready, gs));
+  b->wl_seq = b->fill_seq; b->wl_sig = sig;
+  return OCF_OK;
+}
+
 // Runs a whole step (phase 0) of a single-GPU or column-sharded model. The first time a (batch object,
 // rows, kind) combination is seen the body runs as plain launches (lazy allocations happen there), the
 // second time it is captured into a CUDA graph, from then on the graph is replayed: one launch per step,
@@ -2214,7 +2446,7 @@ static int run_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, bool 
   const bool peer = m->par_mode == OCF_PAR_COLUMNS && use_peer(m, b->dev.B);     // exchange epochs are launch arguments
   bool done = false;
   if (graphs_enabled() && !g_prof.on && !b->store->has_dups && !peer) {
-    const auto key = std::make_tuple(b->uid, b->dev.B, train ? 1 : 0, args ? args->rows_total : 0, args ? args->row0 : 0);
+    const auto key = std::make_tuple(b->uid, b->dev.B, train ? (wl_current(m, b) ? 3 : 1) : 0, args ? args->rows_total : 0, args ? args->row0 : 0);
     ocf_model::StepGraph& g = m->graphs[key];
     if (g.exec == nullptr && !g.failed && g.seen++ >= 1) {
       const long long launched = g_launches.load();
@@ -2252,7 +2484,9 @@ static int run_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, bool 
 
 static int ocf_train_step_impl(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_);
 extern "C" int ocf_train_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, float* host_metrics, void* stream_) {
+  if (m && b && check_step(m, b, true) == OCF_OK && ahead_ok(m, b, args)) OCF_TRY(prepare_worklist(m, b, as_stream(stream_)));
   if (b) OCF_TRY(batch_acquire(b, as_stream(stream_)));          // the batch's fill runs on its own stream
+  if (m && b && wl_current(m, b)) OCF_CUDA(cudaStreamWaitEvent(as_stream(stream_), b->wl_ready, 0));
   const int rc = ocf_train_step_impl(m, b, args, host_metrics, stream_);
   if (b && rc == OCF_OK) OCF_TRY(batch_release(b, as_stream(stream_)));
   return rc;

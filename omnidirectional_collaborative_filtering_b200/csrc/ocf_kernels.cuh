@@ -1164,6 +1164,9 @@ struct RowArgs {
   OptDev opt;
 };
 
+#ifndef OCF_K4B_VARIANT
+#define OCF_K4B_VARIANT 0
+#endif
 constexpr int KIND_GRAD = 4;              // k_row_update: store the gradient row, apply nothing
 
 // WIDE: two matched activation rows in flight per step of a task's walk (more registers, fewer resident warps): for
@@ -1309,16 +1312,7 @@ k_row_update(RowArgs a) {
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const long long n_tasks = a.dense ? (long long)a.n_cols * a.n_arr : (long long)a.counters[1];
-  for (long long t = gwarp; t < n_tasks; t += nwarps) {
-    int c, arr, base, n;
-    if (a.dense) {
-      c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
-      const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
-    } else {
-      const int4 task = a.tasks[t]; c = task.x; arr = task.y; base = task.z; n = task.w;
-      if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
-    }
-    if (HEAVY && a.heavy != nullptr && n > HEAVY_N) continue;            // done above by a whole CTA
+  auto run_task = [&](int c, int arr, int base, int n) {
     const size_t r = row_of(c, arr);
     float4 w[NV], t1[NV], t2[NV], g[NV];
     load_row(arr, r, w, t1, t2);
@@ -1327,6 +1321,55 @@ k_row_update(RowArgs a) {
     float cs = 0.f;
     walk(arr, base, 0, n, g, cs);
     finish(c, arr, r, g, cs, w, t1, t2);
+  };
+#if OCF_K4B_VARIANT == 2
+  // Tasks are dealt out in chunks of 4 through a cursor (zeroed with the work list's counters): a warp that drew a
+  // long match list simply takes fewer chunks, and the kernel has no tail of unlucky warps. The cursor for the next
+  // chunk is bumped before the current chunk is processed (its round trip hides behind the chunk), and the chunk's
+  // four task descriptors arrive in one load.
+  if (!a.dense) {
+    int* cursor = const_cast<int*>(a.counters) + (a.only == 2 ? 4 : 3);
+    int pend = lane == 0 ? atomicAdd(cursor, 4) : 0;
+    for (;;) {
+      const int t0 = __shfl_sync(FULL, pend, 0);
+      if (t0 >= n_tasks) break;
+      if (lane == 0) pend = atomicAdd(cursor, 4);
+      int4 mine = make_int4(0, 0, 0, 0);
+      if (lane < 4 && t0 + lane < n_tasks) mine = a.tasks[t0 + lane];
+      const int cnt = (int)min((long long)4, n_tasks - t0);
+      for (int k = 0; k < cnt; ++k) {
+        const int c = __shfl_sync(FULL, mine.x, k), arr = __shfl_sync(FULL, mine.y, k);
+        const int base = __shfl_sync(FULL, mine.z, k), n = __shfl_sync(FULL, mine.w, k);
+        if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
+        if (HEAVY && a.heavy != nullptr && n > HEAVY_N) continue;          // done above by a whole CTA
+        run_task(c, arr, base, n);
+      }
+    }
+    return;
+  }
+#endif
+#if OCF_K4B_VARIANT == 1
+  // the next task's descriptor is loaded before this task's rows: one L2 round trip less in every task's chain
+  int4 nxt = make_int4(0, 0, 0, 0);
+  if (!a.dense && gwarp < n_tasks) nxt = a.tasks[gwarp];
+#endif
+  for (long long t = gwarp; t < n_tasks; t += nwarps) {
+    int c, arr, base, n;
+    if (a.dense) {
+      c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
+      const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
+    } else {
+#if OCF_K4B_VARIANT == 1
+      const int4 task = nxt;
+      if (t + nwarps < n_tasks) nxt = a.tasks[t + nwarps];
+#else
+      const int4 task = a.tasks[t];
+#endif
+      c = task.x; arr = task.y; base = task.z; n = task.w;
+      if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
+    }
+    if (HEAVY && a.heavy != nullptr && n > HEAVY_N) continue;            // done above by a whole CTA
+    run_task(c, arr, base, n);
   }
 }
 
