@@ -153,8 +153,8 @@ def scoring_run(lib, m, rd, w, aux, rows, reps, warm):
                     "note": "bounded by the PCIe read-back of the [rows, N] float32 score matrix"},
             "roofline": {"kernel": "k_score_tc2 (tcgen05 cta_group::2 kind::tf32)", "bound": "tensor", "achieved": flops / (gemm_ms * 1e-3) / 1e12,
                          "peak": peak, "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak,
-                         # DRAM bytes per launch of the committed ncu --set full capture (profiles/r01_ncu_full_k_score_tc2_v3.txt)
-                         "traffic": 389.3e6 if (rows == 1024 and N == 71567 and hp == 512) else None,
+                         # DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json)
+                         "traffic": ncu_traffic("score_%dx%dx%d" % (rows, N, hp), "k_score_tc2")[0],
                          "peak_source": src, "kernel_ms": gemm_ms, "share_of_step": gemm_ms / ms,
                          "out_GBs": 4.0 * rows * N / (gemm_ms * 1e-3) / 1e9}}
 
@@ -556,7 +556,8 @@ def main():
                 yield b
             done += n
 
-    for b in epochs(max(W, 9)):              # three rounds of the reader's ring of 3 batch buffers: plain, capture, replay
+    ring_depth = max(2, int(os.environ.get("OCF_RING_DEPTH", "3")))
+    for b in epochs(max(W, 3 * ring_depth)):   # three rounds of the reader's ring of batch buffers: plain, capture, replay
         m.train_on_batch(b, sync=True)
     torch.cuda.synchronize()
     h2d = 0

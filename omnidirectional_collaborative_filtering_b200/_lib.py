@@ -12,9 +12,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# $OCF_LIB_VARIANT=<tag> loads csrc/libocf_b200_<tag>.so: kernel variants built side by side for A/B runs on one GPU box
-# (`make variants` in csrc/); unset = the product library
-SO_PATH = os.path.join(HERE, "csrc", "libocf_b200%s.so" % ("_" + os.environ["OCF_LIB_VARIANT"] if os.environ.get("OCF_LIB_VARIANT") else ""))
+SO_PATH = os.path.join(HERE, "csrc", "libocf_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "ocf.h")
 
 

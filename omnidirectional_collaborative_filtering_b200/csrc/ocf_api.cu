@@ -18,7 +18,6 @@
 #include "ocf_gemm_tc.cuh"
 #include "ocf_peer.cuh"
 #include "ocf_topk.cuh"
-#include "ocf_staged.cuh"
 
 namespace ocf {
 
@@ -155,6 +154,7 @@ struct ocf_rng {
   std::vector<char> slot_free_valid;
   std::vector<int> cur;                         // which of its two array buffers worker j holds
   cudaEvent_t placed = nullptr;
+  cudaStream_t io = nullptr;                    // read-backs of the state: never through the legacy stream, which would wait for every step in flight
   int64_t next_block = 0;                       // first block not enqueued yet
   int64_t pos_u = 0;                            // consumers' position (absolute word)
   uint32_t origin[624] = {0};
@@ -306,6 +306,10 @@ struct ocf_model {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool scan_pending = false;
+  // models with hidden layers: the decoder rows' update (needs K3's outputs only) and every hidden layer's gradient
+  // product (needs its own dz only) leave the step's critical path on a second side stream
+  cudaStream_t side2 = nullptr;
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr, ev_dz[8] = {nullptr};
   // multi-GPU (ocf_model_set_comm)
   ocf_comm* comm = nullptr;
   int par_mode = 0;               // 0 none, OCF_PAR_COLUMNS, OCF_PAR_ROWS
@@ -334,16 +338,6 @@ constexpr int N_REGPART = 64;
 static bool pdl_on() {
   static const bool on = [] { const char* e = std::getenv("OCF_NO_PDL"); return !(e && e[0] == '1'); }();
   return on;
-}
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl_smem(bool pdl, size_t smem, void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (pdl && pdl_on()) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
@@ -764,8 +758,9 @@ static int batch_stage(ocf_batch* b, const int32_t* row_ids, int n_rows, const s
     h_rows[r] = row; h_eoff[r] = (int32_t)e; h_inlen[r] = (int32_t)na; h_iptr[r] = it;
     if (with_draws) { h_draw[r] = (int32_t)draw; draw += draw_len ? draw_len[r] : na; }
     const int64_t n = na + nb;
-    if (n == 0) h_items[it++] = make_int4(r, 0, 0, 0);
-    for (int64_t s0 = 0; s0 < n; s0 += ch) h_items[it++] = make_int4(r, (int)s0, (int)std::min<int64_t>(ch, n - s0), 0);
+    // item = (batch row, start inside the row, length, absolute position of the first entry)
+    if (n == 0) h_items[it++] = make_int4(r, 0, 0, (int)e);
+    for (int64_t s0 = 0; s0 < n; s0 += ch) h_items[it++] = make_int4(r, (int)s0, (int)std::min<int64_t>(ch, n - s0), (int)(e + s0));
     e += n; tcount += nb;
   }
   h_eoff[n_rows] = (int32_t)e; h_iptr[n_rows] = it;
@@ -915,6 +910,7 @@ static void rng_release(ocf_rng* r) {
   for (cudaEvent_t e : r->block_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : r->slot_free) cudaEventDestroy(e);
   if (r->placed) cudaEventDestroy(r->placed);
+  if (r->io) { cudaStreamDestroy(r->io); r->io = nullptr; }
   r->wstream.clear(); r->block_ev.clear(); r->slot_free.clear(); r->placed = nullptr;
   r->mem.release();
   r->d_ring = r->d_arrays = r->d_seq = r->d_poly = nullptr;
@@ -1075,7 +1071,11 @@ extern "C" int ocf_rng_get_state(ocf_rng* r, uint32_t* key, int32_t* pos) {
   const int slot = (int)(k % r->R);
   OCF_CUDA(cudaEventSynchronize(r->block_ev[slot]));
   uint32_t tmp[624];
-  OCF_CUDA(cudaMemcpy(tmp, r->d_ring + (size_t)((624 * g) % r->RW), sizeof(tmp), cudaMemcpyDeviceToHost));
+  // the block is complete (event above); a synchronous copy would also wait for every train step queued on the legacy
+  // stream and drain the pipeline at each epoch boundary (the host needs the state for np.random.permutation)
+  if (r->io == nullptr) OCF_CUDA(cudaStreamCreateWithFlags(&r->io, cudaStreamNonBlocking));
+  OCF_CUDA(cudaMemcpyAsync(tmp, r->d_ring + (size_t)((624 * g) % r->RW), sizeof(tmp), cudaMemcpyDeviceToHost, r->io));
+  OCF_CUDA(cudaStreamSynchronize(r->io));
   for (int i = 0; i < 624; ++i) key[i] = mtj::untemper(tmp[i]);
   return OCF_OK;
 }
@@ -1360,8 +1360,14 @@ extern "C" int ocf_model_create(const ocf_model_config* cfg, ocf_model** out) {
   if (cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
       cudaStreamCreateWithPriority(&m->cap, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess)
+      cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&m->side2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_join2, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(OCF_ERR_CUDA, "ocf_model_create: side stream creation failed"));
+  for (int k = 0; k < 8; ++k)
+    if (cudaEventCreateWithFlags(&m->ev_dz[k], cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(OCF_ERR_CUDA, "ocf_model_create: event creation failed"));
   *out = m;
   st = ocf_model_set_optimizer(m, OCF_OPT_ADAGRAD, 0.005f, 0.9f, 0.999f, 1e-8f, 0.f);   // train.py:50-51
   if (st) { *out = nullptr; return bail(st); }
@@ -1379,6 +1385,10 @@ extern "C" int ocf_model_destroy(ocf_model* m) {
     if (m->cap) cudaStreamDestroy(m->cap);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->side2) cudaStreamDestroy(m->side2);
+    if (m->ev_fork2) cudaEventDestroy(m->ev_fork2);
+    if (m->ev_join2) cudaEventDestroy(m->ev_join2);
+    for (int k = 0; k < 8; ++k) if (m->ev_dz[k]) cudaEventDestroy(m->ev_dz[k]);
     delete m;
   }
   return OCF_OK;
@@ -1736,13 +1746,13 @@ static int hidden_dw_tc(ocf_model* m, int l, int B, const float* hin, const OptD
 // xslot: write the row statistics [B, 4] and dL/dh [B, hp] into this exchange slot instead of the
 // model's buffers (a peer all-reduce follows).
 // after_kernel: the previous operation in the stream is a kernel (the phase's first launch may be a dependent launch)
-// K3 through shared memory (ocf_staged.cuh) when the batch object's work items are short: decided by the object's
-// capacity, so that a captured step keeps its kernel whatever a later fill holds. OCF_DEC_STAGED=0|1 forces.
-static bool dec_staged(const ocf_batch* b) {
-  static const int forced = [] { const char* e = std::getenv("OCF_DEC_STAGED"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
-  if (forced >= 0) return forced == 1;
-  return pick_chunk(b->max_entries) <= 256;
+// An unsharded model's K3 leaves dz of the top hidden layer itself (DzFuse): dL/dh of a row is complete on this device.
+// A column shard all-reduces dL/dh first and keeps the separate kernel. OCF_OVERLAP bit 4 off: separate kernel everywhere.
+static int overlap_bits() {
+  static const int bits = [] { const char* e = std::getenv("OCF_OVERLAP"); return e ? std::atoi(e) : 7; }();
+  return bits;
 }
+static bool fuse_dz(const ocf_model* m) { return (overlap_bits() & 4) && !m->cfg.sharded && m->par_mode == 0; }
 
 static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args,
                         float* dense_out, cudaStream_t st, bool act0_done = false, float* xslot = nullptr, bool after_kernel = false) {
@@ -1766,26 +1776,22 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   const float gscale = (float)((m->cfg.loss == OCF_LOSS_MSE ? 2.0 : 1.0) / bn);
   float* stats_out = xslot ? xslot : m->rowstats;
   float4* dh_out = reinterpret_cast<float4*>(xslot ? xslot + (size_t)B * ROWSTAT_W : m->dh_top);
+  DzFuse fz{};
+  if (training && xslot == nullptr && fuse_dz(m)) {
+    fz.a = reinterpret_cast<const float4*>(m->act[L - 1]);
+    fz.dscale = drop ? reinterpret_cast<const float4*>(m->dscale[L - 1]) : nullptr;
+    fz.dz = reinterpret_cast<float4*>(m->dz[L - 1]);
+    fz.act = m->cfg.activation;
+  }
   g_prof.begin(2, st);
-  if (dec_staged(b)) {
-    // short work items: the rows come through shared memory (copy engine), ocf_staged.cuh
-    if (training) {
-      OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, st::k_dec_fwd_st<NV, true>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
-                                             (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2),
-                                             m->itemstats, dense_out, m->cfg.n_cols, m->tail, dh_out, stats_out)));
-    } else {
-      OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, st::k_dec_fwd_st<NV, false>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
-                                             (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, (float*)nullptr, (float4*)nullptr,
-                                             m->itemstats, dense_out, m->cfg.n_cols, m->tail, (float4*)nullptr, stats_out)));
-    }
-  } else if (training) {
+  if (training) {
     OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, k_dec_fwd<NV, true>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
                                            (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, m->dy, reinterpret_cast<float4*>(m->P2),
-                                           m->itemstats, dense_out, m->cfg.n_cols, m->tail, dh_out, stats_out)));
+                                           m->itemstats, dense_out, m->cfg.n_cols, m->tail, dh_out, stats_out, fz)));
   } else {
     OCF_NV_SWITCH(hpt, OCF_CUDA(launch_pdl(dep, k_dec_fwd<NV, false>, dim3(item_grid(m, b)), dim3(128), st, bt, (const float*)m->layers[L].W,
                                            (const float*)m->layers[L].b, htop, gscale, m->cfg.loss, (float*)nullptr, (float4*)nullptr,
-                                           m->itemstats, dense_out, m->cfg.n_cols, m->tail, (float4*)nullptr, stats_out)));
+                                           m->itemstats, dense_out, m->cfg.n_cols, m->tail, (float4*)nullptr, stats_out, fz)));
   }
   OCF_LAUNCHED();
   g_prof.end(2, st);
@@ -1843,38 +1849,7 @@ static int launch_row_update_nv(int kind, int grid, const RowArgs& r, cudaStream
   return OCF_OK;
 }
 
-// K4b with the rows staged through shared memory by the copy engine (ocf_staged.cuh): the lean variant's job,
-// i.e. catalogues far beyond L2. OCF_UPD_STAGED=0 keeps the register version.
-static bool upd_staged() {
-  static const bool on = [] { const char* e = std::getenv("OCF_UPD_STAGED"); return !(e && e[0] == '0'); }();
-  return on;
-}
-template <int NV, int KIND>
-static int launch_row_update_st(int sm_count, const RowArgs& r, cudaStream_t st, bool dep) {
-  using C = st::UpdCfg<NV, KIND>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OCF_CUDA(cudaFuncSetAttribute(st::k_row_update_st<NV, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
-  }
-  OCF_CUDA(launch_pdl_smem(dep, (size_t)C::SMEM, st::k_row_update_st<NV, KIND>, dim3(sm_count * C::CTAS_PER_SM), dim3(C::WARPS * 32), st, r));
-  OCF_LAUNCHED();
-  return OCF_OK;
-}
-template <int NV>
-static int launch_row_update_st_nv(int kind, int sm_count, const RowArgs& r, cudaStream_t st, bool dep) {
-  switch (kind) {
-    case OCF_OPT_SGD: return launch_row_update_st<NV, OCF_OPT_SGD>(sm_count, r, st, dep);
-    case OCF_OPT_ADAGRAD: return launch_row_update_st<NV, OCF_OPT_ADAGRAD>(sm_count, r, st, dep);
-    case OCF_OPT_RMSPROP: return launch_row_update_st<NV, OCF_OPT_RMSPROP>(sm_count, r, st, dep);
-    default: return launch_row_update_st<NV, OCF_OPT_ADAM>(sm_count, r, st, dep);
-  }
-}
-
 static int launch_row_update(int hp, int kind, int sm_count, bool wide, bool heavy, const RowArgs& r, cudaStream_t st, bool dep) {
-  if (!wide && !heavy && kind != KIND_GRAD && upd_staged()) {
-    OCF_NV_SWITCH(hp, return (launch_row_update_st_nv<NV>(kind, sm_count, r, st, dep)));
-  }
   const int grid = sm_count * (wide ? 4 : 6);
   if (wide) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, true, true>(kind, grid, r, st, dep))); }
   else if (heavy) { OCF_NV_SWITCH(hp, return (launch_row_update_nv<NV, false, true>(kind, grid, r, st, dep))); }
@@ -1972,7 +1947,7 @@ static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
 
 // K4b: one warp per (column, array) task: gradient row from the matches, fused optimizer update.
 static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc, int hpx, const OptDev& opt, cudaStream_t st,
-                       bool grad_mode = false, int only = 0) {
+                       bool grad_mode = false, int only = 0, bool after_kernel = true) {
   if (!do_dec && !do_enc) return OCF_OK;
   const int L = m->L;
   const bool drop = m->cfg.dropout_p > 0.f;
@@ -1995,7 +1970,7 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   if (do_enc) for (int blk = 0; blk < m->nblk; ++blk) r.arr_map[r.n_arr++] = 1 + blk;
   g_prof.begin(5, st);
   // a dependent launch: its predecessor in this stream is a kernel (the backward pass, or the first of two row updates)
-  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count, wide, heavy, r, st, !g_prof.on));
+  OCF_TRY(launch_row_update(hpx, grad_mode ? KIND_GRAD : opt.kind, m->sm_count, wide, heavy, r, st, after_kernel && !g_prof.on));
   g_prof.end(5, st);
   return OCF_OK;
 }
@@ -2031,9 +2006,32 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   const int n_reg = launch_reg(m, st);          // L2 term of the reported loss uses pre-update weights
   if (n_reg_out) *n_reg_out = n_reg;
   if (grad_mode) OCF_CUDA(cudaMemsetAsync(m->grads, 0, sizeof(float) * m->grads_count, st));
+  Layer& enc = m->layers[0];
+  Layer& dec = m->layers[L];
+  const int hpd = m->hp[L - 1], hpe = m->hp[0];
+  // What is not on the critical path K3 -> (backward products of the hidden layers) -> encoder rows runs on a second
+  // stream beside it and joins at the end of the step:
+  //   bit 4  the bias gradients (column sums of dz; K3 has already left dz of the top layer, fuse_dz) and, riding along
+  //          with the first of them, the step's metric record;
+  //   bit 1  the gradient product + update of hidden layer l: needs dz_l, and W_l no longer being read by the backward product;
+  //   bit 2  the decoder rows' update: needs nothing after K3 (only when it is a real kernel: a catalogue of a few
+  //          hundred columns updates in one small launch either way).
+  // OCF_OVERLAP=<bits> (default 7), 0: one stream, separate dz kernel.
+  const int bits = overlap_bits();
+  const bool fz = fuse_dz(m) && !grad_mode;
+  const bool side_ok = !grad_mode && m->par_mode == 0 && wl_current(m, b) && m->side2 != nullptr && !g_prof.on;
+  const bool side_bias = side_ok && fz;
+  const bool split_dw = side_ok && L > 1 && tc_hidden() && (bits & 1);
+  const bool split = side_ok && L > 1 && (bits & 2) && (size_t)m->cfg.n_cols * (size_t)hpd >= ((size_t)1 << 20);
+  bool forked = false;
+  if (side_bias || (split && dec.trainable)) {
+    OCF_CUDA(cudaEventRecord(m->ev_fork2, st));
+    OCF_CUDA(cudaStreamWaitEvent(m->side2, m->ev_fork2, 0));
+    forked = true;
+  }
   // dependent launches (PDL) from here on whenever the previous operation in the stream is a kernel
   bool dep = (after_kernel || n_reg > 0) && !grad_mode && !g_prof.on;
-  // top hidden layer: dz and its bias
+  // top hidden layer: dz (unless K3 left it) and its bias
   {
     const int l = L - 1;
     Layer& ly = m->layers[l];
@@ -2041,12 +2039,14 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     // other ranks' row statistics first and computes it after the gather)
     MetricArgs met{};
     if (!grad_mode) met = metric_args(m, B, args, n_reg, true);
-    OCF_CUDA(launch_pdl(dep, k_dz_bias, dim3(m->hp[l] / 32 + (grad_mode ? 0 : 1)), dim3(1024), st, (const float*)m->dh_top, (const float*)m->act[l],
-                        (const float*)(drop ? m->dscale[l] : nullptr), B, m->hp[l], m->cfg.activation, 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt,
+    OCF_CUDA(launch_pdl(side_bias ? false : dep, k_dz_bias, dim3(m->hp[l] / 32 + (grad_mode ? 0 : 1)), dim3(1024), side_bias ? m->side2 : st,
+                        (const float*)(fz ? m->dz[l] : m->dh_top), (const float*)m->act[l],
+                        (const float*)(drop ? m->dscale[l] : nullptr), B, m->hp[l], m->cfg.activation, fz ? 1 : 0, m->dz[l], ly.b, ly.bs1, ly.bs2, opt,
                         ly.trainable ? 1 : 0, grad_mode ? m->gb[l] : (float*)nullptr, met));
     OCF_LAUNCHED();
-    dep = !g_prof.on;
+    if (!side_bias) dep = !g_prof.on;
   }
+  if (split && dec.trainable) OCF_TRY(launch_rows(m, b, 1, 0, hpd, opt, m->side2, false, 1, side_bias));
   for (int l = L - 1; l >= 1; --l) {
     Layer& ly = m->layers[l];
     // dz_{l-1} = (dz_l . W_l^T) * dropout scale * act'(a_{l-1})   (uses W_l before its update)
@@ -2054,8 +2054,16 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
     ep.aux1 = drop ? m->dscale[l - 1] : nullptr; ep.act = m->cfg.activation;
     if (tc_hidden()) OCF_TRY(hidden_dz_tc(m, l, B, drop, st, dep));
     else OCF_TRY(launch_gemm(m, false, true, m->dz[l], m->hp[l], ly.W, m->hp[l], B, m->hp[l - 1], m->hp[l], ep, st));
+    dep = !g_prof.on;
+    const bool to_side = side_bias || (split_dw && ly.trainable);
+    if (to_side) {
+      OCF_CUDA(cudaEventRecord(m->ev_dz[l], st));
+      OCF_CUDA(cudaStreamWaitEvent(m->side2, m->ev_dz[l], 0));
+      forked = true;
+    }
     Layer& lo = m->layers[l - 1];
-    OCF_CUDA(launch_pdl(dep, k_dz_bias, dim3(m->hp[l - 1] / 32), dim3(1024), st, (const float*)m->dz[l - 1], (const float*)nullptr, (const float*)nullptr,
+    OCF_CUDA(launch_pdl(side_bias ? false : dep, k_dz_bias, dim3(m->hp[l - 1] / 32), dim3(1024), side_bias ? m->side2 : st, (const float*)m->dz[l - 1],
+                        (const float*)nullptr, (const float*)nullptr,
                         B, m->hp[l - 1], m->cfg.activation, 1, m->dz[l - 1], lo.b, lo.bs1, lo.bs2, opt, lo.trainable ? 1 : 0,
                         grad_mode ? m->gb[l - 1] : (float*)nullptr, MetricArgs{}));
     OCF_LAUNCHED();
@@ -2064,14 +2072,11 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
       GemmEpi eu{}; eu.kind = EPI_UPDATE; eu.C = ly.W; eu.ldc = m->hp[l]; eu.s1 = ly.Ws1; eu.s2 = ly.Ws2; eu.opt = opt;
       if (grad_mode) { eu.kind = EPI_STORE; eu.C = m->gW[l]; }
       const float* hin = drop ? m->h[l - 1] : m->act[l - 1];
-      if (tc_hidden()) OCF_TRY(hidden_dw_tc(m, l, B, hin, opt, grad_mode ? m->gW[l] : nullptr, st, dep));
+      if (tc_hidden()) OCF_TRY(hidden_dw_tc(m, l, B, hin, opt, grad_mode ? m->gW[l] : nullptr, split_dw ? m->side2 : st, split_dw ? side_bias : dep));
       else OCF_TRY(launch_gemm(m, true, false, hin, m->hp[l - 1], m->dz[l], m->hp[l], m->hp[l - 1], m->hp[l], B, eu, st));
     }
   }
   // catalogue-wide kernels: encoder rows and decoder rows of every touched column
-  Layer& enc = m->layers[0];
-  Layer& dec = m->layers[L];
-  const int hpd = m->hp[L - 1], hpe = m->hp[0];
   const int dense = grad_mode ? 0 : opt.dense;
   // decoder and encoder rows share one padded width in the reference's architectures (one
   // num_hidden_units). A width list with different ends shares the grouping too: its task list holds both kinds of
@@ -2079,11 +2084,17 @@ static int phase_update(ocf_model* m, const ocf_batch* b, const ocf_step_args* a
   if (wl_current(m, b)) {}                        // the batch brought its list along
   else if (m->scan_pending) { OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0)); m->scan_pending = false; }
   else OCF_TRY(launch_scan(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, dense, st, model_wl(m)));
-  if (hpd == hpe) {
+  if (split) {
+    OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st, false, 2));       // the decoder rows are on their way
+  } else if (hpd == hpe) {
     OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, enc.trainable ? 1 : 0, hpd, opt, st, grad_mode));
   } else {
     OCF_TRY(launch_rows(m, b, dec.trainable ? 1 : 0, 0, hpd, opt, st, grad_mode, 1));
     OCF_TRY(launch_rows(m, b, 0, enc.trainable ? 1 : 0, hpe, opt, st, grad_mode, 2));
+  }
+  if (forked) {
+    OCF_CUDA(cudaEventRecord(m->ev_join2, m->side2));
+    OCF_CUDA(cudaStreamWaitEvent(st, m->ev_join2, 0));
   }
   return OCF_OK;
 }

@@ -113,7 +113,7 @@ struct BatchDev {
   const int32_t* row_ids;    // [B] store row of batch row b
   const int32_t* ent_off;    // [B+1] first entry of batch row b
   const int32_t* in_len;     // [B] fixed-split: how many of the row's entries come from the input store
-  const int4* items;         // [n_items] (b, start, len, 0): a chunk of a row's entries
+  const int4* items;         // [n_items] (b, start, len, first entry = ent_off[b] + start): a chunk of a row's entries
   const int32_t* item_ptr;   // [B+1] items of row b
   const uint8_t* flags;      // [n_entries] keep flags (split mode)
   const int32_t* draw_off;   // [B] device-RNG mode: index of the row's first draw in the batch's slice of the stream

@@ -465,11 +465,14 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
   __shared__ float4 red[4][HP / 4];
   __shared__ int2 s_list[128 * 3];          // (weight row, coefficient bits) of the row loads of 128 entries
   __shared__ int s_cnt[3][4];
-  if ((int)blockIdx.x >= bt.hdr->n_items) return;
-  const float aux_val = bt.hdr->aux_value;
+  // header and item are read together (the launch never exceeds the item array's capacity), and the item carries the
+  // absolute position of its first entry: the chain to the first weight row is header/item -> entries -> rows
   const int4 it = bt.items[blockIdx.x];
+  const int n_items = bt.hdr->n_items;
+  const float aux_val = bt.hdr->aux_value;
+  if ((int)blockIdx.x >= n_items) return;
   const int len = it.z;
-  const int p0 = bt.ent_off[it.x] + it.y;
+  const int p0 = it.w;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 acc[NV];
 #pragma unroll
@@ -543,12 +546,17 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
 // The row's last CTA (row_tail) leaves the row's loss statistics in rowstats[b] and, when training,
 // dL/dh of the row in dh_out[b].
 // ============================================================================================
+// With `fz.dz` set (an unsharded model: dL/dh of a row is complete on this device) the row's last CTA goes one step
+// further and leaves dz = dL/dh * dropout scale * act'(a) of the top hidden layer: the first kernel of the backward
+// pass (k_dz_bias) then only sums columns for the bias, off the step's critical path.
+struct DzFuse { const float4* a; const float4* dscale; float4* dz; int act; };
+
 template <int NV, bool TRAIN>
 __global__ void __launch_bounds__(128, NV <= 4 ? 5 : 3)
 k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict__ bdec,
           const float* __restrict__ h, float gscale, int loss_kind,
           float* __restrict__ dy, float4* __restrict__ P2, float* __restrict__ itemstats,
-          float* __restrict__ dense_out, int n_cols, TailBuf tb, float4* __restrict__ dh_out, float* __restrict__ rowstats) {
+          float* __restrict__ dense_out, int n_cols, TailBuf tb, float4* __restrict__ dh_out, float* __restrict__ rowstats, DzFuse fz) {
   pdl_trigger();
   pdl_wait();
   constexpr int HP = NV * 128;
@@ -557,11 +565,12 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
   __shared__ int2 s_list[128];              // (column, entry) of the target entries of 128 entries
   __shared__ float s_t[128];
   __shared__ int s_cnt[4];
-  if ((int)blockIdx.x >= bt.hdr->n_items) return;
+  const int4 it = bt.items[blockIdx.x];     // header and item together, item.w = first entry (see k_enc_fwd)
+  const int n_items = bt.hdr->n_items;
   const float aux_val = bt.hdr->aux_value;
-  const int4 it = bt.items[blockIdx.x];
+  if ((int)blockIdx.x >= n_items) return;
   const int b = it.x, len = it.z;
-  const int p0 = bt.ent_off[b] + it.y;
+  const int p0 = it.w;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 hreg[NV], dh[NV];
 #pragma unroll
@@ -648,7 +657,15 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
         ((sred[0][threadIdx.x] + sred[1][threadIdx.x]) + sred[2][threadIdx.x]) + sred[3][threadIdx.x];
   if (threadIdx.x == 3) itemstats[(size_t)blockIdx.x * ROWSTAT_W + 3] = 0.f;
   row_tail(bt, (int)blockIdx.x, b, P2, TRAIN ? HP / 4 : 0, itemstats, tb,
-           [&](int u, const float4 s) { dh_out[(size_t)b * (HP / 4) + u] = s; },
+           [&](int u, const float4 s) {
+             const size_t idx = (size_t)b * (HP / 4) + u;
+             if (fz.dz == nullptr) { dh_out[idx] = s; return; }
+             float4 d = s;                     // the arithmetic of k_dz_bias, element for element
+             if (fz.dscale != nullptr) { const float4 sc = fz.dscale[idx]; d.x *= sc.x; d.y *= sc.y; d.z *= sc.z; d.w *= sc.w; }
+             const float4 av = fz.a[idx];
+             d.x *= act_bwd(fz.act, av.x); d.y *= act_bwd(fz.act, av.y); d.z *= act_bwd(fz.act, av.z); d.w *= act_bwd(fz.act, av.w);
+             fz.dz[idx] = d;
+           },
            [&](int k, float s) { rowstats[(size_t)b * ROWSTAT_W + k] = s; });
 }
 
@@ -1065,9 +1082,9 @@ struct SortArgs {
 };
 
 __global__ void __launch_bounds__(128) k_sort_count(SortArgs a) {
-  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
   const int4 it = a.bt.items[blockIdx.x];
-  const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
+  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
+  const int b = it.x, p0 = it.w;
   for (int i = threadIdx.x; i < it.z; i += 128) {
     const int code = a.bt.codes[p0 + i];
     if (code == 0) continue;
@@ -1131,9 +1148,9 @@ __global__ void __launch_bounds__(256) k_sort_alloc(SortArgs a) {
 __global__ void __launch_bounds__(128) k_sort_place(SortArgs a) {
   pdl_trigger();
   pdl_wait();
-  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
   const int4 it = a.bt.items[blockIdx.x];
-  const int b = it.x, p0 = a.bt.ent_off[b] + it.y;
+  if ((int)blockIdx.x >= a.bt.hdr->n_items) return;
+  const int b = it.x, p0 = it.w;
   for (int i = threadIdx.x; i < it.z; i += 128) {
     const int p = p0 + i;
     const uint32_t code = a.bt.codes[p];
@@ -1164,9 +1181,6 @@ struct RowArgs {
   OptDev opt;
 };
 
-#ifndef OCF_K4B_VARIANT
-#define OCF_K4B_VARIANT 0
-#endif
 constexpr int KIND_GRAD = 4;              // k_row_update: store the gradient row, apply nothing
 
 // WIDE: two matched activation rows in flight per step of a task's walk (more registers, fewer resident warps): for
@@ -1322,49 +1336,46 @@ k_row_update(RowArgs a) {
     walk(arr, base, 0, n, g, cs);
     finish(c, arr, r, g, cs, w, t1, t2);
   };
-#if OCF_K4B_VARIANT == 2
-  // Tasks are dealt out in chunks of 4 through a cursor (zeroed with the work list's counters): a warp that drew a
-  // long match list simply takes fewer chunks, and the kernel has no tail of unlucky warps. The cursor for the next
-  // chunk is bumped before the current chunk is processed (its round trip hides behind the chunk), and the chunk's
-  // four task descriptors arrive in one load.
-  if (!a.dense) {
+  if (!WIDE && !HEAVY && KIND != KIND_GRAD) {
+    // Lean variant (catalogues far beyond L2, hundreds of tasks per warp): tasks are dealt out in chunks of 4 through
+    // a cursor (zeroed with the work list's counters), so a warp that drew long match lists simply takes fewer
+    // chunks and the kernel has no tail of unlucky warps (Netflix shape: 1.75 -> 1.56 ms, 0.81 -> 0.91 of HBM).
+    // The cursor for the next chunk is bumped before the current chunk is processed (its round trip hides behind
+    // the chunk), and the chunk's four task descriptors arrive in one load.
     int* cursor = const_cast<int*>(a.counters) + (a.only == 2 ? 4 : 3);
     int pend = lane == 0 ? atomicAdd(cursor, 4) : 0;
     for (;;) {
-      const int t0 = __shfl_sync(FULL, pend, 0);
+      const long long t0 = __shfl_sync(FULL, pend, 0);
       if (t0 >= n_tasks) break;
       if (lane == 0) pend = atomicAdd(cursor, 4);
       int4 mine = make_int4(0, 0, 0, 0);
-      if (lane < 4 && t0 + lane < n_tasks) mine = a.tasks[t0 + lane];
+      if (lane < 4 && t0 + lane < n_tasks) {
+        if (a.dense) {
+          const long long t = t0 + lane;
+          const int c = (int)(t / a.n_arr);
+          const int2 seg = a.colseg[c];
+          mine = make_int4(c, a.arr_map[t - (long long)c * a.n_arr], seg.x, seg.y);
+        } else {
+          mine = a.tasks[t0 + lane];
+        }
+      }
       const int cnt = (int)min((long long)4, n_tasks - t0);
       for (int k = 0; k < cnt; ++k) {
         const int c = __shfl_sync(FULL, mine.x, k), arr = __shfl_sync(FULL, mine.y, k);
         const int base = __shfl_sync(FULL, mine.z, k), n = __shfl_sync(FULL, mine.w, k);
-        if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
-        if (HEAVY && a.heavy != nullptr && n > HEAVY_N) continue;          // done above by a whole CTA
+        if (!a.dense && a.only != 0 && (a.only == 1) != (arr == 0)) continue;
         run_task(c, arr, base, n);
       }
     }
     return;
   }
-#endif
-#if OCF_K4B_VARIANT == 1
-  // the next task's descriptor is loaded before this task's rows: one L2 round trip less in every task's chain
-  int4 nxt = make_int4(0, 0, 0, 0);
-  if (!a.dense && gwarp < n_tasks) nxt = a.tasks[gwarp];
-#endif
   for (long long t = gwarp; t < n_tasks; t += nwarps) {
     int c, arr, base, n;
     if (a.dense) {
       c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
       const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
     } else {
-#if OCF_K4B_VARIANT == 1
-      const int4 task = nxt;
-      if (t + nwarps < n_tasks) nxt = a.tasks[t + nwarps];
-#else
       const int4 task = a.tasks[t];
-#endif
       c = task.x; arr = task.y; base = task.z; n = task.w;
       if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
     }

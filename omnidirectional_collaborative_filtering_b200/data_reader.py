@@ -17,6 +17,7 @@ CUDA scatter kernel, so reference-style callers keep working.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import json
 import pickle
 import threading
@@ -168,8 +169,11 @@ class DeviceRng(object):
                 _lib.check(lib.ocf_rng_skip(self.handle, self.pending.pop(t)))   # drawn, never uploaded
             mine = self.pending.pop(ticket)
             self._tune(mine)
-            # the tickets already drawn tell how far the workers may run ahead of this batch
-            _lib.check(lib.ocf_rng_prefetch(self.handle, mine + sum(self.pending.values())))
+            # the tickets already drawn tell how far the workers MAY run ahead of this batch; two more batches is all
+            # they need to (one chain makes a batch's draws in a fifth of a step), and whatever is in flight when the
+            # stream goes back to the host (every epoch start: np.random.permutation) has to drain first
+            ahead = int(os.environ.get("OCF_RNG_AHEAD", "3"))
+            _lib.check(lib.ocf_rng_prefetch(self.handle, min(mine + sum(self.pending.values()), ahead * mine)))
             return self.handle
 
     def release(self):

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -217,8 +218,9 @@ class BatchRing(object):
     """A few DeviceBatch objects used round-robin, so staging batch i+1 on the host overlaps
     the device work of batch i."""
 
-    def __init__(self, max_rows: int, max_entries: int, depth: int = 3):
+    def __init__(self, max_rows: int, max_entries: int, depth: int = 0):
         self.max_rows, self.max_entries = int(max_rows), int(max_entries)
+        depth = depth or max(2, int(os.environ.get("OCF_RING_DEPTH", "3")))
         self.slots = [DeviceBatch(max_rows, max_entries) for _ in range(depth)]
         self.cursor = 0
 
