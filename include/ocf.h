@@ -295,10 +295,8 @@ int64_t ocf_model_steps_logged(const ocf_model* model);
 int ocf_comm_unique_id(uint8_t id[128]);
 int ocf_comm_create(const uint8_t id[128], int32_t rank, int32_t world, ocf_comm** out);
 int ocf_comm_destroy(ocf_comm* comm);
-/* info[0] = rank, [1] = world, [2] = 1 when the ranks have mapped each other's exchange regions
- * (CUDA IPC over NVLink): the two activation exchanges of a column-sharded step then run as
- * one-shot all-reduce kernels fused with the compute that follows (csrc/ocf_peer.cuh) instead of
- * ncclAllReduce. Opt-in: set OCF_P2P=1 in every rank's environment before ocf_comm_create. */
+/* info[0] = rank, [1] = world, [2] = 0 (reserved). The two activation exchanges of a column-sharded step are
+ * ncclAllReduce calls captured in the step's CUDA graph. */
 int ocf_comm_info(const ocf_comm* comm, int32_t info[3]);
 typedef enum {
   OCF_PAR_COLUMNS = 1,   /* item-dimension sharding: the model holds columns [lo, hi) (created with sharded = 1);

@@ -16,7 +16,6 @@
 #include "ocf_mtjump.h"
 #include "ocf_score_tc.cuh"
 #include "ocf_gemm_tc.cuh"
-#include "ocf_peer.cuh"
 #include "ocf_topk.cuh"
 
 namespace ocf {
@@ -103,24 +102,6 @@ using namespace ocf;
 struct ocf_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1, device = 0;
-  // one-shot all-reduce over peer memory (ocf_peer.cuh): [flags | slot 0 | slot 1] on every rank
-  bool p2p = false;
-  uint8_t* region = nullptr;                       // this rank's exchange region
-  uint8_t* peer_region[peer::MAX_PEERS] = {nullptr};   // every rank's region as mapped here (own: region)
-  size_t slot_floats = 0;
-  uint32_t epoch = 0;                              // exchanges done; the same on every rank
-  float* slot(int rank_, uint32_t e) const {
-    return reinterpret_cast<float*>(peer_region[rank_] + peer::FLAG_BYTES) + (size_t)(e & 1u) * slot_floats;
-  }
-  peer::PeerDev dev(uint32_t e) const {
-    peer::PeerDev d{};
-    for (int p = 0; p < world; ++p) {
-      d.slot[p] = reinterpret_cast<const float4*>(slot(p, e));
-      d.flags[p] = reinterpret_cast<uint32_t*>(peer_region[p]);
-    }
-    d.rank = rank; d.world = world; d.epoch = e;
-    return d;
-  }
 };
 
 // ============================================================================================
@@ -1742,9 +1723,7 @@ static int hidden_dw_tc(ocf_model* m, int l, int B, const float* hin, const OptD
 
 // phase 2: activations, hidden layers, decoder at the target entries, loss partials -> dh_top, rowstats
 // act0_done: the first layer's activations are already in place (fused into the encoder's row tails or
-// into the peer exchange).
-// xslot: write the row statistics [B, 4] and dL/dh [B, hp] into this exchange slot instead of the
-// model's buffers (a peer all-reduce follows).
+// into the exchange).
 // after_kernel: the previous operation in the stream is a kernel (the phase's first launch may be a dependent launch)
 // An unsharded model's K3 leaves dz of the top hidden layer itself (DzFuse): dL/dh of a row is complete on this device.
 // A column shard all-reduces dL/dh first and keeps the separate kernel. OCF_OVERLAP bit 4 off: separate kernel everywhere.
@@ -1755,7 +1734,7 @@ static int overlap_bits() {
 static bool fuse_dz(const ocf_model* m) { return (overlap_bits() & 4) && !m->cfg.sharded && m->par_mode == 0; }
 
 static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args,
-                        float* dense_out, cudaStream_t st, bool act0_done = false, float* xslot = nullptr, bool after_kernel = false) {
+                        float* dense_out, cudaStream_t st, bool act0_done = false, bool after_kernel = false) {
   const BatchDev& bt = b->dev;
   const int L = m->L, B = bt.B;
   const bool drop = training && m->cfg.dropout_p > 0.f;
@@ -1774,10 +1753,10 @@ static int phase_decode(ocf_model* m, const ocf_batch* b, bool training, const o
   const int rows_total = (args && args->rows_total > 0) ? args->rows_total : B;
   const double bn = (double)rows_total * (double)m->cfg.n_cols_total;
   const float gscale = (float)((m->cfg.loss == OCF_LOSS_MSE ? 2.0 : 1.0) / bn);
-  float* stats_out = xslot ? xslot : m->rowstats;
-  float4* dh_out = reinterpret_cast<float4*>(xslot ? xslot + (size_t)B * ROWSTAT_W : m->dh_top);
+  float* stats_out = m->rowstats;
+  float4* dh_out = reinterpret_cast<float4*>(m->dh_top);
   DzFuse fz{};
-  if (training && xslot == nullptr && fuse_dz(m)) {
+  if (training && fuse_dz(m)) {
     fz.a = reinterpret_cast<const float4*>(m->act[L - 1]);
     fz.dscale = drop ? reinterpret_cast<const float4*>(m->dscale[L - 1]) : nullptr;
     fz.dz = reinterpret_cast<float4*>(m->dz[L - 1]);
@@ -2124,54 +2103,9 @@ extern "C" int ocf_comm_unique_id(uint8_t* id) {
 
 extern "C" int ocf_comm_destroy(ocf_comm* c);
 
-// With OCF_P2P=1 in the environment of every rank: maps every rank's exchange region into this
-// process (CUDA IPC; the handles travel through an NCCL all-gather). Without it, or when the ranks
-// cannot all map each other, the step's exchanges stay on ncclAllReduce. All ranks take the same
-// decision (all-reduced flag). Opt-in for now: measured on 2 x B200 the one-shot kernels tie with
-// NCCL (profiles/README.md); NCCL is the path verified on 4 and 8 GPUs.
-static int comm_enable_p2p(ocf_comm* c) {
-  const char* env = std::getenv("OCF_P2P");
-  const bool want = c->world >= 2 && c->world <= peer::MAX_PEERS && env != nullptr && env[0] == '1';
-  c->slot_floats = (size_t)MAX_BATCH_ROWS * (MAX_HP + ROWSTAT_W);
-  const size_t bytes = peer::FLAG_BYTES + 2 * c->slot_floats * sizeof(float);
-  cudaIpcMemHandle_t mine{};
-  bool ok = want;
-  if (ok && cudaMalloc(reinterpret_cast<void**>(&c->region), bytes) != cudaSuccess) { cudaGetLastError(); c->region = nullptr; ok = false; }
-  if (ok && cudaMemset(c->region, 0, bytes) != cudaSuccess) ok = false;
-  if (ok && cudaIpcGetMemHandle(&mine, c->region) != cudaSuccess) { cudaGetLastError(); ok = false; }
-  // handles of all ranks (in-place all-gather on a small device buffer); a rank that failed so far
-  // still takes part in the collectives so that nobody hangs
-  const size_t hb = sizeof(cudaIpcMemHandle_t);
-  uint8_t* d_h = nullptr;
-  OCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_h), hb * c->world + sizeof(float)));
-  OCF_CUDA(cudaMemcpy(d_h + hb * c->rank, &mine, hb, cudaMemcpyHostToDevice));
-  OCF_NCCL(nccl_api().allGather(d_h + hb * c->rank, d_h, hb, ncclChar, c->comm, nullptr));
-  OCF_CUDA(cudaStreamSynchronize(nullptr));
-  std::vector<cudaIpcMemHandle_t> all((size_t)c->world);
-  OCF_CUDA(cudaMemcpy(all.data(), d_h, hb * c->world, cudaMemcpyDeviceToHost));
-  if (ok) {
-    for (int p = 0; p < c->world && ok; ++p) {
-      if (p == c->rank) { c->peer_region[p] = c->region; continue; }
-      void* ptr = nullptr;
-      if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
-      c->peer_region[p] = static_cast<uint8_t*>(ptr);
-    }
-  }
-  float* d_flag = reinterpret_cast<float*>(d_h + hb * c->world);
-  const float f = ok ? 1.f : 0.f;
-  OCF_CUDA(cudaMemcpy(d_flag, &f, sizeof(float), cudaMemcpyHostToDevice));
-  OCF_NCCL(nccl_api().allReduce(d_flag, d_flag, 1, ncclFloat, ncclMin, c->comm, nullptr));
-  OCF_CUDA(cudaStreamSynchronize(nullptr));
-  float all_ok = 0.f;
-  OCF_CUDA(cudaMemcpy(&all_ok, d_flag, sizeof(float), cudaMemcpyDeviceToHost));
-  cudaFree(d_h);
-  c->p2p = want && all_ok == 1.f;
-  return OCF_OK;
-}
-
 extern "C" int ocf_comm_info(const ocf_comm* c, int32_t info[3]) {
   OCF_REQUIRE(c && info, "ocf_comm_info: null argument");
-  info[0] = c->rank; info[1] = c->world; info[2] = c->p2p ? 1 : 0;
+  info[0] = c->rank; info[1] = c->world; info[2] = 0;      // [2]: reserved (was: exchanges over peer memory)
   return OCF_OK;
 }
 
@@ -2187,8 +2121,6 @@ extern "C" int ocf_comm_create(const uint8_t* id, int32_t rank, int32_t world, o
   ncclResult_t r = nccl_api().commInitRank(&c->comm, world, u, rank);
   if (r != ncclSuccess) { delete c; return fail(OCF_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_api().getErrorString(r)); }
   g_comms_alive.fetch_add(1);
-  int st = comm_enable_p2p(c);
-  if (st != OCF_OK) { ocf_comm_destroy(c); return st; }
   *out = c;
   return OCF_OK;
 }
@@ -2196,10 +2128,7 @@ extern "C" int ocf_comm_create(const uint8_t* id, int32_t rank, int32_t world, o
 extern "C" int ocf_comm_destroy(ocf_comm* c) {
   if (c) {
     cudaDeviceSynchronize();
-    for (int p = 0; p < c->world && p < peer::MAX_PEERS; ++p)
-      if (p != c->rank && c->peer_region[p]) cudaIpcCloseMemHandle(c->peer_region[p]);
-    if (c->comm) { nccl_api().commDestroy(c->comm); g_comms_alive.fetch_sub(1); }      // after the peers' mappings are closed everywhere
-    if (c->region) cudaFree(c->region);
+    if (c->comm) { nccl_api().commDestroy(c->comm); g_comms_alive.fetch_sub(1); }
     delete c;
   }
   return OCF_OK;
@@ -2230,29 +2159,12 @@ extern "C" int ocf_model_set_comm(ocf_model* m, ocf_comm* comm, int mode) {
 }
 
 // ---- the two exchanges of a column-sharded step ----------------------------------------------
-static bool use_peer(const ocf_model* m, int B) {
-  return m->comm && m->comm->p2p &&
-         (size_t)B * (std::max(m->hp[0], m->hp[m->L - 1]) + ROWSTAT_W) <= m->comm->slot_floats;
-}
-
-// phase 1 + exchange (+ first-layer activations when the peer path fuses them). *act0_done tells
-// the caller whether launch_act(0) is still due.
+// phase 1 + exchange of the encoder's partial sums z [rows, H]. *act0_done tells the caller whether launch_act(0) is
+// still due (it is: the activation needs the summed z).
 static int encode_exchange(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args, cudaStream_t st,
                            bool* act0_done) {
   const int B = b->dev.B;
   *act0_done = false;
-  if (use_peer(m, B)) {
-    ocf_comm* c = m->comm;
-    const uint32_t e = ++c->epoch;
-    OCF_TRY(phase_encode(m, b, st, c->slot(c->rank, e), false, training, args));
-    g_prof.begin(6, st);
-    peer::k_allreduce_bias_act<<<peer::AR_CTAS, peer::AR_THREADS, 0, st>>>(c->dev(e), reinterpret_cast<float4*>(m->zsum[0]),
-                                                                            act_args(m, 0, B, training, args));
-    OCF_LAUNCHED();
-    g_prof.end(6, st);
-    *act0_done = true;
-    return OCF_OK;
-  }
   OCF_TRY(phase_encode(m, b, st, nullptr, false, training, args));
   g_prof.begin(6, st);
   OCF_NCCL(nccl_api().allReduce(m->zsum[0], m->zsum[0], (size_t)B * m->hp[0], ncclFloat, ncclSum, m->comm->comm, st));
@@ -2264,17 +2176,6 @@ static int encode_exchange(ocf_model* m, const ocf_batch* b, bool training, cons
 static int decode_exchange(ocf_model* m, const ocf_batch* b, bool training, const ocf_step_args* args, cudaStream_t st,
                            bool act0_done) {
   const int B = b->dev.B, hpt = m->hp[m->L - 1];
-  if (use_peer(m, B)) {
-    ocf_comm* c = m->comm;
-    const uint32_t e = ++c->epoch;
-    OCF_TRY(phase_decode(m, b, training, args, nullptr, st, act0_done, c->slot(c->rank, e)));
-    g_prof.begin(7, st);
-    peer::k_allreduce_store<<<peer::AR_CTAS, peer::AR_THREADS, 0, st>>>(c->dev(e), B * ROWSTAT_W / 4, reinterpret_cast<float4*>(m->rowstats),
-                                                                         training ? B * hpt / 4 : 0, reinterpret_cast<float4*>(m->dh_top));
-    OCF_LAUNCHED();
-    g_prof.end(7, st);
-    return OCF_OK;
-  }
   OCF_TRY(phase_decode(m, b, training, args, nullptr, st, act0_done));
   g_prof.begin(7, st);
   OCF_NCCL(nccl_api().allReduce(m->rowstats, m->rowstats, (size_t)m->cfg.max_rows * ROWSTAT_W + (training ? (size_t)B * hpt : 0),
@@ -2320,7 +2221,7 @@ static int gather_stats(ocf_model* m, int B, const ocf_step_args* args, const fl
 static int train_body(ocf_model* m, ocf_batch* b, const ocf_step_args* args, cudaStream_t st) {
   if (m->par_mode == OCF_PAR_COLUMNS) {
     // column shards: the three phases back to back with the two activation exchanges between them
-    // (one-shot peer-memory all-reduce kernels fused with the next compute step, or ncclAllReduce)
+    // (ncclAllReduce, captured in the step's graph)
     bool act0 = false;
     OCF_TRY(fork_scan(m, b, st));
     OCF_TRY(encode_exchange(m, b, true, args, st, &act0));
@@ -2329,7 +2230,7 @@ static int train_body(ocf_model* m, ocf_batch* b, const ocf_step_args* args, cud
   }
   OCF_TRY(fork_scan(m, b, st));
   OCF_TRY(phase_encode(m, b, st, nullptr, true, true, args));
-  OCF_TRY(phase_decode(m, b, true, args, nullptr, st, true, nullptr, true));
+  OCF_TRY(phase_decode(m, b, true, args, nullptr, st, true, true));
   return phase_update(m, b, args, st, false, nullptr, true);
 }
 
@@ -2340,7 +2241,7 @@ static int eval_body(ocf_model* m, ocf_batch* b, const ocf_step_args* args, cuda
     OCF_TRY(decode_exchange(m, b, false, args, st, act0));
   } else {
     OCF_TRY(phase_encode(m, b, st, nullptr, true, false, args));
-    OCF_TRY(phase_decode(m, b, false, args, nullptr, st, true, nullptr, true));
+    OCF_TRY(phase_decode(m, b, false, args, nullptr, st, true, true));
   }
   const int n_reg = launch_reg(m, st);
   return launch_metrics(m, b->dev.B, args, n_reg, false, st);
@@ -2454,9 +2355,8 @@ static int prepare_worklist(ocf_model* m, ocf_batch* b, cudaStream_t user) {
 static int run_step(ocf_model* m, ocf_batch* b, const ocf_step_args* args, bool train, cudaStream_t st) {
   OCF_TRY(sync_step_state(m, args, st));
   auto body = [&](cudaStream_t s) { return train ? train_body(m, b, args, s) : eval_body(m, b, args, s); };
-  const bool peer = m->par_mode == OCF_PAR_COLUMNS && use_peer(m, b->dev.B);     // exchange epochs are launch arguments
   bool done = false;
-  if (graphs_enabled() && !g_prof.on && !b->store->has_dups && !peer) {
+  if (graphs_enabled() && !g_prof.on && !b->store->has_dups) {
     const auto key = std::make_tuple(b->uid, b->dev.B, train ? (wl_current(m, b) ? 3 : 1) : 0, args ? args->rows_total : 0, args ? args->row0 : 0);
     ocf_model::StepGraph& g = m->graphs[key];
     if (g.exec == nullptr && !g.failed && g.seen++ >= 1) {

@@ -12,8 +12,8 @@
 // the weight-side products a work list of (catalogue column, array) tasks - built from the batch
 // by a counting sort (k_sort_*) - that a persistent kernel (k_row_update, one warp per task)
 // turns into gradient rows fused with the optimizer update. All floating-point reductions run in
-// a fixed order (no float atomics). The tensor-core scoring GEMM, the peer-memory exchanges and
-// the top-k epilogue live in ocf_score_tc.cuh, ocf_peer.cuh and ocf_topk.cuh.
+// a fixed order (no float atomics). The tensor-core scoring GEMM, the hidden-layer contractions and
+// the top-k epilogue live in ocf_score_tc.cuh, ocf_gemm_tc.cuh and ocf_topk.cuh.
 #pragma once
 
 #include "ocf_common.cuh"

@@ -135,7 +135,6 @@ class NativeComm(object):
         self.handle = out
         info = (C.c_int32 * 3)()
         _lib.check(lib.ocf_comm_info(out, info))
-        self.peer_memory = bool(info[2])     # exchanges run as one-shot all-reduce kernels over NVLink peer memory
 
     def close(self):
         if self.handle is not None:
@@ -376,7 +375,7 @@ def _bench_config(args, w, rank, world, native, B, scaling, parity=False, steps=
     lib.ocf_profile_enable(0)
     dist.barrier()
     names = dict(_KERNEL_TAGS)
-    names[6] = "streaming optimizer pass" if rows_mode else "exchange z [rows, H] (+ bias/act when over peer memory)"
+    names[6] = "streaming optimizer pass" if rows_mode else "exchange z [rows, H] (ncclAllReduce)"
     names[7] = "ncclAllReduce gradients" if rows_mode else "exchange row stats + dL/dh [rows, 4 + H]"
     kernels = {}
     for tag, name in names.items():
@@ -464,9 +463,8 @@ def _bench_config(args, w, rank, world, native, B, scaling, parity=False, steps=
             par = ("row-parallel x%d, global batch %d rows (%d per GPU), replicated weights, one NCCL all-reduce of all gradients per step"
                    % (world, B, B // world))
         else:
-            par = ("column-sharded x%d, global batch %d rows (every rank walks all of them on its own columns), 2 exchanges of [rows, H] per step as %s"
-                   % (world, B, "one-shot all-reduce kernels over NVLink peer memory fused with the next compute step"
-                      if native.peer_memory else "ncclAllReduce (captured in the step's CUDA graph)"))
+            par = ("column-sharded x%d, global batch %d rows (every rank walks all of them on its own columns), 2 exchanges of [rows, H] per step as ncclAllReduce (captured in the step's CUDA graph)"
+                   % (world, B))
         l2 = ("no flush: per-rank weights + optimizer state (%.0f MB) exceed the 126 MB L2 several times over" % state_mb
               if state_mb > 2 * 126 else
               "no flush, and per-rank weights + optimizer state (%.0f MB) fit or nearly fit the 126 MB L2: the rank's kernels "

@@ -74,8 +74,6 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
     native = ocf_dist.NativeComm()
-    if rank == 0:
-        print("exchanges over peer memory:", native.peer_memory)
     ok = all([check(mode, native, rank, world) for mode in ("columns", "rows")])
     dist.barrier()
     dist.destroy_process_group()
