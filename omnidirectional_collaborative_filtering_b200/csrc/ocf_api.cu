@@ -160,7 +160,7 @@ struct WorkList {
   int2* seg = nullptr;            // [n_cols] dense mode: (first match, matches) of every column
   int4* tasks = nullptr;          // [(nblk + 1) * n_cols]
   int4* heavy = nullptr;          //   tasks with more than HEAVY_N matches
-  int* counters = nullptr;        // [8]: matches, tasks, heavy tasks, K4b's task cursors (two launches may share a list)
+  int* counters = nullptr;        // [8]: matches, tasks at the front of the task array, heavy tasks, K4b's two task cursors (two launches may share a list), tasks at the back
   int* state = nullptr;           // [2][n_cols] per-column count / code OR
   int2* info = nullptr;           // [n_cols] (first match, matches) of a touched column
   uint32_t* bits = nullptr;       // presence bitmap [n_cols][ceil(rows / 32)]
@@ -1892,6 +1892,8 @@ static int launch_scan(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
     a.colinfo = wl.info; a.bits = wl.bits; a.W = W; a.counters = wl.counters;
     a.matches = wl.matches; a.tasks = wl.tasks; a.colseg = wl.seg; a.heavy = heavy_model(m) ? wl.heavy : nullptr;
     a.n_cols = m->cfg.n_cols; a.nblk = m->nblk; a.bits3 = m->bits; a.dense = dense; a.do_dec = do_dec; a.do_enc = do_enc;
+    static const bool dec_first = [] { const char* e = std::getenv("OCF_DEC_FIRST"); return !(e && e[0] == '0'); }();
+    a.dec_first = dec_first ? 1 : 0;
     const int grid = item_grid(m, b);
     g_prof.begin(3, st);
     k_sort_count<<<grid, 128, 0, st>>>(a);
@@ -1943,6 +1945,9 @@ static int launch_rows(ocf_model* m, const ocf_batch* b, int do_dec, int do_enc,
   r.WdecT = dec.W; r.Wd_s1 = dec.Ws1; r.Wd_s2 = dec.Ws2; r.bdec = dec.b; r.bd_s1 = dec.bs1; r.bd_s2 = dec.bs2;
   r.Wenc = enc.W; r.We_s1 = enc.Ws1; r.We_s2 = enc.Ws2;
   r.n_cols = m->cfg.n_cols; r.bits = m->bits; r.bt_hdr = b->dev.hdr; r.opt = opt;
+  r.task_cap = m->cfg.n_cols * (m->nblk + 1);
+  static const bool k4b_stream = [] { const char* e = std::getenv("OCF_K4B_STREAM"); return !(e && e[0] == '0'); }();
+  r.stream = k4b_stream ? 1 : 0;
   r.dense = grad_mode ? 0 : opt.dense; r.n_arr = 0; r.only = only;
   if (grad_mode) { r.Gdec = m->gW[L]; r.Genc = m->gW[0]; r.gbdec = m->gb[L]; }
   if (do_dec) r.arr_map[r.n_arr++] = 0;

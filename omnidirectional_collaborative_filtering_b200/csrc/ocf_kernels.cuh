@@ -552,7 +552,7 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
 struct DzFuse { const float4* a; const float4* dscale; float4* dz; int act; };
 
 template <int NV, bool TRAIN>
-__global__ void __launch_bounds__(128, NV <= 4 ? 5 : 3)
+__global__ void __launch_bounds__(128, NV <= 4 ? 6 : 3)
 k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict__ bdec,
           const float* __restrict__ h, float gscale, int loss_kind,
           float* __restrict__ dy, float4* __restrict__ P2, float* __restrict__ itemstats,
@@ -565,6 +565,9 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
   __shared__ int2 s_list[128];              // (column, entry) of the target entries of 128 entries
   __shared__ float s_t[128];
   __shared__ int s_cnt[4];
+  // the batch row's activations sit in shared memory, not in NV float4 registers per lane: the kernel is bound by how
+  // many warps (rows in flight) an SM holds, and 16 registers less is one more resident CTA per SM
+  __shared__ float4 s_h[HP / 4];
   const int4 it = bt.items[blockIdx.x];     // header and item together, item.w = first entry (see k_enc_fwd)
   const int n_items = bt.hdr->n_items;
   const float aux_val = bt.hdr->aux_value;
@@ -572,12 +575,10 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
   const int b = it.x, len = it.z;
   const int p0 = it.w;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 hreg[NV], dh[NV];
+  float4 dh[NV];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    hreg[v] = ldg4(h + (size_t)b * HP + v * 128 + lane * 4);
-    dh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int v = 0; v < NV; ++v) dh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u = threadIdx.x; u < HP / 4; u += 128) s_h[u] = ldg4(h + (size_t)b * HP + u * 4);   // published by the tile loop's first barrier
   float sse = 0.f, sae = 0.f, cnt = 0.f;
 
   // target entries compacted into a list in shared memory, dealt to the four warps in pairs (see k_enc_fwd)
@@ -608,7 +609,7 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
       const float bias0 = __ldg(bdec + c0), bias1 = __ldg(bdec + c1);
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-      for (int v = 0; v < NV; ++v) { d0 = dot4(w0[v], hreg[v], d0); d1 = dot4(w1[v], hreg[v], d1); }
+      for (int v = 0; v < NV; ++v) { const float4 hv = s_h[v * 32 + lane]; d0 = dot4(w0[v], hv, d0); d1 = dot4(w1[v], hv, d1); }
       d0 = warp_sum(d0); d1 = warp_sum(d1);
       {
         const float y = aux_val * (d0 + bias0), e = y - t0;
@@ -1079,6 +1080,7 @@ struct SortArgs {
   uint32_t* matches; int4* tasks; int2* colseg;
   int4* heavy;                              // (column, array, first match, matches) of every task with more than HEAVY_N matches (null: none recorded)
   int n_cols; int nblk; int3 bits3; int dense; int do_dec; int do_enc;
+  int dec_first;                            // decoder tasks fill the task array from the front, encoder tasks from the back
 };
 
 __global__ void __launch_bounds__(128) k_sort_count(SortArgs a) {
@@ -1121,23 +1123,30 @@ __global__ void __launch_bounds__(256) k_sort_alloc(SortArgs a) {
     }
   }
   if (__ballot_sync(FULL, n > 0) == 0u) return;
-  int sn = n, stk = n_tasks;                 // inclusive prefix over the lanes
+  // decoder tasks (array 0, always first in arr[]) and encoder tasks are placed apart when dec_first: K4b then walks
+  // the decoder rows first, while the rows K3 has just read are still in L2
+  const int n_front = a.dec_first ? ((n_tasks > 0 && arr[0] == 0) ? 1 : 0) : n_tasks;
+  const int n_back = n_tasks - n_front;
+  int sn = n, stk = n_front, ste = n_back;   // inclusive prefixes over the lanes
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int t0 = __shfl_up_sync(FULL, sn, o), t1 = __shfl_up_sync(FULL, stk, o);
-    if (lane >= o) { sn += t0; stk += t1; }
+    const int t0 = __shfl_up_sync(FULL, sn, o), t1 = __shfl_up_sync(FULL, stk, o), t2 = __shfl_up_sync(FULL, ste, o);
+    if (lane >= o) { sn += t0; stk += t1; ste += t2; }
   }
-  int b0 = 0, b1 = 0;
+  int b0 = 0, b1 = 0, b2 = 0;
   if (lane == 31) {
     b0 = atomicAdd(&a.counters[0], sn);
     if (stk) b1 = atomicAdd(&a.counters[1], stk);
+    if (ste) b2 = atomicAdd(&a.counters[5], ste);
   }
-  b0 = __shfl_sync(FULL, b0, 31); b1 = __shfl_sync(FULL, b1, 31);
+  b0 = __shfl_sync(FULL, b0, 31); b1 = __shfl_sync(FULL, b1, 31); b2 = __shfl_sync(FULL, b2, 31);
   if (n > 0) {
-    const int base = b0 + sn - n, slot = b1 + stk - n_tasks;
+    const int base = b0 + sn - n, front = b1 + stk - n_front, back = b2 + ste - n_back;
+    const int cap = a.n_cols * (a.nblk + 1);
     a.colinfo[c] = make_int2(base, n);
     if (a.dense) a.colseg[c] = make_int2(base, n);
-    for (int k = 0; k < n_tasks; ++k) a.tasks[slot + k] = make_int4(c, arr[k], base, n);
+    for (int k = 0; k < n_front; ++k) a.tasks[front + k] = make_int4(c, arr[k], base, n);
+    for (int k = 0; k < n_back; ++k) a.tasks[cap - 1 - (back + k)] = make_int4(c, arr[n_front + k], base, n);
     if (n > HEAVY_N && a.heavy != nullptr && n_arr > 0) {
       const int h0 = atomicAdd(&a.counters[2], n_arr);
       for (int k = 0; k < n_arr; ++k) a.heavy[h0 + k] = make_int4(c, arr[k], base, n);
@@ -1177,6 +1186,8 @@ struct RowArgs {
   int n_cols; int3 bits; const BatchHdr* bt_hdr;
   int dense; int n_arr; int arr_map[4];
   const int4* heavy;                        // tasks with more than HEAVY_N matches, walked by whole CTAs (null: every task is a warp's)
+  int stream;                               // lean variant: optimizer state loads and all row stores as evict-first traffic (OCF_K4B_STREAM=0: plain)
+  int task_cap;                             // capacity of the task array: task t >= counters[1] is tasks[task_cap - 1 - (t - counters[1])] (K4a puts the encoder tasks there)
   int only;                                 // task list shared by two launches (decoder and encoder rows of different widths): 1 = decoder tasks only, 2 = encoder tasks only
   OptDev opt;
 };
@@ -1195,6 +1206,10 @@ k_row_update(RowArgs a) {
   pdl_wait();
   constexpr int HP = NV * 128;
   constexpr bool LOAD_W = KIND != KIND_GRAD;
+  // Lean variant (catalogues far beyond L2): optimizer state is read once and every row is written once per step, so
+  // both go through L2 as evict-first traffic (ld/st.global.cs). What then stays in L2 across kernels are the weight
+  // rows K3 has just read: the decoder tasks come first in the list (k_sort_alloc) and find them there.
+  constexpr bool STREAM = !WIDE && !HEAVY && KIND != KIND_GRAD;
   __shared__ float4 hpart[HEAVY ? 8 : 1][HEAVY ? HP / 4 : 1];       // heavy tasks: the eight warps' partial gradient rows
   __shared__ float hcs[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1209,8 +1224,13 @@ k_row_update(RowArgs a) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       w[v] = LOAD_W ? *reinterpret_cast<const float4*>(Wrow + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-      t1[v] = (LOAD_W && KIND != OCF_OPT_SGD) ? *reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-      t2[v] = KIND == OCF_OPT_ADAM ? *reinterpret_cast<const float4*>(S2row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (STREAM && a.stream) {
+        t1[v] = KIND != OCF_OPT_SGD ? __ldcs(reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        t2[v] = KIND == OCF_OPT_ADAM ? __ldcs(reinterpret_cast<const float4*>(S2row + r + lane * 4 + v * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        t1[v] = (LOAD_W && KIND != OCF_OPT_SGD) ? *reinterpret_cast<const float4*>(S1row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+        t2[v] = KIND == OCF_OPT_ADAM ? *reinterpret_cast<const float4*>(S2row + r + lane * 4 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   };
   // g += sum over matches [i_begin, i_end) of the task of coef * X[b, :], in match order
@@ -1273,9 +1293,15 @@ k_row_update(RowArgs a) {
       opt_apply_k<KIND>(a.opt, lr, g[v].y, w[v].y, t1[v].y, t2[v].y);
       opt_apply_k<KIND>(a.opt, lr, g[v].z, w[v].z, t1[v].z, t2[v].z);
       opt_apply_k<KIND>(a.opt, lr, g[v].w, w[v].w, t1[v].w, t2[v].w);
-      *reinterpret_cast<float4*>(Wrow + v * 128) = w[v];
-      if (KIND != OCF_OPT_SGD) *reinterpret_cast<float4*>(S1row + r + lane * 4 + v * 128) = t1[v];
-      if (KIND == OCF_OPT_ADAM) *reinterpret_cast<float4*>(S2row + r + lane * 4 + v * 128) = t2[v];
+      if (STREAM && a.stream) {
+        __stcs(reinterpret_cast<float4*>(Wrow + v * 128), w[v]);
+        if (KIND != OCF_OPT_SGD) __stcs(reinterpret_cast<float4*>(S1row + r + lane * 4 + v * 128), t1[v]);
+        if (KIND == OCF_OPT_ADAM) __stcs(reinterpret_cast<float4*>(S2row + r + lane * 4 + v * 128), t2[v]);
+      } else {
+        *reinterpret_cast<float4*>(Wrow + v * 128) = w[v];
+        if (KIND != OCF_OPT_SGD) *reinterpret_cast<float4*>(S1row + r + lane * 4 + v * 128) = t1[v];
+        if (KIND == OCF_OPT_ADAM) *reinterpret_cast<float4*>(S2row + r + lane * 4 + v * 128) = t2[v];
+      }
     }
     if (arr == 0 && lane == 0) {          // decoder bias: column-local gradient sum_b dy[b,c]
       OptDev ob = a.opt; ob.l2x2 = 0.f;   // Keras regularises kernels only
@@ -1325,7 +1351,9 @@ k_row_update(RowArgs a) {
   // ---- every other task: one warp each ------------------------------------------------------------------------
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const long long n_tasks = a.dense ? (long long)a.n_cols * a.n_arr : (long long)a.counters[1];
+  const int n_front = a.dense ? 0 : a.counters[1];
+  const long long n_tasks = a.dense ? (long long)a.n_cols * a.n_arr : (long long)n_front + a.counters[5];
+  auto task_at = [&](long long t) -> int4 { return a.tasks[t < n_front ? t : (long long)a.task_cap - 1 - (t - n_front)]; };
   auto run_task = [&](int c, int arr, int base, int n) {
     const size_t r = row_of(c, arr);
     float4 w[NV], t1[NV], t2[NV], g[NV];
@@ -1356,7 +1384,7 @@ k_row_update(RowArgs a) {
           const int2 seg = a.colseg[c];
           mine = make_int4(c, a.arr_map[t - (long long)c * a.n_arr], seg.x, seg.y);
         } else {
-          mine = a.tasks[t0 + lane];
+          mine = task_at(t0 + lane);
         }
       }
       const int cnt = (int)min((long long)4, n_tasks - t0);
@@ -1375,7 +1403,7 @@ k_row_update(RowArgs a) {
       c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
       const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
     } else {
-      const int4 task = a.tasks[t];
+      const int4 task = task_at(t);
       c = task.x; arr = task.y; base = task.z; n = task.w;
       if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
     }
