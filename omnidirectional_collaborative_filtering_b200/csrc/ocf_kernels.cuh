@@ -455,6 +455,16 @@ __device__ __forceinline__ void row_tail(const BatchDev& bt, int item, int b, co
 // The row's last CTA (row_tail) sums the row and either stores the pre-activation z (a column shard
 // all-reduces it first) or applies bias + activation + dropout right there (fuse_act).
 // ============================================================================================
+// Ties whatever is computed from `dep` afterwards to every 16-byte load of the row: dep += 0 * (one component of each
+// load), which IEEE arithmetic cannot fold away and which stays 0 for finite weights. ptxas otherwise interleaves the
+// FMAs of row q with the loads of row q + 1 to save registers (cuobjdump: 4 LDG, 7 FFMA, 1 LDG, 9 FFMA, ...), and the
+// warp then waits for row q before row q + 1 is even requested: one row in flight instead of RIF.
+template <int NV>
+__device__ __forceinline__ void depend_on_row(float& dep, const float4 (&w)[NV]) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) dep = fmaf(0.f, w[v].x, dep);
+}
+
 template <int NV>
 __global__ void __launch_bounds__(128)
 k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int3 bits,
@@ -462,6 +472,7 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
   pdl_trigger();
   pdl_wait();
   constexpr int HP = NV * 128;
+  constexpr int RIF = 2;                    // weight rows in flight per warp and round (3 and 4 cost more occupancy than they add: 46-47 vs 42.6 us, ML-10M shape)
   __shared__ float4 red[4][HP / 4];
   __shared__ int2 s_list[128 * 3];          // (weight row, coefficient bits) of the row loads of 128 entries
   __shared__ int s_cnt[3][4];
@@ -504,17 +515,33 @@ k_enc_fwd(BatchDev bt, const float* __restrict__ Wenc, int n_cols, int nblk, int
         s_list[mine + __popc(bal[blk] & ((1u << lane) - 1u))] = make_int2(blk * n_cols + c, __float_as_int(blk == 0 ? val : aux_val));
     }
     __syncthreads();
-    for (int j = warp * 2; j < total; j += 8) {
-      const bool two = j + 1 < total;
-      const int2 e0 = s_list[j], e1 = s_list[two ? j + 1 : j];
-      const float f0 = __int_as_float(e0.y), f1 = two ? __int_as_float(e1.y) : 0.f;
-      const float* r0 = Wenc + (size_t)e0.x * HP + lane * 4;
-      const float* r1 = Wenc + (size_t)e1.x * HP + lane * 4;
-      float4 w0[NV], w1[NV];
+    // RIF rows in flight per warp and round: the kernel is bound by (rounds per warp) x (latency of a round)
+    // (a round past the end of the list re-reads its last row, x 0)
+    for (int j = warp * RIF; j < total; j += 4 * RIF) {
+      float f[RIF];
+      const float* r[RIF];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) { w0[v] = ldg4(r0 + v * 128); w1[v] = ldg4(r1 + v * 128); }
+      for (int q = 0; q < RIF; ++q) {
+        const int2 e = s_list[min(j + q, total - 1)];
+        f[q] = j + q < total ? __int_as_float(e.y) : 0.f;
+        r[q] = Wenc + (size_t)e.x * HP + lane * 4;
+      }
+      float4 w[RIF][NV];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) { fma4(acc[v], f0, w0[v]); fma4(acc[v], f1, w1[v]); }
+      for (int q = 0; q < RIF; ++q)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) w[q][v] = ldg4(r[q] + v * 128);
+      float dep = 0.f;
+      if (NV <= 4) {                           // wide rows: two of them already fill the register file
+#pragma unroll
+        for (int q = 0; q < RIF; ++q) depend_on_row<NV>(dep, w[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < RIF; ++q) {
+        const float fq = f[q] + dep;           // + 0, but only once every row of the round has landed
+#pragma unroll
+        for (int v = 0; v < NV; ++v) fma4(acc[v], fq, w[q][v]);
+      }
     }
     if (tile + 128 < len) __syncthreads();          // the list is rebuilt for the next 128 entries
   }
@@ -607,7 +634,9 @@ k_dec_fwd(BatchDev bt, const float* __restrict__ WdecT, const float* __restrict_
 #pragma unroll
       for (int v = 0; v < NV; ++v) { w0[v] = ldg4(r0 + v * 128); w1[v] = ldg4(r1 + v * 128); }
       const float bias0 = __ldg(bdec + c0), bias1 = __ldg(bdec + c1);
-      float d0 = 0.f, d1 = 0.f;
+      float dep = 0.f;
+      if (NV <= 4) { depend_on_row<NV>(dep, w0); depend_on_row<NV>(dep, w1); }      // both rows requested before either is used (see k_enc_fwd)
+      float d0 = dep, d1 = dep;
 #pragma unroll
       for (int v = 0; v < NV; ++v) { const float4 hv = s_h[v * 32 + lane]; d0 = dot4(w0[v], hv, d0); d1 = dot4(w1[v], hv, d1); }
       d0 = warp_sum(d0); d1 = warp_sum(d1);
