@@ -238,7 +238,10 @@ typedef struct {
  * reduces the buffer ocf_model_buffer() names, in place, over the column shards):
  *   phase 1: gather + encoder partial sums        -> all-reduce OCF_BUF_Z
  *   phase 2: activations, decoder, loss partials  -> all-reduce OCF_BUF_DH and OCF_BUF_ROWSTATS
- *   phase 3: backward, fused optimizer update, metrics */
+ *   phase 3: backward, fused optimizer update, metrics
+ * A phase-0 step of an unsharded model also enqueues, on the batch's own stream and right behind the batch's fill, the
+ * grouping of the batch's ratings by catalogue column that the update walks (it depends on the batch alone): by the
+ * time the caller's stream reaches the step the list is there. Stepping the same fill again reuses it. */
 int ocf_train_step(ocf_model* model, ocf_batch* batch, const ocf_step_args* args,
                    float* host_metrics, void* stream);
 /* model.test_on_batch as driven by evaluate_generator (train.py:208,218): forward only,
