@@ -22,24 +22,28 @@ from tests.test_gpu_model import _close, _close_weights
 pytestmark = pytest.mark.gpu
 
 
-def _models(n_cols, H, B, aux, pdrop, seed, copies=1):
-    kw = dict(dense_activation="sigmoid", use_causal_info=aux is not None, dropout_probability=pdrop)
+def _models(n_cols, H, B, aux, pdrop, seed, copies=1, opt="adagrad", l2=None):
+    kw = dict(dense_activation="sigmoid", use_causal_info=aux is not None, dropout_probability=pdrop,
+              l2_weight_regulatization=l2)
     out = []
     for _ in range(copies):
         np.random.seed(seed)
         om = omni_model(1, H, n_cols, B, auxilliary_mask_type=aux, **kw)
-        om.model.compile(optimizers.Adagrad(lr=0.005, epsilon=1e-08, decay=0.0), "mean_squared_error", rating_range=4.5)
+        o = optimizers.Adagrad(lr=0.005, epsilon=1e-08, decay=0.0) if opt == "adagrad" else optimizers.Adam(lr=0.001)
+        om.model.compile(o, "mean_squared_error", rating_range=4.5)
         out.append(om)
     ref = ref_model.RefModel(1, H, n_cols, B, dtype=np.float32, rng=np.random.RandomState(0), **kw)
     ref.set_weights(out[0].model.get_weights())
     ref.dropout_seed = out[0].dropout_seed
-    ref.compile(ref_model.RefOptimizer("adagrad", lr=0.005), "mean_squared_error", rating_range=4.5)
+    ro = (ref_model.RefOptimizer("adagrad", lr=0.005) if opt == "adagrad" else
+          ref_model.RefOptimizer("adam", lr=o.lr, epsilon=o.epsilon, decay=o.decay, beta_1=o.p1, beta_2=o.p2))
+    ref.compile(ro, "mean_squared_error", rating_range=4.5)
     return out, ref
 
 
-def _run_against_oracle(fs, H, B, aux, sparsity, pass_through, pdrop, steps, copies=1):
+def _run_against_oracle(fs, H, B, aux, sparsity, pass_through, pdrop, steps, copies=1, opt="adagrad", l2=None):
     rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs, rng_on_device=False)
-    oms, ref = _models(fs.n_cols, H, B, aux, pdrop, seed=3, copies=copies)
+    oms, ref = _models(fs.n_cols, H, B, aux, pdrop, seed=3, copies=copies, opt=opt, l2=l2)
     np.random.seed(17)
     gen = rd.data_gen(B, sparsity, "train", True, aux, -1, pass_through_input_training=pass_through)
     logs = [[] for _ in oms]
@@ -53,7 +57,7 @@ def _run_against_oracle(fs, H, B, aux, sparsity, pass_through, pdrop, steps, cop
             _close(got, want)
     weights = [om.model.get_weights() for om in oms]
     for g, w in zip(weights[0], ref.get_weights()):
-        _close_weights(g, w, 0.005)
+        _close_weights(g, w, 0.005 if opt == "adagrad" else 0.001)
     vb = next(rd.data_gen(B, None, "valid", True, aux, -1))
     vfeed, vt = host_densify(vb)
     got_eval = oms[0].model.test_on_batch(vb)
@@ -85,4 +89,14 @@ def test_ml10m_bench_workload_matches_oracle_and_is_reproducible():
     shuffled = Batch(rd, "fixed", vb.source, vb.rows[perm], None, False, vb.aux_type, vb.aux_value, vb.target_count,
                      False, vb.n_ratings)
     _close(oms[0].model.test_on_batch(shuffled), got_eval, rtol=1e-5)
+    rd.close()
+
+
+def test_ml10m_shape_dense_rule_on_the_lean_update():
+    """Adam + L2 at the ML-10M shape: every parameter of the 71 567-column catalogue moves every step, so the row
+    update enumerates all (column, array) pairs, and at this size it is the lean variant (task cursor, evict-first
+    state and stores, three state rows per task) - the combination none of the reduced shapes reaches."""
+    fs = synthetic.make_fixed_split("ml10m", reverse_user_item_data=True, seed=0)
+    rd, oms, logs, _, _, _ = _run_against_oracle(fs, H=512, B=128, aux="dropout", sparsity=[0.5, 0.5], pass_through=False,
+                                                  pdrop=None, steps=2, opt="adam", l2=0.001)
     rd.close()
