@@ -22,17 +22,17 @@ from tests.test_gpu_model import _close, _close_weights
 pytestmark = pytest.mark.gpu
 
 
-def _models(n_cols, H, B, aux, pdrop, seed, copies=1, opt="adagrad", l2=None):
+def _models(n_cols, H, B, aux, pdrop, seed, copies=1, opt="adagrad", l2=None, layers=1):
     kw = dict(dense_activation="sigmoid", use_causal_info=aux is not None, dropout_probability=pdrop,
               l2_weight_regulatization=l2)
     out = []
     for _ in range(copies):
         np.random.seed(seed)
-        om = omni_model(1, H, n_cols, B, auxilliary_mask_type=aux, **kw)
+        om = omni_model(layers, H, n_cols, B, auxilliary_mask_type=aux, **kw)
         o = optimizers.Adagrad(lr=0.005, epsilon=1e-08, decay=0.0) if opt == "adagrad" else optimizers.Adam(lr=0.001)
         om.model.compile(o, "mean_squared_error", rating_range=4.5)
         out.append(om)
-    ref = ref_model.RefModel(1, H, n_cols, B, dtype=np.float32, rng=np.random.RandomState(0), **kw)
+    ref = ref_model.RefModel(layers, H, n_cols, B, dtype=np.float32, rng=np.random.RandomState(0), **kw)
     ref.set_weights(out[0].model.get_weights())
     ref.dropout_seed = out[0].dropout_seed
     ro = (ref_model.RefOptimizer("adagrad", lr=0.005) if opt == "adagrad" else
@@ -41,9 +41,9 @@ def _models(n_cols, H, B, aux, pdrop, seed, copies=1, opt="adagrad", l2=None):
     return out, ref
 
 
-def _run_against_oracle(fs, H, B, aux, sparsity, pass_through, pdrop, steps, copies=1, opt="adagrad", l2=None):
+def _run_against_oracle(fs, H, B, aux, sparsity, pass_through, pdrop, steps, copies=1, opt="adagrad", l2=None, layers=1):
     rd = data_reader(fs.n_cols, fs.train.n_rows, "", eval_mode="fixed_split", data=fs, rng_on_device=False)
-    oms, ref = _models(fs.n_cols, H, B, aux, pdrop, seed=3, copies=copies, opt=opt, l2=l2)
+    oms, ref = _models(fs.n_cols, H, B, aux, pdrop, seed=3, copies=copies, opt=opt, l2=l2, layers=layers)
     np.random.seed(17)
     gen = rd.data_gen(B, sparsity, "train", True, aux, -1, pass_through_input_training=pass_through)
     logs = [[] for _ in oms]
@@ -99,4 +99,13 @@ def test_ml10m_shape_dense_rule_on_the_lean_update():
     fs = synthetic.make_fixed_split("ml10m", reverse_user_item_data=True, seed=0)
     rd, oms, logs, _, _, _ = _run_against_oracle(fs, H=512, B=128, aux="dropout", sparsity=[0.5, 0.5], pass_through=False,
                                                   pdrop=None, steps=2, opt="adam", l2=0.001)
+    rd.close()
+
+
+def test_ml10m_shape_hidden_layer_splits_the_lean_update():
+    """Two layers at the ML-10M shape: the decoder rows' update runs beside the backward pass and the encoder rows'
+    after it - two launches of the lean variant sharing one task list (front / back halves, one cursor each)."""
+    fs = synthetic.make_fixed_split("ml10m", reverse_user_item_data=True, seed=0)
+    rd, oms, logs, _, _, _ = _run_against_oracle(fs, H=512, B=128, aux="dropout", sparsity=[0.5, 0.5], pass_through=False,
+                                                  pdrop=0.2, steps=3, layers=2)
     rd.close()
