@@ -219,7 +219,7 @@ struct ocf_batch {
   // to 48 us on the ML-10M shape). One zeroed region [counters | state | bits | seg], one memset.
   WorkList wl{};
   Arena wl_mem;
-  uint8_t* wl_zero = nullptr; size_t wl_zero_bytes = 0, wl_zero_dense_bytes = 0;
+  uint8_t* wl_zero = nullptr;     // start of the zeroed region (= wl.seg)
   int wl_cols = 0, wl_nblk = 0;   // what the allocation was sized for
   WorkSig wl_sig{};               // what the list in `wl` was built for ...
   uint64_t fill_seq = 0, wl_seq = 0;   // ... and for which fill (0: none)

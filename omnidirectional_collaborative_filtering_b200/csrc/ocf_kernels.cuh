@@ -1378,8 +1378,6 @@ k_row_update(RowArgs a) {
   }
 
   // ---- every other task: one warp each ------------------------------------------------------------------------
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n_front = a.dense ? 0 : a.counters[1];
   const long long n_tasks = a.dense ? (long long)a.n_cols * a.n_arr : (long long)n_front + a.counters[5];
   auto task_at = [&](long long t) -> int4 { return a.tasks[t < n_front ? t : (long long)a.task_cap - 1 - (t - n_front)]; };
@@ -1393,7 +1391,7 @@ k_row_update(RowArgs a) {
     walk(arr, base, 0, n, g, cs);
     finish(c, arr, r, g, cs, w, t1, t2);
   };
-  if (!WIDE && !HEAVY && KIND != KIND_GRAD) {
+  if constexpr (!WIDE && !HEAVY && KIND != KIND_GRAD) {
     // Lean variant (catalogues far beyond L2, hundreds of tasks per warp): tasks are dealt out in chunks of 4 through
     // a cursor (zeroed with the work list's counters), so a warp that drew long match lists simply takes fewer
     // chunks and the kernel has no tail of unlucky warps (Netflix shape: 1.75 -> 1.56 ms, 0.81 -> 0.91 of HBM).
@@ -1424,20 +1422,22 @@ k_row_update(RowArgs a) {
         run_task(c, arr, base, n);
       }
     }
-    return;
-  }
-  for (long long t = gwarp; t < n_tasks; t += nwarps) {
-    int c, arr, base, n;
-    if (a.dense) {
-      c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
-      const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
-    } else {
-      const int4 task = task_at(t);
-      c = task.x; arr = task.y; base = task.z; n = task.w;
-      if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
+  } else {
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (long long t = gwarp; t < n_tasks; t += nwarps) {
+      int c, arr, base, n;
+      if (a.dense) {
+        c = (int)(t / a.n_arr); arr = a.arr_map[t - (long long)c * a.n_arr];
+        const int2 seg = a.colseg[c]; base = seg.x; n = seg.y;
+      } else {
+        const int4 task = task_at(t);
+        c = task.x; arr = task.y; base = task.z; n = task.w;
+        if (a.only != 0 && (a.only == 1) != (arr == 0)) continue;
+      }
+      if (HEAVY && a.heavy != nullptr && n > HEAVY_N) continue;            // done above by a whole CTA
+      run_task(c, arr, base, n);
     }
-    if (HEAVY && a.heavy != nullptr && n > HEAVY_N) continue;            // done above by a whole CTA
-    run_task(c, arr, base, n);
   }
 }
 
