@@ -97,3 +97,26 @@ def test_reseeding_on_the_host_discards_the_device_copy(fake):
     dr.sync_host_rng()
     assert np.random.random_sample() == expect
     assert rng.host_state is None
+
+
+def test_prefetch_runs_at_most_a_few_batches_ahead(fake, monkeypatch):
+    """The generator thread may have drawn tickets for dozens of batches; the device workers are asked to run only
+    OCF_RNG_AHEAD batches ahead of the one being uploaded (what is in flight has to drain whenever the stream goes
+    back to the host, i.e. at every epoch start)."""
+    monkeypatch.delenv("OCF_RNG_AHEAD", raising=False)
+    np.random.seed(1)
+    rng = dr.DeviceRng.get()
+    tickets = [rng.ticket(1000) for _ in range(40)]
+    rng.consume(tickets[0])
+    assert fake.prefetched[-1] == 3 * 1000                      # 40 batches pending, default cap 3
+    fake.rs.random_sample(1000)
+    monkeypatch.setenv("OCF_RNG_AHEAD", "5")
+    rng.consume(tickets[1])
+    assert fake.prefetched[-1] == 5 * 1000
+    fake.rs.random_sample(1000)
+    for t in tickets[2:39]:
+        rng.consume(t)
+        fake.rs.random_sample(1000)
+    monkeypatch.delenv("OCF_RNG_AHEAD")
+    rng.consume(tickets[39])                                    # nothing pending behind it: its own draws only
+    assert fake.prefetched[-1] == 1000
