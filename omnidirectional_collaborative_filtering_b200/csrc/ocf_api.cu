@@ -264,6 +264,7 @@ struct ocf_model {
   struct StepGraph { cudaGraphExec_t exec = nullptr; int kernels = 0; int seen = 0; bool failed = false; };
   std::map<std::tuple<uint64_t, int, int, int, int>, StepGraph> graphs;
   cudaStream_t cap = nullptr;     // capture stream
+  cudaStream_t cap_lo = nullptr;  // capture stream of the batch-side work list when the batch streams run at low priority (OCF_GATHER_PRIO=0)
   bool capturing = false;
   int* d_err = nullptr;
   int64_t steps_logged = 0;
@@ -1364,6 +1365,7 @@ extern "C" int ocf_model_destroy(ocf_model* m) {
     drop_graphs(m);
     if (m->side) cudaStreamDestroy(m->side);
     if (m->cap) cudaStreamDestroy(m->cap);
+    if (m->cap_lo) cudaStreamDestroy(m->cap_lo);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->side2) cudaStreamDestroy(m->side2);
@@ -2329,10 +2331,21 @@ static int prepare_worklist(ocf_model* m, ocf_batch* b, cudaStream_t user) {
       m->capturing = true;                         // grids sized to the batch object's capacity (item_grid)
       cudaGraph_t graph = nullptr;
       int rc = OCF_OK;
-      if (cudaStreamBeginCapture(m->cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); rc = OCF_ERR_CUDA; }
+      // captured kernel nodes inherit the capture stream's priority: the list's kernels follow the batch streams'
+      static const bool low_prio = [] { const char* e = std::getenv("OCF_GATHER_PRIO"); return e && e[0] == '0'; }();
+      cudaStream_t cs = m->cap;
+      if (low_prio) {
+        if (m->cap_lo == nullptr) {
+          int lo = 0, hi = 0;
+          cudaDeviceGetStreamPriorityRange(&lo, &hi);
+          if (cudaStreamCreateWithPriority(&m->cap_lo, cudaStreamNonBlocking, lo) != cudaSuccess) { cudaGetLastError(); m->cap_lo = nullptr; }
+        }
+        if (m->cap_lo != nullptr) cs = m->cap_lo;
+      }
+      if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); rc = OCF_ERR_CUDA; }
       else {
-        rc = worklist_enqueue(m, b, sig, m->cap);
-        if (cudaStreamEndCapture(m->cap, &graph) != cudaSuccess) { cudaGetLastError(); rc = OCF_ERR_CUDA; graph = nullptr; }
+        rc = worklist_enqueue(m, b, sig, cs);
+        if (cudaStreamEndCapture(cs, &graph) != cudaSuccess) { cudaGetLastError(); rc = OCF_ERR_CUDA; graph = nullptr; }
       }
       m->capturing = was_capturing;
       b->wl_graph_kernels = (int)(g_launches.load() - launched);
