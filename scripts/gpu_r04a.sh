@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: ran on commit a1179e3, whose Makefile built the OCF_K4B_VARIANT libraries v1 / v2 that OCF_LIB_VARIANT selected)
 # round 2, session 3, call A: K4a ahead of the step (batch-side work list) + K4b scheduling variants, A/B on one box
 out=gpurun_out; tag=r04a; mkdir -p $out
 python -m pytest tests/test_gpu_model.py tests/test_gpu_train.py tests/test_gpu_checkpoint.py tests/test_gpu_batches.py -q -m gpu -x > $out/${tag}_tests.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_tests.log

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: ran on commit a1179e3 + the staged kernels of csrc/ocf_staged.cuh, OCF_DEC_STAGED / OCF_UPD_STAGED; removed since)
 # round 2, session 3, call B: K3 / K4b staged through shared memory (cp.async.bulk), A/B on one box
 out=gpurun_out; tag=r04b; mkdir -p $out
 timeout 900 python -m pytest tests -q -m gpu -x > $out/${tag}_tests.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_tests.log
