@@ -507,7 +507,7 @@ def main():
     device_steps(resident[W:], W + K)
     torch.cuda.synchronize()
     lib.ocf_profile_enable(0)
-    tag_names = ["k_gather_split (K1)", "k_enc_fwd (K2)", "k_dec_fwd (K3)", "k_col_scan (K4a)", "k_row_update (K4b)"]
+    tag_names = ["k_gather_split (K1)", "k_enc_fwd (K2)", "k_dec_fwd (K3)", "k_sort_count+alloc+place (K4a, on the batch stream)", "k_row_update (K4b)"]
     tag_ms = []
     n_prof_steps = 1
     for t in (0, 1, 2, 3, 5):

@@ -214,7 +214,7 @@ def gather_full_weights(om, group=None) -> List[np.ndarray]:
 
 
 # ---- bench.py, N > 1 ----------------------------------------------------------------------------------
-_KERNEL_TAGS = {0: "k_gather_split (K1)", 1: "k_enc_fwd (K2)", 2: "k_dec_fwd (K3)", 3: "k_col_scan (K4a)", 5: "k_row_update (K4b)"}
+_KERNEL_TAGS = {0: "k_gather_split (K1)", 1: "k_enc_fwd (K2)", 2: "k_dec_fwd (K3)", 3: "k_sort_count+alloc+place (K4a)", 5: "k_row_update (K4b)"}
 
 
 def _model_kwargs(w):
